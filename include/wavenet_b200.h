@@ -1,0 +1,150 @@
+/* wavenet_b200.h — C ABI of libwavenet_b200.so
+ *
+ * B200-native (sm_100a) implementation of the WaveNet residual-stack training pass of
+ * jirsat/wavenets.  The reference has NO native ABI (pure Python on TensorFlow/Keras); each
+ * entry point below names the reference Python interface it stands in for (file:line under
+ * the reference repo).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative wn_status; wn_last_error() gives text.
+ *     The Python shim maps WN_ERR_VALUE -> ValueError and WN_ERR_UNSUPPORTED ->
+ *     NotImplementedError (reference: model.py:52-70,250,307,500,549; layers.py:133,148,162,175).
+ *   - tensors are channels-last, row-major, exactly as the reference's (B,T,C) tensors.
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host" pointers are
+ *     ordinary host memory.  `stream` is a cudaStream_t passed as void* (NULL = legacy default).
+ *   - no CPU fallback: wn_create fails with WN_ERR_CUDA when no sm_100 device is usable.
+ *   - no global state besides the handle (and a thread-local error string).
+ */
+#ifndef WAVENET_B200_H_
+#define WAVENET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wn_handle wn_handle;
+
+enum wn_status {
+  WN_OK = 0,
+  WN_ERR_VALUE = -1,        /* invalid hyper-parameter / shape  -> ValueError            */
+  WN_ERR_UNSUPPORTED = -2,  /* valid in the reference API but not built -> NotImplemented */
+  WN_ERR_CUDA = -3,         /* CUDA runtime / driver failure                              */
+  WN_ERR_STATE = -4         /* call order problem (e.g. backward before forward)          */
+};
+
+enum wn_activation { WN_ACT_LINEAR = 0, WN_ACT_RELU = 1, WN_ACT_LEAKY_RELU = 2, WN_ACT_TANH = 3, WN_ACT_SIGMOID = 4 };
+enum wn_sampling { WN_CATEGORICAL = 0, WN_LOGISTIC = 1, WN_GAUSSIAN = 2 };
+enum wn_precision {
+  WN_FP32 = 0,   /* fp32 storage + FFMA accumulate: the <=1e-4 parity tier                */
+  WN_BF16 = 1    /* bf16 storage, tcgen05/TMEM fp32 accumulate: the throughput tier        */
+};
+
+#define WN_MAX_LIST 8
+#define WN_MAX_DILATIONS 512
+
+/* Mirrors WaveNet.__init__ kwargs (reference model.py:14-34) plus what Keras infers at build
+ * time (cond_in) and what the device workspace needs (max_batch/max_time). */
+typedef struct wn_config {
+  int32_t kernel_size;                 /* model.py:15; layers.py:10 `kernel`                   */
+  int32_t channels;                    /* R                                                     */
+  int32_t blocks;
+  int32_t layers_per_block;
+  int32_t activation;                  /* wn_activation; pre-stack + head hidden layers         */
+  int32_t conditioning;                /* 0 None, 1 'global' ('local' is broken upstream)        */
+  int32_t n_mapping;                   /* len(mapping_layers)                                   */
+  int32_t mapping_layers[WN_MAX_LIST];
+  int32_t mapping_activation;          /* wn_activation                                         */
+  int32_t cond_in;                     /* width of the conditioning input (one-hot depth)       */
+  int32_t dilation_bound;
+  int32_t num_mixtures;                /* 0 = None                                              */
+  int32_t sampling_function;           /* wn_sampling                                           */
+  int32_t bits;
+  int32_t skip_channels;               /* 0 = None (skip aliases conv1 output, layers.py:216-219)*/
+  int32_t dilation_channels;           /* 0 = None (= channels, layers.py:49-50)                */
+  int32_t use_residual;
+  int32_t use_skip;
+  int32_t n_final;                     /* len(final_layers_channels)                            */
+  int32_t final_layers_channels[WN_MAX_LIST];
+  float   l2_reg_factor;
+  float   dropout;                     /* accepted; training with dropout>0 is WN_ERR_UNSUPPORTED */
+  /* explicit per-conv dilations (blocks*layers_per_block entries) — used by the bare
+   * WaveNetLayer mirror (layers.py:10-20 `dilation_rate`); 0 => model.py:79-81 schedule.      */
+  int32_t n_dilations;
+  int32_t dilations[WN_MAX_DILATIONS];
+  int32_t has_input_conv;              /* 1 for WaveNet (model.py:84-88); 0 for a bare layer     */
+  int32_t has_head;                    /* 1 for WaveNet (model.py:105-119); 0 for a bare layer   */
+  int32_t precision;                   /* wn_precision                                          */
+  int32_t max_batch;                   /* workspace is sized for (max_batch, max_time)          */
+  int32_t max_time;
+  int32_t device;                      /* CUDA device ordinal                                   */
+} wn_config;
+
+/* ---- lifetime (replaces WaveNet.__init__ + build, model.py:14-155,171-211) ------------- */
+int wn_create(const wn_config* cfg, wn_handle** out);
+void wn_destroy(wn_handle* h);
+const char* wn_last_error(void);
+
+/* ---- static facts ------------------------------------------------------------------------ */
+/* model.py:79-81,93-94,122: dilation of conv j of block b, and the receptive field */
+int wn_receptive_field(const wn_handle* h);
+int wn_dilation(const wn_handle* h, int block, int j);
+
+/* ---- parameters: Keras `trainable_variables` order and layouts --------------- */
+int wn_num_params(const wn_handle* h);
+int64_t wn_param_count(const wn_handle* h);               /* total scalar count (flat length) */
+/* name: e.g. "block3/dil0/kernel"; shape: up to 3 dims (K,Cin,Cout)/(in,out)/(C); offset into flat buffers */
+int wn_param_info(const wn_handle* h, int i, char* name, int name_len, int32_t* shape, int32_t* ndim, int64_t* offset);
+float* wn_params_dev(wn_handle* h);                        /* flat fp32 master weights (device) */
+float* wn_grads_dev(wn_handle* h);                         /* flat fp32 gradients (device)      */
+int wn_set_param(wn_handle* h, int i, const float* host);  /* Keras layout, fp32 */
+int wn_get_param(wn_handle* h, int i, float* host);
+int wn_get_grad(wn_handle* h, int i, float* host);
+/* call after writing wn_params_dev() directly (e.g. an optimizer step): re-packs the
+ * kernel-side weight copies (transposes, gate interleave, bf16). */
+int wn_params_changed(wn_handle* h, void* stream);
+
+/* ---- target quantiser (model.py:151-155,320: Keras Discretization) ----------------------- */
+/* idx[i] = #{k in 1..2^bits-1 : -1 + k*2^(1-bits) <= x[i]}, bit-exact, comparison based */
+int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void* stream);
+
+/* ---- WaveNet.call (model.py:213-239): x (B,T) fp32, cond (B,cond_in) fp32 or NULL ->
+ *      out (B,T,2^bits) softmax probabilities or (B,T,3M) mixture parameters, fp32 -------- */
+int wn_forward(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, float* out_dev, void* stream);
+
+/* ---- WaveNet.train_step up to the gradients (model.py:309-335) and test_step (:362-381) ---
+ * frames (B,T+1) fp32 in [-1,1]; loss = sum_{b,t} l / (B*n_replicas) written to loss_dev[0];
+ * gradients of every trainable variable land in wn_grads_dev() (overwritten). */
+int wn_train_step(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T,
+                  int n_replicas, float* loss_dev, void* stream);
+int wn_test_step(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T,
+                 int n_replicas, float* loss_dev, void* stream);
+/* same with HOST buffers: H2D of frames/cond, step, D2H of the loss, stream sync. */
+int wn_train_step_host(wn_handle* h, const float* frames_host, const float* cond_host, int B, int T,
+                       int n_replicas, float* loss_host);
+
+/* ---- WaveNetLayer.call (layers.py:178-224) and its adjoint, block granularity -------------
+ * x (B,T,R) fp32; cond (B,Cc) fp32 time-constant conditioning or NULL;
+ * x_out (B,T,R), skip (B,T,S or R) fp32.  Backward takes d x_out / d skip (either may be NULL
+ * = zero) and returns dx (B,T,R) and dcond (B,Cc) (may be NULL); parameter gradients of that
+ * block are written into wn_grads_dev(). */
+int wn_layer_forward(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T,
+                     float* x_out_dev, float* skip_dev, void* stream);
+int wn_layer_backward(wn_handle* h, int block, const float* dx_out_dev, const float* dskip_dev,
+                      float* dx_dev, float* dcond_dev, void* stream);
+
+/* ---- introspection for benchmarks --------------------------------------------------------- */
+/* number of kernel launches issued by the last wn_train_step / wn_forward on this handle */
+int64_t wn_last_launch_count(const wn_handle* h);
+/* accumulate CUDA-event time of one kernel class over subsequent steps: tag 0 = off,
+ * 1 = dilated-conv GEMMs (fwd+dgrad+wgrad), 2 = all GEMMs, 3 = loss/head reductions */
+int wn_profile_begin(wn_handle* h, int tag);
+int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
+const char* wn_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* WAVENET_B200_H_ */

@@ -1,0 +1,92 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares; constructor validation mirrors the reference's exceptions; config loader accepts
+reference YAMLs.  No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  from wavenets_b200 import _lib
+  lib = _lib.load()
+  hdr = open(os.path.join(ROOT, 'include', 'wavenet_b200.h')).read()
+  hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+  declared = sorted(set(re.findall(r'\b(wn_[a-z_0-9]+)\s*\(', hdr)))
+  assert len(declared) >= 20
+  for name in declared:
+    assert hasattr(lib, name), f'{name} declared in include/wavenet_b200.h but not exported'
+  assert sorted(_lib.EXPORTS) == declared
+  assert b'sm_100a' in lib.wn_build_info()
+
+
+def test_config_struct_matches_header_size():
+  from wavenets_b200 import _lib
+  import ctypes as C
+  n_i32 = 4 + 3 + 8 + 2 + 4 + 4 + 1 + 8 + 2 + 1 + 512 + 3 + 3
+  assert C.sizeof(_lib.WnConfig) == 4 * n_i32
+
+
+def test_constructor_validation_matches_reference():
+  from wavenets_b200 import WaveNet
+  ok = dict(final_layers_channels=[8])
+  with pytest.raises(ValueError, match="Conditioning must be"):
+    WaveNet(conditioning='speaker', **ok)
+  with pytest.raises(ValueError, match='Kernel size'):
+    WaveNet(kernel_size=1, **ok)
+  with pytest.raises(ValueError, match='dilation bound'):
+    WaveNet(dilation_bound=100, **ok)
+  with pytest.raises(ValueError, match='Layers per block'):
+    WaveNet(layers_per_block=0, **ok)
+  with pytest.raises(ValueError, match='Blocks'):
+    WaveNet(blocks=0, **ok)
+  with pytest.raises(ValueError, match='mixtures'):
+    WaveNet(num_mixtures=0, sampling_function='gaussian', **ok)
+  with pytest.raises(ValueError, match='Dropout'):
+    WaveNet(dropout=1.5, **ok)
+  with pytest.raises(ValueError, match='Sampling function'):
+    WaveNet(sampling_function='laplace', **ok)
+  with pytest.raises(ValueError, match='Categorical'):
+    WaveNet(num_mixtures=3, **ok)
+  with pytest.raises(ValueError, match='Mapping layers'):
+    WaveNet(mapping_layers='8', **ok)
+  with pytest.raises(NotImplementedError):
+    WaveNet(conditioning='local', **ok)
+  with pytest.raises(NotImplementedError):
+    WaveNet(activation='gelu', **ok)
+  m = WaveNet(kernel_size=2, channels=32, blocks=5, layers_per_block=5, dilation_bound=256, final_layers_channels=[128, 256])
+  assert m.receptive_field == 768
+  assert m.compute_receptive_field(16000) == 768 / 16000
+  with pytest.raises(ValueError, match='Loss must be set'):
+    m.compile(loss='mse')
+
+
+def test_layer_attributes_and_errors():
+  from wavenets_b200 import WaveNetLayer
+  lay = WaveNetLayer(kernel=2, dilation_rate=[1, 2, 4], activation='leaky_relu', channels=16, skip_channels=None)
+  assert lay.input_dilation == 1 and lay.depth == 3 and lay.kernel_size == 2 and lay.channels == 16
+  assert len(lay.dilated_stack) == 3 and lay.dilated_stack[-1].filters == 32 and lay.conv_skip is None
+  with pytest.raises(ValueError, match='not built'):
+    lay.compute_output_shape((1, 8, 16))
+
+
+def test_reference_yaml_loads():
+  from wavenets_b200 import load_config, model_kwargs, CONFIGS
+  ref = '/root/reference/configfiles/defaults.yaml'
+  cfg = load_config(ref if os.path.exists(ref) else None)
+  kw = model_kwargs(cfg)
+  assert kw['use_residual'] is True and kw['channels'] == 32 and kw['final_layers_channels'] == [128, 256]
+  assert set(CONFIGS) == {'c1', 'c2', 'c3', 'c4', 'c5'}
+
+
+def test_no_gpu_fails_loudly():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  from wavenets_b200 import WaveNet
+  import numpy as np
+  m = WaveNet(channels=8, blocks=2, final_layers_channels=[8], dilation_bound=4)
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    m(np.zeros((1, 16, 1), np.float32))

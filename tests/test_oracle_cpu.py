@@ -1,0 +1,138 @@
+"""CPU tests of the oracle (no GPU): known-answer tests derived by hand from the reference
+source, and three-way gradient agreement (manual backward / torch autograd / finite differences).
+The reference ships no tests or golden vectors: parity is UNPINNED and these
+are the pins we create ourselves."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import torch_ref as tr
+from oracle import wavenet_oracle as wo
+from tests.util import COND_IN, SMALL_MODELS, make_inputs, oracle_config, rel_err
+
+
+def test_dilation_schedule_defaults_yaml():
+  # defaults.yaml:9-18: K=2, 5 blocks x 5 layers, bound 256 -> powers 1..128 (never 256), RF 768
+  cfg = wo.Config(channels=32, blocks=5, layers_per_block=5, dilation_bound=256, final_layers_channels=[128, 256])
+  per_block, rf = wo.dilation_schedule(cfg)
+  assert per_block == [[1, 2, 4, 8, 16], [32, 64, 128, 1, 2], [4, 8, 16, 32, 64], [128, 1, 2, 4, 8], [16, 32, 64, 128, 1]]
+  assert rf == 768
+  assert wo.num_params(cfg) == 170816
+  f = wo.flops_fwd_per_sample(cfg)
+  assert f == {'dilated': 122880, 'pointwise': 10240, 'head': 204800, 'input': 128, 'total': 338048}
+
+
+def test_dilation_schedule_deep():
+  cfg = wo.Config(channels=8, blocks=40, layers_per_block=1, dilation_bound=1024, final_layers_channels=[])
+  per_block, rf = wo.dilation_schedule(cfg)
+  assert [d[0] for d in per_block[:11]] == [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1]
+  assert rf == 1 + 4 * 1023 + 1 == 4094
+
+
+def test_validation_errors():
+  with pytest.raises(ValueError):
+    wo.Config(kernel_size=1).validate()
+  with pytest.raises(ValueError):
+    wo.Config(dilation_bound=100).validate()
+  with pytest.raises(ValueError):
+    wo.Config(sampling_function='categorical', num_mixtures=3).validate()
+  with pytest.raises(ValueError):
+    wo.Config(conditioning='speaker').validate()
+
+
+def test_discretize_edges():
+  # model.py:152-153: boundaries linspace(-1,1,257)[1:-1]; idx = #boundaries <= x
+  x = np.array([-1.0, -1e-30, 0.0, 1.0, 0.999, -0.9921875, np.nextafter(np.float32(-0.9921875), np.float32(-2))], dtype=np.float32)
+  assert wo.discretize(x, 8).tolist() == [0, 127, 128, 255, 255, 1, 0]
+  # naive floor((x+1)*128) is wrong for tiny negatives: this is why the quantiser is comparison based
+  assert int(math.floor((np.float32(-1e-30) + np.float32(1.0)) * 128)) == 128
+  # 16 bit: every boundary exactly representable in fp32
+  b = np.linspace(-1, 1, 2 ** 16 + 1)[1:-1]
+  assert np.array_equal(b.astype(np.float32).astype(np.float64), b)
+  assert wo.discretize(np.array([0.0, 1.0, -1.0], np.float32), 16).tolist() == [32768, 65535, 0]
+
+
+def test_causal_conv_indices():
+  # Keras causal Conv1D: tap k multiplies x[t-(K-1-k)d]; zero left padding per batch row
+  x = np.arange(1, 13, dtype=np.float64).reshape(2, 6, 1)
+  W = np.array([10.0, 1.0]).reshape(2, 1, 1)
+  y = wo.causal_conv_fwd(x, W, np.zeros(1), dilation=2)
+  assert y[0, :, 0].tolist() == [1, 2, 13, 24, 35, 46]
+  assert y[1, :, 0].tolist() == [7, 8, 79, 90, 101, 112]   # no leakage across the batch boundary
+
+
+def test_mu_law_matches_formula():
+  x = np.array([-1.0, -0.5, 0.0, 0.25, 1.0], dtype=np.float32)
+  y = wo.mu_law(x)
+  assert y[0] == -1.0 and y[-1] == 1.0 and y[2] == 0.0
+  np.testing.assert_allclose(y[3], math.log(1 + 255 * 0.25) / math.log(256), rtol=1e-6)
+
+
+def test_skip_alias_is_pre_residual():
+  # layers.py:216-223: with skip_channels=None, skip = conv1(g) BEFORE the residual add
+  cfg = wo.Config(channels=4, blocks=1, layers_per_block=1, dilation_bound=2, final_layers_channels=[])
+  p = wo.init_params(cfg, seed=3)
+  x = np.random.default_rng(0).standard_normal((1, 9, 4))
+  lc = wo._layer_cfgs(cfg)[0]
+  xo, skip, _ = wo.layer_forward(p, 'block0', lc, x)
+  np.testing.assert_allclose(xo - x, skip, atol=1e-12)
+
+
+def test_causality_and_receptive_field():
+  cfg = wo.Config(channels=4, blocks=3, layers_per_block=1, dilation_bound=4, final_layers_channels=[4], bits=8)
+  _, rf = wo.dilation_schedule(cfg)   # dilations 1,2,1 -> rf 6
+  assert rf == 6
+  p = wo.init_params(cfg, seed=2)
+  rng = np.random.default_rng(1)
+  x = rng.standard_normal((1, 20, 1)) * 0.3
+  y0, _ = wo.model_forward(p, cfg, x, return_logits=True)
+  t = 15
+  for dt, changed in [(1, False), (0, True), (-(rf - 1), True), (-rf, False)]:  # output[t] sees exactly x[t-rf+1..t]
+    x2 = x.copy()
+    x2[0, t + dt, 0] += 0.5
+    y2, _ = wo.model_forward(p, cfg, x2, return_logits=True)
+    assert (np.abs(y2[0, t] - y0[0, t]).max() > 1e-9) == changed, (dt, changed)
+
+
+@pytest.mark.parametrize('name', sorted(SMALL_MODELS))
+def test_manual_backward_matches_autograd_and_fd(name):
+  kw = SMALL_MODELS[name]
+  cond_in = COND_IN if kw.get('conditioning') else 0
+  cfg = oracle_config(kw, cond_in)
+  p = wo.init_params(cfg, seed=1)
+  x, cond = make_inputs(2, 24, cond_in)
+  x = x.astype(np.float64)
+  cond = None if cond is None else cond.astype(np.float64)
+  loss, g, _ = wo.train_step(p, cfg, x, cond)
+  if cfg.l2_reg_factor == 0:
+    loss_t, g_t = tr.train_step(p, cfg, x, cond)
+    assert abs(loss - loss_t) <= 1e-9 * abs(loss_t)
+    for k in g:
+      assert rel_err(g[k], g_t[k]) < 1e-8, k
+  rng = np.random.default_rng(5)
+  for pname in list(p)[::3]:
+    idx = tuple(int(rng.integers(0, s)) for s in p[pname].shape)
+    eps = 1e-6
+    pp = {k: v.copy() for k, v in p.items()}
+    pp[pname][idx] += eps
+    lp, _, _ = wo.train_step(pp, cfg, x, cond)
+    pp[pname][idx] -= 2 * eps
+    lm, _, _ = wo.train_step(pp, cfg, x, cond)
+    num = (lp - lm) / (2 * eps)
+    assert abs(num - g[pname][idx]) <= 1e-4 * max(1.0, abs(num)) + 5e-3 * abs(num), (pname, num, g[pname][idx])
+
+
+def test_replica_scaling():
+  # compute_average_loss divides by B*replicas: two replicas' grads SUM to the 1-replica grads
+  kw = SMALL_MODELS['categorical_multidil']
+  cfg = oracle_config(kw)
+  p = wo.init_params(cfg, seed=1)
+  x, _ = make_inputs(4, 16)
+  x = x.astype(np.float64)
+  l_all, g_all, _ = wo.train_step(p, cfg, x)
+  l0, g0, _ = wo.train_step(p, cfg, x[:2], n_replicas=2)
+  l1, g1, _ = wo.train_step(p, cfg, x[2:], n_replicas=2)
+  assert abs((l0 + l1) - l_all) < 1e-9
+  for k in g_all:
+    assert rel_err(g0[k] + g1[k], g_all[k]) < 1e-10

@@ -1,0 +1,62 @@
+"""Shared helpers for the parity tests: one set of kwargs drives both the oracle and the product."""
+import numpy as np
+
+from oracle import wavenet_oracle as wo
+
+
+def oracle_config(kw: dict, cond_in: int = 0) -> wo.Config:
+  return wo.Config(
+    kernel_size=kw.get('kernel_size', 2), channels=kw.get('channels', 32), blocks=kw.get('blocks', 10),
+    layers_per_block=kw.get('layers_per_block', 1), activation=kw.get('activation'),
+    conditioning=kw.get('conditioning'), mapping_layers=kw.get('mapping_layers'),
+    mapping_activation=kw.get('mapping_activation'), dropout=kw.get('dropout', 0.0),
+    dilation_bound=kw.get('dilation_bound', 512), num_mixtures=kw.get('num_mixtures'),
+    sampling_function=kw.get('sampling_function', 'categorical'), bits=kw.get('bits', 8),
+    skip_channels=kw.get('skip_channels'), dilation_channels=kw.get('dilation_channels'),
+    use_residual=kw.get('use_residual', True), use_skip=kw.get('use_skip', True),
+    final_layers_channels=kw.get('final_layers_channels', []), l2_reg_factor=kw.get('l2_reg_factor', 0.0),
+    cond_in=cond_in)
+
+
+def make_inputs(B, T, cond_in=0, seed=0):
+  rng = np.random.default_rng(seed)
+  x = np.clip(rng.standard_normal((B, T + 1, 1)) * 0.4, -1, 1).astype(np.float32)
+  cond = None
+  if cond_in:
+    ids = rng.integers(0, cond_in, B)
+    cond = np.eye(cond_in, dtype=np.float32)[ids]
+  return x, cond
+
+
+def rel_err(a, b):
+  a = np.asarray(a, dtype=np.float64)
+  b = np.asarray(b, dtype=np.float64)
+  return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def rel_l2(a, b):
+  a = np.asarray(a, dtype=np.float64).ravel()
+  b = np.asarray(b, dtype=np.float64).ravel()
+  return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+# small model configurations shared by the CPU oracle tests and the GPU parity tests
+SMALL_MODELS = {
+  'categorical_multidil': dict(channels=8, blocks=3, layers_per_block=2, activation='leaky_relu', dilation_bound=8,
+                               final_layers_channels=[12, 16], bits=8),
+  'cond_skip': dict(channels=8, blocks=4, layers_per_block=1, dilation_bound=8, final_layers_channels=[12],
+                    skip_channels=6, dilation_channels=10, conditioning='global', mapping_layers=[4, 6],
+                    mapping_activation='leaky_relu', activation='relu'),
+  'logistic_cond': dict(channels=8, blocks=3, layers_per_block=3, activation='tanh', dilation_bound=4,
+                        final_layers_channels=[12], num_mixtures=3, sampling_function='logistic', bits=16,
+                        conditioning='global', mapping_layers=[4], mapping_activation='relu'),
+  'gaussian_noskip': dict(channels=8, blocks=3, layers_per_block=1, dilation_bound=4, final_layers_channels=[12],
+                          num_mixtures=4, sampling_function='gaussian', use_skip=False, skip_channels=5),
+  'k3_nores': dict(channels=8, blocks=3, layers_per_block=1, dilation_bound=9, final_layers_channels=[],
+                   use_residual=False, kernel_size=3),
+  'wide_ragged': dict(channels=40, blocks=2, layers_per_block=2, activation='sigmoid', dilation_bound=4,
+                      final_layers_channels=[70], skip_channels=72, dilation_channels=36, bits=8),
+  'l2': dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[8],
+             l2_reg_factor=0.01, conditioning='global', mapping_layers=[4], mapping_activation='tanh'),
+}
+COND_IN = 5

@@ -1,0 +1,342 @@
+// kernels_misc.cuh — HBM-bound kernels around the GEMMs: input causal conv, bias/conditioning
+// reductions, output head losses (softmax-256 CE, mixture of logistics / normals), quantiser,
+// weight packing, tiny dense layers of the conditioning MLP.  All coalesced along channels,
+// vectorised where layout allows, reductions via warp shuffles + deterministic 2-stage sums.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------ input causal conv (model.py:84-88,228)
+// h[b,t,c] = sum_k W[k,0,c] * x[b, t-(K-1-k)] + bias[c] ; x (B,T) fp32 with row stride ldx
+template <class T>
+__global__ void input_conv_fwd(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                               T* __restrict__ h, int B, int Tn, int R, int K) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * Tn * R;
+  if (i >= total) return;
+  const int c = (int)(i % R);
+  const long long row = i / R;
+  const int t = (int)(row % Tn), b = (int)(row / Tn);
+  float v = bias[c];
+  for (int k = 0; k < K; ++k) {
+    const int ts = t - (K - 1 - k);
+    if (ts >= 0) v = fmaf(W[k * R + c], x[(long long)b * ldx + ts], v);
+  }
+  h[i] = from_f<T>(v);
+}
+
+// stage 1 of input conv wgrad: partial[(chunk)][k][c] = sum_{t in chunk} dh[b,t,c] * x[b,t-(K-1-k)], k==K => bias
+template <class T>
+__global__ void input_conv_bwd_stage1(const float* __restrict__ x, int ldx, const T* __restrict__ dh, float* __restrict__ partial,
+                                      int B, int Tn, int R, int K, int rows_per_chunk) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= R) return;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * rows_per_chunk, t1 = min(Tn, t0 + rows_per_chunk);
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = t0; t < t1; ++t) {
+    const float d = to_f(dh[((long long)b * Tn + t) * R + c]);
+    for (int k = 0; k < K; ++k) {
+      const int ts = t - (K - 1 - k);
+      if (ts >= 0) acc[k] = fmaf(d, x[(long long)b * ldx + ts], acc[k]);
+    }
+    acc[K] += d;
+  }
+  const long long chunk = (long long)b * gridDim.y + blockIdx.y;
+  for (int k = 0; k <= K; ++k) partial[(chunk * (K + 1) + k) * R + c] = acc[k];
+}
+
+// ------------------------------------------------------------------ generic deterministic reductions
+// out[j] = scale * sum_{i<n_parts} partial[i*stride + j]  (+ addend[j]*add_coef), j < n
+__global__ void reduce_parts(const float* __restrict__ partial, int n_parts, long long stride, float* __restrict__ out, long long n,
+                             const float* __restrict__ addend, float add_coef) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int i = 0; i < n_parts; ++i) s += partial[i * stride + j];
+  if (addend) s = fmaf(add_coef, addend[j], s);
+  out[j] = s;
+}
+
+// column sums of G (B,T,N): stage 1 -> partial[b][chunk][n]
+template <class T>
+__global__ void colsum_stage1(const T* __restrict__ G, int ldg, float* __restrict__ partial, int Tn, int N, int rows_per_chunk) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * rows_per_chunk, t1 = min(Tn, t0 + rows_per_chunk);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const T* p = G + ((long long)b * Tn + t0) * ldg + n;
+  int t = t0;
+  for (; t + 3 < t1; t += 4, p += 4LL * ldg) {
+    s0 += to_f(p[0]); s1 += to_f(p[ldg]); s2 += to_f(p[2LL * ldg]); s3 += to_f(p[3LL * ldg]);
+  }
+  for (; t < t1; ++t, p += ldg) s0 += to_f(p[0]);
+  partial[((long long)b * gridDim.y + blockIdx.y) * N + n] = (s0 + s1) + (s2 + s3);
+}
+// stage 2: per_batch[b][n] (optional) and total[n] (optional) from partial[b][chunk][n]
+__global__ void colsum_stage2(const float* __restrict__ partial, int B, int chunks, int N, float* __restrict__ per_batch, int ldpb,
+                              float* __restrict__ total) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float tot = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[((long long)b * chunks + c) * N + n];
+    if (per_batch) per_batch[(long long)b * ldpb + n] = s;
+    tot += s;
+  }
+  if (total) total[n] = tot;
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+template <class TI, class TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f<TO>(to_f(in[i]));
+}
+template <class T>
+__global__ void add2_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f<T>(to_f(a[i]) + (b ? to_f(b[i]) : 0.f));
+}
+
+// ------------------------------------------------------------------ weight packing
+// dst[r][c] (ld = dst_ld, pre-zeroed) from Keras-layout src (rows x cols, row-major):
+//   mode 0: dst[r][c]  = src[r][c]
+//   mode 1: dst[c][r]  = src[r][c]                       (transpose, for dgrad)
+//   mode 2: gate interleave with tile width `tile`: dst col n' = tile_i*tile + j ;
+//           ch = tile_i*(tile/2) + (j % (tile/2)) ; src col = j < tile/2 ? ch : D + ch
+template <class TO>
+__global__ void pack_weight(const float* __restrict__ src, int rows, int cols, TO* __restrict__ dst, int dst_ld, int mode, int tile, int D,
+                            int dst_cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 2) {
+    const long long total = (long long)rows * dst_cols;
+    if (i >= total) return;
+    const int r = (int)(i / dst_cols), np = (int)(i % dst_cols);
+    const int half = tile >> 1;
+    const int ti = np / tile, j = np % tile;
+    const int ch = ti * half + (j % half);
+    float v = 0.f;
+    if (ch < D) v = src[(long long)r * cols + (j < half ? ch : D + ch)];
+    dst[(long long)r * dst_ld + np] = from_f<TO>(v);
+  } else {
+    const long long total = (long long)rows * cols;
+    if (i >= total) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = src[i];
+    if (mode == 0) dst[(long long)r * dst_ld + c] = from_f<TO>(v);
+    else dst[(long long)c * dst_ld + r] = from_f<TO>(v);
+  }
+}
+
+// ------------------------------------------------------------------ tiny dense layers (conditioning MLP, model.py:141-148)
+// y[b][n] = act(sum_k x[b][k] W[k][n] + bias[n])
+__global__ void dense_small_fwd(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                                float* __restrict__ y, int ldy, int B, int K, int N, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N, n = i % N;
+  float s = bias ? bias[n] : 0.f;
+  for (int k = 0; k < K; ++k) s = fmaf(x[(long long)b * ldx + k], W[(long long)k * N + n], s);
+  y[(long long)b * ldy + n] = wn_act<false>(act, s);
+}
+// dpre[b][n] = dy[b][n] * act'(y[b][n])   (in place on dy)
+__global__ void dense_small_actgrad(float* __restrict__ dy, const float* __restrict__ y, int n_total, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_total) dy[i] *= wn_act_grad_from_out(act, y[i]);
+}
+// dW[k][n] = sum_b x[b][k] dpre[b][n] ; db[n] = sum_b dpre[b][n]  (thread per (k,n), k==K => bias)
+__global__ void dense_small_wgrad(const float* __restrict__ x, int ldx, const float* __restrict__ dpre, int ldd, float* __restrict__ dW,
+                                  float* __restrict__ db, int B, int K, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (K + 1) * N) return;
+  const int k = i / N, n = i % N;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s = fmaf(k < K ? x[(long long)b * ldx + k] : 1.0f, dpre[(long long)b * ldd + n], s);
+  if (k < K) dW[(long long)k * N + n] = s;
+  else if (db) db[n] = s;
+}
+// dx[b][k] (+)= sum_n dpre[b][n] W[k][n]
+__global__ void dense_small_dgrad(const float* __restrict__ dpre, int ldd, const float* __restrict__ W, float* __restrict__ dx, int ldx,
+                                  int B, int K, int N, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K, k = i % K;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s = fmaf(dpre[(long long)b * ldd + n], W[(long long)k * N + n], s);
+  if (accumulate) dx[(long long)b * ldx + k] += s;
+  else dx[(long long)b * ldx + k] = s;
+}
+
+// ------------------------------------------------------------------ softmax-256 cross entropy (model.py:114-118,516)
+// One warp per row.  logits fp32 [rows][C]; the target index is quantised on the fly from
+// frames[b][t+1] (model.py:319-320).  Writes per-block loss partials, dlogits (= scale *
+// (softmax - onehot)) and optionally the probabilities (WaveNet.call output).
+template <class TD>
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, int C, const float* __restrict__ frames, int Tn,
+                                                         long long rows, int bits, float scale, TD* __restrict__ dlogits, int ldd,
+                                                         float* __restrict__ probs, float* __restrict__ loss_partial) {
+  __shared__ float wsum[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  float loss = 0.f;
+  if (row < rows) {
+    const float* lp = logits + row * C;
+    float m = -INFINITY;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(lp + c);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(lp + c);
+      s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+    }
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    int idx = -1;
+    if (frames) {
+      const long long b = row / Tn, t = row % Tn;
+      idx = wn_quantize_idx(frames[b * (Tn + 1) + t + 1], bits);
+      loss = lse - lp[idx];
+    }
+    const float inv = 1.0f / s;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(lp + c);
+      float p[4] = {expf(v.x - m) * inv, expf(v.y - m) * inv, expf(v.z - m) * inv, expf(v.w - m) * inv};
+      if (probs) *reinterpret_cast<float4*>(probs + row * C + c) = make_float4(p[0], p[1], p[2], p[3]);
+      if (dlogits) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dlogits[row * ldd + c + i] = from_f<TD>((p[i] - (c + i == idx ? 1.0f : 0.0f)) * scale);
+      }
+    }
+  }
+  if (loss_partial) {
+    if (lane == 0) wsum[warp] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += wsum[i];
+      loss_partial[blockIdx.x] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ mixture losses (model.py:517-547)
+// One thread per row; pred fp32 [rows][ldp] = [weights M | means M | log-scales M].
+// kind: 1 logistic, 2 gaussian.  SQRT2PI is the fp32 value of sqrt(2*3.14159265359) (model.py:9).
+#define WN_MAX_MIX 32
+template <class TD>
+__global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restrict__ pred, int ldp, int M, const float* __restrict__ frames,
+                                                           int Tn, long long rows, int bits, int kind, float scale, TD* __restrict__ dpred,
+                                                           int ldd, float* __restrict__ loss_partial) {
+  __shared__ float wsum[4];
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f;
+  if (row < rows) {
+    const float* p = pred + row * ldp;
+    const long long b = row / Tn, t = row % Tn;
+    const float y = frames[b * (Tn + 1) + t + 1];
+    float pi[WN_MAX_MIX], comp[WN_MAX_MIX];
+    float wmax = -INFINITY;
+    for (int m = 0; m < M; ++m) wmax = fmaxf(wmax, p[m]);
+    float wsumv = 0.f;
+    for (int m = 0; m < M; ++m) { pi[m] = expf(p[m] - wmax); wsumv += pi[m]; }
+    const float winv = 1.0f / wsumv;
+    float lik = 0.f;
+    const float SQRT2PI = 2.50662827463100050242f;
+    const float h = 0.5f / (float)(1 << bits);
+    for (int m = 0; m < M; ++m) {
+      pi[m] *= winv;
+      const float mu = p[M + m];
+      const float ls = fmaxf(p[2 * M + m], -7.0f);
+      if (kind == 2) {
+        const float sc = expf(ls);
+        const float xx = fminf((y - mu) / sc, 1e8f);
+        comp[m] = expf(-0.5f * xx * xx) / (sc * SQRT2PI);
+      } else {
+        const float e = expf(-ls);
+        comp[m] = wn_sigmoid<false>((y - mu + h) * e) - wn_sigmoid<false>((y - mu - h) * e);
+      }
+      lik += pi[m] * comp[m];
+    }
+    loss = -logf(lik);
+    if (dpred) {
+      const float linv = 1.0f / lik;
+      TD* d = dpred + row * ldd;
+      for (int m = 0; m < M; ++m) {
+        const float mu = p[M + m];
+        const float lsr = p[2 * M + m];
+        const float ls = fmaxf(lsr, -7.0f);
+        const float pass = lsr >= -7.0f ? 1.0f : 0.0f;
+        const float r = pi[m] * comp[m] * linv;
+        float dmu, dls;
+        if (kind == 2) {
+          const float sc = expf(ls);
+          const float xr = (y - mu) / sc;
+          const float nc = xr <= 1e8f ? 1.0f : 0.0f;
+          const float xx = fminf(xr, 1e8f);
+          dmu = -r * xx / sc * nc;
+          dls = -r * (xx * xx * nc - 1.0f) * pass;
+        } else {
+          const float e = expf(-ls);
+          const float a = (y - mu + h) * e, bq = (y - mu - h) * e;
+          const float sa = wn_sigmoid<false>(a), sb = wn_sigmoid<false>(bq);
+          const float dsa = sa * (1.0f - sa), dsb = sb * (1.0f - sb);
+          const float c = pi[m] * linv;
+          dmu = c * e * (dsa - dsb);
+          dls = c * (a * dsa - bq * dsb) * pass;
+        }
+        d[m] = from_f<TD>((pi[m] - r) * scale);
+        d[M + m] = from_f<TD>(dmu * scale);
+        d[2 * M + m] = from_f<TD>(dls * scale);
+      }
+      for (int m = 3 * M; m < ldd; ++m) d[m] = from_f<TD>(0.f);
+    }
+  }
+  if (loss_partial) {
+    loss = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) loss_partial[blockIdx.x] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+  }
+}
+
+// final loss: out[0] = scale * sum(partial) + extra   (single block, deterministic)
+__global__ void loss_finalize(const float* __restrict__ partial, int n, float scale, const float* __restrict__ extra, float extra_coef,
+                              float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v * scale + (extra ? extra_coef * extra[0] : 0.f);
+  }
+}
+
+// sum of squares of a weight tensor (L2 regulariser, model.py:331-334), single block, accumulates
+__global__ void sumsq_accum(const float* __restrict__ w, long long n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(w[i], w[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] += v;
+  }
+}
+
+// ------------------------------------------------------------------ quantiser (model.py:151-155)
+__global__ void quantize_kernel(const float* __restrict__ x, long long* __restrict__ idx, long long n, int bits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = wn_quantize_idx(x[i], bits);
+}

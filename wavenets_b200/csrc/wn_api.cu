@@ -1,0 +1,1367 @@
+// wn_api.cu — host orchestration + C ABI of libwavenet_b200.so  (see include/wavenet_b200.h)
+//
+// Path (reference file:line): WaveNet.train_step model.py:309-335 -> WaveNet.call :213-239 ->
+// WaveNetLayer.call layers.py:178-224, its adjoint, and the loss model.py:505-551.
+//
+// Every contraction of the pass is one of two kernels (gemm_simt.cuh / gemm_tc.cuh):
+//   conv_gemm : shifted-row GEMM with a fused epilogue (forward convs, dgrads, 1x1s, skip sum)
+//   wgrad     : time-contraction GEMM (weight gradients), deterministic split reduction
+// plus the HBM-bound kernels of kernels_misc.cuh.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/wavenet_b200.h"
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels_misc.cuh"
+
+// ============================================================================ errors
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* wn_last_error(void) { return g_err; }
+extern "C" const char* wn_build_info(void) {
+  return "libwavenet_b200 sm_100a; fp32 FFMA tier + bf16 tcgen05/TMEM/TMA tier; built " __DATE__ " " __TIME__;
+}
+
+#define CK(expr)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_err("CUDA error %s (%s) at %s:%d", cudaGetErrorName(e_), cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return WN_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+#define RET(expr)              \
+  do {                         \
+    int r_ = (expr);           \
+    if (r_ != WN_OK) return r_; \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int rup(int a, int b) { return (a + b - 1) / b * b; }
+
+// ============================================================================ model description
+struct ParamInfo {
+  std::string name;
+  int shape[3];
+  int ndim;
+  long long offset, count;
+};
+
+struct ConvP {           // one Conv1D of the reference (dilated K-tap or 1x1)
+  int K = 1, cin = 0, cout = 0, dil = 1;
+  int w_idx = -1, b_idx = -1;
+  bool gate = false;     // gated conv: forward weight columns tile-interleaved [filter|gate]
+  // fp32 tier packed copies
+  float* Wf = nullptr; int Npad = 0;      // [K*cin][Npad]      forward
+  float* Wb = nullptr; int Cpad = 0;      // [K*cout][Cpad]     dgrad (block k = W[k]^T)
+  // bf16 tier packed copies (K-major "B operand" matrices, see gemm_tc.cuh)
+  bf16* Wf16 = nullptr; int Kf16 = 0;     // [Npad16][K*cin]    forward:  row n, contraction contiguous
+  bf16* Wb16 = nullptr; int Kb16 = 0;     // [Cpad16][K*cout]   dgrad
+  int N16 = 0, C16 = 0, tileN16 = 0;
+};
+
+struct BlockP {
+  std::vector<ConvP> stack;   // dilated stack, last one gated (layers.py:64-88)
+  ConvP conv1;                // layers.py:92-96
+  bool has_skip = false;
+  ConvP conv_skip;            // layers.py:98-104
+  bool has_cond = false;
+  int cw_idx = -1, cb_idx = -1;  // conv_cond kernel/bias (layers.py:117-120)
+  // dg GEMM weights [Wr^T ; Ws^T] : fp32 [(R+S)][Dpad] ; bf16 [Dpad16][(R+S)]
+  float* Wdg = nullptr; int Dpad = 0;
+  bf16* Wdg16 = nullptr;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  bool dry = true;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    return p;
+  }
+};
+
+struct wn_handle {
+  wn_config cfg;
+  int R, D, S, Sp /*skip-sum width*/, K, L, Cc, Cout;
+  bool alias_skip;
+  std::vector<int> dil;  // flattened
+  int rf;
+  std::vector<ParamInfo> params;
+  long long n_scalars = 0;
+  float* d_params = nullptr;
+  float* d_grads = nullptr;
+  // network
+  ConvP input_conv;
+  std::vector<BlockP> blocks;
+  std::vector<ConvP> head;
+  std::vector<int> map_w, map_b, map_width;
+  float* Wskip = nullptr; int Spad = 0;   // fp32 [L*D][Spad]
+  bf16* Wskip16 = nullptr;                // bf16 [Spad16][L*D]
+  float* bskip_sum = nullptr;             // [Sp]
+  int* d_bskip_offsets = nullptr;
+  // packed pool
+  Arena pack, ws;
+  int maxB, maxT;
+  // workspace (void*: element type depends on precision)
+  void* h0 = nullptr;
+  std::vector<std::vector<void*>> acts;   // [block][j] pre-stack outputs (B,T,D)
+  std::vector<void*> zbuf, xout;          // per block
+  void* G_all = nullptr;                  // [L][B*T][D]  (sized with maxB*maxT rows per slab)
+  void* skipsum = nullptr;
+  std::vector<void*> hact;                // head hidden activations
+  float* logits = nullptr; int ldl = 0;   // fp32 [rows][ldl]
+  void* dlogits = nullptr; int ldd = 0;
+  void *dhA = nullptr, *dhB = nullptr;    // head backward ping-pong (width max head)
+  void* dskip = nullptr;
+  void *dxA = nullptr, *dxB = nullptr, *dotmp = nullptr;
+  void* dz = nullptr;
+  void *dpA = nullptr, *dpB = nullptr;    // pre-stack backward ping-pong (B,T,D)
+  float* colpart = nullptr; int col_chunks = 0;
+  float* wg_partial = nullptr; long long wg_partial_elems = 0;
+  float* loss_partial = nullptr; int loss_parts_cap = 0;
+  float* cond_act[WN_MAX_LIST + 1] = {};  // mapping activations (B, width)
+  float* cond_dact = nullptr;             // scratch (B, max width)
+  float* cond_dact2 = nullptr;
+  float* cb = nullptr;                    // [L][B][2D]
+  float* dcb = nullptr;                   // [L][B][2D]
+  float* dcond = nullptr;                 // (B,Cc)
+  float* l2_sum = nullptr;
+  float* layer_xin = nullptr;             // layer API staging (fp32 in -> T)
+  void* layer_in = nullptr;
+  float* d_loss = nullptr;                // for the host-buffer entry point
+  float* d_frames = nullptr; float* d_cond_in = nullptr;
+  float* pin_frames = nullptr; float* pin_cond = nullptr; float* pin_loss = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // state
+  int lastB = 0, lastT = 0;
+  bool fwd_valid = false;
+  bool layer_fwd_valid[WN_MAX_DILATIONS] = {};
+  const float* last_cond = nullptr;
+  long long launches = 0;
+  // profiling
+  int prof_tag = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  long long prof_launches = 0;
+  TmapCache tmaps;
+};
+
+enum { CLS_DILATED = 1, CLS_GEMM = 2, CLS_LOSS = 3, CLS_MISC = 4 };
+
+struct LaunchScope {
+  wn_handle* h; cudaStream_t st; bool timed = false; size_t slot = 0;
+  LaunchScope(wn_handle* h_, cudaStream_t st_, int cls) : h(h_), st(st_) {
+    h->launches++;
+    const int t = h->prof_tag;
+    if (t && ((t == 1 && cls == CLS_DILATED) || (t == 2 && (cls == CLS_DILATED || cls == CLS_GEMM)) || (t == 3 && cls == CLS_LOSS) ||
+              (t == 4))) {
+      if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        h->prof_events.push_back({a, b});
+      }
+      slot = h->prof_used++;
+      cudaEventRecord(h->prof_events[slot].first, st);
+      timed = true;
+      h->prof_launches++;
+    }
+  }
+  ~LaunchScope() {
+    if (timed) cudaEventRecord(h->prof_events[slot].second, st);
+  }
+};
+
+// ============================================================================ build
+static int add_param(wn_handle* h, const std::string& name, std::initializer_list<int> shape) {
+  ParamInfo p;
+  p.name = name;
+  p.ndim = (int)shape.size();
+  p.count = 1;
+  int i = 0;
+  for (int s : shape) { p.shape[i++] = s; p.count *= s; }
+  for (; i < 3; ++i) p.shape[i] = 1;
+  p.offset = h->n_scalars;
+  // keep every tensor 16-byte aligned in the flat buffers
+  h->n_scalars += (p.count + 3) / 4 * 4;
+  h->params.push_back(p);
+  return (int)h->params.size() - 1;
+}
+
+static int validate_config(const wn_config& c) {
+  // reference model.py:52-70
+  if (c.conditioning != 0 && c.conditioning != 1) { set_err("Conditioning must be 'global', 'local' or None."); return c.conditioning == 2 ? WN_ERR_UNSUPPORTED : WN_ERR_VALUE; }
+  if (c.kernel_size < 2) { set_err("Kernel size must be at least 2."); return WN_ERR_VALUE; }
+  if (c.dilation_bound < 1) { set_err("dilation bound must be power of kernel_size."); return WN_ERR_VALUE; }
+  {
+    long long v = 1; bool ok = false;
+    for (int i = 0; i < 40 && v <= c.dilation_bound; ++i) { if (v == c.dilation_bound) { ok = true; break; } v *= c.kernel_size; }
+    if (!ok && c.n_dilations == 0) { set_err("dilation bound must be power of kernel_size."); return WN_ERR_VALUE; }
+  }
+  if (c.layers_per_block < 1) { set_err("Layers per block must be at least 1."); return WN_ERR_VALUE; }
+  if (c.blocks < 1) { set_err("Blocks must be at least 1."); return WN_ERR_VALUE; }
+  if (c.num_mixtures < 0) { set_err("Number of mixtures must be at least 1 or None."); return WN_ERR_VALUE; }
+  if (c.dropout < 0 || c.dropout > 1) { set_err("Dropout must be between 0 and 1."); return WN_ERR_VALUE; }
+  if (c.sampling_function < 0 || c.sampling_function > 2) { set_err("Sampling function must be categorical, logistic or gaussian."); return WN_ERR_VALUE; }
+  if (c.sampling_function == WN_CATEGORICAL && c.num_mixtures != 0) { set_err("Categorical sampling cannot be used with mixtures."); return WN_ERR_VALUE; }
+  if (c.has_head && c.sampling_function != WN_CATEGORICAL && c.num_mixtures == 0) { set_err("mixture sampling needs num_mixtures"); return WN_ERR_VALUE; }
+  if (c.channels < 1 || c.max_batch < 1 || c.max_time < 1) { set_err("channels / max_batch / max_time must be positive"); return WN_ERR_VALUE; }
+  if (c.kernel_size > WN_MAX_SEG) { set_err("kernel_size > %d not built", WN_MAX_SEG); return WN_ERR_UNSUPPORTED; }
+  if (c.num_mixtures > WN_MAX_MIX) { set_err("num_mixtures > %d not built", WN_MAX_MIX); return WN_ERR_UNSUPPORTED; }
+  if (c.blocks * c.layers_per_block > WN_MAX_DILATIONS) { set_err("too many dilated convs"); return WN_ERR_UNSUPPORTED; }
+  if (c.n_mapping < 0 || c.n_mapping > WN_MAX_LIST || c.n_final < 0 || c.n_final > WN_MAX_LIST) { set_err("list too long"); return WN_ERR_VALUE; }
+  if (c.has_head && c.sampling_function == WN_CATEGORICAL && (c.bits < 1 || c.bits > 16)) { set_err("bits must be in 1..16"); return WN_ERR_VALUE; }
+  if (c.conditioning && c.cond_in < 1) { set_err("conditioning needs cond_in >= 1"); return WN_ERR_VALUE; }
+  if (c.precision != WN_FP32 && c.precision != WN_BF16) { set_err("unknown precision"); return WN_ERR_VALUE; }
+  return WN_OK;
+}
+
+static ConvP make_conv(wn_handle* h, const std::string& pfx, int K, int cin, int cout, int dil, bool gate) {
+  ConvP c;
+  c.K = K; c.cin = cin; c.cout = cout; c.dil = dil; c.gate = gate;
+  c.w_idx = add_param(h, pfx + "/kernel", {K, cin, cout});
+  c.b_idx = add_param(h, pfx + "/bias", {cout});
+  return c;
+}
+
+template <class T> static size_t esz() { return sizeof(T); }
+
+// lays out (dry==true: only measures) every packed weight copy and workspace buffer
+static void layout_buffers(wn_handle* h) {
+  const bool bf = h->cfg.precision == WN_BF16;
+  const size_t es = bf ? 2 : 4;
+  Arena& P = h->pack;
+  auto lay_conv = [&](ConvP& c) {
+    if (!bf) {
+      c.Npad = rup(c.cout, 64);
+      c.Wf = (float*)P.take((size_t)c.K * c.cin * c.Npad * 4);
+      c.Cpad = rup(c.cin, 64);
+      c.Wb = (float*)P.take((size_t)c.K * c.cout * c.Cpad * 4);
+    } else {
+      tc_pick_tile(c.cout, c.gate, &c.N16, &c.tileN16);
+      c.Kf16 = c.K * c.cin;
+      c.Wf16 = (bf16*)P.take((size_t)c.N16 * c.Kf16 * 2);
+      int tn;
+      tc_pick_tile(c.cin, false, &c.C16, &tn);
+      c.Kb16 = c.K * c.cout;
+      c.Wb16 = (bf16*)P.take((size_t)c.C16 * rup(c.Kb16, 64) * 2);
+    }
+  };
+  if (h->cfg.has_input_conv) { /* input conv is elementwise: uses the flat params directly */ }
+  for (auto& b : h->blocks) {
+    for (auto& c : b.stack) lay_conv(c);
+    lay_conv(b.conv1);
+    if (b.has_skip) lay_conv(b.conv_skip);
+    const int rs = h->R + (b.has_skip ? h->S : 0);
+    if (!bf) {
+      b.Dpad = rup(h->D, 64);
+      b.Wdg = (float*)P.take((size_t)rs * b.Dpad * 4);
+    } else {
+      int n16, tn;
+      tc_pick_tile(h->D, false, &n16, &tn);
+      b.Dpad = n16;
+      b.Wdg16 = (bf16*)P.take((size_t)n16 * rup(rs, 64) * 2);
+    }
+  }
+  for (auto& c : h->head) lay_conv(c);
+  if (!bf) {
+    h->Spad = rup(h->Sp, 64);
+    h->Wskip = (float*)P.take((size_t)h->L * h->D * h->Spad * 4);
+  } else {
+    int tn;
+    tc_pick_tile(h->Sp, false, &h->Spad, &tn);
+    h->Wskip16 = (bf16*)P.take((size_t)h->Spad * h->L * h->D * 2);
+  }
+  h->bskip_sum = (float*)P.take((size_t)h->Sp * 4);
+  h->d_bskip_offsets = (int*)P.take((size_t)h->L * 4 * 2);
+
+  Arena& W = h->ws;
+  const size_t rows = (size_t)h->maxB * h->maxT;
+  const int R = h->R, D = h->D, Sp = h->Sp, L = h->L;
+  h->h0 = W.take(rows * R * es);
+  h->acts.assign(L, {});
+  h->zbuf.assign(L, nullptr);
+  h->xout.assign(L, nullptr);
+  for (int l = 0; l < L; ++l) {
+    const int depth = (int)h->blocks[l].stack.size();
+    h->acts[l].assign(depth - 1 > 0 ? depth - 1 : 0, nullptr);
+    for (int j = 0; j + 1 < depth; ++j) h->acts[l][j] = W.take(rows * D * es);
+    h->zbuf[l] = W.take(rows * 2 * D * es);
+    h->xout[l] = W.take(rows * R * es);
+  }
+  h->G_all = W.take((size_t)L * rows * D * es);
+  h->skipsum = W.take(rows * Sp * es);
+  int maxhead = Sp > R ? Sp : R;
+  h->hact.assign(h->head.size() > 0 ? h->head.size() - 1 : 0, nullptr);
+  for (size_t i = 0; i + 1 < h->head.size(); ++i) {
+    h->hact[i] = W.take(rows * h->head[i].cout * es);
+    if (h->head[i].cout > maxhead) maxhead = h->head[i].cout;
+  }
+  if (h->cfg.has_head) {
+    h->ldl = h->Cout;
+    h->logits = (float*)W.take(rows * h->ldl * 4);
+    h->ldd = bf ? rup(h->Cout, 64) : h->Cout;
+    h->dlogits = W.take(rows * h->ldd * es);
+    h->dhA = W.take(rows * maxhead * es);
+    h->dhB = W.take(rows * maxhead * es);
+  }
+  h->dskip = W.take(rows * Sp * es);
+  h->dxA = W.take(rows * R * es);
+  h->dxB = W.take(rows * R * es);
+  h->dotmp = W.take(rows * R * es);
+  h->dz = W.take(rows * 2 * D * es);
+  h->dpA = W.take(rows * D * es);
+  h->dpB = W.take(rows * D * es);
+  // reductions
+  h->col_chunks = cdiv(h->maxT, 256);
+  int nmax = 2 * D;
+  if (R > nmax) nmax = R;
+  if (Sp > nmax) nmax = Sp;
+  for (auto& c : h->head) if (c.cout > nmax) nmax = c.cout;
+  const int kin = (h->K + 1);
+  size_t colpart_elems = (size_t)h->maxB * h->col_chunks * (nmax > kin * R ? nmax : kin * R);
+  h->colpart = (float*)W.take(colpart_elems * 4);
+  // wgrad partials: nsplit * ktot * N, largest contraction
+  long long maxkn = 0;
+  auto upd = [&](long long k, long long n) { if (k * n > maxkn) maxkn = k * n; };
+  for (auto& b : h->blocks) {
+    for (auto& c : b.stack) upd((long long)c.K * c.cin, c.cout);
+    upd(D, R);
+    if (b.has_skip) upd(D, h->S);
+  }
+  for (auto& c : h->head) upd(c.cin, c.cout);
+  h->wg_partial_elems = maxkn * WN_MAX_WGRAD_SPLITS;
+  h->wg_partial = (float*)W.take((size_t)h->wg_partial_elems * 4);
+  h->loss_parts_cap = cdiv((long long)rows, 8) + 8;
+  h->loss_partial = (float*)W.take((size_t)h->loss_parts_cap * 4);
+  int maxw = h->cfg.cond_in;
+  for (int i = 0; i < h->cfg.n_mapping; ++i) if (h->cfg.mapping_layers[i] > maxw) maxw = h->cfg.mapping_layers[i];
+  if (h->cfg.conditioning) {
+    for (int i = 0; i < h->cfg.n_mapping; ++i) h->cond_act[i] = (float*)W.take((size_t)h->maxB * h->cfg.mapping_layers[i] * 4);
+    h->cond_dact = (float*)W.take((size_t)h->maxB * maxw * 4);
+    h->cond_dact2 = (float*)W.take((size_t)h->maxB * maxw * 4);
+    h->cb = (float*)W.take((size_t)L * h->maxB * 2 * D * 4);
+    h->dcb = (float*)W.take((size_t)L * h->maxB * 2 * D * 4);
+    h->dcond = (float*)W.take((size_t)h->maxB * (h->Cc > 0 ? h->Cc : 1) * 4);
+  }
+  h->l2_sum = (float*)W.take(16);
+  h->d_loss = (float*)W.take(16);
+  h->layer_in = W.take(rows * R * es);
+  h->d_frames = (float*)W.take((size_t)h->maxB * (h->maxT + 1) * 4);
+  h->d_cond_in = (float*)W.take((size_t)h->maxB * (h->cfg.cond_in > 0 ? h->cfg.cond_in : 1) * 4);
+}
+
+extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
+  if (!cfg || !out) { set_err("null argument"); return WN_ERR_VALUE; }
+  *out = nullptr;
+  RET(validate_config(*cfg));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device: libwavenet_b200 has no CPU fallback");
+    return WN_ERR_CUDA;
+  }
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_err("device %d is sm_%d%d; libwavenet_b200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    return WN_ERR_CUDA;
+  }
+  wn_handle* h = new wn_handle();
+  h->cfg = *cfg;
+  const wn_config& c = h->cfg;
+  h->K = c.kernel_size;
+  h->R = c.channels;
+  h->D = c.dilation_channels > 0 ? c.dilation_channels : c.channels;
+  h->S = c.skip_channels;
+  h->alias_skip = c.skip_channels == 0;
+  h->Sp = h->alias_skip ? h->R : h->S;
+  h->L = c.blocks;
+  h->Cout = c.num_mixtures > 0 ? 3 * c.num_mixtures : (1 << c.bits);
+  h->Cc = 0;
+  if (c.conditioning) h->Cc = c.n_mapping > 0 ? c.mapping_layers[c.n_mapping - 1] : c.cond_in;
+  h->maxB = c.max_batch;
+  h->maxT = c.max_time;
+  // dilation schedule (model.py:79-81) unless given explicitly (bare WaveNetLayer)
+  const int nconv = c.blocks * c.layers_per_block;
+  if (c.n_dilations > 0) {
+    if (c.n_dilations != nconv) { set_err("n_dilations must equal blocks*layers_per_block"); delete h; return WN_ERR_VALUE; }
+    h->dil.assign(c.dilations, c.dilations + nconv);
+  } else {
+    int max_power = (int)(log((double)c.dilation_bound) / log((double)c.kernel_size));
+    // guard against floating error exactly like int(math.log(bound, k)) for exact powers
+    { long long v = 1; int pw = 0; while (v < c.dilation_bound) { v *= c.kernel_size; ++pw; } max_power = pw; }
+    if (max_power < 1) { set_err("dilation bound must be power of kernel_size."); delete h; return WN_ERR_VALUE; }
+    for (int i = 0; i < nconv; ++i) {
+      long long d = 1;
+      for (int p = 0; p < i % max_power; ++p) d *= c.kernel_size;
+      h->dil.push_back((int)d);
+    }
+  }
+  long long sumd = 0;
+  for (int d : h->dil) sumd += d;
+  h->rf = (int)(1 + sumd * (c.kernel_size - 1) + 1);  // model.py:122
+
+  // ---- parameters in Keras tracking order
+  if (c.has_input_conv) h->input_conv = make_conv(h, "causal", h->K, 1, h->R, 1, false);
+  h->blocks.resize(h->L);
+  for (int b = 0; b < h->L; ++b) {
+    BlockP& bl = h->blocks[b];
+    char pfx[64];
+    int cin = h->R;
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      const bool last = j == c.layers_per_block - 1;
+      snprintf(pfx, sizeof(pfx), "block%d/dil%d", b, j);
+      bl.stack.push_back(make_conv(h, pfx, h->K, cin, last ? 2 * h->D : h->D, h->dil[b * c.layers_per_block + j], last));
+      cin = h->D;
+    }
+    snprintf(pfx, sizeof(pfx), "block%d/conv1", b);
+    bl.conv1 = make_conv(h, pfx, 1, h->D, h->R, 1, false);
+    bl.has_skip = !h->alias_skip;
+    if (bl.has_skip) {
+      snprintf(pfx, sizeof(pfx), "block%d/conv_skip", b);
+      bl.conv_skip = make_conv(h, pfx, 1, h->D, h->S, 1, false);
+    }
+    bl.has_cond = c.conditioning != 0;
+    if (bl.has_cond) {
+      snprintf(pfx, sizeof(pfx), "block%d/conv_cond", b);
+      bl.cw_idx = add_param(h, std::string(pfx) + "/kernel", {1, h->Cc, 2 * h->D});
+      bl.cb_idx = add_param(h, std::string(pfx) + "/bias", {2 * h->D});
+    }
+  }
+  if (c.has_head) {
+    int cin = c.use_skip ? h->Sp : h->R;
+    for (int i = 0; i <= c.n_final; ++i) {
+      char pfx[32];
+      snprintf(pfx, sizeof(pfx), "final%d", i);
+      const int ch = i < c.n_final ? c.final_layers_channels[i] : h->Cout;
+      h->head.push_back(make_conv(h, pfx, 1, cin, ch, 1, false));
+      cin = ch;
+    }
+  }
+  if (c.conditioning && c.has_head) {
+    int cin = c.cond_in;
+    for (int i = 0; i < c.n_mapping; ++i) {
+      char pfx[32];
+      snprintf(pfx, sizeof(pfx), "mapping%d", i);
+      h->map_w.push_back(add_param(h, std::string(pfx) + "/kernel", {cin, c.mapping_layers[i]}));
+      h->map_b.push_back(add_param(h, std::string(pfx) + "/bias", {c.mapping_layers[i]}));
+      h->map_width.push_back(c.mapping_layers[i]);
+      cin = c.mapping_layers[i];
+    }
+  }
+  if (c.precision == WN_BF16) {
+    int r = tc_check_config(h->R, h->D, h->Sp, c.kernel_size);
+    if (r != 0) {
+      set_err("bf16/tcgen05 tier needs channels, dilation_channels and skip_channels to be multiples of 64 (got R=%d D=%d S=%d); use precision=fp32", h->R, h->D, h->Sp);
+      delete h;
+      return WN_ERR_UNSUPPORTED;
+    }
+    for (auto& hc : h->head)
+      if (hc.cin % 64 != 0) { set_err("bf16 tier needs head widths that are multiples of 64"); delete h; return WN_ERR_UNSUPPORTED; }
+  }
+
+  // ---- allocate
+  h->pack.dry = true; h->ws.dry = true;
+  layout_buffers(h);
+  const size_t pack_bytes = h->pack.off + 256, ws_bytes = h->ws.off + 256;
+  h->pack = Arena(); h->ws = Arena();
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->d_params, (size_t)h->n_scalars * 4 + 64)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_grads, (size_t)h->n_scalars * 4 + 64)) != cudaSuccess ||
+      (e = cudaMalloc(&h->pack.base, pack_bytes)) != cudaSuccess || (e = cudaMalloc(&h->ws.base, ws_bytes)) != cudaSuccess) {
+    set_err("cudaMalloc failed (%s): params %lld scalars, packed %zu B, workspace %zu B", cudaGetErrorString(e), h->n_scalars, pack_bytes, ws_bytes);
+    wn_destroy(h);
+    return WN_ERR_CUDA;
+  }
+  h->pack.cap = pack_bytes; h->ws.cap = ws_bytes;
+  h->pack.dry = false; h->ws.dry = false;
+  layout_buffers(h);
+  cudaMemset(h->d_params, 0, (size_t)h->n_scalars * 4);
+  cudaMemset(h->d_grads, 0, (size_t)h->n_scalars * 4);
+  cudaMemset(h->pack.base, 0, pack_bytes);
+  cudaMemset(h->ws.base, 0, ws_bytes);
+  cudaMallocHost(&h->pin_frames, (size_t)h->maxB * (h->maxT + 1) * 4);
+  cudaMallocHost(&h->pin_cond, (size_t)h->maxB * (c.cond_in > 0 ? c.cond_in : 1) * 4);
+  cudaMallocHost(&h->pin_loss, 16);
+  cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  // offsets of the per-block skip biases (or conv1 biases when aliased) for bskip_sum
+  {
+    std::vector<int> offs;
+    for (auto& b : h->blocks) offs.push_back((int)h->params[b.has_skip ? b.conv_skip.b_idx : b.conv1.b_idx].offset);
+    cudaMemcpy(h->d_bskip_offsets, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice);
+  }
+  if (c.precision == WN_BF16) {
+    int r = tc_init();
+    if (r != 0) { set_err("cannot resolve cuTensorMapEncodeTiled from the driver"); wn_destroy(h); return WN_ERR_CUDA; }
+  }
+  CK(cudaDeviceSynchronize());
+  int r = wn_params_changed(h, nullptr);
+  if (r != WN_OK) { wn_destroy(h); return r; }
+  *out = h;
+  return WN_OK;
+}
+
+extern "C" void wn_destroy(wn_handle* h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  cudaFree(h->d_params); cudaFree(h->d_grads); cudaFree(h->pack.base); cudaFree(h->ws.base);
+  cudaFreeHost(h->pin_frames); cudaFreeHost(h->pin_cond); cudaFreeHost(h->pin_loss);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+extern "C" int wn_receptive_field(const wn_handle* h) { return h ? h->rf : WN_ERR_VALUE; }
+extern "C" int wn_dilation(const wn_handle* h, int block, int j) {
+  if (!h || block < 0 || block >= h->L || j < 0 || j >= h->cfg.layers_per_block) { set_err("bad block/conv index"); return WN_ERR_VALUE; }
+  return h->dil[block * h->cfg.layers_per_block + j];
+}
+extern "C" int wn_num_params(const wn_handle* h) { return h ? (int)h->params.size() : WN_ERR_VALUE; }
+extern "C" int64_t wn_param_count(const wn_handle* h) { return h ? h->n_scalars : WN_ERR_VALUE; }
+extern "C" int wn_param_info(const wn_handle* h, int i, char* name, int name_len, int32_t* shape, int32_t* ndim, int64_t* offset) {
+  if (!h || i < 0 || i >= (int)h->params.size()) { set_err("bad param index"); return WN_ERR_VALUE; }
+  const ParamInfo& p = h->params[i];
+  if (name && name_len > 0) { strncpy(name, p.name.c_str(), name_len - 1); name[name_len - 1] = 0; }
+  if (shape) for (int k = 0; k < 3; ++k) shape[k] = p.shape[k];
+  if (ndim) *ndim = p.ndim;
+  if (offset) *offset = p.offset;
+  return WN_OK;
+}
+extern "C" float* wn_params_dev(wn_handle* h) { return h ? h->d_params : nullptr; }
+extern "C" float* wn_grads_dev(wn_handle* h) { return h ? h->d_grads : nullptr; }
+extern "C" int wn_set_param(wn_handle* h, int i, const float* host) {
+  if (!h || i < 0 || i >= (int)h->params.size() || !host) { set_err("bad param index"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpy(h->d_params + h->params[i].offset, host, h->params[i].count * 4, cudaMemcpyHostToDevice));
+  h->fwd_valid = false;
+  return WN_OK;  // caller must call wn_params_changed() after the last wn_set_param
+}
+extern "C" int wn_get_param(wn_handle* h, int i, float* host) {
+  if (!h || i < 0 || i >= (int)h->params.size() || !host) { set_err("bad param index"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpy(host, h->d_params + h->params[i].offset, h->params[i].count * 4, cudaMemcpyDeviceToHost));
+  return WN_OK;
+}
+extern "C" int wn_get_grad(wn_handle* h, int i, float* host) {
+  if (!h || i < 0 || i >= (int)h->params.size() || !host) { set_err("bad param index"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpy(host, h->d_grads + h->params[i].offset, h->params[i].count * 4, cudaMemcpyDeviceToHost));
+  return WN_OK;
+}
+
+// ============================================================================ weight packing
+__global__ void bias_table_sum(const float* __restrict__ params, const int* __restrict__ offsets, int L, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) s += params[offsets[l] + i];
+  out[i] = s;
+}
+
+template <class TO>
+static void pack_launch(wn_handle* h, cudaStream_t st, const float* src, int rows, int cols, TO* dst, int dst_ld, int mode, int tile, int D,
+                        int dst_cols) {
+  const long long total = mode == 2 ? (long long)rows * dst_cols : (long long)rows * cols;
+  if (total <= 0) return;
+  pack_weight<TO><<<cdiv(total, 256), 256, 0, st>>>(src, rows, cols, dst, dst_ld, mode, tile, D, dst_cols);
+  h->launches++;
+}
+
+extern "C" int wn_params_changed(wn_handle* h, void* stream) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = h->cfg.precision == WN_BF16;
+  const float* P = h->d_params;
+  auto W = [&](const ConvP& c) { return P + h->params[c.w_idx].offset; };
+  auto pack_conv = [&](ConvP& c) {
+    const int ktot = c.K * c.cin;
+    if (!bf) {
+      // forward [ktot][Npad]
+      if (c.gate) pack_launch<float>(h, st, W(c), ktot, c.cout, c.Wf, c.Npad, 2, 64, c.cout / 2, c.Npad);
+      else pack_launch<float>(h, st, W(c), ktot, c.cout, c.Wf, c.Npad, 0, 0, 0, 0);
+      // dgrad: block k = W[k]^T  -> [cout][Cpad]
+      for (int k = 0; k < c.K; ++k)
+        pack_launch<float>(h, st, W(c) + (size_t)k * c.cin * c.cout, c.cin, c.cout, c.Wb + (size_t)k * c.cout * c.Cpad, c.Cpad, 1, 0, 0, 0);
+    } else {
+      // forward B operand [N16][ktot]: row n = (permuted) output column, contraction contiguous
+      if (c.gate) {
+        // transpose of the interleaved matrix: do it via a temporary-free two-step: pack mode 2 into
+        // the dgrad scratch is not possible (sizes differ), so use the dedicated kernel
+        tc_pack_gate_T(st, W(c), ktot, c.cout, c.Wf16, c.Kf16, c.tileN16, c.cout / 2, c.N16);
+        h->launches++;
+      } else {
+        pack_launch<bf16>(h, st, W(c), ktot, c.cout, c.Wf16, c.Kf16, 1, 0, 0, 0);
+      }
+      // dgrad B operand [C16][K*cout]: row = input channel, contraction index (k, cout)
+      for (int k = 0; k < c.K; ++k)
+        pack_launch<bf16>(h, st, W(c) + (size_t)k * c.cin * c.cout, c.cin, c.cout, c.Wb16 + (size_t)k * c.cout, rup(c.Kb16, 64), 0, 0, 0, 0);
+    }
+  };
+  for (int l = 0; l < h->L; ++l) {
+    BlockP& b = h->blocks[l];
+    for (auto& c : b.stack) pack_conv(c);
+    pack_conv(b.conv1);
+    if (b.has_skip) pack_conv(b.conv_skip);
+    const int rs = h->R + (b.has_skip ? h->S : 0);
+    const ConvP& sk = b.has_skip ? b.conv_skip : b.conv1;
+    if (!bf) {
+      pack_launch<float>(h, st, W(b.conv1), h->D, h->R, b.Wdg, b.Dpad, 1, 0, 0, 0);
+      if (b.has_skip) pack_launch<float>(h, st, W(b.conv_skip), h->D, h->S, b.Wdg + (size_t)h->R * b.Dpad, b.Dpad, 1, 0, 0, 0);
+      pack_launch<float>(h, st, W(sk), h->D, h->Sp, h->Wskip + (size_t)l * h->D * h->Spad, h->Spad, 0, 0, 0, 0);
+    } else {
+      // dg B operand [Dpad16][rs]: row = channel of g, contraction over (R | S)
+      pack_launch<bf16>(h, st, W(b.conv1), h->D, h->R, b.Wdg16, rup(rs, 64), 0, 0, 0, 0);
+      if (b.has_skip) pack_launch<bf16>(h, st, W(b.conv_skip), h->D, h->S, b.Wdg16 + h->R, rup(rs, 64), 0, 0, 0, 0);
+      // skip-sum B operand [Spad16][L*D]: row = skip channel, contraction over (l, d)
+      pack_launch<bf16>(h, st, W(sk), h->D, h->Sp, h->Wskip16 + (size_t)l * h->D, h->L * h->D, 1, 0, 0, 0);
+    }
+  }
+  for (auto& c : h->head) pack_conv(c);
+  bias_table_sum<<<cdiv(h->Sp, 128), 128, 0, st>>>(P, h->d_bskip_offsets, h->L, h->Sp, h->bskip_sum);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->fwd_valid = false;
+  return WN_OK;
+}
+
+// ============================================================================ GEMM dispatch
+struct SegH { const void* A; int lda; int shift; int K; };
+struct GemmH {
+  int B, T, N;
+  int nseg; SegH seg[WN_MAX_SEG];
+  int n_outer = 1; long long outer_stride = 0;
+  const float* W32 = nullptr; int Npad = 0;     // fp32: [ktot][Npad]
+  const bf16* W16 = nullptr; int ktot16 = 0; int N16 = 0; int tile16 = 0;  // bf16: [N16][ktot16]
+};
+
+template <class T, class Epi>
+static int run_conv_gemm(wn_handle* h, cudaStream_t st, int cls, const GemmH& g, const typename Epi::Params& ep) {
+  LaunchScope ls(h, st, cls);
+  if constexpr (sizeof(T) == 4) {
+    ConvGemmArgsF a;
+    a.B = g.B; a.T = g.T; a.Npad = g.Npad; a.nseg = g.nseg; a.n_outer = g.n_outer; a.a_outer_stride = g.outer_stride; a.W = g.W32;
+    for (int s = 0; s < g.nseg; ++s) a.seg[s] = SegF{(const float*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
+    dim3 grid(g.B * cdiv(g.T, 64), g.Npad / 64);
+    conv_gemm_simt<Epi><<<grid, 256, 0, st>>>(a, ep);
+    return WN_OK;
+  } else {
+    TcGemmDesc d;
+    d.B = g.B; d.T = g.T; d.nseg = g.nseg; d.n_outer = g.n_outer; d.outer_stride = g.outer_stride;
+    for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
+    d.W = g.W16; d.ktot = g.ktot16; d.N16 = g.N16; d.tileN = g.tile16;
+    int r = tc_conv_gemm<Epi>(h->tmaps, st, d, ep);
+    if (r != 0) { set_err("tcgen05 conv_gemm launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+    return WN_OK;
+  }
+}
+
+struct WgradH {
+  int B, T, N; const void* G; int ldg;
+  int nseg; SegH seg[WN_MAX_SEG];
+  float* dst;          // [ktot][N] Keras layout in the flat grad buffer
+  const float* w; float l2coef;  // optional L2 term: dst += l2coef * w
+};
+
+template <class T>
+static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
+  int ktot = 0;
+  for (int s = 0; s < g.nseg; ++s) ktot += g.seg[s].K;
+  int nsplit = 1;
+  if constexpr (sizeof(T) == 4) {
+    int ktiles = 0;
+    for (int s = 0; s < g.nseg; ++s) ktiles += cdiv(g.seg[s].K, 64);
+    const int ntiles = cdiv(g.N, 64);
+    const int chunks = g.B * cdiv(g.T, 16);
+    nsplit = 296 * 2 / (ktiles * ntiles);
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > WN_MAX_WGRAD_SPLITS) nsplit = WN_MAX_WGRAD_SPLITS;
+    if (nsplit > chunks) nsplit = chunks;
+    const int cps = cdiv(chunks, nsplit);
+    nsplit = cdiv(chunks, cps);
+    WgradArgsF a;
+    a.B = g.B; a.T = g.T; a.N = g.N; a.G = (const float*)g.G; a.ldg = g.ldg; a.nseg = g.nseg; a.ktot = ktot;
+    for (int s = 0; s < g.nseg; ++s) a.seg[s] = SegF{(const float*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
+    a.partial = h->wg_partial; a.chunks_per_split = cps;
+    {
+      LaunchScope ls(h, st, cls);
+      wgrad_simt<<<dim3(ktiles, ntiles, nsplit), 256, 0, st>>>(a);
+    }
+  } else {
+    TcWgradDesc d;
+    d.B = g.B; d.T = g.T; d.N = g.N; d.G = (const bf16*)g.G; d.ldg = g.ldg; d.nseg = g.nseg; d.ktot = ktot;
+    for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
+    d.partial = h->wg_partial;
+    LaunchScope ls(h, st, cls);
+    int r = tc_wgrad(h->tmaps, st, d, &nsplit);
+    if (r != 0) { set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+  }
+  {
+    LaunchScope ls(h, st, cls);
+    const long long n = (long long)ktot * g.N;
+    reduce_parts<<<cdiv(n, 256), 256, 0, st>>>(h->wg_partial, nsplit, n, g.dst, n, g.l2coef != 0.f ? g.w : nullptr, g.l2coef);
+  }
+  return WN_OK;
+}
+
+// column sums of G (B,T,N) -> total[N] and/or per_batch[B][ldpb]
+template <class T>
+static void run_colsum(wn_handle* h, cudaStream_t st, const void* G, int ldg, int B, int Tn, int N, float* per_batch, int ldpb, float* total) {
+  const int chunks = cdiv(Tn, 256);
+  {
+    LaunchScope ls(h, st, CLS_MISC);
+    colsum_stage1<T><<<dim3(cdiv(N, 128), chunks, B), 128, 0, st>>>((const T*)G, ldg, h->colpart, Tn, N, 256);
+  }
+  {
+    LaunchScope ls(h, st, CLS_MISC);
+    colsum_stage2<<<cdiv(N, 128), 128, 0, st>>>(h->colpart, B, chunks, N, per_batch, ldpb, total);
+  }
+}
+
+// ============================================================================ forward pieces
+static inline float* P_(wn_handle* h, int idx) { return h->d_params + h->params[idx].offset; }
+static inline float* G_(wn_handle* h, int idx) { return h->d_grads + h->params[idx].offset; }
+
+template <class T> static inline bool vec_ok(int ld) { return (ld * (int)sizeof(T)) % 16 == 0; }
+
+static void fill_w(GemmH& g, const ConvP& c, bool dgrad) {
+  if (!dgrad) { g.W32 = c.Wf; g.Npad = c.Npad; g.W16 = c.Wf16; g.ktot16 = c.Kf16; g.N16 = c.N16; g.tile16 = c.tileN16; }
+  else { g.W32 = c.Wb; g.Npad = c.Cpad; g.W16 = c.Wb16; g.ktot16 = rup(c.Kb16, 64); g.N16 = c.C16; g.tile16 = 0; }
+}
+
+// conditioning: mapping MLP (model.py:141-148,222) and the per-block time-constant bias
+// cb[l][b][:] = cond[b] @ Wc_l + bc_l  (layers.py:203-204 with cond constant in time)
+static int cond_forward(wn_handle* h, cudaStream_t st, const float* cond_in, int B, bool run_mapping, const float** cond_out) {
+  const float* cur = cond_in;
+  int width = h->cfg.cond_in;
+  if (run_mapping) {
+    for (size_t i = 0; i < h->map_w.size(); ++i) {
+      LaunchScope ls(h, st, CLS_MISC);
+      const int n = h->map_width[i];
+      dense_small_fwd<<<cdiv(B * n, 128), 128, 0, st>>>(cur, width, P_(h, h->map_w[i]), P_(h, h->map_b[i]), h->cond_act[i], n, B, width, n,
+                                                      h->cfg.mapping_activation);
+      cur = h->cond_act[i];
+      width = n;
+    }
+  }
+  *cond_out = cur;
+  return WN_OK;
+}
+static void cond_bias_block(wn_handle* h, cudaStream_t st, int l, const float* cond, int B) {
+  const BlockP& b = h->blocks[l];
+  LaunchScope ls(h, st, CLS_MISC);
+  const int n = 2 * h->D;
+  dense_small_fwd<<<cdiv(B * n, 128), 128, 0, st>>>(cond, h->Cc, P_(h, b.cw_idx), P_(h, b.cb_idx), h->cb + (size_t)l * h->maxB * n, n, B, h->Cc, n,
+                                                  ACT_LINEAR);
+}
+
+// WaveNetLayer.call for block l (layers.py:178-224); x_in (B,T,R) in T
+template <class T>
+static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in, bool has_cb, int B, int Tn) {
+  BlockP& b = h->blocks[l];
+  const int depth = (int)b.stack.size();
+  const size_t rows_cap = (size_t)h->maxB * h->maxT;
+  const void* cur = x_in;
+  int curw = h->R;
+  for (int j = 0; j < depth; ++j) {
+    const ConvP& c = b.stack[j];
+    GemmH g;
+    g.B = B; g.T = Tn; g.N = c.cout; g.nseg = c.K;
+    for (int k = 0; k < c.K; ++k) g.seg[k] = SegH{cur, curw, -(c.K - 1 - k) * c.dil, c.cin};
+    fill_w(g, c, false);
+    if (j < depth - 1) {
+      typename EpiBiasActRes<T, T, sizeof(T) == 2>::Params ep{};
+      ep.out = (T*)h->acts[l][j]; ep.ldo = h->D; ep.bias = P_(h, c.b_idx); ep.cbias = nullptr; ep.ldcb = 0;
+      ep.act = h->cfg.activation; ep.res = nullptr; ep.ldr = 0; ep.N = c.cout; ep.vec = vec_ok<T>(h->D);
+      RET((run_conv_gemm<T, EpiBiasActRes<T, T, sizeof(T) == 2>>(h, st, CLS_DILATED, g, ep)));
+      cur = h->acts[l][j];
+      curw = h->D;
+    } else {
+      typename EpiGate<T, sizeof(T) == 2>::Params ep{};
+      ep.z = (T*)h->zbuf[l];
+      ep.g = (T*)h->G_all + (size_t)l * rows_cap * h->D;
+      ep.ldg = h->D; ep.bias = P_(h, c.b_idx);
+      ep.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
+      ep.D = h->D; ep.vec = vec_ok<T>(h->D);
+      RET((run_conv_gemm<T, EpiGate<T, sizeof(T) == 2>>(h, st, CLS_DILATED, g, ep)));
+    }
+  }
+  // conv1 (+ residual)
+  {
+    const ConvP& c = b.conv1;
+    GemmH g;
+    g.B = B; g.T = Tn; g.N = h->R; g.nseg = 1;
+    g.seg[0] = SegH{(const T*)h->G_all + (size_t)l * rows_cap * h->D, h->D, 0, h->D};
+    fill_w(g, c, false);
+    typename EpiBiasActRes<T, T, sizeof(T) == 2>::Params ep{};
+    ep.out = (T*)h->xout[l]; ep.ldo = h->R; ep.bias = P_(h, c.b_idx); ep.act = ACT_LINEAR;
+    ep.res = h->cfg.use_residual ? (const T*)x_in : nullptr; ep.ldr = h->R; ep.N = h->R; ep.vec = vec_ok<T>(h->R);
+    RET((run_conv_gemm<T, EpiBiasActRes<T, T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
+  }
+  return WN_OK;
+}
+
+// skip of blocks [l0, l0+nl): out = sum_l g_l @ Ws_l + sum_l bs_l  (model.py:236; Ws := Wr when aliased)
+template <class T, class TO>
+static int skip_gemm(wn_handle* h, cudaStream_t st, int l0, int nl, TO* out, int ldo, const float* bias, int B, int Tn) {
+  const size_t rows_cap = (size_t)h->maxB * h->maxT;
+  GemmH g;
+  g.B = B; g.T = Tn; g.N = h->Sp; g.nseg = 1;
+  g.seg[0] = SegH{(const T*)h->G_all + (size_t)l0 * rows_cap * h->D, h->D, 0, h->D};
+  g.n_outer = nl; g.outer_stride = (long long)rows_cap * h->D;
+  g.W32 = h->Wskip ? h->Wskip + (size_t)l0 * h->D * h->Spad : nullptr; g.Npad = h->Spad;
+  g.W16 = h->Wskip16 ? h->Wskip16 + (size_t)l0 * h->D : nullptr; g.ktot16 = h->L * h->D; g.N16 = h->Spad; g.tile16 = 0;
+  typename EpiBiasActRes<T, TO, sizeof(T) == 2>::Params ep{};
+  ep.out = out; ep.ldo = ldo; ep.bias = bias; ep.act = ACT_LINEAR; ep.N = h->Sp; ep.vec = vec_ok<TO>(ldo);
+  return run_conv_gemm<T, EpiBiasActRes<T, TO, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep);
+}
+
+// WaveNet.call up to the logits (model.py:213-239).  x (B,T) fp32 with row stride ldx.
+template <class T>
+static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx, const float* cond_in, int B, int Tn) {
+  const wn_config& c = h->cfg;
+  const float* cond = nullptr;
+  if (c.conditioning) {
+    RET(cond_forward(h, st, cond_in, B, true, &cond));
+    for (int l = 0; l < h->L; ++l) cond_bias_block(h, st, l, cond, B);
+  }
+  h->last_cond = cond;
+  {
+    LaunchScope ls(h, st, CLS_MISC);
+    const long long total = (long long)B * Tn * h->R;
+    input_conv_fwd<T><<<cdiv(total, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
+  }
+  const void* cur = h->h0;
+  for (int l = 0; l < h->L; ++l) {
+    RET(block_forward<T>(h, st, l, cur, c.conditioning != 0, B, Tn));
+    cur = h->xout[l];
+  }
+  const void* head_in = cur;
+  int head_w = h->R;
+  if (c.use_skip) {
+    RET((skip_gemm<T, T>(h, st, 0, h->L, (T*)h->skipsum, h->Sp, h->bskip_sum, B, Tn)));
+    head_in = h->skipsum;
+    head_w = h->Sp;
+  }
+  for (size_t i = 0; i < h->head.size(); ++i) {
+    const ConvP& hc = h->head[i];
+    const bool last = i + 1 == h->head.size();
+    GemmH g;
+    g.B = B; g.T = Tn; g.N = hc.cout; g.nseg = 1;
+    g.seg[0] = SegH{head_in, head_w, 0, hc.cin};
+    fill_w(g, hc, false);
+    if (!last) {
+      typename EpiBiasActRes<T, T, sizeof(T) == 2>::Params ep{};
+      ep.out = (T*)h->hact[i]; ep.ldo = hc.cout; ep.bias = P_(h, hc.b_idx); ep.act = c.activation; ep.N = hc.cout; ep.vec = vec_ok<T>(hc.cout);
+      RET((run_conv_gemm<T, EpiBiasActRes<T, T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
+      head_in = h->hact[i];
+      head_w = hc.cout;
+    } else {
+      typename EpiBiasActRes<T, float, sizeof(T) == 2>::Params ep{};
+      ep.out = h->logits; ep.ldo = h->ldl; ep.bias = P_(h, hc.b_idx); ep.act = ACT_LINEAR; ep.N = hc.cout; ep.vec = vec_ok<float>(h->ldl);
+      RET((run_conv_gemm<T, EpiBiasActRes<T, float, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
+    }
+  }
+  return WN_OK;
+}
+
+// loss (model.py:505-551) on the logits; optionally dlogits and probabilities
+template <class T>
+static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int B, int Tn, float scale, bool want_grad, float* probs, float* loss_out) {
+  const wn_config& c = h->cfg;
+  const long long rows = (long long)B * Tn;
+  int nparts;
+  {
+    LaunchScope ls(h, st, CLS_LOSS);
+    if (c.sampling_function == WN_CATEGORICAL) {
+      nparts = cdiv(rows, 8);
+      softmax_ce_kernel<T><<<nparts, 256, 0, st>>>(h->logits, h->Cout, frames, Tn, rows, c.bits, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
+                                                  probs, loss_out ? h->loss_partial : nullptr);
+    } else {
+      nparts = cdiv(rows, 128);
+      mixture_loss_kernel<T><<<nparts, 128, 0, st>>>(h->logits, h->ldl, c.num_mixtures, frames, Tn, rows, c.bits,
+                                                    c.sampling_function == WN_GAUSSIAN ? 2 : 1, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
+                                                    loss_out ? h->loss_partial : nullptr);
+    }
+  }
+  if (loss_out) {
+    float l2coef = 0.f;
+    if (c.l2_reg_factor > 0.f) {
+      // model.py:331-334: reg * sum(kernel^2), scaled by 1/replicas (folded into `scale`*B)
+      cudaMemsetAsync(h->l2_sum, 0, 4, st);
+      for (auto& p : h->params) {
+        if (p.name.size() < 6 || p.name.compare(p.name.size() - 6, 6, "kernel") != 0) continue;
+        LaunchScope ls(h, st, CLS_MISC);
+        sumsq_accum<<<1, 1024, 0, st>>>(h->d_params + p.offset, p.count, h->l2_sum);
+      }
+      l2coef = c.l2_reg_factor * scale * (float)B;   // reg / n_replicas
+    }
+    LaunchScope ls(h, st, CLS_LOSS);
+    loss_finalize<<<1, 1024, 0, st>>>(h->loss_partial, nparts, scale, l2coef != 0.f ? h->l2_sum : nullptr, l2coef, loss_out);
+  }
+  return WN_OK;
+}
+
+// ============================================================================ backward pieces
+// adjoint of block_forward.  dxout / dskip may be null (zero).  Writes dx_in (if non-null) and
+// this block's parameter gradients.  dcb row l gets per-batch sums of dz when conditioned.
+template <class T>
+static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in, const void* dxout, const void* dskip, void* dx_in, int B, int Tn,
+                          float l2coef) {
+  BlockP& b = h->blocks[l];
+  const int depth = (int)b.stack.size();
+  const size_t rows_cap = (size_t)h->maxB * h->maxT;
+  const long long nR = (long long)B * Tn * h->R;
+  const T* g_l = (const T*)h->G_all + (size_t)l * rows_cap * h->D;
+  const int R = h->R, D = h->D, S = h->S;
+  // ---- d o  (gradient wrt conv1 output)
+  const void* d_o = dxout;
+  if (h->alias_skip) {
+    if (dxout && dskip) {
+      LaunchScope ls(h, st, CLS_MISC);
+      add2_kernel<T><<<cdiv(nR, 256), 256, 0, st>>>((const T*)dxout, (const T*)dskip, (T*)h->dotmp, nR);
+      d_o = h->dotmp;
+    } else if (dskip) {
+      d_o = dskip;
+    }
+  }
+  // ---- conv1 / conv_skip weight + bias grads
+  if (d_o) {
+    WgradH w{};
+    w.B = B; w.T = Tn; w.N = R; w.G = d_o; w.ldg = R; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
+    w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef;
+    RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+    run_colsum<T>(h, st, d_o, R, B, Tn, R, nullptr, 0, G_(h, b.conv1.b_idx));
+  } else {
+    cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
+    cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
+  }
+  if (b.has_skip) {
+    if (dskip) {
+      WgradH w{};
+      w.B = B; w.T = Tn; w.N = S; w.G = dskip; w.ldg = S; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
+      w.dst = G_(h, b.conv_skip.w_idx); w.w = P_(h, b.conv_skip.w_idx); w.l2coef = l2coef;
+      RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+      run_colsum<T>(h, st, dskip, S, B, Tn, S, nullptr, 0, G_(h, b.conv_skip.b_idx));
+    } else {
+      cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
+      cudaMemsetAsync(G_(h, b.conv_skip.b_idx), 0, h->params[b.conv_skip.b_idx].count * 4, st);
+    }
+  }
+  // ---- dz = gate'(z) * (d_o Wr^T + dskip Ws^T)
+  {
+    GemmH g;
+    g.B = B; g.T = Tn; g.N = D; g.nseg = 0;
+    int koff = 0;
+    const bool use_o = d_o != nullptr;
+    const bool use_s = b.has_skip && dskip != nullptr;
+    if (!use_o && !use_s) { set_err("block_backward: no upstream gradient"); return WN_ERR_STATE; }
+    if (use_o) g.seg[g.nseg++] = SegH{d_o, R, 0, R};
+    else koff = R;
+    if (use_s) g.seg[g.nseg++] = SegH{dskip, S, 0, S};
+    const int rs = R + (b.has_skip ? S : 0);
+    g.W32 = b.Wdg ? b.Wdg + (size_t)koff * b.Dpad : nullptr; g.Npad = b.Dpad;
+    g.W16 = b.Wdg16 ? b.Wdg16 + koff : nullptr; g.ktot16 = rup(rs, 64); g.N16 = b.Dpad; g.tile16 = 0;
+    typename EpiGateBwd<T, sizeof(T) == 2>::Params ep{};
+    ep.z = (const T*)h->zbuf[l]; ep.dz = (T*)h->dz; ep.D = D; ep.vec = vec_ok<T>(D);
+    RET((run_conv_gemm<T, EpiGateBwd<T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
+  }
+  // ---- walk the dilated stack downwards
+  const void* dcur = h->dz;
+  int dcw = 2 * D;
+  for (int j = depth - 1; j >= 0; --j) {
+    const ConvP& c = b.stack[j];
+    const void* a_in = j == 0 ? x_in : h->acts[l][j - 1];
+    const int a_w = j == 0 ? R : D;
+    // bias grad (+ conditioning per-batch sums for the gated conv)
+    if (j == depth - 1 && b.has_cond) {
+      run_colsum<T>(h, st, dcur, dcw, B, Tn, c.cout, h->dcb + (size_t)l * h->maxB * 2 * D, 2 * D, G_(h, c.b_idx));
+    } else {
+      run_colsum<T>(h, st, dcur, dcw, B, Tn, c.cout, nullptr, 0, G_(h, c.b_idx));
+    }
+    // weight grad: rows (k, cin) <- taps of a_in shifted by -(K-1-k)*d
+    {
+      WgradH w{};
+      w.B = B; w.T = Tn; w.N = c.cout; w.G = dcur; w.ldg = dcw; w.nseg = c.K;
+      for (int k = 0; k < c.K; ++k) w.seg[k] = SegH{a_in, a_w, -(c.K - 1 - k) * c.dil, c.cin};
+      w.dst = G_(h, c.w_idx); w.w = P_(h, c.w_idx); w.l2coef = l2coef;
+      RET(run_wgrad<T>(h, st, CLS_DILATED, w));
+    }
+    // dgrad
+    const bool need = j > 0 || dx_in != nullptr;
+    if (need) {
+      GemmH g;
+      g.B = B; g.T = Tn; g.N = c.cin; g.nseg = c.K;
+      for (int k = 0; k < c.K; ++k) g.seg[k] = SegH{dcur, dcw, +(c.K - 1 - k) * c.dil, c.cout};
+      fill_w(g, c, true);
+      typename EpiActBwd<T, T>::Params ep{};
+      ep.N = c.cin;
+      if (j > 0) {
+        void* dst = (dcur == h->dpA) ? h->dpB : h->dpA;
+        ep.out = (T*)dst; ep.ldo = D; ep.add = nullptr; ep.y = (const T*)h->acts[l][j - 1]; ep.ldy = D; ep.act = h->cfg.activation;
+        ep.vec = vec_ok<T>(D);
+        RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
+        dcur = dst;
+        dcw = D;
+      } else {
+        ep.out = (T*)dx_in; ep.ldo = R;
+        ep.add = (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr; ep.lda = R;
+        ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(R);
+        RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
+      }
+    }
+  }
+  return WN_OK;
+}
+
+// conditioning adjoint: dWc_l, dbc_l from dcb; dcond = sum_l dcb_l Wc_l^T; then the mapping MLP
+static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, const float* cond, int B, int l0, int nl, bool run_mapping, float* dcond_out,
+                         float l2coef) {
+  const int n = 2 * h->D;
+  for (int l = l0; l < l0 + nl; ++l) {
+    const BlockP& b = h->blocks[l];
+    const float* d = h->dcb + (size_t)l * h->maxB * n;
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      dense_small_wgrad<<<cdiv((h->Cc + 1) * n, 128), 128, 0, st>>>(cond, h->Cc, d, n, G_(h, b.cw_idx), G_(h, b.cb_idx), B, h->Cc, n);
+    }
+    if (l2coef != 0.f) {
+      LaunchScope ls(h, st, CLS_MISC);
+      const long long cnt = h->params[b.cw_idx].count;
+      reduce_parts<<<cdiv(cnt, 256), 256, 0, st>>>(G_(h, b.cw_idx), 1, 0, G_(h, b.cw_idx), cnt, P_(h, b.cw_idx), l2coef);
+    }
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      dense_small_dgrad<<<cdiv(B * h->Cc, 128), 128, 0, st>>>(d, n, P_(h, b.cw_idx), dcond_out, h->Cc, B, h->Cc, n, l != l0);
+    }
+  }
+  if (!run_mapping) return WN_OK;
+  float* dcur = dcond_out;
+  for (int i = (int)h->map_w.size() - 1; i >= 0; --i) {
+    const int nn = h->map_width[i];
+    const int kin = i > 0 ? h->map_width[i - 1] : h->cfg.cond_in;
+    const float* inp = i > 0 ? h->cond_act[i - 1] : cond_in;
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      dense_small_actgrad<<<cdiv(B * nn, 128), 128, 0, st>>>(dcur, h->cond_act[i], B * nn, h->cfg.mapping_activation);
+    }
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      dense_small_wgrad<<<cdiv((kin + 1) * nn, 128), 128, 0, st>>>(inp, kin, dcur, nn, G_(h, h->map_w[i]), G_(h, h->map_b[i]), B, kin, nn);
+    }
+    if (l2coef != 0.f) {
+      LaunchScope ls(h, st, CLS_MISC);
+      const long long cnt = h->params[h->map_w[i]].count;
+      reduce_parts<<<cdiv(cnt, 256), 256, 0, st>>>(G_(h, h->map_w[i]), 1, 0, G_(h, h->map_w[i]), cnt, P_(h, h->map_w[i]), l2coef);
+    }
+    if (i > 0) {
+      float* dn = (dcur == h->cond_dact) ? h->cond_dact2 : h->cond_dact;
+      LaunchScope ls(h, st, CLS_MISC);
+      dense_small_dgrad<<<cdiv(B * kin, 128), 128, 0, st>>>(dcur, nn, P_(h, h->map_w[i]), dn, kin, B, kin, nn, 0);
+      dcur = dn;
+    }
+  }
+  return WN_OK;
+}
+
+template <class T>
+static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx, const float* cond_in, int B, int Tn, float l2coef) {
+  const wn_config& c = h->cfg;
+  // ---- head
+  const void* dcur = h->dlogits;
+  int dw = h->ldd;
+  for (int i = (int)h->head.size() - 1; i >= 0; --i) {
+    const ConvP& hc = h->head[i];
+    const void* a_in;
+    int a_w;
+    if (i > 0) { a_in = h->hact[i - 1]; a_w = h->head[i - 1].cout; }
+    else if (c.use_skip) { a_in = h->skipsum; a_w = h->Sp; }
+    else { a_in = h->xout[h->L - 1]; a_w = h->R; }
+    run_colsum<T>(h, st, dcur, dw, B, Tn, hc.cout, nullptr, 0, G_(h, hc.b_idx));
+    WgradH w{};
+    w.B = B; w.T = Tn; w.N = hc.cout; w.G = dcur; w.ldg = dw; w.nseg = 1; w.seg[0] = SegH{a_in, a_w, 0, hc.cin};
+    w.dst = G_(h, hc.w_idx); w.w = P_(h, hc.w_idx); w.l2coef = l2coef;
+    RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+    GemmH g;
+    g.B = B; g.T = Tn; g.N = hc.cin; g.nseg = 1;
+    g.seg[0] = SegH{dcur, dw, 0, (sizeof(T) == 2 && i + 1 == (int)h->head.size()) ? h->ldd : hc.cout};
+    fill_w(g, hc, true);
+    typename EpiActBwd<T, T>::Params ep{};
+    ep.N = hc.cin; ep.add = nullptr;
+    void* dst;
+    if (i > 0) {
+      dst = (dcur == h->dhA) ? h->dhB : h->dhA;
+      ep.out = (T*)dst; ep.ldo = hc.cin; ep.y = (const T*)h->hact[i - 1]; ep.ldy = hc.cin; ep.act = c.activation; ep.vec = vec_ok<T>(hc.cin);
+    } else {
+      dst = c.use_skip ? h->dskip : h->dxA;
+      ep.out = (T*)dst; ep.ldo = hc.cin; ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(hc.cin);
+    }
+    RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_GEMM, g, ep)));
+    dcur = dst;
+    dw = hc.cin;
+  }
+  // ---- blocks
+  const void* dskip = c.use_skip ? h->dskip : nullptr;
+  const void* dxout = c.use_skip ? nullptr : h->dxA;
+  for (int l = h->L - 1; l >= 0; --l) {
+    const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
+    void* dx_in = (dxout == h->dxA) ? h->dxB : h->dxA;
+    RET(block_backward<T>(h, st, l, x_in, dxout, dskip, dx_in, B, Tn, l2coef));
+    dxout = dx_in;
+  }
+  // ---- input conv (model.py:84-88): dW[k][c], db[c]
+  {
+    const int chunks = cdiv(Tn, 256);
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, h->colpart, B, Tn, h->R, h->K, 256);
+    }
+    const long long kr = (long long)h->K * h->R;
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      reduce_parts<<<cdiv(kr, 128), 128, 0, st>>>(h->colpart, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
+                                               l2coef != 0.f ? P_(h, h->input_conv.w_idx) : nullptr, l2coef);
+    }
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      reduce_parts<<<cdiv(h->R, 128), 128, 0, st>>>(h->colpart + kr, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
+    }
+  }
+  if (c.conditioning) RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef));
+  return WN_OK;
+}
+
+// ============================================================================ public entry points
+static int check_bt(wn_handle* h, int B, int T) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if (B < 1 || T < 1 || B > h->maxB || T > h->maxT) {
+    set_err("batch/time (%d,%d) outside the workspace built for (%d,%d)", B, T, h->maxB, h->maxT);
+    return WN_ERR_VALUE;
+  }
+  return WN_OK;
+}
+
+extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void* stream) {
+  if (!x_dev || !idx_dev || n < 0 || bits < 1 || bits > 16) { set_err("bad quantize arguments"); return WN_ERR_VALUE; }
+  if (n == 0) return WN_OK;
+  quantize_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, (long long*)idx_dev, n, bits);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+
+template <class T>
+static int forward_entry(wn_handle* h, const float* x, const float* cond, int B, int Tn, float* out, cudaStream_t st) {
+  RET(model_forward<T>(h, st, x, Tn, cond, B, Tn));
+  if (h->cfg.sampling_function == WN_CATEGORICAL) {
+    RET(loss_forward<T>(h, st, nullptr, B, Tn, 0.f, false, out, nullptr));
+  } else {
+    CK(cudaMemcpyAsync(out, h->logits, (size_t)B * Tn * h->Cout * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return WN_OK;
+}
+
+extern "C" int wn_forward(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, float* out_dev, void* stream) {
+  RET(check_bt(h, B, T));
+  if (!h->cfg.has_head || !h->cfg.has_input_conv) { set_err("wn_forward needs a full model handle"); return WN_ERR_STATE; }
+  if (h->cfg.conditioning && !cond_dev) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = h->cfg.precision == WN_BF16 ? forward_entry<bf16>(h, x_dev, cond_dev, B, T, out_dev, st) : forward_entry<float>(h, x_dev, cond_dev, B, T, out_dev, st);
+  RET(r);
+  CK(cudaGetLastError());
+  h->fwd_valid = false;
+  return WN_OK;
+}
+
+template <class T>
+static int step_entry(wn_handle* h, const float* frames, const float* cond, int B, int Tn, int nrep, float* loss, cudaStream_t st, bool train) {
+  const float scale = 1.0f / ((float)B * (float)nrep);
+  RET(model_forward<T>(h, st, frames, Tn + 1, cond, B, Tn));
+  RET(loss_forward<T>(h, st, frames, B, Tn, scale, train, nullptr, loss));
+  if (train) {
+    const float l2coef = h->cfg.l2_reg_factor > 0.f ? 2.0f * h->cfg.l2_reg_factor / (float)nrep : 0.f;
+    RET(model_backward<T>(h, st, frames, Tn + 1, cond, B, Tn, l2coef));
+  }
+  return WN_OK;
+}
+
+static int step_common(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T, int n_replicas, float* loss_dev, void* stream, bool train) {
+  RET(check_bt(h, B, T));
+  if (!h->cfg.has_head || !h->cfg.has_input_conv) { set_err("train/test step needs a full model handle"); return WN_ERR_STATE; }
+  if (h->cfg.conditioning && !cond_dev) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
+  if (n_replicas < 1 || !frames_dev || !loss_dev) { set_err("bad step arguments"); return WN_ERR_VALUE; }
+  if (train && h->cfg.dropout > 0.f) { set_err("training with dropout>0 is not built yet (TF RNG stream is not reproducible; use dropout=0)"); return WN_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = h->cfg.precision == WN_BF16 ? step_entry<bf16>(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, st, train)
+                                      : step_entry<float>(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, st, train);
+  RET(r);
+  CK(cudaGetLastError());
+  h->lastB = B; h->lastT = T;
+  return WN_OK;
+}
+
+extern "C" int wn_train_step(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T, int n_replicas, float* loss_dev, void* stream) {
+  return step_common(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, stream, true);
+}
+extern "C" int wn_test_step(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T, int n_replicas, float* loss_dev, void* stream) {
+  return step_common(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, stream, false);
+}
+
+extern "C" int wn_train_step_host(wn_handle* h, const float* frames_host, const float* cond_host, int B, int T, int n_replicas, float* loss_host) {
+  RET(check_bt(h, B, T));
+  if (!frames_host || !loss_host) { set_err("bad step arguments"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->own_stream;
+  const size_t fb = (size_t)B * (T + 1) * 4;
+  memcpy(h->pin_frames, frames_host, fb);
+  CK(cudaMemcpyAsync(h->d_frames, h->pin_frames, fb, cudaMemcpyHostToDevice, st));
+  const float* dc = nullptr;
+  if (h->cfg.conditioning) {
+    if (!cond_host) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
+    const size_t cbz = (size_t)B * h->cfg.cond_in * 4;
+    memcpy(h->pin_cond, cond_host, cbz);
+    CK(cudaMemcpyAsync(h->d_cond_in, h->pin_cond, cbz, cudaMemcpyHostToDevice, st));
+    dc = h->d_cond_in;
+  }
+  RET(step_common(h, h->d_frames, dc, B, T, n_replicas, h->d_loss, st, true));
+  CK(cudaMemcpyAsync(h->pin_loss, h->d_loss, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *loss_host = h->pin_loss[0];
+  return WN_OK;
+}
+
+// ---------------------------------------------------------------- layer-level API
+template <class T>
+static int layer_fwd_entry(wn_handle* h, int l, const float* x, const float* cond, int B, int Tn, float* x_out, float* skip, cudaStream_t st) {
+  const long long nR = (long long)B * Tn * h->R;
+  const void* xin;
+  // keep a private copy of the block input (needed by the backward pass)
+  void* slot = l == 0 ? h->layer_in : h->xout[l - 1];
+  if (l > 0 && h->L > 1) {
+    // blocks of a bare stack are chained by the caller; input of block l lives in xout[l-1]
+  }
+  {
+    LaunchScope ls(h, st, CLS_MISC);
+    convert_kernel<float, T><<<cdiv(nR, 256), 256, 0, st>>>(x, (T*)slot, nR);
+  }
+  xin = slot;
+  bool has_cb = false;
+  if (h->blocks[l].has_cond) {
+    if (!cond) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
+    h->last_cond = cond;
+    cond_bias_block(h, st, l, cond, B);
+    has_cb = true;
+  }
+  RET(block_forward<T>(h, st, l, xin, has_cb, B, Tn));
+  {
+    LaunchScope ls(h, st, CLS_MISC);
+    convert_kernel<T, float><<<cdiv(nR, 256), 256, 0, st>>>((const T*)h->xout[l], x_out, nR);
+  }
+  if (skip) {
+    const BlockP& b = h->blocks[l];
+    RET((skip_gemm<T, float>(h, st, l, 1, skip, h->Sp, P_(h, b.has_skip ? b.conv_skip.b_idx : b.conv1.b_idx), B, Tn)));
+  }
+  return WN_OK;
+}
+
+extern "C" int wn_layer_forward(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T, float* x_out_dev, float* skip_dev,
+                                void* stream) {
+  RET(check_bt(h, B, T));
+  if (block < 0 || block >= h->L || !x_dev || !x_out_dev) { set_err("bad layer arguments"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = h->cfg.precision == WN_BF16 ? layer_fwd_entry<bf16>(h, block, x_dev, cond_dev, B, T, x_out_dev, skip_dev, st)
+                                      : layer_fwd_entry<float>(h, block, x_dev, cond_dev, B, T, x_out_dev, skip_dev, st);
+  RET(r);
+  CK(cudaGetLastError());
+  h->lastB = B; h->lastT = T;
+  h->layer_fwd_valid[block] = true;
+  return WN_OK;
+}
+
+template <class T>
+static int layer_bwd_entry(wn_handle* h, int l, const float* dxo, const float* dsk, float* dx, float* dcond, cudaStream_t st) {
+  const int B = h->lastB, Tn = h->lastT;
+  const long long nR = (long long)B * Tn * h->R, nS = (long long)B * Tn * h->Sp;
+  const void *dxo_t = nullptr, *dsk_t = nullptr;
+  if (dxo) {
+    LaunchScope ls(h, st, CLS_MISC);
+    convert_kernel<float, T><<<cdiv(nR, 256), 256, 0, st>>>(dxo, (T*)h->dxA, nR);
+    dxo_t = h->dxA;
+  }
+  if (dsk) {
+    LaunchScope ls(h, st, CLS_MISC);
+    convert_kernel<float, T><<<cdiv(nS, 256), 256, 0, st>>>(dsk, (T*)h->dskip, nS);
+    dsk_t = h->dskip;
+  }
+  const void* xin = l == 0 ? h->layer_in : h->xout[l - 1];
+  RET(block_backward<T>(h, st, l, xin, dxo_t, dsk_t, dx ? h->dxB : nullptr, B, Tn, 0.f));
+  if (dx) {
+    LaunchScope ls(h, st, CLS_MISC);
+    convert_kernel<T, float><<<cdiv(nR, 256), 256, 0, st>>>((const T*)h->dxB, dx, nR);
+  }
+  if (h->blocks[l].has_cond) {
+    RET(cond_backward(h, st, nullptr, h->last_cond, B, l, 1, false, h->dcond, 0.f));
+    if (dcond) CK(cudaMemcpyAsync(dcond, h->dcond, (size_t)B * h->Cc * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return WN_OK;
+}
+
+extern "C" int wn_layer_backward(wn_handle* h, int block, const float* dx_out_dev, const float* dskip_dev, float* dx_dev, float* dcond_dev, void* stream) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if (block < 0 || block >= h->L) { set_err("bad block index"); return WN_ERR_VALUE; }
+  if (!h->layer_fwd_valid[block]) { set_err("wn_layer_backward before wn_layer_forward"); return WN_ERR_STATE; }
+  if (!dx_out_dev && !dskip_dev) { set_err("need at least one upstream gradient"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = h->cfg.precision == WN_BF16 ? layer_bwd_entry<bf16>(h, block, dx_out_dev, dskip_dev, dx_dev, dcond_dev, st)
+                                      : layer_bwd_entry<float>(h, block, dx_out_dev, dskip_dev, dx_dev, dcond_dev, st);
+  RET(r);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+
+// ---------------------------------------------------------------- introspection
+extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
+extern "C" int wn_profile_begin(wn_handle* h, int tag) {
+  if (!h) return WN_ERR_VALUE;
+  h->prof_tag = tag; h->prof_used = 0; h->prof_launches = 0;
+  return WN_OK;
+}
+extern "C" int wn_profile_end(wn_handle* h, double* ms, int64_t* launches) {
+  if (!h) return WN_ERR_VALUE;
+  CK(cudaDeviceSynchronize());
+  double tot = 0;
+  for (size_t i = 0; i < h->prof_used; ++i) {
+    float t = 0;
+    cudaEventElapsedTime(&t, h->prof_events[i].first, h->prof_events[i].second);
+    tot += t;
+  }
+  if (ms) *ms = tot;
+  if (launches) *launches = h->prof_launches;
+  h->prof_tag = 0; h->prof_used = 0;
+  return WN_OK;
+}

@@ -1,0 +1,295 @@
+"""WaveNet — B200-native stand-in for the reference Keras model (training pass).
+
+Mirrors /root/reference/src/model.py: constructor kwargs and validation (:14-70), dilation
+schedule and receptive field (:79-81,122), `build` (:171-211), `call` (:213-239),
+`train_step` / `test_step` (:309-391, up to and including the gradients), `prepare_target`
+(:151-155), `compute_receptive_field` (:553-556).  The arithmetic runs in libwavenet_b200.so;
+torch holds device buffers, streams and (multi-GPU) the NCCL process group.
+
+Out of scope (inference / observability): `generate`, `sample_waveform`,
+the compiled MSE metric.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._engine import Handle, as_dev
+from .layers import WaveNetLayer  # noqa: F401  (re-export, like `from src.layers import WaveNetLayer`)
+
+
+class WaveNet:
+  """WaveNet model class (same kwargs as the reference)."""
+
+  def __init__(self, kernel_size: int = 2, channels: int = 32, blocks: int = 10, layers_per_block: int = 1,
+               activation=None, conditioning=None, mapping_layers=None, mapping_activation=None,
+               dropout: float = 0, dilation_bound: int = 512, num_mixtures=None,
+               sampling_function: str = 'categorical', bits=8, skip_channels=None, dilation_channels=None,
+               use_residual=True, use_skip=True, final_layers_channels=None, l2_reg_factor: int = 0,
+               precision: str = 'fp32', device: Optional[int] = None, max_batch: Optional[int] = None,
+               max_time: Optional[int] = None, **kwargs):
+    # model.py:52-70 (same messages)
+    if conditioning not in ['global', 'local', None]:
+      raise ValueError("Conditioning must be 'global', 'local' or None.")
+    if kernel_size < 2:
+      raise ValueError('Kernel size must be at least 2.')
+    if math.log(dilation_bound, kernel_size) % 1 != 0:
+      raise ValueError('dilation bound must be power of kernel_size.')
+    if layers_per_block < 1:
+      raise ValueError('Layers per block must be at least 1.')
+    if blocks < 1:
+      raise ValueError('Blocks must be at least 1.')
+    if num_mixtures is not None and num_mixtures < 1:
+      raise ValueError('Number of mixtures must be at least 1 or None.')
+    if dropout < 0 or dropout > 1:
+      raise ValueError('Dropout must be between 0 and 1.')
+    if sampling_function not in ['categorical', 'logistic', 'gaussian']:
+      raise ValueError('Sampling function must be categorical, logistic or gaussian.')
+    if sampling_function == 'categorical' and num_mixtures is not None:
+      raise ValueError('Categorical sampling cannot be used with mixtures.')
+    if conditioning == 'local':
+      # the reference raises at construction too (model.py:137 passes `kernel=` to Conv1D)
+      raise NotImplementedError('local conditioning is untested/broken upstream (README.md:13) and not built')
+    if final_layers_channels is None:
+      raise TypeError("'NoneType' object is not iterable: final_layers_channels must be a list (model.py:111)")
+    if mapping_layers is None:
+      mapping_layers = []
+    elif isinstance(mapping_layers, int):
+      mapping_layers = [mapping_layers]
+    elif not isinstance(mapping_layers, list):
+      raise ValueError('Mapping layers must be a list of integers.')
+    if precision not in _lib.PRECISION:
+      raise ValueError(f'precision must be one of {sorted(_lib.PRECISION)}')
+
+    self.regularization = l2_reg_factor > 0
+    self.l2_reg_factor = l2_reg_factor
+    self.num_mixtures = num_mixtures
+    self.use_skip = use_skip
+    self.use_residual = use_residual
+    self.sampling_function = sampling_function
+    self.bits = bits
+    self.kernel_size = kernel_size
+    self.channels = channels
+    self.blocks = blocks
+    self.layers_per_block = layers_per_block
+    self.activation = activation
+    self.mapping_layers = list(mapping_layers)
+    self.mapping_activation = mapping_activation
+    self.dropout = dropout
+    self.dilation_bound = dilation_bound
+    self.skip_channels = skip_channels
+    self.dilation_channels = dilation_channels
+    self.final_layers_channels = list(final_layers_channels)
+    self.conditioning = conditioning
+    self.precision = precision
+    self.device_index = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else (device or 0)
+    self._max_batch, self._max_time = max_batch, max_time
+
+    # model.py:79-81: dilations never reach dilation_bound
+    max_power = int(math.log(dilation_bound, kernel_size))
+    self.dilations = [kernel_size ** (i % max_power) for i in range(layers_per_block * blocks)]
+    # model.py:122
+    self.receptive_field = 1 + sum(self.dilations) * (kernel_size - 1) + 1
+
+    self._act = _lib.activation_code(activation)
+    self._map_act = _lib.activation_code(mapping_activation)
+    self.optimizer = None
+    self.built = False
+    self._handle: Optional[Handle] = None
+    self._pending_weights = None
+    self.n_replicas = 1          # MirroredStrategy replica count (train.py:203); set by parallel.attach()
+    self._process_group = None
+
+  # ------------------------------------------------------------------ compile (model.py:157-169)
+  def compile(self, **kwargs):
+    if 'loss' in kwargs:
+      raise ValueError('Loss must be set in the model init function.')
+    self.optimizer = kwargs.get('optimizer', None)
+    self._metrics_from_compilation = list(kwargs.get('metrics') or [])
+
+  # ------------------------------------------------------------------ build (model.py:171-211)
+  def build(self, input_shape):
+    if self.conditioning == 'global':
+      x_shape, cond_shape = input_shape
+      cond_in = int(cond_shape[-1])
+    else:
+      x_shape, cond_in = input_shape, 0
+    x_shape = tuple(x_shape)
+    B = int(self._max_batch or x_shape[0])
+    T = int(self._max_time or x_shape[1])
+    cfg = _lib.WnConfig()
+    cfg.kernel_size = self.kernel_size
+    cfg.channels = self.channels
+    cfg.blocks = self.blocks
+    cfg.layers_per_block = self.layers_per_block
+    cfg.activation = self._act
+    cfg.conditioning = 1 if self.conditioning == 'global' else 0
+    cfg.n_mapping = len(self.mapping_layers)
+    for i, m in enumerate(self.mapping_layers):
+      cfg.mapping_layers[i] = m
+    cfg.mapping_activation = self._map_act
+    cfg.cond_in = cond_in
+    cfg.dilation_bound = self.dilation_bound
+    cfg.num_mixtures = 0 if self.num_mixtures is None else self.num_mixtures
+    cfg.sampling_function = _lib.SAMPLING[self.sampling_function]
+    cfg.bits = self.bits
+    cfg.skip_channels = 0 if self.skip_channels is None else self.skip_channels
+    cfg.dilation_channels = 0 if self.dilation_channels is None else self.dilation_channels
+    cfg.use_residual = 1 if self.use_residual else 0
+    cfg.use_skip = 1 if self.use_skip else 0
+    cfg.n_final = len(self.final_layers_channels)
+    for i, m in enumerate(self.final_layers_channels):
+      cfg.final_layers_channels[i] = m
+    cfg.l2_reg_factor = float(self.l2_reg_factor)
+    cfg.dropout = float(self.dropout)
+    cfg.n_dilations = 0
+    cfg.has_input_conv = 1
+    cfg.has_head = 1
+    cfg.precision = _lib.PRECISION[self.precision]
+    cfg.max_batch = B
+    cfg.max_time = T
+    cfg.device = self.device_index
+    old = None
+    if self._handle is not None:
+      old = self._handle.get_weights()
+      self._handle.close()
+    self._handle = Handle(cfg)
+    assert self._handle.lib.wn_receptive_field(self._handle.h) == self.receptive_field
+    if old is not None:
+      self._handle.set_weights(old)
+    elif self._pending_weights is not None:
+      self._handle.set_weights(self._pending_weights)
+      self._pending_weights = None
+    else:
+      self._handle.glorot_init(seed=1, bias_std=0.0)   # Keras defaults: glorot-uniform, zero bias
+    self.built = True
+    self._built_for = (B, T)
+
+  def _ensure_built(self, x, cond):
+    B, T = int(x.shape[0]), int(x.shape[1])
+    if not self.built or B > self._built_for[0] or T > self._built_for[1]:
+      if self.built:
+        self._max_batch = max(B, self._built_for[0])
+        self._max_time = max(T, self._built_for[1])
+      self.build((x.shape, cond.shape) if self.conditioning == 'global' else x.shape)
+
+  # ------------------------------------------------------------------ weights
+  @property
+  def handle(self) -> Handle:
+    if self._handle is None:
+      raise ValueError('Model is not built')
+    return self._handle
+
+  @property
+  def trainable_variables(self):
+    """Zero-copy device views in Keras tracking order and layouts."""
+    h = self.handle
+    return [h.param(i) for i in range(h.n_params)]
+
+  @property
+  def variable_names(self):
+    return list(self.handle.names)
+
+  def get_weights(self):
+    return self.handle.get_weights()
+
+  def set_weights(self, weights):
+    if self._handle is None:
+      self._pending_weights = dict(weights)
+    else:
+      self._handle.set_weights(weights)
+
+  def get_grads(self):
+    return self.handle.get_grads()
+
+  # ------------------------------------------------------------------ call (model.py:213-239)
+  def _unpack(self, inputs):
+    if self.conditioning == 'global':
+      x, cond = inputs
+    else:
+      x, cond = inputs, None
+    return x, cond
+
+  def call(self, inputs, training=False):
+    x, cond = self._unpack(inputs)
+    dev = torch.device('cuda', self.device_index)
+    x = as_dev(x, dev)
+    if x.dim() == 3:
+      if x.shape[2] != 1:
+        raise ValueError('input must be (batch, samples, 1)')
+      x2 = x[:, :, 0].contiguous()
+    else:
+      x2 = x
+    cond = as_dev(cond, dev) if cond is not None else None
+    self._ensure_built(x2, cond)
+    if training and self.dropout > 0:
+      raise NotImplementedError('training with dropout>0 is not built; use dropout=0')
+    h = self.handle
+    B, T = x2.shape
+    cout = 3 * self.num_mixtures if self.num_mixtures is not None else 2 ** self.bits
+    out = torch.empty((B, T, cout), dtype=torch.float32, device=dev)
+    _lib.check(h.lib.wn_forward(h.h, h.ptr(x2), h.ptr(cond), B, T, h.ptr(out), h.stream_ptr()))
+    return out
+
+  __call__ = call
+
+  # ------------------------------------------------------------------ targets (model.py:151-155)
+  def prepare_target(self, x):
+    if self.num_mixtures is not None:
+      return x
+    dev = torch.device('cuda', self.device_index)
+    xt = as_dev(x, dev)
+    idx = torch.empty(xt.shape, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.wn_quantize(C.c_void_p(xt.data_ptr()), C.c_void_p(idx.data_ptr()), xt.numel(), self.bits,
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return idx
+
+  # ------------------------------------------------------------------ steps (model.py:309-391)
+  def _step(self, data, train: bool):
+    x, cond = self._unpack(data) if self.conditioning == 'global' else (data, None)
+    dev = torch.device('cuda', self.device_index)
+    x = as_dev(x, dev)
+    frames = x[:, :, 0].contiguous() if x.dim() == 3 else x
+    cond = as_dev(cond, dev) if cond is not None else None
+    B, T = int(frames.shape[0]), int(frames.shape[1]) - 1
+    self._ensure_built(frames[:, :-1], cond)
+    h = self.handle
+    fn = h.lib.wn_train_step if train else h.lib.wn_test_step
+    _lib.check(fn(h.h, h.ptr(frames), h.ptr(cond), B, T, self.n_replicas, h.ptr(h._loss), h.stream_ptr()))
+    if train and self._process_group is not None:
+      # MirroredStrategy's gradient all-reduce (SUM: the loss is already divided by the global batch)
+      torch.distributed.all_reduce(h.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self._process_group)
+    return h._loss[:1]
+
+  def train_step(self, data):
+    """Forward + loss + backward; gradients land in `get_grads()` / `handle.flat_grads`.
+    Returns {'loss': float} like the Keras metrics dict (optimizer/MSE metric: out of scope)."""
+    loss = self._step(data, True)
+    if self.optimizer is not None:
+      self.optimizer.apply_gradients(self)
+    return {'loss': float(loss.item())}
+
+  def train_step_async(self, data):
+    """Same as train_step without the host read-back: returns a 1-element device tensor."""
+    return self._step(data, True)
+
+  def test_step(self, data):
+    return {'loss': float(self._step(data, False).item())}
+
+  def loss_fn(self, target, pred):
+    raise NotImplementedError('stand-alone loss_fn on materialised predictions is not built: the loss is fused into train_step/test_step')
+
+  def compute_receptive_field(self, sampling_frequency):
+    return self.receptive_field / sampling_frequency
+
+  def sample_waveform(self, inputs, deterministic=False):
+    raise NotImplementedError('sampling is inference-only (model.py:393-503) and out of scope')
+
+  def generate(self, *args, **kwargs):
+    raise NotImplementedError('autoregressive generation (model.py:258-307) is inference-only and out of scope')
