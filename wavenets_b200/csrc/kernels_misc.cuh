@@ -257,8 +257,10 @@ __global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restri
         const float xx = fminf((y - mu) / sc, 1e8f);
         comp[m] = expf(-0.5f * xx * xx) / (sc * SQRT2PI);
       } else {
+        // sigma(a) - sigma(b) == sigma(a) * sigma(-b) * (1 - exp(-(a-b))), a-b = 2h*e: the same
+        // quantity as model.py:543-544 without the fp32 cancellation of two nearly equal sigmoids
         const float e = expf(-ls);
-        comp[m] = wn_sigmoid<false>((y - mu + h) * e) - wn_sigmoid<false>((y - mu - h) * e);
+        comp[m] = wn_sigmoid<false>((y - mu + h) * e) * wn_sigmoid<false>(-(y - mu - h) * e) * (-expm1f(-2.0f * h * e));
       }
       lik += pi[m] * comp[m];
     }
@@ -282,12 +284,14 @@ __global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restri
           dls = -r * (xx * xx * nc - 1.0f) * pass;
         } else {
           const float e = expf(-ls);
-          const float a = (y - mu + h) * e, bq = (y - mu - h) * e;
-          const float sa = wn_sigmoid<false>(a), sb = wn_sigmoid<false>(bq);
-          const float dsa = sa * (1.0f - sa), dsb = sb * (1.0f - sb);
+          const float a = (y - mu + h) * e, bq = (y - mu - h) * e, dab = 2.0f * h * e;
+          const float sa = wn_sigmoid<false>(a), snb = wn_sigmoid<false>(-bq);
+          // sigma'(a) - sigma'(b) = (sigma(a)-sigma(b)) * (1 - sigma(a) - sigma(b)) ; comp[m] holds sigma(a)-sigma(b)
+          const float dd = comp[m] * (snb - sa);
+          const float dsb = snb * (1.0f - snb);
           const float c = pi[m] * linv;
-          dmu = c * e * (dsa - dsb);
-          dls = c * (a * dsa - bq * dsb) * pass;
+          dmu = c * e * dd;
+          dls = c * (a * dd + dab * dsb) * pass;
         }
         d[m] = from_f<TD>((pi[m] - r) * scale);
         d[M + m] = from_f<TD>(dmu * scale);

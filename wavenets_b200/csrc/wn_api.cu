@@ -1160,8 +1160,8 @@ static int check_bt(wn_handle* h, int B, int T) {
 }
 
 extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void* stream) {
+  if (n == 0) return WN_OK;  /* empty input: nothing to do */
   if (!x_dev || !idx_dev || n < 0 || bits < 1 || bits > 16) { set_err("bad quantize arguments"); return WN_ERR_VALUE; }
-  if (n == 0) return WN_OK;
   quantize_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, (long long*)idx_dev, n, bits);
   CK(cudaGetLastError());
   return WN_OK;
