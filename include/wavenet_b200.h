@@ -135,6 +135,16 @@ int wn_layer_forward(wn_handle* h, int block, const float* x_dev, const float* c
 int wn_layer_backward(wn_handle* h, int block, const float* dx_out_dev, const float* dskip_dev,
                       float* dx_dev, float* dcond_dev, void* stream);
 
+/* ---- kernel-level test hooks (bf16 tier; no reference counterpart) -------------------------
+ * The two tcgen05 mainloops without a model around them, for tests against a plain fp32 matmul:
+ *   conv_gemm: out[(b,t), n] = sum_s A[(b, t+shifts[s]), 0:K] . W[n, s*K : (s+1)*K]   (rows outside [0,T) are zero)
+ *   wgrad    : out[s*K + c, n] = sum_{b,t} A[(b, t+shifts[s]), c] * G[(b,t), n]
+ * A (B,T,lda) bf16, W [N16][nseg*K] bf16, G (B,T,ldg) bf16, out fp32.  Synchronous. */
+int wn_debug_conv_gemm(const void* a_bf16_dev, int lda, int B, int T, int nseg, const int* shifts, int K,
+                       const void* w_bf16_dev, int N, int N16, int tile, float* out_dev, void* stream);
+int wn_debug_wgrad(const void* a_bf16_dev, int lda, const void* g_bf16_dev, int ldg, int B, int T, int nseg,
+                   const int* shifts, int K, int N, float* out_dev, void* stream);
+
 /* ---- introspection for benchmarks --------------------------------------------------------- */
 /* number of kernel launches issued by the last wn_train_step / wn_forward on this handle */
 int64_t wn_last_launch_count(const wn_handle* h);

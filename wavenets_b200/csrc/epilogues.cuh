@@ -16,6 +16,7 @@
 // Used by: pre-stack dilated convs (layers.py:66-74), conv1 + residual add (layers.py:213,222-223),
 // skip-sum GEMM (model.py:236), head 1x1 convs (model.py:105-119).
 template <class T, class TO, bool FAST> struct EpiBiasActRes {
+  static constexpr bool kHeavy = false;   // tcgen05 path: 4 epilogue warps are enough
   struct Params {
     TO* out; int ldo;
     const float* bias;                 // [N] or null
@@ -29,7 +30,7 @@ template <class T, class TO, bool FAST> struct EpiBiasActRes {
     for (int c = q * 16; c < bn; c += nq * 16) {
       const int n = n0 + c;
       if (n >= p.N) break;
-      const int nv = min(16, p.N - n);
+      const int nv = acc.clip(min(16, p.N - n));
       float v[16];
       acc.load16(c, v);
       if (p.bias) {
@@ -61,6 +62,7 @@ template <class T, class TO, bool FAST> struct EpiBiasActRes {
 //   z = acc + bias + cbias[b]   (Keras column order [filter D | gate D] in memory)
 //   g = tanh(z_f) * sigmoid(z_s)
 template <class T, bool FAST> struct EpiGate {
+  static constexpr bool kHeavy = true;    // 2 MUFU per output: 8 epilogue warps
   struct Params {
     T* z; T* g;                        // z [rows][2D], g [rows][ldg]
     int ldg;
@@ -74,7 +76,7 @@ template <class T, bool FAST> struct EpiGate {
     for (int c = q * 16; c < half; c += nq * 16) {
       const int ch = (n0 >> 1) + c;
       if (ch >= p.D) break;
-      const int nv = min(16, p.D - ch);
+      const int nv = acc.clip(min(16, p.D - ch));
       float f[16], s[16], g[16];
       acc.load16(c, f);
       acc.load16(half + c, s);
@@ -101,6 +103,7 @@ template <class T, bool FAST> struct EpiGate {
 // Adjoint of the gate: acc = dg for channels [n0, n0+bn) ;
 //   dz_f = dg * sig(z_s) * (1 - tanh(z_f)^2),  dz_s = dg * tanh(z_f) * sig(z_s) * (1 - sig(z_s))
 template <class T, bool FAST> struct EpiGateBwd {
+  static constexpr bool kHeavy = true;
   struct Params {
     const T* z;                        // [rows][2D] cached pre-activations
     T* dz;                             // [rows][2D]
@@ -111,7 +114,7 @@ template <class T, bool FAST> struct EpiGateBwd {
     for (int c = q * 16; c < bn; c += nq * 16) {
       const int ch = n0 + c;
       if (ch >= p.D) break;
-      const int nv = min(16, p.D - ch);
+      const int nv = acc.clip(min(16, p.D - ch));
       float dg[16], f[16], s[16];
       acc.load16(c, dg);
       const T* zrow = p.z + grow * 2 * p.D;
@@ -133,6 +136,7 @@ template <class T, bool FAST> struct EpiGateBwd {
 // Generic dgrad epilogue: out = (acc + add[row][n]) * act'(y[row][n])
 // (residual pass-through of d x_out, and activation adjoint from the cached activation output)
 template <class T, class TO> struct EpiActBwd {
+  static constexpr bool kHeavy = false;
   struct Params {
     TO* out; int ldo;
     const T* add; int lda;             // or null
@@ -144,7 +148,7 @@ template <class T, class TO> struct EpiActBwd {
     for (int c = q * 16; c < bn; c += nq * 16) {
       const int n = n0 + c;
       if (n >= p.N) break;
-      const int nv = min(16, p.N - n);
+      const int nv = acc.clip(min(16, p.N - n));
       float v[16];
       acc.load16(c, v);
       if (p.add) {

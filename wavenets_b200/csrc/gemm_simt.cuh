@@ -38,6 +38,7 @@ struct SmemAccRow {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = rowp[c + i];
   }
+  __device__ __forceinline__ int clip(int nv) const { return nv; }
 };
 
 // tile 64 rows x 64 cols, 256 threads, 4x4 micro-tile, K chunks of 16

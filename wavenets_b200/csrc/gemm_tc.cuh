@@ -1,22 +1,453 @@
-// gemm_tc.cuh — bf16 tcgen05/TMEM/TMA mainloops (throughput tier).  STUB: filled in next.
+// gemm_tc.cuh — bf16 tcgen05/TMEM/TMA mainloops (the throughput tier).
+//
+// Same two contractions as gemm_simt.cuh, re-designed for sm_100a:
+//
+//   tc_conv_gemm : out[(b,t), n] = sum_seg A_seg[(b, t+shift_seg), :] . W[n, kofs_seg + :]
+//     The dilated causal conv is a dense contraction over the [x_{t-d}, x_t] channel concat
+//     that is never materialised: each tap is its own TMA box of the SAME activation tensor,
+//     fetched through a (C, T, B, slab) tensor map at time coordinate t0+shift.  Rows outside
+//     [0,T) are out of bounds for the map and arrive as zeros: causal padding and batch
+//     isolation cost nothing and are exact.  Persistent, warp-specialised CTA:
+//       warp 0      TMA producer  (A box 128 rows x 64 ch, W box BN rows x 64 k; 128B swizzle)
+//       warp 1      tcgen05.mma issuer (one elected lane; M=128, N=BN, K=16 per instruction)
+//       warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
+//       warps 4..   epilogue: tcgen05.ld -> fused epilogue functor (epilogues.cuh) -> HBM
+//     smem ring full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue),
+//     so the epilogue of tile i overlaps the mainloop of tile i+1.
+//
+//   tc_wgrad : dW[kofs_seg + c, n] = sum_{b,t} A_seg[(b, t+shift_seg), c] * G[(b,t), n]
+//     Time is the contraction dimension, so both operands are MN-major straight from their
+//     (B,T,C) layout (no transposes): A box = 64 time rows x 64 channels.  Split over row ranges;
+//     fp32 partials reduced by a second deterministic kernel (no atomics).
 #pragma once
 #include "common.cuh"
+#include "tc_common.cuh"
 
 #define WN_MAX_WGRAD_SPLITS 64
+#define TC_MAX_SEG 4
 
-struct TmapCache { int unused = 0; };
 struct TcSeg { const bf16* A; int lda; int shift; int K; };
 struct TcGemmDesc {
-  int B, T, nseg; TcSeg seg[4]; int n_outer; long long outer_stride;
+  int B, T, nseg; TcSeg seg[TC_MAX_SEG]; int n_outer; long long outer_stride;
   const bf16* W; int ktot; int N16; int tileN;
 };
 struct TcWgradDesc {
-  int B, T, N; const bf16* G; int ldg; int nseg; TcSeg seg[4]; int ktot; float* partial;
+  int B, T, N; const bf16* G; int ldg; int nseg; TcSeg seg[TC_MAX_SEG]; int ktot; float* partial;
 };
-static inline const char* tc_last_error() { return "tcgen05 tier not built"; }
-static inline int tc_init() { return -1; }
-static inline int tc_check_config(int R, int D, int S, int K) { return -1; }
-static inline void tc_pick_tile(int n, bool gate, int* n16, int* tile) { *n16 = (n + 63) / 64 * 64; *tile = 64; }
-static inline void tc_pack_gate_T(cudaStream_t, const float*, int, int, bf16*, int, int, int, int) {}
-template <class Epi> static int tc_conv_gemm(TmapCache&, cudaStream_t, const TcGemmDesc&, const typename Epi::Params&) { return -1; }
-static inline int tc_wgrad(TmapCache&, cudaStream_t, const TcWgradDesc&, int* nsplit) { *nsplit = 1; return -1; }
+
+static inline int tc_check_config(int R, int D, int S, int K) {
+  if (R % 64 || D % 64 || S % 64) return -1;
+  if (K > TC_MAX_SEG) return -2;
+  return 0;
+}
+// column tiling of an N-wide output: N16 = padded width, tile = CTA tile width (64/128/256).
+// gate == true: n = 2D and a tile must hold matching filter and gate halves (tile/2 | D).
+static inline void tc_pick_tile(int n, bool gate, int* n16, int* tile) {
+  int t;
+  if (gate) t = ((n / 2) % 128 == 0) ? 256 : 128;
+  else t = n > 128 ? 256 : (n > 64 ? 128 : 64);
+  *tile = t;
+  *n16 = (n + t - 1) / t * t;
+}
+
+// ---------------------------------------------------------------- gate weight pack (transposed + interleaved)
+// dst[n'][k] = W[k][src(n')] : tile-interleaved columns [filter ch0.. | gate ch0..) per tile of width `tile`
+__global__ void tc_pack_gate_T_kernel(const float* __restrict__ src, int ktot, int cout, bf16* __restrict__ dst, int ld, int tile, int D, int n16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n16 * ktot) return;
+  const int np = (int)(i / ktot), k = (int)(i % ktot);
+  const int half = tile >> 1;
+  const int ti = np / tile, j = np % tile;
+  const int ch = ti * half + (j % half);
+  float v = 0.f;
+  if (ch < D) v = src[(long long)k * cout + (j < half ? ch : D + ch)];
+  dst[(long long)np * ld + k] = __float2bfloat16_rn(v);
+}
+static inline void tc_pack_gate_T(cudaStream_t st, const float* src, int ktot, int cout, bf16* dst, int ld, int tile, int D, int n16) {
+  const long long total = (long long)n16 * ktot;
+  tc_pack_gate_T_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, ktot, cout, dst, ld, tile, D, n16);
+}
+
+// ---------------------------------------------------------------- conv GEMM kernel
+struct TcGemmParams {
+  int B, T;
+  int tiles_t;      // ceil(T / 128)
+  int n_tiles;      // N16 / BN
+  int num_tiles;    // B * tiles_t * n_tiles
+  int nseg;
+  int segK[TC_MAX_SEG];
+  int segShift[TC_MAX_SEG];
+  int n_outer;
+};
+
+template <int BN> struct TcGemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <class Epi, int BN, int NEPI>
+__global__ void __launch_bounds__(128 + 32 * NEPI, 1)
+tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW, const TcGemmParams p,
+                    const typename Epi::Params ep) {
+  using Cfg = TcGemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.nseg > 1) tma_prefetch_desc(&tmA1);
+    if (p.nseg > 2) tma_prefetch_desc(&tmA2);
+    if (p.nseg > 3) tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NEPI); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM, n0 = nt * BN;
+        int wk = 0;
+        for (int o = 0; o < p.n_outer; ++o) {
+          for (int s = 0; s < p.nseg; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
+            const int kseg = p.segK[s], tcoord = t0 + p.segShift[s];
+            for (int k0 = 0; k0 < kseg; k0 += Cfg::BK) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, tm, &full_bar[stage], k0, tcoord, b, o);
+              tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            wk += kseg;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    int ksteps = 0;
+    for (int s = 0; s < p.nseg; ++s) ksteps += (p.segK[s] + Cfg::BK - 1) / Cfg::BK;
+    ksteps *= p.n_outer;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the 128B swizzle row
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int q = e >> 2;                    // column-chunk phase when NEPI == 8
+    constexpr int nq = NEPI / 4;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM, n0 = nt * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int t = t0 + quarter * 32 + lane;
+      TmemAccRow acc{tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16), t < p.T};
+      Epi::row(ep, acc, b, (long long)b * p.T + (t < p.T ? t : 0), n0, BN, q, nq);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+static int g_tc_num_sms = 0;
+static inline int tc_num_sms() {
+  if (g_tc_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_tc_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_tc_num_sms <= 0) g_tc_num_sms = 148;
+  }
+  return g_tc_num_sms;
+}
+
+// activation operand map: (C = K channels, T, B, slabs) with box (64, rows, 1, 1)
+static inline const CUtensorMap* tc_act_map(TmapCache& tc, const bf16* A, int lda, int K, int T, int B, int n_outer, long long outer_stride,
+                                            int box_rows) {
+  uint64_t dims[4] = {(uint64_t)K, (uint64_t)T, (uint64_t)B, (uint64_t)(n_outer > 0 ? n_outer : 1)};
+  uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)T * lda * 2, (uint64_t)(n_outer > 1 ? outer_stride * 2 : (long long)B * T * lda * 2)};
+  uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+  return tc.get(A, 4, dims, str, box);
+}
+
+template <class Epi, int BN, int NEPI>
+static int tc_conv_gemm_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep) {
+  using Cfg = TcGemmCfg<BN>;
+  const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
+  for (int s = 0; s < d.nseg; ++s) {
+    ma[s] = tc_act_map(tc, d.seg[s].A, d.seg[s].lda, d.seg[s].K, d.T, d.B, s == 0 ? d.n_outer : 1, d.outer_stride, 128);
+    if (!ma[s]) return -10;
+  }
+  for (int s = d.nseg; s < TC_MAX_SEG; ++s) ma[s] = ma[0];
+  uint64_t wd[2] = {(uint64_t)d.ktot, (uint64_t)d.N16};
+  uint64_t ws[1] = {(uint64_t)d.ktot * 2};
+  uint32_t wb[2] = {64, (uint32_t)BN};
+  const CUtensorMap* mw = tc.get(d.W, 2, wd, ws, wb);
+  if (!mw) return -11;
+  TcGemmParams p{};
+  p.B = d.B; p.T = d.T; p.tiles_t = (d.T + 127) / 128; p.n_tiles = d.N16 / BN; p.num_tiles = d.B * p.tiles_t * p.n_tiles;
+  p.nseg = d.nseg; p.n_outer = d.n_outer > 0 ? d.n_outer : 1;
+  for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
+  auto kern = tc_conv_gemm_kernel<Epi, BN, NEPI>;
+  static bool attr_done = false;   // per template instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  const int grid = p.num_tiles < tc_num_sms() ? p.num_tiles : tc_num_sms();
+  kern<<<grid, 128 + 32 * NEPI, Cfg::SMEM_BYTES, st>>>(*ma[0], *ma[1], *ma[2], *ma[3], *mw, p, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "conv_gemm launch: %s", cudaGetErrorString(e)); return -13; }
+  return 0;
+}
+
+template <class Epi> static int tc_conv_gemm(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep) {
+  int tile = d.tileN;
+  if (tile == 0) tile = d.N16 % 256 == 0 ? 256 : (d.N16 % 128 == 0 ? 128 : 64);
+  if (d.N16 % tile != 0 || d.nseg < 1 || d.nseg > TC_MAX_SEG) { snprintf(g_tc_err, sizeof(g_tc_err), "bad tiling N16=%d tile=%d nseg=%d", d.N16, tile, d.nseg); return -1; }
+  constexpr int NEPI = Epi::kHeavy ? 8 : 4;
+  switch (tile) {
+    case 256: return tc_conv_gemm_launch<Epi, 256, NEPI>(tc, st, d, ep);
+    case 128: return tc_conv_gemm_launch<Epi, 128, NEPI>(tc, st, d, ep);
+    case 64: return tc_conv_gemm_launch<Epi, 64, NEPI>(tc, st, d, ep);
+  }
+  return -2;
+}
+
+// ---------------------------------------------------------------- wgrad kernel
+struct TcWgradParams {
+  int B, T, N;
+  int chunks_t;          // ceil(T / 64)
+  int total_chunks;      // B * chunks_t
+  int chunks_per_split;
+  int ktot;
+  int nseg;
+  int segK[TC_MAX_SEG];
+  int segShift[TC_MAX_SEG];
+  float* partial;        // [nsplit][ktot][N]
+};
+
+template <int BN> struct TcWgradCfg {
+  static constexpr int BKT = 64;                         // time rows per stage
+  static constexpr int A_BYTES = 2 * 64 * BKT * 2;       // two 64-channel atoms: 16 KB
+  static constexpr int G_BYTES = (BN / 64) * 64 * BKT * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + G_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+// grid: x = 128-row tiles of the (seg, channel) axis, y = BN-wide tiles of N, z = row-range split
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmG, const TcWgradParams p) {
+  using Cfg = TcWgradCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // locate segment / channel offset of this m tile
+  int mt = blockIdx.x, s = 0, koff = 0;
+  while (true) {
+    const int nt = (p.segK[s] + 127) >> 7;
+    if (mt < nt) break;
+    mt -= nt; koff += p.segK[s]; ++s;
+  }
+  const int k0 = mt << 7;
+  const int n0 = blockIdx.y * BN;
+  const int c_begin = blockIdx.z * p.chunks_per_split;
+  const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
+  const int nchunks = c_end - c_begin;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
+      tma_prefetch_desc(tm);
+      tma_prefetch_desc(&tmG);
+      const int shift = p.segShift[s];
+      int stage = 0; uint32_t phase = 0;
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        const int b = ch / p.chunks_t, t0 = (ch % p.chunks_t) * Cfg::BKT;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_4d(sa, tm, &full_bar[stage], k0, t0 + shift, b, 0);
+        tma_load_4d(sa + 8192, tm, &full_bar[stage], k0 + 64, t0 + shift, b, 0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + Cfg::A_BYTES + j * 8192, &tmG, &full_bar[stage], n0 + 64 * j, t0, b, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);   // both operands MN-major
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        // MN-major, 128B swizzle: 64-wide channel atoms 8192 B apart (LBO), 8 time rows = 1024 B (SBO)
+        const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
+        const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < Cfg::BKT / 16; ++k)   // 16 time rows = 2048 bytes (>>4 = 128) per step
+          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (it == nchunks - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int k = k0 + quarter * 32 + lane;        // channel index inside the segment
+    float* out = p.partial + ((long long)blockIdx.z * p.ktot + koff + k) * p.N;
+    const bool valid = k < p.segK[s];
+    if (nchunks > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c = 0; c < BN; c += 16) {
+      const int n = n0 + c;
+      if (n >= p.N) break;
+      float v[16];
+      if (nchunks > 0) tmem_ld16(taddr + (uint32_t)c, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      if (valid) {
+        const int nv = min(16, p.N - n);
+        if (nv == 16 && ((p.N & 3) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + n)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (i < nv) out[n + i] = v[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, int* nsplit_out) {
+  using Cfg = TcWgradCfg<BN>;
+  const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
+  int mtiles = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    ma[s] = tc_act_map(tc, d.seg[s].A, d.seg[s].lda, d.seg[s].K, d.T, d.B, 1, 0, 64);
+    if (!ma[s]) return -10;
+    mtiles += (d.seg[s].K + 127) / 128;
+  }
+  for (int s = d.nseg; s < TC_MAX_SEG; ++s) ma[s] = ma[0];
+  const CUtensorMap* mg = tc_act_map(tc, d.G, d.ldg, d.N, d.T, d.B, 1, 0, 64);
+  if (!mg) return -11;
+  TcWgradParams p{};
+  p.B = d.B; p.T = d.T; p.N = d.N; p.chunks_t = (d.T + 63) / 64; p.total_chunks = d.B * p.chunks_t; p.ktot = d.ktot; p.nseg = d.nseg;
+  for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
+  p.partial = d.partial;
+  const int ntiles = (d.N + BN - 1) / BN;
+  int nsplit = (tc_num_sms() + mtiles * ntiles - 1) / (mtiles * ntiles);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > WN_MAX_WGRAD_SPLITS) nsplit = WN_MAX_WGRAD_SPLITS;
+  if (nsplit > p.total_chunks) nsplit = p.total_chunks;
+  p.chunks_per_split = (p.total_chunks + nsplit - 1) / nsplit;
+  nsplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  *nsplit_out = nsplit;
+  auto kern = tc_wgrad_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  kern<<<dim3(mtiles, ntiles, nsplit), 256, Cfg::SMEM_BYTES, st>>>(*ma[0], *ma[1], *ma[2], *ma[3], *mg, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "wgrad launch: %s", cudaGetErrorString(e)); return -13; }
+  return 0;
+}
+
+static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, int* nsplit) {
+  if (d.nseg < 1 || d.nseg > TC_MAX_SEG) return -1;
+  if (d.N > 128) return tc_wgrad_launch<256>(tc, st, d, nsplit);
+  if (d.N > 64) return tc_wgrad_launch<128>(tc, st, d, nsplit);
+  return tc_wgrad_launch<64>(tc, st, d, nsplit);
+}

@@ -1,0 +1,216 @@
+// tc_common.cuh — sm_100a building blocks of the bf16 throughput tier: mbarrier, TMA
+// (cp.async.bulk.tensor), tcgen05.mma / TMEM, shared-memory + instruction descriptors, and the
+// host-side tensor-map cache.  Inline PTX only (no CUTLASS): the descriptor bit layouts follow
+// the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <unordered_map>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------- small PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug turns into a trap (CUDA error on the host) instead of a hung GPU.
+#ifndef WN_WATCHDOG_CYCLES
+#define WN_WATCHDOG_CYCLES 4000000000ll
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WN_WATCHDOG_CYCLES) {
+      printf("libwavenet_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// generic-proxy writes -> visible to the async proxy (TMA / tcgen05 operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- TMA
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; bf16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (lane_base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Accumulator row view handed to the epilogues (see epilogues.cuh): one thread = one TMEM lane.
+struct TmemAccRow {
+  uint32_t taddr;   // lane base in bits [16,32), first column of the tile in bits [0,16)
+  bool valid;       // false for rows past the end of the sequence: loads still run (warp-collective), stores clip to 0
+  __device__ __forceinline__ void load16(int c, float* v) const { tmem_ld16(taddr + (uint32_t)c, v); }
+  __device__ __forceinline__ int clip(int nv) const { return valid ? nv : 0; }
+};
+
+// ---------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor, 128-byte swizzle (what a TMA box with 128-byte inner extent
+// and CU_TENSOR_MAP_SWIZZLE_128B produces).  Rows of 128 B; 8-row groups of 1024 B.
+//   K-major operand  (rows = M/N index, 128 B = 64 bf16 of K): SBO = 1024 (next 8 rows), LBO unused.
+//   MN-major operand (rows = K index,   128 B = 64 bf16 of M/N): SBO = 1024 (next 8 K), LBO = bytes
+//   between consecutive 64-wide M/N atoms.
+// Fields: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | swizzle=2 (128B) [61,64)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1,
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- host: tensor maps
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_tmap_encode = nullptr;
+static thread_local char g_tc_err[256] = "";
+static inline const char* tc_last_error() { return g_tc_err; }
+
+static inline int tc_init() {
+  if (g_tmap_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return -1;
+  g_tmap_encode = (PFN_tmapEncodeTiled)fn;
+  return 0;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t d[4], s[3];
+  uint32_t box[4];
+  uint32_t rank;
+  bool operator==(const TmapKey& o) const {
+    if (base != o.base || rank != o.rank) return false;
+    for (int i = 0; i < 4; ++i) if (d[i] != o.d[i] || box[i] != o.box[i]) return false;
+    for (int i = 0; i < 3; ++i) if (s[i] != o.s[i]) return false;
+    return true;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 4; ++i) h = (h ^ (k.d[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2))) * 1099511628211ull;
+    for (int i = 0; i < 3; ++i) h = (h ^ k.s[i]) * 1099511628211ull;
+    for (int i = 0; i < 4; ++i) h = (h ^ k.box[i]) * 1099511628211ull;
+    return (size_t)(h ^ k.rank);
+  }
+};
+// Encoding a tensor map costs microseconds on the host; a training step reuses the same few
+// hundred (buffer, shape) combinations every iteration, so they are cached per handle.
+struct TmapCache {
+  std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> maps;
+  // bf16 tensor, rank 2..4, dims innermost first, strides in BYTES for dims 1..rank-1, 128B swizzle, zero OOB fill
+  const CUtensorMap* get(const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+    TmapKey k{};
+    k.base = base; k.rank = (uint32_t)rank;
+    for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides[i];
+    auto it = maps.find(k);
+    if (it != maps.end()) return &it->second;
+    if (!g_tmap_encode) { snprintf(g_tc_err, sizeof(g_tc_err), "tensor-map encoder not initialised"); return nullptr; }
+    if (((uintptr_t)base & 15) != 0) { snprintf(g_tc_err, sizeof(g_tc_err), "TMA base %p not 16-byte aligned", base); return nullptr; }
+    for (int i = 0; i + 1 < rank; ++i)
+      if (strides[i] % 16 != 0) { snprintf(g_tc_err, sizeof(g_tc_err), "TMA stride %llu not a multiple of 16 bytes", (unsigned long long)strides[i]); return nullptr; }
+    CUtensorMap m;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_tmap_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
+                               (const cuuint64_t*)strides, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r, rank,
+               (unsigned long long)k.d[0], (unsigned long long)k.d[1], (unsigned long long)k.d[2], (unsigned long long)k.d[3], box[0], box[1],
+               rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+      return nullptr;
+    }
+    auto ins = maps.emplace(k, m);
+    return &ins.first->second;
+  }
+};

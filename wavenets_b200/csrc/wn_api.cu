@@ -1344,6 +1344,51 @@ extern "C" int wn_layer_backward(wn_handle* h, int block, const float* dx_out_de
   return WN_OK;
 }
 
+// ---------------------------------------------------------------- kernel-level test hooks (bf16 tier)
+// Raw contractions of gemm_tc.cuh without a model around them, so tests can compare each
+// tcgen05 mainloop against a plain torch fp32 matmul on the same bf16 inputs.
+extern "C" int wn_debug_conv_gemm(const void* a_bf16_dev, int lda, int B, int T, int nseg, const int* shifts, int K, const void* w_bf16_dev, int N,
+                                  int N16, int tile, float* out_dev, void* stream) {
+  if (!a_bf16_dev || !w_bf16_dev || !out_dev || !shifts || nseg < 1 || nseg > TC_MAX_SEG) { set_err("bad debug gemm arguments"); return WN_ERR_VALUE; }
+  if (tc_init() != 0) { set_err("cannot resolve cuTensorMapEncodeTiled from the driver"); return WN_ERR_CUDA; }
+  static TmapCache cache;
+  cache.maps.clear();
+  TcGemmDesc d{};
+  d.B = B; d.T = T; d.nseg = nseg; d.n_outer = 1; d.outer_stride = 0;
+  for (int s = 0; s < nseg; ++s) d.seg[s] = TcSeg{(const bf16*)a_bf16_dev, lda, shifts[s], K};
+  d.W = (const bf16*)w_bf16_dev; d.ktot = nseg * K; d.N16 = N16; d.tileN = tile;
+  typedef EpiBiasActRes<bf16, float, true> E;
+  E::Params ep{};
+  ep.out = out_dev; ep.ldo = N; ep.act = ACT_LINEAR; ep.N = N; ep.vec = (N % 4) == 0;
+  int r = tc_conv_gemm<E>(cache, (cudaStream_t)stream, d, ep);
+  if (r != 0) { set_err("tcgen05 conv_gemm launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return WN_OK;
+}
+
+extern "C" int wn_debug_wgrad(const void* a_bf16_dev, int lda, const void* g_bf16_dev, int ldg, int B, int T, int nseg, const int* shifts, int K, int N,
+                              float* out_dev, void* stream) {
+  if (!a_bf16_dev || !g_bf16_dev || !out_dev || !shifts || nseg < 1 || nseg > TC_MAX_SEG) { set_err("bad debug wgrad arguments"); return WN_ERR_VALUE; }
+  if (tc_init() != 0) { set_err("cannot resolve cuTensorMapEncodeTiled from the driver"); return WN_ERR_CUDA; }
+  static TmapCache cache;
+  cache.maps.clear();
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long kn = (long long)nseg * K * N;
+  float* partial = nullptr;
+  CK(cudaMalloc(&partial, (size_t)kn * WN_MAX_WGRAD_SPLITS * 4));
+  TcWgradDesc d{};
+  d.B = B; d.T = T; d.N = N; d.G = (const bf16*)g_bf16_dev; d.ldg = ldg; d.nseg = nseg; d.ktot = nseg * K; d.partial = partial;
+  for (int s = 0; s < nseg; ++s) d.seg[s] = TcSeg{(const bf16*)a_bf16_dev, lda, shifts[s], K};
+  int nsplit = 1;
+  int r = tc_wgrad(cache, st, d, &nsplit);
+  if (r != 0) { cudaFree(partial); set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+  reduce_parts<<<cdiv(kn, 256), 256, 0, st>>>(partial, nsplit, kn, out_dev, kn, nullptr, 0.f);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(partial);
+  CK(e);
+  return WN_OK;
+}
+
 // ---------------------------------------------------------------- introspection
 extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
 extern "C" int wn_profile_begin(wn_handle* h, int tag) {
