@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — audio samples/s of one fwd+bwd WaveNet training pass (forward, loss, backward,
+gradient all-reduce; optimizer and metrics excluded) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # the reference path on the host CPU cores
+  torchrun --nproc-per-node N bench.py --gpus N ...      # N > 1: one rank per GPU, NCCL
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = 'audio samples/sec fwd+bwd WaveNet stack'
+UNIT = 'samples/s'
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      pk = json.load(f)
+    return dict(hbm=pk['hbm_gbs'], tensor=pk['bf16_tflops_sustained'], tensor_burst=pk['bf16_tflops'], source='measured')
+  return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source='fallback')
+
+
+class ClockSampler:
+  """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index, self.proc, self.lines = index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._pump, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _pump(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.12)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ln in self.lines:
+      f = [x.strip() for x in ln.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, v in zip(names, f[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(name)
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def work_model(cfg_kw, cond_in):
+  """Algorithmic FLOPs per audio sample (SURVEY.md 8d / BASELINE.md): F = 3 x F_fwd."""
+  from oracle import wavenet_oracle as wo   # flop accounting only (no compute)
+  from tests.util import oracle_config
+  ocfg = oracle_config(cfg_kw, cond_in)
+  return wo.flops_fwd_per_sample(ocfg), ocfg
+
+
+def cpu_reference_run(cfg, kw, cond_in, steps, warmup, budget_s, threads=None):
+  """The reference path restated on torch CPU ops (oracle/torch_ref.py; TF is not installable):
+  fwd+bwd, fp32, all host threads, on a bounded sample (B=1, T_sample) of the same workload."""
+  import torch
+  from oracle import wavenet_oracle as wo
+  from oracle import torch_ref
+  from tests.util import oracle_config
+  from wavenets_b200 import synth
+  threads = threads or os.cpu_count()
+  torch.set_num_threads(threads)
+  ocfg = oracle_config(kw, cond_in)
+  flops = 3 * wo.flops_fwd_per_sample(ocfg)['total']
+  # size the sample for a few seconds per step (~4e11 FLOP), within [512, recording_length]
+  T_full = cfg['recording_length']
+  T_s = int(min(T_full, max(512, 4.0e11 / flops)))
+  p = wo.init_params(ocfg, seed=1, dtype=np.float32)
+  stepper = torch_ref.CpuStepper(ocfg, p, threads=threads)
+  x = synth.frames(1, T_s, seed=0, apply_mulaw=cfg.get('apply_mulaw', True))
+  cond = synth.speakers_onehot(1, cond_in, seed=0) if cond_in else None
+  for _ in range(warmup):
+    stepper.step(x, cond)
+  times = []
+  t_begin = time.perf_counter()
+  for _ in range(steps):
+    t0 = time.perf_counter()
+    stepper.step(x, cond)
+    times.append(time.perf_counter() - t0)
+    if time.perf_counter() - t_begin > budget_s:
+      break
+  dt = float(np.median(times))
+  return {'value': T_s / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+          'sample': f'B=1 x T={T_s} of the {cfg["recording_length"]}-sample segments, fp32, {len(times)} timed steps (median), '
+                    'torch-CPU restatement of the reference path (TensorFlow not installable)',
+          'ms_per_step': dt * 1e3, 'steps': len(times)}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--config', default='c2')
+  ap.add_argument('--precision', default=None)
+  ap.add_argument('--batch', type=int, default=None, help='sequences per GPU')
+  ap.add_argument('--time', type=int, default=None, help='recording_length override')
+  ap.add_argument('--channels', type=int, default=None)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--profile-steps', type=int, default=2)
+  args = ap.parse_args()
+  if args.warmup < 3 and args.impl == 'b200':
+    args.warmup = 3   # timing rule: W >= 3
+
+  from wavenets_b200 import CONFIGS, model_kwargs, synth
+  cfg = dict(CONFIGS[args.config])
+  if args.time:
+    cfg['recording_length'] = args.time
+  if args.channels:
+    cfg['channels'] = args.channels
+    if cfg.get('skip_channels'):
+      cfg['skip_channels'] = args.channels
+  precision = args.precision or cfg.get('precision', 'bf16')
+  B_local = args.batch or cfg['batch_size']
+  T = cfg['recording_length']
+  kw = model_kwargs(cfg)
+  cond_in = cfg.get('n_speakers', 109) if kw['conditioning'] == 'global' else 0
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  workload = (f'{args.config}: WaveNet {kw["blocks"]}x{kw["layers_per_block"]} R={kw["channels"]} S={kw["skip_channels"]} '
+              f'{"global-cond(" + str(cond_in) + ")" if cond_in else "uncond"} '
+              f'{kw["sampling_function"]}{"-" + str(kw["num_mixtures"]) if kw["num_mixtures"] else "-" + str(2 ** kw["bits"])} '
+              f'T={T} B={B_local}/GPU')
+
+  # ------------------------------------------------------------------ reference arm (host CPU)
+  if args.impl == 'reference':
+    if rank != 0:
+      return 0
+    r = cpu_reference_run(cfg, kw, cond_in, max(1, args.steps), max(1, min(args.warmup, 2)), budget_s=120.0)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': r['steps'],
+            'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload, 'sample': r['sample']},
+            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+    return 0
+
+  # ------------------------------------------------------------------ this repo's CUDA path
+  import torch
+  import torch.distributed as dist
+  from wavenets_b200 import WaveNet, parallel
+  if not torch.cuda.is_available():
+    raise RuntimeError('bench.py needs a B200 (no CPU fallback); use --impl reference for the host baseline')
+  rank, local, world = parallel.init_from_env()
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world != args.gpus and rank == 0:
+    print(f'# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE', file=sys.stderr)
+
+  model = WaveNet(**kw, precision=precision, device=local, max_batch=B_local, max_time=T)
+  x_shape = (B_local, T, 1)
+  model.build((x_shape, (B_local, cond_in)) if cond_in else x_shape)
+  model.handle.glorot_init(seed=1, bias_std=0.0)
+  parallel.attach(model)
+  h = model.handle
+
+  # synthetic mu-law audio + speaker ids; every rank gets its own shard of the global batch
+  frames_np = synth.frames(B_local, T, seed=rank, apply_mulaw=cfg.get('apply_mulaw', True))
+  cond_np = synth.speakers_onehot(B_local, cond_in, seed=rank) if cond_in else None
+  frames_pin = torch.from_numpy(frames_np).pin_memory()
+  cond_pin = torch.from_numpy(cond_np).pin_memory() if cond_np is not None else None
+  frames_dev = frames_pin.to(dev)
+  cond_dev = cond_pin.to(dev) if cond_pin is not None else None
+  data_dev = (frames_dev, cond_dev) if cond_dev is not None else frames_dev
+  data_host = (frames_pin, cond_pin) if cond_pin is not None else frames_pin
+
+  def sync_all():
+    torch.cuda.synchronize(dev)
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  def max_over_ranks(ms):
+    if world == 1:
+      return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  # ---- warm-up (also builds tensor maps, NCCL channels)
+  for _ in range(args.warmup):
+    model.train_step_async(data_dev)
+  loss0 = float(model.train_step(data_host)['loss'])
+
+  # ---- timed region 1: inputs resident in HBM
+  sampler = ClockSampler(local) if rank == 0 else None
+  sync_all()
+  if sampler:
+    sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    loss_t = model.train_step_async(data_dev)
+  e1.record()
+  sync_all()
+  ms_total = max_over_ranks(e0.elapsed_time(e1))
+  launches = int(h.lib.wn_last_launch_count(h.h)) * args.steps
+  clocks = sampler.stop() if sampler else None
+  loss_last = float(loss_t.item())
+
+  # ---- timed region 2: end to end through the public API with HOST buffers
+  sync_all()
+  e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e2.record()
+  for _ in range(args.steps):
+    out = model.train_step(data_host)       # pinned H2D of frames (+cond), step, all-reduce, D2H of the loss
+  e3.record()
+  sync_all()
+  ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+  h2d = frames_pin.numel() * 4 + (cond_pin.numel() * 4 if cond_pin is not None else 0)
+
+  # ---- roofline of the dominant kernel class: the dilated-conv GEMMs (fwd + dgrad + wgrad)
+  flops, ocfg = work_model(kw, cond_in)
+  peaks = load_peaks()
+  import ctypes as C
+  prof = {}
+  for tag, name in ((1, 'dilated'), (2, 'gemm_all')):
+    h.lib.wn_profile_begin(h.h, tag)
+    for _ in range(args.profile_steps):
+      model.train_step_async(data_dev)
+    ms = C.c_double()
+    n = C.c_int64()
+    h.lib.wn_profile_end(h.h, C.byref(ms), C.byref(n))
+    prof[name] = (ms.value / args.profile_steps, n.value // args.profile_steps)
+  rows = B_local * T
+  dil_flops_step = 3.0 * flops['dilated'] * rows
+  dil_ms, dil_launches = prof['dilated']
+  achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
+  roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
+              'frac': achieved / peaks['tensor'], 'traffic': None,
+              'kernel': 'tc_conv_gemm_kernel + tc_wgrad_kernel on the dilated convs (fwd + dgrad + wgrad)' if precision == 'bf16'
+              else 'conv_gemm_simt + wgrad_simt on the dilated convs',
+              'launches_per_step': dil_launches, 'ms_per_step_in_kernel': dil_ms,
+              'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
+              'share_of_step': dil_ms / (ms_total / args.steps)}
+  step_ms = ms_total / args.steps
+  total_flops_step = 3.0 * flops['total'] * rows
+  whole = {'tflops_all_gemms_whole_step': total_flops_step / (step_ms * 1e-3) / 1e12,
+           'frac_of_tensor_peak_whole_step': total_flops_step / (step_ms * 1e-3) / 1e12 / peaks['tensor'],
+           'gemm_ms_per_step': prof['gemm_all'][0]}
+
+  line = {
+    'metric': METRIC, 'value': world * rows * args.steps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+    'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+    'dtype': 'bf16' if precision == 'bf16' else 'f32', 'data': 'synthetic',
+    'config': {'workload': workload, 'global_batch': B_local * world, 'segment': T, 'receptive_field': model.receptive_field,
+               'params': int(h.n_scalars), 'parallelism': f'dp{world}',
+               'l2': 'per-step working set (activations cached for backward) is GBs >> 126 MB L2; no explicit flush needed',
+               'flops_per_sample_fwd_bwd': 3 * flops['total']},
+    'e2e': {'value': world * rows * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+            'ms_per_step': ms_e2e / args.steps},
+    'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'whole_step': whole,
+    'loss': {'first': loss0, 'last': loss_last, 'e2e_last': out['loss']},
+  }
+  if rank == 0:
+    if world == 1 and not args.no_cpu_baseline:
+      r = cpu_reference_run(cfg, kw, cond_in, steps=5, warmup=1, budget_s=25.0)
+      line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    print(json.dumps(line))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+if __name__ == '__main__':
+  sys.exit(main())

@@ -110,7 +110,7 @@ def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, dtype
   loss = loss_per_sample(cfg, logits, x[:, 1:, :]).sum() / (x.shape[0] * n_replicas)
   loss.backward()
   grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
-  return float(loss), grads
+  return float(loss.detach()), grads
 
 
 class CpuStepper:
@@ -130,4 +130,4 @@ class CpuStepper:
     logits = forward_logits(self.p, self.cfg, x[:, :-1, :], c)
     loss = loss_per_sample(self.cfg, logits, x[:, 1:, :]).sum() / x.shape[0]
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
