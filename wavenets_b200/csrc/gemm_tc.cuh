@@ -33,7 +33,9 @@ struct TcGemmDesc {
 };
 struct TcWgradDesc {
   int B, T, N; const bf16* G; int ldg; int nseg; TcSeg seg[TC_MAX_SEG]; int ktot; float* partial;
+  float* cs_partial;   // optional: per-(split, batch slot) column sums of G, [nsplit][slots][N] (bias / conditioning gradients)
 };
+struct TcWgradPlan { int nsplit, chunks_per_split, chunks_t, slots; };
 
 static inline int tc_check_config(int R, int D, int S, int K) {
   if (R % 64 || D % 64 || S % 64) return -1;
@@ -281,6 +283,8 @@ struct TcWgradParams {
   int segK[TC_MAX_SEG];
   int segShift[TC_MAX_SEG];
   float* partial;        // [nsplit][ktot][N]
+  float* cs_partial;     // [nsplit][slots][N] or null
+  int slots;
 };
 
 template <int BN> struct TcWgradCfg {
@@ -321,8 +325,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
   const int nchunks = c_end - c_begin;
 
+  // CTAs of the first m-tile also reduce the columns of G (bias / conditioning gradients) with
+  // their otherwise idle epilogue warps, straight from the TMA-staged G tiles in shared memory.
+  const bool do_cs = p.cs_partial != nullptr && blockIdx.x == 0;
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], do_cs ? 5 : 1); }
     mbar_init(tfull_bar, 1);
     mbar_fence_init();
   }
@@ -372,6 +379,48 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
+    if (do_cs) {
+      // thread -> two adjacent columns (one bf16x2 word); rows past T are TMA zero fill
+      const int tid = threadIdx.x - 128;
+      const int c = 2 * tid;                         // column inside the BN tile
+      const bool act = c < BN;
+      const int atom = c >> 6, cc = c & 63;
+      const uint32_t col_off = (uint32_t)(atom * 8192 + (cc & 7) * 2);
+      const uint32_t chunk = (uint32_t)(cc >> 3);
+      float s0 = 0.f, s1 = 0.f;
+      int stage = 0; uint32_t phase = 0;
+      int cur_b = c_begin / p.chunks_t;
+      const int b_first = cur_b;
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        const int b = ch / p.chunks_t;
+        if (b != cur_b) {
+          if (act && n0 + c < p.N) {
+            float* o = p.cs_partial + ((long long)blockIdx.z * p.slots + (cur_b - b_first)) * p.N + n0 + c;
+            o[0] = s0;
+            if (n0 + c + 1 < p.N) o[1] = s1;
+          }
+          s0 = s1 = 0.f; cur_b = b;
+        }
+        mbar_wait(&full_bar[stage], phase);
+        if (act) {
+          const uint8_t* g = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES + col_off;
+#pragma unroll 16
+          for (int r = 0; r < Cfg::BKT; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(g + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4));
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (nchunks > 0 && act && n0 + c < p.N) {
+        float* o = p.cs_partial + ((long long)blockIdx.z * p.slots + (cur_b - b_first)) * p.N + n0 + c;
+        o[0] = s0;
+        if (n0 + c + 1 < p.N) o[1] = s1;
+      }
+    }
     const int quarter = warp & 3;
     const int k = k0 + quarter * 32 + lane;        // channel index inside the segment
     float* out = p.partial + ((long long)blockIdx.z * p.ktot + koff + k) * p.N;
@@ -408,7 +457,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 }
 
 template <int BN>
-static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, int* nsplit_out) {
+static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, TcWgradPlan* plan) {
   using Cfg = TcWgradCfg<BN>;
   const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
   int mtiles = 0;
@@ -431,7 +480,9 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   if (nsplit > p.total_chunks) nsplit = p.total_chunks;
   p.chunks_per_split = (p.total_chunks + nsplit - 1) / nsplit;
   nsplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
-  *nsplit_out = nsplit;
+  p.slots = (p.chunks_per_split + p.chunks_t - 2) / p.chunks_t + 1;
+  p.cs_partial = d.cs_partial;
+  plan->nsplit = nsplit; plan->chunks_per_split = p.chunks_per_split; plan->chunks_t = p.chunks_t; plan->slots = p.slots;
   auto kern = tc_wgrad_kernel<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -445,9 +496,33 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   return 0;
 }
 
-static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, int* nsplit) {
+static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, TcWgradPlan* plan) {
   if (d.nseg < 1 || d.nseg > TC_MAX_SEG) return -1;
-  if (d.N > 128) return tc_wgrad_launch<256>(tc, st, d, nsplit);
-  if (d.N > 64) return tc_wgrad_launch<128>(tc, st, d, nsplit);
-  return tc_wgrad_launch<64>(tc, st, d, nsplit);
+  if (d.N > 128) return tc_wgrad_launch<256>(tc, st, d, plan);
+  if (d.N > 64) return tc_wgrad_launch<128>(tc, st, d, plan);
+  return tc_wgrad_launch<64>(tc, st, d, plan);
+}
+// upper bound of cs_partial rows for a (B, T) problem: nsplit * slots <= this
+static inline long long tc_wgrad_cs_rows(int B, int T) {
+  return (long long)WN_MAX_WGRAD_SPLITS * 2 + B + 2;
+}
+
+// bias / conditioning gradient from the per-(split, slot) column sums: total[n] and per_batch[b][n]
+__global__ void tc_colsum_finish(const float* __restrict__ cs, int nsplit, int slots, int cps, int chunks_t, int B, int N,
+                                 float* __restrict__ per_batch, int ldpb, float* __restrict__ total) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float tot = 0.f;
+  for (int b = 0; b < B; ++b) {
+    // splits whose chunk range [z*cps, (z+1)*cps) intersects batch b's chunks [b*chunks_t, (b+1)*chunks_t)
+    const int z0 = (b * chunks_t) / cps, z1 = min(nsplit - 1, ((b + 1) * chunks_t - 1) / cps);
+    float sb = 0.f;
+    for (int z = z0; z <= z1; ++z) {
+      const int b_first = (z * cps) / chunks_t;
+      sb += cs[((long long)z * slots + (b - b_first)) * N + n];
+    }
+    if (per_batch) per_batch[(long long)b * ldpb + n] = sb;
+    tot += sb;
+  }
+  if (total) total[n] = tot;
 }

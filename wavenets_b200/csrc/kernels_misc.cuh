@@ -157,16 +157,20 @@ __global__ void dense_small_wgrad(const float* __restrict__ x, int ldx, const fl
   if (k < K) dW[(long long)k * N + n] = s;
   else if (db) db[n] = s;
 }
-// dx[b][k] (+)= sum_n dpre[b][n] W[k][n]
-__global__ void dense_small_dgrad(const float* __restrict__ dpre, int ldd, const float* __restrict__ W, float* __restrict__ dx, int ldx,
-                                  int B, int K, int N, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// dx[b][k] (+)= sum_n dpre[b][n] W[k][n] ; one warp per output, lanes stride over n (coalesced rows of W)
+__global__ void __launch_bounds__(128) dense_small_dgrad(const float* __restrict__ dpre, int ldd, const float* __restrict__ W, float* __restrict__ dx,
+                                                         int ldx, int B, int K, int N, int accumulate) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= B * K) return;
   const int b = i / K, k = i % K;
   float s = 0.f;
-  for (int n = 0; n < N; ++n) s = fmaf(dpre[(long long)b * ldd + n], W[(long long)k * N + n], s);
-  if (accumulate) dx[(long long)b * ldx + k] += s;
-  else dx[(long long)b * ldx + k] = s;
+  for (int n = lane; n < N; n += 32) s = fmaf(dpre[(long long)b * ldd + n], W[(long long)k * N + n], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (accumulate) dx[(long long)b * ldx + k] += s;
+    else dx[(long long)b * ldx + k] = s;
+  }
 }
 
 // ------------------------------------------------------------------ softmax-256 cross entropy (model.py:114-118,516)

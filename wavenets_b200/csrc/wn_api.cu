@@ -136,6 +136,7 @@ struct wn_handle {
   void *dpA = nullptr, *dpB = nullptr;    // pre-stack backward ping-pong (B,T,D)
   float* colpart = nullptr; int col_chunks = 0;
   float* wg_partial = nullptr; long long wg_partial_elems = 0;
+  float* cs_partial = nullptr;            // [splits*slots][max N] column-sum partials of the tcgen05 wgrad
   float* loss_partial = nullptr; int loss_parts_cap = 0;
   float* cond_act[WN_MAX_LIST + 1] = {};  // mapping activations (B, width)
   float* cond_dact = nullptr;             // scratch (B, max width)
@@ -349,6 +350,7 @@ static void layout_buffers(wn_handle* h) {
   for (auto& c : h->head) upd(c.cin, c.cout);
   h->wg_partial_elems = maxkn * WN_MAX_WGRAD_SPLITS;
   h->wg_partial = (float*)W.take((size_t)h->wg_partial_elems * 4);
+  if (bf) h->cs_partial = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT) * (size_t)rup(nmax, 4) * 4);
   h->loss_parts_cap = cdiv((long long)rows, 8) + 8;
   h->loss_partial = (float*)W.take((size_t)h->loss_parts_cap * 4);
   int maxw = h->cfg.cond_in;
@@ -679,7 +681,12 @@ struct WgradH {
   int nseg; SegH seg[WN_MAX_SEG];
   float* dst;          // [ktot][N] Keras layout in the flat grad buffer
   const float* w; float l2coef;  // optional L2 term: dst += l2coef * w
+  // column sums of G ride along: bias gradient [N] and (conditioning) per-batch sums [B][ldpb]
+  float* bias_dst = nullptr; float* per_batch = nullptr; int ldpb = 0;
 };
+
+template <class T>
+static void run_colsum(wn_handle* h, cudaStream_t st, const void* G, int ldg, int B, int Tn, int N, float* per_batch, int ldpb, float* total);
 
 template <class T>
 static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
@@ -705,14 +712,26 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
       LaunchScope ls(h, st, cls);
       wgrad_simt<<<dim3(ktiles, ntiles, nsplit), 256, 0, st>>>(a);
     }
+    if (g.bias_dst || g.per_batch) run_colsum<T>(h, st, g.G, g.ldg, g.B, g.T, g.N, g.per_batch, g.ldpb, g.bias_dst);
   } else {
     TcWgradDesc d;
     d.B = g.B; d.T = g.T; d.N = g.N; d.G = (const bf16*)g.G; d.ldg = g.ldg; d.nseg = g.nseg; d.ktot = ktot;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     d.partial = h->wg_partial;
-    LaunchScope ls(h, st, cls);
-    int r = tc_wgrad(h->tmaps, st, d, &nsplit);
-    if (r != 0) { set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+    const bool want_cs = g.bias_dst || g.per_batch;
+    d.cs_partial = want_cs ? h->cs_partial : nullptr;
+    TcWgradPlan plan{};
+    {
+      LaunchScope ls(h, st, cls);
+      int r = tc_wgrad(h->tmaps, st, d, &plan);
+      if (r != 0) { set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+    }
+    nsplit = plan.nsplit;
+    if (want_cs) {
+      LaunchScope ls(h, st, CLS_MISC);
+      tc_colsum_finish<<<cdiv(g.N, 128), 128, 0, st>>>(h->cs_partial, plan.nsplit, plan.slots, plan.chunks_per_split, plan.chunks_t, g.B, g.N,
+                                                     g.per_batch, g.ldpb, g.bias_dst);
+    }
   }
   {
     LaunchScope ls(h, st, cls);
@@ -948,8 +967,8 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     WgradH w{};
     w.B = B; w.T = Tn; w.N = R; w.G = d_o; w.ldg = R; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
     w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef;
+    w.bias_dst = G_(h, b.conv1.b_idx);
     RET(run_wgrad<T>(h, st, CLS_GEMM, w));
-    run_colsum<T>(h, st, d_o, R, B, Tn, R, nullptr, 0, G_(h, b.conv1.b_idx));
   } else {
     cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
     cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
@@ -959,8 +978,8 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       WgradH w{};
       w.B = B; w.T = Tn; w.N = S; w.G = dskip; w.ldg = S; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
       w.dst = G_(h, b.conv_skip.w_idx); w.w = P_(h, b.conv_skip.w_idx); w.l2coef = l2coef;
+      w.bias_dst = G_(h, b.conv_skip.b_idx);
       RET(run_wgrad<T>(h, st, CLS_GEMM, w));
-      run_colsum<T>(h, st, dskip, S, B, Tn, S, nullptr, 0, G_(h, b.conv_skip.b_idx));
     } else {
       cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
       cudaMemsetAsync(G_(h, b.conv_skip.b_idx), 0, h->params[b.conv_skip.b_idx].count * 4, st);
@@ -991,15 +1010,12 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     const ConvP& c = b.stack[j];
     const void* a_in = j == 0 ? x_in : h->acts[l][j - 1];
     const int a_w = j == 0 ? R : D;
-    // bias grad (+ conditioning per-batch sums for the gated conv)
-    if (j == depth - 1 && b.has_cond) {
-      run_colsum<T>(h, st, dcur, dcw, B, Tn, c.cout, h->dcb + (size_t)l * h->maxB * 2 * D, 2 * D, G_(h, c.b_idx));
-    } else {
-      run_colsum<T>(h, st, dcur, dcw, B, Tn, c.cout, nullptr, 0, G_(h, c.b_idx));
-    }
-    // weight grad: rows (k, cin) <- taps of a_in shifted by -(K-1-k)*d
+    // weight grad: rows (k, cin) <- taps of a_in shifted by -(K-1-k)*d ; the bias grad (and the
+    // conditioning per-batch sums for the gated conv) are the column sums of the same G
     {
       WgradH w{};
+      w.bias_dst = G_(h, c.b_idx);
+      if (j == depth - 1 && b.has_cond) { w.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; w.ldpb = 2 * D; }
       w.B = B; w.T = Tn; w.N = c.cout; w.G = dcur; w.ldg = dcw; w.nseg = c.K;
       for (int k = 0; k < c.K; ++k) w.seg[k] = SegH{a_in, a_w, -(c.K - 1 - k) * c.dil, c.cin};
       w.dst = G_(h, c.w_idx); w.w = P_(h, c.w_idx); w.l2coef = l2coef;
@@ -1050,7 +1066,7 @@ static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, co
     }
     {
       LaunchScope ls(h, st, CLS_MISC);
-      dense_small_dgrad<<<cdiv(B * h->Cc, 128), 128, 0, st>>>(d, n, P_(h, b.cw_idx), dcond_out, h->Cc, B, h->Cc, n, l != l0);
+      dense_small_dgrad<<<cdiv(B * h->Cc, 4), 128, 0, st>>>(d, n, P_(h, b.cw_idx), dcond_out, h->Cc, B, h->Cc, n, l != l0);
     }
   }
   if (!run_mapping) return WN_OK;
@@ -1075,7 +1091,7 @@ static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, co
     if (i > 0) {
       float* dn = (dcur == h->cond_dact) ? h->cond_dact2 : h->cond_dact;
       LaunchScope ls(h, st, CLS_MISC);
-      dense_small_dgrad<<<cdiv(B * kin, 128), 128, 0, st>>>(dcur, nn, P_(h, h->map_w[i]), dn, kin, B, kin, nn, 0);
+      dense_small_dgrad<<<cdiv(B * kin, 4), 128, 0, st>>>(dcur, nn, P_(h, h->map_w[i]), dn, kin, B, kin, nn, 0);
       dcur = dn;
     }
   }
@@ -1095,8 +1111,8 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     if (i > 0) { a_in = h->hact[i - 1]; a_w = h->head[i - 1].cout; }
     else if (c.use_skip) { a_in = h->skipsum; a_w = h->Sp; }
     else { a_in = h->xout[h->L - 1]; a_w = h->R; }
-    run_colsum<T>(h, st, dcur, dw, B, Tn, hc.cout, nullptr, 0, G_(h, hc.b_idx));
     WgradH w{};
+    w.bias_dst = G_(h, hc.b_idx);
     w.B = B; w.T = Tn; w.N = hc.cout; w.G = dcur; w.ldg = dw; w.nseg = 1; w.seg[0] = SegH{a_in, a_w, 0, hc.cin};
     w.dst = G_(h, hc.w_idx); w.w = P_(h, hc.w_idx); w.l2coef = l2coef;
     RET(run_wgrad<T>(h, st, CLS_GEMM, w));
@@ -1379,10 +1395,11 @@ extern "C" int wn_debug_wgrad(const void* a_bf16_dev, int lda, const void* g_bf1
   TcWgradDesc d{};
   d.B = B; d.T = T; d.N = N; d.G = (const bf16*)g_bf16_dev; d.ldg = ldg; d.nseg = nseg; d.ktot = nseg * K; d.partial = partial;
   for (int s = 0; s < nseg; ++s) d.seg[s] = TcSeg{(const bf16*)a_bf16_dev, lda, shifts[s], K};
-  int nsplit = 1;
-  int r = tc_wgrad(cache, st, d, &nsplit);
+  d.cs_partial = nullptr;
+  TcWgradPlan plan{};
+  int r = tc_wgrad(cache, st, d, &plan);
   if (r != 0) { cudaFree(partial); set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
-  reduce_parts<<<cdiv(kn, 256), 256, 0, st>>>(partial, nsplit, kn, out_dev, kn, nullptr, 0.f);
+  reduce_parts<<<cdiv(kn, 256), 256, 0, st>>>(partial, plan.nsplit, kn, out_dev, kn, nullptr, 0.f);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(partial);
   CK(e);
