@@ -22,6 +22,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogues.cuh"
 
 #define WN_MAX_WGRAD_SPLITS 64
 #define TC_MAX_SEG 4
@@ -268,6 +269,308 @@ template <class Epi> static int tc_conv_gemm(TmapCache& tc, cudaStream_t st, con
     case 256: return tc_conv_gemm_launch<Epi, 256, NEPI>(tc, st, d, ep);
     case 128: return tc_conv_gemm_launch<Epi, 128, NEPI>(tc, st, d, ep);
     case 64: return tc_conv_gemm_launch<Epi, 64, NEPI>(tc, st, d, ep);
+  }
+  return -2;
+}
+
+// ---------------------------------------------------------------- conv GEMM kernel, TMA-staged epilogue
+// Same mainloop; the epilogue moves every HBM tensor through shared memory (tc_epilogues.cuh):
+//   warp 3      epilogue-input producer: TMA loads of 128x32 half-panels (residual / cached z / ...)
+//   warps 4..11 epilogue: tcgen05.ld -> functor -> bf16 -> swizzled st.shared; one thread issues the
+//               TMA stores (bulk async groups, double-buffered output slots, one named barrier per step)
+struct TcEpiIo { const bf16* base; int ld; int C; int col_off; };
+struct TcStagedParams {
+  uint32_t in_mask;
+  int in_col[2];
+  int out_col[3];
+};
+
+template <int BN, int NIN, int NOUT> struct TcStagedCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PANEL = 128 * 64;                 // 128 rows x 32 bf16
+  static constexpr int IN_SLOTS = 2, OUT_SLOTS = 2;
+  static constexpr int STAGING = (IN_SLOTS * NIN + OUT_SLOTS * NOUT) * PANEL;
+  static constexpr int MAX_SMEM = 232448;
+  static constexpr int ST0 = (MAX_SMEM - 2048 - STAGING) / STAGE_BYTES;
+  static constexpr int STAGES = ST0 > 6 ? 6 : ST0;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 + 512;
+  static_assert(STAGES >= 2, "not enough shared memory for the mainloop ring");
+};
+
+template <class Epi, int BN>
+__global__ void __launch_bounds__(384, 1)
+tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                           const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
+                           const __grid_constant__ CUtensorMap tmI0, const __grid_constant__ CUtensorMap tmI1,
+                           const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+                           const TcGemmParams p, const TcStagedParams sp, const typename Epi::Params ep) {
+  constexpr int NIN = Epi::NIN, NOUT = Epi::NOUT;
+  using Cfg = TcStagedCfg<BN, NIN, NOUT>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int NEPI = 8;
+  constexpr int STEPS = Epi::kGate ? BN / 64 : BN / 32;   // 32 output columns per step
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* in_ring = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* out_ring = in_ring + Cfg::IN_SLOTS * NIN * Cfg::PANEL;
+  uint64_t* full_bar = (uint64_t*)(out_ring + Cfg::OUT_SLOTS * NOUT * Cfg::PANEL);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* in_full = tempty_bar + 2;
+  uint64_t* in_empty = in_full + Cfg::IN_SLOTS;
+  uint32_t* tmem_ptr = (uint32_t*)(in_empty + Cfg::IN_SLOTS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool use_in = NIN > 0 && sp.in_mask != 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.nseg > 1) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO0);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NEPI); }
+    for (int i = 0; i < Cfg::IN_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], NEPI); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (mainloop operands) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM, n0 = nt * BN;
+        int wk = 0;
+        for (int o = 0; o < p.n_outer; ++o) {
+          for (int s = 0; s < p.nseg; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
+            const int kseg = p.segK[s], tcoord = t0 + p.segShift[s];
+            for (int k0 = 0; k0 < kseg; k0 += Cfg::BK) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, tm, &full_bar[stage], k0, tcoord, b, o);
+              tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            wk += kseg;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    int ksteps = 0;
+    for (int s = 0; s < p.nseg; ++s) ksteps += (p.segK[s] + Cfg::BK - 1) / Cfg::BK;
+    ksteps *= p.n_outer;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp == 3) {
+    // ===================== epilogue-input producer =====================
+    if (NIN > 0 && use_in && lane == 0) {
+      int nact = 0;
+      for (int k = 0; k < NIN; ++k) nact += (sp.in_mask >> k) & 1;
+      int islot = 0; uint32_t iphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM;
+        const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
+        for (int step = 0; step < STEPS; ++step) {
+          mbar_wait(&in_empty[islot], iphase ^ 1);
+          mbar_expect_tx(&in_full[islot], (uint32_t)(nact * Cfg::PANEL));
+          uint8_t* dst = in_ring + islot * NIN * Cfg::PANEL;
+          if (sp.in_mask & 1u) tma_load_3d(dst, &tmI0, &in_full[islot], sp.in_col[0] + tile_col0 + step * 32, t0, b);
+          if (NIN > 1 && (sp.in_mask & 2u)) tma_load_3d(dst + Cfg::PANEL, &tmI1, &in_full[islot], sp.in_col[1] + tile_col0 + step * 32, t0, b);
+          if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int quarter = warp & 3;
+    const int q = e >> 2;                         // which 16-column chunk of the 32-column step
+    const int row = quarter * 32 + lane;          // TMEM lane == tile row
+    const uint32_t row_off = (uint32_t)row * 64u;
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    const uint32_t u0 = (uint32_t)(2 * q), u1 = u0 + 1;   // 16-byte units of this chunk inside the 64-byte row
+    const uint32_t off0 = row_off + ((u0 ^ sw) << 4), off1 = row_off + ((u1 ^ sw) << 4);
+    const bool store_thread = threadIdx.x == 128;
+    int as = 0; uint32_t aphase = 0;
+    int islot = 0; uint32_t iphase = 0;
+    int oslot = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM;
+      const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      TmemAccRow acc{tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16), true};
+#pragma unroll 1
+      for (int step = 0; step < STEPS; ++step) {
+        const int col0 = tile_col0 + step * 32;
+        float in[NIN > 0 ? NIN : 1][16];
+        float out[NOUT][16];
+        if (NIN > 0 && use_in) {
+          mbar_wait(&in_full[islot], iphase);
+          const uint8_t* ib = in_ring + islot * NIN * Cfg::PANEL;
+#pragma unroll
+          for (int k = 0; k < NIN; ++k) {
+            if ((sp.in_mask >> k) & 1u) {
+              const uint4 a = *reinterpret_cast<const uint4*>(ib + k * Cfg::PANEL + off0);
+              const uint4 c = *reinterpret_cast<const uint4*>(ib + k * Cfg::PANEL + off1);
+              const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                in[k][2 * j] = __uint_as_float(w[j] << 16);
+                in[k][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&in_empty[islot]);
+          if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+        }
+        Epi::chunk(ep, acc, b, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out);
+        uint8_t* ob = out_ring + oslot * NOUT * Cfg::PANEL;
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+          uint4 a, c;
+          a.x = pack_bf16x2(out[k][0], out[k][1]); a.y = pack_bf16x2(out[k][2], out[k][3]);
+          a.z = pack_bf16x2(out[k][4], out[k][5]); a.w = pack_bf16x2(out[k][6], out[k][7]);
+          c.x = pack_bf16x2(out[k][8], out[k][9]); c.y = pack_bf16x2(out[k][10], out[k][11]);
+          c.z = pack_bf16x2(out[k][12], out[k][13]); c.w = pack_bf16x2(out[k][14], out[k][15]);
+          *reinterpret_cast<uint4*>(ob + k * Cfg::PANEL + off0) = a;
+          *reinterpret_cast<uint4*>(ob + k * Cfg::PANEL + off1) = c;
+        }
+        fence_proxy_async();
+        // all stores of the previous step's slot partner must have been read before anyone reuses it
+        if (store_thread) bulk_wait_group_read<0>();
+        named_bar_sync(1, NEPI * 32);
+        if (store_thread) {
+          tma_store_3d(ob, &tmO0, sp.out_col[0] + col0, t0, b);
+          if (NOUT > 1) tma_store_3d(ob + Cfg::PANEL, &tmO1, sp.out_col[1] + col0, t0, b);
+          if (NOUT > 2) tma_store_3d(ob + 2 * Cfg::PANEL, &tmO2, sp.out_col[2] + col0, t0, b);
+          bulk_commit_group();
+        }
+        oslot ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (store_thread) bulk_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// half-panel map over a (B,T,ld) bf16 tensor restricted to C columns: box (32 cols, 128 rows, 1), 64B swizzle
+static inline const CUtensorMap* tc_panel_map(TmapCache& tc, const TcEpiIo& io, int T, int B) {
+  uint64_t dims[3] = {(uint64_t)io.C, (uint64_t)T, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)io.ld * 2, (uint64_t)T * io.ld * 2};
+  uint32_t box[3] = {32, 128, 1};
+  return tc.get(io.base, 3, dims, str, box, 64);
+}
+
+template <class Epi, int BN>
+static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep, const TcEpiIo* ins,
+                                      uint32_t in_mask, const TcEpiIo* outs) {
+  using Cfg = TcStagedCfg<BN, Epi::NIN, Epi::NOUT>;
+  const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
+  for (int s = 0; s < d.nseg; ++s) {
+    ma[s] = tc_act_map(tc, d.seg[s].A, d.seg[s].lda, d.seg[s].K, d.T, d.B, s == 0 ? d.n_outer : 1, d.outer_stride, 128);
+    if (!ma[s]) return -10;
+  }
+  for (int s = d.nseg; s < TC_MAX_SEG; ++s) ma[s] = ma[0];
+  uint64_t wd[2] = {(uint64_t)d.ktot, (uint64_t)d.N16};
+  uint64_t ws[1] = {(uint64_t)d.ktot * 2};
+  uint32_t wb[2] = {64, (uint32_t)BN};
+  const CUtensorMap* mw = tc.get(d.W, 2, wd, ws, wb);
+  if (!mw) return -11;
+  TcStagedParams sp{};
+  sp.in_mask = in_mask;
+  const CUtensorMap* mo[3] = {nullptr, nullptr, nullptr};
+  const CUtensorMap* mi[2] = {nullptr, nullptr};
+  for (int k = 0; k < Epi::NOUT; ++k) {
+    mo[k] = tc_panel_map(tc, outs[k], d.T, d.B);
+    if (!mo[k]) return -14;
+    sp.out_col[k] = outs[k].col_off;
+  }
+  for (int k = Epi::NOUT; k < 3; ++k) mo[k] = mo[0];
+  for (int k = 0; k < Epi::NIN; ++k) {
+    if ((in_mask >> k) & 1u) {
+      mi[k] = tc_panel_map(tc, ins[k], d.T, d.B);
+      if (!mi[k]) return -15;
+      sp.in_col[k] = ins[k].col_off;
+    }
+  }
+  for (int k = 0; k < 2; ++k) if (!mi[k]) mi[k] = mo[0];
+  TcGemmParams p{};
+  p.B = d.B; p.T = d.T; p.tiles_t = (d.T + 127) / 128; p.n_tiles = d.N16 / BN; p.num_tiles = d.B * p.tiles_t * p.n_tiles;
+  p.nseg = d.nseg; p.n_outer = d.n_outer > 0 ? d.n_outer : 1;
+  for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
+  auto kern = tc_conv_gemm_staged_kernel<Epi, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  const int grid = p.num_tiles < tc_num_sms() ? p.num_tiles : tc_num_sms();
+  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(*ma[0], *ma[1], *ma[2], *ma[3], *mw, *mi[0], *mi[1], *mo[0], *mo[1], *mo[2], p, sp, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "staged conv_gemm launch: %s", cudaGetErrorString(e)); return -13; }
+  return 0;
+}
+
+template <class Epi>
+static int tc_conv_gemm_staged(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep, const TcEpiIo* ins, uint32_t in_mask,
+                               const TcEpiIo* outs) {
+  int tile = d.tileN;
+  if (tile == 0) tile = d.N16 % 256 == 0 ? 256 : (d.N16 % 128 == 0 ? 128 : 64);
+  if (d.N16 % tile != 0 || d.nseg < 1 || d.nseg > TC_MAX_SEG) { snprintf(g_tc_err, sizeof(g_tc_err), "bad tiling N16=%d tile=%d nseg=%d", d.N16, tile, d.nseg); return -1; }
+  switch (tile) {
+    case 256: return tc_conv_gemm_staged_launch<Epi, 256>(tc, st, d, ep, ins, in_mask, outs);
+    case 128: return tc_conv_gemm_staged_launch<Epi, 128>(tc, st, d, ep, ins, in_mask, outs);
+    case 64: return tc_conv_gemm_staged_launch<Epi, 64>(tc, st, d, ep, ins, in_mask, outs);
   }
   return -2;
 }

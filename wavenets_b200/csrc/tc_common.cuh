@@ -77,6 +77,23 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// smem -> global tile store (bulk async group); rows / columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
@@ -167,8 +184,9 @@ struct TmapKey {
   uint64_t d[4], s[3];
   uint32_t box[4];
   uint32_t rank;
+  uint32_t swz;
   bool operator==(const TmapKey& o) const {
-    if (base != o.base || rank != o.rank) return false;
+    if (base != o.base || rank != o.rank || swz != o.swz) return false;
     for (int i = 0; i < 4; ++i) if (d[i] != o.d[i] || box[i] != o.box[i]) return false;
     for (int i = 0; i < 3; ++i) if (s[i] != o.s[i]) return false;
     return true;
@@ -180,7 +198,7 @@ struct TmapKeyHash {
     for (int i = 0; i < 4; ++i) h = (h ^ (k.d[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2))) * 1099511628211ull;
     for (int i = 0; i < 3; ++i) h = (h ^ k.s[i]) * 1099511628211ull;
     for (int i = 0; i < 4; ++i) h = (h ^ k.box[i]) * 1099511628211ull;
-    return (size_t)(h ^ k.rank);
+    return (size_t)(h ^ k.rank ^ ((uint64_t)k.swz << 8));
   }
 };
 // Encoding a tensor map costs microseconds on the host; a training step reuses the same few
@@ -188,9 +206,10 @@ struct TmapKeyHash {
 struct TmapCache {
   std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> maps;
   // bf16 tensor, rank 2..4, dims innermost first, strides in BYTES for dims 1..rank-1, 128B swizzle, zero OOB fill
-  const CUtensorMap* get(const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  // swizzle_bytes: 128 (inner box extent 128 B) or 64 (inner box extent 64 B)
+  const CUtensorMap* get(const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box, int swizzle_bytes = 128) {
     TmapKey k{};
-    k.base = base; k.rank = (uint32_t)rank;
+    k.base = base; k.rank = (uint32_t)rank; k.swz = (uint32_t)swizzle_bytes;
     for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.box[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides[i];
     auto it = maps.find(k);
@@ -203,7 +222,8 @@ struct TmapCache {
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_tmap_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
                                (const cuuint64_t*)strides, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r, rank,
                (unsigned long long)k.d[0], (unsigned long long)k.d[1], (unsigned long long)k.d[2], (unsigned long long)k.d[3], box[0], box[1],

@@ -1,0 +1,141 @@
+// tc_epilogues.cuh — fused epilogues of the tcgen05 conv GEMM, TMA-staged variant.
+//
+// The accumulator lives in TMEM with one ROW per thread, but HBM wants whole rows per warp.
+// So every epilogue tensor moves through shared memory as half-panels of 128 rows x 32 bf16
+// columns (64-byte rows, 64B swizzle): inputs (residual, cached pre-activations, ...) arrive by
+// TMA load, outputs leave by TMA store, and rows / columns outside the tensor are clipped by
+// the tensor map (no per-thread bounds logic).  A functor only sees 16 columns of one row:
+//
+//   Epi::chunk(params, acc, b, acc_col, half, col, in_mask, in, out)
+//     acc.load16(c, v)  accumulator columns [c, c+16) of this row, relative to the CTA tile
+//     acc_col           first accumulator column of this chunk (gate: filter half; gate half at +half)
+//     col               first output column of this chunk in the output tensors' own numbering
+//     in[k][16]         staged inputs (fp32), valid when bit k of in_mask is set
+//     out[k][16]        results (fp32; the kernel rounds to bf16 and stages them for the TMA store)
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ void ld_bias16(const float* __restrict__ p, float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+  }
+}
+
+// out = act(acc + bias[n] + cbias[b][n]) + res      (layers.py:66-74,213,222-223; model.py:105-119,236)
+template <bool FAST> struct TcEpiBiasActRes {
+  static constexpr int NIN = 1, NOUT = 1;
+  static constexpr bool kGate = false;
+  struct Params { const float* bias; const float* cbias; int ldcb; int act; int N; };
+  template <class Acc>
+  static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
+                                               const float (*in)[16], float (*out)[16]) {
+    float v[16];
+    acc.load16(acc_col, v);
+    if (col + 16 <= p.N) {
+      if (p.bias) {
+        float t[16];
+        ld_bias16(p.bias + col, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+      }
+      if (p.cbias) {
+        float t[16];
+        ld_bias16(p.cbias + (long long)b * p.ldcb + col, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+      }
+    }
+    if (p.act != ACT_LINEAR) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = wn_act<FAST>(p.act, v[i]);
+    }
+    if (in_mask & 1u) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += in[0][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[0][i] = v[i];
+  }
+};
+
+// gated activation (layers.py:203-210): tile = [filter half | gate half]; outputs z_f, z_s, g
+template <bool FAST> struct TcEpiGate {
+  static constexpr int NIN = 0, NOUT = 3;
+  static constexpr bool kGate = true;
+  struct Params { const float* bias; const float* cbias; int D; };
+  template <class Acc>
+  static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
+                                               const float (*in)[16], float (*out)[16]) {
+    float f[16], s[16];
+    acc.load16(acc_col, f);
+    acc.load16(half + acc_col, s);
+    if (col + 16 <= p.D) {
+      float t[16];
+      ld_bias16(p.bias + col, t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] += t[i];
+      ld_bias16(p.bias + p.D + col, t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s[i] += t[i];
+      if (p.cbias) {
+        const float* cb = p.cbias + (long long)b * 2 * p.D;
+        ld_bias16(cb + col, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] += t[i];
+        ld_bias16(cb + p.D + col, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[i] += t[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      out[0][i] = f[i];
+      out[1][i] = s[i];
+      out[2][i] = wn_tanh<FAST>(f[i]) * wn_sigmoid<FAST>(s[i]);
+    }
+  }
+};
+
+// adjoint of the gate: acc = dg; inputs cached z_f, z_s; outputs dz_f, dz_s
+template <bool FAST> struct TcEpiGateBwd {
+  static constexpr int NIN = 2, NOUT = 2;
+  static constexpr bool kGate = false;
+  struct Params { int D; };
+  template <class Acc>
+  static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
+                                               const float (*in)[16], float (*out)[16]) {
+    float dg[16];
+    acc.load16(acc_col, dg);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float th = wn_tanh<FAST>(in[0][i]), sg = wn_sigmoid<FAST>(in[1][i]);
+      out[0][i] = dg[i] * sg * (1.0f - th * th);
+      out[1][i] = dg[i] * th * sg * (1.0f - sg);
+    }
+  }
+};
+
+// dgrad: out = (acc + add) * act'(y)    (residual pass-through; activation adjoint from its cached output)
+struct TcEpiActBwd {
+  static constexpr int NIN = 2, NOUT = 1;
+  static constexpr bool kGate = false;
+  struct Params { int act; };
+  template <class Acc>
+  static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
+                                               const float (*in)[16], float (*out)[16]) {
+    float v[16];
+    acc.load16(acc_col, v);
+    if (in_mask & 1u) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += in[0][i];
+    }
+    if (in_mask & 2u) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= wn_act_grad_from_out(p.act, in[1][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[0][i] = v[i];
+  }
+};

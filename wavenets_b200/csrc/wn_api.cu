@@ -655,6 +655,44 @@ struct GemmH {
   const bf16* W16 = nullptr; int ktot16 = 0; int N16 = 0; int tile16 = 0;  // bf16: [N16][ktot16]
 };
 
+// bf16 tier: map the generic epilogue description onto the TMA-staged tcgen05 kernel (tc_epilogues.cuh);
+// the fp32-output head GEMM (logits) and shapes the half-panel maps cannot express use the direct-store kernel.
+static inline bool tc_io_ok(const void* p, int ld, int n) { return ((uintptr_t)p & 15) == 0 && ld % 8 == 0 && n % 16 == 0; }
+
+template <class Epi>
+static int tc_dispatch(wn_handle* h, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep) { return tc_conv_gemm<Epi>(h->tmaps, st, d, ep); }
+template <>
+int tc_dispatch<EpiBiasActRes<bf16, bf16, true>>(wn_handle* h, cudaStream_t st, const TcGemmDesc& d, const EpiBiasActRes<bf16, bf16, true>::Params& ep) {
+  if (!tc_io_ok(ep.out, ep.ldo, ep.N) || (ep.res && !tc_io_ok(ep.res, ep.ldr, ep.N))) return tc_conv_gemm<EpiBiasActRes<bf16, bf16, true>>(h->tmaps, st, d, ep);
+  TcEpiBiasActRes<true>::Params q{ep.bias, ep.cbias, ep.ldcb, ep.act, ep.N};
+  TcEpiIo in[2] = {{ep.res, ep.ldr, ep.N, 0}, {nullptr, 0, 0, 0}};
+  TcEpiIo out[3] = {{ep.out, ep.ldo, ep.N, 0}, {}, {}};
+  return tc_conv_gemm_staged<TcEpiBiasActRes<true>>(h->tmaps, st, d, q, in, ep.res ? 1u : 0u, out);
+}
+template <>
+int tc_dispatch<EpiGate<bf16, true>>(wn_handle* h, cudaStream_t st, const TcGemmDesc& d, const EpiGate<bf16, true>::Params& ep) {
+  TcEpiGate<true>::Params q{ep.bias, ep.cbias, ep.D};
+  TcEpiIo out[3] = {{ep.z, 2 * ep.D, ep.D, 0}, {ep.z + ep.D, 2 * ep.D, ep.D, 0}, {ep.g, ep.ldg, ep.D, 0}};
+  return tc_conv_gemm_staged<TcEpiGate<true>>(h->tmaps, st, d, q, nullptr, 0u, out);
+}
+template <>
+int tc_dispatch<EpiGateBwd<bf16, true>>(wn_handle* h, cudaStream_t st, const TcGemmDesc& d, const EpiGateBwd<bf16, true>::Params& ep) {
+  TcEpiGateBwd<true>::Params q{ep.D};
+  TcEpiIo in[2] = {{ep.z, 2 * ep.D, ep.D, 0}, {ep.z + ep.D, 2 * ep.D, ep.D, 0}};
+  TcEpiIo out[3] = {{ep.dz, 2 * ep.D, ep.D, 0}, {ep.dz + ep.D, 2 * ep.D, ep.D, 0}, {}};
+  return tc_conv_gemm_staged<TcEpiGateBwd<true>>(h->tmaps, st, d, q, in, 3u, out);
+}
+template <>
+int tc_dispatch<EpiActBwd<bf16, bf16>>(wn_handle* h, cudaStream_t st, const TcGemmDesc& d, const EpiActBwd<bf16, bf16>::Params& ep) {
+  const bool use_y = ep.y && ep.act != ACT_LINEAR;
+  if (!tc_io_ok(ep.out, ep.ldo, ep.N) || (ep.add && !tc_io_ok(ep.add, ep.lda, ep.N)) || (use_y && !tc_io_ok(ep.y, ep.ldy, ep.N)))
+    return tc_conv_gemm<EpiActBwd<bf16, bf16>>(h->tmaps, st, d, ep);
+  TcEpiActBwd::Params q{ep.act};
+  TcEpiIo in[2] = {{ep.add, ep.lda, ep.N, 0}, {ep.y, ep.ldy, ep.N, 0}};
+  TcEpiIo out[3] = {{ep.out, ep.ldo, ep.N, 0}, {}, {}};
+  return tc_conv_gemm_staged<TcEpiActBwd>(h->tmaps, st, d, q, in, (ep.add ? 1u : 0u) | (use_y ? 2u : 0u), out);
+}
+
 template <class T, class Epi>
 static int run_conv_gemm(wn_handle* h, cudaStream_t st, int cls, const GemmH& g, const typename Epi::Params& ep) {
   LaunchScope ls(h, st, cls);
@@ -670,7 +708,7 @@ static int run_conv_gemm(wn_handle* h, cudaStream_t st, int cls, const GemmH& g,
     d.B = g.B; d.T = g.T; d.nseg = g.nseg; d.n_outer = g.n_outer; d.outer_stride = g.outer_stride;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     d.W = g.W16; d.ktot = g.ktot16; d.N16 = g.N16; d.tileN = g.tile16;
-    int r = tc_conv_gemm<Epi>(h->tmaps, st, d, ep);
+    int r = tc_dispatch<Epi>(h, st, d, ep);
     if (r != 0) { set_err("tcgen05 conv_gemm launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
     return WN_OK;
   }
