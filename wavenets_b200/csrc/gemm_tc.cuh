@@ -777,7 +777,7 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
   p.partial = d.partial;
   const int ntiles = (d.N + BN - 1) / BN;
-  int nsplit = (tc_num_sms() + mtiles * ntiles - 1) / (mtiles * ntiles);
+  int nsplit = tc_num_sms() / (mtiles * ntiles);   // one wave: never more CTAs than SMs
   if (nsplit < 1) nsplit = 1;
   if (nsplit > WN_MAX_WGRAD_SPLITS) nsplit = WN_MAX_WGRAD_SPLITS;
   if (nsplit > p.total_chunks) nsplit = p.total_chunks;
@@ -810,22 +810,68 @@ static inline long long tc_wgrad_cs_rows(int B, int T) {
   return (long long)WN_MAX_WGRAD_SPLITS * 2 + B + 2;
 }
 
-// bias / conditioning gradient from the per-(split, slot) column sums: total[n] and per_batch[b][n]
-__global__ void tc_colsum_finish(const float* __restrict__ cs, int nsplit, int slots, int cps, int chunks_t, int B, int N,
-                                 float* __restrict__ per_batch, int ldpb, float* __restrict__ total) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float tot = 0.f;
-  for (int b = 0; b < B; ++b) {
-    // splits whose chunk range [z*cps, (z+1)*cps) intersects batch b's chunks [b*chunks_t, (b+1)*chunks_t)
-    const int z0 = (b * chunks_t) / cps, z1 = min(nsplit - 1, ((b + 1) * chunks_t - 1) / cps);
-    float sb = 0.f;
-    for (int z = z0; z <= z1; ++z) {
-      const int b_first = (z * cps) / chunks_t;
-      sb += cs[((long long)z * slots + (b - b_first)) * N + n];
+// Second stage of the wgrad: deterministic sum of the split partials (no atomics), written in
+// Keras layout.  The N output columns may belong to two variables (conv1 | conv_skip share one
+// launch): columns [0,N0) -> dst0 [ktot][N0], columns [N0,N) -> dst1 [ktot][N-N0].  Optional
+// L2 term dst += l2coef * w.  Blocks past the weight part finish the column sums of G:
+// bias gradients (total over all rows) and the conditioning per-batch sums.
+struct TcWgradFinish {
+  const float* partial; int nsplit; int ktot; int N; int N0;
+  float* dst0; float* dst1; const float* w0; const float* w1; float l2coef;
+  const float* cs; int slots; int cps; int chunks_t; int B;
+  float* bias0; float* bias1; float* per_batch; int ldpb;
+  int wblocks;   // blocks of the weight part
+};
+__global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
+  if ((int)blockIdx.x < f.wblocks) {
+    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long n_all = (long long)f.ktot * f.N;
+    if (j >= n_all) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float* p = f.partial + j;
+    int i = 0;
+    for (; i + 3 < f.nsplit; i += 4) {
+      s0 += p[(long long)i * n_all]; s1 += p[(long long)(i + 1) * n_all];
+      s2 += p[(long long)(i + 2) * n_all]; s3 += p[(long long)(i + 3) * n_all];
     }
-    if (per_batch) per_batch[(long long)b * ldpb + n] = sb;
-    tot += sb;
+    for (; i < f.nsplit; ++i) s0 += p[(long long)i * n_all];
+    float s = (s0 + s1) + (s2 + s3);
+    const int k = (int)(j / f.N), n = (int)(j % f.N);
+    if (n < f.N0) {
+      const long long o = (long long)k * f.N0 + n;
+      if (f.w0) s = fmaf(f.l2coef, f.w0[o], s);
+      f.dst0[o] = s;
+    } else {
+      const long long o = (long long)k * (f.N - f.N0) + (n - f.N0);
+      if (f.w1) s = fmaf(f.l2coef, f.w1[o], s);
+      f.dst1[o] = s;
+    }
+    return;
   }
-  if (total) total[n] = tot;
+  // ---- column sums: 32 columns x 8 batch lanes per block
+  __shared__ float red[8][33];
+  const int nl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int n = ((int)blockIdx.x - f.wblocks) * 32 + nl;
+  float tot = 0.f;
+  if (n < f.N) {
+    for (int b = bl; b < f.B; b += 8) {
+      const int z0 = (b * f.chunks_t) / f.cps, z1 = min(f.nsplit - 1, ((b + 1) * f.chunks_t - 1) / f.cps);
+      float sb = 0.f;
+      for (int z = z0; z <= z1; ++z) {
+        const int b_first = (z * f.cps) / f.chunks_t;
+        sb += f.cs[((long long)z * f.slots + (b - b_first)) * f.N + n];
+      }
+      if (f.per_batch) f.per_batch[(long long)b * f.ldpb + n] = sb;
+      tot += sb;
+    }
+  }
+  red[bl][nl] = tot;
+  __syncthreads();
+  if (bl == 0 && n < f.N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][nl];
+    if (n < f.N0) { if (f.bias0) f.bias0[n] = t; }
+    else if (f.bias1) f.bias1[n - f.N0] = t;
+  }
 }

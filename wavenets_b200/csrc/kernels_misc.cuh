@@ -26,7 +26,7 @@ __global__ void input_conv_fwd(const float* __restrict__ x, int ldx, const float
 
 // stage 1 of input conv wgrad: partial[(chunk)][k][c] = sum_{t in chunk} dh[b,t,c] * x[b,t-(K-1-k)], k==K => bias
 template <class T>
-__global__ void input_conv_bwd_stage1(const float* __restrict__ x, int ldx, const T* __restrict__ dh, float* __restrict__ partial,
+__global__ void input_conv_bwd_stage1(const float* __restrict__ x, int ldx, const T* __restrict__ dh, int lddh, float* __restrict__ partial,
                                       int B, int Tn, int R, int K, int rows_per_chunk) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= R) return;
@@ -34,7 +34,7 @@ __global__ void input_conv_bwd_stage1(const float* __restrict__ x, int ldx, cons
   const int t0 = blockIdx.y * rows_per_chunk, t1 = min(Tn, t0 + rows_per_chunk);
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int t = t0; t < t1; ++t) {
-    const float d = to_f(dh[((long long)b * Tn + t) * R + c]);
+    const float d = to_f(dh[((long long)b * Tn + t) * lddh + c]);
     for (int k = 0; k < K; ++k) {
       const int ts = t - (K - 1 - k);
       if (ts >= 0) acc[k] = fmaf(d, x[(long long)b * ldx + ts], acc[k]);

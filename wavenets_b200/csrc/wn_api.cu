@@ -132,6 +132,7 @@ struct wn_handle {
   void *dhA = nullptr, *dhB = nullptr;    // head backward ping-pong (width max head)
   void* dskip = nullptr;
   void *dxA = nullptr, *dxB = nullptr, *dotmp = nullptr;
+  void *dcatA = nullptr, *dcatB = nullptr;   // bf16 tier: [d x_out (R) | d skip (S)] side by side, ping-pong
   void* dz = nullptr;
   void *dpA = nullptr, *dpB = nullptr;    // pre-stack backward ping-pong (B,T,D)
   float* colpart = nullptr; int col_chunks = 0;
@@ -327,6 +328,10 @@ static void layout_buffers(wn_handle* h) {
   h->dxA = W.take(rows * R * es);
   h->dxB = W.take(rows * R * es);
   h->dotmp = W.take(rows * R * es);
+  if (bf && !h->alias_skip && h->cfg.use_skip) {
+    h->dcatA = W.take(rows * (size_t)(R + h->S) * es);
+    h->dcatB = W.take(rows * (size_t)(R + h->S) * es);
+  }
   h->dz = W.take(rows * 2 * D * es);
   h->dpA = W.take(rows * D * es);
   h->dpB = W.take(rows * D * es);
@@ -721,6 +726,8 @@ struct WgradH {
   const float* w; float l2coef;  // optional L2 term: dst += l2coef * w
   // column sums of G ride along: bias gradient [N] and (conditioning) per-batch sums [B][ldpb]
   float* bias_dst = nullptr; float* per_batch = nullptr; int ldpb = 0;
+  // bf16 tier only: columns [N0, N) belong to a second variable (conv1 | conv_skip in one launch)
+  int N0 = 0; float* dst1 = nullptr; const float* w1 = nullptr; float* bias1 = nullptr;
 };
 
 template <class T>
@@ -756,7 +763,7 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     d.B = g.B; d.T = g.T; d.N = g.N; d.G = (const bf16*)g.G; d.ldg = g.ldg; d.nseg = g.nseg; d.ktot = ktot;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     d.partial = h->wg_partial;
-    const bool want_cs = g.bias_dst || g.per_batch;
+    const bool want_cs = g.bias_dst || g.per_batch || g.bias1;
     d.cs_partial = want_cs ? h->cs_partial : nullptr;
     TcWgradPlan plan{};
     {
@@ -764,12 +771,16 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
       int r = tc_wgrad(h->tmaps, st, d, &plan);
       if (r != 0) { set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
     }
-    nsplit = plan.nsplit;
-    if (want_cs) {
-      LaunchScope ls(h, st, CLS_MISC);
-      tc_colsum_finish<<<cdiv(g.N, 128), 128, 0, st>>>(h->cs_partial, plan.nsplit, plan.slots, plan.chunks_per_split, plan.chunks_t, g.B, g.N,
-                                                     g.per_batch, g.ldpb, g.bias_dst);
-    }
+    TcWgradFinish f{};
+    f.partial = h->wg_partial; f.nsplit = plan.nsplit; f.ktot = ktot; f.N = g.N; f.N0 = g.dst1 ? g.N0 : g.N;
+    f.dst0 = g.dst; f.dst1 = g.dst1; f.l2coef = g.l2coef;
+    f.w0 = g.l2coef != 0.f ? g.w : nullptr; f.w1 = g.l2coef != 0.f ? g.w1 : nullptr;
+    f.cs = h->cs_partial; f.slots = plan.slots; f.cps = plan.chunks_per_split; f.chunks_t = plan.chunks_t; f.B = g.B;
+    f.bias0 = g.bias_dst; f.bias1 = g.bias1; f.per_batch = g.per_batch; f.ldpb = g.ldpb;
+    f.wblocks = cdiv((long long)ktot * g.N, 256);
+    LaunchScope ls(h, st, cls);
+    tc_wgrad_finish<<<f.wblocks + (want_cs ? cdiv(g.N, 32) : 0), 256, 0, st>>>(f);
+    return WN_OK;
   }
   {
     LaunchScope ls(h, st, cls);
@@ -981,29 +992,41 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
 // adjoint of block_forward.  dxout / dskip may be null (zero).  Writes dx_in (if non-null) and
 // this block's parameter gradients.  dcb row l gets per-batch sums of dz when conditioned.
 template <class T>
-static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in, const void* dxout, const void* dskip, void* dx_in, int B, int Tn,
-                          float l2coef) {
+static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in, const void* dxout, int ldxo, const void* dskip, int ldsk,
+                          void* dx_in, int ldxi, int B, int Tn, float l2coef) {
   BlockP& b = h->blocks[l];
   const int depth = (int)b.stack.size();
   const size_t rows_cap = (size_t)h->maxB * h->maxT;
   const long long nR = (long long)B * Tn * h->R;
   const T* g_l = (const T*)h->G_all + (size_t)l * rows_cap * h->D;
   const int R = h->R, D = h->D, S = h->S;
+  // bf16 tier: d x_out and d skip live side by side in one (rows, R+S) buffer -> conv1 and conv_skip
+  // share one wgrad launch (g is read once) and the dg GEMM reads a single K = R+S segment
+  const bool cat = sizeof(T) == 2 && b.has_skip && dxout && dskip && ldxo == ldsk && (const T*)dskip == (const T*)dxout + R;
   // ---- d o  (gradient wrt conv1 output)
   const void* d_o = dxout;
+  int ld_o = ldxo;
   if (h->alias_skip) {
     if (dxout && dskip) {
       LaunchScope ls(h, st, CLS_MISC);
       add2_kernel<T><<<cdiv(nR, 256), 256, 0, st>>>((const T*)dxout, (const T*)dskip, (T*)h->dotmp, nR);
       d_o = h->dotmp;
+      ld_o = R;
     } else if (dskip) {
       d_o = dskip;
+      ld_o = ldsk;
     }
   }
   // ---- conv1 / conv_skip weight + bias grads
-  if (d_o) {
+  if (cat) {
     WgradH w{};
-    w.B = B; w.T = Tn; w.N = R; w.G = d_o; w.ldg = R; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
+    w.B = B; w.T = Tn; w.N = R + S; w.G = dxout; w.ldg = ldxo; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
+    w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef; w.bias_dst = G_(h, b.conv1.b_idx);
+    w.N0 = R; w.dst1 = G_(h, b.conv_skip.w_idx); w.w1 = P_(h, b.conv_skip.w_idx); w.bias1 = G_(h, b.conv_skip.b_idx);
+    RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+  } else if (d_o) {
+    WgradH w{};
+    w.B = B; w.T = Tn; w.N = R; w.G = d_o; w.ldg = ld_o; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
     w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef;
     w.bias_dst = G_(h, b.conv1.b_idx);
     RET(run_wgrad<T>(h, st, CLS_GEMM, w));
@@ -1011,10 +1034,10 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
     cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
   }
-  if (b.has_skip) {
+  if (b.has_skip && !cat) {
     if (dskip) {
       WgradH w{};
-      w.B = B; w.T = Tn; w.N = S; w.G = dskip; w.ldg = S; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
+      w.B = B; w.T = Tn; w.N = S; w.G = dskip; w.ldg = ldsk; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
       w.dst = G_(h, b.conv_skip.w_idx); w.w = P_(h, b.conv_skip.w_idx); w.l2coef = l2coef;
       w.bias_dst = G_(h, b.conv_skip.b_idx);
       RET(run_wgrad<T>(h, st, CLS_GEMM, w));
@@ -1031,9 +1054,13 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     const bool use_o = d_o != nullptr;
     const bool use_s = b.has_skip && dskip != nullptr;
     if (!use_o && !use_s) { set_err("block_backward: no upstream gradient"); return WN_ERR_STATE; }
-    if (use_o) g.seg[g.nseg++] = SegH{d_o, R, 0, R};
-    else koff = R;
-    if (use_s) g.seg[g.nseg++] = SegH{dskip, S, 0, S};
+    if (cat) {
+      g.seg[g.nseg++] = SegH{dxout, ldxo, 0, R + S};
+    } else {
+      if (use_o) g.seg[g.nseg++] = SegH{d_o, ld_o, 0, R};
+      else koff = R;
+      if (use_s) g.seg[g.nseg++] = SegH{dskip, ldsk, 0, S};
+    }
     const int rs = R + (b.has_skip ? S : 0);
     g.W32 = b.Wdg ? b.Wdg + (size_t)koff * b.Dpad : nullptr; g.Npad = b.Dpad;
     g.W16 = b.Wdg16 ? b.Wdg16 + koff : nullptr; g.ktot16 = rup(rs, 64); g.N16 = b.Dpad; g.tile16 = 0;
@@ -1076,8 +1103,8 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         dcur = dst;
         dcw = D;
       } else {
-        ep.out = (T*)dx_in; ep.ldo = R;
-        ep.add = (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr; ep.lda = R;
+        ep.out = (T*)dx_in; ep.ldo = ldxi;
+        ep.add = (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr; ep.lda = ldxo;
         ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(R);
         RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
       }
@@ -1139,6 +1166,8 @@ static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, co
 template <class T>
 static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx, const float* cond_in, int B, int Tn, float l2coef) {
   const wn_config& c = h->cfg;
+  const bool cat = sizeof(T) == 2 && h->dcatA != nullptr;
+  const int ldc = h->R + h->S;
   // ---- head
   const void* dcur = h->dlogits;
   int dw = h->ldd;
@@ -1164,6 +1193,9 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     if (i > 0) {
       dst = (dcur == h->dhA) ? h->dhB : h->dhA;
       ep.out = (T*)dst; ep.ldo = hc.cin; ep.y = (const T*)h->hact[i - 1]; ep.ldy = hc.cin; ep.act = c.activation; ep.vec = vec_ok<T>(hc.cin);
+    } else if (cat) {
+      dst = (T*)h->dcatA + h->R;
+      ep.out = (T*)dst; ep.ldo = ldc; ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(ldc);
     } else {
       dst = c.use_skip ? h->dskip : h->dxA;
       ep.out = (T*)dst; ep.ldo = hc.cin; ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(hc.cin);
@@ -1173,20 +1205,39 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     dw = hc.cin;
   }
   // ---- blocks
-  const void* dskip = c.use_skip ? h->dskip : nullptr;
-  const void* dxout = c.use_skip ? nullptr : h->dxA;
-  for (int l = h->L - 1; l >= 0; --l) {
-    const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
-    void* dx_in = (dxout == h->dxA) ? h->dxB : h->dxA;
-    RET(block_backward<T>(h, st, l, x_in, dxout, dskip, dx_in, B, Tn, l2coef));
-    dxout = dx_in;
+  const void* dxout;
+  int ld_dx;
+  if (cat) {
+    // d skip is the same for every block (model.py:236): keep a copy beside each d x_out ping-pong buffer
+    CK(cudaMemcpy2DAsync((T*)h->dcatB + h->R, (size_t)ldc * sizeof(T), (const T*)h->dcatA + h->R, (size_t)ldc * sizeof(T), (size_t)h->S * sizeof(T),
+                         (size_t)B * Tn, cudaMemcpyDeviceToDevice, st));
+    const void* cur = nullptr;          // buffer holding d x_out of the block being processed
+    void* nxt = h->dcatB;
+    for (int l = h->L - 1; l >= 0; --l) {
+      const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
+      const void* dsk = cur ? (const void*)((const T*)cur + h->R) : (const void*)((const T*)h->dcatA + h->R);
+      RET(block_backward<T>(h, st, l, x_in, cur, ldc, dsk, ldc, nxt, ldc, B, Tn, l2coef));
+      cur = nxt;
+      nxt = (nxt == h->dcatB) ? h->dcatA : h->dcatB;
+    }
+    dxout = cur; ld_dx = ldc;
+  } else {
+    const void* dskip = c.use_skip ? h->dskip : nullptr;
+    dxout = c.use_skip ? nullptr : h->dxA;
+    for (int l = h->L - 1; l >= 0; --l) {
+      const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
+      void* dx_in = (dxout == h->dxA) ? h->dxB : h->dxA;
+      RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef));
+      dxout = dx_in;
+    }
+    ld_dx = h->R;
   }
   // ---- input conv (model.py:84-88): dW[k][c], db[c]
   {
     const int chunks = cdiv(Tn, 256);
     {
       LaunchScope ls(h, st, CLS_MISC);
-      input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, h->colpart, B, Tn, h->R, h->K, 256);
+      input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 256);
     }
     const long long kr = (long long)h->K * h->R;
     {
@@ -1371,7 +1422,7 @@ static int layer_bwd_entry(wn_handle* h, int l, const float* dxo, const float* d
     dsk_t = h->dskip;
   }
   const void* xin = l == 0 ? h->layer_in : h->xout[l - 1];
-  RET(block_backward<T>(h, st, l, xin, dxo_t, dsk_t, dx ? h->dxB : nullptr, B, Tn, 0.f));
+  RET(block_backward<T>(h, st, l, xin, dxo_t, h->R, dsk_t, h->Sp, dx ? h->dxB : nullptr, h->R, B, Tn, 0.f));
   if (dx) {
     LaunchScope ls(h, st, CLS_MISC);
     convert_kernel<T, float><<<cdiv(nR, 256), 256, 0, st>>>((const T*)h->dxB, dx, nR);
