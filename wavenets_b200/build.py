@@ -26,12 +26,16 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags():
+  return NVCC_FLAGS + os.environ.get('WN_NVCC_EXTRA', '').split()
+
+
 def _digest() -> str:
   h = hashlib.sha256()
   for f in SOURCES + HEADERS:
     with open(os.path.join(CSRC, f), 'rb') as fh:
       h.update(fh.read())
-  h.update(' '.join(NVCC_FLAGS).encode())
+  h.update(' '.join(_flags()).encode())
   return h.hexdigest()
 
 
@@ -42,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
       if fh.read().strip() == dig:
         return LIB
   nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-  cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
+  cmd = [nvcc] + _flags() + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB]
   res = subprocess.run(cmd, capture_output=True, text=True)
   log = os.path.join(HERE, 'build.log')
   with open(log, 'w') as fh:

@@ -294,10 +294,13 @@ template <int BN, int NIN, int NOUT> struct TcStagedCfg {
   static constexpr int IN_SLOTS = 2, OUT_SLOTS = 2;
   static constexpr int STAGING = (IN_SLOTS * NIN + OUT_SLOTS * NOUT) * PANEL;
   static constexpr int MAX_SMEM = 232448;
-  static constexpr int ST0 = (MAX_SMEM - 2048 - STAGING) / STAGE_BYTES;
-  static constexpr int STAGES = ST0 > 6 ? 6 : ST0;
+  static constexpr int ST0 = (MAX_SMEM - 3072 - STAGING) / STAGE_BYTES;
+#ifndef TC_STAGES_CAP
+#define TC_STAGES_CAP 6
+#endif
+  static constexpr int STAGES = ST0 > TC_STAGES_CAP ? TC_STAGES_CAP : ST0;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 + 512 + 1024 /*bias table*/;
   static_assert(STAGES >= 2, "not enough shared memory for the mainloop ring");
 };
 
@@ -324,6 +327,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
   uint64_t* in_full = tempty_bar + 2;
   uint64_t* in_empty = in_full + Cfg::IN_SLOTS;
   uint32_t* tmem_ptr = (uint32_t*)(in_empty + Cfg::IN_SLOTS);
+  float* bias_s = (float*)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);   // per-tile bias table (<= 256 floats)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool use_in = NIN > 0 && sp.in_mask != 0;
@@ -410,6 +414,21 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
         const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM;
         const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
+#ifdef TC_L2_PREFETCH
+        {
+          // pull the NEXT tile's epilogue inputs into L2 while this tile is being computed
+          const int tn = tile + gridDim.x;
+          if (tn < p.num_tiles) {
+            const int nt2 = tn % p.n_tiles, mt2 = tn / p.n_tiles;
+            const int b2 = mt2 / p.tiles_t, t2 = (mt2 % p.tiles_t) * Cfg::BM;
+            const int c2 = Epi::kGate ? nt2 * (BN / 2) : nt2 * BN;
+            for (int step = 0; step < STEPS; ++step) {
+              if (sp.in_mask & 1u) tma_prefetch_l2_3d(&tmI0, sp.in_col[0] + c2 + step * 32, t2, b2);
+              if (NIN > 1 && (sp.in_mask & 2u)) tma_prefetch_l2_3d(&tmI1, sp.in_col[1] + c2 + step * 32, t2, b2);
+            }
+          }
+        }
+#endif
         for (int step = 0; step < STEPS; ++step) {
           mbar_wait(&in_empty[islot], iphase ^ 1);
           mbar_expect_tx(&in_full[islot], (uint32_t)(nact * Cfg::PANEL));
@@ -438,8 +457,17 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
       const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
       const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM;
       const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
+      const int bsafe = b < p.B ? b : p.B - 1;
+      constexpr int NBIAS = Epi::kBiasFloats(BN);
+      float bias_reg = 0.f;
+      if (NBIAS > 0 && (int)threadIdx.x - 128 < NBIAS) bias_reg = Epi::bias_load(ep, bsafe, tile_col0, BN, (int)threadIdx.x - 128);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (NBIAS > 0) {
+        // every reader of the previous tile's table is past that tile's last step barrier
+        if ((int)threadIdx.x - 128 < NBIAS) bias_s[threadIdx.x - 128] = bias_reg;
+        named_bar_sync(2, NEPI * 32);
+      }
       TmemAccRow acc{tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16), true};
 #pragma unroll 1
       for (int step = 0; step < STEPS; ++step) {
@@ -466,7 +494,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           if (lane == 0) mbar_arrive(&in_empty[islot]);
           if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
         }
-        Epi::chunk(ep, acc, b, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out);
+        Epi::chunk(ep, acc, bsafe, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out, bias_s);
         uint8_t* ob = out_ring + oslot * NOUT * Cfg::PANEL;
 #pragma unroll
         for (int k = 0; k < NOUT; ++k) {

@@ -12,13 +12,18 @@
 //     col               first output column of this chunk in the output tensors' own numbering
 //     in[k][16]         staged inputs (fp32), valid when bit k of in_mask is set
 //     out[k][16]        results (fp32; the kernel rounds to bf16 and stages them for the TMA store)
+//     bs                per-tile bias table in shared memory (the kernel's L1 is carved down to a few KB by
+//                       the operand ring, so per-chunk global bias loads would each pay an L2 round trip):
+//                       Epi::bias_load() fetches this thread's entries at tile start (latency hidden behind
+//                       the wait for the accumulator), the kernel stores them, chunk() reads them by broadcast
+//   kBiasFloats(BN) table entries; each of the 256 epilogue threads loads entry `tid` (and tid+256 if needed)
 #pragma once
 #include "common.cuh"
 
-__device__ __forceinline__ void ld_bias16(const float* __restrict__ p, float* v) {
+__device__ __forceinline__ void ld_bias16(const float* p, float* v) {   // shared-memory broadcast read
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+    const float4 q = reinterpret_cast<const float4*>(p)[i];
     v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
   }
 }
@@ -28,24 +33,27 @@ template <bool FAST> struct TcEpiBiasActRes {
   static constexpr int NIN = 1, NOUT = 1;
   static constexpr bool kGate = false;
   struct Params { const float* bias; const float* cbias; int ldcb; int act; int N; };
+  static constexpr int kBiasFloats(int BN) { return BN; }
+  // entry i of the tile's table: bias[n0+i] + cbias[b][n0+i]
+  static __device__ __forceinline__ float bias_load(const Params& p, int b, int tile_col0, int BN, int i) {
+    const int n = tile_col0 + i;
+    float v = 0.f;
+    if (n < p.N) {
+      if (p.bias) v = __ldg(p.bias + n);
+      if (p.cbias) v += __ldg(p.cbias + (long long)b * p.ldcb + n);
+    }
+    return v;
+  }
   template <class Acc>
   static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
-                                               const float (*in)[16], float (*out)[16]) {
+                                               const float (*in)[16], float (*out)[16], const float* bs) {
     float v[16];
     acc.load16(acc_col, v);
-    if (col + 16 <= p.N) {
-      if (p.bias) {
-        float t[16];
-        ld_bias16(p.bias + col, t);
+    {
+      float t[16];
+      ld_bias16(bs + acc_col, t);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += t[i];
-      }
-      if (p.cbias) {
-        float t[16];
-        ld_bias16(p.cbias + (long long)b * p.ldcb + col, t);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += t[i];
-      }
+      for (int i = 0; i < 16; ++i) v[i] += t[i];
     }
     if (p.act != ACT_LINEAR) {
 #pragma unroll
@@ -65,29 +73,33 @@ template <bool FAST> struct TcEpiGate {
   static constexpr int NIN = 0, NOUT = 3;
   static constexpr bool kGate = true;
   struct Params { const float* bias; const float* cbias; int D; };
+  static constexpr int kBiasFloats(int BN) { return BN; }
+  // table = [filter half (BN/2) | gate half (BN/2)], same order as the accumulator tile; tile_col0 = first channel
+  static __device__ __forceinline__ float bias_load(const Params& p, int b, int tile_col0, int BN, int i) {
+    const int half = BN >> 1;
+    const int ch = tile_col0 + (i < half ? i : i - half);
+    float v = 0.f;
+    if (ch < p.D) {
+      const int n = i < half ? ch : p.D + ch;
+      v = __ldg(p.bias + n);
+      if (p.cbias) v += __ldg(p.cbias + (long long)b * 2 * p.D + n);
+    }
+    return v;
+  }
   template <class Acc>
   static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
-                                               const float (*in)[16], float (*out)[16]) {
+                                               const float (*in)[16], float (*out)[16], const float* bs) {
     float f[16], s[16];
     acc.load16(acc_col, f);
     acc.load16(half + acc_col, s);
-    if (col + 16 <= p.D) {
+    {
       float t[16];
-      ld_bias16(p.bias + col, t);
+      ld_bias16(bs + acc_col, t);
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] += t[i];
-      ld_bias16(p.bias + p.D + col, t);
+      ld_bias16(bs + half + acc_col, t);
 #pragma unroll
       for (int i = 0; i < 16; ++i) s[i] += t[i];
-      if (p.cbias) {
-        const float* cb = p.cbias + (long long)b * 2 * p.D;
-        ld_bias16(cb + col, t);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] += t[i];
-        ld_bias16(cb + p.D + col, t);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s[i] += t[i];
-      }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -103,9 +115,11 @@ template <bool FAST> struct TcEpiGateBwd {
   static constexpr int NIN = 2, NOUT = 2;
   static constexpr bool kGate = false;
   struct Params { int D; };
+  static constexpr int kBiasFloats(int BN) { return 0; }
+  static __device__ __forceinline__ float bias_load(const Params& p, int b, int tile_col0, int BN, int i) { return 0.f; }
   template <class Acc>
   static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
-                                               const float (*in)[16], float (*out)[16]) {
+                                               const float (*in)[16], float (*out)[16], const float* bs) {
     float dg[16];
     acc.load16(acc_col, dg);
 #pragma unroll
@@ -122,9 +136,11 @@ struct TcEpiActBwd {
   static constexpr int NIN = 2, NOUT = 1;
   static constexpr bool kGate = false;
   struct Params { int act; };
+  static constexpr int kBiasFloats(int BN) { return 0; }
+  static __device__ __forceinline__ float bias_load(const Params& p, int b, int tile_col0, int BN, int i) { return 0.f; }
   template <class Acc>
   static __device__ __forceinline__ void chunk(const Params& p, Acc& acc, int b, int acc_col, int half, int col, uint32_t in_mask,
-                                               const float (*in)[16], float (*out)[16]) {
+                                               const float (*in)[16], float (*out)[16], const float* bs) {
     float v[16];
     acc.load16(acc_col, v);
     if (in_mask & 1u) {
