@@ -145,6 +145,11 @@ int wn_debug_conv_gemm(const void* a_bf16_dev, int lda, int B, int T, int nseg, 
 int wn_debug_wgrad(const void* a_bf16_dev, int lda, const void* g_bf16_dev, int ldg, int B, int T, int nseg,
                    const int* shifts, int K, int N, float* out_dev, void* stream);
 
+/* micro-benchmark of one mainloop: `reps` back-to-back launches, CUDA-event timed (ms per launch).
+ * which: 0 conv GEMM (W = g_or_w [N][nseg*K], bf16 out (B,T,ldo)), 1 wgrad + split reduction, 2 wgrad kernel alone */
+int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int lda, const void* g_or_w_bf16_dev, int ldg, int B, int T,
+                   int nseg, const int* shifts, int K, int N, void* out_dev, int ldo, float* ms_out);
+
 /* ---- introspection for benchmarks --------------------------------------------------------- */
 /* number of kernel launches issued by the last wn_train_step / wn_forward on this handle */
 int64_t wn_last_launch_count(const wn_handle* h);

@@ -21,7 +21,7 @@ EXPORTS = [
   'wn_param_count', 'wn_param_info', 'wn_params_dev', 'wn_grads_dev', 'wn_set_param', 'wn_get_param',
   'wn_get_grad', 'wn_params_changed', 'wn_quantize', 'wn_forward', 'wn_train_step', 'wn_test_step',
   'wn_train_step_host', 'wn_layer_forward', 'wn_layer_backward', 'wn_last_launch_count',
-  'wn_profile_begin', 'wn_profile_end', 'wn_build_info', 'wn_debug_conv_gemm', 'wn_debug_wgrad',
+  'wn_profile_begin', 'wn_profile_end', 'wn_build_info', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
 ]
 
 
@@ -92,6 +92,7 @@ def load():
   ip = C.POINTER(C.c_int)
   lib.wn_debug_conv_gemm.argtypes = [vp, i32, i32, i32, i32, ip, i32, vp, i32, i32, i32, vp, vp]
   lib.wn_debug_wgrad.argtypes = [vp, i32, vp, i32, i32, i32, i32, ip, i32, i32, vp, vp]
+  lib.wn_debug_bench.argtypes = [i32, i32, vp, i32, vp, i32, i32, i32, i32, ip, i32, i32, vp, i32, C.POINTER(C.c_float)]
   _LIB = lib
   return lib
 

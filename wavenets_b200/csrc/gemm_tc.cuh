@@ -36,7 +36,7 @@ struct TcWgradDesc {
   int B, T, N; const bf16* G; int ldg; int nseg; TcSeg seg[TC_MAX_SEG]; int ktot; float* partial;
   float* cs_partial;   // optional: per-(split, batch slot) column sums of G, [nsplit][slots][N] (bias / conditioning gradients)
 };
-struct TcWgradPlan { int nsplit, chunks_per_split, chunks_t, slots; };
+struct TcWgradPlan { int nsplit, chunks_per_split, chunks_t, slots, mtiles; };
 
 static inline int tc_check_config(int R, int D, int S, int K) {
   if (R % 64 || D % 64 || S % 64) return -1;
@@ -364,9 +364,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
             for (int k0 = 0; k0 < kseg; k0 += Cfg::BK) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+#ifdef TC_EXP_NO_TMA
+              mbar_arrive(&full_bar[stage]);
+#else
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               tma_load_4d(sa, tm, &full_bar[stage], k0, tcoord, b, o);
               tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0);
+#endif
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             wk += kseg;
@@ -393,9 +397,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+#ifndef TC_EXP_NO_MMA
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+#endif
           umma_commit(&empty_bar[stage]);
           if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
         }
@@ -406,7 +412,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
     }
   } else if (warp == 3) {
     // ===================== epilogue-input producer =====================
+#ifdef TC_EXP_NO_EPI
+    if (false) {
+#else
     if (NIN > 0 && use_in && lane == 0) {
+#endif
       int nact = 0;
       for (int k = 0; k < NIN; ++k) nact += (sp.in_mask >> k) & 1;
       int islot = 0; uint32_t iphase = 0;
@@ -469,8 +479,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
         named_bar_sync(2, NEPI * 32);
       }
       TmemAccRow acc{tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16), true};
+#ifdef TC_EXP_NO_EPI
+      constexpr int STEPS_RUN = 0;
+#else
+      constexpr int STEPS_RUN = STEPS;
+#endif
 #pragma unroll 1
-      for (int step = 0; step < STEPS; ++step) {
+      for (int step = 0; step < STEPS_RUN; ++step) {
         const int col0 = tile_col0 + step * 32;
         float in[NIN > 0 ? NIN : 1][16];
         float out[NOUT][16];
@@ -656,9 +671,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
   const int nchunks = c_end - c_begin;
 
-  // CTAs of the first m-tile also reduce the columns of G (bias / conditioning gradients) with
-  // their otherwise idle epilogue warps, straight from the TMA-staged G tiles in shared memory.
-  const bool do_cs = p.cs_partial != nullptr && blockIdx.x == 0;
+  // The otherwise idle epilogue warps also reduce the columns of G (bias / conditioning gradients)
+  // straight from the TMA-staged G tiles in shared memory; the gridDim.x CTAs that share a G tile
+  // split its 64 time rows between them so no CTA becomes the long pole.
+#ifdef TC_EXP_WG_NO_CS
+  const bool do_cs = false;
+#else
+  const bool do_cs = p.cs_partial != nullptr;
+#endif
+  const int cs_r0 = (Cfg::BKT * (int)blockIdx.x) / (int)gridDim.x, cs_r1 = (Cfg::BKT * ((int)blockIdx.x + 1)) / (int)gridDim.x;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], do_cs ? 5 : 1); }
     mbar_init(tfull_bar, 1);
@@ -681,11 +702,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int b = ch / p.chunks_t, t0 = (ch % p.chunks_t) * Cfg::BKT;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+#ifdef TC_EXP_WG_NO_TMA
+        mbar_arrive(&full_bar[stage]);
+#else
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_4d(sa, tm, &full_bar[stage], k0, t0 + shift, b, 0);
         tma_load_4d(sa + 8192, tm, &full_bar[stage], k0 + 64, t0 + shift, b, 0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + Cfg::A_BYTES + j * 8192, &tmG, &full_bar[stage], n0 + 64 * j, t0, b, 0);
+#endif
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -700,9 +725,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         // MN-major, 128B swizzle: 64-wide channel atoms 8192 B apart (LBO), 8 time rows = 1024 B (SBO)
         const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
         const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 8192, 1024);
+#ifndef TC_EXP_WG_NO_MMA
 #pragma unroll
         for (int k = 0; k < Cfg::BKT / 16; ++k)   // 16 time rows = 2048 bytes (>>4 = 128) per step
           umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+#endif
         umma_commit(&empty_bar[stage]);
         if (it == nchunks - 1) umma_commit(tfull_bar);
       }
@@ -726,7 +753,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int b = ch / p.chunks_t;
         if (b != cur_b) {
           if (act && n0 + c < p.N) {
-            float* o = p.cs_partial + ((long long)blockIdx.z * p.slots + (cur_b - b_first)) * p.N + n0 + c;
+            float* o = p.cs_partial + (((long long)blockIdx.z * gridDim.x + blockIdx.x) * p.slots + (cur_b - b_first)) * p.N + n0 + c;
             o[0] = s0;
             if (n0 + c + 1 < p.N) o[1] = s1;
           }
@@ -735,8 +762,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait(&full_bar[stage], phase);
         if (act) {
           const uint8_t* g = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES + col_off;
-#pragma unroll 16
-          for (int r = 0; r < Cfg::BKT; ++r) {
+#pragma unroll 8
+          for (int r = cs_r0; r < cs_r1; ++r) {
             const uint32_t w = *reinterpret_cast<const uint32_t*>(g + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4));
             s0 += __uint_as_float(w << 16);
             s1 += __uint_as_float(w & 0xffff0000u);
@@ -747,7 +774,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (nchunks > 0 && act && n0 + c < p.N) {
-        float* o = p.cs_partial + ((long long)blockIdx.z * p.slots + (cur_b - b_first)) * p.N + n0 + c;
+        float* o = p.cs_partial + (((long long)blockIdx.z * gridDim.x + blockIdx.x) * p.slots + (cur_b - b_first)) * p.N + n0 + c;
         o[0] = s0;
         if (n0 + c + 1 < p.N) o[1] = s1;
       }
@@ -770,7 +797,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
+#ifdef TC_EXP_WG_NO_ST
+      if (valid && v[0] == 123.456f) {
+#else
       if (valid) {
+#endif
         const int nv = min(16, p.N - n);
         if (nv == 16 && ((p.N & 3) == 0)) {
 #pragma unroll
@@ -813,7 +844,7 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   nsplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   p.slots = (p.chunks_per_split + p.chunks_t - 2) / p.chunks_t + 1;
   p.cs_partial = d.cs_partial;
-  plan->nsplit = nsplit; plan->chunks_per_split = p.chunks_per_split; plan->chunks_t = p.chunks_t; plan->slots = p.slots;
+  plan->nsplit = nsplit; plan->chunks_per_split = p.chunks_per_split; plan->chunks_t = p.chunks_t; plan->slots = p.slots; plan->mtiles = mtiles;
   auto kern = tc_wgrad_kernel<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -834,8 +865,8 @@ static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   return tc_wgrad_launch<64>(tc, st, d, plan);
 }
 // upper bound of cs_partial rows for a (B, T) problem: nsplit * slots <= this
-static inline long long tc_wgrad_cs_rows(int B, int T) {
-  return (long long)WN_MAX_WGRAD_SPLITS * 2 + B + 2;
+static inline long long tc_wgrad_cs_rows(int B, int T, int max_mtiles) {
+  return ((long long)WN_MAX_WGRAD_SPLITS * 2 + B + 2) * (max_mtiles > 0 ? max_mtiles : 1);
 }
 
 // Second stage of the wgrad: deterministic sum of the split partials (no atomics), written in
@@ -846,7 +877,7 @@ static inline long long tc_wgrad_cs_rows(int B, int T) {
 struct TcWgradFinish {
   const float* partial; int nsplit; int ktot; int N; int N0;
   float* dst0; float* dst1; const float* w0; const float* w1; float l2coef;
-  const float* cs; int slots; int cps; int chunks_t; int B;
+  const float* cs; int slots; int cps; int chunks_t; int B; int mtiles;
   float* bias0; float* bias1; float* per_batch; int ldpb;
   int wblocks;   // blocks of the weight part
 };
@@ -887,7 +918,7 @@ __global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
       float sb = 0.f;
       for (int z = z0; z <= z1; ++z) {
         const int b_first = (z * f.cps) / f.chunks_t;
-        sb += f.cs[((long long)z * f.slots + (b - b_first)) * f.N + n];
+        for (int m = 0; m < f.mtiles; ++m) sb += f.cs[(((long long)z * f.mtiles + m) * f.slots + (b - b_first)) * f.N + n];
       }
       if (f.per_batch) f.per_batch[(long long)b * f.ldpb + n] = sb;
       tot += sb;

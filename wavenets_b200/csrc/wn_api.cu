@@ -355,7 +355,13 @@ static void layout_buffers(wn_handle* h) {
   for (auto& c : h->head) upd(c.cin, c.cout);
   h->wg_partial_elems = maxkn * WN_MAX_WGRAD_SPLITS;
   h->wg_partial = (float*)W.take((size_t)h->wg_partial_elems * 4);
-  if (bf) h->cs_partial = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT) * (size_t)rup(nmax, 4) * 4);
+  if (bf) {
+    int max_mt = 1;
+    auto mt = [&](int K, int cin) { const int m = K * cdiv(cin, 128); if (m > max_mt) max_mt = m; };
+    for (auto& b : h->blocks) { for (auto& c : b.stack) mt(c.K, c.cin); mt(1, D); }
+    for (auto& c : h->head) mt(1, c.cin);
+    h->cs_partial = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4);
+  }
   h->loss_parts_cap = cdiv((long long)rows, 8) + 8;
   h->loss_partial = (float*)W.take((size_t)h->loss_parts_cap * 4);
   int maxw = h->cfg.cond_in;
@@ -775,7 +781,7 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     f.partial = h->wg_partial; f.nsplit = plan.nsplit; f.ktot = ktot; f.N = g.N; f.N0 = g.dst1 ? g.N0 : g.N;
     f.dst0 = g.dst; f.dst1 = g.dst1; f.l2coef = g.l2coef;
     f.w0 = g.l2coef != 0.f ? g.w : nullptr; f.w1 = g.l2coef != 0.f ? g.w1 : nullptr;
-    f.cs = h->cs_partial; f.slots = plan.slots; f.cps = plan.chunks_per_split; f.chunks_t = plan.chunks_t; f.B = g.B;
+    f.cs = h->cs_partial; f.slots = plan.slots; f.cps = plan.chunks_per_split; f.chunks_t = plan.chunks_t; f.B = g.B; f.mtiles = plan.mtiles;
     f.bias0 = g.bias_dst; f.bias1 = g.bias1; f.per_batch = g.per_batch; f.ldpb = g.ldpb;
     f.wblocks = cdiv((long long)ktot * g.N, 256);
     LaunchScope ls(h, st, cls);
@@ -1491,6 +1497,52 @@ extern "C" int wn_debug_wgrad(const void* a_bf16_dev, int lda, const void* g_bf1
   reduce_parts<<<cdiv(kn, 256), 256, 0, st>>>(partial, plan.nsplit, kn, out_dev, kn, nullptr, 0.f);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(partial);
+  CK(e);
+  return WN_OK;
+}
+
+// micro-benchmark hook: `reps` back-to-back launches of one mainloop on caller buffers, CUDA-event timed.
+// which: 0 = conv GEMM (bf16 out, no bias), 1 = wgrad (+finish), 2 = wgrad kernel alone
+extern "C" int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int lda, const void* g_or_w_bf16_dev, int ldg, int B, int T, int nseg,
+                              const int* shifts, int K, int N, void* out_dev, int ldo, float* ms_out) {
+  if (tc_init() != 0) { set_err("cannot resolve cuTensorMapEncodeTiled from the driver"); return WN_ERR_CUDA; }
+  static TmapCache cache;
+  cache.maps.clear();
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float* partial = nullptr;
+  const long long kn = (long long)nseg * K * N;
+  if (which >= 1) CK(cudaMalloc(&partial, (size_t)kn * WN_MAX_WGRAD_SPLITS * 4));
+  int rc = 0;
+  for (int it = -2; it < reps && rc == 0; ++it) {
+    if (it == 0) cudaEventRecord(e0, st);
+    if (which == 0) {
+      TcGemmDesc d{};
+      d.B = B; d.T = T; d.nseg = nseg; d.n_outer = 1;
+      for (int s = 0; s < nseg; ++s) d.seg[s] = TcSeg{(const bf16*)a_bf16_dev, lda, shifts[s], K};
+      d.W = (const bf16*)g_or_w_bf16_dev; d.ktot = nseg * K; d.N16 = N; d.tileN = 0;
+      TcEpiBiasActRes<true>::Params q{nullptr, nullptr, 0, ACT_LINEAR, N};
+      TcEpiIo in[2] = {{}, {}};
+      TcEpiIo out[3] = {{(const bf16*)out_dev, ldo, N, 0}, {}, {}};
+      rc = tc_conv_gemm_staged<TcEpiBiasActRes<true>>(cache, st, d, q, in, 0u, out);
+    } else {
+      TcWgradDesc d{};
+      d.B = B; d.T = T; d.N = N; d.G = (const bf16*)g_or_w_bf16_dev; d.ldg = ldg; d.nseg = nseg; d.ktot = nseg * K; d.partial = partial;
+      for (int s = 0; s < nseg; ++s) d.seg[s] = TcSeg{(const bf16*)a_bf16_dev, lda, shifts[s], K};
+      TcWgradPlan plan{};
+      rc = tc_wgrad(cache, st, d, &plan);
+      if (rc == 0 && which == 1) reduce_parts<<<cdiv(kn, 256), 256, 0, st>>>(partial, plan.nsplit, kn, (float*)out_dev, kn, nullptr, 0.f);
+    }
+  }
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / (reps > 0 ? reps : 1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (partial) cudaFree(partial);
+  if (rc != 0) { set_err("debug bench launch failed (%d): %s", rc, tc_last_error()); return WN_ERR_CUDA; }
   CK(e);
   return WN_OK;
 }
