@@ -173,6 +173,57 @@ __global__ void __launch_bounds__(128) dense_small_dgrad(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------ conditioning, all blocks in one launch
+// The per-block conv_cond (layers.py:117-120,203-204) on a time-constant conditioning vector is a
+// (B,Cc)x(Cc,2D) product per block; offs[2*l] / offs[2*l+1] = offsets of Wc_l / bc_l in the flat
+// parameter (and gradient) buffers.  blockIdx.y = block index l.
+// cb[l][b][n] = sum_k cond[b][k] Wc_l[k][n] + bc_l[n]
+__global__ void cond_bias_all(const float* __restrict__ cond, int Cc, const float* __restrict__ params, const int* __restrict__ offs,
+                              float* __restrict__ cb, long long cb_stride, int B, int N) {
+  const int l = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N, n = i % N;
+  const float* W = params + offs[2 * l];
+  float s = params[offs[2 * l + 1] + n];
+  for (int k = 0; k < Cc; ++k) s = fmaf(cond[(long long)b * Cc + k], W[(long long)k * N + n], s);
+  cb[(long long)l * cb_stride + (long long)b * N + n] = s;
+}
+// dWc_l[k][n] = sum_b cond[b][k] dcb_l[b][n] (+ l2coef * Wc_l[k][n]) ; dbc_l[n] = sum_b dcb_l[b][n]   (k == Cc => bias)
+__global__ void cond_wgrad_all(const float* __restrict__ cond, int Cc, const float* __restrict__ dcb, long long dcb_stride,
+                               const float* __restrict__ params, float* __restrict__ grads, const int* __restrict__ offs, int B, int N,
+                               float l2coef) {
+  const int l = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (Cc + 1) * N) return;
+  const int k = i / N, n = i % N;
+  const float* d = dcb + (long long)l * dcb_stride;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s = fmaf(k < Cc ? cond[(long long)b * Cc + k] : 1.0f, d[(long long)b * N + n], s);
+  if (k < Cc) {
+    const long long o = offs[2 * l] + (long long)k * N + n;
+    grads[o] = l2coef != 0.f ? fmaf(l2coef, params[o], s) : s;
+  } else {
+    grads[offs[2 * l + 1] + n] = s;
+  }
+}
+// dcond[b][k] = sum_l sum_n dcb_l[b][n] Wc_l[k][n] ; one warp per output, fixed summation order
+__global__ void __launch_bounds__(128) cond_dgrad_all(const float* __restrict__ dcb, long long dcb_stride, const float* __restrict__ params,
+                                                      const int* __restrict__ offs, float* __restrict__ dcond, int L, int B, int Cc, int N) {
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= B * Cc) return;
+  const int b = i / Cc, k = i % Cc;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float* d = dcb + (long long)l * dcb_stride + (long long)b * N;
+    const float* W = params + offs[2 * l] + (long long)k * N;
+    for (int n = lane; n < N; n += 32) s = fmaf(d[n], W[n], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) dcond[(long long)b * Cc + k] = s;
+}
+
 // ------------------------------------------------------------------ softmax-256 cross entropy (model.py:114-118,516)
 // One warp per row.  logits fp32 [rows][C]; the target index is quantised on the fly from
 // frames[b][t+1] (model.py:319-320).  Writes per-block loss partials, dlogits (= scale *

@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -117,6 +118,7 @@ struct wn_handle {
   bf16* Wskip16 = nullptr;                // bf16 [Spad16][L*D]
   float* bskip_sum = nullptr;             // [Sp]
   int* d_bskip_offsets = nullptr;
+  int* d_cond_offsets = nullptr;          // [2L]: offsets of conv_cond kernel / bias of every block in the flat buffers
   // packed pool
   Arena pack, ws;
   int maxB, maxT;
@@ -164,6 +166,11 @@ struct wn_handle {
   size_t prof_used = 0;
   long long prof_launches = 0;
   TmapCache tmaps;
+  // CUDA graphs of whole steps, keyed by the call's arguments (buffers are fixed at create time)
+  struct StepGraph { const float* frames; const float* cond; int B, T, nrep; float* loss; bool train; int seen; long long launches; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
+  int use_graphs = 1;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 enum { CLS_DILATED = 1, CLS_GEMM = 2, CLS_LOSS = 3, CLS_MISC = 4 };
@@ -293,6 +300,7 @@ static void layout_buffers(wn_handle* h) {
   }
   h->bskip_sum = (float*)P.take((size_t)h->Sp * 4);
   h->d_bskip_offsets = (int*)P.take((size_t)h->L * 4 * 2);
+  h->d_cond_offsets = (int*)P.take((size_t)h->L * 4 * 2);
 
   Arena& W = h->ws;
   const size_t rows = (size_t)h->maxB * h->maxT;
@@ -515,11 +523,19 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   cudaMallocHost(&h->pin_cond, (size_t)h->maxB * (c.cond_in > 0 ? c.cond_in : 1) * 4);
   cudaMallocHost(&h->pin_loss, 16);
   cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming);
+  { const char* e = getenv("WN_CUDA_GRAPH"); if (e && e[0] == '0') h->use_graphs = 0; }
   // offsets of the per-block skip biases (or conv1 biases when aliased) for bskip_sum
   {
     std::vector<int> offs;
     for (auto& b : h->blocks) offs.push_back((int)h->params[b.has_skip ? b.conv_skip.b_idx : b.conv1.b_idx].offset);
     cudaMemcpy(h->d_bskip_offsets, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice);
+    if (c.conditioning) {
+      std::vector<int> co;
+      for (auto& b : h->blocks) { co.push_back((int)h->params[b.cw_idx].offset); co.push_back((int)h->params[b.cb_idx].offset); }
+      cudaMemcpy(h->d_cond_offsets, co.data(), co.size() * 4, cudaMemcpyHostToDevice);
+    }
   }
   if (c.precision == WN_BF16) {
     int r = tc_init();
@@ -536,6 +552,9 @@ extern "C" void wn_destroy(wn_handle* h) {
   if (!h) return;
   cudaDeviceSynchronize();
   for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
   cudaFree(h->d_params); cudaFree(h->d_grads); cudaFree(h->pack.base); cudaFree(h->ws.base);
   cudaFreeHost(h->pin_frames); cudaFreeHost(h->pin_cond); cudaFreeHost(h->pin_loss);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -915,7 +934,11 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   const float* cond = nullptr;
   if (c.conditioning) {
     RET(cond_forward(h, st, cond_in, B, true, &cond));
-    for (int l = 0; l < h->L; ++l) cond_bias_block(h, st, l, cond, B);
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      const int n = 2 * h->D;
+      cond_bias_all<<<dim3(cdiv(B * n, 128), h->L), 128, 0, st>>>(cond, h->Cc, h->d_params, h->d_cond_offsets, h->cb, (long long)h->maxB * n, B, n);
+    }
   }
   h->last_cond = cond;
   {
@@ -1123,6 +1146,17 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
 static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, const float* cond, int B, int l0, int nl, bool run_mapping, float* dcond_out,
                          float l2coef) {
   const int n = 2 * h->D;
+  if (l0 == 0 && nl == h->L) {
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      cond_wgrad_all<<<dim3(cdiv((h->Cc + 1) * n, 128), h->L), 128, 0, st>>>(cond, h->Cc, h->dcb, (long long)h->maxB * n, h->d_params, h->d_grads,
+                                                                          h->d_cond_offsets, B, n, l2coef);
+    }
+    {
+      LaunchScope ls(h, st, CLS_MISC);
+      cond_dgrad_all<<<cdiv(B * h->Cc, 4), 128, 0, st>>>(h->dcb, (long long)h->maxB * n, h->d_params, h->d_cond_offsets, dcond_out, h->L, B, h->Cc, n);
+    }
+  } else
   for (int l = l0; l < l0 + nl; ++l) {
     const BlockP& b = h->blocks[l];
     const float* d = h->dcb + (size_t)l * h->maxB * n;
@@ -1322,11 +1356,55 @@ static int step_common(wn_handle* h, const float* frames_dev, const float* cond_
   if (n_replicas < 1 || !frames_dev || !loss_dev) { set_err("bad step arguments"); return WN_ERR_VALUE; }
   if (train && h->cfg.dropout > 0.f) { set_err("training with dropout>0 is not built yet (TF RNG stream is not reproducible; use dropout=0)"); return WN_ERR_UNSUPPORTED; }
   CK(cudaSetDevice(h->cfg.device));
-  h->launches = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int r = h->cfg.precision == WN_BF16 ? step_entry<bf16>(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, st, train)
-                                      : step_entry<float>(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, st, train);
-  RET(r);
+  auto run = [&](cudaStream_t s) -> int {
+    h->launches = 0;
+    return h->cfg.precision == WN_BF16 ? step_entry<bf16>(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, s, train)
+                                       : step_entry<float>(h, frames_dev, cond_dev, B, T, n_replicas, loss_dev, s, train);
+  };
+  // The step is ~350 dependent launches: replay it as one CUDA graph from the second identical call on
+  // (first call runs eagerly and warms function attributes and the tensor-map cache).
+  if (h->use_graphs && h->prof_tag == 0) {
+    wn_handle::StepGraph* sg = nullptr;
+    for (auto& g : h->graphs)
+      if (g.frames == frames_dev && g.cond == cond_dev && g.B == B && g.T == T && g.nrep == n_replicas && g.loss == loss_dev && g.train == train) { sg = &g; break; }
+    if (!sg) {
+      if (h->graphs.size() >= 8) { for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec); h->graphs.clear(); }
+      h->graphs.push_back({frames_dev, cond_dev, B, T, n_replicas, loss_dev, train, 0, 0, nullptr});
+      sg = &h->graphs.back();
+    }
+    // the legacy default stream cannot be captured: run the graph on the handle's stream, ordered by events
+    const bool legacy = st == nullptr || st == cudaStreamLegacy;
+    cudaStream_t gs = legacy ? h->own_stream : st;
+    if (sg->seen >= 1 && !sg->exec) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int r = run(gs);
+        cudaError_t e = cudaStreamEndCapture(gs, &graph);
+        if (r == WN_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&sg->exec, graph, 0) == cudaSuccess) {
+          sg->launches = h->launches;
+        } else {
+          sg->exec = nullptr;
+          h->use_graphs = 0;       // fall back to eager launches for good
+          cudaGetLastError();
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        h->use_graphs = 0;
+        cudaGetLastError();
+      }
+    }
+    if (sg->exec) {
+      if (legacy) { CK(cudaEventRecord(h->ev_in, st)); CK(cudaStreamWaitEvent(gs, h->ev_in, 0)); }
+      CK(cudaGraphLaunch(sg->exec, gs));
+      if (legacy) { CK(cudaEventRecord(h->ev_out, gs)); CK(cudaStreamWaitEvent(st, h->ev_out, 0)); }
+      h->launches = sg->launches;
+      h->lastB = B; h->lastT = T;
+      return WN_OK;
+    }
+    sg->seen++;
+  }
+  RET(run(st));
   CK(cudaGetLastError());
   h->lastB = B; h->lastT = T;
   return WN_OK;
