@@ -441,10 +441,14 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
 #endif
         for (int step = 0; step < STEPS; ++step) {
           mbar_wait(&in_empty[islot], iphase ^ 1);
+#ifdef TC_EXP_NO_IN
+          mbar_arrive(&in_full[islot]);
+#else
           mbar_expect_tx(&in_full[islot], (uint32_t)(nact * Cfg::PANEL));
           uint8_t* dst = in_ring + islot * NIN * Cfg::PANEL;
           if (sp.in_mask & 1u) tma_load_3d(dst, &tmI0, &in_full[islot], sp.in_col[0] + tile_col0 + step * 32, t0, b);
           if (NIN > 1 && (sp.in_mask & 2u)) tma_load_3d(dst + Cfg::PANEL, &tmI1, &in_full[islot], sp.in_col[1] + tile_col0 + step * 32, t0, b);
+#endif
           if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
         }
       }
@@ -523,9 +527,15 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
         }
         fence_proxy_async();
         // all stores of the previous step's slot partner must have been read before anyone reuses it
+#ifndef TC_EXP_NO_OUT
         if (store_thread) bulk_wait_group_read<0>();
+#endif
         named_bar_sync(1, NEPI * 32);
+#ifdef TC_EXP_NO_OUT
+        if (false) {
+#else
         if (store_thread) {
+#endif
           tma_store_3d(ob, &tmO0, sp.out_col[0] + col0, t0, b);
           if (NOUT > 1) tma_store_3d(ob + Cfg::PANEL, &tmO1, sp.out_col[1] + col0, t0, b);
           if (NOUT > 2) tma_store_3d(ob + 2 * Cfg::PANEL, &tmO2, sp.out_col[2] + col0, t0, b);
