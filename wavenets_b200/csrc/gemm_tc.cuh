@@ -285,14 +285,16 @@ struct TcStagedParams {
   int out_col[3];
 };
 
-template <int BN, int NIN, int NOUT> struct TcStagedCfg {
+// IN_PANELS: capacity of the epilogue-input ring in half-panels (slots = IN_PANELS / active inputs, decided at
+// run time); OUT_SLOTS: output slots of NOUT half-panels each.
+template <int BN, int NIN, int NOUT, int IN_PANELS, int OUT_SLOTS_> struct TcStagedCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int PANEL = 128 * 64;                 // 128 rows x 32 bf16
-  static constexpr int IN_SLOTS = 2, OUT_SLOTS = 2;
-  static constexpr int STAGING = (IN_SLOTS * NIN + OUT_SLOTS * NOUT) * PANEL;
+  static constexpr int IN_MAX = IN_PANELS > 0 ? IN_PANELS : 1, OUT_SLOTS = OUT_SLOTS_;
+  static constexpr int STAGING = (IN_PANELS + OUT_SLOTS * NOUT) * PANEL;
   static constexpr int MAX_SMEM = 232448;
   static constexpr int ST0 = (MAX_SMEM - 3072 - STAGING) / STAGE_BYTES;
 #ifndef TC_STAGES_CAP
@@ -312,25 +314,28 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
                            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
                            const TcGemmParams p, const TcStagedParams sp, const typename Epi::Params ep) {
   constexpr int NIN = Epi::NIN, NOUT = Epi::NOUT;
-  using Cfg = TcStagedCfg<BN, NIN, NOUT>;
+  using Cfg = TcStagedCfg<BN, NIN, NOUT, Epi::kInPanels, Epi::kOutSlots>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NEPI = 8;
   constexpr int STEPS = Epi::kGate ? BN / 64 : BN / 32;   // 32 output columns per step
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* in_ring = smem + STAGES * Cfg::STAGE_BYTES;
-  uint8_t* out_ring = in_ring + Cfg::IN_SLOTS * NIN * Cfg::PANEL;
+  uint8_t* out_ring = in_ring + Epi::kInPanels * Cfg::PANEL;
   uint64_t* full_bar = (uint64_t*)(out_ring + Cfg::OUT_SLOTS * NOUT * Cfg::PANEL);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* in_full = tempty_bar + 2;
-  uint64_t* in_empty = in_full + Cfg::IN_SLOTS;
-  uint32_t* tmem_ptr = (uint32_t*)(in_empty + Cfg::IN_SLOTS);
+  uint64_t* in_empty = in_full + Cfg::IN_MAX;
+  uint32_t* tmem_ptr = (uint32_t*)(in_empty + Cfg::IN_MAX);
   float* bias_s = (float*)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);   // per-tile bias table (<= 256 floats)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool use_in = NIN > 0 && sp.in_mask != 0;
+  // active inputs are packed densely: slot = nact consecutive half-panels, so fewer inputs => a deeper ring
+  const int nact = NIN > 0 ? __popc(sp.in_mask) : 0;
+  const int in_slots = nact > 0 ? Epi::kInPanels / nact : 1;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     if (p.nseg > 1) tma_prefetch_desc(&tmA1);
@@ -340,7 +345,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NEPI); }
-    for (int i = 0; i < Cfg::IN_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], NEPI); }
+    for (int i = 0; i < Cfg::IN_MAX; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], NEPI); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
@@ -417,8 +422,6 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
 #else
     if (NIN > 0 && use_in && lane == 0) {
 #endif
-      int nact = 0;
-      for (int k = 0; k < NIN; ++k) nact += (sp.in_mask >> k) & 1;
       int islot = 0; uint32_t iphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -445,11 +448,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           mbar_arrive(&in_full[islot]);
 #else
           mbar_expect_tx(&in_full[islot], (uint32_t)(nact * Cfg::PANEL));
-          uint8_t* dst = in_ring + islot * NIN * Cfg::PANEL;
-          if (sp.in_mask & 1u) tma_load_3d(dst, &tmI0, &in_full[islot], sp.in_col[0] + tile_col0 + step * 32, t0, b);
-          if (NIN > 1 && (sp.in_mask & 2u)) tma_load_3d(dst + Cfg::PANEL, &tmI1, &in_full[islot], sp.in_col[1] + tile_col0 + step * 32, t0, b);
+          uint8_t* dst = in_ring + islot * nact * Cfg::PANEL;
+          if (sp.in_mask & 1u) { tma_load_3d(dst, &tmI0, &in_full[islot], sp.in_col[0] + tile_col0 + step * 32, t0, b); dst += Cfg::PANEL; }
+          if (NIN > 1 && (sp.in_mask & 2u)) tma_load_3d(dst, &tmI1, &in_full[islot], sp.in_col[1] + tile_col0 + step * 32, t0, b);
 #endif
-          if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+          if (++islot == in_slots) { islot = 0; iphase ^= 1; }
         }
       }
     }
@@ -495,12 +498,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
         float out[NOUT][16];
         if (NIN > 0 && use_in) {
           mbar_wait(&in_full[islot], iphase);
-          const uint8_t* ib = in_ring + islot * NIN * Cfg::PANEL;
+          const uint8_t* ib = in_ring + islot * nact * Cfg::PANEL;
 #pragma unroll
           for (int k = 0; k < NIN; ++k) {
             if ((sp.in_mask >> k) & 1u) {
-              const uint4 a = *reinterpret_cast<const uint4*>(ib + k * Cfg::PANEL + off0);
-              const uint4 c = *reinterpret_cast<const uint4*>(ib + k * Cfg::PANEL + off1);
+              const uint4 a = *reinterpret_cast<const uint4*>(ib + off0);
+              const uint4 c = *reinterpret_cast<const uint4*>(ib + off1);
+              ib += Cfg::PANEL;
               const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -511,7 +515,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&in_empty[islot]);
-          if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+          if (++islot == in_slots) { islot = 0; iphase ^= 1; }
         }
         Epi::chunk(ep, acc, bsafe, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out, bias_s);
         uint8_t* ob = out_ring + oslot * NOUT * Cfg::PANEL;
@@ -528,7 +532,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
         fence_proxy_async();
         // all stores of the previous step's slot partner must have been read before anyone reuses it
 #ifndef TC_EXP_NO_OUT
-        if (store_thread) bulk_wait_group_read<0>();
+        if (store_thread) bulk_wait_group_read<Cfg::OUT_SLOTS - 2>();
 #endif
         named_bar_sync(1, NEPI * 32);
 #ifdef TC_EXP_NO_OUT
@@ -541,7 +545,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           if (NOUT > 2) tma_store_3d(ob + 2 * Cfg::PANEL, &tmO2, sp.out_col[2] + col0, t0, b);
           bulk_commit_group();
         }
-        oslot ^= 1;
+        if (++oslot == Cfg::OUT_SLOTS) oslot = 0;
       }
       tc_fence_before();
       __syncwarp();
@@ -566,7 +570,7 @@ static inline const CUtensorMap* tc_panel_map(TmapCache& tc, const TcEpiIo& io, 
 template <class Epi, int BN>
 static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep, const TcEpiIo* ins,
                                       uint32_t in_mask, const TcEpiIo* outs) {
-  using Cfg = TcStagedCfg<BN, Epi::NIN, Epi::NOUT>;
+  using Cfg = TcStagedCfg<BN, Epi::NIN, Epi::NOUT, Epi::kInPanels, Epi::kOutSlots>;
   const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
   for (int s = 0; s < d.nseg; ++s) {
     ma[s] = tc_act_map(tc, d.seg[s].A, d.seg[s].lda, d.seg[s].K, d.T, d.B, s == 0 ? d.n_outer : 1, d.outer_stride, 128);
