@@ -658,7 +658,10 @@ template <int BN> struct TcWgradCfg {
 };
 
 // grid: x = 128-row tiles of the (seg, channel) axis, y = BN-wide tiles of N, z = row-range split
-template <int BN>
+// CL = cluster size along x: the CL CTAs of a cluster work on different m-tiles (channel blocks of A) against the
+// SAME G tile, so each loads 1/CL of its rows and multicasts them to all (L2 -> SM traffic per MMA step: 16 KB of A
+// + 32/CL KB of G instead of 48 KB).  Stage release is cluster-wide: every consumer arrives on every CTA's barrier.
+template <int BN, int CL>
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmG, const TcWgradParams p) {
@@ -694,14 +697,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const bool do_cs = p.cs_partial != nullptr;
 #endif
   const int cs_r0 = (Cfg::BKT * (int)blockIdx.x) / (int)gridDim.x, cs_r1 = (Cfg::BKT * ((int)blockIdx.x + 1)) / (int)gridDim.x;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], do_cs ? 5 : 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL * (do_cs ? 5 : 1)); }
     mbar_init(tfull_bar, 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -722,8 +728,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_4d(sa, tm, &full_bar[stage], k0, t0 + shift, b, 0);
         tma_load_4d(sa + 8192, tm, &full_bar[stage], k0 + 64, t0 + shift, b, 0);
+        if (CL == 1) {
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + Cfg::A_BYTES + j * 8192, &tmG, &full_bar[stage], n0 + 64 * j, t0, b, 0);
+          for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + Cfg::A_BYTES + j * 8192, &tmG, &full_bar[stage], n0 + 64 * j, t0, b, 0);
+        } else {
+          constexpr int RPC = Cfg::BKT / CL;          // time rows of every G atom this CTA fetches for the whole cluster
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d_mc(sa + Cfg::A_BYTES + j * 8192 + crank * (RPC * 128), &tmG, &full_bar[stage], n0 + 64 * j, t0 + (int)crank * RPC, b, 0, cmask);
+        }
 #endif
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -744,7 +757,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int k = 0; k < Cfg::BKT / 16; ++k)   // 16 time rows = 2048 bytes (>>4 = 128) per step
           umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
 #endif
-        umma_commit(&empty_bar[stage]);
+        if (CL == 1) umma_commit(&empty_bar[stage]);
+        else umma_commit_mc(&empty_bar[stage], cmask);
         if (it == nchunks - 1) umma_commit(tfull_bar);
       }
       __syncwarp();
@@ -784,7 +798,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (CL == 1) { if (lane == 0) mbar_arrive(&empty_bar[stage]); }
+        else if (lane < CL) mbar_arrive_remote(&empty_bar[stage], (uint32_t)lane);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (nchunks > 0 && act && n0 + c < p.N) {
@@ -829,7 +844,53 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still signal its barriers
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// CTAs of one wave for cluster size CL (clusters must fit inside a GPC, so fewer than #SMs may be usable)
+template <int BN, int CL>
+static int tc_wgrad_wave_ctas() {
+  using Cfg = TcWgradCfg<BN>;
+  static int cached = 0;
+  if (cached) return cached;
+  auto kern = tc_wgrad_kernel<BN, CL>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  int n = 0;
+  if (CL > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * tc_num_sms()); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    n *= CL;
+  }
+  if (n <= 0 || n > tc_num_sms()) n = CL > 1 ? (tc_num_sms() / CL) * CL * 7 / 8 : tc_num_sms();
+  cached = n;
+  return n;
+}
+
+template <int BN, int CL>
+static int tc_wgrad_launch_cl(const CUtensorMap* const* ma, const CUtensorMap* mg, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = TcWgradCfg<BN>;
+  auto kern = tc_wgrad_kernel<BN, CL>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mg, p);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "wgrad launch (cluster %d): %s", CL, cudaGetErrorString(e)); return -13; }
+  return 0;
 }
 
 template <int BN>
@@ -843,14 +904,24 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
     mtiles += (d.seg[s].K + 127) / 128;
   }
   for (int s = d.nseg; s < TC_MAX_SEG; ++s) ma[s] = ma[0];
-  const CUtensorMap* mg = tc_act_map(tc, d.G, d.ldg, d.N, d.T, d.B, 1, 0, 64);
+  // cluster along the m-tiles that share a G tile (multicast): 4, 2 or 1
+  // Measured on B200 (C2 dilated wgrad, profiles/README.md): multicast clusters of 4 are SLOWER (43 vs 37 us
+  // in isolation, +1.9 ms per step in situ: lock-step coupling, 2 KB boxes, remote barrier arrivals, and only
+  // 132 SMs host 4-clusters) — L2 already coalesces same-line requests of neighbouring SMs.  Off by default.
+#ifdef TC_WGRAD_CLUSTER
+  const int cl = mtiles % 4 == 0 ? 4 : (mtiles % 2 == 0 ? 2 : 1);
+#else
+  const int cl = 1;
+#endif
+  const CUtensorMap* mg = tc_act_map(tc, d.G, d.ldg, d.N, d.T, d.B, 1, 0, 64 / cl);
   if (!mg) return -11;
   TcWgradParams p{};
   p.B = d.B; p.T = d.T; p.N = d.N; p.chunks_t = (d.T + 63) / 64; p.total_chunks = d.B * p.chunks_t; p.ktot = d.ktot; p.nseg = d.nseg;
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
   p.partial = d.partial;
   const int ntiles = (d.N + BN - 1) / BN;
-  int nsplit = tc_num_sms() / (mtiles * ntiles);   // one wave: never more CTAs than SMs
+  const int wave = cl == 4 ? tc_wgrad_wave_ctas<BN, 4>() : (cl == 2 ? tc_wgrad_wave_ctas<BN, 2>() : tc_num_sms());
+  int nsplit = wave / (mtiles * ntiles);   // one wave: never more CTAs than can be resident
   if (nsplit < 1) nsplit = 1;
   if (nsplit > WN_MAX_WGRAD_SPLITS) nsplit = WN_MAX_WGRAD_SPLITS;
   if (nsplit > p.total_chunks) nsplit = p.total_chunks;
@@ -859,17 +930,10 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   p.slots = (p.chunks_per_split + p.chunks_t - 2) / p.chunks_t + 1;
   p.cs_partial = d.cs_partial;
   plan->nsplit = nsplit; plan->chunks_per_split = p.chunks_per_split; plan->chunks_t = p.chunks_t; plan->slots = p.slots; plan->mtiles = mtiles;
-  auto kern = tc_wgrad_kernel<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
-  }
-  kern<<<dim3(mtiles, ntiles, nsplit), 256, Cfg::SMEM_BYTES, st>>>(*ma[0], *ma[1], *ma[2], *ma[3], *mg, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "wgrad launch: %s", cudaGetErrorString(e)); return -13; }
-  return 0;
+  const dim3 grid(mtiles, ntiles, nsplit);
+  if (cl == 4) return tc_wgrad_launch_cl<BN, 4>(ma, mg, p, grid, st);
+  if (cl == 2) return tc_wgrad_launch_cl<BN, 2>(ma, mg, p, grid, st);
+  return tc_wgrad_launch_cl<BN, 1>(ma, mg, p, grid, st);
 }
 
 static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, TcWgradPlan* plan) {
