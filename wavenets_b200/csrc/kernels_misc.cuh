@@ -24,6 +24,40 @@ __global__ void input_conv_fwd(const float* __restrict__ x, int ldx, const float
   h[i] = from_f<T>(v);
 }
 
+// same, 8 channels per thread (R % 8 == 0): 16/32-byte stores, no per-element div/mod
+template <class T>
+__global__ void __launch_bounds__(256) input_conv_fwd_vec8(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                                                           T* __restrict__ h, int B, int Tn, int R, int K) {
+  const int r8 = R >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Tn * r8) return;
+  const int c = (int)(i % r8) << 3;
+  const long long row = i / r8;
+  const int t = (int)(row % Tn), b = (int)(row / Tn);
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = bias[c + j];
+#pragma unroll
+  for (int j = 8; j < 16; ++j) v[j] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int ts = t - (K - 1 - k);
+    if (ts >= 0) {
+      const float xv = x[(long long)b * ldx + ts];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(W[k * R + c + j], xv, v[j]);
+    }
+  }
+  T* o = h + row * R + c;
+  if constexpr (sizeof(T) == 2) {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(o) = q;
+  } else {
+    reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 // stage 1 of input conv wgrad: partial[(chunk)][k][c] = sum_{t in chunk} dh[b,t,c] * x[b,t-(K-1-k)], k==K => bias
 template <class T>
 __global__ void input_conv_bwd_stage1(const float* __restrict__ x, int ldx, const T* __restrict__ dh, int lddh, float* __restrict__ partial,
@@ -55,6 +89,29 @@ __global__ void reduce_parts(const float* __restrict__ partial, int n_parts, lon
   for (int i = 0; i < n_parts; ++i) s += partial[i * stride + j];
   if (addend) s = fmaf(add_coef, addend[j], s);
   out[j] = s;
+}
+
+// same contract for MANY partials (hundreds): 32 outputs x 8 partial-lanes per block, fixed summation order
+__global__ void __launch_bounds__(256) reduce_parts_tall(const float* __restrict__ partial, int n_parts, long long stride, float* __restrict__ out,
+                                                         long long n, const float* __restrict__ addend, float add_coef) {
+  __shared__ float red[8][33];
+  const int jl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const long long j = (long long)blockIdx.x * 32 + jl;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < n) {
+    int i = pl;
+    for (; i + 8 < n_parts; i += 16) { s0 += partial[i * stride + j]; s1 += partial[(i + 8) * stride + j]; }
+    if (i < n_parts) s0 += partial[i * stride + j];
+  }
+  red[pl][jl] = s0 + s1;
+  __syncthreads();
+  if (pl == 0 && j < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][jl];
+    if (addend) s = fmaf(add_coef, addend[j], s);
+    out[j] = s;
+  }
 }
 
 // column sums of G (B,T,N): stage 1 -> partial[b][chunk][n]
@@ -207,21 +264,29 @@ __global__ void cond_wgrad_all(const float* __restrict__ cond, int Cc, const flo
     grads[offs[2 * l + 1] + n] = s;
   }
 }
-// dcond[b][k] = sum_l sum_n dcb_l[b][n] Wc_l[k][n] ; one warp per output, fixed summation order
-__global__ void __launch_bounds__(128) cond_dgrad_all(const float* __restrict__ dcb, long long dcb_stride, const float* __restrict__ params,
+// dcond[b][k] = sum_l sum_n dcb_l[b][n] Wc_l[k][n] ; one block per output: 8 warps stride over the blocks l,
+// lanes over n; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) cond_dgrad_all(const float* __restrict__ dcb, long long dcb_stride, const float* __restrict__ params,
                                                       const int* __restrict__ offs, float* __restrict__ dcond, int L, int B, int Cc, int N) {
-  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i >= B * Cc) return;
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = i / Cc, k = i % Cc;
   float s = 0.f;
-  for (int l = 0; l < L; ++l) {
+  for (int l = w; l < L; l += 8) {
     const float* d = dcb + (long long)l * dcb_stride + (long long)b * N;
     const float* W = params + offs[2 * l] + (long long)k * N;
     for (int n = lane; n < N; n += 32) s = fmaf(d[n], W[n], s);
   }
   s = warp_sum(s);
-  if (lane == 0) dcond[(long long)b * Cc + k] = s;
+  if (lane == 0) red[w] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += red[j];
+    dcond[(long long)b * Cc + k] = tot;
+  }
 }
 
 // ------------------------------------------------------------------ softmax-256 cross entropy (model.py:114-118,516)

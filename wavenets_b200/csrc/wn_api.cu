@@ -344,7 +344,7 @@ static void layout_buffers(wn_handle* h) {
   h->dpA = W.take(rows * D * es);
   h->dpB = W.take(rows * D * es);
   // reductions
-  h->col_chunks = cdiv(h->maxT, 256);
+  h->col_chunks = cdiv(h->maxT, 64);   // input-conv wgrad partials use 64-row chunks; column sums 256-row chunks
   int nmax = 2 * D;
   if (R > nmax) nmax = R;
   if (Sp > nmax) nmax = Sp;
@@ -944,7 +944,10 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   {
     LaunchScope ls(h, st, CLS_MISC);
     const long long total = (long long)B * Tn * h->R;
-    input_conv_fwd<T><<<cdiv(total, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
+    if (h->R % 8 == 0)
+      input_conv_fwd_vec8<T><<<cdiv(total / 8, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
+    else
+      input_conv_fwd<T><<<cdiv(total, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
   }
   const void* cur = h->h0;
   for (int l = 0; l < h->L; ++l) {
@@ -1154,7 +1157,7 @@ static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, co
     }
     {
       LaunchScope ls(h, st, CLS_MISC);
-      cond_dgrad_all<<<cdiv(B * h->Cc, 4), 128, 0, st>>>(h->dcb, (long long)h->maxB * n, h->d_params, h->d_cond_offsets, dcond_out, h->L, B, h->Cc, n);
+      cond_dgrad_all<<<B * h->Cc, 256, 0, st>>>(h->dcb, (long long)h->maxB * n, h->d_params, h->d_cond_offsets, dcond_out, h->L, B, h->Cc, n);
     }
   } else
   for (int l = l0; l < l0 + nl; ++l) {
@@ -1274,20 +1277,20 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   }
   // ---- input conv (model.py:84-88): dW[k][c], db[c]
   {
-    const int chunks = cdiv(Tn, 256);
+    const int chunks = cdiv(Tn, 64);
     {
       LaunchScope ls(h, st, CLS_MISC);
-      input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 256);
+      input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 64);
     }
     const long long kr = (long long)h->K * h->R;
     {
       LaunchScope ls(h, st, CLS_MISC);
-      reduce_parts<<<cdiv(kr, 128), 128, 0, st>>>(h->colpart, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
-                                               l2coef != 0.f ? P_(h, h->input_conv.w_idx) : nullptr, l2coef);
+      reduce_parts_tall<<<cdiv(kr, 32), 256, 0, st>>>(h->colpart, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
+                                                   l2coef != 0.f ? P_(h, h->input_conv.w_idx) : nullptr, l2coef);
     }
     {
       LaunchScope ls(h, st, CLS_MISC);
-      reduce_parts<<<cdiv(h->R, 128), 128, 0, st>>>(h->colpart + kr, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
+      reduce_parts_tall<<<cdiv(h->R, 32), 256, 0, st>>>(h->colpart + kr, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
     }
   }
   if (c.conditioning) RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef));
