@@ -140,6 +140,8 @@ struct wn_handle {
   float* colpart = nullptr; int col_chunks = 0;
   float* wg_partial = nullptr; long long wg_partial_elems = 0;
   float* cs_partial = nullptr;            // [splits*slots][max N] column-sum partials of the tcgen05 wgrad
+  float* wg_partial_side = nullptr; float* cs_partial_side = nullptr;   // same, for wgrads issued on the side stream
+  void* dz2 = nullptr;                    // second dz buffer (side-stream wgrad of block l reads dz while block l-1 writes)
   float* loss_partial = nullptr; int loss_parts_cap = 0;
   float* cond_act[WN_MAX_LIST + 1] = {};  // mapping activations (B, width)
   float* cond_dact = nullptr;             // scratch (B, max width)
@@ -171,6 +173,10 @@ struct wn_handle {
   std::vector<StepGraph> graphs;
   int use_graphs = 1;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // backward on two streams: the weight-gradient kernels of a block run beside its dgrad chain
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> ev_blk_in, ev_blk_dz, ev_blk_done;
+  int use_side = 1;
 };
 
 enum { CLS_DILATED = 1, CLS_GEMM = 2, CLS_LOSS = 3, CLS_MISC = 4 };
@@ -341,6 +347,7 @@ static void layout_buffers(wn_handle* h) {
     h->dcatB = W.take(rows * (size_t)(R + h->S) * es);
   }
   h->dz = W.take(rows * 2 * D * es);
+  h->dz2 = W.take(rows * 2 * D * es);
   h->dpA = W.take(rows * D * es);
   h->dpB = W.take(rows * D * es);
   // reductions
@@ -363,12 +370,14 @@ static void layout_buffers(wn_handle* h) {
   for (auto& c : h->head) upd(c.cin, c.cout);
   h->wg_partial_elems = maxkn * WN_MAX_WGRAD_SPLITS;
   h->wg_partial = (float*)W.take((size_t)h->wg_partial_elems * 4);
+  h->wg_partial_side = (float*)W.take((size_t)h->wg_partial_elems * 4);
   if (bf) {
     int max_mt = 1;
     auto mt = [&](int K, int cin) { const int m = K * cdiv(cin, 128); if (m > max_mt) max_mt = m; };
     for (auto& b : h->blocks) { for (auto& c : b.stack) mt(c.K, c.cin); mt(1, D); }
     for (auto& c : h->head) mt(1, c.cin);
     h->cs_partial = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4);
+    h->cs_partial_side = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4);
   }
   h->loss_parts_cap = cdiv((long long)rows, 8) + 8;
   h->loss_partial = (float*)W.take((size_t)h->loss_parts_cap * 4);
@@ -526,6 +535,13 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming);
   { const char* e = getenv("WN_CUDA_GRAPH"); if (e && e[0] == '0') h->use_graphs = 0; }
+  { const char* e = getenv("WN_SIDE_STREAM"); if (e && e[0] == '0') h->use_side = 0; }
+  cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < h->L; ++i) {
+    cudaEvent_t a, b2, c2;
+    cudaEventCreateWithFlags(&a, cudaEventDisableTiming); cudaEventCreateWithFlags(&b2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c2, cudaEventDisableTiming);
+    h->ev_blk_in.push_back(a); h->ev_blk_dz.push_back(b2); h->ev_blk_done.push_back(c2);
+  }
   // offsets of the per-block skip biases (or conv1 biases when aliased) for bskip_sum
   {
     std::vector<int> offs;
@@ -553,6 +569,10 @@ extern "C" void wn_destroy(wn_handle* h) {
   cudaDeviceSynchronize();
   for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto e : h->ev_blk_in) cudaEventDestroy(e);
+  for (auto e : h->ev_blk_dz) cudaEventDestroy(e);
+  for (auto e : h->ev_blk_done) cudaEventDestroy(e);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   cudaFree(h->d_params); cudaFree(h->d_grads); cudaFree(h->pack.base); cudaFree(h->ws.base);
@@ -753,6 +773,7 @@ struct WgradH {
   float* bias_dst = nullptr; float* per_batch = nullptr; int ldpb = 0;
   // bf16 tier only: columns [N0, N) belong to a second variable (conv1 | conv_skip in one launch)
   int N0 = 0; float* dst1 = nullptr; const float* w1 = nullptr; float* bias1 = nullptr;
+  bool side = false;   // issued on the side stream: uses the side copies of the partial buffers
 };
 
 template <class T>
@@ -787,9 +808,11 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     TcWgradDesc d;
     d.B = g.B; d.T = g.T; d.N = g.N; d.G = (const bf16*)g.G; d.ldg = g.ldg; d.nseg = g.nseg; d.ktot = ktot;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
-    d.partial = h->wg_partial;
+    float* const wgp = g.side ? h->wg_partial_side : h->wg_partial;
+    float* const csp = g.side ? h->cs_partial_side : h->cs_partial;
+    d.partial = wgp;
     const bool want_cs = g.bias_dst || g.per_batch || g.bias1;
-    d.cs_partial = want_cs ? h->cs_partial : nullptr;
+    d.cs_partial = want_cs ? csp : nullptr;
     TcWgradPlan plan{};
     {
       LaunchScope ls(h, st, cls);
@@ -797,10 +820,10 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
       if (r != 0) { set_err("tcgen05 wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
     }
     TcWgradFinish f{};
-    f.partial = h->wg_partial; f.nsplit = plan.nsplit; f.ktot = ktot; f.N = g.N; f.N0 = g.dst1 ? g.N0 : g.N;
+    f.partial = wgp; f.nsplit = plan.nsplit; f.ktot = ktot; f.N = g.N; f.N0 = g.dst1 ? g.N0 : g.N;
     f.dst0 = g.dst; f.dst1 = g.dst1; f.l2coef = g.l2coef;
     f.w0 = g.l2coef != 0.f ? g.w : nullptr; f.w1 = g.l2coef != 0.f ? g.w1 : nullptr;
-    f.cs = h->cs_partial; f.slots = plan.slots; f.cps = plan.chunks_per_split; f.chunks_t = plan.chunks_t; f.B = g.B; f.mtiles = plan.mtiles;
+    f.cs = csp; f.slots = plan.slots; f.cps = plan.chunks_per_split; f.chunks_t = plan.chunks_t; f.B = g.B; f.mtiles = plan.mtiles;
     f.bias0 = g.bias_dst; f.bias1 = g.bias1; f.per_batch = g.per_batch; f.ldpb = g.ldpb;
     f.wblocks = cdiv((long long)ktot * g.N, 256);
     LaunchScope ls(h, st, cls);
@@ -1023,10 +1046,24 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
 // ============================================================================ backward pieces
 // adjoint of block_forward.  dxout / dskip may be null (zero).  Writes dx_in (if non-null) and
 // this block's parameter gradients.  dcb row l gets per-batch sums of dz when conditioned.
+// Two-stream schedule of one block's backward: the dgrad chain (gate adjoint -> dgrad) is the critical path on
+// the main stream; the weight-gradient kernels only consume, so they run on a side stream and fill the SMs the
+// persistent GEMMs leave idle in their last partial wave.  Events order producer -> consumer and protect the
+// ping-pong buffers (dz, d x_out) from being overwritten while a side kernel still reads them.
+struct BwdSide {
+  cudaStream_t side;
+  cudaEvent_t ev_in;     // recorded on MAIN by the caller: this block's upstream gradients are complete
+  cudaEvent_t ev_dz;     // recorded on MAIN here: dz of this block is complete
+  cudaEvent_t ev_done;   // recorded on SIDE here: all side work of this block is complete
+  cudaEvent_t wait_dz;   // MAIN waits before writing dz      (side work of block l+2 read the same buffer), may be null
+  cudaEvent_t wait_dx;   // MAIN waits before writing dx_in   (side work of block l+1 read that buffer), may be null
+};
+
 template <class T>
 static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in, const void* dxout, int ldxo, const void* dskip, int ldsk,
-                          void* dx_in, int ldxi, int B, int Tn, float l2coef) {
+                          void* dx_in, int ldxi, int B, int Tn, float l2coef, void* dzbuf = nullptr, const BwdSide* sd = nullptr) {
   BlockP& b = h->blocks[l];
+  if (!dzbuf) dzbuf = h->dz;
   const int depth = (int)b.stack.size();
   const size_t rows_cap = (size_t)h->maxB * h->maxT;
   const long long nR = (long long)B * Tn * h->R;
@@ -1049,19 +1086,24 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       ld_o = ldsk;
     }
   }
-  // ---- conv1 / conv_skip weight + bias grads
+  // ---- conv1 / conv_skip weight + bias grads (side stream unless they read the shared d_o scratch)
+  const bool side1 = sd != nullptr && d_o != h->dotmp;
+  cudaStream_t s1 = side1 ? sd->side : st;
+  if (side1) CK(cudaStreamWaitEvent(sd->side, sd->ev_in, 0));
   if (cat) {
     WgradH w{};
     w.B = B; w.T = Tn; w.N = R + S; w.G = dxout; w.ldg = ldxo; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
     w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef; w.bias_dst = G_(h, b.conv1.b_idx);
     w.N0 = R; w.dst1 = G_(h, b.conv_skip.w_idx); w.w1 = P_(h, b.conv_skip.w_idx); w.bias1 = G_(h, b.conv_skip.b_idx);
-    RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+    w.side = side1;
+    RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
   } else if (d_o) {
     WgradH w{};
     w.B = B; w.T = Tn; w.N = R; w.G = d_o; w.ldg = ld_o; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
     w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef;
     w.bias_dst = G_(h, b.conv1.b_idx);
-    RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+    w.side = side1;
+    RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
   } else {
     cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
     cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
@@ -1072,7 +1114,8 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       w.B = B; w.T = Tn; w.N = S; w.G = dskip; w.ldg = ldsk; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
       w.dst = G_(h, b.conv_skip.w_idx); w.w = P_(h, b.conv_skip.w_idx); w.l2coef = l2coef;
       w.bias_dst = G_(h, b.conv_skip.b_idx);
-      RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+      w.side = side1;
+      RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
     } else {
       cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
       cudaMemsetAsync(G_(h, b.conv_skip.b_idx), 0, h->params[b.conv_skip.b_idx].count * 4, st);
@@ -1097,11 +1140,13 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     g.W32 = b.Wdg ? b.Wdg + (size_t)koff * b.Dpad : nullptr; g.Npad = b.Dpad;
     g.W16 = b.Wdg16 ? b.Wdg16 + koff : nullptr; g.ktot16 = rup(rs, 64); g.N16 = b.Dpad; g.tile16 = 0;
     typename EpiGateBwd<T, sizeof(T) == 2>::Params ep{};
-    ep.z = (const T*)h->zbuf[l]; ep.dz = (T*)h->dz; ep.D = D; ep.vec = vec_ok<T>(D);
+    ep.z = (const T*)h->zbuf[l]; ep.dz = (T*)dzbuf; ep.D = D; ep.vec = vec_ok<T>(D);
+    if (sd && sd->wait_dz) CK(cudaStreamWaitEvent(st, sd->wait_dz, 0));
     RET((run_conv_gemm<T, EpiGateBwd<T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
+    if (sd) CK(cudaEventRecord(sd->ev_dz, st));
   }
   // ---- walk the dilated stack downwards
-  const void* dcur = h->dz;
+  const void* dcur = dzbuf;
   int dcw = 2 * D;
   for (int j = depth - 1; j >= 0; --j) {
     const ConvP& c = b.stack[j];
@@ -1116,7 +1161,11 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       w.B = B; w.T = Tn; w.N = c.cout; w.G = dcur; w.ldg = dcw; w.nseg = c.K;
       for (int k = 0; k < c.K; ++k) w.seg[k] = SegH{a_in, a_w, -(c.K - 1 - k) * c.dil, c.cin};
       w.dst = G_(h, c.w_idx); w.w = P_(h, c.w_idx); w.l2coef = l2coef;
-      RET(run_wgrad<T>(h, st, CLS_DILATED, w));
+      // the gated conv's wgrad reads dz and forward activations only: side stream
+      const bool side2 = sd != nullptr && j == depth - 1;
+      if (side2) CK(cudaStreamWaitEvent(sd->side, sd->ev_dz, 0));
+      w.side = side2;
+      RET(run_wgrad<T>(h, side2 ? sd->side : st, CLS_DILATED, w));
     }
     // dgrad
     const bool need = j > 0 || dx_in != nullptr;
@@ -1138,10 +1187,12 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         ep.out = (T*)dx_in; ep.ldo = ldxi;
         ep.add = (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr; ep.lda = ldxo;
         ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(R);
+        if (sd && sd->wait_dx) CK(cudaStreamWaitEvent(st, sd->wait_dx, 0));
         RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
       }
     }
   }
+  if (sd) CK(cudaEventRecord(sd->ev_done, sd->side));
   return WN_OK;
 }
 
@@ -1206,9 +1257,22 @@ static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, co
   return WN_OK;
 }
 
+// per-block events of the two-stream backward (see BwdSide); records "upstream gradients ready" on the main stream
+static const BwdSide* side_setup(wn_handle* h, cudaStream_t st, int l, bool on, BwdSide* sd) {
+  if (!on) return nullptr;
+  sd->side = h->side_stream;
+  sd->ev_in = h->ev_blk_in[l]; sd->ev_dz = h->ev_blk_dz[l]; sd->ev_done = h->ev_blk_done[l];
+  sd->wait_dz = l + 2 < h->L ? h->ev_blk_done[l + 2] : nullptr;
+  sd->wait_dx = l + 1 < h->L ? h->ev_blk_done[l + 1] : nullptr;
+  cudaEventRecord(sd->ev_in, st);
+  return sd;
+}
+
 template <class T>
 static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx, const float* cond_in, int B, int Tn, float l2coef) {
   const wn_config& c = h->cfg;
+  // (bf16 tier only: the fp32 tier's wgrad / column-sum scratch buffers are not duplicated for a second stream)
+  const bool use_side = sizeof(T) == 2 && h->use_side && h->prof_tag == 0 && h->side_stream != nullptr;
   const bool cat = sizeof(T) == 2 && h->dcatA != nullptr;
   const int ldc = h->R + h->S;
   // ---- head
@@ -1259,7 +1323,8 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     for (int l = h->L - 1; l >= 0; --l) {
       const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
       const void* dsk = cur ? (const void*)((const T*)cur + h->R) : (const void*)((const T*)h->dcatA + h->R);
-      RET(block_backward<T>(h, st, l, x_in, cur, ldc, dsk, ldc, nxt, ldc, B, Tn, l2coef));
+      BwdSide sd; const BwdSide* sdp = side_setup(h, st, l, use_side, &sd);
+      RET(block_backward<T>(h, st, l, x_in, cur, ldc, dsk, ldc, nxt, ldc, B, Tn, l2coef, (l & 1) ? h->dz2 : h->dz, sdp));
       cur = nxt;
       nxt = (nxt == h->dcatB) ? h->dcatA : h->dcatB;
     }
@@ -1270,11 +1335,14 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     for (int l = h->L - 1; l >= 0; --l) {
       const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
       void* dx_in = (dxout == h->dxA) ? h->dxB : h->dxA;
-      RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef));
+      BwdSide sd; const BwdSide* sdp = side_setup(h, st, l, use_side, &sd);
+      RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef, (l & 1) ? h->dz2 : h->dz, sdp));
       dxout = dx_in;
     }
     ld_dx = h->R;
   }
+  // join: every side-stream wgrad (and its finish kernel) is complete before anything below reads the gradients
+  if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
   // ---- input conv (model.py:84-88): dW[k][c], db[c]
   {
     const int chunks = cdiv(Tn, 64);
