@@ -240,7 +240,7 @@ def main():
   ms_total = max_over_ranks(e0.elapsed_time(e1))
   launches = int(h.lib.wn_last_launch_count(h.h)) * args.steps
   clocks = sampler.stop() if sampler else None
-  loss_last = float(loss_t.item())
+  loss_last = float(loss_t[0].item())
 
   # ---- timed region 2: end to end through the public API with HOST buffers
   sync_all()
@@ -291,7 +291,7 @@ def main():
                'params': int(h.n_scalars), 'parallelism': f'dp{world}',
                'l2': 'per-step working set (activations cached for backward) is GBs >> 126 MB L2; no explicit flush needed',
                'flops_per_sample_fwd_bwd': 3 * flops['total']},
-    'e2e': {'value': world * rows * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+    'e2e': {'value': world * rows * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
             'ms_per_step': ms_e2e / args.steps},
     'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'whole_step': whole,
     'loss': {'first': loss0, 'last': loss_last, 'e2e_last': out['loss']},

@@ -69,7 +69,7 @@ typedef struct wn_config {
   int32_t n_final;                     /* len(final_layers_channels)                            */
   int32_t final_layers_channels[WN_MAX_LIST];
   float   l2_reg_factor;
-  float   dropout;                     /* accepted; training with dropout>0 is WN_ERR_UNSUPPORTED */
+  float   dropout;                     /* layers.py:109-112: inverted dropout on each block's conv branch, training passes only */
   /* explicit per-conv dilations (blocks*layers_per_block entries) — used by the bare
    * WaveNetLayer mirror (layers.py:10-20 `dilation_rate`); 0 => model.py:79-81 schedule.      */
   int32_t n_dilations;
@@ -106,6 +106,13 @@ int wn_get_grad(wn_handle* h, int i, float* host);
  * kernel-side weight copies (transposes, gate interleave, bf16). */
 int wn_params_changed(wn_handle* h, void* stream);
 
+/* ---- dropout (layers.py:109-112,195-196; Keras Dropout on the block input of the conv branch) --------
+ * Training passes draw keep-masks with a counter-based Philox-4x32-10 keyed by (seed, step): TF's RNG
+ * stream cannot be reproduced, so parity runs inject the masks instead.
+ * keep_host: [blocks][B*T*channels] bytes (1 = keep), NULL returns to Philox masks. */
+int wn_set_dropout_masks(wn_handle* h, const uint8_t* keep_host, int B, int T);
+int wn_set_dropout_seed(wn_handle* h, uint64_t seed);
+
 /* ---- target quantiser (model.py:151-155,320: Keras Discretization) ----------------------- */
 /* idx[i] = #{k in 1..2^bits-1 : -1 + k*2^(1-bits) <= x[i]}, bit-exact, comparison based */
 int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void* stream);
@@ -115,13 +122,15 @@ int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void*
 int wn_forward(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, float* out_dev, void* stream);
 
 /* ---- WaveNet.train_step up to the gradients (model.py:309-335) and test_step (:362-381) ---
- * frames (B,T+1) fp32 in [-1,1]; loss = sum_{b,t} l / (B*n_replicas) written to loss_dev[0];
- * gradients of every trainable variable land in wn_grads_dev() (overwritten). */
+ * frames (B,T+1) fp32 in [-1,1]; loss_dev points at TWO floats, the reference's two metrics
+ * (model.py:340-344): loss_dev[0] = sum_{b,t} l / (B*n_replicas)  ('loss', compute_average_loss),
+ * loss_dev[1] = l2_reg_factor * sum(kernel^2) / n_replicas ('reg_loss', 0 when l2_reg_factor == 0);
+ * the gradients are those of their sum (model.py:334-335) and land in wn_grads_dev() (overwritten). */
 int wn_train_step(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T,
                   int n_replicas, float* loss_dev, void* stream);
 int wn_test_step(wn_handle* h, const float* frames_dev, const float* cond_dev, int B, int T,
                  int n_replicas, float* loss_dev, void* stream);
-/* same with HOST buffers: H2D of frames/cond, step, D2H of the loss, stream sync. */
+/* same with HOST buffers: H2D of frames/cond, step, D2H of the two loss floats, stream sync. */
 int wn_train_step_host(wn_handle* h, const float* frames_host, const float* cond_host, int B, int T,
                        int n_replicas, float* loss_host);
 

@@ -248,15 +248,19 @@ def mu_law(x):
 
 
 # --------------------------------------------------------------------------- layer
-def layer_forward(p: Dict[str, np.ndarray], prefix: str, cfg_layer: dict, x, cond=None):
-  """WaveNetLayer.call (layers.py:178-224), dropout disabled.
+def layer_forward(p: Dict[str, np.ndarray], prefix: str, cfg_layer: dict, x, cond=None, keep=None, rate=0.0):
+  """WaveNetLayer.call (layers.py:178-224).
   cfg_layer: dict(dilations=[...], activation=str|None, residual=bool, has_skip=bool, condition=bool).
   cond: (B,T,Cc) or (B,Cc) (time-constant global conditioning).
+  keep/rate: training-mode dropout (layers.py:195-196) with an explicit keep-mask (B,T,R): the conv
+  branch sees x*keep/(1-rate), the residual is taken before it (layers.py:192-193).  keep=None: off.
   Returns x_out, skip, cache."""
   dils = cfg_layer['dilations']
   act = cfg_layer['activation'] if len(dils) > 1 else None
-  cache = {'x_in': x, 'stack_in': [], 'stack_out': []}
+  cache = {'x_in': x, 'stack_in': [], 'stack_out': [], 'keep': keep, 'rate': rate}
   h = x
+  if keep is not None:
+    h = x * keep.astype(x.dtype) / x.dtype.type(1.0 - rate)
   for j, d in enumerate(dils):
     cache['stack_in'].append(h)
     h = causal_conv_fwd(h, p[f'{prefix}/dil{j}/kernel'], p[f'{prefix}/dil{j}/bias'], d)
@@ -328,6 +332,8 @@ def layer_backward(p, prefix, cfg_layer, cache, dx_out, dskip, need_dx=True):
     grads[f'{prefix}/dil{j}/bias'] = db
     dh = dh_in
   dx = dh
+  if need_dx and cache.get('keep') is not None:
+    dx = dx * cache['keep'].astype(dx.dtype) / dx.dtype.type(1.0 - cache['rate'])
   if need_dx and cfg_layer['residual'] and dx_out is not None:
     dx = dx + dx_out
   return dx, dcond, grads
@@ -351,9 +357,10 @@ def mapping_forward(p, cfg: Config, cond_in):
   return h, acts
 
 
-def model_forward(p, cfg: Config, x, cond_in=None, return_logits=False):
+def model_forward(p, cfg: Config, x, cond_in=None, return_logits=False, keep_masks=None):
   """WaveNet.call (model.py:213-239).  x (B,T,1); cond_in (B,cond_in).  Returns the model
-  output (softmax probabilities or 3M mixture parameters) and a cache for backward."""
+  output (softmax probabilities or 3M mixture parameters) and a cache for backward.
+  keep_masks: per-block dropout keep-masks (training mode, see layer_forward) or None."""
   cache = {'x': x, 'cond_in': cond_in}
   cond = None
   if cfg.conditioning == 'global':
@@ -361,7 +368,7 @@ def model_forward(p, cfg: Config, x, cond_in=None, return_logits=False):
   h = causal_conv_fwd(x, p['causal/kernel'], p['causal/bias'], 1)
   skips, lcaches = [], []
   for b, lc in enumerate(_layer_cfgs(cfg)):
-    h, skip, c = layer_forward(p, f'block{b}', lc, h, cond)
+    h, skip, c = layer_forward(p, f'block{b}', lc, h, cond, keep=None if keep_masks is None else keep_masks[b], rate=cfg.dropout)
     skips.append(skip)
     lcaches.append(c)
   if cfg.use_skip:
@@ -434,28 +441,44 @@ def loss_and_dlogits(cfg: Config, logits, y, scale):
   return loss, np.concatenate([dw, dmu, dls], axis=-1) * scale
 
 
-def train_step(p, cfg: Config, x_frames, cond_in=None, n_replicas: int = 1):
+def train_step(p, cfg: Config, x_frames, cond_in=None, n_replicas: int = 1, keep_masks=None):
   """train_step (model.py:309-335) up to the gradients: returns (loss, grads, aux).
   x_frames: (B,T+1,1).  loss = sum_{b,t} l[b,t] / (B * n_replicas)  (compute_average_loss)."""
   cfg.validate()
   dt = x_frames.dtype
   y = x_frames[:, 1:, :]
   inputs = x_frames[:, :-1, :]
-  logits, cache = model_forward(p, cfg, inputs, cond_in, return_logits=True)
+  logits, cache = model_forward(p, cfg, inputs, cond_in, return_logits=True, keep_masks=keep_masks)
   B = x_frames.shape[0]
   scale = dt.type(1.0 / (B * n_replicas))
   lpt, dlogits = loss_and_dlogits(cfg, logits, y, scale)
   loss = lpt.sum() * scale
   grads = model_backward(p, cfg, cache, dlogits)
+  loss_no_reg = float(loss)
+  reg = 0.0
   if cfg.l2_reg_factor > 0:
     # model.py:331-334: reg * sum(w^2) over kernels, scaled by 1/replicas
-    reg = 0.0
     for name, _ in param_specs(cfg):
       if name.endswith('kernel'):
         reg += cfg.l2_reg_factor * float((p[name] ** 2).sum())
         grads[name] = grads[name] + 2.0 * cfg.l2_reg_factor * p[name] / n_replicas
     loss = loss + reg / n_replicas
-  return float(loss), grads, {'loss_per_sample': lpt, 'logits': logits, 'dlogits': dlogits, 'cache': cache}
+  # the reference reports the two parts separately (metrics 'loss' and 'reg_loss', model.py:340-344)
+  return float(loss), grads, {'loss_per_sample': lpt, 'logits': logits, 'dlogits': dlogits, 'cache': cache,
+                              'loss_no_reg': loss_no_reg, 'reg_loss': reg / n_replicas}
+
+
+def sample_deterministic(cfg: Config, pred):
+  """sample_waveform(pred, deterministic=True) (model.py:411-418,452-459,484-499): categorical ->
+  argmax bin mapped to [-1,1) as idx/2^(bits-1) - 1, shape (B,T); mixtures -> mean of the heaviest
+  component clipped to [-1,1], shape (B,T,1).  pred = model output (probabilities / 3M params)."""
+  if cfg.num_mixtures is None:
+    idx = np.argmax(pred, axis=-1)
+    return idx.astype(pred.dtype) / pred.dtype.type(2.0 ** (cfg.bits - 1)) - pred.dtype.type(1.0)
+  M = cfg.num_mixtures
+  sel = np.argmax(pred[..., :M], axis=-1)
+  mu = np.take_along_axis(pred[..., M:2 * M], sel[..., None], axis=-1)
+  return np.clip(mu, -1.0, 1.0)
 
 
 def model_backward(p, cfg: Config, cache, dlogits):

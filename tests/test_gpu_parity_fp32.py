@@ -53,7 +53,10 @@ def test_train_step_matches_oracle(name, BT):
   m, cfg, p, x, cond = _model_and_oracle(kw, B, T)
   loss_o, g_o, aux = wo.train_step(p, cfg, x.astype(np.float64), None if cond is None else cond.astype(np.float64))
   out = m.train_step((x, cond) if cond is not None else x)
-  assert abs(out['loss'] - loss_o) <= TOL * abs(loss_o), (out['loss'], loss_o)
+  # the reference reports the regulariser separately (metrics 'loss' and 'reg_loss', model.py:340-344)
+  assert abs(out['loss'] - aux['loss_no_reg']) <= TOL * abs(loss_o), (out['loss'], aux['loss_no_reg'])
+  assert abs(out.get('reg_loss', 0.0) - aux['reg_loss']) <= TOL * abs(loss_o)
+  assert ('reg_loss' in out) == (cfg.l2_reg_factor > 0)
   g = m.get_grads()
   for k in g_o:
     assert rel_err(g[k], g_o[k]) < TOL, (k, rel_err(g[k], g_o[k]))
@@ -63,7 +66,7 @@ def test_train_step_matches_oracle(name, BT):
   assert pred.shape == pred_o.shape
   assert rel_err(pred, pred_o) < TOL
   # test_step = same loss without gradients
-  assert abs(m.test_step((x, cond) if cond is not None else x)['loss'] - loss_o) <= TOL * abs(loss_o)
+  assert abs(m.test_step((x, cond) if cond is not None else x)['loss'] - aux['loss_no_reg']) <= TOL * abs(loss_o)
 
 
 LAYERS = {

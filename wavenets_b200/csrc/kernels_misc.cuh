@@ -157,6 +157,55 @@ __global__ void add2_kernel(const T* __restrict__ a, const T* __restrict__ b, T*
   if (i < n) out[i] = from_f<T>(to_f(a[i]) + (b ? to_f(b[i]) : 0.f));
 }
 
+// ------------------------------------------------------------------ dropout (layers.py:109-112,195-196)
+// Inverted dropout on the conv branch of a block (the residual is taken before it, layers.py:192-193).
+// Keep-masks are one byte per element, [block][b*T+t][r]; either injected by the caller (parity tests: TF's RNG
+// stream cannot be reproduced) or drawn here with Philox-4x32-10 keyed by (seed, step counter): counter-based,
+// so the backward pass re-reads the same bytes and a replayed CUDA graph still gets fresh masks every step.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__global__ void dropout_step_bump(unsigned long long* ctr) { ctr[0] += 1ull; }
+// n4 = groups of 4 elements per block slab; slab stride in bytes between blocks
+__global__ void dropout_mask_philox(uint8_t* __restrict__ mask, long long n4, long long slab_stride, float rate, unsigned long long seed,
+                                    const unsigned long long* __restrict__ step_ctr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const unsigned long long step = step_ctr[0];
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), blockIdx.y, (uint32_t)step),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+  const float sc = 1.0f / 16777216.0f;
+  uchar4 m;
+  m.x = (float)(r.x >> 8) * sc >= rate; m.y = (float)(r.y >> 8) * sc >= rate;
+  m.z = (float)(r.z >> 8) * sc >= rate; m.w = (float)(r.w >> 8) * sc >= rate;
+  reinterpret_cast<uchar4*>(mask + (long long)blockIdx.y * slab_stride)[i] = m;
+}
+// xd = keep ? x / (1 - rate) : 0
+template <class T>
+__global__ void dropout_apply(const T* __restrict__ x, const uint8_t* __restrict__ keep, T* __restrict__ xd, long long n, float inv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) xd[i] = from_f<T>(keep[i] ? to_f(x[i]) * inv : 0.f);
+}
+// dx[row][c] = (keep ? draw / (1 - rate) : 0) + add[row][c]   (add: residual gradient, may be null)
+template <class T>
+__global__ void dropout_bwd(const T* __restrict__ draw, const uint8_t* __restrict__ keep, const T* __restrict__ add, int ld_add,
+                            T* __restrict__ out, int ld_out, long long rows, int R, float inv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * R) return;
+  const long long row = i / R;
+  const int c = (int)(i % R);
+  float v = keep[i] ? to_f(draw[i]) * inv : 0.f;
+  if (add) v += to_f(add[row * ld_add + c]);
+  out[row * ld_out + c] = from_f<T>(v);
+}
+
 // ------------------------------------------------------------------ weight packing
 // dst[r][c] (ld = dst_ld, pre-zeroed) from Keras-layout src (rows x cols, row-major):
 //   mode 0: dst[r][c]  = src[r][c]
@@ -428,7 +477,8 @@ __global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restri
   }
 }
 
-// final loss: out[0] = scale * sum(partial) + extra   (single block, deterministic)
+// final loss: out[0] = scale * sum(partial) (metric 'loss'), out[1] = extra_coef * extra (metric 'reg_loss', model.py:340-344)
+// (single block, deterministic)
 __global__ void loss_finalize(const float* __restrict__ partial, int n, float scale, const float* __restrict__ extra, float extra_coef,
                               float* __restrict__ out) {
   __shared__ float sh[32];
@@ -440,7 +490,7 @@ __global__ void loss_finalize(const float* __restrict__ partial, int n, float sc
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) out[0] = v * scale + (extra ? extra_coef * extra[0] : 0.f);
+    if (threadIdx.x == 0) { out[0] = v * scale; out[1] = extra ? extra_coef * extra[0] : 0.f; }
   }
 }
 

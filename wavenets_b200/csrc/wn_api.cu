@@ -150,6 +150,14 @@ struct wn_handle {
   float* dcb = nullptr;                   // [L][B][2D]
   float* dcond = nullptr;                 // (B,Cc)
   float* l2_sum = nullptr;
+  // dropout (layers.py:195-196): keep-masks [L][maxB*maxT*R] bytes, dropped block inputs, raw dgrad scratch
+  uint8_t* drop_mask = nullptr;
+  std::vector<void*> xdrop;
+  void* ddrop = nullptr;
+  unsigned long long* d_drop_ctr = nullptr;
+  unsigned long long drop_seed = 0x243F6A8885A308D3ull;
+  bool drop_injected = false;   // masks were supplied by wn_set_dropout_masks: do not redraw
+  bool drop_active = false;     // the pass being enqueued is a training pass with dropout > 0
   float* layer_xin = nullptr;             // layer API staging (fp32 in -> T)
   void* layer_in = nullptr;
   float* d_loss = nullptr;                // for the host-buffer entry point
@@ -392,6 +400,13 @@ static void layout_buffers(wn_handle* h) {
     h->dcond = (float*)W.take((size_t)h->maxB * (h->Cc > 0 ? h->Cc : 1) * 4);
   }
   h->l2_sum = (float*)W.take(16);
+  if (h->cfg.dropout > 0.f) {
+    h->drop_mask = (uint8_t*)W.take((size_t)L * rows * R);
+    h->xdrop.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) h->xdrop[l] = W.take(rows * R * es);
+    h->ddrop = W.take(rows * R * es);
+    h->d_drop_ctr = (unsigned long long*)W.take(16);
+  }
   h->d_loss = (float*)W.take(16);
   h->layer_in = W.take(rows * R * es);
   h->d_frames = (float*)W.take((size_t)h->maxB * (h->maxT + 1) * 4);
@@ -897,6 +912,14 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
   const size_t rows_cap = (size_t)h->maxB * h->maxT;
   const void* cur = x_in;
   int curw = h->R;
+  if (h->drop_active) {
+    // training-mode dropout on the conv branch only; the residual below still reads x_in (layers.py:192-196)
+    LaunchScope ls(h, st, CLS_MISC);
+    const long long n = (long long)B * Tn * h->R;
+    dropout_apply<T><<<cdiv(n, 256), 256, 0, st>>>((const T*)x_in, h->drop_mask + (size_t)l * rows_cap * h->R, (T*)h->xdrop[l], n,
+                                                  1.0f / (1.0f - h->cfg.dropout));
+    cur = h->xdrop[l];
+  }
   for (int j = 0; j < depth; ++j) {
     const ConvP& c = b.stack[j];
     GemmH g;
@@ -1150,7 +1173,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
   int dcw = 2 * D;
   for (int j = depth - 1; j >= 0; --j) {
     const ConvP& c = b.stack[j];
-    const void* a_in = j == 0 ? x_in : h->acts[l][j - 1];
+    const void* a_in = j == 0 ? (h->drop_active ? (const void*)h->xdrop[l] : x_in) : h->acts[l][j - 1];
     const int a_w = j == 0 ? R : D;
     // weight grad: rows (k, cin) <- taps of a_in shifted by -(K-1-k)*d ; the bias grad (and the
     // conditioning per-batch sums for the gated conv) are the column sums of the same G
@@ -1183,6 +1206,15 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
         dcur = dst;
         dcw = D;
+      } else if (h->drop_active) {
+        // d(conv branch input) first, then dx = keep/(1-p) * that + residual gradient
+        ep.out = (T*)h->ddrop; ep.ldo = R; ep.add = nullptr; ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(R);
+        RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
+        if (sd && sd->wait_dx) CK(cudaStreamWaitEvent(st, sd->wait_dx, 0));
+        LaunchScope ls(h, st, CLS_MISC);
+        dropout_bwd<T><<<cdiv(nR, 256), 256, 0, st>>>((const T*)h->ddrop, h->drop_mask + (size_t)l * rows_cap * R,
+                                                     (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr, ldxo, (T*)dx_in, ldxi,
+                                                     (long long)B * Tn, R, 1.0f / (1.0f - h->cfg.dropout));
       } else {
         ep.out = (T*)dx_in; ep.ldo = ldxi;
         ep.add = (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr; ep.lda = ldxo;
@@ -1375,6 +1407,33 @@ static int check_bt(wn_handle* h, int B, int T) {
   return WN_OK;
 }
 
+static void drop_graphs(wn_handle* h) {
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+extern "C" int wn_set_dropout_masks(wn_handle* h, const uint8_t* keep_host, int B, int T) {
+  RET(check_bt(h, B, T));
+  if (h->cfg.dropout <= 0.f || !h->drop_mask) { set_err("model was built with dropout == 0"); return WN_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  drop_graphs(h);
+  if (!keep_host) { h->drop_injected = false; return WN_OK; }
+  const size_t n = (size_t)B * T * h->R, slab = (size_t)h->maxB * h->maxT * h->R;
+  for (int l = 0; l < h->L; ++l) CK(cudaMemcpy(h->drop_mask + l * slab, keep_host + l * n, n, cudaMemcpyHostToDevice));
+  h->drop_injected = true;
+  return WN_OK;
+}
+extern "C" int wn_set_dropout_seed(wn_handle* h, uint64_t seed) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  drop_graphs(h);
+  h->drop_seed = seed;
+  h->drop_injected = false;
+  if (h->d_drop_ctr) CK(cudaMemset(h->d_drop_ctr, 0, 8));
+  return WN_OK;
+}
+
 extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void* stream) {
   if (n == 0) return WN_OK;  /* empty input: nothing to do */
   if (!x_dev || !idx_dev || n < 0 || bits < 1 || bits > 16) { set_err("bad quantize arguments"); return WN_ERR_VALUE; }
@@ -1385,6 +1444,7 @@ extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int 
 
 template <class T>
 static int forward_entry(wn_handle* h, const float* x, const float* cond, int B, int Tn, float* out, cudaStream_t st) {
+  h->drop_active = false;   // WaveNet.call(training=False)
   RET(model_forward<T>(h, st, x, Tn, cond, B, Tn));
   if (h->cfg.sampling_function == WN_CATEGORICAL) {
     RET(loss_forward<T>(h, st, nullptr, B, Tn, 0.f, false, out, nullptr));
@@ -1411,6 +1471,15 @@ extern "C" int wn_forward(wn_handle* h, const float* x_dev, const float* cond_de
 template <class T>
 static int step_entry(wn_handle* h, const float* frames, const float* cond, int B, int Tn, int nrep, float* loss, cudaStream_t st, bool train) {
   const float scale = 1.0f / ((float)B * (float)nrep);
+  h->drop_active = train && h->cfg.dropout > 0.f;
+  if (h->drop_active && !h->drop_injected) {
+    const size_t rows_cap = (size_t)h->maxB * h->maxT;
+    const long long n4 = ((long long)B * Tn * h->R + 3) / 4;
+    { LaunchScope ls(h, st, CLS_MISC); dropout_step_bump<<<1, 1, 0, st>>>(h->d_drop_ctr); }
+    LaunchScope ls(h, st, CLS_MISC);
+    dropout_mask_philox<<<dim3(cdiv(n4, 256), h->L), 256, 0, st>>>(h->drop_mask, n4, (long long)rows_cap * h->R, h->cfg.dropout, h->drop_seed,
+                                                                  h->d_drop_ctr);
+  }
   RET(model_forward<T>(h, st, frames, Tn + 1, cond, B, Tn));
   RET(loss_forward<T>(h, st, frames, B, Tn, scale, train, nullptr, loss));
   if (train) {
@@ -1425,7 +1494,7 @@ static int step_common(wn_handle* h, const float* frames_dev, const float* cond_
   if (!h->cfg.has_head || !h->cfg.has_input_conv) { set_err("train/test step needs a full model handle"); return WN_ERR_STATE; }
   if (h->cfg.conditioning && !cond_dev) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
   if (n_replicas < 1 || !frames_dev || !loss_dev) { set_err("bad step arguments"); return WN_ERR_VALUE; }
-  if (train && h->cfg.dropout > 0.f) { set_err("training with dropout>0 is not built yet (TF RNG stream is not reproducible; use dropout=0)"); return WN_ERR_UNSUPPORTED; }
+  if (train && h->cfg.dropout >= 1.f) { set_err("dropout must be < 1 for training"); return WN_ERR_VALUE; }
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   auto run = [&](cudaStream_t s) -> int {
@@ -1505,15 +1574,17 @@ extern "C" int wn_train_step_host(wn_handle* h, const float* frames_host, const 
     dc = h->d_cond_in;
   }
   RET(step_common(h, h->d_frames, dc, B, T, n_replicas, h->d_loss, st, true));
-  CK(cudaMemcpyAsync(h->pin_loss, h->d_loss, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->pin_loss, h->d_loss, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  *loss_host = h->pin_loss[0];
+  loss_host[0] = h->pin_loss[0];
+  loss_host[1] = h->pin_loss[1];
   return WN_OK;
 }
 
 // ---------------------------------------------------------------- layer-level API
 template <class T>
 static int layer_fwd_entry(wn_handle* h, int l, const float* x, const float* cond, int B, int Tn, float* x_out, float* skip, cudaStream_t st) {
+  h->drop_active = false;   // WaveNetLayer.call(training=False), layers.py:178
   const long long nR = (long long)B * Tn * h->R;
   const void* xin;
   // keep a private copy of the block input (needed by the backward pass)
@@ -1563,6 +1634,7 @@ extern "C" int wn_layer_forward(wn_handle* h, int block, const float* x_dev, con
 
 template <class T>
 static int layer_bwd_entry(wn_handle* h, int l, const float* dxo, const float* dsk, float* dx, float* dcond, cudaStream_t st) {
+  h->drop_active = false;
   const int B = h->lastB, Tn = h->lastT;
   const long long nR = (long long)B * Tn * h->R, nS = (long long)B * Tn * h->Sp;
   const void *dxo_t = nullptr, *dsk_t = nullptr;

@@ -102,6 +102,7 @@ class WaveNet:
     self.built = False
     self._handle: Optional[Handle] = None
     self._pending_weights = None
+    self._staging = {}
     self.n_replicas = 1          # MirroredStrategy replica count (train.py:203); set by parallel.attach()
     self._process_group = None
 
@@ -207,6 +208,24 @@ class WaveNet:
   def get_grads(self):
     return self.handle.get_grads()
 
+  # ------------------------------------------------------------------ dropout (layers.py:109-112,195-196)
+  def set_dropout_masks(self, keep_masks):
+    """Inject per-block keep-masks, each (B,T,channels) bool, for the next training steps (parity runs:
+    TF's dropout RNG stream cannot be reproduced).  None returns to the built-in Philox masks."""
+    h = self.handle
+    if keep_masks is None:
+      _lib.check(h.lib.wn_set_dropout_masks(h.h, None, 1, 1))
+      return
+    if len(keep_masks) != self.blocks:
+      raise ValueError('one keep-mask per block expected')
+    B, T = keep_masks[0].shape[0], keep_masks[0].shape[1]
+    a = np.ascontiguousarray(np.stack([np.asarray(k).reshape(B, T, self.channels) for k in keep_masks]).astype(np.uint8))
+    _lib.check(h.lib.wn_set_dropout_masks(h.h, a.ctypes.data_as(C.c_void_p), B, T))
+
+  def set_dropout_seed(self, seed: int):
+    h = self.handle
+    _lib.check(h.lib.wn_set_dropout_seed(h.h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+
   # ------------------------------------------------------------------ call (model.py:213-239)
   def _unpack(self, inputs):
     if self.conditioning == 'global':
@@ -228,7 +247,7 @@ class WaveNet:
     cond = as_dev(cond, dev) if cond is not None else None
     self._ensure_built(x2, cond)
     if training and self.dropout > 0:
-      raise NotImplementedError('training with dropout>0 is not built; use dropout=0')
+      raise NotImplementedError('call(training=True) with dropout>0 is only available fused inside train_step')
     h = self.handle
     B, T = x2.shape
     cout = 3 * self.num_mixtures if self.num_mixtures is not None else 2 ** self.bits
@@ -251,13 +270,32 @@ class WaveNet:
     return idx
 
   # ------------------------------------------------------------------ steps (model.py:309-391)
+  def _stage(self, name, src, shape, dev):
+    """Host input -> persistent device staging buffer (fixed address, so the captured step graph is
+    replayed instead of being re-captured for every fresh allocation); device input -> used in place."""
+    if isinstance(src, torch.Tensor) and src.is_cuda:
+      t = src.detach()
+      if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(dtype=torch.float32).contiguous()
+      return t.reshape(shape)
+    t = src.detach() if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(src, dtype=np.float32)))
+    buf = self._staging.get(name)
+    if buf is None or tuple(buf.shape) != tuple(shape) or buf.device != dev:
+      buf = torch.empty(shape, dtype=torch.float32, device=dev)
+      self._staging[name] = buf
+    buf.copy_(t.reshape(shape), non_blocking=True)
+    return buf
+
   def _step(self, data, train: bool):
     x, cond = self._unpack(data) if self.conditioning == 'global' else (data, None)
+    if not torch.cuda.is_available():
+      raise RuntimeError('wavenets_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
     dev = torch.device('cuda', self.device_index)
-    x = as_dev(x, dev)
-    frames = x[:, :, 0].contiguous() if x.dim() == 3 else x
-    cond = as_dev(cond, dev) if cond is not None else None
-    B, T = int(frames.shape[0]), int(frames.shape[1]) - 1
+    if len(x.shape) == 3 and x.shape[2] != 1:
+      raise ValueError('input must be (batch, samples, 1)')
+    B, T = int(x.shape[0]), int(x.shape[1]) - 1
+    frames = self._stage('frames', x, (B, T + 1), dev)
+    cond = self._stage('cond', cond, (B, int(cond.shape[-1])), dev) if cond is not None else None
     self._ensure_built(frames[:, :-1], cond)
     h = self.handle
     fn = h.lib.wn_train_step if train else h.lib.wn_test_step
@@ -265,7 +303,7 @@ class WaveNet:
     if train and self._process_group is not None:
       # MirroredStrategy's gradient all-reduce (SUM: the loss is already divided by the global batch)
       torch.distributed.all_reduce(h.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self._process_group)
-    return h._loss[:1]
+    return h._loss[:2]
 
   def train_step(self, data):
     """Forward + loss + backward; gradients land in `get_grads()` / `handle.flat_grads`.
@@ -273,14 +311,22 @@ class WaveNet:
     loss = self._step(data, True)
     if self.optimizer is not None:
       self.optimizer.apply_gradients(self)
-    return {'loss': float(loss.item())}
+    return self._metrics_dict(loss)
+
+  def _metrics_dict(self, loss_dev):
+    # model.py:340-348: 'loss' excludes the regulariser, which is reported as 'reg_loss'
+    vals = loss_dev.tolist()
+    out = {'loss': vals[0]}
+    if self.regularization:
+      out['reg_loss'] = vals[1]
+    return out
 
   def train_step_async(self, data):
-    """Same as train_step without the host read-back: returns a 1-element device tensor."""
+    """Same as train_step without the host read-back: returns a device tensor [loss, reg_loss]."""
     return self._step(data, True)
 
   def test_step(self, data):
-    return {'loss': float(self._step(data, False).item())}
+    return {'loss': self._step(data, False).tolist()[0]}
 
   def loss_fn(self, target, pred):
     raise NotImplementedError('stand-alone loss_fn on materialised predictions is not built: the loss is fused into train_step/test_step')
