@@ -166,6 +166,9 @@ int64_t wn_last_launch_count(const wn_handle* h);
  * 1 = dilated-conv GEMMs (fwd+dgrad+wgrad), 2 = all GEMMs, 3 = loss/head reductions */
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
+/* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a
+ * short label ("gate", "bias_act_res", "gate_bwd", "dgrad", "wgrad_dilated", "wgrad_1x1", "misc") of launch i */
+int wn_profile_get(wn_handle* h, int i, double* ms, char* label, int label_len);
 const char* wn_build_info(void);
 
 #ifdef __cplusplus

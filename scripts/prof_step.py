@@ -17,4 +17,4 @@ c = torch.from_numpy(synth.speakers_onehot(B, cond_in, seed=0)).cuda() if cond_i
 for _ in range(steps):
   loss = m.train_step_async((x, c) if c is not None else x)
 torch.cuda.synchronize()
-print('loss', float(loss.item()), 'launches/step', m.handle.lib.wn_last_launch_count(m.handle.h))
+print('loss', float(loss[0].item()), 'launches/step', m.handle.lib.wn_last_launch_count(m.handle.h))

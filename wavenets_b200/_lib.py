@@ -21,7 +21,7 @@ EXPORTS = [
   'wn_param_count', 'wn_param_info', 'wn_params_dev', 'wn_grads_dev', 'wn_set_param', 'wn_get_param',
   'wn_get_grad', 'wn_params_changed', 'wn_quantize', 'wn_forward', 'wn_train_step', 'wn_test_step',
   'wn_train_step_host', 'wn_layer_forward', 'wn_layer_backward', 'wn_last_launch_count',
-  'wn_profile_begin', 'wn_profile_end', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
+  'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
 ]
 
 
@@ -41,7 +41,8 @@ class WnConfig(C.Structure):
 
 
 def lib_path() -> str:
-  return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libwavenet_b200.so')
+  # WN_LIB selects an alternative build of the same library (ablation builds under scripts/exp.sh)
+  return os.environ.get('WN_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libwavenet_b200.so')
 
 
 _LIB = None
@@ -89,6 +90,7 @@ def load():
   lib.wn_last_launch_count.restype = i64
   lib.wn_profile_begin.argtypes = [vp, i32]
   lib.wn_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+  lib.wn_profile_get.argtypes = [vp, i32, C.POINTER(C.c_double), C.c_char_p, i32]
   lib.wn_set_dropout_masks.argtypes = [vp, vp, i32, i32]
   lib.wn_set_dropout_seed.argtypes = [vp, C.c_uint64]
   ip = C.POINTER(C.c_int)

@@ -16,6 +16,7 @@
 // Used by: pre-stack dilated convs (layers.py:66-74), conv1 + residual add (layers.py:213,222-223),
 // skip-sum GEMM (model.py:236), head 1x1 convs (model.py:105-119).
 template <class T, class TO, bool FAST> struct EpiBiasActRes {
+  static constexpr const char* kLabel = "bias_act_res";
   static constexpr bool kHeavy = false;   // tcgen05 path: 4 epilogue warps are enough
   struct Params {
     TO* out; int ldo;
@@ -62,6 +63,7 @@ template <class T, class TO, bool FAST> struct EpiBiasActRes {
 //   z = acc + bias + cbias[b]   (Keras column order [filter D | gate D] in memory)
 //   g = tanh(z_f) * sigmoid(z_s)
 template <class T, bool FAST> struct EpiGate {
+  static constexpr const char* kLabel = "gate";
   static constexpr bool kHeavy = true;    // 2 MUFU per output: 8 epilogue warps
   struct Params {
     T* z; T* g;                        // z [rows][2D], g [rows][ldg]
@@ -103,6 +105,7 @@ template <class T, bool FAST> struct EpiGate {
 // Adjoint of the gate: acc = dg for channels [n0, n0+bn) ;
 //   dz_f = dg * sig(z_s) * (1 - tanh(z_f)^2),  dz_s = dg * tanh(z_f) * sig(z_s) * (1 - sig(z_s))
 template <class T, bool FAST> struct EpiGateBwd {
+  static constexpr const char* kLabel = "gate_bwd";
   static constexpr bool kHeavy = true;
   struct Params {
     const T* z;                        // [rows][2D] cached pre-activations
@@ -136,6 +139,7 @@ template <class T, bool FAST> struct EpiGateBwd {
 // Generic dgrad epilogue: out = (acc + add[row][n]) * act'(y[row][n])
 // (residual pass-through of d x_out, and activation adjoint from the cached activation output)
 template <class T, class TO> struct EpiActBwd {
+  static constexpr const char* kLabel = "dgrad";
   static constexpr bool kHeavy = false;
   struct Params {
     TO* out; int ldo;

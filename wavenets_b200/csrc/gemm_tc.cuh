@@ -20,6 +20,8 @@
 //     (B,T,C) layout (no transposes): A box = 64 time rows x 64 channels.  Split over row ranges;
 //     fp32 partials reduced by a second deterministic kernel (no atomics).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_epilogues.cuh"
@@ -28,11 +30,24 @@
 #define TC_MAX_SEG 4
 
 struct TcSeg { const bf16* A; int lda; int shift; int K; };
+// L2 policy per tensor of a launch: 0 = normal, 1 = evict_first (streaming), 2 = evict_last (the next kernel reads it)
+enum { TC_L2_NORMAL = 0, TC_L2_FIRST = 1, TC_L2_LAST = 2 };
+static inline int tc_l2_hints_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("WN_TC_L2_HINTS"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+static inline unsigned long long tc_policy(int code) {
+  if (!tc_l2_hints_on()) return TC_POL_NORMAL;
+  return code == TC_L2_FIRST ? TC_POL_FIRST : (code == TC_L2_LAST ? TC_POL_LAST : TC_POL_NORMAL);
+}
 struct TcGemmDesc {
   int B, T, nseg; TcSeg seg[TC_MAX_SEG]; int n_outer; long long outer_stride;
   const bf16* W; int ktot; int N16; int tileN;
+  int l2_a = 0, l2_in[2] = {0, 0}, l2_out[3] = {0, 0, 0};   // TC_L2_* codes: activation operand, epilogue inputs, outputs
 };
 struct TcWgradDesc {
+  int l2_a = 0, l2_g = 0;
   int B, T, N; const bf16* G; int ldg; int nseg; TcSeg seg[TC_MAX_SEG]; int ktot; float* partial;
   float* cs_partial;   // optional: per-(split, batch slot) column sums of G, [nsplit][slots][N] (bias / conditioning gradients)
 };
@@ -283,14 +298,18 @@ struct TcStagedParams {
   uint32_t in_mask;
   int in_col[2];
   int out_col[3];
+  unsigned long long pol_a, pol_w, pol_in[2], pol_out[3];   // L2 cache policies (TC_POL_*)
 };
 
 // IN_PANELS: capacity of the epilogue-input ring in half-panels (slots = IN_PANELS / active inputs, decided at
 // run time); OUT_SLOTS: output slots of NOUT half-panels each.
-template <int BN, int NIN, int NOUT, int IN_PANELS, int OUT_SLOTS_> struct TcStagedCfg {
+// CG: CTAs per MMA (cta_group).  CG == 2: a CTA pair works on 256 rows x BN columns; each CTA stages its own
+// 128 rows of A and HALF of the W tile, so one k-step moves 32 KB per SM instead of 48 KB for the same FLOPs
+// (the conv GEMMs at cta_group::1 top out on L2 -> SM bandwidth, profiles/README.md).
+template <int BN, int NIN, int NOUT, int IN_PANELS, int OUT_SLOTS_, int CG = 1> struct TcStagedCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int PANEL = 128 * 64;                 // 128 rows x 32 bf16
   static constexpr int IN_MAX = IN_PANELS > 0 ? IN_PANELS : 1, OUT_SLOTS = OUT_SLOTS_;
@@ -306,7 +325,7 @@ template <int BN, int NIN, int NOUT, int IN_PANELS, int OUT_SLOTS_> struct TcSta
   static_assert(STAGES >= 2, "not enough shared memory for the mainloop ring");
 };
 
-template <class Epi, int BN>
+template <class Epi, int BN, int CG>
 __global__ void __launch_bounds__(384, 1)
 tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                            const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmW,
@@ -314,10 +333,21 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
                            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
                            const TcGemmParams p, const TcStagedParams sp, const typename Epi::Params ep) {
   constexpr int NIN = Epi::NIN, NOUT = Epi::NOUT;
-  using Cfg = TcStagedCfg<BN, NIN, NOUT, Epi::kInPanels, Epi::kOutSlots>;
+  using Cfg = TcStagedCfg<BN, NIN, NOUT, Epi::kInPanels, Epi::kOutSlots, CG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NEPI = 8;
   constexpr int STEPS = Epi::kGate ? BN / 64 : BN / 32;   // 32 output columns per step
+  // CTA pair: rank 0 leads (issues the MMAs, owns the barriers the pair synchronises on)
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  const int tile_first = (int)blockIdx.x / CG, tile_stride = (int)gridDim.x / CG;
+  const int pair_row0 = (int)crank * Cfg::BM;     // first row of this CTA inside the pair's 256-row tile
+#ifdef TC_DEBUG_PAIR
+  if (threadIdx.x == 0) {
+    uint32_t nr; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nr));
+    printf("blk %d/%d crank %u nctarank %u CG %d tiles %d tiles_t %d\n", blockIdx.x, gridDim.x, crank, nr, CG, p.num_tiles, p.tiles_t);
+  }
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* in_ring = smem + STAGES * Cfg::STAGE_BYTES;
@@ -328,7 +358,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* in_full = tempty_bar + 2;
   uint64_t* in_empty = in_full + Cfg::IN_MAX;
-  uint32_t* tmem_ptr = (uint32_t*)(in_empty + Cfg::IN_MAX);
+  uint64_t* out_empty = in_empty + Cfg::IN_MAX;          // output slot has been read by its TMA stores
+  uint32_t* tmem_ptr = (uint32_t*)(out_empty + Cfg::OUT_SLOTS);
   float* bias_s = (float*)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);   // per-tile bias table (<= 256 floats)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -344,13 +375,18 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NEPI); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NEPI * CG); }
     for (int i = 0; i < Cfg::IN_MAX; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], NEPI); }
+    for (int i = 0; i < Cfg::OUT_SLOTS; ++i) mbar_init(&out_empty[i], 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -358,9 +394,9 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
     // ===================== TMA producer (mainloop operands) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM, n0 = nt * BN;
+        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (Cfg::BM * CG) + pair_row0, n0 = nt * BN;
         int wk = 0;
         for (int o = 0; o < p.n_outer; ++o) {
           for (int s = 0; s < p.nseg; ++s) {
@@ -372,9 +408,16 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
 #ifdef TC_EXP_NO_TMA
               mbar_arrive(&full_bar[stage]);
 #else
-              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              tma_load_4d(sa, tm, &full_bar[stage], k0, tcoord, b, o);
-              tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0);
+              if (CG == 1) {
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_4d_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
+                tma_load_2d_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0, sp.pol_w);
+              } else {
+                // the leader's barrier counts the bytes of both CTAs' operand halves
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
+                tma_load_2d_pair_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0 + (int)crank * (BN / 2), sp.pol_w);
+              }
 #endif
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -384,16 +427,26 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    // ===================== MMA issuer (leader CTA of a pair only) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, 0, 0);
+    if (leader) {
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     int ksteps = 0;
     for (int s = 0; s < p.nseg; ++s) ksteps += (p.segK[s] + Cfg::BK - 1) / Cfg::BK;
     ksteps *= p.n_outer;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+#ifdef TC_TIMELINE
+    long long tl_m[8][3]; int tl_mi = 0;
+#endif
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+#ifdef TC_TIMELINE
+      const long long tl_a = clock64();
+#endif
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
+#ifdef TC_TIMELINE
+      const long long tl_b = clock64();
+#endif
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
@@ -404,17 +457,65 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
 #ifndef TC_EXP_NO_MMA
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k)
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            if (CG == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+            else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+          }
 #endif
-          umma_commit(&empty_bar[stage]);
-          if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
+          if (CG == 1) {
+            umma_commit(&empty_bar[stage]);
+            if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
+          } else {
+            umma_commit_pair(&empty_bar[stage]);
+            if (ks == ksteps - 1) umma_commit_pair(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+#ifdef TC_TIMELINE
+      if (tl_mi < 8) { tl_m[tl_mi][0] = tl_a; tl_m[tl_mi][1] = tl_b; tl_m[tl_mi][2] = clock64(); ++tl_mi; }
+#endif
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+#ifdef TC_TIMELINE
+    if (blockIdx.x == 0 && lane == 0)
+      for (int i = 0; i < tl_mi; ++i) printf("MMA tile %d: wait_tempty %lld issue %lld (t0 %lld)\n", i, tl_m[i][1] - tl_m[i][0], tl_m[i][2] - tl_m[i][1], tl_m[i][0] - tl_m[0][0]);
+#endif
+    }
+  } else if (warp == 2) {
+    // ===================== output store warp =====================
+    // waits for the 8 epilogue warps to fill an output slot (named barrier per slot), issues its TMA stores, and
+    // frees the slot of the previous step once those stores have read shared memory
+#ifndef TC_EXP_NO_EPI
+    int oslot = 0, prev = -1;
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (Cfg::BM * CG) + pair_row0;
+      const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
+#pragma unroll 1
+      for (int step = 0; step < STEPS; ++step) {
+        const int col0 = tile_col0 + step * 32;
+        named_bar_sync(3 + oslot, NEPI * 32 + 32);
+        if (lane == 0) {
+          const uint8_t* ob = out_ring + oslot * NOUT * Cfg::PANEL;
+#ifndef TC_EXP_NO_OUT
+          tma_store_3d_h(ob, &tmO0, sp.out_col[0] + col0, t0, b, sp.pol_out[0]);
+          if (NOUT > 1) tma_store_3d_h(ob + Cfg::PANEL, &tmO1, sp.out_col[1] + col0, t0, b, sp.pol_out[1]);
+          if (NOUT > 2) tma_store_3d_h(ob + 2 * Cfg::PANEL, &tmO2, sp.out_col[2] + col0, t0, b, sp.pol_out[2]);
+          bulk_commit_group();
+          if (prev >= 0) { bulk_wait_group_read<1>(); mbar_arrive(&out_empty[prev]); }
+#else
+          if (prev >= 0) mbar_arrive(&out_empty[prev]);
+#endif
+          prev = oslot;
+        }
+        __syncwarp();
+        if (++oslot == Cfg::OUT_SLOTS) oslot = 0;
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+#endif
   } else if (warp == 3) {
     // ===================== epilogue-input producer =====================
 #ifdef TC_EXP_NO_EPI
@@ -423,17 +524,17 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
     if (NIN > 0 && use_in && lane == 0) {
 #endif
       int islot = 0; uint32_t iphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM;
+        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (Cfg::BM * CG) + pair_row0;
         const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
 #ifdef TC_L2_PREFETCH
         {
           // pull the NEXT tile's epilogue inputs into L2 while this tile is being computed
-          const int tn = tile + gridDim.x;
+          const int tn = tile + tile_stride;
           if (tn < p.num_tiles) {
             const int nt2 = tn % p.n_tiles, mt2 = tn / p.n_tiles;
-            const int b2 = mt2 / p.tiles_t, t2 = (mt2 % p.tiles_t) * Cfg::BM;
+            const int b2 = mt2 / p.tiles_t, t2 = (mt2 % p.tiles_t) * (Cfg::BM * CG) + pair_row0;
             const int c2 = Epi::kGate ? nt2 * (BN / 2) : nt2 * BN;
             for (int step = 0; step < STEPS; ++step) {
               if (sp.in_mask & 1u) tma_prefetch_l2_3d(&tmI0, sp.in_col[0] + c2 + step * 32, t2, b2);
@@ -449,8 +550,8 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
 #else
           mbar_expect_tx(&in_full[islot], (uint32_t)(nact * Cfg::PANEL));
           uint8_t* dst = in_ring + islot * nact * Cfg::PANEL;
-          if (sp.in_mask & 1u) { tma_load_3d(dst, &tmI0, &in_full[islot], sp.in_col[0] + tile_col0 + step * 32, t0, b); dst += Cfg::PANEL; }
-          if (NIN > 1 && (sp.in_mask & 2u)) tma_load_3d(dst, &tmI1, &in_full[islot], sp.in_col[1] + tile_col0 + step * 32, t0, b);
+          if (sp.in_mask & 1u) { tma_load_3d_h(dst, &tmI0, &in_full[islot], sp.in_col[0] + tile_col0 + step * 32, t0, b, sp.pol_in[0]); dst += Cfg::PANEL; }
+          if (NIN > 1 && (sp.in_mask & 2u)) tma_load_3d_h(dst, &tmI1, &in_full[islot], sp.in_col[1] + tile_col0 + step * 32, t0, b, sp.pol_in[1]);
 #endif
           if (++islot == in_slots) { islot = 0; iphase ^= 1; }
         }
@@ -466,13 +567,18 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
     const uint32_t sw = (uint32_t)((row >> 1) & 3);
     const uint32_t u0 = (uint32_t)(2 * q), u1 = u0 + 1;   // 16-byte units of this chunk inside the 64-byte row
     const uint32_t off0 = row_off + ((u0 ^ sw) << 4), off1 = row_off + ((u1 ^ sw) << 4);
-    const bool store_thread = threadIdx.x == 128;
     int as = 0; uint32_t aphase = 0;
     int islot = 0; uint32_t iphase = 0;
-    int oslot = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int oslot = 0; uint32_t ophase = 0;
+#ifdef TC_TIMELINE
+    long long tl_e[8][3]; int tl_ei = 0;
+#endif
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_stride) {
+#ifdef TC_TIMELINE
+      const long long tl_a = clock64();
+#endif
       const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-      const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * Cfg::BM;
+      const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (Cfg::BM * CG) + pair_row0;
       const int tile_col0 = Epi::kGate ? nt * (BN / 2) : nt * BN;
       const int bsafe = b < p.B ? b : p.B - 1;
       constexpr int NBIAS = Epi::kBiasFloats(BN);
@@ -480,6 +586,9 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
       if (NBIAS > 0 && (int)threadIdx.x - 128 < NBIAS) bias_reg = Epi::bias_load(ep, bsafe, tile_col0, BN, (int)threadIdx.x - 128);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+#ifdef TC_TIMELINE
+      const long long tl_b = clock64();
+#endif
       if (NBIAS > 0) {
         // every reader of the previous tile's table is past that tile's last step barrier
         if ((int)threadIdx.x - 128 < NBIAS) bias_s[threadIdx.x - 128] = bias_reg;
@@ -490,6 +599,13 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
       constexpr int STEPS_RUN = 0;
 #else
       constexpr int STEPS_RUN = STEPS;
+#endif
+#ifdef TC_TIMELINE
+      long long ph[6] = {0, 0, 0, 0, 0, 0};
+#define TL_MARK(i) { const long long tl_now = clock64(); ph[i] += tl_now - tl_prev; tl_prev = tl_now; }
+      long long tl_prev = clock64();
+#else
+#define TL_MARK(i)
 #endif
 #pragma unroll 1
       for (int step = 0; step < STEPS_RUN; ++step) {
@@ -517,8 +633,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           if (lane == 0) mbar_arrive(&in_empty[islot]);
           if (++islot == in_slots) { islot = 0; iphase ^= 1; }
         }
+        TL_MARK(0)
         Epi::chunk(ep, acc, bsafe, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out, bias_s);
+        TL_MARK(1)
         uint8_t* ob = out_ring + oslot * NOUT * Cfg::PANEL;
+        mbar_wait(&out_empty[oslot], ophase ^ 1);     // the TMA stores of this slot's previous use have read it
 #pragma unroll
         for (int k = 0; k < NOUT; ++k) {
           uint4 a, c;
@@ -530,33 +649,40 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           *reinterpret_cast<uint4*>(ob + k * Cfg::PANEL + off1) = c;
         }
         fence_proxy_async();
-        // all stores of the previous step's slot partner must have been read before anyone reuses it
-#ifndef TC_EXP_NO_OUT
-        if (store_thread) bulk_wait_group_read<Cfg::OUT_SLOTS - 2>();
-#endif
-        named_bar_sync(1, NEPI * 32);
-#ifdef TC_EXP_NO_OUT
-        if (false) {
-#else
-        if (store_thread) {
-#endif
-          tma_store_3d(ob, &tmO0, sp.out_col[0] + col0, t0, b);
-          if (NOUT > 1) tma_store_3d(ob + Cfg::PANEL, &tmO1, sp.out_col[1] + col0, t0, b);
-          if (NOUT > 2) tma_store_3d(ob + 2 * Cfg::PANEL, &tmO2, sp.out_col[2] + col0, t0, b);
-          bulk_commit_group();
-        }
-        if (++oslot == Cfg::OUT_SLOTS) oslot = 0;
+        TL_MARK(2)
+        // hand the slot to the store warp (warp 2) and move on: no epilogue thread waits for TMA issue or read-back
+        named_bar_arrive(3 + oslot, NEPI * 32 + 32);
+        TL_MARK(3)
+        TL_MARK(4)
+        TL_MARK(5)
+        if (++oslot == Cfg::OUT_SLOTS) { oslot = 0; ophase ^= 1; }
       }
+#ifdef TC_TIMELINE
+      if (blockIdx.x == 0 && (threadIdx.x == 128 || threadIdx.x == 320) && tl_ei >= 2 && tl_ei < 4)
+        printf("  EPI phases thr %d tile %d: in %lld chunk %lld pack+sts+fence %lld wait_read %lld bar %lld tma %lld\n", threadIdx.x, tl_ei, ph[0], ph[1], ph[2],
+               ph[3], ph[4], ph[5]);
+      if (tl_ei < 8) { tl_e[tl_ei][0] = tl_a; tl_e[tl_ei][1] = tl_b; tl_e[tl_ei][2] = clock64(); ++tl_ei; }
+#endif
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tempty_bar[as]);
+        else mbar_arrive_remote_relaxed(&tempty_bar[as], 0u);      // the leader's MMA warp waits for both CTAs' epilogues
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (store_thread) bulk_wait_group<0>();
+#ifdef TC_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 128)
+      for (int i = 0; i < tl_ei; ++i) printf("EPI tile %d: wait_tfull %lld work %lld (t0 %lld)\n", i, tl_e[i][1] - tl_e[i][0], tl_e[i][2] - tl_e[i][1], tl_e[i][0] - tl_e[0][0]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (CG == 2) cluster_sync_all();       // nobody leaves (or frees TMEM) while the pair may still signal / read
+  if (warp == 2) {
+    if (CG == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 // half-panel map over a (B,T,ld) bf16 tensor restricted to C columns: box (32 cols, 128 rows, 1), 64B swizzle
@@ -567,10 +693,10 @@ static inline const CUtensorMap* tc_panel_map(TmapCache& tc, const TcEpiIo& io, 
   return tc.get(io.base, 3, dims, str, box, 64);
 }
 
-template <class Epi, int BN>
+template <class Epi, int BN, int CG>
 static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep, const TcEpiIo* ins,
                                       uint32_t in_mask, const TcEpiIo* outs) {
-  using Cfg = TcStagedCfg<BN, Epi::NIN, Epi::NOUT, Epi::kInPanels, Epi::kOutSlots>;
+  using Cfg = TcStagedCfg<BN, Epi::NIN, Epi::NOUT, Epi::kInPanels, Epi::kOutSlots, CG>;
   const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
   for (int s = 0; s < d.nseg; ++s) {
     ma[s] = tc_act_map(tc, d.seg[s].A, d.seg[s].lda, d.seg[s].K, d.T, d.B, s == 0 ? d.n_outer : 1, d.outer_stride, 128);
@@ -579,11 +705,14 @@ static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGe
   for (int s = d.nseg; s < TC_MAX_SEG; ++s) ma[s] = ma[0];
   uint64_t wd[2] = {(uint64_t)d.ktot, (uint64_t)d.N16};
   uint64_t ws[1] = {(uint64_t)d.ktot * 2};
-  uint32_t wb[2] = {64, (uint32_t)BN};
+  uint32_t wb[2] = {64, (uint32_t)(BN / CG)};
   const CUtensorMap* mw = tc.get(d.W, 2, wd, ws, wb);
   if (!mw) return -11;
   TcStagedParams sp{};
   sp.in_mask = in_mask;
+  sp.pol_a = tc_policy(d.l2_a); sp.pol_w = tc_policy(TC_L2_LAST);      // weights: every CTA re-reads them all kernel long
+  for (int k = 0; k < 2; ++k) sp.pol_in[k] = tc_policy(d.l2_in[k]);
+  for (int k = 0; k < 3; ++k) sp.pol_out[k] = tc_policy(d.l2_out[k]);
   const CUtensorMap* mo[3] = {nullptr, nullptr, nullptr};
   const CUtensorMap* mi[2] = {nullptr, nullptr};
   for (int k = 0; k < Epi::NOUT; ++k) {
@@ -601,21 +730,37 @@ static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGe
   }
   for (int k = 0; k < 2; ++k) if (!mi[k]) mi[k] = mo[0];
   TcGemmParams p{};
-  p.B = d.B; p.T = d.T; p.tiles_t = (d.T + 127) / 128; p.n_tiles = d.N16 / BN; p.num_tiles = d.B * p.tiles_t * p.n_tiles;
+  p.B = d.B; p.T = d.T; p.tiles_t = (d.T + 128 * CG - 1) / (128 * CG); p.n_tiles = d.N16 / BN; p.num_tiles = d.B * p.tiles_t * p.n_tiles;
   p.nseg = d.nseg; p.n_outer = d.n_outer > 0 ? d.n_outer : 1;
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
-  auto kern = tc_conv_gemm_staged_kernel<Epi, BN>;
+  auto kern = tc_conv_gemm_staged_kernel<Epi, BN, CG>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
     attr_done = true;
   }
-  const int grid = p.num_tiles < tc_num_sms() ? p.num_tiles : tc_num_sms();
-  kern<<<grid, 384, Cfg::SMEM_BYTES, st>>>(*ma[0], *ma[1], *ma[2], *ma[3], *mw, *mi[0], *mi[1], *mo[0], *mo[1], *mo[2], p, sp, ep);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "staged conv_gemm launch: %s", cudaGetErrorString(e)); return -13; }
+  const int slots = tc_num_sms() / CG;      // one CTA (or CTA pair) per SM (pair of SMs of a TPC)
+  const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mw, *mi[0], *mi[1], *mo[0], *mo[1], *mo[2], p, sp, ep);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "staged conv_gemm launch (cta_group %d): %s", CG, cudaGetErrorString(e)); return -13; }
   return 0;
+}
+
+// cta_group of the conv GEMMs: 2 (CTA pairs) unless overridden (WN_TC_CTA_GROUP=1 in the environment, for A/B runs)
+static inline int tc_cta_group() {
+  static int cg = 0;
+  if (cg == 0) {
+    const char* e = getenv("WN_TC_CTA_GROUP");
+    cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cg;
 }
 
 template <class Epi>
@@ -624,10 +769,18 @@ static int tc_conv_gemm_staged(TmapCache& tc, cudaStream_t st, const TcGemmDesc&
   int tile = d.tileN;
   if (tile == 0) tile = d.N16 % 256 == 0 ? 256 : (d.N16 % 128 == 0 ? 128 : 64);
   if (d.N16 % tile != 0 || d.nseg < 1 || d.nseg > TC_MAX_SEG) { snprintf(g_tc_err, sizeof(g_tc_err), "bad tiling N16=%d tile=%d nseg=%d", d.N16, tile, d.nseg); return -1; }
+  if (tc_cta_group() == 2) {
+    switch (tile) {
+      case 256: return tc_conv_gemm_staged_launch<Epi, 256, 2>(tc, st, d, ep, ins, in_mask, outs);
+      case 128: return tc_conv_gemm_staged_launch<Epi, 128, 2>(tc, st, d, ep, ins, in_mask, outs);
+      case 64: return tc_conv_gemm_staged_launch<Epi, 64, 2>(tc, st, d, ep, ins, in_mask, outs);
+    }
+    return -2;
+  }
   switch (tile) {
-    case 256: return tc_conv_gemm_staged_launch<Epi, 256>(tc, st, d, ep, ins, in_mask, outs);
-    case 128: return tc_conv_gemm_staged_launch<Epi, 128>(tc, st, d, ep, ins, in_mask, outs);
-    case 64: return tc_conv_gemm_staged_launch<Epi, 64>(tc, st, d, ep, ins, in_mask, outs);
+    case 256: return tc_conv_gemm_staged_launch<Epi, 256, 1>(tc, st, d, ep, ins, in_mask, outs);
+    case 128: return tc_conv_gemm_staged_launch<Epi, 128, 1>(tc, st, d, ep, ins, in_mask, outs);
+    case 64: return tc_conv_gemm_staged_launch<Epi, 64, 1>(tc, st, d, ep, ins, in_mask, outs);
   }
   return -2;
 }
@@ -645,6 +798,7 @@ struct TcWgradParams {
   float* partial;        // [nsplit][ktot][N]
   float* cs_partial;     // [nsplit][slots][N] or null
   int slots;
+  unsigned long long pol_a, pol_g;   // L2 cache policies of the two operands
 };
 
 template <int BN> struct TcWgradCfg {
@@ -726,11 +880,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_arrive(&full_bar[stage]);
 #else
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        tma_load_4d(sa, tm, &full_bar[stage], k0, t0 + shift, b, 0);
-        tma_load_4d(sa + 8192, tm, &full_bar[stage], k0 + 64, t0 + shift, b, 0);
+        tma_load_4d_h(sa, tm, &full_bar[stage], k0, t0 + shift, b, 0, p.pol_a);
+        tma_load_4d_h(sa + 8192, tm, &full_bar[stage], k0 + 64, t0 + shift, b, 0, p.pol_a);
         if (CL == 1) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_4d(sa + Cfg::A_BYTES + j * 8192, &tmG, &full_bar[stage], n0 + 64 * j, t0, b, 0);
+          for (int j = 0; j < BN / 64; ++j) tma_load_4d_h(sa + Cfg::A_BYTES + j * 8192, &tmG, &full_bar[stage], n0 + 64 * j, t0, b, 0, p.pol_g);
         } else {
           constexpr int RPC = Cfg::BKT / CL;          // time rows of every G atom this CTA fetches for the whole cluster
 #pragma unroll
@@ -919,6 +1073,7 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   p.B = d.B; p.T = d.T; p.N = d.N; p.chunks_t = (d.T + 63) / 64; p.total_chunks = d.B * p.chunks_t; p.ktot = d.ktot; p.nseg = d.nseg;
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
   p.partial = d.partial;
+  p.pol_a = tc_policy(d.l2_a); p.pol_g = tc_policy(d.l2_g);
   const int ntiles = (d.N + BN - 1) / BN;
   const int wave = cl == 4 ? tc_wgrad_wave_ctas<BN, 4>() : (cl == 2 ? tc_wgrad_wave_ctas<BN, 2>() : tc_num_sms());
   int nsplit = wave / (mtiles * ntiles);   // one wave: never more CTAs than can be resident

@@ -31,7 +31,7 @@ __device__ __forceinline__ void ld_bias16(const float* p, float* v) {   // share
 // out = act(acc + bias[n] + cbias[b][n]) + res      (layers.py:66-74,213,222-223; model.py:105-119,236)
 template <bool FAST> struct TcEpiBiasActRes {
   static constexpr int NIN = 1, NOUT = 1;
-  static constexpr int kInPanels = 4, kOutSlots = 4;
+  static constexpr int kInPanels = 8, kOutSlots = 4;
   static constexpr bool kGate = false;
   struct Params { const float* bias; const float* cbias; int ldcb; int act; int N; };
   static constexpr int kBiasFloats(int BN) { return BN; }
@@ -115,7 +115,7 @@ template <bool FAST> struct TcEpiGate {
 // adjoint of the gate: acc = dg; inputs cached z_f, z_s; outputs dz_f, dz_s
 template <bool FAST> struct TcEpiGateBwd {
   static constexpr int NIN = 2, NOUT = 2;
-  static constexpr int kInPanels = 4, kOutSlots = 2;
+  static constexpr int kInPanels = 8, kOutSlots = 2;
   static constexpr bool kGate = false;
   struct Params { int D; };
   static constexpr int kBiasFloats(int BN) { return 0; }
@@ -137,7 +137,7 @@ template <bool FAST> struct TcEpiGateBwd {
 // dgrad: out = (acc + add) * act'(y)    (residual pass-through; activation adjoint from its cached output)
 struct TcEpiActBwd {
   static constexpr int NIN = 2, NOUT = 1;
-  static constexpr int kInPanels = 4, kOutSlots = 4;
+  static constexpr int kInPanels = 8, kOutSlots = 4;
   static constexpr bool kGate = false;
   struct Params { int act; };
   static constexpr int kBiasFloats(int BN) { return 0; }

@@ -173,6 +173,10 @@ struct wn_handle {
   // profiling
   int prof_tag = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<const char*> prof_labels;   // what was launched in each timed slot
+  const char* cur_label = "misc";
+  std::vector<float> prof_ms;             // per-slot durations of the last wn_profile_end
+  std::vector<const char*> prof_last_labels;
   size_t prof_used = 0;
   long long prof_launches = 0;
   TmapCache tmaps;
@@ -202,6 +206,8 @@ struct LaunchScope {
         h->prof_events.push_back({a, b});
       }
       slot = h->prof_used++;
+      if (h->prof_labels.size() <= slot) h->prof_labels.resize(slot + 1);
+      h->prof_labels[slot] = h->cur_label;
       cudaEventRecord(h->prof_events[slot].first, st);
       timed = true;
       h->prof_launches++;
@@ -718,6 +724,7 @@ struct GemmH {
   int n_outer = 1; long long outer_stride = 0;
   const float* W32 = nullptr; int Npad = 0;     // fp32: [ktot][Npad]
   const bf16* W16 = nullptr; int ktot16 = 0; int N16 = 0; int tile16 = 0;  // bf16: [N16][ktot16]
+  int l2_a = 0, l2_in[2] = {0, 0}, l2_out[3] = {0, 0, 0};   // bf16 tier: L2 policy codes (TC_L2_*), see tc_common.cuh
 };
 
 // bf16 tier: map the generic epilogue description onto the TMA-staged tcgen05 kernel (tc_epilogues.cuh);
@@ -760,6 +767,7 @@ int tc_dispatch<EpiActBwd<bf16, bf16>>(wn_handle* h, cudaStream_t st, const TcGe
 
 template <class T, class Epi>
 static int run_conv_gemm(wn_handle* h, cudaStream_t st, int cls, const GemmH& g, const typename Epi::Params& ep) {
+  struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, Epi::kLabel);
   LaunchScope ls(h, st, cls);
   if constexpr (sizeof(T) == 4) {
     ConvGemmArgsF a;
@@ -773,6 +781,9 @@ static int run_conv_gemm(wn_handle* h, cudaStream_t st, int cls, const GemmH& g,
     d.B = g.B; d.T = g.T; d.nseg = g.nseg; d.n_outer = g.n_outer; d.outer_stride = g.outer_stride;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     d.W = g.W16; d.ktot = g.ktot16; d.N16 = g.N16; d.tileN = g.tile16;
+    d.l2_a = g.l2_a;
+    for (int k = 0; k < 2; ++k) d.l2_in[k] = g.l2_in[k];
+    for (int k = 0; k < 3; ++k) d.l2_out[k] = g.l2_out[k];
     int r = tc_dispatch<Epi>(h, st, d, ep);
     if (r != 0) { set_err("tcgen05 conv_gemm launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
     return WN_OK;
@@ -789,6 +800,7 @@ struct WgradH {
   // bf16 tier only: columns [N0, N) belong to a second variable (conv1 | conv_skip in one launch)
   int N0 = 0; float* dst1 = nullptr; const float* w1 = nullptr; float* bias1 = nullptr;
   bool side = false;   // issued on the side stream: uses the side copies of the partial buffers
+  int l2_a = 0, l2_g = 0;   // bf16 tier: L2 policy codes of the two operands
 };
 
 template <class T>
@@ -796,6 +808,7 @@ static void run_colsum(wn_handle* h, cudaStream_t st, const void* G, int ldg, in
 
 template <class T>
 static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
+  struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, cls == CLS_DILATED ? "wgrad_dilated" : "wgrad_1x1");
   int ktot = 0;
   for (int s = 0; s < g.nseg; ++s) ktot += g.seg[s].K;
   int nsplit = 1;
@@ -823,6 +836,7 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     TcWgradDesc d;
     d.B = g.B; d.T = g.T; d.N = g.N; d.G = (const bf16*)g.G; d.ldg = g.ldg; d.nseg = g.nseg; d.ktot = ktot;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
+    d.l2_a = g.l2_a; d.l2_g = g.l2_g;
     float* const wgp = g.side ? h->wg_partial_side : h->wg_partial;
     float* const csp = g.side ? h->cs_partial_side : h->cs_partial;
     d.partial = wgp;
@@ -930,6 +944,7 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
       typename EpiBiasActRes<T, T, sizeof(T) == 2>::Params ep{};
       ep.out = (T*)h->acts[l][j]; ep.ldo = h->D; ep.bias = P_(h, c.b_idx); ep.cbias = nullptr; ep.ldcb = 0;
       ep.act = h->cfg.activation; ep.res = nullptr; ep.ldr = 0; ep.N = c.cout; ep.vec = vec_ok<T>(h->D);
+      g.l2_out[0] = TC_L2_LAST;   // the next conv of the stack reads it right away
       RET((run_conv_gemm<T, EpiBiasActRes<T, T, sizeof(T) == 2>>(h, st, CLS_DILATED, g, ep)));
       cur = h->acts[l][j];
       curw = h->D;
@@ -940,6 +955,9 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
       ep.ldg = h->D; ep.bias = P_(h, c.b_idx);
       ep.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
       ep.D = h->D; ep.vec = vec_ok<T>(h->D);
+      // z is not needed before the backward pass (streaming store); g feeds conv1 next; x_in is conv1's residual
+      g.l2_a = depth == 1 ? TC_L2_LAST : TC_L2_NORMAL;
+      g.l2_out[0] = g.l2_out[1] = TC_L2_FIRST; g.l2_out[2] = TC_L2_LAST;
       RET((run_conv_gemm<T, EpiGate<T, sizeof(T) == 2>>(h, st, CLS_DILATED, g, ep)));
     }
   }
@@ -953,6 +971,8 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
     typename EpiBiasActRes<T, T, sizeof(T) == 2>::Params ep{};
     ep.out = (T*)h->xout[l]; ep.ldo = h->R; ep.bias = P_(h, c.b_idx); ep.act = ACT_LINEAR;
     ep.res = h->cfg.use_residual ? (const T*)x_in : nullptr; ep.ldr = h->R; ep.N = h->R; ep.vec = vec_ok<T>(h->R);
+    // g and x_in are next used a whole pass later; x_out is the next block's operand
+    g.l2_a = TC_L2_FIRST; g.l2_in[0] = TC_L2_FIRST; g.l2_out[0] = TC_L2_LAST;
     RET((run_conv_gemm<T, EpiBiasActRes<T, T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
   }
   return WN_OK;
@@ -970,6 +990,7 @@ static int skip_gemm(wn_handle* h, cudaStream_t st, int l0, int nl, TO* out, int
   g.W16 = h->Wskip16 ? h->Wskip16 + (size_t)l0 * h->D : nullptr; g.ktot16 = h->L * h->D; g.N16 = h->Spad; g.tile16 = 0;
   typename EpiBiasActRes<T, TO, sizeof(T) == 2>::Params ep{};
   ep.out = out; ep.ldo = ldo; ep.bias = bias; ep.act = ACT_LINEAR; ep.N = h->Sp; ep.vec = vec_ok<TO>(ldo);
+  g.l2_a = TC_L2_FIRST; g.l2_out[0] = TC_L2_LAST;
   return run_conv_gemm<T, EpiBiasActRes<T, TO, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep);
 }
 
@@ -1119,6 +1140,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef; w.bias_dst = G_(h, b.conv1.b_idx);
     w.N0 = R; w.dst1 = G_(h, b.conv_skip.w_idx); w.w1 = P_(h, b.conv_skip.w_idx); w.bias1 = G_(h, b.conv_skip.b_idx);
     w.side = side1;
+    w.l2_a = TC_L2_FIRST;   // last use of g_l
     RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
   } else if (d_o) {
     WgradH w{};
@@ -1164,6 +1186,8 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     g.W16 = b.Wdg16 ? b.Wdg16 + koff : nullptr; g.ktot16 = rup(rs, 64); g.N16 = b.Dpad; g.tile16 = 0;
     typename EpiGateBwd<T, sizeof(T) == 2>::Params ep{};
     ep.z = (const T*)h->zbuf[l]; ep.dz = (T*)dzbuf; ep.D = D; ep.vec = vec_ok<T>(D);
+    // last use of z; dz is read next by the dgrad and the weight-gradient kernels
+    g.l2_in[0] = g.l2_in[1] = TC_L2_FIRST; g.l2_out[0] = g.l2_out[1] = TC_L2_LAST;
     if (sd && sd->wait_dz) CK(cudaStreamWaitEvent(st, sd->wait_dz, 0));
     RET((run_conv_gemm<T, EpiGateBwd<T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
     if (sd) CK(cudaEventRecord(sd->ev_dz, st));
@@ -1188,6 +1212,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       const bool side2 = sd != nullptr && j == depth - 1;
       if (side2) CK(cudaStreamWaitEvent(sd->side, sd->ev_dz, 0));
       w.side = side2;
+      w.l2_a = TC_L2_FIRST;   // last use of this forward activation
       RET(run_wgrad<T>(h, side2 ? sd->side : st, CLS_DILATED, w));
     }
     // dgrad
@@ -1203,6 +1228,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         void* dst = (dcur == h->dpA) ? h->dpB : h->dpA;
         ep.out = (T*)dst; ep.ldo = D; ep.add = nullptr; ep.y = (const T*)h->acts[l][j - 1]; ep.ldy = D; ep.act = h->cfg.activation;
         ep.vec = vec_ok<T>(D);
+        g.l2_in[1] = TC_L2_FIRST; g.l2_out[0] = TC_L2_LAST;
         RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
         dcur = dst;
         dcw = D;
@@ -1219,6 +1245,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         ep.out = (T*)dx_in; ep.ldo = ldxi;
         ep.add = (h->cfg.use_residual && dxout) ? (const T*)dxout : nullptr; ep.lda = ldxo;
         ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(R);
+        g.l2_in[0] = TC_L2_FIRST; g.l2_out[0] = TC_L2_LAST;   // d x_out is dead after this; dx feeds the next block's kernels
         if (sd && sd->wait_dx) CK(cudaStreamWaitEvent(st, sd->wait_dx, 0));
         RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
       }
@@ -1770,6 +1797,15 @@ extern "C" int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int l
 
 // ---------------------------------------------------------------- introspection
 extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
+// per-launch record of the last wn_profile_end: returns the number of timed launches; i in [0,n): duration + label
+extern "C" int wn_profile_get(wn_handle* h, int i, double* ms, char* label, int label_len) {
+  if (!h) return WN_ERR_VALUE;
+  if (i >= 0 && i < (int)h->prof_ms.size()) {
+    if (ms) *ms = h->prof_ms[i];
+    if (label && label_len > 0) snprintf(label, label_len, "%s", h->prof_last_labels[i] ? h->prof_last_labels[i] : "");
+  }
+  return (int)h->prof_ms.size();
+}
 extern "C" int wn_profile_begin(wn_handle* h, int tag) {
   if (!h) return WN_ERR_VALUE;
   h->prof_tag = tag; h->prof_used = 0; h->prof_launches = 0;
@@ -1779,9 +1815,12 @@ extern "C" int wn_profile_end(wn_handle* h, double* ms, int64_t* launches) {
   if (!h) return WN_ERR_VALUE;
   CK(cudaDeviceSynchronize());
   double tot = 0;
+  h->prof_ms.assign(h->prof_used, 0.f);
+  h->prof_last_labels.assign(h->prof_labels.begin(), h->prof_labels.begin() + h->prof_used);
   for (size_t i = 0; i < h->prof_used; ++i) {
     float t = 0;
     cudaEventElapsedTime(&t, h->prof_events[i].first, h->prof_events[i].second);
+    h->prof_ms[i] = t;
     tot += t;
   }
   if (ms) *ms = tot;
