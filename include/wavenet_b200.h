@@ -106,6 +106,16 @@ int wn_get_grad(wn_handle* h, int i, float* host);
  * kernel-side weight copies (transposes, gate interleave, bf16). */
 int wn_params_changed(wn_handle* h, void* stream);
 
+/* ---- optimizer: train.py:225-226 `tf.keras.optimizers.Adam(learning_rate=lr, clipnorm=1.0)` applied by
+ *      model.py:336 `optimizer.apply_gradients`.  Keras 3 semantics: every variable's gradient is clipped to L2 norm
+ *      <= clipnorm (tf.clip_by_norm) on each replica BEFORE the cross-replica sum; then
+ *      m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
+ *      Call order per step: wn_train_step -> wn_clip_grads -> [all-reduce of wn_grads_dev()] -> wn_adam_step. */
+int wn_adam_init(wn_handle* h, float lr, float beta1, float beta2, float eps, float clipnorm /* 0 = off */);
+int wn_clip_grads(wn_handle* h, void* stream);
+int wn_adam_step(wn_handle* h, float lr /* < 0: keep */, void* stream);   /* also re-packs the kernel-side weights */
+int wn_adam_state(wn_handle* h, float** m_dev, float** v_dev, float** grad_norms_dev, int64_t* step);
+
 /* ---- dropout (layers.py:109-112,195-196; Keras Dropout on the block input of the conv branch) --------
  * Training passes draw keep-masks with a counter-based Philox-4x32-10 keyed by (seed, step): TF's RNG
  * stream cannot be reproduced, so parity runs inject the masks instead.

@@ -468,6 +468,36 @@ def train_step(p, cfg: Config, x_frames, cond_in=None, n_replicas: int = 1, keep
                               'loss_no_reg': loss_no_reg, 'reg_loss': reg / n_replicas}
 
 
+def clip_by_norm(g, clipnorm):
+  """tf.clip_by_norm on one tensor: g * clipnorm / max(||g||_2, clipnorm)."""
+  n = float(np.sqrt((np.asarray(g, dtype=np.float64) ** 2).sum()))
+  return g * (clipnorm / max(n, clipnorm))
+
+
+def adam_step(params, grads, state, lr, beta_1=0.9, beta_2=0.999, epsilon=1e-7, clipnorm=None, n_replicas=1):
+  """One `optimizer.apply_gradients` (model.py:336) of tf.keras.optimizers.Adam(lr, clipnorm) as train.py:225-226
+  builds it, Keras 3 semantics (restated, TF-internal): per-variable clip_by_norm of each replica's gradient, sum over
+  replicas (here: `grads` is one replica's gradient and every replica is assumed identical -> x n_replicas), then
+  m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v)+eps).
+  state: {'t': int, 'm': {...}, 'v': {...}} (created on first use).  Returns (new params, state)."""
+  if not state:
+    state.update(t=0, m={k: np.zeros_like(v) for k, v in params.items()}, v={k: np.zeros_like(v) for k, v in params.items()})
+  state['t'] += 1
+  t = state['t']
+  alpha = lr * math.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+  out = {}
+  for k, w in params.items():
+    g = grads[k]
+    if clipnorm:
+      g = clip_by_norm(g, clipnorm)
+    g = g * n_replicas
+    m = state['m'][k] + (g - state['m'][k]) * (1.0 - beta_1)
+    v = state['v'][k] + (g * g - state['v'][k]) * (1.0 - beta_2)
+    state['m'][k], state['v'][k] = m, v
+    out[k] = w - alpha * m / (np.sqrt(v) + epsilon)
+  return out, state
+
+
 def sample_deterministic(cfg: Config, pred):
   """sample_waveform(pred, deterministic=True) (model.py:411-418,452-459,484-499): categorical ->
   argmax bin mapped to [-1,1) as idx/2^(bits-1) - 1, shape (B,T); mixtures -> mean of the heaviest

@@ -1,0 +1,66 @@
+"""`tf.keras.optimizers.Adam(lr, clipnorm=1.0)` + `optimizer.apply_gradients` (train.py:225-226,
+model.py:336) on the GPU vs the oracle restatement of Keras 3 Adam, over several training steps."""
+import numpy as np
+import pytest
+
+from oracle import wavenet_oracle as wo
+from tests.util import COND_IN, SMALL_MODELS, make_inputs, oracle_config, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name,precision,tol', [('cond_skip', 'fp32', 1e-4), ('categorical_multidil', 'fp32', 1e-4), ('l2', 'fp32', 1e-4)])
+def test_adam_clipnorm_trajectory(name, precision, tol):
+  from wavenets_b200 import WaveNet
+  from wavenets_b200.optimizers import Adam
+  kw = SMALL_MODELS[name]
+  cond_in = COND_IN if kw.get('conditioning') else 0
+  cfg = oracle_config(kw, cond_in)
+  p = {k: v.astype(np.float32).astype(np.float64) for k, v in wo.init_params(cfg, seed=1).items()}
+  x, cond = make_inputs(3, 97, cond_in)
+  m = WaveNet(**kw, precision=precision)
+  opt = Adam(learning_rate=3e-3, clipnorm=1.0)
+  m.compile(optimizer=opt)
+  m.build((x[:, :-1].shape, cond.shape) if cond is not None else x[:, :-1].shape)
+  m.set_weights({k: v.astype(np.float32) for k, v in p.items()})
+  data = (x, cond) if cond is not None else x
+  state = {}
+  c64 = None if cond is None else cond.astype(np.float64)
+  clipped_any = False
+  for step in range(4):
+    loss_o, g_o, aux = wo.train_step(p, cfg, x.astype(np.float64), c64)
+    out = m.train_step(data)
+    assert abs(out['loss'] - aux['loss_no_reg']) <= 10 * tol * abs(loss_o), (step, out['loss'], aux['loss_no_reg'])
+    norms = opt.grad_norms(m)
+    for k, g in g_o.items():
+      n_o = float(np.sqrt((g ** 2).sum()))
+      assert abs(norms[k] - n_o) <= 1e-3 * max(n_o, 1e-6), (k, norms[k], n_o)
+      clipped_any |= n_o > 1.0
+    p, state = wo.adam_step(p, g_o, state, lr=3e-3, clipnorm=1.0)
+    w = m.get_weights()
+    for k in p:
+      assert rel_err(w[k], p[k]) < 10 * tol, (step, k, rel_err(w[k], p[k]))
+  assert clipped_any and opt.iterations == 4
+  st = opt.get_state(m)
+  for k in p:
+    assert rel_err(st['m'][k], state['m'][k]) < 1e-3 and rel_err(st['v'][k], state['v'][k]) < 1e-3, k
+  # learning-rate changes (ReduceLROnPlateau, train.py:167-171) take effect on the next step
+  opt.learning_rate = 0.0
+  w0 = m.get_weights()
+  m.train_step(data)
+  w1 = m.get_weights()
+  assert all(np.array_equal(w0[k], w1[k]) for k in w0)
+
+
+def test_adam_bf16_tier_trains():
+  """bf16 tier: the update runs on the fp32 master weights and the packed bf16 copies follow; the loss goes down."""
+  from wavenets_b200 import WaveNet
+  from wavenets_b200.optimizers import Adam
+  kw = dict(channels=64, blocks=3, layers_per_block=1, dilation_bound=8, skip_channels=64, final_layers_channels=[64])
+  x, _ = make_inputs(4, 400, 0, seed=3)
+  m = WaveNet(**kw, precision='bf16')
+  m.compile(optimizer=Adam(learning_rate=2e-3, clipnorm=1.0))
+  m.build(x[:, :-1].shape)
+  losses = [m.train_step(x)['loss'] for _ in range(12)]
+  assert losses[-1] < 0.97 * losses[0] and all(b < a for a, b in zip(losses, losses[1:])), losses
+  assert m.test_step(x)['loss'] < losses[0]

@@ -136,3 +136,18 @@ def test_replica_scaling():
   assert abs((l0 + l1) - l_all) < 1e-9
   for k in g_all:
     assert rel_err(g0[k] + g1[k], g_all[k]) < 1e-10
+
+
+def test_adam_known_answer():
+  """Keras 3 Adam, one scalar weight, by hand: t=1: m=0.1g, v=0.001g^2, alpha=lr*sqrt(0.001)/0.1 -> w -= lr*g/(|g|+eps*...)."""
+  p = {'w': np.array([1.0])}
+  g = {'w': np.array([0.5])}
+  st = {}
+  p1, st = wo.adam_step(p, g, st, lr=0.1)
+  alpha = 0.1 * np.sqrt(1 - 0.999) / (1 - 0.9)
+  expect = 1.0 - alpha * (0.1 * 0.5) / (np.sqrt(0.001 * 0.25) + 1e-7)
+  assert abs(p1['w'][0] - expect) < 1e-15
+  # clipnorm: a gradient of norm 5 is scaled to norm 1 per variable before the moments are updated
+  p2, st2 = wo.adam_step({'w': np.array([3.0, 4.0])}, {'w': np.array([3.0, 4.0])}, {}, lr=0.1, clipnorm=1.0)
+  assert np.allclose(st2['m']['w'], 0.1 * np.array([0.6, 0.8]))
+  assert np.allclose(wo.clip_by_norm(np.array([0.3, 0.4]), 1.0), [0.3, 0.4])

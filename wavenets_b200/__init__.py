@@ -8,5 +8,6 @@ from .layers import WaveNetLayer
 from .model import WaveNet
 from .config import load_config, model_kwargs, CONFIGS
 from . import synth
+from . import optimizers
 
-__all__ = ['WaveNetLayer', 'WaveNet', 'load_config', 'model_kwargs', 'CONFIGS', 'synth']
+__all__ = ['WaveNetLayer', 'WaveNet', 'load_config', 'model_kwargs', 'CONFIGS', 'synth', 'optimizers']

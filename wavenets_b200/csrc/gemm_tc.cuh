@@ -86,6 +86,25 @@ static inline void tc_pack_gate_T(cudaStream_t st, const float* src, int ktot, i
   tc_pack_gate_T_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, ktot, cout, dst, ld, tile, D, n16);
 }
 
+// programmatic dependent launch of the GEMM-class kernels (WN_TC_PDL=0 turns it off for A/B runs)
+static inline int tc_pdl_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("WN_TC_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+static inline int tc_launch_attrs(cudaLaunchAttribute* attr, int cluster) {
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeClusterDimension;
+  attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+  ++n;
+  if (tc_pdl_on()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  return n;
+}
+
 // ---------------------------------------------------------------- conv GEMM kernel
 struct TcGemmParams {
   int B, T;
@@ -389,6 +408,9 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
   if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above touched only shared memory / TMEM; global data of the previous kernel is read below
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (mainloop operands) =====================
@@ -744,10 +766,8 @@ static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGe
   const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, CG);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mw, *mi[0], *mi[1], *mo[0], *mo[1], *mo[2], p, sp, ep);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "staged conv_gemm launch (cta_group %d): %s", CG, cudaGetErrorString(e)); return -13; }
   return 0;
@@ -864,6 +884,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (CL > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1038,10 +1060,8 @@ static int tc_wgrad_launch_cl(const CUtensorMap* const* ma, const CUtensorMap* m
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, CL);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mg, p);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "wgrad launch (cluster %d): %s", CL, cudaGetErrorString(e)); return -13; }
   return 0;
@@ -1115,6 +1135,8 @@ struct TcWgradFinish {
   int wblocks;   // blocks of the weight part
 };
 __global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
+  pdl_launch_dependents();
+  pdl_wait();
   if ((int)blockIdx.x < f.wblocks) {
     const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long n_all = (long long)f.ktot * f.N;

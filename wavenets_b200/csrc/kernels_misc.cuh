@@ -514,3 +514,55 @@ __global__ void quantize_kernel(const float* __restrict__ x, long long* __restri
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) idx[i] = wn_quantize_idx(x[i], bits);
 }
+
+// ------------------------------------------------------------------ optimizer (train.py:225-226, model.py:336)
+// tf.keras.optimizers.Adam(learning_rate, clipnorm=1.0) on the flat fp32 buffers.  The flat buffer is cut into chunks
+// of OPT_CHUNK elements that never straddle a variable: chunk c = (variable id, first element, count).
+#define OPT_CHUNK 4096
+struct OptChunk { int var; int count; long long start; };
+// per-chunk sum of squares of the gradient (deterministic: fixed tree per chunk)
+__global__ void __launch_bounds__(256) opt_sumsq_kernel(const float* __restrict__ g, const OptChunk* __restrict__ chunks, float* __restrict__ partial) {
+  const OptChunk c = chunks[blockIdx.x];
+  const float* p = g + c.start;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < c.count; i += 256) s = fmaf(p[i], p[i], s);
+  __shared__ float sh[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+// per variable: norm = sqrt(sum of its chunk partials, in chunk order); tf.clip_by_norm scale = clipnorm / max(norm, clipnorm)
+__global__ void opt_clip_scale_kernel(const float* __restrict__ partial, const int* __restrict__ var_first_chunk, int n_vars, float clipnorm,
+                                      float* __restrict__ scale, float* __restrict__ norms) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vars) return;
+  float s = 0.f;
+  for (int c = var_first_chunk[v]; c < var_first_chunk[v + 1]; ++c) s += partial[c];
+  const float n = sqrtf(s);
+  norms[v] = n;
+  scale[v] = clipnorm > 0.f ? clipnorm / fmaxf(n, clipnorm) : 1.0f;
+}
+__global__ void __launch_bounds__(256) opt_clip_apply_kernel(float* __restrict__ g, const OptChunk* __restrict__ chunks, const float* __restrict__ scale) {
+  const OptChunk c = chunks[blockIdx.x];
+  const float sc = scale[c.var];
+  if (sc == 1.0f) return;
+  float* p = g + c.start;
+  for (int i = threadIdx.x; i < c.count; i += 256) p[i] *= sc;
+}
+// Keras 3 Adam.update_step: m += (g - m)(1 - b1); v += (g^2 - v)(1 - b2); w -= alpha * m / (sqrt(v) + eps),
+// alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
+__global__ void __launch_bounds__(256) opt_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                       long long n, float alpha, float one_minus_b1, float one_minus_b2, float eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = fmaf(gi - m[i], one_minus_b1, m[i]);
+  const float vi = fmaf(fmaf(gi, gi, -v[i]), one_minus_b2, v[i]);
+  m[i] = mi; v[i] = vi;
+  w[i] -= alpha * mi / (sqrtf(vi) + eps);
+}

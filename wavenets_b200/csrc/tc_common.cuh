@@ -204,6 +204,14 @@ template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatil
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The step is ~270 dependent launches of 25-40 us; without PDL every one pays launch latency, block scheduling and
+// its prologue (barrier init, TMEM allocation, tensor-map fetch) after the previous kernel has fully drained.
+// launch_dependents lets the next kernel's CTAs take over an SM as soon as this kernel's CTA there exits and run
+// their prologue; wait blocks until the previous grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");

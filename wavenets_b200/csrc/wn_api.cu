@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -158,6 +159,13 @@ struct wn_handle {
   unsigned long long drop_seed = 0x243F6A8885A308D3ull;
   bool drop_injected = false;   // masks were supplied by wn_set_dropout_masks: do not redraw
   bool drop_active = false;     // the pass being enqueued is a training pass with dropout > 0
+  // optimizer state (wn_adam_*): allocated on first use
+  float* opt_m = nullptr; float* opt_v = nullptr;
+  OptChunk* opt_chunks = nullptr; int opt_n_chunks = 0;
+  int* opt_var_first = nullptr;
+  float* opt_partial = nullptr; float* opt_scale = nullptr; float* opt_norms = nullptr;
+  float opt_lr = 1e-3f, opt_b1 = 0.9f, opt_b2 = 0.999f, opt_eps = 1e-7f, opt_clipnorm = 0.f;
+  long long opt_t = 0;
   float* layer_xin = nullptr;             // layer API staging (fp32 in -> T)
   void* layer_in = nullptr;
   float* d_loss = nullptr;                // for the host-buffer entry point
@@ -596,6 +604,8 @@ extern "C" void wn_destroy(wn_handle* h) {
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
+  cudaFree(h->opt_m); cudaFree(h->opt_v); cudaFree(h->opt_chunks); cudaFree(h->opt_var_first);
+  cudaFree(h->opt_partial); cudaFree(h->opt_scale); cudaFree(h->opt_norms);
   cudaFree(h->d_params); cudaFree(h->d_grads); cudaFree(h->pack.base); cudaFree(h->ws.base);
   cudaFreeHost(h->pin_frames); cudaFreeHost(h->pin_cond); cudaFreeHost(h->pin_loss);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -856,7 +866,13 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     f.bias0 = g.bias_dst; f.bias1 = g.bias1; f.per_batch = g.per_batch; f.ldpb = g.ldpb;
     f.wblocks = cdiv((long long)ktot * g.N, 256);
     LaunchScope ls(h, st, cls);
-    tc_wgrad_finish<<<f.wblocks + (want_cs ? cdiv(g.N, 32) : 0), 256, 0, st>>>(f);
+    {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(f.wblocks + (want_cs ? cdiv(g.N, 32) : 0)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 1);
+      CK(cudaLaunchKernelEx(&cfg, tc_wgrad_finish, f));
+    }
     return WN_OK;
   }
   {
@@ -1431,6 +1447,71 @@ static int check_bt(wn_handle* h, int B, int T) {
     set_err("batch/time (%d,%d) outside the workspace built for (%d,%d)", B, T, h->maxB, h->maxT);
     return WN_ERR_VALUE;
   }
+  return WN_OK;
+}
+
+// ============================================================================ optimizer (train.py:225-226; model.py:336)
+extern "C" int wn_adam_init(wn_handle* h, float lr, float beta1, float beta2, float eps, float clipnorm) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if (lr < 0.f || beta1 < 0.f || beta1 >= 1.f || beta2 < 0.f || beta2 >= 1.f || eps <= 0.f || clipnorm < 0.f) { set_err("bad Adam hyper-parameters"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  h->opt_lr = lr; h->opt_b1 = beta1; h->opt_b2 = beta2; h->opt_eps = eps; h->opt_clipnorm = clipnorm; h->opt_t = 0;
+  const size_t bytes = (size_t)h->n_scalars * 4;
+  if (!h->opt_m) {
+    CK(cudaMalloc(&h->opt_m, bytes)); CK(cudaMalloc(&h->opt_v, bytes));
+    std::vector<OptChunk> ch; std::vector<int> first;
+    for (size_t v = 0; v < h->params.size(); ++v) {
+      first.push_back((int)ch.size());
+      for (long long o = 0; o < h->params[v].count; o += OPT_CHUNK)
+        ch.push_back(OptChunk{(int)v, (int)std::min<long long>(OPT_CHUNK, h->params[v].count - o), h->params[v].offset + o});
+    }
+    first.push_back((int)ch.size());
+    h->opt_n_chunks = (int)ch.size();
+    CK(cudaMalloc(&h->opt_chunks, ch.size() * sizeof(OptChunk)));
+    CK(cudaMalloc(&h->opt_var_first, first.size() * sizeof(int)));
+    CK(cudaMalloc(&h->opt_partial, ch.size() * 4));
+    CK(cudaMalloc(&h->opt_scale, h->params.size() * 4));
+    CK(cudaMalloc(&h->opt_norms, h->params.size() * 4));
+    CK(cudaMemcpy(h->opt_chunks, ch.data(), ch.size() * sizeof(OptChunk), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->opt_var_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemset(h->opt_m, 0, bytes)); CK(cudaMemset(h->opt_v, 0, bytes));
+  return WN_OK;
+}
+// per-variable tf.clip_by_norm of the gradients in place (Keras clips each replica's gradients before the cross-replica sum)
+extern "C" int wn_clip_grads(wn_handle* h, void* stream) {
+  if (!h || !h->opt_m) { set_err("call wn_adam_init first"); return WN_ERR_STATE; }
+  if (h->opt_clipnorm <= 0.f) return WN_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  opt_sumsq_kernel<<<h->opt_n_chunks, 256, 0, st>>>(h->d_grads, h->opt_chunks, h->opt_partial);
+  const int nv = (int)h->params.size();
+  opt_clip_scale_kernel<<<cdiv(nv, 128), 128, 0, st>>>(h->opt_partial, h->opt_var_first, nv, h->opt_clipnorm, h->opt_scale, h->opt_norms);
+  opt_clip_apply_kernel<<<h->opt_n_chunks, 256, 0, st>>>(h->d_grads, h->opt_chunks, h->opt_scale);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+// one Adam update from wn_grads_dev (already clipped / all-reduced by the caller); lr < 0 keeps the current learning rate.
+// Re-packs the kernel-side weight copies.
+extern "C" int wn_adam_step(wn_handle* h, float lr, void* stream) {
+  if (!h || !h->opt_m) { set_err("call wn_adam_init first"); return WN_ERR_STATE; }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lr >= 0.f) h->opt_lr = lr;
+  h->opt_t += 1;
+  const double b1t = pow((double)h->opt_b1, (double)h->opt_t), b2t = pow((double)h->opt_b2, (double)h->opt_t);
+  const float alpha = (float)((double)h->opt_lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  opt_adam_kernel<<<cdiv(h->n_scalars, 256), 256, 0, st>>>(h->d_params, h->d_grads, h->opt_m, h->opt_v, h->n_scalars, alpha, 1.0f - h->opt_b1,
+                                                          1.0f - h->opt_b2, h->opt_eps);
+  CK(cudaGetLastError());
+  return wn_params_changed(h, stream);
+}
+extern "C" int wn_adam_state(wn_handle* h, float** m_dev, float** v_dev, float** grad_norms_dev, int64_t* step) {
+  if (!h || !h->opt_m) { set_err("call wn_adam_init first"); return WN_ERR_STATE; }
+  if (m_dev) *m_dev = h->opt_m;
+  if (v_dev) *v_dev = h->opt_v;
+  if (grad_norms_dev) *grad_norms_dev = h->opt_norms;
+  if (step) *step = h->opt_t;
   return WN_OK;
 }
 

@@ -112,6 +112,8 @@ class WaveNet:
       raise ValueError('Loss must be set in the model init function.')
     self.optimizer = kwargs.get('optimizer', None)
     self._metrics_from_compilation = list(kwargs.get('metrics') or [])
+    if self.optimizer is not None and self.built and hasattr(self.optimizer, 'build'):
+      self.optimizer.build(self)
 
   # ------------------------------------------------------------------ build (model.py:171-211)
   def build(self, input_shape):
@@ -170,6 +172,8 @@ class WaveNet:
       self._handle.glorot_init(seed=1, bias_std=0.0)   # Keras defaults: glorot-uniform, zero bias
     self.built = True
     self._built_for = (B, T)
+    if self.optimizer is not None and hasattr(self.optimizer, 'build'):
+      self.optimizer.build(self)      # model.py:211
 
   def _ensure_built(self, x, cond):
     B, T = int(x.shape[0]), int(x.shape[1])
@@ -300,6 +304,8 @@ class WaveNet:
     h = self.handle
     fn = h.lib.wn_train_step if train else h.lib.wn_test_step
     _lib.check(fn(h.h, h.ptr(frames), h.ptr(cond), B, T, self.n_replicas, h.ptr(h._loss), h.stream_ptr()))
+    if train and self.optimizer is not None and getattr(self.optimizer, 'clipnorm', None):
+      self.optimizer.clip(self)      # Keras: each replica clips its own gradients, then they are summed
     if train and self._process_group is not None:
       # MirroredStrategy's gradient all-reduce (SUM: the loss is already divided by the global batch)
       torch.distributed.all_reduce(h.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self._process_group)
