@@ -106,6 +106,16 @@ int wn_get_grad(wn_handle* h, int i, float* host);
  * kernel-side weight copies (transposes, gate interleave, bf16). */
 int wn_params_changed(wn_handle* h, void* stream);
 
+/* ---- sampling + MSE metric: WaveNet.sample_waveform (model.py:393-503) and the compiled
+ *      MeanSquaredError between y_true and the sampled waveform inside train_step/test_step (model.py:338-346).
+ *      deterministic != 0: argmax bin / mean of the heaviest mixture component (bit-comparable with the reference);
+ *      otherwise a Philox draw per (b,t) keyed by `seed` — TF's stateless RNG stream (seed (4,2), identical for every
+ *      batch row, model.py:408,428,437) cannot be reproduced, so stochastic parity is statistical.
+ *      out (B,T) fp32 in [-1,1]. */
+int wn_sample_waveform(wn_handle* h, const float* pred_dev, int B, int T, int deterministic, uint64_t seed, float* out_dev, void* stream);
+int wn_sample_last_step(wn_handle* h, const float* frames_dev, int deterministic, uint64_t seed, float* out_dev, float* mse_dev /* 2 floats or NULL */,
+                        void* stream);
+
 /* ---- optimizer: train.py:225-226 `tf.keras.optimizers.Adam(learning_rate=lr, clipnorm=1.0)` applied by
  *      model.py:336 `optimizer.apply_gradients`.  Keras 3 semantics: every variable's gradient is clipped to L2 norm
  *      <= clipnorm (tf.clip_by_norm) on each replica BEFORE the cross-replica sum; then

@@ -566,3 +566,90 @@ __global__ void __launch_bounds__(256) opt_adam_kernel(float* __restrict__ w, co
   m[i] = mi; v[i] = vi;
   w[i] -= alpha * mi / (sqrtf(vi) + eps);
 }
+
+// ------------------------------------------------------------------ sample_waveform (model.py:393-503) + MSE metric (model.py:338-346)
+// One warp per (b,t) row.  kind 0: categorical over C classes; `is_logits` says whether `pred` holds pre-softmax logits
+// (the fused train step keeps those) or probabilities (WaveNet.call output).  deterministic: argmax (first maximum);
+// otherwise inverse-CDF draw with a Philox uniform per row (TF's stateless_categorical / seed (4,2) stream cannot be
+// reproduced: statistical parity only).  Output idx / 2^(bits-1) - 1.
+// kinds 1/2: logistic / gaussian mixtures, pred = [weights M | means M | log-scales M]: component = argmax or a
+// categorical draw over softmax(weights); sample = mu (deterministic) or mu + scale*(log u - log(1-u)) / mu + scale*z;
+// clipped to [-1,1].  Optional: squared error against y (frames[b][t+1]) accumulated per block -> mse_partial.
+__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ pred, int ld, int C, int M, int kind, int is_logits, int bits,
+                                                     int deterministic, unsigned long long seed, const float* __restrict__ frames, int Tn,
+                                                     long long rows, float* __restrict__ out, float* __restrict__ mse_partial) {
+  __shared__ float wsum[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  float err2 = 0.f;
+  if (row < rows) {
+    const float* p = pred + row * ld;
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), 0x5A17u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u0 = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+    const float u1 = ((float)(rnd.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(rnd.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const int n = kind == 0 ? C : M;
+    // softmax statistics of the n selection weights (identity for probabilities)
+    float mx = -INFINITY;
+    for (int c = lane; c < n; c += 32) mx = fmaxf(mx, p[c]);
+    mx = warp_max(mx);
+    const bool soft = kind != 0 || is_logits;
+    float sum = 0.f;
+    for (int c = lane; c < n; c += 32) sum += soft ? expf(p[c] - mx) : p[c];
+    sum = warp_sum(sum);
+    int sel;
+    if (deterministic) {
+      // first index attaining the maximum (tf.argmax)
+      int best = 0x7fffffff;
+      for (int c = lane; c < n; c += 32) if (p[c] == mx) { best = c; break; }
+      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      sel = best;
+    } else {
+      // smallest k with cdf(k) > u*sum : lane-strided partial sums in class order chunks of 32
+      const float target = u0 * sum;
+      float run = 0.f;
+      sel = n - 1;
+      bool found = false;
+      for (int c0 = 0; c0 < n && !found; c0 += 32) {
+        const int c = c0 + lane;
+        float w = c < n ? (soft ? expf(p[c] - mx) : p[c]) : 0.f;
+        float incl = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const unsigned hit = __ballot_sync(0xffffffffu, c < n && run + incl > target);
+        if (hit) { sel = c0 + __ffs(hit) - 1; found = true; }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    float val;
+    if (kind == 0) {
+      val = (float)sel / exp2f((float)(bits - 1)) - 1.0f;
+    } else {
+      const float mu = p[M + sel];
+      if (deterministic) val = mu;
+      else {
+        const float sc = expf(p[2 * M + sel]);
+        if (kind == 1) val = mu + sc * (logf(u1) - logf(1.0f - u1));
+        else val = mu + sc * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+      }
+      val = fminf(fmaxf(val, -1.0f), 1.0f);
+    }
+    if (lane == 0) {
+      out[row] = val;
+      if (frames) {
+        const long long b = row / Tn, t = row % Tn;
+        const float d = frames[b * (Tn + 1) + t + 1] - val;
+        err2 = d * d;
+      }
+    }
+  }
+  if (mse_partial) {
+    if (lane == 0) wsum[warp] = err2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += wsum[i];
+      mse_partial[blockIdx.x] = t;
+    }
+  }
+}

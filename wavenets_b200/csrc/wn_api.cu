@@ -1450,6 +1450,36 @@ static int check_bt(wn_handle* h, int B, int T) {
   return WN_OK;
 }
 
+// ============================================================================ sampling + MSE metric (model.py:338-346,393-503)
+static int sample_common(wn_handle* h, const float* pred, int ld, int is_logits, const float* frames, int B, int T, int deterministic, uint64_t seed,
+                         float* out_dev, float* mse_dev, cudaStream_t st) {
+  const wn_config& c = h->cfg;
+  const long long rows = (long long)B * T;
+  const int kind = c.sampling_function == WN_CATEGORICAL ? 0 : (c.sampling_function == WN_GAUSSIAN ? 2 : 1);
+  const int nparts = cdiv(rows, 8);
+  if (mse_dev && nparts > h->loss_parts_cap) { set_err("sample: workspace too small"); return WN_ERR_STATE; }
+  sample_kernel<<<nparts, 256, 0, st>>>(pred, ld, h->Cout, c.num_mixtures, kind, is_logits, c.bits, deterministic, seed, frames, T, rows, out_dev,
+                                       mse_dev ? h->loss_partial : nullptr);
+  if (mse_dev) loss_finalize<<<1, 1024, 0, st>>>(h->loss_partial, nparts, 1.0f / (float)rows, nullptr, 0.f, mse_dev);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+// sample_waveform(pred) for a caller-held WaveNet.call output (probabilities or mixture parameters), (B,T,Cout) fp32
+extern "C" int wn_sample_waveform(wn_handle* h, const float* pred_dev, int B, int T, int deterministic, uint64_t seed, float* out_dev, void* stream) {
+  RET(check_bt(h, B, T));
+  if (!pred_dev || !out_dev || !h->cfg.has_head) { set_err("bad sample arguments"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  return sample_common(h, pred_dev, h->Cout, 0, nullptr, B, T, deterministic, seed, out_dev, nullptr, (cudaStream_t)stream);
+}
+// the same on the predictions of the LAST train/test step (kept on the device as logits), plus the MSE metric against
+// y_true = frames[:,1:] (model.py:338-346): mse_dev[0] = mean over (b,t) of (y - sample)^2; mse_dev needs 2 floats
+extern "C" int wn_sample_last_step(wn_handle* h, const float* frames_dev, int deterministic, uint64_t seed, float* out_dev, float* mse_dev, void* stream) {
+  if (!h || !h->cfg.has_head || h->lastB < 1) { set_err("no train/test step to sample from"); return WN_ERR_STATE; }
+  if (!out_dev) { set_err("bad sample arguments"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  return sample_common(h, h->logits, h->ldl, 1, mse_dev ? frames_dev : nullptr, h->lastB, h->lastT, deterministic, seed, out_dev, mse_dev, (cudaStream_t)stream);
+}
+
 // ============================================================================ optimizer (train.py:225-226; model.py:336)
 extern "C" int wn_adam_init(wn_handle* h, float lr, float beta1, float beta2, float eps, float clipnorm) {
   if (!h) { set_err("null handle"); return WN_ERR_VALUE; }

@@ -103,6 +103,9 @@ class WaveNet:
     self._handle: Optional[Handle] = None
     self._pending_weights = None
     self._staging = {}
+    self._metrics_from_compilation = []
+    self._sample_seed, self._sample_calls = 0x42, 0
+    self._last_frames, self._last_rows = None, 0
     self.n_replicas = 1          # MirroredStrategy replica count (train.py:203); set by parallel.attach()
     self._process_group = None
 
@@ -302,6 +305,7 @@ class WaveNet:
     cond = self._stage('cond', cond, (B, int(cond.shape[-1])), dev) if cond is not None else None
     self._ensure_built(frames[:, :-1], cond)
     h = self.handle
+    self._last_frames, self._last_rows = frames, B * T
     fn = h.lib.wn_train_step if train else h.lib.wn_test_step
     _lib.check(fn(h.h, h.ptr(frames), h.ptr(cond), B, T, self.n_replicas, h.ptr(h._loss), h.stream_ptr()))
     if train and self.optimizer is not None and getattr(self.optimizer, 'clipnorm', None):
@@ -320,19 +324,44 @@ class WaveNet:
     return self._metrics_dict(loss)
 
   def _metrics_dict(self, loss_dev):
-    # model.py:340-348: 'loss' excludes the regulariser, which is reported as 'reg_loss'
-    vals = loss_dev.tolist()
+    # model.py:338-348: 'loss' excludes the regulariser, which is reported as 'reg_loss'; every compiled metric is
+    # fed (y_true, waveform sampled from this step's predictions)
+    mse = None
+    if self._metrics_from_compilation:
+      h = self.handle
+      self._sample_calls += 1
+      out_buf = self._stage_like('sample', (self._last_rows,))
+      _lib.check(h.lib.wn_sample_last_step(h.h, h.ptr(self._last_frames), 0, C.c_uint64(self._sample_seed + self._sample_calls),
+                                           h.ptr(out_buf), h.ptr(h._loss[2:]), h.stream_ptr()))
+    vals = loss_dev.tolist() if not self._metrics_from_compilation else self.handle._loss.tolist()
     out = {'loss': vals[0]}
     if self.regularization:
       out['reg_loss'] = vals[1]
+    for metric in self._metrics_from_compilation:
+      metric.update_state(vals[2])
+      out[metric.name] = metric.result()
     return out
+
+  def _stage_like(self, name, shape):
+    buf = self._staging.get(name)
+    dev = torch.device('cuda', self.device_index)
+    if buf is None or tuple(buf.shape) != tuple(shape):
+      buf = torch.empty(shape, dtype=torch.float32, device=dev)
+      self._staging[name] = buf
+    return buf
+
+  def reset_metrics(self):
+    for metric in self._metrics_from_compilation:
+      metric.reset_state()
 
   def train_step_async(self, data):
     """Same as train_step without the host read-back: returns a device tensor [loss, reg_loss]."""
     return self._step(data, True)
 
   def test_step(self, data):
-    return {'loss': self._step(data, False).tolist()[0]}
+    out = self._metrics_dict(self._step(data, False))
+    out.pop('reg_loss', None)     # model.py:384-389: test_step reports the loss and the compiled metrics only
+    return out
 
   def loss_fn(self, target, pred):
     raise NotImplementedError('stand-alone loss_fn on materialised predictions is not built: the loss is fused into train_step/test_step')
@@ -340,8 +369,24 @@ class WaveNet:
   def compute_receptive_field(self, sampling_frequency):
     return self.receptive_field / sampling_frequency
 
-  def sample_waveform(self, inputs, deterministic=False):
-    raise NotImplementedError('sampling is inference-only (model.py:393-503) and out of scope')
+  def sample_waveform(self, inputs, deterministic=False, seed=None):
+    """model.py:393-503 on a `call` output (probabilities or mixture parameters), (B,T,C) -> (B,T,1)
+    ((B,T) for deterministic categorical, like the reference).  Stochastic draws use a Philox stream keyed by
+    `seed` (TF's stateless seed-(4,2) stream cannot be reproduced: statistical parity)."""
+    dev = torch.device('cuda', self.device_index)
+    pred = as_dev(inputs, dev)
+    if pred.dim() != 3:
+      raise ValueError('pred must be (batch, samples, channels)')
+    B, T = int(pred.shape[0]), int(pred.shape[1])
+    h = self.handle
+    out = torch.empty((B, T), dtype=torch.float32, device=dev)
+    if seed is None:
+      self._sample_calls += 1
+      seed = self._sample_seed + self._sample_calls
+    _lib.check(h.lib.wn_sample_waveform(h.h, h.ptr(pred), B, T, 1 if deterministic else 0, C.c_uint64(int(seed)), h.ptr(out), h.stream_ptr()))
+    if deterministic and self.num_mixtures is None:
+      return out
+    return out.unsqueeze(-1)
 
   def generate(self, *args, **kwargs):
     raise NotImplementedError('autoregressive generation (model.py:258-307) is inference-only and out of scope')
