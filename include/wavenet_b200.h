@@ -106,6 +106,16 @@ int wn_get_grad(wn_handle* h, int i, float* host);
  * kernel-side weight copies (transposes, gate interleave, bf16). */
 int wn_params_changed(wn_handle* h, void* stream);
 
+/* ---- device input pipeline: preprocess_dataset (utils.py:22-85) and inverse_mu_law (callbacks.py:126-131)
+ * speech (n_samples) int16 (scaled by 2^-15, utils.py:52-55) or fp32 -> optional mu-law (utils.py:35) ->
+ * frames (wn_num_frames, T+1) with hop T (utils.py:36-38); valid[f] = 1 iff the frame is finite and inside [-1,1]
+ * (utils.py:58-70).  wn_one_hot = tf.one_hot (utils.py:47). */
+int64_t wn_num_frames(int64_t n_samples, int T);
+int wn_preprocess_frames(const void* speech_dev, int is_int16, int64_t n_samples, int T, int apply_mulaw, float* frames_dev, int32_t* valid_dev,
+                         void* stream);
+int wn_inverse_mu_law(const float* y_dev, float* x_dev, int64_t n, void* stream);
+int wn_one_hot(const int32_t* ids_dev, int n, int depth, float* out_dev, void* stream);
+
 /* ---- sampling + MSE metric: WaveNet.sample_waveform (model.py:393-503) and the compiled
  *      MeanSquaredError between y_true and the sampled waveform inside train_step/test_step (model.py:338-346).
  *      deterministic != 0: argmax bin / mean of the heaviest mixture component (bit-comparable with the reference);

@@ -90,3 +90,14 @@ def test_no_gpu_fails_loudly():
   m = WaveNet(channels=8, blocks=2, final_layers_channels=[8], dilation_bound=4)
   with pytest.raises(RuntimeError, match='no CPU fallback'):
     m(np.zeros((1, 16, 1), np.float32))
+
+
+def test_checkpoint_names_and_resume_parse(tmp_path):
+  """train.py:68-86,149-154: file pattern and resume-by-filename."""
+  from wavenets_b200 import checkpoint as ck
+  assert ck.checkpoint_name(7, 0.0005) == 'weights-e0007-lr0.0005.weights.npz'
+  assert ck.find_last_checkpoint(str(tmp_path / 'nope')) is None
+  for e, lr in [(1, 0.0005), (12, 0.00025), (3, 0.0005)]:
+    (tmp_path / ck.checkpoint_name(e, lr)).write_bytes(b'')
+  path, epoch, lr = ck.find_last_checkpoint(str(tmp_path))
+  assert path.endswith('weights-e0012-lr0.00025.weights.npz') and epoch == 12 and lr == 0.00025

@@ -653,3 +653,47 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ p
     }
   }
 }
+
+// ------------------------------------------------------------------ device input pipeline (utils.py:31-70, callbacks.py:126-131)
+// mu-law companding utils.py:35: sign(x) * log(1 + 255|x|) / log(256).  Evaluated in fp64 and rounded once, i.e. the
+// correctly rounded fp32 value of the formula (TF evaluates it with its own fp32 log: <= 1 ulp from this).
+__device__ __forceinline__ float wn_mu_law(float x) {
+  const double a = fabs((double)x);
+  const double y = log(1.0 + 255.0 * a) / 5.545177444479562;   // log(256)
+  const float r = (float)y;
+  return x > 0.f ? r : (x < 0.f ? -r : 0.f * x);
+}
+// frames[f][i] = g(speech[f*T + i]), i in [0, T], f in [0, n_frames): tf.signal.frame(frame_length=T+1, frame_step=T)
+// (utils.py:36-38), g = optional /2^15 for int16 input (utils.py:52-55) then optional mu-law.  valid[f] = every sample
+// finite and within [-1,1] (utils.py:58-70; the length test is always true for un-padded frames).
+template <class TIN>
+__global__ void preprocess_frames_kernel(const TIN* __restrict__ speech, float in_scale, int T, int n_frames, int apply_mulaw,
+                                         float* __restrict__ frames, int* __restrict__ valid) {
+  const int f = blockIdx.y;
+  int bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= T; i += gridDim.x * blockDim.x) {
+    float x = (float)speech[(long long)f * T + i] * in_scale;
+    if (apply_mulaw) x = wn_mu_law(x);
+    frames[(long long)f * (T + 1) + i] = x;
+    if (!(isfinite(x) && x >= -1.0f && x <= 1.0f)) bad = 1;
+  }
+  if (bad) atomicAnd(valid + f, 0);     // idempotent flag clear: order-independent
+}
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// callbacks.py:126-131: sign(y) * (256^|y| - 1) / 255
+__global__ void inverse_mu_law_kernel(const float* __restrict__ y, float* __restrict__ x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = y[i];
+  const float r = (float)((exp(fabs((double)v) * 5.545177444479562) - 1.0) / 255.0);
+  x[i] = v > 0.f ? r : (v < 0.f ? -r : 0.f * v);
+}
+// tf.one_hot(ids, depth): rows of zeros with a one at ids[i] (all zeros when the id is out of range)
+__global__ void one_hot_kernel(const int* __restrict__ ids, int n, int depth, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * depth) return;
+  out[i] = ids[i / depth] == (int)(i % depth) ? 1.0f : 0.0f;
+}

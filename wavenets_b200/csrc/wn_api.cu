@@ -1450,6 +1450,39 @@ static int check_bt(wn_handle* h, int B, int T) {
   return WN_OK;
 }
 
+// ============================================================================ device input pipeline (utils.py:31-70)
+extern "C" int64_t wn_num_frames(int64_t n_samples, int T) {
+  if (T < 1 || n_samples < (int64_t)T + 1) return 0;
+  return 1 + (n_samples - (T + 1)) / T;
+}
+extern "C" int wn_preprocess_frames(const void* speech_dev, int is_int16, int64_t n_samples, int T, int apply_mulaw, float* frames_dev, int32_t* valid_dev,
+                                    void* stream) {
+  const int64_t nf = wn_num_frames(n_samples, T);
+  if (nf == 0) return WN_OK;      /* shorter than one frame: nothing to emit */
+  if (!speech_dev || !frames_dev || !valid_dev || nf > 65535) { set_err("bad preprocess arguments (at most 65535 frames per call)"); return WN_ERR_VALUE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  fill_int_kernel<<<cdiv(nf, 256), 256, 0, st>>>(valid_dev, (int)nf, 1);
+  const dim3 grid(cdiv(T + 1, 256) < 64 ? cdiv(T + 1, 256) : 64, (unsigned)nf);
+  if (is_int16) preprocess_frames_kernel<short><<<grid, 256, 0, st>>>((const short*)speech_dev, 1.0f / 32768.0f, T, (int)nf, apply_mulaw, frames_dev, valid_dev);
+  else preprocess_frames_kernel<float><<<grid, 256, 0, st>>>((const float*)speech_dev, 1.0f, T, (int)nf, apply_mulaw, frames_dev, valid_dev);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+extern "C" int wn_inverse_mu_law(const float* y_dev, float* x_dev, int64_t n, void* stream) {
+  if (n == 0) return WN_OK;
+  if (!y_dev || !x_dev || n < 0) { set_err("bad inverse_mu_law arguments"); return WN_ERR_VALUE; }
+  inverse_mu_law_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(y_dev, x_dev, n);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+extern "C" int wn_one_hot(const int32_t* ids_dev, int n, int depth, float* out_dev, void* stream) {
+  if (n == 0) return WN_OK;
+  if (!ids_dev || !out_dev || n < 0 || depth < 1) { set_err("bad one_hot arguments"); return WN_ERR_VALUE; }
+  one_hot_kernel<<<cdiv((long long)n * depth, 256), 256, 0, (cudaStream_t)stream>>>(ids_dev, n, depth, out_dev);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+
 // ============================================================================ sampling + MSE metric (model.py:338-346,393-503)
 static int sample_common(wn_handle* h, const float* pred, int ld, int is_logits, const float* frames, int B, int T, int deterministic, uint64_t seed,
                          float* out_dev, float* mse_dev, cudaStream_t st) {
