@@ -30,3 +30,9 @@ tot = sum(v[1] for v in agg.values())
 print(f'{cnt // 3} launches/step, {tot / 3:.3f} ms/step summed (serial, warm)')
 for k, (nn, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
   print(f'{t / 3:8.3f} ms/step {nn // 3:4d}x {1e3 * t / nn:8.1f} us  {k}')
+if '--misc' in sys.argv:
+  per = cnt // 3
+  for i in range(2 * per, cnt):
+    h.lib.wn_profile_get(h.h, i, C.byref(d), lab, 64)
+    if lab.value.decode() == 'misc':
+      print(f'  launch {i - 2 * per:4d}  {1e3 * d.value:8.1f} us')

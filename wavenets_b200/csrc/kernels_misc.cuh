@@ -24,6 +24,52 @@ __global__ void input_conv_fwd(const float* __restrict__ x, int ldx, const float
   h[i] = from_f<T>(v);
 }
 
+// 8 channels per thread held across ROWS_PER_BLOCK rows: the K taps and the bias of those channels are loaded once
+// into registers (the per-row variant below re-loads 8*(K+1) floats for every 16-byte store)
+#define ICF_ROWS 64
+template <class T>
+__global__ void __launch_bounds__(256) input_conv_fwd_rows(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                                                           T* __restrict__ h, int B, int Tn, int R, int K) {
+  const int r8 = R >> 3;                       // channel groups per row
+  const int groups = 256 / r8 > 0 ? 256 / r8 : 1;   // rows processed side by side (r8 <= 256)
+  const int cg = threadIdx.x % r8, rg = threadIdx.x / r8;
+  if (rg >= groups) return;
+  const int c = cg << 3;
+  float w[4][8], bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = bias[c + j];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[k][j] = k < K ? W[k * R + c + j] : 0.f;
+  const long long rows = (long long)B * Tn;
+  const long long r_end = min(rows, ((long long)blockIdx.x + 1) * ICF_ROWS);
+  for (long long row = (long long)blockIdx.x * ICF_ROWS + rg; row < r_end; row += groups) {
+    const int t = (int)(row % Tn), b = (int)(row / Tn);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = bv[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ts = t - (K - 1 - k);
+      if (k < K && ts >= 0) {
+        const float xv = x[(long long)b * ldx + ts];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(w[k][j], xv, v[j]);
+      }
+    }
+    T* o = h + row * R + c;
+    if constexpr (sizeof(T) == 2) {
+      uint4 q;
+      q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(o) = q;
+    } else {
+      reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
 // same, 8 channels per thread (R % 8 == 0): 16/32-byte stores, no per-element div/mod
 template <class T>
 __global__ void __launch_bounds__(256) input_conv_fwd_vec8(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
@@ -77,6 +123,58 @@ __global__ void input_conv_bwd_stage1(const float* __restrict__ x, int ldx, cons
   }
   const long long chunk = (long long)b * gridDim.y + blockIdx.y;
   for (int k = 0; k <= K; ++k) partial[(chunk * (K + 1) + k) * R + c] = acc[k];
+}
+
+// wide variant (R even, R/2 <= 256): one block = ICB_ROWS flattened (b,t) rows x all channels; a thread owns a channel
+// pair (one 32-bit load per row for bf16) for every `groups`-th row, then the row groups are summed through shared
+// memory in a fixed order.  partial[block][k][c], k == K => bias.
+#define ICB_ROWS 128
+template <class T>
+__global__ void __launch_bounds__(256) input_conv_bwd_stage1_wide(const float* __restrict__ x, int ldx, const T* __restrict__ dh, int lddh,
+                                                                  float* __restrict__ partial, int B, int Tn, int R, int K) {
+  __shared__ float red[256][11];
+  const int cp_n = R >> 1;
+  const int groups = 256 / cp_n;
+  const int cp = threadIdx.x % cp_n, rg = threadIdx.x / cp_n;
+  float acc[5][2];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) acc[k][0] = acc[k][1] = 0.f;
+  const long long rows = (long long)B * Tn;
+  const long long r_end = min(rows, ((long long)blockIdx.x + 1) * ICB_ROWS);
+  if (rg < groups) {
+    for (long long row = (long long)blockIdx.x * ICB_ROWS + rg; row < r_end; row += groups) {
+      const int t = (int)(row % Tn), b = (int)(row / Tn);
+      float d0, d1;
+      if constexpr (sizeof(T) == 2) {
+        const uint32_t wv = *reinterpret_cast<const uint32_t*>(dh + row * lddh + 2 * cp);
+        d0 = __uint_as_float(wv << 16); d1 = __uint_as_float(wv & 0xffff0000u);
+      } else {
+        const float2 wv = *reinterpret_cast<const float2*>(dh + row * lddh + 2 * cp);
+        d0 = wv.x; d1 = wv.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ts = t - (K - 1 - k);
+        if (k < K && ts >= 0) {
+          const float xv = x[(long long)b * ldx + ts];
+          acc[k][0] = fmaf(d0, xv, acc[k][0]); acc[k][1] = fmaf(d1, xv, acc[k][1]);
+        }
+      }
+      acc[4][0] += d0; acc[4][1] += d1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { red[threadIdx.x][2 * k] = acc[k][0]; red[threadIdx.x][2 * k + 1] = acc[k][1]; }
+  __syncthreads();
+  if (rg == 0) {
+    float* out = partial + (long long)blockIdx.x * (K + 1) * R;
+    for (int k = 0; k <= K; ++k) {
+      const int kk = k < K ? k : 4;
+      float s0 = 0.f, s1 = 0.f;
+      for (int g = 0; g < groups; ++g) { s0 += red[g * cp_n + cp][2 * kk]; s1 += red[g * cp_n + cp][2 * kk + 1]; }
+      out[k * R + 2 * cp] = s0; out[k * R + 2 * cp + 1] = s1;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ generic deterministic reductions
@@ -379,6 +477,70 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
       if (dlogits) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) dlogits[row * ldd + c + i] = from_f<TD>((p[i] - (c + i == idx ? 1.0f : 0.0f)) * scale);
+      }
+    }
+  }
+  if (loss_partial) {
+    if (lane == 0) wsum[warp] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += wsum[i];
+      loss_partial[blockIdx.x] = t;
+    }
+  }
+}
+
+// register-resident variant for C = 128 * NV4 classes (C = 256 for 8-bit audio): the row is read from memory ONCE,
+// exp is evaluated once per element; same arithmetic order as softmax_ce_kernel (bit-identical results)
+template <class TD, int NV4>
+__global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __restrict__ logits, const float* __restrict__ frames, int Tn, long long rows,
+                                                             int bits, float scale, TD* __restrict__ dlogits, int ldd, float* __restrict__ probs,
+                                                             float* __restrict__ loss_partial) {
+  constexpr int C = 128 * NV4;
+  __shared__ float wsum[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  float loss = 0.f;
+  if (row < rows) {
+    const float* lp = logits + row * C;
+    float4 v[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) v[i] = *reinterpret_cast<const float4*>(lp + lane * 4 + i * 128);
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      v[i].x = expf(v[i].x - m); v[i].y = expf(v[i].y - m); v[i].z = expf(v[i].z - m); v[i].w = expf(v[i].w - m);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    s = warp_sum(s);
+    int idx = -1;
+    if (frames) {
+      const long long b = row / Tn, t = row % Tn;
+      idx = wn_quantize_idx(frames[b * (Tn + 1) + t + 1], bits);
+      loss = (m + logf(s)) - lp[idx];
+    }
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane * 4 + i * 128;
+      const float p[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
+      if (probs) *reinterpret_cast<float4*>(probs + row * C + c) = make_float4(p[0], p[1], p[2], p[3]);
+      if (dlogits) {
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = (p[j] - (c + j == idx ? 1.0f : 0.0f)) * scale;
+        if constexpr (sizeof(TD) == 2) {
+          uint2 q;
+          q.x = pack_bf16x2(d[0], d[1]); q.y = pack_bf16x2(d[2], d[3]);
+          *reinterpret_cast<uint2*>(dlogits + row * ldd + c) = q;
+        } else {
+          *reinterpret_cast<float4*>(dlogits + row * ldd + c) = make_float4(d[0], d[1], d[2], d[3]);
+        }
       }
     }
   }

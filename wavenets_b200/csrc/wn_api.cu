@@ -1027,7 +1027,9 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   {
     LaunchScope ls(h, st, CLS_MISC);
     const long long total = (long long)B * Tn * h->R;
-    if (h->R % 8 == 0)
+    if (h->R % 8 == 0 && h->R / 8 <= 256)
+      input_conv_fwd_rows<T><<<cdiv((long long)B * Tn, ICF_ROWS), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
+    else if (h->R % 8 == 0)
       input_conv_fwd_vec8<T><<<cdiv(total / 8, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
     else
       input_conv_fwd<T><<<cdiv(total, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
@@ -1076,8 +1078,12 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
     LaunchScope ls(h, st, CLS_LOSS);
     if (c.sampling_function == WN_CATEGORICAL) {
       nparts = cdiv(rows, 8);
-      softmax_ce_kernel<T><<<nparts, 256, 0, st>>>(h->logits, h->Cout, frames, Tn, rows, c.bits, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
-                                                  probs, loss_out ? h->loss_partial : nullptr);
+      if (h->Cout == 256 && h->ldl == 256 && h->ldd % 4 == 0)
+        softmax_ce_reg_kernel<T, 2><<<nparts, 256, 0, st>>>(h->logits, frames, Tn, rows, c.bits, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd, probs,
+                                                           loss_out ? h->loss_partial : nullptr);
+      else
+        softmax_ce_kernel<T><<<nparts, 256, 0, st>>>(h->logits, h->Cout, frames, Tn, rows, c.bits, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
+                                                    probs, loss_out ? h->loss_partial : nullptr);
     } else {
       nparts = cdiv(rows, 128);
       mixture_loss_kernel<T><<<nparts, 128, 0, st>>>(h->logits, h->ldl, c.num_mixtures, frames, Tn, rows, c.bits,
@@ -1420,20 +1426,25 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
   // ---- input conv (model.py:84-88): dW[k][c], db[c]
   {
+    const bool wide = h->R % 2 == 0 && h->R / 2 <= 256 && ld_dx % 2 == 0;
     const int chunks = cdiv(Tn, 64);
+    const int nparts = wide ? cdiv((long long)B * Tn, ICB_ROWS) : B * chunks;
     {
       LaunchScope ls(h, st, CLS_MISC);
-      input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 64);
+      if (wide)
+        input_conv_bwd_stage1_wide<T><<<nparts, 256, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K);
+      else
+        input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 64);
     }
     const long long kr = (long long)h->K * h->R;
     {
       LaunchScope ls(h, st, CLS_MISC);
-      reduce_parts_tall<<<cdiv(kr, 32), 256, 0, st>>>(h->colpart, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
+      reduce_parts_tall<<<cdiv(kr, 32), 256, 0, st>>>(h->colpart, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
                                                    l2coef != 0.f ? P_(h, h->input_conv.w_idx) : nullptr, l2coef);
     }
     {
       LaunchScope ls(h, st, CLS_MISC);
-      reduce_parts_tall<<<cdiv(h->R, 32), 256, 0, st>>>(h->colpart + kr, B * chunks, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
+      reduce_parts_tall<<<cdiv(h->R, 32), 256, 0, st>>>(h->colpart + kr, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
     }
   }
   if (c.conditioning) RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef));
