@@ -262,6 +262,16 @@ static inline const CUtensorMap* tc_act_map(TmapCache& tc, const bf16* A, int ld
   return tc.get(A, 4, dims, str, box);
 }
 
+// the same tensor seen as 64-channel atoms: (64 ch, T, C/64 atoms, B) with box (64, rows, atoms, 1).  One TMA op then
+// fills `atoms` consecutive [rows][128 B] slabs (8 KB apart for 64 rows) = the MN-major operand layout of the wgrad,
+// instead of one op per atom: a TMA issue costs the producer thread ~150-200 cycles (timeline, profiles/README.md)
+static inline const CUtensorMap* tc_atom_map(TmapCache& tc, const bf16* A, int lda, int K, int T, int B, int box_rows, int atoms) {
+  uint64_t dims[4] = {64, (uint64_t)T, (uint64_t)(K / 64), (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)lda * 2, 128, (uint64_t)T * lda * 2};
+  uint32_t box[4] = {64, (uint32_t)box_rows, (uint32_t)atoms, 1};
+  return tc.get(A, 4, dims, str, box);
+}
+
 template <class Epi, int BN, int NEPI>
 static int tc_conv_gemm_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep) {
   using Cfg = TcGemmCfg<BN>;
@@ -1024,6 +1034,281 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ---------------------------------------------------------------- wgrad kernel, CTA pairs (cta_group::2)
+// Same contraction, M = 256 channels per pair: CTA rank r stages ITS 128 channels of A and ITS half of the BN columns
+// of G, so one 64-row step moves 32 KB per SM instead of 48 KB (the cta_group::1 kernel is bound by L2 -> SM
+// bandwidth: 387 MB per dilated wgrad launch).  The leader's barrier counts both CTAs' TMA bytes; the column sums
+// read the local G half after the MMAs of the stage have completed (mma_done), then release the stage.
+// Requires every segment width to be a multiple of 256 (pair tiles never straddle a segment).
+template <int BN> struct TcWgradPairCfg {
+  static constexpr int BKT = 64;
+  static constexpr int A_BYTES = 2 * 64 * BKT * 2;               // two 64-channel atoms: 16 KB
+  static constexpr int G_ATOMS = BN / 2 / 64;                    // 64-column atoms of this CTA's half
+  static constexpr int G_BYTES = G_ATOMS * 64 * BKT * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + G_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + 1024;   // align slack, barriers, column-sum scratch
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                     const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmG, const TcWgradParams p) {
+  using Cfg = TcWgradPairCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int HALF = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* mma_done = empty_bar + STAGES;
+  uint64_t* tfull_bar = mma_done + STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(tfull_bar + 1);
+  float* cs_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 1024);      // [2][HALF] column-sum hand-over between row halves
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+#ifdef TC_TIMELINE
+  long long te0 = 0, te1 = 0;
+#endif
+  // segment / channel offset of this pair's m tile
+  int mp = (int)blockIdx.x >> 1, s = 0, koff = 0;
+  while (true) {
+    const int nt = p.segK[s] >> 8;
+    if (mp < nt) break;
+    mp -= nt; koff += p.segK[s]; ++s;
+  }
+  const int k0 = (mp << 8) + (int)crank * 128;
+  const int n0 = blockIdx.y * BN;
+  const int gcol0 = n0 + (int)crank * HALF;
+  const int c_begin = blockIdx.z * p.chunks_per_split;
+  const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
+  const int nchunks = c_end - c_begin;
+  const bool do_cs = p.cs_partial != nullptr;
+  // the pairs of this (n tile, split) share the G tile: each takes a slice of its 64 time rows for the column sums
+  const int npairs = (int)gridDim.x >> 1, pidx = (int)blockIdx.x >> 1;
+  const int cs_r0 = (Cfg::BKT * pidx) / npairs, cs_r1 = (Cfg::BKT * (pidx + 1)) / npairs;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], do_cs ? 4 : 1); mbar_init(&mma_done[i], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
+      tma_prefetch_desc(tm);
+      tma_prefetch_desc(&tmG);
+      const int shift = p.segShift[s];
+      int stage = 0; uint32_t phase = 0;
+#ifdef TC_TIMELINE
+      long long tw = 0, tt0 = clock64();
+#endif
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        const int b = ch / p.chunks_t, t0 = (ch % p.chunks_t) * Cfg::BKT;
+#ifdef TC_TIMELINE
+        const long long ta = clock64();
+#endif
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+#ifdef TC_TIMELINE
+        tw += clock64() - ta;
+#endif
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+        // one op per operand: boxes of 2 (A) and G_ATOMS (G) 64-channel atoms (tc_atom_map)
+        tma_load_4d_pair_h(sa, tm, &full_bar[stage], 0, t0 + shift, k0 >> 6, b, p.pol_a);
+        tma_load_4d_pair_h(sa + Cfg::A_BYTES, &tmG, &full_bar[stage], 0, t0, gcol0 >> 6, b, p.pol_g);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+#ifdef TC_TIMELINE
+      if (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0) printf("WG producer blk %d: chunks %d total %lld wait_empty %lld\n", blockIdx.x, nchunks, clock64() - tt0, tw);
+#endif
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 1, 1);   // both operands MN-major
+      int stage = 0; uint32_t phase = 0;
+#ifdef TC_TIMELINE
+      long long tw = 0, tt0 = clock64(), tfirst = 0;
+#endif
+      for (int it = 0; it < nchunks; ++it) {
+#ifdef TC_TIMELINE
+        const long long ta = clock64();
+#endif
+        mbar_wait(&full_bar[stage], phase);
+#ifdef TC_TIMELINE
+        if (it == 0) tfirst = clock64() - ta; else tw += clock64() - ta;
+#endif
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
+          const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < Cfg::BKT / 16; ++k)
+            umma_bf16_pair(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+          // with column sums the stage is released by the summing warps, which first wait for these MMAs
+          umma_commit_pair(do_cs ? &mma_done[stage] : &empty_bar[stage]);
+          if (it == nchunks - 1) umma_commit_pair(tfull_bar);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+#ifdef TC_TIMELINE
+      if (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) printf("WG mma blk %d: chunks %d total %lld first_wait %lld wait_full(rest) %lld\n", blockIdx.x, nchunks, clock64() - tt0, tfirst, tw);
+#endif
+    }
+  } else if (warp >= 4) {
+    if (do_cs) {
+      // 128 threads: column pair (tid & 63 .. of HALF/2 pairs) x row half (tid >> 6) of this pair's row slice
+      const int tid = threadIdx.x - 128;
+      constexpr int NPAIR = HALF / 2;
+      const int pr = tid % NPAIR, rh = tid / NPAIR;          // rh in [0, 128 / NPAIR)
+      constexpr int RH = 128 / NPAIR;
+      const int c = 2 * pr;
+      const int atom = c >> 6, cc = c & 63;
+      const uint32_t col_off = (uint32_t)(atom * 8192 + (cc & 7) * 2);
+      const uint32_t chunk = (uint32_t)(cc >> 3);
+      const int len = cs_r1 - cs_r0;
+      const int r_lo = cs_r0 + (len * rh) / RH, r_hi = cs_r0 + (len * (rh + 1)) / RH;
+      float s0 = 0.f, s1 = 0.f;
+      int stage = 0; uint32_t phase = 0;
+      int cur_b = c_begin / p.chunks_t;
+      const int b_first = cur_b;
+      auto flush = [&](int slot) {
+        // combine the row halves in a fixed order, write this CTA's columns and zero the peer's half
+        cs_s[rh * HALF + c] = s0; cs_s[rh * HALF + c + 1] = s1;
+        named_bar_sync(7, 128);
+        if (rh == 0) {
+          float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+          for (int h2 = 0; h2 < RH; ++h2) { t0 += cs_s[h2 * HALF + c]; t1 += cs_s[h2 * HALF + c + 1]; }
+          float* o = p.cs_partial + (((long long)blockIdx.z * gridDim.x + blockIdx.x) * p.slots + slot) * p.N;
+          const int mine = gcol0 + c, other = n0 + (1 - (int)crank) * HALF + c;
+          if (mine < p.N) o[mine] = t0;
+          if (mine + 1 < p.N) o[mine + 1] = t1;
+          if (other < p.N) o[other] = 0.f;
+          if (other + 1 < p.N) o[other + 1] = 0.f;
+        }
+        named_bar_sync(7, 128);
+      };
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        const int b = ch / p.chunks_t;
+        if (b != cur_b) { flush(cur_b - b_first); s0 = s1 = 0.f; cur_b = b; }
+        mbar_wait(&mma_done[stage], phase);
+        const uint8_t* g = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES + col_off;
+#pragma unroll 8
+        for (int r = r_lo; r < r_hi; ++r) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(g + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4));
+          s0 += __uint_as_float(w << 16);
+          s1 += __uint_as_float(w & 0xffff0000u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (nchunks > 0) flush(cur_b - b_first);
+    }
+    const int quarter = warp & 3;
+    const int k = k0 + quarter * 32 + lane;        // channel index inside the segment
+    float* out = p.partial + ((long long)blockIdx.z * p.ktot + koff + k) * p.N;
+    const bool valid = k < p.segK[s];
+#ifdef TC_TIMELINE
+    te0 = clock64();
+#endif
+    if (nchunks > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+#ifdef TC_TIMELINE
+    te1 = clock64();
+#endif
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c = 0; c < BN; c += 16) {
+      const int n = n0 + c;
+      if (n >= p.N) break;
+      float v[16];
+      if (nchunks > 0) tmem_ld16(taddr + (uint32_t)c, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      if (valid) {
+        const int nv = min(16, p.N - n);
+        if (nv == 16 && ((p.N & 3) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + n)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (i < nv) out[n + i] = v[i];
+        }
+      }
+    }
+  }
+#ifdef TC_TIMELINE
+  if (warp == 4 && lane == 0 && blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0) printf("WG epi blk %d: wait_tfull(after cs) %lld store %lld\n", blockIdx.x, te1 - te0, clock64() - te1);
+#endif
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, TcWgradPlan* plan) {
+  using Cfg = TcWgradPairCfg<BN>;
+  const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
+  int mpairs = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    ma[s] = tc_atom_map(tc, d.seg[s].A, d.seg[s].lda, d.seg[s].K, d.T, d.B, 64, 2);
+    if (!ma[s]) return -10;
+    mpairs += d.seg[s].K / 256;
+  }
+  for (int s = d.nseg; s < TC_MAX_SEG; ++s) ma[s] = ma[0];
+  const CUtensorMap* mg = tc_atom_map(tc, d.G, d.ldg, d.N, d.T, d.B, 64, Cfg::G_ATOMS);
+  if (!mg) return -11;
+  TcWgradParams p{};
+  p.B = d.B; p.T = d.T; p.N = d.N; p.chunks_t = (d.T + 63) / 64; p.total_chunks = d.B * p.chunks_t; p.ktot = d.ktot; p.nseg = d.nseg;
+  for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
+  p.partial = d.partial;
+  p.pol_a = tc_policy(d.l2_a); p.pol_g = tc_policy(d.l2_g);
+  const int ntiles = (d.N + BN - 1) / BN;
+  int nsplit = (tc_num_sms() / 2) / (mpairs * ntiles);     // one wave of CTA pairs
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > WN_MAX_WGRAD_SPLITS) nsplit = WN_MAX_WGRAD_SPLITS;
+  if (nsplit > p.total_chunks) nsplit = p.total_chunks;
+  p.chunks_per_split = (p.total_chunks + nsplit - 1) / nsplit;
+  nsplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  p.slots = (p.chunks_per_split + p.chunks_t - 2) / p.chunks_t + 1;
+  p.cs_partial = d.cs_partial;
+  plan->nsplit = nsplit; plan->chunks_per_split = p.chunks_per_split; plan->chunks_t = p.chunks_t; plan->slots = p.slots; plan->mtiles = 2 * mpairs;
+  auto kern = tc_wgrad_pair_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * mpairs, ntiles, nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 2);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mg, p);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "wgrad launch (cta pairs): %s", cudaGetErrorString(e)); return -13; }
+  return 0;
+}
+
 // CTAs of one wave for cluster size CL (clusters must fit inside a GPC, so fewer than #SMs may be usable)
 template <int BN, int CL>
 static int tc_wgrad_wave_ctas() {
@@ -1113,6 +1398,12 @@ static int tc_wgrad_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
 
 static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, TcWgradPlan* plan) {
   if (d.nseg < 1 || d.nseg > TC_MAX_SEG) return -1;
+  // CTA pairs when the pair's 256-channel tiles fit the segments exactly (WN_TC_WGRAD_PAIR=0: A/B switch)
+  static int pair_on = -1;
+  if (pair_on < 0) { const char* e = getenv("WN_TC_WGRAD_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
+  bool pair_ok = pair_on && d.N > 64 && d.N % 64 == 0;
+  for (int s = 0; s < d.nseg; ++s) pair_ok = pair_ok && d.seg[s].K % 256 == 0;
+  if (pair_ok) return d.N > 128 ? tc_wgrad_pair_launch<256>(tc, st, d, plan) : tc_wgrad_pair_launch<128>(tc, st, d, plan);
   if (d.N > 128) return tc_wgrad_launch<256>(tc, st, d, plan);
   if (d.N > 64) return tc_wgrad_launch<128>(tc, st, d, plan);
   return tc_wgrad_launch<64>(tc, st, d, plan);
