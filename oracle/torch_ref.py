@@ -8,7 +8,7 @@ Second, independently written restatement of /root/reference/src/layers.py:178-2
   * bench.py: the `cpu_baseline` / `--impl reference` arm ("CPU restatement of the
     reference path; TensorFlow is not installable here"), multi-threaded.
 
-PARITY UNPINNED (see wavenet_oracle.py header).  Never imported by wavenets_b200/.
+Parity pin: see the wavenet_oracle.py header (golden vectors from the reference's own source over oracle/tf_shim).  Never imported by wavenets_b200/.
 """
 from __future__ import annotations
 

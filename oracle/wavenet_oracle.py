@@ -13,12 +13,15 @@ of the reference hot path:
 with a hand-derived backward pass.  Only tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline leg may import it; the product (wavenets_b200/) never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or recorded outputs, and
-its arithmetic lives in TensorFlow 2 / Keras 3 (un-vendored, unpinned; not installable
-here).  The Keras/TF semantics below are restated from their published definitions
-(SURVEY.md section 8c lists them) and cross-checked three ways in tests/: this manual
-backward vs torch.autograd on an independent torch restatement (oracle/torch_ref.py)
-vs central finite differences; plus hand-derived known-answer tests.
+PARITY PIN: the reference ships no tests, golden vectors or recorded outputs, and its arithmetic
+lives in TensorFlow 2 / Keras 3 (un-vendored, unpinned; not installable here).  This restatement is
+therefore pinned against tests/golden/*.npz, produced by oracle/make_golden.py from the reference's
+OWN source files (src/layers.py, src/model.py, imported unmodified) executed over oracle/tf_shim — a
+restatement of only the TF/Keras primitives they call (tests/test_golden_cpu.py).  What stays
+restated rather than executed from upstream are those primitives (SURVEY.md section 8c lists them);
+they are additionally cross-checked three ways in tests/: this manual backward vs torch.autograd on
+an independent torch restatement (oracle/torch_ref.py) vs central finite differences, plus
+hand-derived known-answer tests.
 """
 from __future__ import annotations
 

@@ -304,6 +304,12 @@ __global__ void dropout_bwd(const T* __restrict__ draw, const uint8_t* __restric
   out[row * ld_out + c] = from_f<T>(v);
 }
 
+// dst[i][i] = 1 for i < n (row stride ld): identity block of the residual-in-the-GEMM operand
+__global__ void set_identity_bf16(bf16* __restrict__ dst, int ld, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[(long long)i * ld + i] = __float2bfloat16_rn(1.0f);
+}
+
 // ------------------------------------------------------------------ weight packing
 // dst[r][c] (ld = dst_ld, pre-zeroed) from Keras-layout src (rows x cols, row-major):
 //   mode 0: dst[r][c]  = src[r][c]
@@ -331,6 +337,52 @@ __global__ void pack_weight(const float* __restrict__ src, int rows, int cols, T
     const float v = src[i];
     if (mode == 0) dst[(long long)r * dst_ld + c] = from_f<TO>(v);
     else dst[(long long)c * dst_ld + r] = from_f<TO>(v);
+  }
+}
+
+// all weight re-packs of a handle in ONE launch (after every optimizer step): a table of jobs, each job = one former
+// pack_weight / tc_pack_gate_T / set_identity launch; a block finds its job by binary search over first-block indices
+struct PackJob {
+  const float* src; void* dst;
+  int rows, cols, dst_ld, mode, tile, D, dst_cols;   // modes 0,1,2 as pack_weight; 3 = gate transposed+interleaved; 4 = identity
+  long long first, total;                              // first block index, number of elements
+};
+template <class TO>
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackJob* __restrict__ jobs, int n) {
+  const long long gb = blockIdx.x;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first <= gb) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const long long i = (gb - j.first) * 256 + threadIdx.x;
+  if (i >= j.total) return;
+  TO* dst = (TO*)j.dst;
+  if (j.mode == 2) {
+    const int r = (int)(i / j.dst_cols), np = (int)(i % j.dst_cols);
+    const int half = j.tile >> 1;
+    const int ti = np / j.tile, jj = np % j.tile;
+    const int ch = ti * half + (jj % half);
+    float v = 0.f;
+    if (ch < j.D) v = j.src[(long long)r * j.cols + (jj < half ? ch : j.D + ch)];
+    dst[(long long)r * j.dst_ld + np] = from_f<TO>(v);
+  } else if (j.mode == 3) {
+    // rows = ktot, cols = cout, dst_cols = n16: dst[np][k] = src[k][col(np)]
+    const int np = (int)(i / j.rows), k = (int)(i % j.rows);
+    const int half = j.tile >> 1;
+    const int ti = np / j.tile, jj = np % j.tile;
+    const int ch = ti * half + (jj % half);
+    float v = 0.f;
+    if (ch < j.D) v = j.src[(long long)k * j.cols + (jj < half ? ch : j.D + ch)];
+    dst[(long long)np * j.dst_ld + k] = from_f<TO>(v);
+  } else if (j.mode == 4) {
+    dst[i * j.dst_ld + i] = from_f<TO>(1.0f);
+  } else {
+    const int r = (int)(i / j.cols), c = (int)(i % j.cols);
+    const float v = j.src[i];
+    if (j.mode == 0) dst[(long long)r * j.dst_ld + c] = from_f<TO>(v);
+    else dst[(long long)c * j.dst_ld + r] = from_f<TO>(v);
   }
 }
 

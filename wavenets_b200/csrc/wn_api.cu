@@ -86,6 +86,10 @@ struct BlockP {
   // dg GEMM weights [Wr^T ; Ws^T] : fp32 [(R+S)][Dpad] ; bf16 [Dpad16][(R+S)]
   float* Wdg = nullptr; int Dpad = 0;
   bf16* Wdg16 = nullptr;
+  // bf16 tier: conv1 with the residual folded into the contraction, B operand [R16][D + R] = [Wr^T | I]:
+  // x_out = [g | x] . [Wr ; I] + b  (the x . I products are exact in the fp32 accumulator).  Takes the residual
+  // read out of the epilogue, whose TMA input ring was the long pole of this kernel (3 k cycles per tile).
+  bf16* Wres16 = nullptr;
 };
 
 struct Arena {
@@ -197,6 +201,10 @@ struct wn_handle {
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> ev_blk_in, ev_blk_dz, ev_blk_done;
   int use_side = 1;
+  int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
+  // every weight re-pack as one launch: job table recorded on the first wn_params_changed (buffers never move)
+  std::vector<PackJob> pack_jobs;
+  PackJob* d_pack_jobs = nullptr; long long pack_blocks = 0; bool pack_ready = false;
 };
 
 enum { CLS_DILATED = 1, CLS_GEMM = 2, CLS_LOSS = 3, CLS_MISC = 4 };
@@ -315,6 +323,7 @@ static void layout_buffers(wn_handle* h) {
       tc_pick_tile(h->D, false, &n16, &tn);
       b.Dpad = n16;
       b.Wdg16 = (bf16*)P.take((size_t)n16 * rup(rs, 64) * 2);
+      if (h->cfg.use_residual) b.Wres16 = (bf16*)P.take((size_t)b.conv1.N16 * (h->D + h->R) * 2);
     }
   }
   for (auto& c : h->head) lay_conv(c);
@@ -430,6 +439,7 @@ static void layout_buffers(wn_handle* h) {
 extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   if (!cfg || !out) { set_err("null argument"); return WN_ERR_VALUE; }
   *out = nullptr;
+  const char* env_res = getenv("WN_TC_RES_GEMM");
   RET(validate_config(*cfg));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -565,6 +575,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming);
   { const char* e = getenv("WN_CUDA_GRAPH"); if (e && e[0] == '0') h->use_graphs = 0; }
   { const char* e = getenv("WN_SIDE_STREAM"); if (e && e[0] == '0') h->use_side = 0; }
+  if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   for (int i = 0; i < h->L; ++i) {
     cudaEvent_t a, b2, c2;
@@ -604,6 +615,7 @@ extern "C" void wn_destroy(wn_handle* h) {
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
+  cudaFree(h->d_pack_jobs);
   cudaFree(h->opt_m); cudaFree(h->opt_v); cudaFree(h->opt_chunks); cudaFree(h->opt_var_first);
   cudaFree(h->opt_partial); cudaFree(h->opt_scale); cudaFree(h->opt_norms);
   cudaFree(h->d_params); cudaFree(h->d_grads); cudaFree(h->pack.base); cudaFree(h->ws.base);
@@ -659,13 +671,17 @@ __global__ void bias_table_sum(const float* __restrict__ params, const int* __re
   out[i] = s;
 }
 
+static void pack_emit(wn_handle* h, const float* src, int rows, int cols, void* dst, int dst_ld, int mode, int tile, int D, int dst_cols, long long total) {
+  if (total <= 0) return;
+  PackJob j{src, dst, rows, cols, dst_ld, mode, tile, D, dst_cols, h->pack_blocks, total};
+  h->pack_jobs.push_back(j);
+  h->pack_blocks += (total + 255) / 256;
+}
 template <class TO>
 static void pack_launch(wn_handle* h, cudaStream_t st, const float* src, int rows, int cols, TO* dst, int dst_ld, int mode, int tile, int D,
                         int dst_cols) {
-  const long long total = mode == 2 ? (long long)rows * dst_cols : (long long)rows * cols;
-  if (total <= 0) return;
-  pack_weight<TO><<<cdiv(total, 256), 256, 0, st>>>(src, rows, cols, dst, dst_ld, mode, tile, D, dst_cols);
-  h->launches++;
+  (void)st;
+  pack_emit(h, src, rows, cols, dst, dst_ld, mode, tile, D, dst_cols, mode == 2 ? (long long)rows * dst_cols : (long long)rows * cols);
 }
 
 extern "C" int wn_params_changed(wn_handle* h, void* stream) {
@@ -674,6 +690,16 @@ extern "C" int wn_params_changed(wn_handle* h, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool bf = h->cfg.precision == WN_BF16;
   const float* P = h->d_params;
+  auto run_jobs = [&]() -> int {
+    if (bf) pack_all_kernel<bf16><<<(unsigned)h->pack_blocks, 256, 0, st>>>(h->d_pack_jobs, (int)h->pack_jobs.size());
+    else pack_all_kernel<float><<<(unsigned)h->pack_blocks, 256, 0, st>>>(h->d_pack_jobs, (int)h->pack_jobs.size());
+    bias_table_sum<<<cdiv(h->Sp, 128), 128, 0, st>>>(P, h->d_bskip_offsets, h->L, h->Sp, h->bskip_sum);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    h->fwd_valid = false;
+    return WN_OK;
+  };
+  if (h->pack_ready) return run_jobs();
   auto W = [&](const ConvP& c) { return P + h->params[c.w_idx].offset; };
   auto pack_conv = [&](ConvP& c) {
     const int ktot = c.K * c.cin;
@@ -689,8 +715,7 @@ extern "C" int wn_params_changed(wn_handle* h, void* stream) {
       if (c.gate) {
         // transpose of the interleaved matrix: do it via a temporary-free two-step: pack mode 2 into
         // the dgrad scratch is not possible (sizes differ), so use the dedicated kernel
-        tc_pack_gate_T(st, W(c), ktot, c.cout, c.Wf16, c.Kf16, c.tileN16, c.cout / 2, c.N16);
-        h->launches++;
+        pack_emit(h, W(c), ktot, c.cout, c.Wf16, c.Kf16, 3, c.tileN16, c.cout / 2, c.N16, (long long)c.N16 * ktot);
       } else {
         pack_launch<bf16>(h, st, W(c), ktot, c.cout, c.Wf16, c.Kf16, 1, 0, 0, 0);
       }
@@ -716,14 +741,17 @@ extern "C" int wn_params_changed(wn_handle* h, void* stream) {
       if (b.has_skip) pack_launch<bf16>(h, st, W(b.conv_skip), h->D, h->S, b.Wdg16 + h->R, rup(rs, 64), 0, 0, 0, 0);
       // skip-sum B operand [Spad16][L*D]: row = skip channel, contraction over (l, d)
       pack_launch<bf16>(h, st, W(sk), h->D, h->Sp, h->Wskip16 + (size_t)l * h->D, h->L * h->D, 1, 0, 0, 0);
+      if (b.Wres16) {
+        pack_launch<bf16>(h, st, W(b.conv1), h->D, h->R, b.Wres16, h->D + h->R, 1, 0, 0, 0);
+        pack_emit(h, nullptr, 0, 0, b.Wres16 + h->D, h->D + h->R, 4, 0, 0, 0, h->R);
+      }
     }
   }
   for (auto& c : h->head) pack_conv(c);
-  bias_table_sum<<<cdiv(h->Sp, 128), 128, 0, st>>>(P, h->d_bskip_offsets, h->L, h->Sp, h->bskip_sum);
-  h->launches++;
-  CK(cudaGetLastError());
-  h->fwd_valid = false;
-  return WN_OK;
+  CK(cudaMalloc(&h->d_pack_jobs, h->pack_jobs.size() * sizeof(PackJob)));
+  CK(cudaMemcpy(h->d_pack_jobs, h->pack_jobs.data(), h->pack_jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  h->pack_ready = true;
+  return run_jobs();
 }
 
 // ============================================================================ GEMM dispatch
@@ -987,6 +1015,13 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
     typename EpiBiasActRes<T, T, sizeof(T) == 2>::Params ep{};
     ep.out = (T*)h->xout[l]; ep.ldo = h->R; ep.bias = P_(h, c.b_idx); ep.act = ACT_LINEAR;
     ep.res = h->cfg.use_residual ? (const T*)x_in : nullptr; ep.ldr = h->R; ep.N = h->R; ep.vec = vec_ok<T>(h->R);
+    if (sizeof(T) == 2 && b.Wres16 && h->use_res_gemm) {
+      // residual through the contraction: second segment x_in against the identity block of [Wr^T | I]
+      g.nseg = 2;
+      g.seg[1] = SegH{x_in, h->R, 0, h->R};
+      g.W16 = b.Wres16; g.ktot16 = h->D + h->R;
+      ep.res = nullptr;
+    }
     // g and x_in are next used a whole pass later; x_out is the next block's operand
     g.l2_a = TC_L2_FIRST; g.l2_in[0] = TC_L2_FIRST; g.l2_out[0] = TC_L2_LAST;
     RET((run_conv_gemm<T, EpiBiasActRes<T, T, sizeof(T) == 2>>(h, st, CLS_GEMM, g, ep)));
