@@ -271,9 +271,13 @@ def main():
   dil_ms, dil_launches = prof['dilated']
   achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
   roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
-              'frac': achieved / peaks['tensor'], 'traffic': None,
-              'kernel': 'tc_conv_gemm_kernel + tc_wgrad_kernel on the dilated convs (fwd + dgrad + wgrad)' if precision == 'bf16'
-              else 'conv_gemm_simt + wgrad_simt on the dilated convs',
+              'frac': achieved / peaks['tensor'],
+              # dram__bytes_read+write per launch, mean over the class's kernels, from one `ncu --set full` capture of the C2
+              # step (cold cache; profiles/ncu_full_r1d_c2_{fwd,bwd}.txt): gate 70.3 MB, dgrad 111.4 MB, dilated wgrad 110.5 MB,
+              # its finish 19.1 MB.  Only valid for the default workload.
+              'traffic': 7.78e7 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels) else None,
+              'kernel': 'tc_conv_gemm_staged_kernel<gate | dgrad, cta_group::2> + tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'
+              if precision == 'bf16' else 'conv_gemm_simt + wgrad_simt on the dilated convs',
               'launches_per_step': dil_launches, 'ms_per_step_in_kernel': dil_ms,
               'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
               'share_of_step': dil_ms / (ms_total / args.steps)}
@@ -296,6 +300,22 @@ def main():
     'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'whole_step': whole,
     'loss': {'first': loss0, 'last': loss_last, 'e2e_last': out['loss']},
   }
+  # ---- informational: one FULL training iteration as the reference runs it (model.py:309-348): the step above plus
+  # per-variable clipnorm, Adam on the fp32 master weights, weight re-pack and the sampled-waveform MSE metric
+  if world == 1:
+    from wavenets_b200.optimizers import Adam
+    from wavenets_b200.metrics import MeanSquaredError
+    model.compile(optimizer=Adam(learning_rate=5e-4, clipnorm=1.0), metrics=[MeanSquaredError()])
+    for _ in range(2):
+      model.train_step(data_dev)
+    sync_all()
+    t0 = time.perf_counter()
+    n_it = max(3, min(10, args.steps))
+    for _ in range(n_it):
+      logs = model.train_step(data_dev)
+    sync_all()
+    line['full_iteration'] = {'ms': (time.perf_counter() - t0) / n_it * 1e3, 'includes': 'fwd+loss+bwd, clipnorm, Adam, re-pack, sampled-waveform MSE',
+                              'loss': logs['loss'], 'mean_squared_error': logs.get('mean_squared_error')}
   if rank == 0:
     if world == 1 and not args.no_cpu_baseline:
       r = cpu_reference_run(cfg, kw, cond_in, steps=5, warmup=1, budget_s=25.0)
