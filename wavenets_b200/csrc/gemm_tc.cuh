@@ -344,13 +344,13 @@ template <int BN, int NIN, int NOUT, int IN_PANELS, int OUT_SLOTS_, int CG = 1> 
   static constexpr int IN_MAX = IN_PANELS > 0 ? IN_PANELS : 1, OUT_SLOTS = OUT_SLOTS_;
   static constexpr int STAGING = (IN_PANELS + OUT_SLOTS * NOUT) * PANEL;
   static constexpr int MAX_SMEM = 232448;
-  static constexpr int ST0 = (MAX_SMEM - 3072 - STAGING) / STAGE_BYTES;
+  static constexpr int ST0 = (MAX_SMEM - 4096 - STAGING) / STAGE_BYTES;
 #ifndef TC_STAGES_CAP
 #define TC_STAGES_CAP 6
 #endif
   static constexpr int STAGES = ST0 > TC_STAGES_CAP ? TC_STAGES_CAP : ST0;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 + 512 + 1024 /*bias table*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 + 512 + 2048 /*bias tables (double-buffered)*/;
   static_assert(STAGES >= 2, "not enough shared memory for the mainloop ring");
 };
 
@@ -621,9 +621,11 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
 #ifdef TC_TIMELINE
       const long long tl_b = clock64();
 #endif
+      // table double-buffered by tile parity: since the TMA-store warp took over, the epilogue warps only meet at this
+      // barrier (once per tile), so a warp running ahead must not overwrite entries the others still read
+      float* const bs = bias_s + as * 256;
       if (NBIAS > 0) {
-        // every reader of the previous tile's table is past that tile's last step barrier
-        if ((int)threadIdx.x - 128 < NBIAS) bias_s[threadIdx.x - 128] = bias_reg;
+        if ((int)threadIdx.x - 128 < NBIAS) bs[threadIdx.x - 128] = bias_reg;
         named_bar_sync(2, NEPI * 32);
       }
       TmemAccRow acc{tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16), true};
@@ -666,7 +668,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           if (++islot == in_slots) { islot = 0; iphase ^= 1; }
         }
         TL_MARK(0)
-        Epi::chunk(ep, acc, bsafe, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out, bias_s);
+        Epi::chunk(ep, acc, bsafe, step * 32 + q * 16, BN / 2, col0 + q * 16, sp.in_mask, in, out, bs);
         TL_MARK(1)
         uint8_t* ob = out_ring + oslot * NOUT * Cfg::PANEL;
         mbar_wait(&out_empty[oslot], ophase ^ 1);     // the TMA stores of this slot's previous use have read it

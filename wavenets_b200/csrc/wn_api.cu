@@ -23,6 +23,7 @@
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc_block.cuh"
 #include "kernels_misc.cuh"
 
 // ============================================================================ errors
@@ -202,6 +203,7 @@ struct wn_handle {
   std::vector<cudaEvent_t> ev_blk_in, ev_blk_dz, ev_blk_done;
   int use_side = 1;
   int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
+  int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
   // every weight re-pack as one launch: job table recorded on the first wn_params_changed (buffers never move)
   std::vector<PackJob> pack_jobs;
   PackJob* d_pack_jobs = nullptr; long long pack_blocks = 0; bool pack_ready = false;
@@ -576,6 +578,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_CUDA_GRAPH"); if (e && e[0] == '0') h->use_graphs = 0; }
   { const char* e = getenv("WN_SIDE_STREAM"); if (e && e[0] == '0') h->use_side = 0; }
   if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
+  { const char* e = getenv("WN_TC_FUSED_FWD"); if (e && e[0] == '0') h->use_fused_fwd = 0; }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   for (int i = 0; i < h->L; ++i) {
     cudaEvent_t a, b2, c2;
@@ -993,6 +996,28 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
       cur = h->acts[l][j];
       curw = h->D;
     } else {
+      if constexpr (sizeof(T) == 2) {
+        // bf16 tier: gated conv + gate + conv1 (+ residual) as ONE kernel when the shapes allow (gemm_tc_block.cuh)
+        if (h->use_fused_fwd && b.Wres16 && h->cfg.use_residual && tc_cta_group() == 2 && c.K <= TC_MAX_SEG) {
+          TcBlockDesc d{};
+          d.B = B; d.T = Tn; d.nseg = c.K; d.Cin = c.cin; d.D = h->D; d.R = h->R; d.has_res = 1;
+          for (int k = 0; k < c.K; ++k) d.shift[k] = -(c.K - 1 - k) * c.dil;
+          d.A = (const bf16*)cur; d.lda = curw; d.X = (const bf16*)x_in; d.ldx = h->R;
+          d.W1 = c.Wf16; d.k1 = c.Kf16; d.W2 = b.Wres16;
+          d.z = (bf16*)h->zbuf[l]; d.g = (bf16*)h->G_all + (size_t)l * rows_cap * h->D; d.xout = (bf16*)h->xout[l];
+          d.bias_g = P_(h, c.b_idx); d.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
+          d.bias_r = P_(h, b.conv1.b_idx);
+          int r;
+          {
+            struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "block_fwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
+            LaunchScope ls(h, st, CLS_DILATED);
+            r = c.tileN16 == 256 ? tc_block_fwd(h->tmaps, st, d) : -100;
+          }
+          if (r == 0) return WN_OK;
+          if (r != -100) { set_err("fused block forward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+          h->launches--;      // not launched: fall through to the separate kernels
+        }
+      }
       typename EpiGate<T, sizeof(T) == 2>::Params ep{};
       ep.z = (T*)h->zbuf[l];
       ep.g = (T*)h->G_all + (size_t)l * rows_cap * h->D;
