@@ -40,6 +40,12 @@ BF16_MODELS = {
                       final_layers_channels=[64], num_mixtures=4, sampling_function='gaussian'),
   'r256': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=4, skip_channels=256,
                final_layers_channels=[256], activation='leaky_relu'),
+  # shapes the fused block-forward kernel takes (gemm_tc_block.cuh): D = R in {128, 256}, residual on
+  'fused128_multidil_cond': dict(channels=128, blocks=2, layers_per_block=2, dilation_bound=8, skip_channels=128, activation='tanh',
+                                 final_layers_channels=[128], conditioning='global', mapping_layers=[8], mapping_activation='tanh'),
+  'fused256_k3_alias': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=9, kernel_size=3, final_layers_channels=[128]),
+  'unfused256_nores': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=4, skip_channels=128, use_residual=False,
+                           final_layers_channels=[128]),
 }
 
 
@@ -130,13 +136,17 @@ def test_bf16_causality_and_batch_isolation_exact():
     assert np.array_equal(y2[1], y0[1])
 
 
-def test_bf16_determinism():
-  kw = BF16_MODELS['single_dil_skip_cond']
-  m, cfg, p, x, cond = _build(kw, 3, 200)
-  m.train_step((x, cond))
+@pytest.mark.parametrize('name', ['single_dil_skip_cond', 'r256', 'fused128_multidil_cond'])
+def test_bf16_determinism(name):
+  """Bit-identical gradients run to run (no atomics anywhere; also through CUDA-graph replays, steps 3+)."""
+  kw = BF16_MODELS[name]
+  m, cfg, p, x, cond = _build(kw, 3, 700)
+  data = (x, cond) if cond is not None else x
+  m.train_step(data)
   g1 = m.handle.flat_grads.clone()
-  m.train_step((x, cond))
-  assert torch.equal(g1, m.handle.flat_grads)
+  for _ in range(3):
+    m.train_step(data)
+    assert torch.equal(g1, m.handle.flat_grads)
 
 
 def test_bf16_rejects_unaligned_widths():
