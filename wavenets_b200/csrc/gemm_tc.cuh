@@ -446,9 +446,17 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
                 tma_load_2d_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0, sp.pol_w);
               } else {
                 // the leader's barrier counts the bytes of both CTAs' operand halves
+#if defined(TC_EXP_NO_W)
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::A_BYTES);
+                tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
+#elif defined(TC_EXP_NO_A)
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
+                tma_load_2d_pair_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0 + (int)crank * (BN / 2), sp.pol_w);
+#else
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                 tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
                 tma_load_2d_pair_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0 + (int)crank * (BN / 2), sp.pol_w);
+#endif
               }
 #endif
               if (++stage == STAGES) { stage = 0; phase ^= 1; }

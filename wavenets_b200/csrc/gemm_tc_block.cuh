@@ -48,13 +48,15 @@ template <int D_, int R_> struct TcBlockCfg {
   static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
   static constexpr int B_BYTES = (BN / 2) * BK * 2;            // this CTA's half of a 256-wide weight tile: 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 4;
   static constexpr int G_BYTES = BM * D_ * 2;                  // 64 KB for D = 256
   static constexpr int PANEL = 128 * 64;                       // 128 rows x 32 bf16
-  static constexpr int OUT_SLOTS = 3, SLOT_PANELS = 2;
+  static constexpr int OUT_SLOTS = 2, SLOT_PANELS = 2;
   static constexpr int NT1 = 2 * D_ / BN;                      // GATE tiles per m tile
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + OUT_SLOTS * SLOT_PANELS * PANEL + 1024 /*align*/ + 512 /*barriers*/ + 2048 /*bias tables*/;
+  // the dynamic shared memory is declared __align__(1024) (128B-swizzled TMA tiles need it), so no alignment slack:
+  // 4 x 32 KB ring + 64 KB g + 32 KB staging + 2.5 KB = 231,936 B of the 232,448 B a CTA may have
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + OUT_SLOTS * SLOT_PANELS * PANEL + 512 /*barriers*/ + 2048 /*bias tables*/;
   static_assert(D_ % 128 == 0 && D_ <= 256 && R_ % 64 == 0 && R_ <= 256, "fused block kernel: D in {128,256}, R <= 256");
   static_assert(SMEM_BYTES <= 232448, "fused block kernel does not fit shared memory");
 };
@@ -67,8 +69,9 @@ tc_block_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cfg = TcBlockCfg<D_, R_>;
   constexpr int STAGES = Cfg::STAGES, NEPI = 8, NT1 = Cfg::NT1;
   constexpr int KB_G = D_ / 64, KB_X = R_ / 64;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_blk[];
+  uint8_t* smem = smem_blk;
+  if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("libwavenet_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
   uint8_t* gbuf = smem + STAGES * Cfg::STAGE_BYTES;                       // [D/64][128 rows][128 B], 128B swizzle
   uint8_t* out_ring = gbuf + Cfg::G_BYTES;
   uint64_t* full_bar = (uint64_t*)(out_ring + Cfg::OUT_SLOTS * Cfg::SLOT_PANELS * Cfg::PANEL);
