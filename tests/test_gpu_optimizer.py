@@ -85,3 +85,23 @@ def test_checkpoint_round_trip(tmp_path):
   m3.build((x[:, :-1].shape, cond.shape))
   with pytest.raises(ValueError):
     ck.load_weights(m3, path)
+
+
+def test_train_step_deferred_matches_train_step():
+  """Deferred logs (read one call later, pinned D2H + event) carry exactly the values of the synchronous call."""
+  from wavenets_b200 import WaveNet
+  from wavenets_b200.metrics import MeanSquaredError
+  kw = SMALL_MODELS['l2']
+  x, cond = make_inputs(2, 80, COND_IN)
+  m = WaveNet(**kw)
+  m.compile(metrics=[MeanSquaredError()])
+  m.build((x[:, :-1].shape, cond.shape))
+  ref = m.train_step((x, cond))
+  m.reset_metrics()
+  m._sample_calls -= 1                       # same Philox stream for the sampled-waveform metric
+  handles = [m.train_step_deferred((x, cond)) for _ in range(3)]
+  outs = [h.result() for h in handles]
+  assert outs[0]['loss'] == ref['loss'] and outs[0]['reg_loss'] == ref['reg_loss']
+  assert outs[0]['mean_squared_error'] == ref['mean_squared_error']
+  assert outs[1]['loss'] == ref['loss'] and outs[2]['loss'] == ref['loss']
+  assert handles[0].result() is outs[0]

@@ -23,6 +23,27 @@ from ._engine import Handle, as_dev
 from .layers import WaveNetLayer  # noqa: F401  (re-export, like `from src.layers import WaveNetLayer`)
 
 
+class _PendingLogs:
+  """Metrics of one deferred training step (see WaveNet.train_step_deferred)."""
+
+  def __init__(self, model, slot, event):
+    self._model, self._slot, self._event, self._out = model, slot, event, None
+
+  def result(self):
+    if self._out is None:
+      self._event.synchronize()
+      m = self._model
+      vals = m._pin_logs[self._slot].tolist()
+      out = {'loss': vals[0]}
+      if m.regularization:
+        out['reg_loss'] = vals[1]
+      for metric in m._metrics_from_compilation:
+        metric.update_state(vals[2])
+        out[metric.name] = metric.result()
+      self._out = out
+    return self._out
+
+
 class WaveNet:
   """WaveNet model class (same kwargs as the reference)."""
 
@@ -105,6 +126,7 @@ class WaveNet:
     self._staging = {}
     self._metrics_from_compilation = []
     self._sample_seed, self._sample_calls = 0x42, 0
+    self._pin_logs, self._pin_events, self._pending_slot = None, None, 0
     self._last_frames, self._last_rows = None, 0
     self.n_replicas = 1          # MirroredStrategy replica count (train.py:203); set by parallel.attach()
     self._process_group = None
@@ -175,6 +197,9 @@ class WaveNet:
       self._handle.glorot_init(seed=1, bias_std=0.0)   # Keras defaults: glorot-uniform, zero bias
     self.built = True
     self._built_for = (B, T)
+    if self._pin_logs is None:
+      self._pin_logs = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(4)]
+      self._pin_events = [torch.cuda.Event() for _ in range(4)]
     if self.optimizer is not None and hasattr(self.optimizer, 'build'):
       self.optimizer.build(self)      # model.py:211
 
@@ -357,6 +382,27 @@ class WaveNet:
   def train_step_async(self, data):
     """Same as train_step without the host read-back: returns a device tensor [loss, reg_loss]."""
     return self._step(data, True)
+
+  def train_step_deferred(self, data):
+    """train_step whose metrics are read one call later, the way Keras `fit` fetches its logs asynchronously:
+    enqueues the H2D copy of the inputs, the step, the optimizer (if compiled), the metrics and a D2H copy of the
+    loss floats into pinned memory, and returns a handle; `handle.result()` waits for THAT step only and returns
+    the same dict as `train_step`.  The host never idles the GPU between steps."""
+    loss = self._step(data, True)
+    if self.optimizer is not None:
+      self.optimizer.apply_gradients(self)
+    h = self.handle
+    if self._metrics_from_compilation:
+      self._sample_calls += 1
+      out_buf = self._stage_like('sample', (self._last_rows,))
+      _lib.check(h.lib.wn_sample_last_step(h.h, h.ptr(self._last_frames), 0, C.c_uint64(self._sample_seed + self._sample_calls),
+                                           h.ptr(out_buf), h.ptr(h._loss[2:]), h.stream_ptr()))
+    slot = self._pending_slot
+    self._pending_slot = (slot + 1) % len(self._pin_logs)
+    self._pin_logs[slot].copy_(h._loss, non_blocking=True)
+    ev = self._pin_events[slot]
+    ev.record(torch.cuda.current_stream(h.device))
+    return _PendingLogs(self, slot, ev)
 
   def test_step(self, data):
     out = self._metrics_dict(self._step(data, False))
