@@ -1435,11 +1435,9 @@ struct TcWgradFinish {
   float* bias0; float* bias1; float* per_batch; int ldpb;
   int wblocks;   // blocks of the weight part
 };
-__global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
-  pdl_launch_dependents();
-  pdl_wait();
-  if ((int)blockIdx.x < f.wblocks) {
-    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+__device__ __forceinline__ void tc_wgrad_finish_body(const TcWgradFinish& f, const int bid, float (*red)[33]) {
+  if (bid < f.wblocks) {
+    const long long j = (long long)bid * 256 + threadIdx.x;
     const long long n_all = (long long)f.ktot * f.N;
     if (j >= n_all) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -1464,9 +1462,8 @@ __global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
     return;
   }
   // ---- column sums: 32 columns x 8 batch lanes per block
-  __shared__ float red[8][33];
   const int nl = threadIdx.x & 31, bl = threadIdx.x >> 5;
-  const int n = ((int)blockIdx.x - f.wblocks) * 32 + nl;
+  const int n = (bid - f.wblocks) * 32 + nl;
   float tot = 0.f;
   if (n < f.N) {
     for (int b = bl; b < f.B; b += 8) {
@@ -1489,4 +1486,20 @@ __global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
     if (n < f.N0) { if (f.bias0) f.bias0[n] = t; }
     else if (f.bias1) f.bias1[n - f.N0] = t;
   }
+}
+
+__global__ void __launch_bounds__(256) tc_wgrad_finish(const TcWgradFinish f) {
+  __shared__ float red[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  tc_wgrad_finish_body(f, (int)blockIdx.x, red);
+}
+// the finishes of two weight-gradient launches (the [conv1|skip] and the dilated-conv wgrad of one block) in one launch:
+// blocks [0, n0) work on f0, the rest on f1
+__global__ void __launch_bounds__(256) tc_wgrad_finish2(const TcWgradFinish f0, const TcWgradFinish f1, const int n0) {
+  __shared__ float red[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  if ((int)blockIdx.x < n0) tc_wgrad_finish_body(f0, (int)blockIdx.x, red);
+  else tc_wgrad_finish_body(f1, (int)blockIdx.x - n0, red);
 }

@@ -204,7 +204,11 @@ struct wn_handle {
   int use_side = 1;
   int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
   int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
+  int use_merged_finish = 0;  // WN_TC_MERGED_FINISH=1: one finish launch for both wgrads of a block. Measured SLOWER on C2 (7.48 vs
+                              // 7.38 ms/step: the deferred partials fall out of L2 before the merged finish reads them) -> off
   // every weight re-pack as one launch: job table recorded on the first wn_params_changed (buffers never move)
+  // deferred wgrad finish (see WgradH::defer_finish)
+  TcWgradFinish pend_finish{}; bool pend_valid = false; int pend_blocks = 0; long long pend_partial_elems = 0, pend_cs_elems = 0;
   std::vector<PackJob> pack_jobs;
   PackJob* d_pack_jobs = nullptr; long long pack_blocks = 0; bool pack_ready = false;
 };
@@ -402,15 +406,16 @@ static void layout_buffers(wn_handle* h) {
   }
   for (auto& c : h->head) upd(c.cin, c.cout);
   h->wg_partial_elems = maxkn * WN_MAX_WGRAD_SPLITS;
-  h->wg_partial = (float*)W.take((size_t)h->wg_partial_elems * 4);
-  h->wg_partial_side = (float*)W.take((size_t)h->wg_partial_elems * 4);
+  // x2: a deferred finish keeps one problem's partials in place while the next wgrad writes behind them
+  h->wg_partial = (float*)W.take((size_t)h->wg_partial_elems * 4 * 2);
+  h->wg_partial_side = (float*)W.take((size_t)h->wg_partial_elems * 4 * 2);
   if (bf) {
     int max_mt = 1;
     auto mt = [&](int K, int cin) { const int m = K * cdiv(cin, 128); if (m > max_mt) max_mt = m; };
     for (auto& b : h->blocks) { for (auto& c : b.stack) mt(c.K, c.cin); mt(1, D); }
     for (auto& c : h->head) mt(1, c.cin);
-    h->cs_partial = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4);
-    h->cs_partial_side = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4);
+    h->cs_partial = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4 * 2);
+    h->cs_partial_side = (float*)W.take((size_t)tc_wgrad_cs_rows(h->maxB, h->maxT, max_mt) * (size_t)rup(nmax, 4) * 4 * 2);
   }
   h->loss_parts_cap = cdiv((long long)rows, 8) + 8;
   h->loss_partial = (float*)W.take((size_t)h->loss_parts_cap * 4);
@@ -579,6 +584,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_SIDE_STREAM"); if (e && e[0] == '0') h->use_side = 0; }
   if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
   { const char* e = getenv("WN_TC_FUSED_FWD"); if (e && e[0] == '0') h->use_fused_fwd = 0; }
+  { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   for (int i = 0; i < h->L; ++i) {
     cudaEvent_t a, b2, c2;
@@ -842,6 +848,9 @@ struct WgradH {
   int N0 = 0; float* dst1 = nullptr; const float* w1 = nullptr; float* bias1 = nullptr;
   bool side = false;   // issued on the side stream: uses the side copies of the partial buffers
   int l2_a = 0, l2_g = 0;   // bf16 tier: L2 policy codes of the two operands
+  // bf16 tier: `defer_finish` leaves the split partials in place (no finish launch); the next wgrad on the same stream
+  // with `merge_prev` writes its partials behind them and finishes both problems with ONE launch
+  bool defer_finish = false, merge_prev = false;
 };
 
 template <class T>
@@ -878,8 +887,15 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     d.B = g.B; d.T = g.T; d.N = g.N; d.G = (const bf16*)g.G; d.ldg = g.ldg; d.nseg = g.nseg; d.ktot = ktot;
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     d.l2_a = g.l2_a; d.l2_g = g.l2_g;
-    float* const wgp = g.side ? h->wg_partial_side : h->wg_partial;
-    float* const csp = g.side ? h->cs_partial_side : h->cs_partial;
+    if (h->pend_valid && !g.merge_prev) {
+      // a deferred finish that nobody merged (should not happen): run it on its own before its partials are reused
+      LaunchScope ls(h, st, cls);
+      tc_wgrad_finish<<<h->pend_blocks, 256, 0, st>>>(h->pend_finish);
+      h->pend_valid = false;
+    }
+    const bool merging = g.merge_prev && h->pend_valid;
+    float* const wgp = (g.side ? h->wg_partial_side : h->wg_partial) + (merging ? h->pend_partial_elems : 0);
+    float* const csp = (g.side ? h->cs_partial_side : h->cs_partial) + (merging ? h->pend_cs_elems : 0);
     d.partial = wgp;
     const bool want_cs = g.bias_dst || g.per_batch || g.bias1;
     d.cs_partial = want_cs ? csp : nullptr;
@@ -896,13 +912,29 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     f.cs = csp; f.slots = plan.slots; f.cps = plan.chunks_per_split; f.chunks_t = plan.chunks_t; f.B = g.B; f.mtiles = plan.mtiles;
     f.bias0 = g.bias_dst; f.bias1 = g.bias1; f.per_batch = g.per_batch; f.ldpb = g.ldpb;
     f.wblocks = cdiv((long long)ktot * g.N, 256);
+    const int nblocks = f.wblocks + (want_cs ? cdiv(g.N, 32) : 0);
+    const long long part_elems = (long long)plan.nsplit * ktot * g.N;
+    const long long cs_elems = (long long)plan.nsplit * plan.mtiles * plan.slots * g.N;
+    if (g.defer_finish && !merging) {
+      // keep the partials; the next wgrad of this stream finishes both
+      h->pend_finish = f; h->pend_valid = true; h->pend_blocks = nblocks;
+      h->pend_partial_elems = (part_elems + 63) / 64 * 64; h->pend_cs_elems = (cs_elems + 63) / 64 * 64;
+      return WN_OK;
+    }
     LaunchScope ls(h, st, cls);
     {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(f.wblocks + (want_cs ? cdiv(g.N, 32) : 0)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
       cudaLaunchAttribute attr[2];
       cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 1);
-      CK(cudaLaunchKernelEx(&cfg, tc_wgrad_finish, f));
+      if (merging) {
+        cfg.gridDim = dim3(h->pend_blocks + nblocks);
+        h->pend_valid = false;
+        CK(cudaLaunchKernelEx(&cfg, tc_wgrad_finish2, h->pend_finish, f, h->pend_blocks));
+      } else {
+        cfg.gridDim = dim3(nblocks);
+        CK(cudaLaunchKernelEx(&cfg, tc_wgrad_finish, f));
+      }
     }
     return WN_OK;
   }
@@ -1223,6 +1255,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     w.N0 = R; w.dst1 = G_(h, b.conv_skip.w_idx); w.w1 = P_(h, b.conv_skip.w_idx); w.bias1 = G_(h, b.conv_skip.b_idx);
     w.side = side1;
     w.l2_a = TC_L2_FIRST;   // last use of g_l
+    w.defer_finish = side1 && h->use_merged_finish;   // finished together with the gated conv's wgrad below (same stream)
     RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
   } else if (d_o) {
     WgradH w{};
@@ -1294,6 +1327,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       const bool side2 = sd != nullptr && j == depth - 1;
       if (side2) CK(cudaStreamWaitEvent(sd->side, sd->ev_dz, 0));
       w.side = side2;
+      w.merge_prev = side2 && h->pend_valid;
       w.l2_a = TC_L2_FIRST;   // last use of this forward activation
       RET(run_wgrad<T>(h, side2 ? sd->side : st, CLS_DILATED, w));
     }
@@ -1332,6 +1366,12 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_DILATED, g, ep)));
       }
     }
+  }
+  if (h->pend_valid) {
+    // deferred finish that found no partner in this block: run it on the stream its wgrad used
+    LaunchScope ls(h, s1, CLS_GEMM);
+    tc_wgrad_finish<<<h->pend_blocks, 256, 0, s1>>>(h->pend_finish);
+    h->pend_valid = false;
   }
   if (sd) CK(cudaEventRecord(sd->ev_done, sd->side));
   return WN_OK;
