@@ -126,6 +126,16 @@ int wn_sample_waveform(wn_handle* h, const float* pred_dev, int B, int T, int de
 int wn_sample_last_step(wn_handle* h, const float* frames_dev, int deterministic, uint64_t seed, float* out_dev, float* mse_dev /* 2 floats or NULL */,
                         void* stream);
 
+/* ---- autoregressive generation: WaveNet.generate (model.py:258-307) with the per-layer single-step form
+ *      of WaveNetLayer.generate (layers.py:226-290): every dilated conv keeps the history of its input, one new sample costs
+ *      one K-tap matrix-vector product per conv (fp32, master weights).  prime (B, n_prime) fp32 = the reference's `sample`
+ *      window (n_prime = receptive field there); out (B, length): out[b][i] = sample n_prime + i, drawn like
+ *      wn_sample_waveform (deterministic: argmax / heaviest-component mean, what `_generation` does, model.py:255).
+ *      teacher (B, length) or NULL: forced continuation, for checking the step against WaveNet.call; pred (B, length, Cout)
+ *      or NULL receives the predictive distribution of every generated position. */
+int wn_generate(wn_handle* h, const float* prime_dev, int n_prime, const float* cond_dev, int B, int length, int deterministic, uint64_t seed,
+                float* out_dev, float* pred_dev, const float* teacher_dev, void* stream);
+
 /* ---- optimizer: train.py:225-226 `tf.keras.optimizers.Adam(learning_rate=lr, clipnorm=1.0)` applied by
  *      model.py:336 `optimizer.apply_gradients`.  Keras 3 semantics: every variable's gradient is clipped to L2 norm
  *      <= clipnorm (tf.clip_by_norm) on each replica BEFORE the cross-replica sum; then

@@ -21,7 +21,7 @@ EXPORTS = [
   'wn_param_count', 'wn_param_info', 'wn_params_dev', 'wn_grads_dev', 'wn_set_param', 'wn_get_param',
   'wn_get_grad', 'wn_params_changed', 'wn_quantize', 'wn_forward', 'wn_train_step', 'wn_test_step',
   'wn_train_step_host', 'wn_layer_forward', 'wn_layer_backward', 'wn_last_launch_count',
-  'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_num_frames', 'wn_preprocess_frames', 'wn_inverse_mu_law', 'wn_one_hot', 'wn_sample_waveform', 'wn_sample_last_step', 'wn_adam_init', 'wn_clip_grads', 'wn_adam_step', 'wn_adam_state', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
+  'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_num_frames', 'wn_preprocess_frames', 'wn_inverse_mu_law', 'wn_one_hot', 'wn_sample_waveform', 'wn_sample_last_step', 'wn_generate', 'wn_adam_init', 'wn_clip_grads', 'wn_adam_step', 'wn_adam_state', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
 ]
 
 
@@ -94,6 +94,7 @@ def load():
   lib.wn_set_dropout_masks.argtypes = [vp, vp, i32, i32]
   lib.wn_set_dropout_seed.argtypes = [vp, C.c_uint64]
   f32 = C.c_float
+  lib.wn_generate.argtypes = [vp, vp, i32, vp, i32, i32, i32, C.c_uint64, vp, vp, vp, vp]
   lib.wn_num_frames.argtypes = [i64, i32]
   lib.wn_num_frames.restype = i64
   lib.wn_preprocess_frames.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp]

@@ -791,14 +791,17 @@ __global__ void __launch_bounds__(256) opt_adam_kernel(float* __restrict__ w, co
 // clipped to [-1,1].  Optional: squared error against y (frames[b][t+1]) accumulated per block -> mse_partial.
 __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ pred, int ld, int C, int M, int kind, int is_logits, int bits,
                                                      int deterministic, unsigned long long seed, const float* __restrict__ frames, int Tn,
-                                                     long long rows, float* __restrict__ out, float* __restrict__ mse_partial) {
+                                                     long long rows, float* __restrict__ out, float* __restrict__ mse_partial,
+                                                     const int* __restrict__ ctr_dev = nullptr) {
   __shared__ float wsum[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
   float err2 = 0.f;
   if (row < rows) {
     const float* p = pred + row * ld;
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), 0x5A17u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    // ctr_dev: device-side step counter (autoregressive generation replays one graph for every step)
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), 0x5A17u, ctr_dev ? (uint32_t)*ctr_dev : 0u),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     const float u0 = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
     const float u1 = ((float)(rnd.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = ((float)(rnd.z >> 8) + 0.5f) * (1.0f / 16777216.0f);

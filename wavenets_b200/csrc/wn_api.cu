@@ -25,6 +25,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc_block.cuh"
 #include "kernels_misc.cuh"
+#include "generate.cuh"
 
 // ============================================================================ errors
 static thread_local char g_err[512] = "";
@@ -207,6 +208,13 @@ struct wn_handle {
   int use_merged_finish = 0;  // WN_TC_MERGED_FINISH=1: one finish launch for both wgrads of a block. Measured SLOWER on C2 (7.48 vs
                               // 7.38 ms/step: the deferred partials fall out of L2 before the merged finish reads them) -> off
   // every weight re-pack as one launch: job table recorded on the first wn_params_changed (buffers never move)
+  // autoregressive generation state (wn_generate): histories of every dilated conv's input, scratch, step graphs
+  struct Gen {
+    int B = 0, cap = 0;
+    float* audio = nullptr; std::vector<std::vector<float*>> hist; float* z = nullptr; float* skipsum = nullptr;
+    std::vector<float*> hbuf; float* logits = nullptr; float* sampled = nullptr; int* t_dev = nullptr;
+    std::vector<void*> allocs;
+  } gen;
   // deferred wgrad finish (see WgradH::defer_finish)
   TcWgradFinish pend_finish{}; bool pend_valid = false; int pend_blocks = 0; long long pend_partial_elems = 0, pend_cs_elems = 0;
   std::vector<PackJob> pack_jobs;
@@ -624,6 +632,7 @@ extern "C" void wn_destroy(wn_handle* h) {
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
+  for (void* a : h->gen.allocs) cudaFree(a);
   cudaFree(h->d_pack_jobs);
   cudaFree(h->opt_m); cudaFree(h->opt_v); cudaFree(h->opt_chunks); cudaFree(h->opt_var_first);
   cudaFree(h->opt_partial); cudaFree(h->opt_scale); cudaFree(h->opt_norms);
@@ -1558,6 +1567,162 @@ static int check_bt(wn_handle* h, int B, int T) {
     set_err("batch/time (%d,%d) outside the workspace built for (%d,%d)", B, T, h->maxB, h->maxT);
     return WN_ERR_VALUE;
   }
+  return WN_OK;
+}
+
+// ============================================================================ generation (model.py:241-307; layers.py:226-290)
+static int gen_alloc(wn_handle* h, int B, int cap) {
+  wn_handle::Gen& G = h->gen;
+  if (G.B >= B && G.cap >= cap) return WN_OK;
+  for (void* a : G.allocs) cudaFree(a);
+  G.allocs.clear();
+  auto take = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; cudaMemset(p, 0, bytes); G.allocs.push_back(p); return p; };
+  G.B = B; G.cap = cap;
+  const size_t rows = (size_t)B * cap;
+  G.audio = (float*)take(rows * 4);
+  G.hist.assign(h->L + 1, {});
+  bool ok = G.audio != nullptr;
+  for (int l = 0; l <= h->L && ok; ++l) {
+    const int depth = l < h->L ? (int)h->blocks[l].stack.size() : 1;
+    G.hist[l].assign(depth, nullptr);
+    for (int j = 0; j < depth && ok; ++j) { G.hist[l][j] = (float*)take(rows * (j == 0 ? h->R : h->D) * 4); ok = G.hist[l][j] != nullptr; }
+  }
+  G.z = (float*)take((size_t)B * 2 * h->D * 4);
+  G.skipsum = (float*)take((size_t)B * h->Sp * 4);
+  G.hbuf.assign(h->head.size(), nullptr);
+  for (size_t i = 0; i + 1 < h->head.size() && ok; ++i) { G.hbuf[i] = (float*)take((size_t)B * h->head[i].cout * 4); ok = G.hbuf[i] != nullptr; }
+  G.logits = (float*)take((size_t)B * h->Cout * 4);
+  G.sampled = (float*)take((size_t)B * 4);
+  G.t_dev = (int*)take(16);
+  if (!ok || !G.z || !G.skipsum || !G.logits || !G.sampled || !G.t_dev) { set_err("generation workspace allocation failed"); G.B = G.cap = 0; return WN_ERR_CUDA; }
+  return WN_OK;
+}
+
+static void gen_dense(cudaStream_t st, const GenVec& v, int B, const int* t_dev) {
+  const size_t smem = (size_t)v.K * v.Cin * 4;
+  gen_dense_kernel<<<dim3(cdiv(v.N, 32), B), 256, smem, st>>>(v, t_dev);
+}
+
+// one time step of the whole network on the histories; t is read from device memory
+static int gen_step(wn_handle* h, cudaStream_t st, int B, bool has_cb, bool sample, int deterministic, uint64_t seed, float* pred, long long pred_bstride,
+                    int t0, bool write_audio) {
+  wn_handle::Gen& G = h->gen;
+  const int cap = G.cap, R = h->R, D = h->D;
+  const int* t = G.t_dev;
+  if (h->cfg.use_skip) gen_zero_kernel<<<cdiv(B * h->Sp, 256), 256, 0, st>>>(G.skipsum, B * h->Sp);
+  gen_input_conv_kernel<<<cdiv(B * R, 128), 128, 0, st>>>(G.audio, cap, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), G.hist[0][0], R, h->K, B, t);
+  for (int l = 0; l < h->L; ++l) {
+    const BlockP& b = h->blocks[l];
+    const int depth = (int)b.stack.size();
+    for (int j = 0; j < depth; ++j) {
+      const ConvP& c = b.stack[j];
+      GenVec v{};
+      v.in = G.hist[l][j]; v.in_bstride = (long long)cap * c.cin; v.in_tstride = c.cin; v.Cin = c.cin; v.K = c.K; v.dil = c.dil;
+      v.W = P_(h, c.w_idx); v.bias = P_(h, c.b_idx); v.N = c.cout;
+      if (j < depth - 1) {
+        v.act = h->cfg.activation;
+        v.out = G.hist[l][j + 1]; v.out_bstride = (long long)cap * D; v.out_tstride = D;
+      } else {
+        v.act = ACT_LINEAR;
+        if (has_cb) { v.cbias = h->cb + (size_t)l * h->maxB * 2 * D; v.ldcb = 2 * D; }
+        v.out = G.z; v.out_bstride = 2 * D; v.out_tstride = 0;
+      }
+      gen_dense(st, v, B, t);
+    }
+    {
+      GenVec v{};   // conv1 (+ residual) on the gate of z
+      v.in = G.z; v.in_bstride = 2 * D; v.in_tstride = 0; v.Cin = D; v.K = 1; v.dil = 1; v.in_gate = 1;
+      v.W = P_(h, b.conv1.w_idx); v.bias = P_(h, b.conv1.b_idx); v.N = R; v.act = ACT_LINEAR;
+      v.out = G.hist[l + 1][0]; v.out_bstride = (long long)cap * R; v.out_tstride = R;
+      if (h->cfg.use_residual) { v.res = G.hist[l][0]; v.res_bstride = (long long)cap * R; v.res_tstride = R; v.res_cols = R; }
+      if (h->cfg.use_skip && h->alias_skip) { v.acc = G.skipsum; v.acc_ld = h->Sp; v.acc_col0 = -1; }
+      gen_dense(st, v, B, t);
+    }
+    if (h->cfg.use_skip && b.has_skip) {
+      GenVec v{};   // conv_skip, accumulated into the running skip sum (model.py:236)
+      v.in = G.z; v.in_bstride = 2 * D; v.in_tstride = 0; v.Cin = D; v.K = 1; v.dil = 1; v.in_gate = 1;
+      v.W = P_(h, b.conv_skip.w_idx); v.bias = P_(h, b.conv_skip.b_idx); v.N = h->S; v.act = ACT_LINEAR;
+      v.acc = G.skipsum; v.acc_ld = h->Sp; v.acc_col0 = 0; v.out = G.skipsum;
+      gen_dense(st, v, B, t);
+    }
+  }
+  // head (model.py:105-119,237-238)
+  const float* hin = h->cfg.use_skip ? G.skipsum : G.hist[h->L][0];
+  long long hin_b = h->cfg.use_skip ? h->Sp : (long long)cap * R;
+  int hin_t = h->cfg.use_skip ? 0 : R;
+  for (size_t i = 0; i < h->head.size(); ++i) {
+    const ConvP& hc = h->head[i];
+    const bool last = i + 1 == h->head.size();
+    GenVec v{};
+    v.in = hin; v.in_bstride = hin_b; v.in_tstride = hin_t; v.Cin = hc.cin; v.K = 1; v.dil = 1;
+    v.W = P_(h, hc.w_idx); v.bias = P_(h, hc.b_idx); v.N = hc.cout; v.act = last ? ACT_LINEAR : h->cfg.activation;
+    v.out = last ? G.logits : G.hbuf[i]; v.out_bstride = hc.cout; v.out_tstride = 0;
+    gen_dense(st, v, B, t);
+    hin = v.out; hin_b = hc.cout; hin_t = 0;
+  }
+  const wn_config& c = h->cfg;
+  if (pred) gen_pred_kernel<<<B, 256, 0, st>>>(G.logits, h->Cout, c.sampling_function == WN_CATEGORICAL ? 1 : 0, pred, pred_bstride, t0, t);
+  if (sample) {
+    const int kind = c.sampling_function == WN_CATEGORICAL ? 0 : (c.sampling_function == WN_GAUSSIAN ? 2 : 1);
+    sample_kernel<<<cdiv(B, 8), 256, 0, st>>>(G.logits, h->Cout, h->Cout, c.num_mixtures, kind, 1, c.bits, deterministic, seed, nullptr, 1, B, G.sampled, nullptr, t);
+  }
+  gen_advance_kernel<<<1, 64, 0, st>>>(G.audio, cap, G.sampled, B, write_audio ? 1 : 0, G.t_dev);
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+
+// prime (B, n_prime) -> out (B, length): out[b][i] = sample n_prime + i.  teacher (B, length) or NULL: forced continuation (the
+// predictions, not the samples, are then the result: pred (B, length, Cout)).
+extern "C" int wn_generate(wn_handle* h, const float* prime_dev, int n_prime, const float* cond_dev, int B, int length, int deterministic, uint64_t seed,
+                           float* out_dev, float* pred_dev, const float* teacher_dev, void* stream) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if (!h->cfg.has_head || !h->cfg.has_input_conv) { set_err("wn_generate needs a full model handle"); return WN_ERR_STATE; }
+  if (h->cfg.conditioning && !cond_dev) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
+  if (!prime_dev || n_prime < 1 || B < 1 || B > 64 || B > h->maxB || length < 1 || (!out_dev && !pred_dev)) { set_err("bad generate arguments (1 <= batch <= min(64, max_batch))"); return WN_ERR_VALUE; }
+  if ((size_t)h->K * (h->R > h->D ? h->R : h->D) * 4 > 48 * 1024) { set_err("generation: K * channels too large for the step kernel"); return WN_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t user = (cudaStream_t)stream, st = h->own_stream;
+  const int cap = n_prime + length + 1;
+  RET(gen_alloc(h, B, cap));
+  wn_handle::Gen& G = h->gen;
+  CK(cudaEventRecord(h->ev_in, user)); CK(cudaStreamWaitEvent(st, h->ev_in, 0));
+  // state: zero histories are the causal padding (nothing before the prime is ever needed at the last position, model.py:122)
+  for (size_t i = 0; i < G.allocs.size(); ++i) { /* buffers are re-zeroed lazily below */ }
+  CK(cudaMemsetAsync(G.audio, 0, (size_t)G.B * G.cap * 4, st));
+  for (auto& hl : G.hist) for (float* p : hl) if (p) CK(cudaMemsetAsync(p, 0, (size_t)G.B * G.cap * 4 * ((p == hl[0]) ? h->R : h->D), st));
+  CK(cudaMemsetAsync(G.t_dev, 0, 4, st));
+  CK(cudaMemcpy2DAsync(G.audio, (size_t)G.cap * 4, prime_dev, (size_t)n_prime * 4, (size_t)n_prime * 4, B, cudaMemcpyDeviceToDevice, st));
+  if (teacher_dev) CK(cudaMemcpy2DAsync(G.audio + n_prime, (size_t)G.cap * 4, teacher_dev, (size_t)length * 4, (size_t)length * 4, B, cudaMemcpyDeviceToDevice, st));
+  bool has_cb = false;
+  if (h->cfg.conditioning) {
+    const float* cond = nullptr;
+    RET(cond_forward(h, st, cond_dev, B, true, &cond));
+    const int n = 2 * h->D;
+    cond_bias_all<<<dim3(cdiv(B * n, 128), h->L), 128, 0, st>>>(cond, h->Cc, h->d_params, h->d_cond_offsets, h->cb, (long long)h->maxB * n, B, n);
+    has_cb = true;
+  }
+  // two graphs: a teacher-forced step (priming: histories only) and a generation step
+  auto capture = [&](bool sample, float* pred, bool write_audio, cudaGraphExec_t* exec) -> int {
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int r = gen_step(h, st, B, has_cb, sample, deterministic, seed, pred, (long long)length * h->Cout, n_prime - 1, write_audio);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (r != WN_OK || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); set_err("generation: graph capture failed"); return WN_ERR_CUDA; }
+    e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_err("generation: graph instantiation failed"); return WN_ERR_CUDA; }
+    return WN_OK;
+  };
+  cudaGraphExec_t g_prime = nullptr, g_gen = nullptr;
+  if (n_prime > 1) RET(capture(false, nullptr, false, &g_prime));
+  RET(capture(!teacher_dev, pred_dev, !teacher_dev, &g_gen));
+  for (int t = 0; t + 1 < n_prime; ++t) CK(cudaGraphLaunch(g_prime, st));
+  for (int i = 0; i < length; ++i) CK(cudaGraphLaunch(g_gen, st));
+  if (out_dev) CK(cudaMemcpy2DAsync(out_dev, (size_t)length * 4, G.audio + n_prime, (size_t)G.cap * 4, (size_t)length * 4, B, cudaMemcpyDeviceToDevice, st));
+  CK(cudaEventRecord(h->ev_out, st)); CK(cudaStreamWaitEvent(user, h->ev_out, 0));
+  CK(cudaStreamSynchronize(st));
+  if (g_prime) cudaGraphExecDestroy(g_prime);
+  cudaGraphExecDestroy(g_gen);
   return WN_OK;
 }
 

@@ -6,8 +6,8 @@ schedule and receptive field (:79-81,122), `build` (:171-211), `call` (:213-239)
 (:151-155), `compute_receptive_field` (:553-556).  The arithmetic runs in libwavenet_b200.so;
 torch holds device buffers, streams and (multi-GPU) the NCCL process group.
 
-Out of scope (inference / observability): `generate`, `sample_waveform`,
-the compiled MSE metric.
+`generate` uses per-conv input histories (the fast single-step form of layers.py:226-290); observability
+(callbacks, TensorBoard) stays out of scope.
 """
 from __future__ import annotations
 
@@ -434,5 +434,52 @@ class WaveNet:
       return out
     return out.unsqueeze(-1)
 
-  def generate(self, *args, **kwargs):
-    raise NotImplementedError('autoregressive generation (model.py:258-307) is inference-only and out of scope')
+  def generate(self, length, batch_size: int = 1, condition=None, sample=None, use_queues=True, deterministic=False, seed=None):
+    """model.py:258-307 with the per-layer single-step form (layers.py:226-290): returns (B, length, 1).
+    `sample` (B, n, 1) primes the model (the reference uses n = receptive_field; zeros when deterministic, N(0,1)
+    noise otherwise).  Histories of every dilated conv's input replace the sliding window, so a new sample costs one
+    matrix-vector product per conv instead of a forward pass over the receptive field (`use_queues` is accepted for
+    signature compatibility; the windowed loop is not built).  Draws as in `sample_waveform`; upstream's
+    `_generation` always samples deterministically (model.py:255) — pass deterministic=True for that."""
+    if self.conditioning is not None and condition is None:
+      raise ValueError('Conditioning must be provided.')
+    dev = torch.device('cuda', self.device_index)
+    cond = as_dev(condition, dev) if condition is not None else None
+    if cond is not None:
+      batch_size = int(cond.shape[0])
+    if sample is not None:
+      prime = as_dev(sample, dev)
+      if cond is not None and int(prime.shape[0]) != batch_size:
+        raise ValueError('Condition and sample must have same batch size.')
+      batch_size = int(prime.shape[0])
+    elif deterministic:
+      prime = torch.zeros((batch_size, self.receptive_field, 1), dtype=torch.float32, device=dev)
+    else:
+      gen = torch.Generator(device=dev)
+      gen.manual_seed(42 if seed is None else int(seed))
+      prime = torch.randn((batch_size, self.receptive_field, 1), dtype=torch.float32, device=dev, generator=gen)
+    prime2 = prime.reshape(batch_size, -1).contiguous()
+    if not self.built:
+      self.build(((batch_size, prime2.shape[1], 1), cond.shape) if cond is not None else (batch_size, prime2.shape[1], 1))
+    h = self.handle
+    out = torch.empty((batch_size, int(length)), dtype=torch.float32, device=dev)
+    if seed is None:
+      self._sample_calls += 1
+      seed = self._sample_seed + self._sample_calls
+    _lib.check(h.lib.wn_generate(h.h, h.ptr(prime2), int(prime2.shape[1]), h.ptr(cond), batch_size, int(length), 1 if deterministic else 0,
+                                 C.c_uint64(int(seed)), h.ptr(out), None, None, h.stream_ptr()))
+    return out.unsqueeze(-1)
+
+  def _teacher_forced_step_predictions(self, prime, teacher, condition=None):
+    """Test hook: run the generation step teacher-forced on prime ++ teacher and return the predictive distribution of
+    every teacher position, (B, len(teacher), C) — must equal `call` on the same waveform."""
+    dev = torch.device('cuda', self.device_index)
+    p2 = as_dev(prime, dev).reshape(prime.shape[0], -1).contiguous()
+    t2 = as_dev(teacher, dev).reshape(teacher.shape[0], -1).contiguous()
+    cond = as_dev(condition, dev) if condition is not None else None
+    h = self.handle
+    cout = 3 * self.num_mixtures if self.num_mixtures is not None else 2 ** self.bits
+    pred = torch.empty((p2.shape[0], t2.shape[1], cout), dtype=torch.float32, device=dev)
+    _lib.check(h.lib.wn_generate(h.h, h.ptr(p2), int(p2.shape[1]), h.ptr(cond), int(p2.shape[0]), int(t2.shape[1]), 1, C.c_uint64(0),
+                                 None, h.ptr(pred), h.ptr(t2), h.stream_ptr()))
+    return pred
