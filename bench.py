@@ -285,17 +285,23 @@ def main():
     prof[name] = (ms.value / args.profile_steps, n.value // args.profile_steps)
   rows = B_local * T
   dil_flops_step = 3.0 * flops['dilated'] * rows
+  # the fused block-forward kernel (gated conv + gate + conv1 + residual in one launch) is timed in this class: its
+  # conv1 products are algorithmic work of the class too (forward only; their adjoints run in other kernels)
+  fused_blocks = int(h.lib.wn_fused_forward_blocks(h.h))
+  dmodel = kw['dilation_channels'] or kw['channels']
+  dil_flops_step += fused_blocks * 2.0 * dmodel * kw['channels'] * rows
   dil_ms, dil_launches = prof['dilated']
   achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
   roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
               'frac': achieved / peaks['tensor'],
               # dram__bytes_read+write per launch, mean over the class's kernels, from one `ncu --set full` capture of the C2
-              # step (cold cache; profiles/ncu_full_r1d_c2_{fwd,bwd}.txt): gate 70.3 MB, dgrad 111.4 MB, dilated wgrad 110.5 MB,
-              # its finish 19.1 MB.  Only valid for the default workload.
-              'traffic': 7.78e7 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels) else None,
-              'kernel': 'tc_conv_gemm_staged_kernel<gate | dgrad, cta_group::2> + tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'
+              # step (cold cache; profiles/ncu_full_r1e_c2_{blockfwd,bwd}.txt): fused block forward 98.0 MB, dgrad 110.5 MB,
+              # dilated wgrad 107.5 MB, its finish 19.1 MB.  Only valid for the default workload.
+              'traffic': 8.38e7 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and fused_blocks) else None,
+              'kernel': ('tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ' if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + ')
+              + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'
               if precision == 'bf16' else 'conv_gemm_simt + wgrad_simt on the dilated convs',
-              'launches_per_step': dil_launches, 'ms_per_step_in_kernel': dil_ms,
+              'launches_per_step': dil_launches, 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
               'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
               'share_of_step': dil_ms / (ms_total / args.steps)}
   step_ms = ms_total / args.steps

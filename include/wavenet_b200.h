@@ -204,6 +204,7 @@ int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int lda, const v
 int64_t wn_last_launch_count(const wn_handle* h);
 /* accumulate CUDA-event time of one kernel class over subsequent steps: tag 0 = off,
  * 1 = dilated-conv GEMMs (fwd+dgrad+wgrad), 2 = all GEMMs, 3 = loss/head reductions */
+int wn_fused_forward_blocks(const wn_handle* h);  /* blocks of the last forward that ran as one fused gate+conv1 launch */
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
 /* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a

@@ -205,6 +205,7 @@ struct wn_handle {
   int use_side = 1;
   int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
   int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
+  int fused_fwd_launches = 0;  // fused block-forward launches of the last step (0: separate gate / conv1 kernels)
   int use_merged_finish = 0;  // WN_TC_MERGED_FINISH=1: one finish launch for both wgrads of a block. Measured SLOWER on C2 (7.48 vs
                               // 7.38 ms/step: the deferred partials fall out of L2 before the merged finish reads them) -> off
   // every weight re-pack as one launch: job table recorded on the first wn_params_changed (buffers never move)
@@ -1054,7 +1055,7 @@ static int block_forward(wn_handle* h, cudaStream_t st, int l, const void* x_in,
             LaunchScope ls(h, st, CLS_DILATED);
             r = c.tileN16 == 256 ? tc_block_fwd(h->tmaps, st, d) : -100;
           }
-          if (r == 0) return WN_OK;
+          if (r == 0) { h->fused_fwd_launches++; return WN_OK; }
           if (r != -100) { set_err("fused block forward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
           h->launches--;      // not launched: fall through to the separate kernels
         }
@@ -1115,6 +1116,7 @@ static int skip_gemm(wn_handle* h, cudaStream_t st, int l0, int nl, TO* out, int
 template <class T>
 static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx, const float* cond_in, int B, int Tn) {
   const wn_config& c = h->cfg;
+  h->fused_fwd_launches = 0;
   const float* cond = nullptr;
   if (c.conditioning) {
     RET(cond_forward(h, st, cond_in, B, true, &cond));
@@ -2217,6 +2219,8 @@ extern "C" int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int l
 
 // ---------------------------------------------------------------- introspection
 extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
+// number of blocks whose gated conv + conv1 ran as ONE fused launch in the last enqueued forward (0 = separate kernels)
+extern "C" int wn_fused_forward_blocks(const wn_handle* h) { return h ? h->fused_fwd_launches : 0; }
 // per-launch record of the last wn_profile_end: returns the number of timed launches; i in [0,n): duration + label
 extern "C" int wn_profile_get(wn_handle* h, int i, double* ms, char* label, int label_len) {
   if (!h) return WN_ERR_VALUE;
