@@ -22,18 +22,23 @@ struct GenVec {           // one K-tap dense layer evaluated at time t for every
   float* acc; int acc_ld; int acc_col0;                    // columns [acc_col0, N) are ACCUMULATED into acc[b][n - acc_col0] (skip sum)
 };
 
-// grid (ceil(N / 32), B), 256 threads: warp w sums the (k, c) pairs congruent to w mod 8, lanes = 32 consecutive outputs
-__global__ void __launch_bounds__(256) gen_dense_kernel(const GenVec v, const int* __restrict__ t_dev) {
-  extern __shared__ float xs[];              // [K][Cin] staged input taps
-  __shared__ float red[8][33];
+// grid (ceil(N / 32), ceil(B / GEN_ROWS)), 256 threads: a CTA computes 32 consecutive outputs for GEN_ROWS batch rows (every
+// weight fetched once per GEN_ROWS rows; measured: 1 row per CTA is fastest, the step is latency- not traffic-bound);
+// warp w sums the (k, c) pairs congruent to w mod 8, then warp r finishes row r
+#define GEN_ROWS 1
+__global__ void __launch_bounds__(256) gen_dense_kernel(const GenVec v, const int B, const int* __restrict__ t_dev) {
+  extern __shared__ float xs[];              // [GEN_ROWS][K*Cin] staged input taps
+  __shared__ float red[8][GEN_ROWS][33];
   const int t = *t_dev;
-  const int b = blockIdx.y;
+  const int b0 = blockIdx.y * GEN_ROWS;
   const int kc = v.K * v.Cin;
-  for (int i = threadIdx.x; i < kc; i += 256) {
-    const int k = i / v.Cin, c = i % v.Cin;
+  for (int i = threadIdx.x; i < GEN_ROWS * kc; i += 256) {
+    const int r = i / kc, j = i % kc;
+    const int k = j / v.Cin, c = j % v.Cin;
     const int ts = t - (v.K - 1 - k) * v.dil;
+    const int b = b0 + r;
     float x = 0.f;
-    if (ts >= 0 || v.in_tstride == 0) {
+    if (b < B && (ts >= 0 || v.in_tstride == 0)) {
       const float* p = v.in + (long long)b * v.in_bstride + (v.in_tstride ? (long long)ts * v.in_tstride : 0);   // gate inputs are plain vectors
       if (v.in_gate) x = tanhf(p[c]) * (1.0f / (1.0f + expf(-p[v.Cin + c])));
       else x = p[c];
@@ -43,16 +48,24 @@ __global__ void __launch_bounds__(256) gen_dense_kernel(const GenVec v, const in
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 32 + lane;
-  float s = 0.f;
+  float s[GEN_ROWS];
+#pragma unroll
+  for (int r = 0; r < GEN_ROWS; ++r) s[r] = 0.f;
   if (n < v.N) {
-    for (int i = warp; i < kc; i += 8) s = fmaf(v.W[(long long)i * v.N + n], xs[i], s);
+    for (int i = warp; i < kc; i += 8) {
+      const float w = v.W[(long long)i * v.N + n];
+#pragma unroll
+      for (int r = 0; r < GEN_ROWS; ++r) s[r] = fmaf(w, xs[r * kc + i], s[r]);
+    }
   }
-  red[warp][lane] = s;
+#pragma unroll
+  for (int r = 0; r < GEN_ROWS; ++r) red[warp][r][lane] = s[r];
   __syncthreads();
-  if (warp == 0 && n < v.N) {
+  const int b = b0 + warp;                   // warp r finishes batch row b0 + r
+  if (warp < GEN_ROWS && b < B && n < v.N) {
     float r = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) r += red[w][lane];
+    for (int w = 0; w < 8; ++w) r += red[w][warp][lane];
     if (v.bias) r += v.bias[n];
     if (v.cbias) r += v.cbias[(long long)b * v.ldcb + n];
     r = wn_act<false>(v.act, r);

@@ -214,6 +214,7 @@ struct wn_handle {
     int B = 0, cap = 0;
     float* audio = nullptr; std::vector<std::vector<float*>> hist; float* z = nullptr; float* skipsum = nullptr;
     std::vector<float*> hbuf; float* logits = nullptr; float* sampled = nullptr; int* t_dev = nullptr;
+    std::vector<float*> wcat, bcat;          // per block [D][R+S] = [Wr | Ws], [R+S]: conv1 and conv_skip as one product
     std::vector<void*> allocs;
   } gen;
   // deferred wgrad finish (see WgradH::defer_finish)
@@ -1596,13 +1597,22 @@ static int gen_alloc(wn_handle* h, int B, int cap) {
   G.logits = (float*)take((size_t)B * h->Cout * 4);
   G.sampled = (float*)take((size_t)B * 4);
   G.t_dev = (int*)take(16);
+  G.wcat.assign(h->L, nullptr); G.bcat.assign(h->L, nullptr);
+  for (int l = 0; l < h->L && ok; ++l) {
+    if (!(h->cfg.use_skip && h->blocks[l].has_skip)) continue;
+    G.wcat[l] = (float*)take((size_t)h->D * (h->R + h->S) * 4);
+    G.bcat[l] = (float*)take((size_t)(h->R + h->S) * 4);
+    ok = G.wcat[l] && G.bcat[l];
+  }
   if (!ok || !G.z || !G.skipsum || !G.logits || !G.sampled || !G.t_dev) { set_err("generation workspace allocation failed"); G.B = G.cap = 0; return WN_ERR_CUDA; }
   return WN_OK;
 }
 
 static void gen_dense(cudaStream_t st, const GenVec& v, int B, const int* t_dev) {
-  const size_t smem = (size_t)v.K * v.Cin * 4;
-  gen_dense_kernel<<<dim3(cdiv(v.N, 32), B), 256, smem, st>>>(v, t_dev);
+  const size_t smem = (size_t)GEN_ROWS * v.K * v.Cin * 4;
+  static bool attr_done = false;
+  if (!attr_done) { cudaFuncSetAttribute(gen_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_done = true; }
+  gen_dense_kernel<<<dim3(cdiv(v.N, 32), cdiv(B, GEN_ROWS)), 256, smem, st>>>(v, B, t_dev);
 }
 
 // one time step of the whole network on the histories; t is read from device memory
@@ -1632,19 +1642,18 @@ static int gen_step(wn_handle* h, cudaStream_t st, int B, bool has_cb, bool samp
       gen_dense(st, v, B, t);
     }
     {
-      GenVec v{};   // conv1 (+ residual) on the gate of z
+      GenVec v{};   // conv1 (+ residual) [| conv_skip -> running skip sum, model.py:236] on the gate of z
       v.in = G.z; v.in_bstride = 2 * D; v.in_tstride = 0; v.Cin = D; v.K = 1; v.dil = 1; v.in_gate = 1;
-      v.W = P_(h, b.conv1.w_idx); v.bias = P_(h, b.conv1.b_idx); v.N = R; v.act = ACT_LINEAR;
+      v.act = ACT_LINEAR;
       v.out = G.hist[l + 1][0]; v.out_bstride = (long long)cap * R; v.out_tstride = R;
       if (h->cfg.use_residual) { v.res = G.hist[l][0]; v.res_bstride = (long long)cap * R; v.res_tstride = R; v.res_cols = R; }
-      if (h->cfg.use_skip && h->alias_skip) { v.acc = G.skipsum; v.acc_ld = h->Sp; v.acc_col0 = -1; }
-      gen_dense(st, v, B, t);
-    }
-    if (h->cfg.use_skip && b.has_skip) {
-      GenVec v{};   // conv_skip, accumulated into the running skip sum (model.py:236)
-      v.in = G.z; v.in_bstride = 2 * D; v.in_tstride = 0; v.Cin = D; v.K = 1; v.dil = 1; v.in_gate = 1;
-      v.W = P_(h, b.conv_skip.w_idx); v.bias = P_(h, b.conv_skip.b_idx); v.N = h->S; v.act = ACT_LINEAR;
-      v.acc = G.skipsum; v.acc_ld = h->Sp; v.acc_col0 = 0; v.out = G.skipsum;
+      if (G.wcat[l]) {
+        v.W = G.wcat[l]; v.bias = G.bcat[l]; v.N = R + h->S;
+        v.acc = G.skipsum; v.acc_ld = h->Sp; v.acc_col0 = R;
+      } else {
+        v.W = P_(h, b.conv1.w_idx); v.bias = P_(h, b.conv1.b_idx); v.N = R;
+        if (h->cfg.use_skip && h->alias_skip) { v.acc = G.skipsum; v.acc_ld = h->Sp; v.acc_col0 = -1; }
+      }
       gen_dense(st, v, B, t);
     }
   }
@@ -1681,7 +1690,7 @@ extern "C" int wn_generate(wn_handle* h, const float* prime_dev, int n_prime, co
   if (!h->cfg.has_head || !h->cfg.has_input_conv) { set_err("wn_generate needs a full model handle"); return WN_ERR_STATE; }
   if (h->cfg.conditioning && !cond_dev) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
   if (!prime_dev || n_prime < 1 || B < 1 || B > 64 || B > h->maxB || length < 1 || (!out_dev && !pred_dev)) { set_err("bad generate arguments (1 <= batch <= min(64, max_batch))"); return WN_ERR_VALUE; }
-  if ((size_t)h->K * (h->R > h->D ? h->R : h->D) * 4 > 48 * 1024) { set_err("generation: K * channels too large for the step kernel"); return WN_ERR_UNSUPPORTED; }
+  if ((size_t)GEN_ROWS * h->K * (h->R > h->D ? h->R : h->D) * 4 > 160 * 1024) { set_err("generation: K * channels too large for the step kernel"); return WN_ERR_UNSUPPORTED; }
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t user = (cudaStream_t)stream, st = h->own_stream;
   const int cap = n_prime + length + 1;
@@ -1702,6 +1711,15 @@ extern "C" int wn_generate(wn_handle* h, const float* prime_dev, int n_prime, co
     const int n = 2 * h->D;
     cond_bias_all<<<dim3(cdiv(B * n, 128), h->L), 128, 0, st>>>(cond, h->Cc, h->d_params, h->d_cond_offsets, h->cb, (long long)h->maxB * n, B, n);
     has_cb = true;
+  }
+  for (int l = 0; l < h->L; ++l) {
+    if (!G.wcat[l]) continue;
+    const BlockP& b = h->blocks[l];
+    const size_t ld = (size_t)(h->R + h->S) * 4;
+    CK(cudaMemcpy2DAsync(G.wcat[l], ld, P_(h, b.conv1.w_idx), (size_t)h->R * 4, (size_t)h->R * 4, h->D, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(G.wcat[l] + h->R, ld, P_(h, b.conv_skip.w_idx), (size_t)h->S * 4, (size_t)h->S * 4, h->D, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(G.bcat[l], P_(h, b.conv1.b_idx), (size_t)h->R * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(G.bcat[l] + h->R, P_(h, b.conv_skip.b_idx), (size_t)h->S * 4, cudaMemcpyDeviceToDevice, st));
   }
   // two graphs: a teacher-forced step (priming: histories only) and a generation step
   auto capture = [&](bool sample, float* pred, bool write_audio, cudaGraphExec_t* exec) -> int {
