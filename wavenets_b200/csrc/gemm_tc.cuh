@@ -1064,7 +1064,8 @@ template <int BN> struct TcWgradPairCfg {
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                     const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmG, const TcWgradParams p) {
+                     const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmP,
+                     const TcWgradParams p) {
   using Cfg = TcWgradPairCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF = BN / 2;
@@ -1245,24 +1246,34 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     te1 = clock64();
 #endif
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int c = 0; c < BN; c += 16) {
-      const int n = n0 + c;
-      if (n >= p.N) break;
-      float v[16];
-      if (nchunks > 0) tmem_ld16(taddr + (uint32_t)c, v);
-      else {
+    // partial tile (128 channels x BN fp32) -> the operand ring (free now: every MMA has completed and read it) as BN/32
+    // boxes of 128 rows x 32 floats, 128B swizzle -> TMA stores.  Row-per-thread global stores took 9.5 k cycles here.
+    {
+      const int r = quarter * 32 + lane;
+      const uint32_t rsw = (uint32_t)(r & 7);
+      uint8_t* const rowp = smem + (uint32_t)r * 128u;
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        if (nchunks > 0) tmem_ld16(taddr + (uint32_t)c, v);
+        else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      if (valid) {
-        const int nv = min(16, p.N - n);
-        if (nv == 16 && ((p.N & 3) == 0)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(out + n)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (i < nv) out[n + i] = v[i];
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
+        uint8_t* const boxp = rowp + (c >> 5) * 16384;
+        const uint32_t j0 = (uint32_t)((c & 31) >> 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(boxp + (((j0 + i) ^ rsw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(6, 128);
+      if (threadIdx.x == 128) {
+        const int row0 = koff + k0;
+#pragma unroll
+        for (int bx = 0; bx < BN / 32; ++bx)
+          if (n0 + bx * 32 < p.N) tma_store_3d_h(smem + bx * 16384, &tmP, n0 + bx * 32, row0, (int)blockIdx.z, TC_POL_LAST);
+        bulk_commit_group();
+        bulk_wait_group<0>();
       }
     }
   }
@@ -1303,6 +1314,12 @@ static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDes
   p.slots = (p.chunks_per_split + p.chunks_t - 2) / p.chunks_t + 1;
   p.cs_partial = d.cs_partial;
   plan->nsplit = nsplit; plan->chunks_per_split = p.chunks_per_split; plan->chunks_t = p.chunks_t; plan->slots = p.slots; plan->mtiles = 2 * mpairs;
+  // partials [nsplit][ktot][N] fp32 as a TMA-store target: boxes of 32 floats x 128 rows
+  uint64_t pd[3] = {(uint64_t)d.N, (uint64_t)d.ktot, (uint64_t)nsplit};
+  uint64_t ps[2] = {(uint64_t)d.N * 4, (uint64_t)d.ktot * d.N * 4};
+  uint32_t pb[3] = {32, 128, 1};
+  const CUtensorMap* mp = tc.get(d.partial, 3, pd, ps, pb, 128, true);
+  if (!mp) return -14;
   auto kern = tc_wgrad_pair_kernel<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1314,7 +1331,7 @@ static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDes
   cfg.gridDim = dim3(2 * mpairs, ntiles, nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 2);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mg, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *ma[0], *ma[1], *ma[2], *ma[3], *mg, *mp, p);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "wgrad launch (cta pairs): %s", cudaGetErrorString(e)); return -13; }
   return 0;
 }

@@ -352,9 +352,11 @@ struct TmapCache {
   std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> maps;
   // bf16 tensor, rank 2..4, dims innermost first, strides in BYTES for dims 1..rank-1, 128B swizzle, zero OOB fill
   // swizzle_bytes: 128 (inner box extent 128 B) or 64 (inner box extent 64 B)
-  const CUtensorMap* get(const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box, int swizzle_bytes = 128) {
+  // swizzle_bytes: 128 / 64; fp32 = true encodes a FLOAT32 tensor (swizzle code 128 + 1 in the key), else bf16
+  const CUtensorMap* get(const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box, int swizzle_bytes = 128,
+                         bool fp32 = false) {
     TmapKey k{};
-    k.base = base; k.rank = (uint32_t)rank; k.swz = (uint32_t)swizzle_bytes;
+    k.base = base; k.rank = (uint32_t)rank; k.swz = (uint32_t)swizzle_bytes + (fp32 ? 1u : 0u);
     for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.box[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides[i];
     auto it = maps.find(k);
@@ -365,7 +367,7 @@ struct TmapCache {
       if (strides[i] % 16 != 0) { snprintf(g_tc_err, sizeof(g_tc_err), "TMA stride %llu not a multiple of 16 bytes", (unsigned long long)strides[i]); return nullptr; }
     CUtensorMap m;
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_tmap_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
+    CUresult r = g_tmap_encode(&m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
                                (const cuuint64_t*)strides, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
