@@ -1050,23 +1050,26 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 // bandwidth: 387 MB per dilated wgrad launch).  The leader's barrier counts both CTAs' TMA bytes; the column sums
 // read the local G half after the MMAs of the stage have completed (mma_done), then release the stage.
 // Requires every segment width to be a multiple of 256 (pair tiles never straddle a segment).
-template <int BN> struct TcWgradPairCfg {
+// NH: BN-wide column blocks per pair (1 or 2).  NH = 2 (N = 512 per pair, all 512 TMEM columns): the A tile of a stage is
+// used for two MMAs, 48 KB per SM per 2 x the products instead of 32 KB per 1 x -> a third less L2 -> SM traffic per FLOP.
+template <int BN, int NH = 1> struct TcWgradPairCfg {
   static constexpr int BKT = 64;
   static constexpr int A_BYTES = 2 * 64 * BKT * 2;               // two 64-channel atoms: 16 KB
-  static constexpr int G_ATOMS = BN / 2 / 64;                    // 64-column atoms of this CTA's half
-  static constexpr int G_BYTES = G_ATOMS * 64 * BKT * 2;
+  static constexpr int G_ATOMS = BN / 2 / 64;                    // 64-column atoms of this CTA's half of ONE column block
+  static constexpr int GH_BYTES = G_ATOMS * 64 * BKT * 2;
+  static constexpr int G_BYTES = NH * GH_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + G_BYTES;
-  static constexpr int STAGES = 6;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + 1024;   // align slack, barriers, column-sum scratch
+  static constexpr int STAGES = NH == 2 ? 4 : 6;
+  static constexpr int TMEM_COLS = BN * NH < 32 ? 32 : BN * NH;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + 2048;   // align slack, barriers, column-sum scratch
 };
 
-template <int BN>
+template <int BN, int NH>
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                      const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmP,
                      const TcWgradParams p) {
-  using Cfg = TcWgradPairCfg<BN>;
+  using Cfg = TcWgradPairCfg<BN, NH>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int HALF = BN / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -1076,7 +1079,7 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   uint64_t* mma_done = empty_bar + STAGES;
   uint64_t* tfull_bar = mma_done + STAGES;
   uint32_t* tmem_ptr = (uint32_t*)(tfull_bar + 1);
-  float* cs_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 1024);      // [2][HALF] column-sum hand-over between row halves
+  float* cs_s = (float*)(smem + STAGES * Cfg::STAGE_BYTES + 1024);      // [RH][NH * HALF] column-sum hand-over between row halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -1092,8 +1095,8 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     mp -= nt; koff += p.segK[s]; ++s;
   }
   const int k0 = (mp << 8) + (int)crank * 128;
-  const int n0 = blockIdx.y * BN;
-  const int gcol0 = n0 + (int)crank * HALF;
+  const int n0 = blockIdx.y * (BN * NH);
+  const int gcol0 = n0 + (int)crank * HALF;           // first column of this CTA's half of column block 0 (block h: + h * BN)
   const int c_begin = blockIdx.z * p.chunks_per_split;
   const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
   const int nchunks = c_end - c_begin;
@@ -1139,7 +1142,9 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
         // one op per operand: boxes of 2 (A) and G_ATOMS (G) 64-channel atoms (tc_atom_map)
         tma_load_4d_pair_h(sa, tm, &full_bar[stage], 0, t0 + shift, k0 >> 6, b, p.pol_a);
-        tma_load_4d_pair_h(sa + Cfg::A_BYTES, &tmG, &full_bar[stage], 0, t0, gcol0 >> 6, b, p.pol_g);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+          tma_load_4d_pair_h(sa + Cfg::A_BYTES + hh * Cfg::GH_BYTES, &tmG, &full_bar[stage], 0, t0, (gcol0 + hh * BN) >> 6, b, p.pol_g);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
 #ifdef TC_TIMELINE
@@ -1165,10 +1170,13 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < Cfg::BKT / 16; ++k)
-            umma_bf16_pair(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+          for (int hh = 0; hh < NH; ++hh) {
+            const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES + hh * Cfg::GH_BYTES, 8192, 1024);
+#pragma unroll
+            for (int k = 0; k < Cfg::BKT / 16; ++k)
+              umma_bf16_pair(tmem_base + (uint32_t)(hh * BN), adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
+          }
           // with column sums the stage is released by the summing warps, which first wait for these MMAs
           umma_commit_pair(do_cs ? &mma_done[stage] : &empty_bar[stage]);
           if (it == nchunks - 1) umma_commit_pair(tfull_bar);
@@ -1193,37 +1201,51 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       const uint32_t chunk = (uint32_t)(cc >> 3);
       const int len = cs_r1 - cs_r0;
       const int r_lo = cs_r0 + (len * rh) / RH, r_hi = cs_r0 + (len * (rh + 1)) / RH;
-      float s0 = 0.f, s1 = 0.f;
+      float s0[NH], s1[NH];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) s0[hh] = s1[hh] = 0.f;
       int stage = 0; uint32_t phase = 0;
       int cur_b = c_begin / p.chunks_t;
       const int b_first = cur_b;
       auto flush = [&](int slot) {
         // combine the row halves in a fixed order, write this CTA's columns and zero the peer's half
-        cs_s[rh * HALF + c] = s0; cs_s[rh * HALF + c + 1] = s1;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) { cs_s[(rh * NH + hh) * HALF + c] = s0[hh]; cs_s[(rh * NH + hh) * HALF + c + 1] = s1[hh]; }
         named_bar_sync(7, 128);
         if (rh == 0) {
-          float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-          for (int h2 = 0; h2 < RH; ++h2) { t0 += cs_s[h2 * HALF + c]; t1 += cs_s[h2 * HALF + c + 1]; }
           float* o = p.cs_partial + (((long long)blockIdx.z * gridDim.x + blockIdx.x) * p.slots + slot) * p.N;
-          const int mine = gcol0 + c, other = n0 + (1 - (int)crank) * HALF + c;
-          if (mine < p.N) o[mine] = t0;
-          if (mine + 1 < p.N) o[mine + 1] = t1;
-          if (other < p.N) o[other] = 0.f;
-          if (other + 1 < p.N) o[other + 1] = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int h2 = 0; h2 < RH; ++h2) { t0 += cs_s[(h2 * NH + hh) * HALF + c]; t1 += cs_s[(h2 * NH + hh) * HALF + c + 1]; }
+            const int mine = gcol0 + hh * BN + c, other = n0 + hh * BN + (1 - (int)crank) * HALF + c;
+            if (mine < p.N) o[mine] = t0;
+            if (mine + 1 < p.N) o[mine + 1] = t1;
+            if (other < p.N) o[other] = 0.f;
+            if (other + 1 < p.N) o[other + 1] = 0.f;
+          }
         }
         named_bar_sync(7, 128);
       };
       for (int ch = c_begin; ch < c_end; ++ch) {
         const int b = ch / p.chunks_t;
-        if (b != cur_b) { flush(cur_b - b_first); s0 = s1 = 0.f; cur_b = b; }
+        if (b != cur_b) {
+          flush(cur_b - b_first);
+#pragma unroll
+          for (int hh = 0; hh < NH; ++hh) s0[hh] = s1[hh] = 0.f;
+          cur_b = b;
+        }
         mbar_wait(&mma_done[stage], phase);
-        const uint8_t* g = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES + col_off;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          const uint8_t* g = smem + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES + hh * Cfg::GH_BYTES + col_off;
 #pragma unroll 8
-        for (int r = r_lo; r < r_hi; ++r) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(g + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4));
-          s0 += __uint_as_float(w << 16);
-          s1 += __uint_as_float(w & 0xffff0000u);
+          for (int r = r_lo; r < r_hi; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(g + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4));
+            s0[hh] += __uint_as_float(w << 16);
+            s1[hh] += __uint_as_float(w & 0xffff0000u);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -1252,29 +1274,37 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       const int r = quarter * 32 + lane;
       const uint32_t rsw = (uint32_t)(r & 7);
       uint8_t* const rowp = smem + (uint32_t)r * 128u;
-      for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        if (nchunks > 0) tmem_ld16(taddr + (uint32_t)c, v);
-        else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll 1
+      for (int hh = 0; hh < NH; ++hh) {
+        if (hh > 0) {
+          // the staging area is reused: its TMA stores must have read it
+          if (threadIdx.x == 128) bulk_wait_group_read<0>();
+          named_bar_sync(6, 128);
         }
-        uint8_t* const boxp = rowp + (c >> 5) * 16384;
-        const uint32_t j0 = (uint32_t)((c & 31) >> 2);
+        for (int c = 0; c < BN; c += 16) {
+          float v[16];
+          if (nchunks > 0) tmem_ld16(taddr + (uint32_t)(hh * BN + c), v);
+          else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4*>(boxp + (((j0 + i) ^ rsw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
-      fence_proxy_async();
-      named_bar_sync(6, 128);
-      if (threadIdx.x == 128) {
-        const int row0 = koff + k0;
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+          uint8_t* const boxp = rowp + (c >> 5) * 16384;
+          const uint32_t j0 = (uint32_t)((c & 31) >> 2);
 #pragma unroll
-        for (int bx = 0; bx < BN / 32; ++bx)
-          if (n0 + bx * 32 < p.N) tma_store_3d_h(smem + bx * 16384, &tmP, n0 + bx * 32, row0, (int)blockIdx.z, TC_POL_LAST);
-        bulk_commit_group();
-        bulk_wait_group<0>();
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(boxp + (((j0 + i) ^ rsw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        fence_proxy_async();
+        named_bar_sync(6, 128);
+        if (threadIdx.x == 128) {
+          const int row0 = koff + k0;
+#pragma unroll
+          for (int bx = 0; bx < BN / 32; ++bx)
+            if (n0 + hh * BN + bx * 32 < p.N) tma_store_3d_h(smem + bx * 16384, &tmP, n0 + hh * BN + bx * 32, row0, (int)blockIdx.z, TC_POL_LAST);
+          bulk_commit_group();
+        }
       }
+      if (threadIdx.x == 128) bulk_wait_group<0>();
     }
   }
 #ifdef TC_TIMELINE
@@ -1286,9 +1316,9 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   if (warp == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int BN>
+template <int BN, int NH>
 static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d, TcWgradPlan* plan) {
-  using Cfg = TcWgradPairCfg<BN>;
+  using Cfg = TcWgradPairCfg<BN, NH>;
   const CUtensorMap* ma[TC_MAX_SEG] = {nullptr, nullptr, nullptr, nullptr};
   int mpairs = 0;
   for (int s = 0; s < d.nseg; ++s) {
@@ -1304,7 +1334,7 @@ static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDes
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
   p.partial = d.partial;
   p.pol_a = tc_policy(d.l2_a); p.pol_g = tc_policy(d.l2_g);
-  const int ntiles = (d.N + BN - 1) / BN;
+  const int ntiles = (d.N + BN * NH - 1) / (BN * NH);
   int nsplit = (tc_num_sms() / 2) / (mpairs * ntiles);     // one wave of CTA pairs
   if (nsplit < 1) nsplit = 1;
   if (nsplit > WN_MAX_WGRAD_SPLITS) nsplit = WN_MAX_WGRAD_SPLITS;
@@ -1320,7 +1350,7 @@ static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDes
   uint32_t pb[3] = {32, 128, 1};
   const CUtensorMap* mp = tc.get(d.partial, 3, pd, ps, pb, 128, true);
   if (!mp) return -14;
-  auto kern = tc_wgrad_pair_kernel<BN>;
+  auto kern = tc_wgrad_pair_kernel<BN, NH>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -1430,7 +1460,17 @@ static inline int tc_wgrad(TmapCache& tc, cudaStream_t st, const TcWgradDesc& d,
   if (pair_on < 0) { const char* e = getenv("WN_TC_WGRAD_PAIR"); pair_on = (e && e[0] == '0') ? 0 : 1; }
   bool pair_ok = pair_on && d.N > 64 && d.N % 64 == 0;
   for (int s = 0; s < d.nseg; ++s) pair_ok = pair_ok && d.seg[s].K % 256 == 0;
-  if (pair_ok) return d.N > 128 ? tc_wgrad_pair_launch<256>(tc, st, d, plan) : tc_wgrad_pair_launch<128>(tc, st, d, plan);
+  if (pair_ok) {
+    // two 256-column blocks per pair (N = 512, all of TMEM): a third less L2 -> SM traffic per FLOP, but twice the splits
+    // (37 instead of 18) and therefore twice the partial bytes to write and to reduce: measured SLOWER on C2 (7.41 vs
+    // 7.31 ms/step), off unless WN_TC_WGRAD_NH2=1
+    static int nh2_on = -1;
+    if (nh2_on < 0) { const char* e = getenv("WN_TC_WGRAD_NH2"); nh2_on = (e && e[0] == '1') ? 1 : 0; }
+    int mp = 0;
+    for (int s = 0; s < d.nseg; ++s) mp += d.seg[s].K / 256;
+    if (nh2_on && d.N % 512 == 0 && mp >= 2) return tc_wgrad_pair_launch<256, 2>(tc, st, d, plan);
+    return d.N > 128 ? tc_wgrad_pair_launch<256, 1>(tc, st, d, plan) : tc_wgrad_pair_launch<128, 1>(tc, st, d, plan);
+  }
   if (d.N > 128) return tc_wgrad_launch<256>(tc, st, d, plan);
   if (d.N > 64) return tc_wgrad_launch<128>(tc, st, d, plan);
   return tc_wgrad_launch<64>(tc, st, d, plan);
