@@ -275,7 +275,7 @@ def main():
   peaks = load_peaks()
   import ctypes as C
   prof = {}
-  for tag, name in ((1, 'dilated'), (2, 'gemm_all')):
+  for tag, name in ((1, 'dilated'), (2, 'gemm_all'), (4, 'all')):
     h.lib.wn_profile_begin(h.h, tag)
     for _ in range(args.profile_steps):
       model.train_step_async(data_dev)
@@ -290,7 +290,13 @@ def main():
   fused_blocks = int(h.lib.wn_fused_forward_blocks(h.h))
   dmodel = kw['dilation_channels'] or kw['channels']
   dil_flops_step += fused_blocks * 2.0 * dmodel * kw['channels'] * rows
-  dil_ms, dil_launches = prof['dilated']
+  dil_ms_eager, dil_launches = prof['dilated']
+  # The timed region replays the step as a CUDA graph (two streams), where single kernels cannot be bracketed by events.
+  # Each launch is therefore timed with an event pair in an eager, single-stream pass over the same inputs; that pass pays
+  # a few microseconds of launch gap per kernel, so the class is charged its SHARE of the eager pass times the measured
+  # graph-replay step (the ncu launch list under profiles/ must show the same share).
+  share = dil_ms_eager / prof['all'][0] if prof['all'][0] > 0 else 0.0
+  dil_ms = share * (ms_total / args.steps)
   achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
   roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
               'frac': achieved / peaks['tensor'],
@@ -302,8 +308,9 @@ def main():
               + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'
               if precision == 'bf16' else 'conv_gemm_simt + wgrad_simt on the dilated convs',
               'launches_per_step': dil_launches, 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
+              'ms_per_step_in_kernel_eager_events': dil_ms_eager, 'ms_per_step_all_launches_eager_events': prof['all'][0],
               'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
-              'share_of_step': dil_ms / (ms_total / args.steps)}
+              'share_of_step': share}
   step_ms = ms_total / args.steps
   total_flops_step = 3.0 * flops['total'] * rows
   whole = {'tflops_all_gemms_whole_step': total_flops_step / (step_ms * 1e-3) / 1e12,
