@@ -205,6 +205,7 @@ struct wn_handle {
   int use_side = 1;
   int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
   int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
+  int tile_gate_bwd = 0, tile_dgrad = 0;   // forced CTA tile widths of the two backward conv GEMMs (0 = widest that divides N)
   int fused_fwd_launches = 0;  // fused block-forward launches of the last step (0: separate gate / conv1 kernels)
   int use_merged_finish = 0;  // WN_TC_MERGED_FINISH=1: one finish launch for both wgrads of a block. Measured SLOWER on C2 (7.48 vs
                               // 7.38 ms/step: the deferred partials fall out of L2 before the merged finish reads them) -> off
@@ -594,6 +595,8 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_SIDE_STREAM"); if (e && e[0] == '0') h->use_side = 0; }
   if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
   { const char* e = getenv("WN_TC_FUSED_FWD"); if (e && e[0] == '0') h->use_fused_fwd = 0; }
+  { const char* e = getenv("WN_TC_TILE_GATE_BWD"); if (e) h->tile_gate_bwd = atoi(e); }
+  { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   for (int i = 0; i < h->L; ++i) {
@@ -1310,7 +1313,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     }
     const int rs = R + (b.has_skip ? S : 0);
     g.W32 = b.Wdg ? b.Wdg + (size_t)koff * b.Dpad : nullptr; g.Npad = b.Dpad;
-    g.W16 = b.Wdg16 ? b.Wdg16 + koff : nullptr; g.ktot16 = rup(rs, 64); g.N16 = b.Dpad; g.tile16 = 0;
+    g.W16 = b.Wdg16 ? b.Wdg16 + koff : nullptr; g.ktot16 = rup(rs, 64); g.N16 = b.Dpad; g.tile16 = h->tile_gate_bwd;
     typename EpiGateBwd<T, sizeof(T) == 2>::Params ep{};
     ep.z = (const T*)h->zbuf[l]; ep.dz = (T*)dzbuf; ep.D = D; ep.vec = vec_ok<T>(D);
     // last use of z; dz is read next by the dgrad and the weight-gradient kernels
@@ -1350,6 +1353,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       g.B = B; g.T = Tn; g.N = c.cin; g.nseg = c.K;
       for (int k = 0; k < c.K; ++k) g.seg[k] = SegH{dcur, dcw, +(c.K - 1 - k) * c.dil, c.cout};
       fill_w(g, c, true);
+      g.tile16 = h->tile_dgrad;
       typename EpiActBwd<T, T>::Params ep{};
       ep.N = c.cin;
       if (j > 0) {
