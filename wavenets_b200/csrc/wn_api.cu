@@ -24,6 +24,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc_block.cuh"
+#include "gemm_tc_wgroup.cuh"
 #include "kernels_misc.cuh"
 #include "generate.cuh"
 
@@ -207,6 +208,15 @@ struct wn_handle {
   int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
   int tile_gate_bwd = 0, tile_dgrad = 0;   // forced CTA tile widths of the two backward conv GEMMs (0 = widest that divides N)
   int fused_fwd_launches = 0;  // fused block-forward launches of the last step (0: separate gate / conv1 kernels)
+  // grouped weight gradients (gemm_tc_wgroup.cuh): d z and d x_out of EVERY block are kept (no ping-pong) and all block
+  // weight gradients run as one launch behind the dgrad chain.  WN_TC_GROUP_WGRAD=0 switches back to per-block launches.
+  int use_group_wgrad = 0;
+  void* dz_all = nullptr;     // [L][rows][2D]
+  void* dx_all = nullptr;     // [L][rows][R]: d x_out of block l
+  struct WgPlan { int B, T; bool drop; TcWgGroupPlan plan; };
+  std::vector<WgPlan> wg_plans;
+  std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
+  int wg_force_split = 0, wg_pair_tiles = 1;   // WN_TC_GROUP_SPLIT=n / WN_TC_GROUP_NH2=0: A/B switches
   int use_merged_finish = 0;  // WN_TC_MERGED_FINISH=1: one finish launch for both wgrads of a block. Measured SLOWER on C2 (7.48 vs
                               // 7.38 ms/step: the deferred partials fall out of L2 before the merged finish reads them) -> off
   // every weight re-pack as one launch: job table recorded on the first wn_params_changed (buffers never move)
@@ -390,7 +400,10 @@ static void layout_buffers(wn_handle* h) {
   h->dxA = W.take(rows * R * es);
   h->dxB = W.take(rows * R * es);
   h->dotmp = W.take(rows * R * es);
-  if (bf && !h->alias_skip && h->cfg.use_skip) {
+  if (h->use_group_wgrad) {
+    h->dz_all = W.take((size_t)L * rows * 2 * D * es);
+    h->dx_all = W.take((size_t)L * rows * R * es);
+  } else if (bf && !h->alias_skip && h->cfg.use_skip) {
     h->dcatA = W.take(rows * (size_t)(R + h->S) * es);
     h->dcatB = W.take(rows * (size_t)(R + h->S) * es);
   }
@@ -565,6 +578,23 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
       if (hc.cin % 64 != 0) { set_err("bf16 tier needs head widths that are multiples of 64"); delete h; return WN_ERR_UNSUPPORTED; }
   }
 
+  // ---- grouped weight gradients: bf16 tier, separate skip projection (or none), widths in whole 256-channel pair tiles
+  // (skip_channels=None with use_skip adds d x_out + d skip into a shared scratch buffer: per-block launches there)
+  if (c.precision == WN_BF16 && !(h->alias_skip && c.use_skip)) {
+    const char* e = getenv("WN_TC_GROUP_WGRAD");
+    bool ok = !(e && e[0] == '0') && h->R % 256 == 0 && h->D % 256 == 0 && h->K <= TC_MAX_SEG;
+    for (auto& b : h->blocks) if (b.has_skip && h->S % 256 != 0) ok = false;
+    if (ok) {
+      // d z and d x_out of every block stay resident: (2D + R) bf16 per row and block
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const double extra = (double)h->L * h->maxB * h->maxT * (2.0 * h->D + h->R) * 2.0;
+      if (extra > 0.25 * (double)free_b) ok = false;
+    }
+    h->use_group_wgrad = ok ? 1 : 0;
+    { const char* s = getenv("WN_TC_GROUP_SPLIT"); if (s) h->wg_force_split = atoi(s); }
+    { const char* s = getenv("WN_TC_GROUP_NH2"); if (s && s[0] == '0') h->wg_pair_tiles = 0; }
+  }
   // ---- allocate
   h->pack.dry = true; h->ws.dry = true;
   layout_buffers(h);
@@ -638,6 +668,7 @@ extern "C" void wn_destroy(wn_handle* h) {
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   for (void* a : h->gen.allocs) cudaFree(a);
+  for (auto& wp : h->wg_plans) wp.plan.release();
   cudaFree(h->d_pack_jobs);
   cudaFree(h->opt_m); cudaFree(h->opt_v); cudaFree(h->opt_chunks); cudaFree(h->opt_var_first);
   cudaFree(h->opt_partial); cudaFree(h->opt_scale); cudaFree(h->opt_norms);
@@ -1234,7 +1265,10 @@ struct BwdSide {
 
 template <class T>
 static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in, const void* dxout, int ldxo, const void* dskip, int ldsk,
-                          void* dx_in, int ldxi, int B, int Tn, float l2coef, void* dzbuf = nullptr, const BwdSide* sd = nullptr) {
+                          void* dx_in, int ldxi, int B, int Tn, float l2coef, void* dzbuf = nullptr, const BwdSide* sd = nullptr,
+                          bool group = false) {
+  // group: the weight gradients of conv1, conv_skip and the gated conv are not launched here; their operands stay in
+  // per-block buffers and the problems are appended to h->wg_jobs for the grouped launch (gemm_tc_wgroup.cuh)
   BlockP& b = h->blocks[l];
   if (!dzbuf) dzbuf = h->dz;
   const int depth = (int)b.stack.size();
@@ -1263,7 +1297,33 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
   const bool side1 = sd != nullptr && d_o != h->dotmp;
   cudaStream_t s1 = side1 ? sd->side : st;
   if (side1) CK(cudaStreamWaitEvent(sd->side, sd->ev_in, 0));
-  if (cat) {
+  if (group) {
+    if constexpr (sizeof(T) == 2) {
+      const bool l2 = h->cfg.l2_reg_factor > 0.f;
+      if (d_o) {
+        TcWgJobDesc j{};
+        j.A = (const bf16*)g_l; j.lda = D; j.cin = D; j.ntaps = 1; j.shift[0] = 0;
+        j.G = (const bf16*)d_o; j.ldg = ld_o; j.N = R;
+        j.dst = G_(h, b.conv1.w_idx); j.w = l2 ? P_(h, b.conv1.w_idx) : nullptr; j.bias = G_(h, b.conv1.b_idx);
+        h->wg_jobs.push_back(j);
+      } else {
+        cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
+        cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
+      }
+      if (b.has_skip) {
+        if (dskip) {
+          TcWgJobDesc j{};
+          j.A = (const bf16*)g_l; j.lda = D; j.cin = D; j.ntaps = 1; j.shift[0] = 0;
+          j.G = (const bf16*)dskip; j.ldg = ldsk; j.N = S;
+          j.dst = G_(h, b.conv_skip.w_idx); j.w = l2 ? P_(h, b.conv_skip.w_idx) : nullptr; j.bias = G_(h, b.conv_skip.b_idx);
+          h->wg_jobs.push_back(j);
+        } else {
+          cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
+          cudaMemsetAsync(G_(h, b.conv_skip.b_idx), 0, h->params[b.conv_skip.b_idx].count * 4, st);
+        }
+      }
+    }
+  } else if (cat) {
     WgradH w{};
     w.B = B; w.T = Tn; w.N = R + S; w.G = dxout; w.ldg = ldxo; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
     w.dst = G_(h, b.conv1.w_idx); w.w = P_(h, b.conv1.w_idx); w.l2coef = l2coef; w.bias_dst = G_(h, b.conv1.b_idx);
@@ -1283,7 +1343,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
     cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
   }
-  if (b.has_skip && !cat) {
+  if (b.has_skip && !cat && !group) {
     if (dskip) {
       WgradH w{};
       w.B = B; w.T = Tn; w.N = S; w.G = dskip; w.ldg = ldsk; w.nseg = 1; w.seg[0] = SegH{g_l, D, 0, D};
@@ -1331,7 +1391,17 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     const int a_w = j == 0 ? R : D;
     // weight grad: rows (k, cin) <- taps of a_in shifted by -(K-1-k)*d ; the bias grad (and the
     // conditioning per-batch sums for the gated conv) are the column sums of the same G
-    {
+    if (group && j == depth - 1) {
+      if constexpr (sizeof(T) == 2) {
+        TcWgJobDesc jd{};
+        jd.A = (const bf16*)a_in; jd.lda = a_w; jd.cin = c.cin; jd.ntaps = c.K;
+        for (int k = 0; k < c.K; ++k) jd.shift[k] = -(c.K - 1 - k) * c.dil;
+        jd.G = (const bf16*)dcur; jd.ldg = dcw; jd.N = c.cout;
+        jd.dst = G_(h, c.w_idx); jd.w = h->cfg.l2_reg_factor > 0.f ? P_(h, c.w_idx) : nullptr; jd.bias = G_(h, c.b_idx);
+        if (b.has_cond) { jd.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; jd.ldpb = 2 * D; }
+        h->wg_jobs.push_back(jd);
+      }
+    } else {
       WgradH w{};
       w.bias_dst = G_(h, c.b_idx);
       if (j == depth - 1 && b.has_cond) { w.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; w.ldpb = 2 * D; }
@@ -1469,9 +1539,14 @@ template <class T>
 static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx, const float* cond_in, int B, int Tn, float l2coef) {
   const wn_config& c = h->cfg;
   // (bf16 tier only: the fp32 tier's wgrad / column-sum scratch buffers are not duplicated for a second stream)
-  const bool use_side = sizeof(T) == 2 && h->use_side && h->prof_tag == 0 && h->side_stream != nullptr;
+  const bool group = sizeof(T) == 2 && h->use_group_wgrad;
+  const bool use_side = sizeof(T) == 2 && h->use_side && h->prof_tag == 0 && h->side_stream != nullptr && !group;
   const bool cat = sizeof(T) == 2 && h->dcatA != nullptr;
   const int ldc = h->R + h->S;
+  const size_t rows_cap = (size_t)h->maxB * h->maxT;
+  auto dz_of = [&](int l) -> void* { return (T*)h->dz_all + (size_t)l * rows_cap * 2 * h->D; };
+  auto dx_of = [&](int l) -> void* { return (T*)h->dx_all + (size_t)l * rows_cap * h->R; };
+  h->wg_jobs.clear();
   // ---- head
   const void* dcur = h->dlogits;
   int dw = h->ldd;
@@ -1501,7 +1576,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       dst = (T*)h->dcatA + h->R;
       ep.out = (T*)dst; ep.ldo = ldc; ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(ldc);
     } else {
-      dst = c.use_skip ? h->dskip : h->dxA;
+      dst = c.use_skip ? h->dskip : (group ? dx_of(h->L - 1) : h->dxA);
       ep.out = (T*)dst; ep.ldo = hc.cin; ep.y = nullptr; ep.act = ACT_LINEAR; ep.vec = vec_ok<T>(hc.cin);
     }
     RET((run_conv_gemm<T, EpiActBwd<T, T>>(h, st, CLS_GEMM, g, ep)));
@@ -1528,15 +1603,47 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     dxout = cur; ld_dx = ldc;
   } else {
     const void* dskip = c.use_skip ? h->dskip : nullptr;
-    dxout = c.use_skip ? nullptr : h->dxA;
+    dxout = c.use_skip ? nullptr : (group ? dx_of(h->L - 1) : h->dxA);
     for (int l = h->L - 1; l >= 0; --l) {
       const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
-      void* dx_in = (dxout == h->dxA) ? h->dxB : h->dxA;
+      // grouped weight gradients: d x_out and d z of every block keep their own buffers until the grouped launch below
+      void* dx_in = group ? (l > 0 ? dx_of(l - 1) : h->dxA) : ((dxout == h->dxA) ? h->dxB : h->dxA);
       BwdSide sd; const BwdSide* sdp = side_setup(h, st, l, use_side, &sd);
-      RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef, (l & 1) ? h->dz2 : h->dz, sdp));
+      RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef, group ? dz_of(l) : ((l & 1) ? h->dz2 : h->dz), sdp,
+                            group));
       dxout = dx_in;
     }
     ld_dx = h->R;
+  }
+  if constexpr (sizeof(T) == 2) {
+    if (group && !h->wg_jobs.empty()) {
+      // ---- every block's conv1 / conv_skip / gated-conv weight gradients in ONE launch (+ one finish)
+      TcWgGroupPlan* plan = nullptr;
+      for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active) plan = &wp.plan;
+      if (!plan) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs != cudaStreamCaptureStatusNone) { set_err("grouped wgrad: no plan for (%d, %d) while capturing", B, Tn); return WN_ERR_STATE; }
+        if (h->wg_plans.size() >= 4) { CK(cudaStreamSynchronize(st)); for (auto& wp : h->wg_plans) wp.plan.release(); h->wg_plans.clear(); }
+        h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, TcWgGroupPlan{}});
+        plan = &h->wg_plans.back().plan;
+        int r = tc_wgrad_group_build(h->tmaps, h->wg_jobs, B, Tn, h->wg_force_split, h->wg_pair_tiles != 0, plan);
+        if (r != 0) { h->wg_plans.pop_back(); set_err("grouped wgrad plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+      }
+      {
+        struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, "wgrad_group");
+        {
+          LaunchScope ls(h, st, CLS_DILATED);
+          int r = tc_wgrad_group_launch(st, *plan);
+          if (r != 0) { set_err("grouped wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+        }
+        {
+          LaunchScope ls(h, st, CLS_DILATED);
+          int r = tc_wgrad_group_finish_launch(st, *plan, l2coef);
+          if (r != 0) { set_err("grouped wgrad finish failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+        }
+      }
+    }
   }
   // join: every side-stream wgrad (and its finish kernel) is complete before anything below reads the gradients
   if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
