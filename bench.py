@@ -25,6 +25,10 @@ if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
 METRIC = 'audio samples/sec fwd+bwd WaveNet stack'
+# dram__bytes_read + write per launch, mean over the launches of the dilated-conv kernel class in one C2 step (ncu, cold cache,
+# profiles/launches_r1_c2_v5_summary.txt): 30 fused block forwards (93.9 MB), 30 dgrads (102.1 MB), the grouped weight-gradient
+# launches (5.44 GB together) and their finish (0.22 GB) = 11.54 GB over 68 launches
+TRAFFIC_C2 = 1.70e8
 UNIT = 'samples/s'
 
 
@@ -239,6 +243,9 @@ def main():
   sync_all()
   ms_total = max_over_ranks(e0.elapsed_time(e1))
   launches = int(h.lib.wn_last_launch_count(h.h)) * args.steps
+  import ctypes as C
+  side_l = C.c_int(0)
+  wg_tiles = int(h.lib.wn_grouped_wgrad_tiles(h.h, C.byref(side_l)))   # of the timed (graph-replayed) step
   clocks = sampler.stop() if sampler else None
   loss_last = float(loss_t[0].item())
 
@@ -284,7 +291,9 @@ def main():
     h.lib.wn_profile_end(h.h, C.byref(ms), C.byref(n))
     prof[name] = (ms.value / args.profile_steps, n.value // args.profile_steps)
   rows = B_local * T
-  dil_flops_step = 3.0 * flops['dilated'] * rows
+  # grouped weight gradients: ONE launch (+ side launches) computes the gated-conv, conv1, conv_skip and head filter
+  # gradients as 256 x 256 tiles; the launch is timed in this class, so all of its products count as the class's work
+  dil_flops_step = (2.0 * flops['dilated'] + (wg_tiles * 2.0 * 256 * 256 if wg_tiles else flops['dilated'])) * rows
   # the fused block-forward kernel (gated conv + gate + conv1 + residual in one launch) is timed in this class: its
   # conv1 products are algorithmic work of the class too (forward only; their adjoints run in other kernels)
   fused_blocks = int(h.lib.wn_fused_forward_blocks(h.h))
@@ -303,11 +312,13 @@ def main():
               # dram__bytes_read+write per launch, mean over the class's kernels, from one `ncu --set full` capture of the C2
               # step (cold cache; profiles/ncu_full_r1e_c2_{blockfwd,bwd}.txt): fused block forward 98.0 MB, dgrad 110.5 MB,
               # dilated wgrad 107.5 MB, its finish 19.1 MB.  Only valid for the default workload.
-              'traffic': 8.38e7 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and fused_blocks) else None,
+              'traffic': TRAFFIC_C2 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and fused_blocks and wg_tiles) else None,
               'kernel': ('tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ' if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + ')
-              + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'
+              + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + '
+              + ('tc_wgrad_group_kernel (+ finish): gated-conv, conv1, conv_skip and head filter gradients of all blocks in one launch'
+                 if wg_tiles else 'tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs')
               if precision == 'bf16' else 'conv_gemm_simt + wgrad_simt on the dilated convs',
-              'launches_per_step': dil_launches, 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
+              'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles, 'wgrad_side_launches': int(side_l.value), 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
               'ms_per_step_in_kernel_eager_events': dil_ms_eager, 'ms_per_step_all_launches_eager_events': prof['all'][0],
               'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
               'share_of_step': share}

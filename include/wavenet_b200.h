@@ -205,6 +205,10 @@ int64_t wn_last_launch_count(const wn_handle* h);
 /* accumulate CUDA-event time of one kernel class over subsequent steps: tag 0 = off,
  * 1 = dilated-conv GEMMs (fwd+dgrad+wgrad), 2 = all GEMMs, 3 = loss/head reductions */
 int wn_fused_forward_blocks(const wn_handle* h);  /* blocks of the last forward that ran as one fused gate+conv1 launch */
+/* 256x256 weight-gradient tiles (conv1, conv_skip, gated conv, head; tape.gradient of model.py:335) that the last training
+ * step computed in the grouped launch behind the dgrad chain; 0 = per-block launches. side_launches (may be null): how many
+ * of the launches ran beside the chain on the SMs it leaves idle */
+int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches);
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
 /* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a

@@ -44,6 +44,13 @@ BF16_MODELS = {
   'fused128_multidil_cond': dict(channels=128, blocks=2, layers_per_block=2, dilation_bound=8, skip_channels=128, activation='tanh',
                                  final_layers_channels=[128], conditioning='global', mapping_layers=[8], mapping_activation='tanh'),
   'fused256_k3_alias': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=9, kernel_size=3, final_layers_channels=[128]),
+  # shapes whose block weight gradients take the grouped launch (gemm_tc_wgroup.cuh): R, D, S multiples of 256
+  'group256_cond_l2': dict(channels=256, blocks=3, layers_per_block=1, dilation_bound=4, skip_channels=256, final_layers_channels=[256],
+                           activation='tanh', conditioning='global', mapping_layers=[8], mapping_activation='tanh', l2_reg_factor=0.01),
+  'group256_noskip_k3': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=9, kernel_size=3, use_skip=False,
+                             final_layers_channels=[128]),
+  'group256_multidil': dict(channels=256, blocks=2, layers_per_block=2, dilation_bound=8, skip_channels=256, final_layers_channels=[128],
+                            activation='tanh'),
   'unfused256_nores': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=4, skip_channels=128, use_residual=False,
                            final_layers_channels=[128]),
 }

@@ -272,6 +272,16 @@ static inline const CUtensorMap* tc_atom_map(TmapCache& tc, const bf16* A, int l
   return tc.get(A, 4, dims, str, box);
 }
 
+// Persistent kernels walk their tiles round-robin: with 256 tiles on 74 CTA pairs the last of 4 rounds keeps 34 pairs busy.
+// The same 4 rounds fit on 64 pairs; the SMs left over can run other work (the side-stream weight gradients) meanwhile.
+// g_tc_balance: 0 = always the whole GPU, 1 = the fewest CTAs (pairs) that keep the number of rounds.
+static int g_tc_balance = 0;
+static inline int tc_balanced_slots(int tiles, int slots) {
+  if (!g_tc_balance || tiles <= slots) return slots;
+  const int rounds = (tiles + slots - 1) / slots;
+  return (tiles + rounds - 1) / rounds;
+}
+
 template <class Epi, int BN, int NEPI>
 static int tc_conv_gemm_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc& d, const typename Epi::Params& ep) {
   using Cfg = TcGemmCfg<BN>;
@@ -782,7 +792,7 @@ static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGe
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
     attr_done = true;
   }
-  const int slots = tc_num_sms() / CG;      // one CTA (or CTA pair) per SM (pair of SMs of a TPC)
+  const int slots = tc_balanced_slots(p.num_tiles, tc_num_sms() / CG);      // one CTA (or CTA pair) per SM (pair of SMs of a TPC)
   const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;

@@ -456,7 +456,7 @@ static int tc_block_fwd_launch(TmapCache& tc, cudaStream_t st, const TcBlockDesc
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
     attr_done = true;
   }
-  const int slots = tc_num_sms() / 2;
+  const int slots = tc_balanced_slots(p.num_mtiles, tc_num_sms() / 2);
   const int grid = (p.num_mtiles < slots ? p.num_mtiles : slots) * 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;

@@ -35,6 +35,7 @@ struct TcWgGroupParams {
   const TcWgUnit* units;
   float* cs;
   int chunks_t;              // ceil(T / 64)
+  int unit_base;             // this launch works on units [unit_base, unit_base + gridDim.x / 2)
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -54,7 +55,7 @@ tc_wgrad_group_kernel(const __grid_constant__ CUtensorMap tmP, const TcWgGroupPa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
-  const TcWgUnit u = p.units[blockIdx.x >> 1];
+  const TcWgUnit u = p.units[p.unit_base + (blockIdx.x >> 1)];
   const int nchunks = u.c_end - u.c_begin;
   const bool cs_on[2] = {u.cs_r1 > u.cs_r0 && u.cs_row0[0] >= 0, u.nh > 1 && u.cs_r1 > u.cs_r0 && u.cs_row0[1] >= 0};
   const bool do_cs = cs_on[0] || cs_on[1];
@@ -297,6 +298,8 @@ struct TcWgJobDesc {         // one weight-gradient problem dW[k * Cin + c, n] =
   float* dst; const float* w;            // [ntaps * cin][N] fp32 gradient (Keras layout), weights for L2 (or null)
   float* bias;                           // [N] column sums of G, or null
   float* per_batch; int ldpb;            // [B][ldpb] per-batch column sums of G, or null
+  int group = -1;                        // -1: the launch at the end of the backward pass; g >= 0: side launch g (one per block
+                                         // that hands its weight gradients to the SMs the dgrad chain leaves idle)
   // several problems may share one G (conv_skip of every block reads d skip): the column sums are computed once, by the
   // first problem that names the tensor, and the finish writes them to every bias that asks for them
 };
@@ -304,6 +307,8 @@ struct TcWgJobDesc {         // one weight-gradient problem dW[k * Cin + c, n] =
 struct TcWgGroupPlan {
   int B = 0, T = 0;
   int nunits = 0, ntiles = 0, ncs = 0, nsplit = 1;
+  int final_units = 0;                                   // units [0, final_units): the launch at the end
+  std::vector<std::pair<int, int>> side;                 // per side group: (first unit, units)
   CUtensorMap* d_maps = nullptr; TcWgUnit* d_units = nullptr; TcWgFinTile* d_tiles = nullptr; TcWgFinCs* d_css = nullptr;
   float* d_partial = nullptr; float* d_cs = nullptr;
   CUtensorMap tmP;
@@ -316,7 +321,7 @@ struct TcWgGroupPlan {
 // every problem must have cin % 256 == 0 and N % 256 == 0
 static inline bool tc_wgrad_group_ok(int cin, int N) { return cin % 256 == 0 && N % 256 == 0; }
 
-static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& jobs, int B, int T, int force_split, bool pair_tiles, TcWgGroupPlan* plan) {
+static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& jobs, int B, int T, int force_split, bool pair_tiles, int side_pairs, TcWgGroupPlan* plan) {
   plan->release();
   plan->B = B; plan->T = T;
   std::vector<CUtensorMap> maps;
@@ -333,7 +338,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   };
   const int chunks_t = (T + 63) / 64, total_chunks = B * chunks_t;
   // ---- 256 x 256 output tiles, column-sum entries
-  struct Tile { int a_map, a_atom, shift, g_map, g_atom; int cs_entry; int cs_r0, cs_r1; bool used; };
+  struct Tile { int a_map, a_atom, shift, g_map, g_atom; int cs_entry; int cs_r0, cs_r1; bool used; int group; };
   std::vector<Tile> tl;
   std::vector<TcWgFinTile> tiles;
   std::vector<TcWgFinCs> css;
@@ -374,7 +379,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
           t.a_map = am; t.a_atom = mt * 4; t.shift = j.shift[k]; t.g_map = gm; t.g_atom = nt * 4;
           t.cs_entry = own_cs ? cs0 + nt : -1;
           t.cs_r0 = (64 * sh) / sharers; t.cs_r1 = (64 * (sh + 1)) / sharers;
-          t.used = false;
+          t.used = false; t.group = j.group;
           tl.push_back(t);
         }
     if (want_cs && !own_cs) {
@@ -402,7 +407,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
       for (int k = i + 1; k < ntiles && k < i + 64; ++k) {
         if (tl[k].used) continue;
         const Tile &x = tl[i], &y = tl[k];
-        if (x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift != y.shift) continue;
+        if (x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift != y.shift || x.group != y.group) continue;
         const bool cx = x.cs_entry >= 0, cy = y.cs_entry >= 0;
         if (cx && cy && (x.cs_r0 != y.cs_r0 || x.cs_r1 != y.cs_r1)) continue;
         uu.t[1] = k; uu.nh = 2; tl[k].used = true;
@@ -410,16 +415,21 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
       }
     ut.push_back(uu);
   }
-  // ---- splits: simulate the block scheduler (units in launch order onto the earliest free CTA pair)
+  // ---- launch order: the units of the final launch first, then every side group's units side by side
+  int ngroups = 0;
+  for (const auto& t : tl) if (t.group + 1 > ngroups) ngroups = t.group + 1;
+  std::vector<std::vector<int>> by_group(ngroups + 1);     // [0]: final, [1 + g]: side group g
+  for (int i = 0; i < (int)ut.size(); ++i) by_group[tl[ut[i].t[0]].group + 1].push_back(i);
+  // ---- splits of the final launch: simulate the block scheduler (units in launch order onto the earliest free CTA pair)
   const int npairs = tc_num_sms() / 2;
   int nsplit = 1;
   if (force_split > 0) nsplit = force_split;
-  else {
+  else if (!by_group[0].empty()) {
     double best = 1e30;
     for (int s = 1; s <= 8; ++s) {
       if (s > total_chunks) break;
       std::vector<double> free_at(npairs, 0.0);
-      for (int z0 = 0; z0 < (int)ut.size(); ++z0)
+      for (int z0 : by_group[0])
         for (int z = 0; z < s; ++z) {
           auto it = std::min_element(free_at.begin(), free_at.end());
           // mainloop chunks x products (+ a per-unit fixed cost: fill, partial store and its later reduction, in chunk units)
@@ -431,34 +441,57 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   }
   if (nsplit > total_chunks) nsplit = total_chunks;
   if (nsplit > 8) nsplit = 8;
-  const int cps = (total_chunks + nsplit - 1) / nsplit;
-  nsplit = (total_chunks + cps - 1) / cps;
-  for (int i = 0; i < ntiles; ++i) { tiles[i].tile0 = i * nsplit; tiles[i].nsplit = nsplit; }
+  auto norm_split = [&](int s) { const int cps = (total_chunks + s - 1) / s; return (total_chunks + cps - 1) / cps; };
+  nsplit = norm_split(nsplit);
+  std::vector<int> split_of(ngroups + 1, nsplit);
+  for (int g = 0; g < ngroups; ++g) {
+    // a side launch never asks for more CTA pairs than the dgrad chain leaves free
+    const int n = (int)by_group[1 + g].size();
+    int s = n > 0 ? side_pairs / n : 1;
+    if (s < 1) s = 1;
+    if (s > 8) s = 8;
+    if (s > total_chunks) s = total_chunks;
+    split_of[1 + g] = norm_split(s);
+  }
+  {
+    int t0 = 0;
+    for (int i = 0; i < ntiles; ++i) { const int s = split_of[tl[i].group + 1]; tiles[i].tile0 = t0; tiles[i].nsplit = s; t0 += s; }
+  }
   std::vector<TcWgUnit> units;
   int cs_rows = 0;
-  for (const auto& uu : ut)
-    for (int z = 0; z < nsplit; ++z) {
-      TcWgUnit u{};
-      const Tile& t0 = tl[uu.t[0]];
-      u.a_map = t0.a_map; u.a_atom = t0.a_atom; u.shift = t0.shift; u.nh = uu.nh;
-      u.c_begin = z * cps; u.c_end = std::min(total_chunks, (z + 1) * cps);
-      const int b0 = u.c_begin / chunks_t, b1 = (u.c_end - 1) / chunks_t;
-      u.cs_r0 = u.cs_r1 = 0;
-      for (int hh = 0; hh < 2; ++hh) {
-        const Tile& t = tl[uu.t[hh] >= 0 ? uu.t[hh] : uu.t[0]];
-        u.g_map[hh] = t.g_map; u.g_atom[hh] = t.g_atom; u.out_tile[hh] = uu.t[hh] >= 0 ? uu.t[hh] * nsplit + z : 0;
-        u.cs_row0[hh] = -1;
-        if (uu.t[hh] >= 0 && t.cs_entry >= 0 && t.cs_r1 > t.cs_r0) {
-          u.cs_r0 = t.cs_r0; u.cs_r1 = t.cs_r1;
-          TcWgFinCs& e = css[t.cs_entry];
-          if (e.nsrc >= TC_WG_MAX_CS_SRC) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: too many column-sum sources"); return -22; }
-          u.cs_row0[hh] = cs_rows;
-          e.row0[e.nsrc] = cs_rows; e.b_first[e.nsrc] = b0; e.nb[e.nsrc] = b1 - b0 + 1; e.nsrc++;
-          cs_rows += b1 - b0 + 1;
+  plan->side.assign(ngroups, std::make_pair(0, 0));
+  for (int gi = 0; gi <= ngroups; ++gi) {
+    const int first = (int)units.size();
+    const int gs = split_of[gi];
+    const int cps = (total_chunks + gs - 1) / gs;
+    for (int ui : by_group[gi]) {
+      const UnitT& uu = ut[ui];
+      for (int z = 0; z < gs; ++z) {
+        TcWgUnit u{};
+        const Tile& t0 = tl[uu.t[0]];
+        u.a_map = t0.a_map; u.a_atom = t0.a_atom; u.shift = t0.shift; u.nh = uu.nh;
+        u.c_begin = z * cps; u.c_end = std::min(total_chunks, (z + 1) * cps);
+        const int b0 = u.c_begin / chunks_t, b1 = (u.c_end - 1) / chunks_t;
+        u.cs_r0 = u.cs_r1 = 0;
+        for (int hh = 0; hh < 2; ++hh) {
+          const Tile& t = tl[uu.t[hh] >= 0 ? uu.t[hh] : uu.t[0]];
+          u.g_map[hh] = t.g_map; u.g_atom[hh] = t.g_atom; u.out_tile[hh] = uu.t[hh] >= 0 ? tiles[uu.t[hh]].tile0 + z : 0;
+          u.cs_row0[hh] = -1;
+          if (uu.t[hh] >= 0 && t.cs_entry >= 0 && t.cs_r1 > t.cs_r0) {
+            u.cs_r0 = t.cs_r0; u.cs_r1 = t.cs_r1;
+            TcWgFinCs& e = css[t.cs_entry];
+            if (e.nsrc >= TC_WG_MAX_CS_SRC) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: too many column-sum sources"); return -22; }
+            u.cs_row0[hh] = cs_rows;
+            e.row0[e.nsrc] = cs_rows; e.b_first[e.nsrc] = b0; e.nb[e.nsrc] = b1 - b0 + 1; e.nsrc++;
+            cs_rows += b1 - b0 + 1;
+          }
         }
+        units.push_back(u);
       }
-      units.push_back(u);
     }
+    if (gi == 0) plan->final_units = (int)units.size();
+    else plan->side[gi - 1] = std::make_pair(first, (int)units.size() - first);
+  }
   for (auto& e : css)
     if (e.nsrc < 0) {
       const TcWgFinCs& o = css[-1 - e.nsrc];
@@ -473,7 +506,8 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   };
   bool ok = up((void**)&plan->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap)) && up((void**)&plan->d_units, units.data(), units.size() * sizeof(TcWgUnit)) &&
             up((void**)&plan->d_tiles, tiles.data(), tiles.size() * sizeof(TcWgFinTile)) && up((void**)&plan->d_css, css.data(), css.size() * sizeof(TcWgFinCs));
-  const size_t npart = (size_t)ntiles * nsplit;
+  size_t npart = 0;
+  for (int i = 0; i < ntiles; ++i) npart += (size_t)tiles[i].nsplit;
   ok = ok && cudaMalloc((void**)&plan->d_partial, npart * 65536 * 4) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&plan->d_cs, (size_t)(cs_rows > 0 ? cs_rows : 1) * 256 * 4) == cudaSuccess;
   if (!ok) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: plan allocation failed: %s", cudaGetErrorString(cudaGetLastError())); plan->release(); return -23; }
@@ -486,7 +520,8 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   return 0;
 }
 
-static int tc_wgrad_group_launch(cudaStream_t st, const TcWgGroupPlan& plan) {
+static int tc_wgrad_group_launch(cudaStream_t st, const TcWgGroupPlan& plan, int unit_base, int nunits) {
+  if (nunits <= 0) return 0;
   using Cfg = TcWgradPairCfg<256, 2>;
   auto kern = tc_wgrad_group_kernel;
   static bool attr_done = false;
@@ -496,9 +531,9 @@ static int tc_wgrad_group_launch(cudaStream_t st, const TcWgGroupPlan& plan) {
     attr_done = true;
   }
   TcWgGroupParams p{};
-  p.maps = plan.d_maps; p.units = plan.d_units; p.cs = plan.d_cs; p.chunks_t = (plan.T + 63) / 64;
+  p.maps = plan.d_maps; p.units = plan.d_units; p.cs = plan.d_cs; p.chunks_t = (plan.T + 63) / 64; p.unit_base = unit_base;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * plan.nunits); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(2 * nunits); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 2);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan.tmP, p);

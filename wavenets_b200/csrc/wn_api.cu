@@ -216,6 +216,10 @@ struct wn_handle {
   struct WgPlan { int B, T; bool drop; TcWgGroupPlan plan; };
   std::vector<WgPlan> wg_plans;
   std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
+  int wg_last_tiles = 0, wg_last_side = 0;   // grouped tiles / side launches of the last backward pass
+  int wg_cur_group = -1;              // side group of the jobs block_backward appends (-1: final launch)
+  int wg_side_every = 5;              // every n-th block hands its weight gradients to a side launch (WN_TC_GROUP_SIDE_EVERY, 0 = off)
+  cudaEvent_t ev_wg_side = nullptr;
   int wg_force_split = 0, wg_pair_tiles = 1;   // WN_TC_GROUP_SPLIT=n / WN_TC_GROUP_NH2=0: A/B switches
   int use_merged_finish = 0;  // WN_TC_MERGED_FINISH=1: one finish launch for both wgrads of a block. Measured SLOWER on C2 (7.48 vs
                               // 7.38 ms/step: the deferred partials fall out of L2 before the merged finish reads them) -> off
@@ -594,6 +598,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
     h->use_group_wgrad = ok ? 1 : 0;
     { const char* s = getenv("WN_TC_GROUP_SPLIT"); if (s) h->wg_force_split = atoi(s); }
     { const char* s = getenv("WN_TC_GROUP_NH2"); if (s && s[0] == '0') h->wg_pair_tiles = 0; }
+    { const char* s = getenv("WN_TC_GROUP_SIDE_EVERY"); if (s) h->wg_side_every = atoi(s); }
   }
   // ---- allocate
   h->pack.dry = true; h->ws.dry = true;
@@ -628,7 +633,9 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_TC_TILE_GATE_BWD"); if (e) h->tile_gate_bwd = atoi(e); }
   { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
+  { const char* e = getenv("WN_TC_BALANCE_GRID"); if (e) g_tc_balance = atoi(e); }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_wg_side, cudaEventDisableTiming);
   for (int i = 0; i < h->L; ++i) {
     cudaEvent_t a, b2, c2;
     cudaEventCreateWithFlags(&a, cudaEventDisableTiming); cudaEventCreateWithFlags(&b2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c2, cudaEventDisableTiming);
@@ -665,6 +672,7 @@ extern "C" void wn_destroy(wn_handle* h) {
   for (auto e : h->ev_blk_dz) cudaEventDestroy(e);
   for (auto e : h->ev_blk_done) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_wg_side) cudaEventDestroy(h->ev_wg_side);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   for (void* a : h->gen.allocs) cudaFree(a);
@@ -1305,6 +1313,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         j.A = (const bf16*)g_l; j.lda = D; j.cin = D; j.ntaps = 1; j.shift[0] = 0;
         j.G = (const bf16*)d_o; j.ldg = ld_o; j.N = R;
         j.dst = G_(h, b.conv1.w_idx); j.w = l2 ? P_(h, b.conv1.w_idx) : nullptr; j.bias = G_(h, b.conv1.b_idx);
+        j.group = h->wg_cur_group;
         h->wg_jobs.push_back(j);
       } else {
         cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
@@ -1316,6 +1325,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
           j.A = (const bf16*)g_l; j.lda = D; j.cin = D; j.ntaps = 1; j.shift[0] = 0;
           j.G = (const bf16*)dskip; j.ldg = ldsk; j.N = S;
           j.dst = G_(h, b.conv_skip.w_idx); j.w = l2 ? P_(h, b.conv_skip.w_idx) : nullptr; j.bias = G_(h, b.conv_skip.b_idx);
+          j.group = h->wg_cur_group;
           h->wg_jobs.push_back(j);
         } else {
           cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
@@ -1399,6 +1409,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         jd.G = (const bf16*)dcur; jd.ldg = dcw; jd.N = c.cout;
         jd.dst = G_(h, c.w_idx); jd.w = h->cfg.l2_reg_factor > 0.f ? P_(h, c.w_idx) : nullptr; jd.bias = G_(h, c.b_idx);
         if (b.has_cond) { jd.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; jd.ldpb = 2 * D; }
+        jd.group = h->wg_cur_group;
         h->wg_jobs.push_back(jd);
       }
     } else {
@@ -1547,6 +1558,25 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   auto dz_of = [&](int l) -> void* { return (T*)h->dz_all + (size_t)l * rows_cap * 2 * h->D; };
   auto dx_of = [&](int l) -> void* { return (T*)h->dx_all + (size_t)l * rows_cap * h->R; };
   h->wg_jobs.clear();
+  h->wg_last_tiles = 0; h->wg_last_side = 0;
+  // Side launches: the persistent chain kernels need ceil(tiles / pairs) rounds; the same rounds fit on fewer CTA pairs
+  // (256 tiles: 4 rounds on 74 or on 64 pairs), and the pairs left over run the weight gradients of every n-th block
+  // beside the chain.  The plan (unit ranges per side group) exists from the second call on; the first call launches
+  // every group at the end.
+  int side_pairs = 0;
+  if (group && h->use_side && h->side_stream != nullptr && h->wg_side_every > 0) {
+    const int pairs = tc_num_sms() / 2, tiles = B * cdiv(Tn, 256);
+    if (tiles > pairs) {
+      const int rounds = cdiv(tiles, pairs);
+      side_pairs = pairs - cdiv(tiles, rounds);
+    }
+    if (side_pairs < 6) side_pairs = 0;
+  }
+  auto side_group_of = [&](int l) -> int { return (side_pairs > 0 && (h->L - 1 - l) % h->wg_side_every == 0) ? (h->L - 1 - l) / h->wg_side_every : -1; };
+  TcWgGroupPlan* wplan = nullptr;
+  if (group) for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active) wplan = &wp.plan;
+  const bool side_now = wplan != nullptr && side_pairs > 0 && h->prof_tag == 0 && !wplan->side.empty();
+  g_tc_balance = side_now ? 1 : 0;
   // ---- head
   const void* dcur = h->dlogits;
   int dw = h->ldd;
@@ -1557,11 +1587,26 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     if (i > 0) { a_in = h->hact[i - 1]; a_w = h->head[i - 1].cout; }
     else if (c.use_skip) { a_in = h->skipsum; a_w = h->Sp; }
     else { a_in = h->xout[h->L - 1]; a_w = h->R; }
-    WgradH w{};
-    w.bias_dst = G_(h, hc.b_idx);
-    w.B = B; w.T = Tn; w.N = hc.cout; w.G = dcur; w.ldg = dw; w.nseg = 1; w.seg[0] = SegH{a_in, a_w, 0, hc.cin};
-    w.dst = G_(h, hc.w_idx); w.w = P_(h, hc.w_idx); w.l2coef = l2coef;
-    RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+    // (the head's d-activation buffers dlogits / dhA / dhB stay intact until the end of the pass when the head has <= 3 convs)
+    bool head_grouped = false;
+    if constexpr (sizeof(T) == 2) {
+      if (group && h->head.size() <= 3 && tc_wgrad_group_ok(hc.cin, hc.cout) && a_w == hc.cin) {
+        TcWgJobDesc j{};
+        j.A = (const bf16*)a_in; j.lda = a_w; j.cin = hc.cin; j.ntaps = 1; j.shift[0] = 0;
+        j.G = (const bf16*)dcur; j.ldg = dw; j.N = hc.cout;
+        j.dst = G_(h, hc.w_idx); j.w = c.l2_reg_factor > 0.f ? P_(h, hc.w_idx) : nullptr; j.bias = G_(h, hc.b_idx);
+        j.group = -1;
+        h->wg_jobs.push_back(j);
+        head_grouped = true;
+      }
+    }
+    if (!head_grouped) {
+      WgradH w{};
+      w.bias_dst = G_(h, hc.b_idx);
+      w.B = B; w.T = Tn; w.N = hc.cout; w.G = dcur; w.ldg = dw; w.nseg = 1; w.seg[0] = SegH{a_in, a_w, 0, hc.cin};
+      w.dst = G_(h, hc.w_idx); w.w = P_(h, hc.w_idx); w.l2coef = l2coef;
+      RET(run_wgrad<T>(h, st, CLS_GEMM, w));
+    }
     GemmH g;
     g.B = B; g.T = Tn; g.N = hc.cin; g.nseg = 1;
     g.seg[0] = SegH{dcur, dw, 0, (sizeof(T) == 2 && i + 1 == (int)h->head.size()) ? h->ldd : hc.cout};
@@ -1609,17 +1654,31 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       // grouped weight gradients: d x_out and d z of every block keep their own buffers until the grouped launch below
       void* dx_in = group ? (l > 0 ? dx_of(l - 1) : h->dxA) : ((dxout == h->dxA) ? h->dxB : h->dxA);
       BwdSide sd; const BwdSide* sdp = side_setup(h, st, l, use_side, &sd);
+      h->wg_cur_group = side_group_of(l);
       RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef, group ? dz_of(l) : ((l & 1) ? h->dz2 : h->dz), sdp,
                             group));
+      if constexpr (sizeof(T) == 2) {
+        if (side_now && h->wg_cur_group >= 0 && h->wg_cur_group < (int)wplan->side.size() && wplan->side[h->wg_cur_group].second > 0) {
+          // d z_l and d x_out_l are complete behind this block's kernels: its weight gradients start on the side stream
+          CK(cudaEventRecord(h->ev_blk_dz[l], st));
+          CK(cudaStreamWaitEvent(h->side_stream, h->ev_blk_dz[l], 0));
+          struct Label { wn_handle* h; Label(wn_handle* h_, const char* lb) : h(h_) { h->cur_label = lb; } ~Label() { h->cur_label = "misc"; } } lab(h, "wgrad_group");
+          LaunchScope ls(h, h->side_stream, CLS_DILATED);
+          int r = tc_wgrad_group_launch(h->side_stream, *wplan, wplan->side[h->wg_cur_group].first, wplan->side[h->wg_cur_group].second);
+          if (r != 0) { set_err("grouped wgrad side launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+          h->wg_last_side++;
+        }
+      }
       dxout = dx_in;
     }
+    h->wg_cur_group = -1;
     ld_dx = h->R;
   }
+  g_tc_balance = 0;
   if constexpr (sizeof(T) == 2) {
     if (group && !h->wg_jobs.empty()) {
       // ---- every block's conv1 / conv_skip / gated-conv weight gradients in ONE launch (+ one finish)
-      TcWgGroupPlan* plan = nullptr;
-      for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active) plan = &wp.plan;
+      TcWgGroupPlan* plan = wplan;
       if (!plan) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
@@ -1627,15 +1686,23 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
         if (h->wg_plans.size() >= 4) { CK(cudaStreamSynchronize(st)); for (auto& wp : h->wg_plans) wp.plan.release(); h->wg_plans.clear(); }
         h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, TcWgGroupPlan{}});
         plan = &h->wg_plans.back().plan;
-        int r = tc_wgrad_group_build(h->tmaps, h->wg_jobs, B, Tn, h->wg_force_split, h->wg_pair_tiles != 0, plan);
+        int r = tc_wgrad_group_build(h->tmaps, h->wg_jobs, B, Tn, h->wg_force_split, h->wg_pair_tiles != 0, side_pairs, plan);
         if (r != 0) { h->wg_plans.pop_back(); set_err("grouped wgrad plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
       }
       {
         struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, "wgrad_group");
         {
           LaunchScope ls(h, st, CLS_DILATED);
-          int r = tc_wgrad_group_launch(st, *plan);
+          h->wg_last_tiles = plan->ntiles;
+          // without side launches (first call of a shape, profiling passes, WN_SIDE_STREAM=0) the side groups' units, which
+          // follow the final group's in the table, run in the same launch
+          int r = tc_wgrad_group_launch(st, *plan, 0, side_now ? plan->final_units : plan->nunits);
           if (r != 0) { set_err("grouped wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+        }
+        if (side_now) {
+          // the side launches of this pass must be complete before the finish reads their partial tiles
+          CK(cudaEventRecord(h->ev_wg_side, h->side_stream));
+          CK(cudaStreamWaitEvent(st, h->ev_wg_side, 0));
         }
         {
           LaunchScope ls(h, st, CLS_DILATED);
@@ -2350,6 +2417,10 @@ extern "C" int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int l
 extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
 // number of blocks whose gated conv + conv1 ran as ONE fused launch in the last enqueued forward (0 = separate kernels)
 extern "C" int wn_fused_forward_blocks(const wn_handle* h) { return h ? h->fused_fwd_launches : 0; }
+extern "C" int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches) {
+  if (side_launches) *side_launches = h ? h->wg_last_side : 0;
+  return h ? h->wg_last_tiles : 0;
+}
 // per-launch record of the last wn_profile_end: returns the number of timed launches; i in [0,n): duration + label
 extern "C" int wn_profile_get(wn_handle* h, int i, double* ms, char* label, int label_len) {
   if (!h) return WN_ERR_VALUE;
