@@ -45,6 +45,7 @@ struct TcGemmDesc {
   int B, T, nseg; TcSeg seg[TC_MAX_SEG]; int n_outer; long long outer_stride;
   const bf16* W; int ktot; int N16; int tileN;
   int l2_a = 0, l2_in[2] = {0, 0}, l2_out[3] = {0, 0, 0};   // TC_L2_* codes: activation operand, epilogue inputs, outputs
+  int l2_seg[TC_MAX_SEG] = {-1, -1, -1, -1};                // per-segment override of l2_a (-1: none)
 };
 struct TcWgradDesc {
   int l2_a = 0, l2_g = 0;
@@ -338,6 +339,7 @@ struct TcStagedParams {
   int in_col[2];
   int out_col[3];
   unsigned long long pol_a, pol_w, pol_in[2], pol_out[3];   // L2 cache policies (TC_POL_*)
+  unsigned long long pol_seg[TC_MAX_SEG];                    // per-segment policy of the activation operand
 };
 
 // IN_PANELS: capacity of the epilogue-input ring in half-panels (slots = IN_PANELS / active inputs, decided at
@@ -444,6 +446,7 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
           for (int s = 0; s < p.nseg; ++s) {
             const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : (s == 2 ? &tmA2 : &tmA3));
             const int kseg = p.segK[s], tcoord = t0 + p.segShift[s];
+            const unsigned long long pol_as = sp.pol_seg[s];
             for (int k0 = 0; k0 < kseg; k0 += Cfg::BK) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -452,19 +455,19 @@ tc_conv_gemm_staged_kernel(const __grid_constant__ CUtensorMap tmA0, const __gri
 #else
               if (CG == 1) {
                 mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_4d_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
+                tma_load_4d_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, pol_as);
                 tma_load_2d_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0, sp.pol_w);
               } else {
                 // the leader's barrier counts the bytes of both CTAs' operand halves
 #if defined(TC_EXP_NO_W)
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::A_BYTES);
-                tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
+                tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, pol_as);
 #elif defined(TC_EXP_NO_A)
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
                 tma_load_2d_pair_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0 + (int)crank * (BN / 2), sp.pol_w);
 #else
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, sp.pol_a);
+                tma_load_4d_pair_h(sa, tm, &full_bar[stage], k0, tcoord, b, o, pol_as);
                 tma_load_2d_pair_h(sa + Cfg::A_BYTES, &tmW, &full_bar[stage], wk + k0, n0 + (int)crank * (BN / 2), sp.pol_w);
 #endif
               }
@@ -762,7 +765,8 @@ static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGe
   if (!mw) return -11;
   TcStagedParams sp{};
   sp.in_mask = in_mask;
-  sp.pol_a = tc_policy(d.l2_a); sp.pol_w = tc_policy(TC_L2_LAST);      // weights: every CTA re-reads them all kernel long
+  sp.pol_a = tc_policy(d.l2_a); sp.pol_w = tc_policy(TC_L2_LAST);
+  for (int s = 0; s < TC_MAX_SEG; ++s) sp.pol_seg[s] = tc_policy(d.l2_seg[s] >= 0 ? d.l2_seg[s] : d.l2_a);      // weights: every CTA re-reads them all kernel long
   for (int k = 0; k < 2; ++k) sp.pol_in[k] = tc_policy(d.l2_in[k]);
   for (int k = 0; k < 3; ++k) sp.pol_out[k] = tc_policy(d.l2_out[k]);
   const CUtensorMap* mo[3] = {nullptr, nullptr, nullptr};

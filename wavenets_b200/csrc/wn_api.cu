@@ -216,6 +216,7 @@ struct wn_handle {
   struct WgPlan { int B, T; bool drop; TcWgGroupPlan plan; };
   std::vector<WgPlan> wg_plans;
   std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
+  int dskip_l2_last = 0;
   int wg_last_tiles = 0, wg_last_side = 0;   // grouped tiles / side launches of the last backward pass
   int wg_cur_group = -1;              // side group of the jobs block_backward appends (-1: final launch)
   int wg_side_every = 5;              // every n-th block hands its weight gradients to a side launch (WN_TC_GROUP_SIDE_EVERY, 0 = off)
@@ -634,6 +635,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
   { const char* e = getenv("WN_TC_BALANCE_GRID"); if (e) g_tc_balance = atoi(e); }
+  { const char* e = getenv("WN_TC_DSKIP_LAST"); if (e) h->dskip_l2_last = atoi(e); }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_wg_side, cudaEventDisableTiming);
   for (int i = 0; i < h->L; ++i) {
@@ -825,6 +827,7 @@ struct GemmH {
   const float* W32 = nullptr; int Npad = 0;     // fp32: [ktot][Npad]
   const bf16* W16 = nullptr; int ktot16 = 0; int N16 = 0; int tile16 = 0;  // bf16: [N16][ktot16]
   int l2_a = 0, l2_in[2] = {0, 0}, l2_out[3] = {0, 0, 0};   // bf16 tier: L2 policy codes (TC_L2_*), see tc_common.cuh
+  int l2_seg[WN_MAX_SEG] = {-1, -1, -1, -1};                // per-segment override of l2_a
 };
 
 // bf16 tier: map the generic epilogue description onto the TMA-staged tcgen05 kernel (tc_epilogues.cuh);
@@ -882,6 +885,7 @@ static int run_conv_gemm(wn_handle* h, cudaStream_t st, int cls, const GemmH& g,
     for (int s = 0; s < g.nseg; ++s) d.seg[s] = TcSeg{(const bf16*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     d.W = g.W16; d.ktot = g.ktot16; d.N16 = g.N16; d.tileN = g.tile16;
     d.l2_a = g.l2_a;
+    for (int s = 0; s < g.nseg && s < TC_MAX_SEG; ++s) d.l2_seg[s] = g.l2_seg[s];
     for (int k = 0; k < 2; ++k) d.l2_in[k] = g.l2_in[k];
     for (int k = 0; k < 3; ++k) d.l2_out[k] = g.l2_out[k];
     int r = tc_dispatch<Epi>(h, st, d, ep);
@@ -1379,7 +1383,11 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     } else {
       if (use_o) g.seg[g.nseg++] = SegH{d_o, ld_o, 0, R};
       else koff = R;
-      if (use_s) g.seg[g.nseg++] = SegH{dskip, ldsk, 0, S};
+      if (use_s) {
+        // d skip is the same tensor for every block (model.py:236): ask L2 to keep it between the blocks' launches
+        if (group && h->dskip_l2_last) g.l2_seg[g.nseg] = TC_L2_LAST;
+        g.seg[g.nseg++] = SegH{dskip, ldsk, 0, S};
+      }
     }
     const int rs = R + (b.has_skip ? S : 0);
     g.W32 = b.Wdg ? b.Wdg + (size_t)koff * b.Dpad : nullptr; g.Npad = b.Dpad;
