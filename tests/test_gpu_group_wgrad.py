@@ -21,6 +21,8 @@ CASES = {
   'noskip_k3': (dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=9, kernel_size=3, use_skip=False, final_layers_channels=[128]), 2, 200),
   'multidil': (dict(channels=256, blocks=2, layers_per_block=2, dilation_bound=8, skip_channels=256, final_layers_channels=[128],
                     activation='leaky_relu'), 2, 257),
+  # skip_channels=None: the skip is conv1's output (d x_out + d skip feeds conv1's gradient); three dilations per block
+  'alias_multidil': (dict(channels=256, blocks=2, layers_per_block=3, dilation_bound=8, final_layers_channels=[128], activation='tanh'), 2, 300),
   'wide512': (dict(channels=256, dilation_channels=512, blocks=2, layers_per_block=1, dilation_bound=4, skip_channels=512,
                    final_layers_channels=[128]), 5, 130),
   'side_launches': (dict(channels=256, blocks=6, layers_per_block=1, dilation_bound=16, skip_channels=256, final_layers_channels=[256],

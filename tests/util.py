@@ -56,6 +56,11 @@ SMALL_MODELS = {
                    use_residual=False, kernel_size=3),
   'wide_ragged': dict(channels=40, blocks=2, layers_per_block=2, activation='sigmoid', dilation_bound=4,
                       final_layers_channels=[70], skip_channels=72, dilation_channels=36, bits=8),
+  # L2 on convs whose output nothing reads: conv1 of the last block under use_skip, conv_skip without use_skip —
+  # their data gradient is zero, the regulariser's is not (model.py:331-334)
+  'l2_skip': dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[8], l2_reg_factor=0.01, skip_channels=6),
+  'l2_unused_skip': dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[8], l2_reg_factor=0.01,
+                         skip_channels=6, use_skip=False),
   'l2': dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[8],
              l2_reg_factor=0.01, conditioning='global', mapping_layers=[4], mapping_activation='tanh'),
 }

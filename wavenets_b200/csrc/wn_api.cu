@@ -213,6 +213,8 @@ struct wn_handle {
   int use_group_wgrad = 0;
   void* dz_all = nullptr;     // [L][rows][2D]
   void* dx_all = nullptr;     // [L][rows][R]: d x_out of block l
+  void* do_all = nullptr;     // [L][rows][R]: d x_out + d skip of block l (skip_channels=None with use_skip: skip = conv1 output)
+  std::vector<std::vector<void*>> dp_keep;   // [block][j]: gradient wrt the output of pre-stack conv j (B,T,D)
   struct WgPlan { int B, T; bool drop; TcWgGroupPlan plan; };
   std::vector<WgPlan> wg_plans;
   std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
@@ -408,6 +410,12 @@ static void layout_buffers(wn_handle* h) {
   if (h->use_group_wgrad) {
     h->dz_all = W.take((size_t)L * rows * 2 * D * es);
     h->dx_all = W.take((size_t)L * rows * R * es);
+    if (h->alias_skip && h->cfg.use_skip) h->do_all = W.take((size_t)L * rows * R * es);
+    h->dp_keep.assign(L, {});
+    for (int l = 0; l < L; ++l) {
+      const int depth = (int)h->blocks[l].stack.size();
+      for (int j = 0; j + 1 < depth; ++j) h->dp_keep[l].push_back(W.take(rows * D * es));
+    }
   } else if (bf && !h->alias_skip && h->cfg.use_skip) {
     h->dcatA = W.take(rows * (size_t)(R + h->S) * es);
     h->dcatB = W.take(rows * (size_t)(R + h->S) * es);
@@ -584,16 +592,18 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   }
 
   // ---- grouped weight gradients: bf16 tier, separate skip projection (or none), widths in whole 256-channel pair tiles
-  // (skip_channels=None with use_skip adds d x_out + d skip into a shared scratch buffer: per-block launches there)
-  if (c.precision == WN_BF16 && !(h->alias_skip && c.use_skip)) {
+  if (c.precision == WN_BF16) {
     const char* e = getenv("WN_TC_GROUP_WGRAD");
     bool ok = !(e && e[0] == '0') && h->R % 256 == 0 && h->D % 256 == 0 && h->K <= TC_MAX_SEG;
     for (auto& b : h->blocks) if (b.has_skip && h->S % 256 != 0) ok = false;
     if (ok) {
-      // d z and d x_out of every block stay resident: (2D + R) bf16 per row and block
+      // d z, d x_out (and d x_out + d skip when the skip aliases conv1, and the pre-stack gradients of multi-dilation
+      // blocks) of every block stay resident
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
-      const double extra = (double)h->L * h->maxB * h->maxT * (2.0 * h->D + h->R) * 2.0;
+      double per_row = 0.0;
+      for (auto& b : h->blocks) per_row += 2.0 * h->D + h->R + ((h->alias_skip && c.use_skip) ? h->R : 0) + ((double)b.stack.size() - 1.0) * h->D;
+      const double extra = per_row * h->maxB * h->maxT * 2.0;
       if (extra > 0.25 * (double)free_b) ok = false;
     }
     h->use_group_wgrad = ok ? 1 : 0;
@@ -1266,6 +1276,19 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
 // the main stream; the weight-gradient kernels only consume, so they run on a side stream and fill the SMs the
 // persistent GEMMs leave idle in their last partial wave.  Events order producer -> consumer and protect the
 // ping-pong buffers (dz, d x_out) from being overwritten while a side kernel still reads them.
+// a conv whose output nothing reads (conv1 of the last block under use_skip, conv_skip without use_skip): the data term
+// of its gradients is zero, the L2 term (model.py:331-334) is not
+static void unused_conv_grads(wn_handle* h, cudaStream_t st, int w_idx, int b_idx, float l2coef) {
+  const long long cnt = h->params[w_idx].count;
+  if (l2coef != 0.f) {
+    LaunchScope ls(h, st, CLS_MISC);
+    reduce_parts<<<cdiv(cnt, 256), 256, 0, st>>>(G_(h, w_idx), 0, 0, G_(h, w_idx), cnt, P_(h, w_idx), l2coef);
+  } else {
+    cudaMemsetAsync(G_(h, w_idx), 0, cnt * 4, st);
+  }
+  cudaMemsetAsync(G_(h, b_idx), 0, h->params[b_idx].count * 4, st);
+}
+
 struct BwdSide {
   cudaStream_t side;
   cudaEvent_t ev_in;     // recorded on MAIN by the caller: this block's upstream gradients are complete
@@ -1297,8 +1320,10 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
   if (h->alias_skip) {
     if (dxout && dskip) {
       LaunchScope ls(h, st, CLS_MISC);
-      add2_kernel<T><<<cdiv(nR, 256), 256, 0, st>>>((const T*)dxout, (const T*)dskip, (T*)h->dotmp, nR);
-      d_o = h->dotmp;
+      // (grouped weight gradients read d_o at the end of the pass: one buffer per block instead of the shared scratch)
+      void* const d_o_buf = group && h->do_all ? (void*)((T*)h->do_all + (size_t)l * rows_cap * R) : h->dotmp;
+      add2_kernel<T><<<cdiv(nR, 256), 256, 0, st>>>((const T*)dxout, (const T*)dskip, (T*)d_o_buf, nR);
+      d_o = d_o_buf;
       ld_o = R;
     } else if (dskip) {
       d_o = dskip;
@@ -1320,8 +1345,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         j.group = h->wg_cur_group;
         h->wg_jobs.push_back(j);
       } else {
-        cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
-        cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
+        unused_conv_grads(h, st, b.conv1.w_idx, b.conv1.b_idx, l2coef);
       }
       if (b.has_skip) {
         if (dskip) {
@@ -1332,8 +1356,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
           j.group = h->wg_cur_group;
           h->wg_jobs.push_back(j);
         } else {
-          cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
-          cudaMemsetAsync(G_(h, b.conv_skip.b_idx), 0, h->params[b.conv_skip.b_idx].count * 4, st);
+          unused_conv_grads(h, st, b.conv_skip.w_idx, b.conv_skip.b_idx, l2coef);
         }
       }
     }
@@ -1354,8 +1377,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     w.side = side1;
     RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
   } else {
-    cudaMemsetAsync(G_(h, b.conv1.w_idx), 0, h->params[b.conv1.w_idx].count * 4, st);
-    cudaMemsetAsync(G_(h, b.conv1.b_idx), 0, h->params[b.conv1.b_idx].count * 4, st);
+    unused_conv_grads(h, st, b.conv1.w_idx, b.conv1.b_idx, l2coef);
   }
   if (b.has_skip && !cat && !group) {
     if (dskip) {
@@ -1366,8 +1388,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       w.side = side1;
       RET(run_wgrad<T>(h, s1, CLS_GEMM, w));
     } else {
-      cudaMemsetAsync(G_(h, b.conv_skip.w_idx), 0, h->params[b.conv_skip.w_idx].count * 4, st);
-      cudaMemsetAsync(G_(h, b.conv_skip.b_idx), 0, h->params[b.conv_skip.b_idx].count * 4, st);
+      unused_conv_grads(h, st, b.conv_skip.w_idx, b.conv_skip.b_idx, l2coef);
     }
   }
   // ---- dz = gate'(z) * (d_o Wr^T + dskip Ws^T)
@@ -1409,14 +1430,14 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     const int a_w = j == 0 ? R : D;
     // weight grad: rows (k, cin) <- taps of a_in shifted by -(K-1-k)*d ; the bias grad (and the
     // conditioning per-batch sums for the gated conv) are the column sums of the same G
-    if (group && j == depth - 1) {
+    if (group) {
       if constexpr (sizeof(T) == 2) {
         TcWgJobDesc jd{};
         jd.A = (const bf16*)a_in; jd.lda = a_w; jd.cin = c.cin; jd.ntaps = c.K;
         for (int k = 0; k < c.K; ++k) jd.shift[k] = -(c.K - 1 - k) * c.dil;
         jd.G = (const bf16*)dcur; jd.ldg = dcw; jd.N = c.cout;
         jd.dst = G_(h, c.w_idx); jd.w = h->cfg.l2_reg_factor > 0.f ? P_(h, c.w_idx) : nullptr; jd.bias = G_(h, c.b_idx);
-        if (b.has_cond) { jd.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; jd.ldpb = 2 * D; }
+        if (j == depth - 1 && b.has_cond) { jd.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; jd.ldpb = 2 * D; }
         jd.group = h->wg_cur_group;
         h->wg_jobs.push_back(jd);
       }
@@ -1446,7 +1467,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       typename EpiActBwd<T, T>::Params ep{};
       ep.N = c.cin;
       if (j > 0) {
-        void* dst = (dcur == h->dpA) ? h->dpB : h->dpA;
+        void* dst = group ? h->dp_keep[l][j - 1] : ((dcur == h->dpA) ? h->dpB : h->dpA);
         ep.out = (T*)dst; ep.ldo = D; ep.add = nullptr; ep.y = (const T*)h->acts[l][j - 1]; ep.ldy = D; ep.act = h->cfg.activation;
         ep.vec = vec_ok<T>(D);
         g.l2_in[1] = TC_L2_FIRST; g.l2_out[0] = TC_L2_LAST;
