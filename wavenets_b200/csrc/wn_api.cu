@@ -1704,6 +1704,38 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     ld_dx = h->R;
   }
   g_tc_balance = 0;
+  // ---- input conv (model.py:84-88): dW[k][c], db[c].  HBM-bound, small CTAs: with side launches it runs on the side stream
+  // beside the final grouped weight-gradient launch (its CTAs fit next to the tensor kernel's on the same SMs)
+  bool input_conv_done = false;
+  auto input_conv_bwd = [&](cudaStream_t s_) {
+    const bool wide = h->R % 2 == 0 && h->R / 2 <= 256 && ld_dx % 2 == 0;
+    const int chunks = cdiv(Tn, 64);
+    const int nparts = wide ? cdiv((long long)B * Tn, ICB_ROWS) : B * chunks;
+    {
+      LaunchScope ls(h, s_, CLS_MISC);
+      if (wide)
+        input_conv_bwd_stage1_wide<T><<<nparts, 256, 0, s_>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K);
+      else
+        input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, s_>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 64);
+    }
+    const long long kr = (long long)h->K * h->R;
+    {
+      LaunchScope ls(h, s_, CLS_MISC);
+      reduce_parts_tall<<<cdiv(kr, 32), 256, 0, s_>>>(h->colpart, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
+                                                   l2coef != 0.f ? P_(h, h->input_conv.w_idx) : nullptr, l2coef);
+    }
+    {
+      LaunchScope ls(h, s_, CLS_MISC);
+      reduce_parts_tall<<<cdiv(h->R, 32), 256, 0, s_>>>(h->colpart + kr, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
+    }
+  };
+  if (side_now) {
+    CK(cudaEventRecord(h->ev_blk_in[0], st));
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev_blk_in[0], 0));
+    input_conv_bwd(h->side_stream);
+    input_conv_done = true;
+    if (!(group && !h->wg_jobs.empty())) { CK(cudaEventRecord(h->ev_wg_side, h->side_stream)); CK(cudaStreamWaitEvent(st, h->ev_wg_side, 0)); }
+  }
   if constexpr (sizeof(T) == 2) {
     if (group && !h->wg_jobs.empty()) {
       // ---- every block's conv1 / conv_skip / gated-conv weight gradients in ONE launch (+ one finish)
@@ -1743,29 +1775,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   }
   // join: every side-stream wgrad (and its finish kernel) is complete before anything below reads the gradients
   if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
-  // ---- input conv (model.py:84-88): dW[k][c], db[c]
-  {
-    const bool wide = h->R % 2 == 0 && h->R / 2 <= 256 && ld_dx % 2 == 0;
-    const int chunks = cdiv(Tn, 64);
-    const int nparts = wide ? cdiv((long long)B * Tn, ICB_ROWS) : B * chunks;
-    {
-      LaunchScope ls(h, st, CLS_MISC);
-      if (wide)
-        input_conv_bwd_stage1_wide<T><<<nparts, 256, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K);
-      else
-        input_conv_bwd_stage1<T><<<dim3(cdiv(h->R, 64), chunks, B), 64, 0, st>>>(x, ldx, (const T*)dxout, ld_dx, h->colpart, B, Tn, h->R, h->K, 64);
-    }
-    const long long kr = (long long)h->K * h->R;
-    {
-      LaunchScope ls(h, st, CLS_MISC);
-      reduce_parts_tall<<<cdiv(kr, 32), 256, 0, st>>>(h->colpart, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.w_idx), kr,
-                                                   l2coef != 0.f ? P_(h, h->input_conv.w_idx) : nullptr, l2coef);
-    }
-    {
-      LaunchScope ls(h, st, CLS_MISC);
-      reduce_parts_tall<<<cdiv(h->R, 32), 256, 0, st>>>(h->colpart + kr, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
-    }
-  }
+  if (!input_conv_done) input_conv_bwd(st);
   if (c.conditioning) RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef));
   return WN_OK;
 }
