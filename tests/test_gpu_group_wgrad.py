@@ -88,3 +88,16 @@ def test_grouped_schedules_agree(env):
     err = float(np.abs(a[2][1][k] - ref).max() / (np.abs(ref).max() + 1e-30))
     # 24,000 rows accumulated in fp32 by the tensor core in one chain (no row split) or in up to 7 chains: measured <= 1.0e-4
     assert err < 3e-4, (k, err)
+
+
+def test_stack_forward_equals_per_block_launches():
+  """The whole residual stack as ONE persistent launch (csrc/gemm_tc_stack.cuh: tiles of layer l wait for the x_out tiles
+  of layer l-1 written by other CTA pairs of the same launch) against one fused launch per block: the same tile
+  arithmetic, so the loss, every gradient and the forward output are bit-equal (block loop of WaveNet.call, model.py:229-234)."""
+  kw, B, T = CASES['side_launches']
+  a = _run(kw, B, T, True)
+  b = _run(kw, B, T, True, {'WN_TC_STACK_FWD': '0'})
+  for i in range(3):
+    assert a[i][0] == b[i][0]
+    for k in b[i][1]:
+      assert np.array_equal(a[i][1][k], b[i][1][k]), (k, i)

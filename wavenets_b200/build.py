@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, 'libwavenet_b200.so')
 STAMP = os.path.join(HERE, '.libwavenet_b200.stamp')
 
 SOURCES = ['wn_api.cu']
-HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh',
+HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'gemm_tc_stack.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh',
            os.path.join('..', '..', 'include', 'wavenet_b200.h')]
 
 NVCC_FLAGS = [

@@ -1,0 +1,517 @@
+// gemm_tc_stack.cuh — the fused block forward of gemm_tc_block.cuh (layers.py:199-224) over the WHOLE residual stack
+// (the block loop of WaveNet.call, model.py:229-234) as ONE persistent launch.
+//
+// Per-block launches walk 256 row tiles on 74 CTA pairs in 4 rounds (the last a third full) and pay a launch, a fill and a
+// drain per block.  Here a CTA pair walks the (layer, m tile) list of all L layers in layer-major order with the same
+// software-pipelined tile order; per-layer tensor maps, tap shifts and bias pointers come from a table in global memory.
+// Tile (l, m) reads x_out tiles of layer l-1 (its own rows and the rows its causal taps reach back to, same sequence);
+// those were written by OTHER pairs of this launch, so every CTA publishes a tile (TMA stores complete -> proxy fence ->
+// release add on flags[l][m]) and a producer acquires the 2-4 flags its boxes touch before the first load of an m tile.
+// Dependencies point to smaller ids and every pair walks its ids in ascending order with all CTAs resident (grid <= SMs,
+// 1 CTA per SM), so the wait graph has no cycle as long as a layer has more m tiles than the launch has pairs (the
+// pipelined order issues G_0 of a pair's NEXT tile before OUT of its current one: that next tile must not depend on it).
+#pragma once
+#include "gemm_tc_block.cuh"
+
+struct alignas(128) TcStackLayer {
+  CUtensorMap tmA, tmX, tmW1, tmW2, tmZf, tmZs, tmG, tmO;
+  int shift[TC_MAX_SEG];
+  const float* bias_g; const float* cbias; const float* bias_r;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders async-proxy (TMA) accesses to global memory against generic-proxy ones of this thread
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+template <int D_, int R_>
+__global__ void __launch_bounds__(384, 1)
+tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* __restrict__ flags, const TcBlockParams p) {
+
+  using Cfg = TcBlockCfg<D_, R_>;
+  constexpr int STAGES = Cfg::STAGES, NEPI = 8, NT1 = Cfg::NT1;
+  constexpr int KB_G = D_ / 64, KB_X = R_ / 64;
+  extern __shared__ __align__(1024) uint8_t smem_blk[];
+  uint8_t* smem = smem_blk;
+  if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("libwavenet_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+  uint8_t* gbuf = smem + STAGES * Cfg::STAGE_BYTES;                       // [D/64][128 rows][128 B], 128B swizzle
+  uint8_t* out_ring = gbuf + Cfg::G_BYTES;
+  uint64_t* full_bar = (uint64_t*)(out_ring + Cfg::OUT_SLOTS * Cfg::SLOT_PANELS * Cfg::PANEL);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* out_empty = tempty_bar + 2;
+  uint64_t* g_done = out_empty + Cfg::OUT_SLOTS;     // local: this CTA's epilogue has written (and fenced) all of g
+  uint64_t* g_full = g_done + 1;                     // leader's: both CTAs' g buffers are complete
+  uint64_t* g_free = g_full + 1;                     // local: the TMA stores of g have read the buffer
+  uint64_t* g_cons = g_free + 1;                     // [2] local: OUT has consumed the slabs written by gate tile h
+  uint32_t* tmem_ptr = (uint32_t*)(g_cons + 2);
+  float* bias_s = (float*)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int tile_first = (int)blockIdx.x >> 1, tile_stride = (int)gridDim.x >> 1;
+  const int pair_row0 = (int)crank * Cfg::BM;
+  const int kb_a = p.Cin / 64;                        // k-blocks per tap of the gated conv
+  const int total_tiles = L * p.num_mtiles;            // (layer, m tile) in layer-major order: dependencies always point to smaller ids
+  const int n_mt = tile_first < total_tiles ? (total_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+  const int n_pos = n_mt * (NT1 + 1);
+
+  if (warp == 0 && lane == 0 && n_mt > 0) {
+    const TcStackLayer& L0 = layers[tile_first / p.num_mtiles];
+    tma_prefetch_desc(&L0.tmA); tma_prefetch_desc(&L0.tmW1); tma_prefetch_desc(&L0.tmW2); tma_prefetch_desc(&L0.tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], NEPI * 2); }
+    for (int i = 0; i < Cfg::OUT_SLOTS; ++i) mbar_init(&out_empty[i], 1);
+    mbar_init(g_done, NEPI); mbar_init(g_full, 2); mbar_init(g_free, 1); mbar_init(&g_cons[0], 1); mbar_init(&g_cons[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      auto next = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1; } };
+      constexpr int W2_BYTES = (R_ / 2) * 64 * 2;
+      for (int pos = 0; pos < n_pos; ++pos) {
+        int kind, j;
+        blk_tile<NT1>(pos, n_mt, kind, j);
+        const int gt = tile_first + j * tile_stride, ly = gt / p.num_mtiles, mt = gt - ly * p.num_mtiles;
+        const TcStackLayer& Ly = layers[ly];
+        const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (2 * Cfg::BM) + pair_row0;
+        if (kind < NT1) {
+          if (kind == 0 && ly > 0) {
+            // the rows the taps (and the residual) read are x_out tiles of the previous layer, written by other CTA pairs
+            // of this launch: wait for both CTAs of each of those tiles (ids are smaller than this tile's: no cycles)
+            const int tb = mt % p.tiles_t, row0 = tb * (2 * Cfg::BM);
+            const int* fl = flags + (size_t)(ly - 1) * p.num_mtiles + (mt - tb);
+            for (int s = 0; s < p.nseg; ++s) {
+              const int lo = row0 + Ly.shift[s], hi = lo + 2 * Cfg::BM - 1;
+              if (hi < 0) continue;
+              const int t_lo = lo < 0 ? 0 : lo / (2 * Cfg::BM);
+              int t_hi = hi / (2 * Cfg::BM);
+              if (t_hi > p.tiles_t - 1) t_hi = p.tiles_t - 1;
+              for (int tt = t_lo; tt <= t_hi; ++tt) {
+                const long long spin0 = clock64();
+                while (ld_acquire_gpu(fl + tt) < 2) {
+                  __nanosleep(32);
+                  // every CTA of the launch is resident by construction; if that ever fails, fail loudly instead of hanging
+                  if (clock64() - spin0 > 6000000000ll) { printf("libwavenet_b200: stack forward waited > 3 s for tile (%d, %d)\n", ly - 1, mt - tb + tt); __trap(); }
+                }
+              }
+            }
+            fence_proxy_async_global();
+          }
+          int wk = 0;
+          for (int s = 0; s < p.nseg; ++s) {
+            for (int kb = 0; kb < kb_a; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_pair_h(sa, &Ly.tmA, &full_bar[stage], kb * 64, t0 + Ly.shift[s], b, 0, p.pol_a);
+              tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmW1, &full_bar[stage], wk + kb * 64, kind * Cfg::BN + (int)crank * (Cfg::BN / 2), p.pol_w);
+              next();
+            }
+            wk += p.Cin;
+          }
+        } else {
+          // OUT tile: [g | x] . [Wr ; I]; this CTA's half of the R output columns
+          for (int kb = 0; kb < KB_G; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * W2_BYTES);
+            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmW2, &full_bar[stage], kb * 64, (int)crank * (R_ / 2), p.pol_w);
+            next();
+          }
+          if (p.has_res) {
+            for (int kb = 0; kb < KB_X; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + W2_BYTES));
+              tma_load_4d_pair_h(sa, &Ly.tmX, &full_bar[stage], kb * 64, t0, b, 0, p.pol_a);
+              tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmW2, &full_bar[stage], D_ + kb * 64, (int)crank * (R_ / 2), p.pol_w);
+              next();
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (leader) {
+      constexpr uint32_t idesc_g = umma_idesc_bf16(256, Cfg::BN, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(256, R_, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      uint32_t gphase = 0;
+      const int ksteps_g = p.nseg * kb_a;
+      const int ksteps_o = KB_G + (p.has_res ? KB_X : 0);
+#ifdef TC_TIMELINE_STACK_UNUSED
+      long long tl_rec[12][4]; int tl_n = 0; const long long tl_start = clock64();
+#endif
+      for (int pos = 0; pos < n_pos; ++pos) {
+        {
+          int kind, j;
+          blk_tile<NT1>(pos, n_mt, kind, j);
+          const bool is_out = kind == NT1;
+          const int ksteps = is_out ? ksteps_o : ksteps_g;
+#ifdef TC_TIMELINE_STACK_UNUSED
+          const long long tl0 = clock64();
+#endif
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+#ifdef TC_TIMELINE_STACK_UNUSED
+          const long long tl1 = clock64();
+#endif
+          if (is_out) { mbar_wait(g_full, gphase); gphase ^= 1; }     // both CTAs' g tiles are in shared memory
+#ifdef TC_TIMELINE_STACK_UNUSED
+          const long long tl2 = clock64();
+#endif
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * Cfg::BN);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+              const uint32_t a_addr = (is_out && ks < KB_G) ? smem_u32(gbuf) + (uint32_t)ks * (uint32_t)Cfg::A_BYTES : sa;
+              const uint64_t adesc = umma_smem_desc(a_addr, 16, 1024);
+              const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k)
+                umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), is_out ? idesc_o : idesc_g, (ks | k) != 0);
+              umma_commit_pair(&empty_bar[stage]);
+              if (ks == ksteps - 1) umma_commit_pair(&tfull_bar[as]);
+              // the slabs of g written by gate tile h have been read once k-step (h+1)*KB_G/NT1 - 1 of OUT is done
+              if (is_out && ks < KB_G && (ks + 1) % (KB_G / NT1) == 0) umma_commit_pair(&g_cons[(ks + 1) / (KB_G / NT1) - 1]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+#ifdef TC_TIMELINE_STACK_UNUSED
+          if (tl_n < 12) { tl_rec[tl_n][0] = tl1 - tl0; tl_rec[tl_n][1] = tl2 - tl1; tl_rec[tl_n][2] = clock64() - tl2; tl_rec[tl_n][3] = tl0 - tl_start; ++tl_n; }
+#endif
+          if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+      }
+#ifdef TC_TIMELINE_STACK_UNUSED
+      if (blockIdx.x == 0 && lane == 0)
+        for (int i = 0; i < tl_n; ++i) printf("BLK mma tile %d: t0 %lld wait_tempty %lld wait_g %lld issue %lld\n", i, tl_rec[i][3], tl_rec[i][0], tl_rec[i][1], tl_rec[i][2]);
+#endif
+    }
+  } else if (warp == 2) {
+    // ===================== TMA-store warp =====================
+    int oslot = 0, prev = -1;
+    auto step_store = [&](const CUtensorMap* m0, const CUtensorMap* m1, int c0, int t0, int b, unsigned long long pol) {
+      named_bar_sync(3 + oslot, NEPI * 32 + 32);
+      if (lane == 0) {
+        const uint8_t* ob = out_ring + oslot * Cfg::SLOT_PANELS * Cfg::PANEL;
+        tma_store_3d_h(ob, m0, c0, t0, b, pol);
+        if (m1) tma_store_3d_h(ob + Cfg::PANEL, m1, c0, t0, b, pol);
+        bulk_commit_group();
+        if (prev >= 0) { bulk_wait_group_read<1>(); mbar_arrive(&out_empty[prev]); }
+        prev = oslot;
+      }
+      __syncwarp();
+      if (++oslot == Cfg::OUT_SLOTS) oslot = 0;
+    };
+    for (int pos = 0; pos < n_pos; ++pos) {
+      int kind, j;
+      blk_tile<NT1>(pos, n_mt, kind, j);
+      const int gt = tile_first + j * tile_stride, ly = gt / p.num_mtiles, mt = gt - ly * p.num_mtiles;
+      const TcStackLayer& Ly = layers[ly];
+      const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (2 * Cfg::BM) + pair_row0;
+      if (kind < NT1) {
+        for (int step = 0; step < Cfg::BN / 64; ++step) step_store(&Ly.tmZf, &Ly.tmZs, kind * (Cfg::BN / 2) + step * 32, t0, b, p.pol_z);
+        if (kind == NT1 - 1) {
+          // g: the whole 128 x D tile straight out of the operand buffer (same 128B-swizzled K-major slabs as a TMA box)
+          named_bar_sync(8, NEPI * 32 + 32);
+          if (lane == 0) {
+#pragma unroll
+            for (int kb = 0; kb < KB_G; ++kb) tma_store_3d_h(gbuf + kb * Cfg::A_BYTES, &Ly.tmG, kb * 64, t0, b, p.pol_g);
+            bulk_commit_group();
+            // the very next epilogue tile overwrites g: wait until every store group issued so far has read shared memory
+            bulk_wait_group_read<0>();
+            if (prev >= 0) { mbar_arrive(&out_empty[prev]); prev = -1; }
+            mbar_arrive(g_free);
+          }
+          __syncwarp();
+        }
+      } else {
+        for (int step = 0; step < R_ / 32; ++step) step_store(&Ly.tmO, nullptr, step * 32, t0, b, p.pol_o);
+        if (ly + 1 < L) {
+          // this CTA's 128 rows of x_out are the next layer's operand: publish them once the stores have completed
+          if (lane == 0) {
+            bulk_wait_group<0>();
+            if (prev >= 0) { mbar_arrive(&out_empty[prev]); prev = -1; }
+            fence_proxy_async_global();
+            __threadfence();
+            red_release_gpu_add(flags + (size_t)ly * p.num_mtiles + mt, 1);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  } else if (warp == 3) {
+    // ===================== pair hand-off of g =====================
+    if (lane == 0) {
+      uint32_t dphase = 0;
+      for (int j = 0; j < n_mt; ++j) {
+        mbar_wait(g_done, dphase); dphase ^= 1;
+        if (leader) mbar_arrive(g_full);
+        else mbar_arrive_remote(g_full, 0u);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int quarter = warp & 3;
+    const int q = e >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 64u;
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    const uint32_t u0 = (uint32_t)(2 * q), u1 = u0 + 1;
+    const uint32_t off0 = row_off + ((u0 ^ sw) << 4), off1 = row_off + ((u1 ^ sw) << 4);
+    const uint32_t grow = (uint32_t)row * 128u, gsw = (uint32_t)(row & 7);
+    int as = 0; uint32_t aphase = 0;
+    int oslot = 0; uint32_t ophase = 0;
+
+#ifdef TC_TIMELINE_STACK_UNUSED
+    long long tl_rec[12][3]; int tl_n = 0; const long long tl_start = clock64();
+#endif
+    for (int pos = 0; pos < n_pos; ++pos) {
+      int nt, j;
+      blk_tile<NT1>(pos, n_mt, nt, j);
+      const int gt = tile_first + j * tile_stride, ly = gt / p.num_mtiles, mt = gt - ly * p.num_mtiles;
+      const TcStackLayer& Ly = layers[ly];
+      const int b = mt / p.tiles_t;
+      const int bsafe = b < p.B ? b : p.B - 1;
+      const TcEpiGate<true>::Params pg{Ly.bias_g, Ly.cbias, D_};
+      const TcEpiBiasActRes<true>::Params po{Ly.bias_r, nullptr, 0, ACT_LINEAR, R_};
+      {
+        const bool is_out = nt == NT1;
+        const int tid = (int)threadIdx.x - 128;
+        float bias_reg = 0.f;
+        if (is_out) { if (tid < R_) bias_reg = TcEpiBiasActRes<true>::bias_load(po, bsafe, 0, R_, tid); }
+        else bias_reg = TcEpiGate<true>::bias_load(pg, bsafe, nt * (Cfg::BN / 2), Cfg::BN, tid);
+#ifdef TC_TIMELINE_STACK_UNUSED
+        const long long te0 = clock64();
+#endif
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#ifdef TC_TIMELINE_STACK_UNUSED
+        const long long te1 = clock64();
+#endif
+        // table double-buffered by tile parity: a warp that runs ahead into the next tile must not overwrite entries
+        // other warps still read (the epilogue warps only meet at this barrier, once per tile)
+        float* const bs = bias_s + as * 256;
+        bs[tid] = bias_reg;
+        named_bar_sync(2, NEPI * 32);
+        TmemAccRow acc{tmem_base + (uint32_t)(as * Cfg::BN) + ((uint32_t)(quarter * 32) << 16), true};
+        if (!is_out) {
+          if (j > 0) {
+            // this tile's half of the g buffer still holds the previous m tile's g: wait until OUT has consumed it and
+            // (first gate tile) until the TMA stores of that g have read the buffer
+            mbar_wait(&g_cons[nt], (uint32_t)((j - 1) & 1));
+            if (nt == 0) mbar_wait(g_free, (uint32_t)((j - 1) & 1));
+          }
+#pragma unroll 1
+          for (int step = 0; step < Cfg::BN / 64; ++step) {
+            float in[1][16];
+            float out[3][16];
+            TcEpiGate<true>::chunk(pg, acc, bsafe, step * 32 + q * 16, Cfg::BN / 2, 0, 0u, in, out, bs);
+            uint8_t* ob = out_ring + oslot * Cfg::SLOT_PANELS * Cfg::PANEL;
+            mbar_wait(&out_empty[oslot], ophase ^ 1);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              uint4 a, c;
+              a.x = pack_bf16x2(out[k][0], out[k][1]); a.y = pack_bf16x2(out[k][2], out[k][3]);
+              a.z = pack_bf16x2(out[k][4], out[k][5]); a.w = pack_bf16x2(out[k][6], out[k][7]);
+              c.x = pack_bf16x2(out[k][8], out[k][9]); c.y = pack_bf16x2(out[k][10], out[k][11]);
+              c.z = pack_bf16x2(out[k][12], out[k][13]); c.w = pack_bf16x2(out[k][14], out[k][15]);
+              *reinterpret_cast<uint4*>(ob + k * Cfg::PANEL + off0) = a;
+              *reinterpret_cast<uint4*>(ob + k * Cfg::PANEL + off1) = c;
+            }
+            {
+              // g channels [ch, ch+16) of this row -> operand buffer: slab ch/64, 16-byte units (ch%64)/8 and +1, 128B swizzle
+              const int ch = nt * (Cfg::BN / 2) + step * 32 + q * 16;
+              uint8_t* gs = gbuf + (ch >> 6) * Cfg::A_BYTES + grow;
+              const uint32_t j0 = (uint32_t)((ch & 63) >> 3);
+              uint4 a, c;
+              a.x = pack_bf16x2(out[2][0], out[2][1]); a.y = pack_bf16x2(out[2][2], out[2][3]);
+              a.z = pack_bf16x2(out[2][4], out[2][5]); a.w = pack_bf16x2(out[2][6], out[2][7]);
+              c.x = pack_bf16x2(out[2][8], out[2][9]); c.y = pack_bf16x2(out[2][10], out[2][11]);
+              c.z = pack_bf16x2(out[2][12], out[2][13]); c.w = pack_bf16x2(out[2][14], out[2][15]);
+              *reinterpret_cast<uint4*>(gs + ((j0 ^ gsw) << 4)) = a;
+              *reinterpret_cast<uint4*>(gs + (((j0 + 1) ^ gsw) << 4)) = c;
+            }
+            fence_proxy_async();
+            named_bar_arrive(3 + oslot, NEPI * 32 + 32);
+            if (++oslot == Cfg::OUT_SLOTS) { oslot = 0; ophase ^= 1; }
+          }
+          if (nt == NT1 - 1) {
+            // g is complete in this CTA (every writer fenced above): let the store warp and the MMA side know
+            named_bar_arrive(8, NEPI * 32 + 32);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_done);
+          }
+        } else {
+#pragma unroll 1
+          for (int step = 0; step < R_ / 32; ++step) {
+            float in[1][16];
+            float out[1][16];
+            TcEpiBiasActRes<true>::chunk(po, acc, bsafe, step * 32 + q * 16, 0, 0, 0u, in, out, bs);
+            uint8_t* ob = out_ring + oslot * Cfg::SLOT_PANELS * Cfg::PANEL;
+            mbar_wait(&out_empty[oslot], ophase ^ 1);
+            uint4 a, c;
+            a.x = pack_bf16x2(out[0][0], out[0][1]); a.y = pack_bf16x2(out[0][2], out[0][3]);
+            a.z = pack_bf16x2(out[0][4], out[0][5]); a.w = pack_bf16x2(out[0][6], out[0][7]);
+            c.x = pack_bf16x2(out[0][8], out[0][9]); c.y = pack_bf16x2(out[0][10], out[0][11]);
+            c.z = pack_bf16x2(out[0][12], out[0][13]); c.w = pack_bf16x2(out[0][14], out[0][15]);
+            *reinterpret_cast<uint4*>(ob + off0) = a;
+            *reinterpret_cast<uint4*>(ob + off1) = c;
+            fence_proxy_async();
+            named_bar_arrive(3 + oslot, NEPI * 32 + 32);
+            if (++oslot == Cfg::OUT_SLOTS) { oslot = 0; ophase ^= 1; }
+          }
+        }
+#ifdef TC_TIMELINE_STACK_UNUSED
+        if (tl_n < 12) { tl_rec[tl_n][0] = te1 - te0; tl_rec[tl_n][1] = clock64() - te1; tl_rec[tl_n][2] = te0 - tl_start; ++tl_n; }
+#endif
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(&tempty_bar[as], 0u);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+#ifdef TC_TIMELINE_STACK_UNUSED
+    if (blockIdx.x == 0 && threadIdx.x == 128)
+      for (int i = 0; i < tl_n; ++i) printf("BLK epi tile %d: t0 %lld wait_tfull %lld work %lld\n", i, tl_rec[i][2], tl_rec[i][0], tl_rec[i][1]);
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+}
+
+
+struct TcStackPlan {
+  int B = 0, T = 0, L = 0, num_mtiles = 0; bool cb = false;
+  TcStackLayer* d_layers = nullptr; int* d_flags = nullptr;
+  void release() { cudaFree(d_layers); cudaFree(d_flags); d_layers = nullptr; d_flags = nullptr; }
+};
+
+// layers[l]: the TcBlockDesc of block l (same shapes for every block)
+template <int D_, int R_>
+static int tc_stack_build_t(TmapCache& tc, const std::vector<TcBlockDesc>& descs, TcStackPlan* plan) {
+  std::vector<TcStackLayer> tab(descs.size());
+  for (size_t l = 0; l < descs.size(); ++l) {
+    const TcBlockDesc& d = descs[l];
+    const CUtensorMap* mA = tc_act_map(tc, d.A, d.lda, d.Cin, d.T, d.B, 1, 0, 128);
+    const CUtensorMap* mX = tc_act_map(tc, d.X, d.ldx, d.R, d.T, d.B, 1, 0, 128);
+    uint64_t w1d[2] = {(uint64_t)d.k1, (uint64_t)(2 * d.D)}, w1s[1] = {(uint64_t)d.k1 * 2};
+    uint32_t w1b[2] = {64, 128};
+    const CUtensorMap* mW1 = tc.get(d.W1, 2, w1d, w1s, w1b);
+    uint64_t w2d[2] = {(uint64_t)(d.D + d.R), (uint64_t)d.R}, w2s[1] = {(uint64_t)(d.D + d.R) * 2};
+    uint32_t w2b[2] = {64, (uint32_t)(R_ / 2)};
+    const CUtensorMap* mW2 = tc.get(d.W2, 2, w2d, w2s, w2b);
+    const TcEpiIo zf{d.z, 2 * d.D, d.D, 0}, zs{d.z + d.D, 2 * d.D, d.D, 0}, xo{d.xout, d.R, d.R, 0};
+    const CUtensorMap* mZf = tc_panel_map(tc, zf, d.T, d.B);
+    const CUtensorMap* mZs = tc_panel_map(tc, zs, d.T, d.B);
+    const CUtensorMap* mO = tc_panel_map(tc, xo, d.T, d.B);
+    const CUtensorMap* mG = tc_slab_map(tc, d.g, d.D, d.D, d.T, d.B);
+    if (!mA || !mX || !mW1 || !mW2 || !mZf || !mZs || !mO || !mG) return -10;
+    TcStackLayer& t = tab[l];
+    t.tmA = *mA; t.tmX = *mX; t.tmW1 = *mW1; t.tmW2 = *mW2; t.tmZf = *mZf; t.tmZs = *mZs; t.tmG = *mG; t.tmO = *mO;
+    for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
+    t.bias_g = d.bias_g; t.cbias = d.cbias; t.bias_r = d.bias_r;
+  }
+  const TcBlockDesc& d0 = descs[0];
+  plan->release();
+  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->cb = d0.cbias != nullptr;
+  if (cudaMalloc((void**)&plan->d_layers, tab.size() * sizeof(TcStackLayer)) != cudaSuccess ||
+      cudaMemcpy(plan->d_layers, tab.data(), tab.size() * sizeof(TcStackLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc((void**)&plan->d_flags, (size_t)plan->L * plan->num_mtiles * sizeof(int)) != cudaSuccess) {
+    snprintf(g_tc_err, sizeof(g_tc_err), "stack forward: plan allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    plan->release();
+    return -23;
+  }
+  return 0;
+}
+
+// pairs a stack launch would use; the launch is only valid when a layer has MORE m tiles than that
+static inline int tc_stack_pairs(int num_mtiles) { return tc_balanced_slots(num_mtiles, tc_num_sms() / 2); }
+
+template <int D_, int R_>
+static int tc_stack_launch_t(cudaStream_t st, const TcStackPlan& plan, const TcBlockDesc& d0) {
+  using Cfg = TcBlockCfg<D_, R_>;
+  TcBlockParams p{};
+  p.B = d0.B; p.T = d0.T; p.tiles_t = (d0.T + 255) / 256; p.num_mtiles = d0.B * p.tiles_t;
+  p.nseg = d0.nseg;
+  p.Cin = d0.Cin; p.D = d0.D; p.R = d0.R; p.has_res = d0.has_res;
+  p.pol_a = tc_policy(TC_L2_NORMAL); p.pol_w = tc_policy(TC_L2_LAST);
+  p.pol_z = tc_policy(TC_L2_FIRST); p.pol_g = tc_policy(TC_L2_FIRST); p.pol_o = tc_policy(TC_L2_LAST);
+  auto kern = tc_stack_fwd_kernel<D_, R_>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  const int pairs = tc_stack_pairs(p.num_mtiles);
+  if (p.num_mtiles <= pairs) return -100;
+  {
+    // every CTA pair of the launch must be resident at the same time (tiles wait for tiles of other pairs)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t oc{};
+      oc.gridDim = dim3(tc_num_sms()); oc.blockDim = dim3(384); oc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute oa[1];
+      oa[0].id = cudaLaunchAttributeClusterDimension;
+      oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+      oc.attrs = oa; oc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &oc) != cudaSuccess) { n = 0; cudaGetLastError(); }
+      max_clusters = n;
+    }
+    if (pairs > max_clusters) return -100;
+  }
+  if (cudaMemsetAsync(plan.d_flags, 0, (size_t)plan.L * plan.num_mtiles * sizeof(int), st) != cudaSuccess) return -14;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 2);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const TcStackLayer*)plan.d_layers, plan.L, plan.d_flags, p);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "stack forward launch: %s", cudaGetErrorString(e)); return -13; }
+  return 0;
+}
+
+static inline int tc_stack_build(TmapCache& tc, const std::vector<TcBlockDesc>& descs, TcStackPlan* plan) {
+  const TcBlockDesc& d = descs[0];
+  if (d.D == 256 && d.R == 256) return tc_stack_build_t<256, 256>(tc, descs, plan);
+  if (d.D == 128 && d.R == 128) return tc_stack_build_t<128, 128>(tc, descs, plan);
+  return -100;
+}
+static inline int tc_stack_launch(cudaStream_t st, const TcStackPlan& plan, const TcBlockDesc& d) {
+  if (d.D == 256 && d.R == 256) return tc_stack_launch_t<256, 256>(st, plan, d);
+  if (d.D == 128 && d.R == 128) return tc_stack_launch_t<128, 128>(st, plan, d);
+  return -100;
+}

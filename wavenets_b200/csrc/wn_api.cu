@@ -25,6 +25,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc_block.cuh"
 #include "gemm_tc_wgroup.cuh"
+#include "gemm_tc_stack.cuh"
 #include "kernels_misc.cuh"
 #include "generate.cuh"
 
@@ -206,6 +207,8 @@ struct wn_handle {
   int use_side = 1;
   int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
   int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
+  int use_stack_fwd = 1;    // WN_TC_STACK_FWD=0: one fused launch per block instead of one for the whole stack (gemm_tc_stack.cuh)
+  std::vector<TcStackPlan> stack_plans;
   int tile_gate_bwd = 0, tile_dgrad = 0;   // forced CTA tile widths of the two backward conv GEMMs (0 = widest that divides N)
   int fused_fwd_launches = 0;  // fused block-forward launches of the last step (0: separate gate / conv1 kernels)
   // grouped weight gradients (gemm_tc_wgroup.cuh): d z and d x_out of EVERY block are kept (no ping-pong) and all block
@@ -641,6 +644,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_SIDE_STREAM"); if (e && e[0] == '0') h->use_side = 0; }
   if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
   { const char* e = getenv("WN_TC_FUSED_FWD"); if (e && e[0] == '0') h->use_fused_fwd = 0; }
+  { const char* e = getenv("WN_TC_STACK_FWD"); if (e && e[0] == '0') h->use_stack_fwd = 0; }
   { const char* e = getenv("WN_TC_TILE_GATE_BWD"); if (e) h->tile_gate_bwd = atoi(e); }
   { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
@@ -689,6 +693,7 @@ extern "C" void wn_destroy(wn_handle* h) {
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   for (void* a : h->gen.allocs) cudaFree(a);
   for (auto& wp : h->wg_plans) wp.plan.release();
+  for (auto& sp : h->stack_plans) sp.release();
   cudaFree(h->d_pack_jobs);
   cudaFree(h->opt_m); cudaFree(h->opt_v); cudaFree(h->opt_chunks); cudaFree(h->opt_var_first);
   cudaFree(h->opt_partial); cudaFree(h->opt_scale); cudaFree(h->opt_norms);
@@ -1195,6 +1200,60 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
       input_conv_fwd<T><<<cdiv(total, 256), 256, 0, st>>>(x, ldx, P_(h, h->input_conv.w_idx), P_(h, h->input_conv.b_idx), (T*)h->h0, B, Tn, h->R, h->K);
   }
   const void* cur = h->h0;
+  bool stacked = false;
+  if constexpr (sizeof(T) == 2) {
+    // the whole residual stack as ONE persistent launch (gemm_tc_stack.cuh) when every block takes the fused forward
+    // and a layer has more 256-row tiles than the GPU has CTA pairs
+    bool ok = h->use_stack_fwd && h->use_fused_fwd && tc_cta_group() == 2 && !h->drop_active && c.use_residual && h->L >= 2 && h->D == h->R &&
+              (h->D == 256 || h->D == 128) && B * cdiv(Tn, 256) > tc_num_sms() / 2;
+    for (auto& b : h->blocks) {
+      if (!ok) break;
+      const ConvP& cv = b.stack.back();
+      ok = b.stack.size() == 1 && b.Wres16 != nullptr && cv.tileN16 == 256 && cv.K <= TC_MAX_SEG && cv.cin % 64 == 0;
+    }
+    if (ok) {
+      const size_t rows_cap = (size_t)h->maxB * h->maxT;
+      const bool has_cb = c.conditioning != 0;
+      auto desc_of = [&](int l) {
+        BlockP& b = h->blocks[l];
+        const ConvP& cv = b.stack[0];
+        const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
+        TcBlockDesc d{};
+        d.B = B; d.T = Tn; d.nseg = cv.K; d.Cin = cv.cin; d.D = h->D; d.R = h->R; d.has_res = 1;
+        for (int k = 0; k < cv.K; ++k) d.shift[k] = -(cv.K - 1 - k) * cv.dil;
+        d.A = (const bf16*)x_in; d.lda = h->R; d.X = (const bf16*)x_in; d.ldx = h->R;
+        d.W1 = cv.Wf16; d.k1 = cv.Kf16; d.W2 = b.Wres16;
+        d.z = (bf16*)h->zbuf[l]; d.g = (bf16*)h->G_all + (size_t)l * rows_cap * h->D; d.xout = (bf16*)h->xout[l];
+        d.bias_g = P_(h, cv.b_idx); d.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
+        d.bias_r = P_(h, b.conv1.b_idx);
+        return d;
+      };
+      TcStackPlan* sp = nullptr;
+      for (auto& q : h->stack_plans) if (q.B == B && q.T == Tn && q.cb == has_cb) sp = &q;
+      int r = 0;
+      if (!sp) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+          if (h->stack_plans.size() >= 4) { CK(cudaStreamSynchronize(st)); for (auto& q : h->stack_plans) q.release(); h->stack_plans.clear(); }
+          std::vector<TcBlockDesc> descs;
+          for (int l = 0; l < h->L; ++l) descs.push_back(desc_of(l));
+          h->stack_plans.push_back(TcStackPlan{});
+          r = tc_stack_build(h->tmaps, descs, &h->stack_plans.back());
+          if (r == 0) sp = &h->stack_plans.back(); else h->stack_plans.pop_back();
+        }
+      }
+      if (sp) {
+        struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_fwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
+        LaunchScope ls(h, st, CLS_DILATED);
+        r = tc_stack_launch(st, *sp, desc_of(0));
+        if (r == 0) { stacked = true; h->fused_fwd_launches = h->L; cur = h->xout[h->L - 1]; }
+        else if (r == -100) h->launches--;
+        else { set_err("stack forward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+      } else if (r != 0 && r != -100) { set_err("stack forward plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+    }
+  }
+  if (!stacked)
   for (int l = 0; l < h->L; ++l) {
     RET(block_forward<T>(h, st, l, cur, c.conditioning != 0, B, Tn));
     cur = h->xout[l];
