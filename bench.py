@@ -248,6 +248,7 @@ def main():
   import ctypes as C
   side_l = C.c_int(0)
   wg_tiles = int(h.lib.wn_grouped_wgrad_tiles(h.h, C.byref(side_l)))   # of the timed (graph-replayed) step
+  stack_layers = int(h.lib.wn_stack_forward_layers(h.h))
   clocks = sampler.stop() if sampler else None
   loss_last = float(loss_t[0].item())
 
@@ -315,12 +316,13 @@ def main():
               # step (cold cache; profiles/ncu_full_r1e_c2_{blockfwd,bwd}.txt): fused block forward 98.0 MB, dgrad 110.5 MB,
               # dilated wgrad 107.5 MB, its finish 19.1 MB.  Only valid for the default workload.
               'traffic': TRAFFIC_C2 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and fused_blocks and wg_tiles) else None,
-              'kernel': ('tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ' if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + ')
+              'kernel': (('tc_stack_fwd_kernel (gated conv + gate + conv1 + residual of ALL layers in one persistent launch, CTA pairs) + ' if stack_layers else
+                          'tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ') if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + ')
               + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + '
               + ('tc_wgrad_group_kernel (+ finish): gated-conv, conv1, conv_skip and head filter gradients of all blocks in one launch'
                  if wg_tiles else 'tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs')
               if precision == 'bf16' else 'conv_gemm_simt + wgrad_simt on the dilated convs',
-              'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles, 'wgrad_side_launches': int(side_l.value), 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
+              'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles, 'stack_forward_layers': stack_layers, 'wgrad_side_launches': int(side_l.value), 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
               'ms_per_step_in_kernel_eager_events': dil_ms_eager, 'ms_per_step_all_launches_eager_events': prof['all'][0],
               'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
               'share_of_step': share}

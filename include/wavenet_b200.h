@@ -209,6 +209,9 @@ int wn_fused_forward_blocks(const wn_handle* h);  /* blocks of the last forward 
  * step computed in the grouped launch behind the dgrad chain; 0 = per-block launches. side_launches (may be null): how many
  * of the launches ran beside the chain on the SMs it leaves idle */
 int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches);
+/* layers of the last forward (block loop of WaveNet.call, model.py:229-234) that ran inside the ONE persistent stack launch;
+ * 0 = one launch (or more) per block */
+int wn_stack_forward_layers(const wn_handle* h);
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
 /* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a

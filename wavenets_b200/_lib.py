@@ -21,7 +21,7 @@ EXPORTS = [
   'wn_param_count', 'wn_param_info', 'wn_params_dev', 'wn_grads_dev', 'wn_set_param', 'wn_get_param',
   'wn_get_grad', 'wn_params_changed', 'wn_quantize', 'wn_forward', 'wn_train_step', 'wn_test_step',
   'wn_train_step_host', 'wn_layer_forward', 'wn_layer_backward', 'wn_last_launch_count',
-  'wn_fused_forward_blocks', 'wn_grouped_wgrad_tiles', 'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_num_frames', 'wn_preprocess_frames', 'wn_inverse_mu_law', 'wn_one_hot', 'wn_sample_waveform', 'wn_sample_last_step', 'wn_generate', 'wn_adam_init', 'wn_clip_grads', 'wn_adam_step', 'wn_adam_state', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
+  'wn_fused_forward_blocks', 'wn_grouped_wgrad_tiles', 'wn_stack_forward_layers', 'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_num_frames', 'wn_preprocess_frames', 'wn_inverse_mu_law', 'wn_one_hot', 'wn_sample_waveform', 'wn_sample_last_step', 'wn_generate', 'wn_adam_init', 'wn_clip_grads', 'wn_adam_step', 'wn_adam_state', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
 ]
 
 
@@ -90,6 +90,7 @@ def load():
   lib.wn_last_launch_count.restype = i64
   lib.wn_fused_forward_blocks.argtypes = [vp]
   lib.wn_grouped_wgrad_tiles.argtypes = [vp, C.POINTER(C.c_int)]
+  lib.wn_stack_forward_layers.argtypes = [vp]
   lib.wn_profile_begin.argtypes = [vp, i32]
   lib.wn_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   lib.wn_profile_get.argtypes = [vp, i32, C.POINTER(C.c_double), C.c_char_p, i32]

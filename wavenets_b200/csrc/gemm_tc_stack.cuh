@@ -217,7 +217,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
     }
   } else if (warp == 2) {
     // ===================== TMA-store warp =====================
-    int oslot = 0, prev = -1;
+    int oslot = 0, prev = -1, pend_flag = -1;
     auto step_store = [&](const CUtensorMap* m0, const CUtensorMap* m1, int c0, int t0, int b, unsigned long long pol) {
       named_bar_sync(3 + oslot, NEPI * 32 + 32);
       if (lane == 0) {
@@ -255,17 +255,28 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
         }
       } else {
         for (int step = 0; step < R_ / 32; ++step) step_store(&Ly.tmO, nullptr, step * 32, t0, b, p.pol_o);
-        if (ly + 1 < L) {
-          // this CTA's 128 rows of x_out are the next layer's operand: publish them once the stores have completed
-          if (lane == 0) {
-            bulk_wait_group<0>();
-            if (prev >= 0) { mbar_arrive(&out_empty[prev]); prev = -1; }
-            fence_proxy_async_global();
-            __threadfence();
-            red_release_gpu_add(flags + (size_t)ly * p.num_mtiles + mt, 1);
-          }
-          __syncwarp();
+        // this CTA's 128 rows of x_out are the next layer's operand: published behind the NEXT tile's stores (below), so
+        // that the store warp never waits for a write to land while the epilogue warps are filling the output slots
+        if (ly + 1 < L) pend_flag = ly * p.num_mtiles + mt;
+      }
+      if (kind < NT1 && pend_flag >= 0) {
+        // a gate tile commits at least BN/64 = 4 store groups: once at most 4 are pending, the OUT tile's have completed
+        if (lane == 0) {
+          bulk_wait_group<4>();
+          fence_proxy_async_global();
+          __threadfence();
+          red_release_gpu_add(flags + pend_flag, 1);
         }
+        __syncwarp();
+        pend_flag = -1;
+      }
+    }
+    if (lane == 0) {
+      bulk_wait_group<0>();
+      if (pend_flag >= 0) {
+        fence_proxy_async_global();
+        __threadfence();
+        red_release_gpu_add(flags + pend_flag, 1);
       }
     }
     if (lane == 0) bulk_wait_group<0>();

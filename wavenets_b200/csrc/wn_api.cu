@@ -207,6 +207,7 @@ struct wn_handle {
   int use_side = 1;
   int use_res_gemm = 1;     // WN_TC_RES_GEMM=0: residual added in the epilogue (A/B switch)
   int use_fused_fwd = 1;    // WN_TC_FUSED_FWD=0: gated conv and conv1 as separate launches (A/B switch)
+  int stack_fwd_layers = 0;   // layers of the last forward inside the stack launch
   int use_stack_fwd = 1;    // WN_TC_STACK_FWD=0: one fused launch per block instead of one for the whole stack (gemm_tc_stack.cuh)
   std::vector<TcStackPlan> stack_plans;
   int tile_gate_bwd = 0, tile_dgrad = 0;   // forced CTA tile widths of the two backward conv GEMMs (0 = widest that divides N)
@@ -1201,6 +1202,7 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   }
   const void* cur = h->h0;
   bool stacked = false;
+  h->stack_fwd_layers = 0;
   if constexpr (sizeof(T) == 2) {
     // the whole residual stack as ONE persistent launch (gemm_tc_stack.cuh) when every block takes the fused forward
     // and a layer has more 256-row tiles than the GPU has CTA pairs
@@ -1247,7 +1249,7 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
         struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_fwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
         LaunchScope ls(h, st, CLS_DILATED);
         r = tc_stack_launch(st, *sp, desc_of(0));
-        if (r == 0) { stacked = true; h->fused_fwd_launches = h->L; cur = h->xout[h->L - 1]; }
+        if (r == 0) { stacked = true; h->fused_fwd_launches = h->L; h->stack_fwd_layers = h->L; cur = h->xout[h->L - 1]; }
         else if (r == -100) h->launches--;
         else { set_err("stack forward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
       } else if (r != 0 && r != -100) { set_err("stack forward plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
@@ -2515,6 +2517,7 @@ extern "C" int wn_debug_bench(int which, int reps, const void* a_bf16_dev, int l
 extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->launches : 0; }
 // number of blocks whose gated conv + conv1 ran as ONE fused launch in the last enqueued forward (0 = separate kernels)
 extern "C" int wn_fused_forward_blocks(const wn_handle* h) { return h ? h->fused_fwd_launches : 0; }
+extern "C" int wn_stack_forward_layers(const wn_handle* h) { return h ? h->stack_fwd_layers : 0; }
 extern "C" int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches) {
   if (side_launches) *side_launches = h ? h->wg_last_side : 0;
   return h ? h->wg_last_tiles : 0;
