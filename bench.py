@@ -228,6 +228,12 @@ def main():
   # ---- warm-up (also builds tensor maps, NCCL channels)
   for _ in range(args.warmup):
     model.train_step_async(data_dev)
+  # W steps are ~20 ms of work: 40 more untimed steps (a quarter of a second; the same count on every rank, each step
+  # holds an all-reduce) so that the timed regions do not start on clocks that are still ramping up from idle
+  for i in range(40):
+    model.train_step_async(data_dev)
+    if i % 8 == 7:
+      torch.cuda.synchronize(dev)
   # (the host-buffer path stages into its own device buffers = its own CUDA graph: warm it up as well)
   for _ in range(max(1, args.warmup)):
     loss0 = float(model.train_step(data_host)['loss'])

@@ -8,5 +8,5 @@ PER_STEP=$(grep -o "launches/step [0-9]*" gpurun_out/plain_$TAG.log | grep -o "[
 # setup = 2 launches (one-launch re-pack), then PER_STEP per step; third step = side launches active (plan exists, eager)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip $((2 + 2 * PER_STEP)) -c $PER_STEP --csv --log-file gpurun_out/launches_${TAG}.csv python scripts/prof_step.py c2 3 > gpurun_out/ncu_${TAG}_list.log 2>&1
 WN_SIDE_STREAM=0 ncu --set full --clock-control none --import-source on -k "regex:tc_wgrad_group" --launch-skip 2 --launch-count 2 -f -o gpurun_out/prof_${TAG}_wgroup python scripts/prof_step.py c2 3 > gpurun_out/ncu_${TAG}_a.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:tc_conv_gemm_staged_kernel<TcEpiGateBwd|tc_conv_gemm_staged_kernel<TcEpiActBwd" --launch-skip 80 --launch-count 2 -f -o gpurun_out/prof_${TAG}_bwd python scripts/prof_step.py c2 3 > gpurun_out/ncu_${TAG}_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:tc_stack_fwd" --launch-skip 1 --launch-count 1 -f -o gpurun_out/prof_${TAG}_stackfwd python scripts/prof_step.py c2 3 > gpurun_out/ncu_${TAG}_b.log 2>&1
 tail -n 2 gpurun_out/ncu_${TAG}_a.log; tail -n 2 gpurun_out/ncu_${TAG}_b.log; echo per_step $PER_STEP
