@@ -42,14 +42,62 @@ def load_peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+  """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe: `nvidia-smi --query-gpu=clocks.sm,
+  clocks.max.sm,clocks_event_reasons.*`).  The same counters are read through NVML (pynvml) from a thread every 5 ms — the
+  timed region of a default run is ~60 ms, less than nvidia-smi needs to start up; nvidia-smi -lms is the fallback."""
   Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+  BITS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown'}
 
   def __init__(self, index):
     self.index, self.proc, self.lines = index, None, []
+    self.nvml, self.handle, self.samples, self.stop_flag = None, None, [], False
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      h = None
+      try:
+        import torch
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        if not uuid.startswith('GPU-'):
+          uuid = 'GPU-' + uuid
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
+      except Exception:
+        h = None
+      if h is None:
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = index
+        if vis:
+          try:
+            phys = int(vis.split(',')[index])
+          except Exception:
+            phys = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.nvml, self.handle = pynvml, h
+      self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception:
+      self.nvml = None
+
+  def _poll(self):
+    n = self.nvml
+    while not self.stop_flag:
+      try:
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+          mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+          mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((mhz, mask))
+      except Exception:
+        pass
+      time.sleep(0.005)
 
   def start(self):
+    if self.nvml is not None:
+      self.stop_flag = False
+      self.thread = threading.Thread(target=self._poll, daemon=True)
+      self.thread.start()
+      return
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -63,6 +111,17 @@ class ClockSampler:
       self.lines.append(line.strip())
 
   def stop(self):
+    if self.nvml is not None:
+      self.stop_flag = True
+      self.thread.join(timeout=1.0)
+      sm = [m for m, _ in self.samples]
+      reasons = set()
+      for _, mask in self.samples:
+        for bit, name in self.BITS.items():
+          if mask & bit:
+            reasons.add(name)
+      return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.sm_max, 'reasons': sorted(reasons), 'samples': len(sm),
+              'source': 'nvml'}
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     time.sleep(0.12)
@@ -85,7 +144,7 @@ class ClockSampler:
         if v.lower().startswith('active'):
           reasons.add(name)
     return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-            'reasons': sorted(reasons), 'samples': len(sm)}
+            'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 def work_model(cfg_kw, cond_in):
@@ -239,7 +298,7 @@ def main():
     loss0 = float(model.train_step(data_host)['loss'])
 
   # ---- timed region 1: inputs resident in HBM
-  sampler = ClockSampler(local) if rank == 0 else None
+  sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('WN_BENCH_NO_CLOCKS')) else None
   sync_all()
   if sampler:
     sampler.start()
