@@ -1237,7 +1237,13 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
         if (cs == cudaStreamCaptureStatusNone) {
-          if (h->stack_plans.size() >= 4) { CK(cudaStreamSynchronize(st)); for (auto& q : h->stack_plans) q.release(); h->stack_plans.clear(); }
+          if (h->stack_plans.size() >= 4) {
+            CK(cudaDeviceSynchronize());
+            for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+            h->graphs.clear();
+            for (auto& q : h->stack_plans) q.release();
+            h->stack_plans.clear();
+          }
           std::vector<TcBlockDesc> descs;
           for (int l = 0; l < h->L; ++l) descs.push_back(desc_of(l));
           h->stack_plans.push_back(TcStackPlan{});
@@ -1805,7 +1811,14 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
         if (cs != cudaStreamCaptureStatusNone) { set_err("grouped wgrad: no plan for (%d, %d) while capturing", B, Tn); return WN_ERR_STATE; }
-        if (h->wg_plans.size() >= 4) { CK(cudaStreamSynchronize(st)); for (auto& wp : h->wg_plans) wp.plan.release(); h->wg_plans.clear(); }
+        if (h->wg_plans.size() >= 4) {
+          // captured step graphs hold pointers into the plans' tables: they go with them
+          CK(cudaDeviceSynchronize());
+          for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+          h->graphs.clear();
+          for (auto& wp : h->wg_plans) wp.plan.release();
+          h->wg_plans.clear();
+        }
         h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, TcWgGroupPlan{}});
         plan = &h->wg_plans.back().plan;
         int r = tc_wgrad_group_build(h->tmaps, h->wg_jobs, B, Tn, h->wg_force_split, h->wg_pair_tiles != 0, side_pairs, plan);
