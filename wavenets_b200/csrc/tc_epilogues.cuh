@@ -29,9 +29,12 @@ __device__ __forceinline__ void ld_bias16(const float* p, float* v) {   // share
 }
 
 // out = act(acc + bias[n] + cbias[b][n]) + res      (layers.py:66-74,213,222-223; model.py:105-119,236)
+#ifndef TC_BIASACTRES_IN_PANELS
+#define TC_BIASACTRES_IN_PANELS 8
+#endif
 template <bool FAST> struct TcEpiBiasActRes {
   static constexpr int NIN = 1, NOUT = 1;
-  static constexpr int kInPanels = 8, kOutSlots = 4;
+  static constexpr int kInPanels = TC_BIASACTRES_IN_PANELS, kOutSlots = 4;
   static constexpr bool kGate = false;
   struct Params { const float* bias; const float* cbias; int ldcb; int act; int N; };
   static constexpr int kBiasFloats(int BN) { return BN; }
@@ -113,9 +116,24 @@ template <bool FAST> struct TcEpiGate {
 };
 
 // adjoint of the gate: acc = dg; inputs cached z_f, z_s; outputs dz_f, dz_s
+#ifndef TC_GATEBWD_IN_PANELS
+#define TC_GATEBWD_IN_PANELS 8
+#endif
+#ifndef TC_GATEBWD_OUT_SLOTS
+#define TC_GATEBWD_OUT_SLOTS 2
+#endif
+// Ring depths trade against mainloop stages (every 4 half-panels = one 32 KB operand stage).  Measured on C2 (same box, ms/step):
+// dgrad with 4 input half-panels (4 mainloop stages instead of 3) 6.10 vs 6.25; gate adjoint with 4 instead of 8: 6.36 (its
+// epilogue streams z from HBM and wants the deep ring).
+#ifndef TC_ACTBWD_IN_PANELS
+#define TC_ACTBWD_IN_PANELS 4
+#endif
+#ifndef TC_ACTBWD_OUT_SLOTS
+#define TC_ACTBWD_OUT_SLOTS 4
+#endif
 template <bool FAST> struct TcEpiGateBwd {
   static constexpr int NIN = 2, NOUT = 2;
-  static constexpr int kInPanels = 8, kOutSlots = 2;
+  static constexpr int kInPanels = TC_GATEBWD_IN_PANELS, kOutSlots = TC_GATEBWD_OUT_SLOTS;
   static constexpr bool kGate = false;
   struct Params { int D; };
   static constexpr int kBiasFloats(int BN) { return 0; }
@@ -137,7 +155,7 @@ template <bool FAST> struct TcEpiGateBwd {
 // dgrad: out = (acc + add) * act'(y)    (residual pass-through; activation adjoint from its cached output)
 struct TcEpiActBwd {
   static constexpr int NIN = 2, NOUT = 1;
-  static constexpr int kInPanels = 8, kOutSlots = 4;
+  static constexpr int kInPanels = TC_ACTBWD_IN_PANELS, kOutSlots = TC_ACTBWD_OUT_SLOTS;
   static constexpr bool kGate = false;
   struct Params { int act; };
   static constexpr int kBiasFloats(int BN) { return 0; }
