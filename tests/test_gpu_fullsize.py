@@ -70,3 +70,39 @@ def test_fullsize_batch_permutation(c2):
   assert abs(l2 - l1) <= 1e-5 * abs(l1)
   num = float((g2 - g1).norm()); den = float(g1.norm())
   assert num <= 2e-3 * den, num / den
+
+
+def test_fullsize_schedules_agree(c2):
+  """C2 at full size through the default schedules (stack forward as one persistent launch, grouped weight gradients with
+  side launches) against one launch per block for everything (WN_TC_STACK_FWD=0, WN_TC_GROUP_WGRAD=0): the forward is the
+  same tile arithmetic (loss bit-equal), the gradients differ by fp32 summation order only."""
+  import os
+  from wavenets_b200 import CONFIGS, WaveNet, model_kwargs
+  m, x, c, B, T = c2
+  m.n_replicas = 1
+  for _ in range(3):                                     # plan built, side launches, graph replay
+    l_new = m.train_step((x, c))['loss']
+  g_new = m.get_grads()
+  old = {k: os.environ.get(k) for k in ('WN_TC_STACK_FWD', 'WN_TC_GROUP_WGRAD')}
+  os.environ['WN_TC_STACK_FWD'] = '0'
+  os.environ['WN_TC_GROUP_WGRAD'] = '0'
+  try:
+    kw = model_kwargs(dict(CONFIGS['c2']))
+    m2 = WaveNet(**kw, precision='bf16', max_batch=B, max_time=T)     # the switches are read at wn_create
+    m2.build(((B, T, 1), (B, 109)))
+    m2.set_weights(m.get_weights())
+    l_old = m2.train_step((x, c))['loss']
+    g_old = m2.get_grads()
+  finally:
+    for k, v in old.items():
+      if v is None:
+        os.environ.pop(k, None)
+      else:
+        os.environ[k] = v
+  assert int(m.handle.lib.wn_stack_forward_layers(m.handle.h)) == 30 and int(m2.handle.lib.wn_stack_forward_layers(m2.handle.h)) == 0
+  assert int(m.handle.lib.wn_grouped_wgrad_tiles(m.handle.h, None)) > 0 and int(m2.handle.lib.wn_grouped_wgrad_tiles(m2.handle.h, None)) == 0
+  assert l_new == l_old
+  for k in g_old:
+    ref = g_old[k]
+    err = float(np.abs(g_new[k] - ref).max() / (np.abs(ref).max() + 1e-30))
+    assert err < 3e-4, (k, err)       # 64,000 rows per gradient entry, fp32 chains of different lengths
