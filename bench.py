@@ -243,6 +243,12 @@ def main():
     return 0
 
   # ------------------------------------------------------------------ this repo's CUDA path
+  # stdout carries ONE JSON line: NCCL writes its version banner there when NCCL_DEBUG is VERSION or INFO
+  # (it does on this image even without NCCL_DEBUG in the environment): until the line is printed, file descriptor 1
+  # points at stderr
+  sys.stdout.flush()
+  saved_stdout = os.dup(1)
+  os.dup2(2, 1)
   import torch
   import torch.distributed as dist
   from wavenets_b200 import WaveNet, parallel
@@ -427,6 +433,9 @@ def main():
     sync_all()
     line['full_iteration'] = {'ms': (time.perf_counter() - t0) / n_it * 1e3, 'includes': 'fwd+loss+bwd, clipnorm, Adam, re-pack, sampled-waveform MSE',
                               'loss': logs['loss'], 'mean_squared_error': logs.get('mean_squared_error')}
+  sys.stdout.flush()
+  os.dup2(saved_stdout, 1)
+  os.close(saved_stdout)
   if rank == 0:
     if world == 1 and not args.no_cpu_baseline:
       r = cpu_reference_run(cfg, kw, cond_in, steps=5, warmup=1, budget_s=25.0)
