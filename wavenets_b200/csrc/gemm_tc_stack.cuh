@@ -163,26 +163,14 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
       uint32_t gphase = 0;
       const int ksteps_g = p.nseg * kb_a;
       const int ksteps_o = KB_G + (p.has_res ? KB_X : 0);
-#ifdef TC_TIMELINE_STACK_UNUSED
-      long long tl_rec[12][4]; int tl_n = 0; const long long tl_start = clock64();
-#endif
       for (int pos = 0; pos < n_pos; ++pos) {
         {
           int kind, j;
           blk_tile<NT1>(pos, n_mt, kind, j);
           const bool is_out = kind == NT1;
           const int ksteps = is_out ? ksteps_o : ksteps_g;
-#ifdef TC_TIMELINE_STACK_UNUSED
-          const long long tl0 = clock64();
-#endif
           mbar_wait(&tempty_bar[as], aphase ^ 1);
-#ifdef TC_TIMELINE_STACK_UNUSED
-          const long long tl1 = clock64();
-#endif
           if (is_out) { mbar_wait(g_full, gphase); gphase ^= 1; }     // both CTAs' g tiles are in shared memory
-#ifdef TC_TIMELINE_STACK_UNUSED
-          const long long tl2 = clock64();
-#endif
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * Cfg::BN);
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -204,16 +192,9 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-#ifdef TC_TIMELINE_STACK_UNUSED
-          if (tl_n < 12) { tl_rec[tl_n][0] = tl1 - tl0; tl_rec[tl_n][1] = tl2 - tl1; tl_rec[tl_n][2] = clock64() - tl2; tl_rec[tl_n][3] = tl0 - tl_start; ++tl_n; }
-#endif
           if (++as == 2) { as = 0; aphase ^= 1; }
         }
       }
-#ifdef TC_TIMELINE_STACK_UNUSED
-      if (blockIdx.x == 0 && lane == 0)
-        for (int i = 0; i < tl_n; ++i) printf("BLK mma tile %d: t0 %lld wait_tempty %lld wait_g %lld issue %lld\n", i, tl_rec[i][3], tl_rec[i][0], tl_rec[i][1], tl_rec[i][2]);
-#endif
     }
   } else if (warp == 2) {
     // ===================== TMA-store warp =====================
@@ -304,9 +285,6 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
     int as = 0; uint32_t aphase = 0;
     int oslot = 0; uint32_t ophase = 0;
 
-#ifdef TC_TIMELINE_STACK_UNUSED
-    long long tl_rec[12][3]; int tl_n = 0; const long long tl_start = clock64();
-#endif
     for (int pos = 0; pos < n_pos; ++pos) {
       int nt, j;
       blk_tile<NT1>(pos, n_mt, nt, j);
@@ -322,14 +300,8 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
         float bias_reg = 0.f;
         if (is_out) { if (tid < R_) bias_reg = TcEpiBiasActRes<true>::bias_load(po, bsafe, 0, R_, tid); }
         else bias_reg = TcEpiGate<true>::bias_load(pg, bsafe, nt * (Cfg::BN / 2), Cfg::BN, tid);
-#ifdef TC_TIMELINE_STACK_UNUSED
-        const long long te0 = clock64();
-#endif
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-#ifdef TC_TIMELINE_STACK_UNUSED
-        const long long te1 = clock64();
-#endif
         // table double-buffered by tile parity: a warp that runs ahead into the next tile must not overwrite entries
         // other warps still read (the epilogue warps only meet at this barrier, once per tile)
         float* const bs = bias_s + as * 256;
@@ -403,19 +375,12 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             if (++oslot == Cfg::OUT_SLOTS) { oslot = 0; ophase ^= 1; }
           }
         }
-#ifdef TC_TIMELINE_STACK_UNUSED
-        if (tl_n < 12) { tl_rec[tl_n][0] = te1 - te0; tl_rec[tl_n][1] = clock64() - te1; tl_rec[tl_n][2] = te0 - tl_start; ++tl_n; }
-#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote_relaxed(&tempty_bar[as], 0u);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-#ifdef TC_TIMELINE_STACK_UNUSED
-    if (blockIdx.x == 0 && threadIdx.x == 128)
-      for (int i = 0; i < tl_n; ++i) printf("BLK epi tile %d: t0 %lld wait_tfull %lld work %lld\n", i, tl_rec[i][2], tl_rec[i][0], tl_rec[i][1]);
-#endif
   }
   tc_fence_before();
   __syncthreads();
