@@ -26,9 +26,9 @@ if ROOT not in sys.path:
 
 METRIC = 'audio samples/sec fwd+bwd WaveNet stack'
 # dram__bytes_read + write per launch, mean over the launches of the dilated-conv kernel class in one C2 step (ncu launch list,
-# cold cache, profiles/launches_r1_c2_v5_summary.txt): 30 fused block forwards (94.1 MB), 30 dgrads (107.4 MB), the 7 grouped
-# weight-gradient launches (6.01 GB together) and their finish (0.25 GB) = 12.3 GB over 68 launches
-TRAFFIC_C2 = 1.81e8
+# cold cache, profiles/launches_r1_c2_v7_summary.txt): the stack forward (3.99 GB: 30 blocks in one launch), 30 dgrads
+# (108.2 MB each), the 7 grouped weight-gradient launches (6.00 GB together) and their finish (0.25 GB) = 13.49 GB over 39 launches
+TRAFFIC_C2 = 3.46e8
 UNIT = 'samples/s'
 
 
@@ -386,7 +386,7 @@ def main():
               # dram__bytes_read+write per launch, mean over the class's kernels, from one `ncu --set full` capture of the C2
               # step (cold cache; profiles/ncu_full_r1e_c2_{blockfwd,bwd}.txt): fused block forward 98.0 MB, dgrad 110.5 MB,
               # dilated wgrad 107.5 MB, its finish 19.1 MB.  Only valid for the default workload.
-              'traffic': TRAFFIC_C2 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and fused_blocks and wg_tiles) else None,
+              'traffic': TRAFFIC_C2 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and stack_layers and wg_tiles) else None,
               'kernel': (('tc_stack_fwd_kernel (gated conv + gate + conv1 + residual of ALL layers in one persistent launch, CTA pairs) + ' if stack_layers else
                           'tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ') if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + ')
               + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + '
