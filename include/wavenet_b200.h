@@ -145,6 +145,10 @@ int wn_adam_init(wn_handle* h, float lr, float beta1, float beta2, float eps, fl
 int wn_clip_grads(wn_handle* h, void* stream);
 int wn_adam_step(wn_handle* h, float lr /* < 0: keep */, void* stream);   /* also re-packs the kernel-side weights */
 int wn_adam_state(wn_handle* h, float** m_dev, float** v_dev, float** grad_norms_dev, int64_t* step);
+/* copies Adam's moments (flat fp32 device buffers of wn_param_count() floats, e.g. another handle's wn_adam_state) and the
+ * step counter into this handle: a model rebuilt for a larger (batch, time) workspace keeps training where it was, like a
+ * Keras optimizer whose slots outlive a re-traced train_step (model.py:211,336). */
+int wn_adam_restore(wn_handle* h, const float* m_dev, const float* v_dev, int64_t step);
 
 /* ---- dropout (layers.py:109-112,195-196; Keras Dropout on the block input of the conv branch) --------
  * Training passes draw keep-masks with a counter-based Philox-4x32-10 keyed by (seed, step): TF's RNG
@@ -160,6 +164,17 @@ int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void*
 /* ---- WaveNet.call (model.py:213-239): x (B,T) fp32, cond (B,cond_in) fp32 or NULL ->
  *      out (B,T,2^bits) softmax probabilities or (B,T,3M) mixture parameters, fp32 -------- */
 int wn_forward(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, float* out_dev, void* stream);
+/* the same with Keras' `training` argument (model.py:213, layers.py:178,195-196): training != 0 applies the block dropout
+ * (fresh Philox masks, or the masks injected with wn_set_dropout_masks) exactly as the forward half of wn_train_step does. */
+int wn_forward_ex(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, int training, float* out_dev, void* stream);
+
+/* ---- WaveNet.loss_fn(target, pred) (model.py:505-551) on MATERIALISED predictions ------------------------------------
+ * pred (B,T,Cout) fp32 = a WaveNet.call output (softmax probabilities, or [weights | means | log-scales] mixture
+ * parameters); out (B,T) fp32 per-position losses, NOT reduced (the caller applies tf.nn.compute_average_loss, model.py:328).
+ * categorical: target_is_int64 != 0: (B,T) int64 class indices (prepare_target's output), else (B,T) fp32 samples that are
+ *   quantised on the fly; Keras 3 sparse_categorical_crossentropy on probabilities: clip to [1e-7, 1-1e-7], log, softmax
+ *   cross entropy on those logits.  mixtures: (B,T) fp32 samples (model.py:155: the target is the waveform itself). */
+int wn_loss_fn(wn_handle* h, const void* target_dev, int target_is_int64, const float* pred_dev, int B, int T, float* out_dev, void* stream);
 
 /* ---- WaveNet.train_step up to the gradients (model.py:309-335) and test_step (:362-381) ---
  * frames (B,T+1) fp32 in [-1,1]; loss_dev points at TWO floats, the reference's two metrics
@@ -173,6 +188,22 @@ int wn_test_step(wn_handle* h, const float* frames_dev, const float* cond_dev, i
 /* same with HOST buffers: H2D of frames/cond, step, D2H of the two loss floats, stream sync. */
 int wn_train_step_host(wn_handle* h, const float* frames_host, const float* cond_host, int B, int T,
                        int n_replicas, float* loss_host);
+
+/* ---- data parallelism: tf.distribute.MirroredStrategy (train.py:203) = one replica per GPU, gradients SUM-reduced inside
+ *      optimizer.apply_gradients (model.py:336; the loss is already divided by the global batch, model.py:328).  One
+ *      process per GPU here; the replicas' handles share an NCCL communicator (NCCL is dlopen'ed: libnccl.so.2 already in
+ *      the process, else the system one, else $WN_NCCL_LIB).  Rank 0 draws the 128-byte id, every rank passes it (sent by
+ *      whatever channel the host has: torch.distributed, MPI, a file) to wn_comm_init together with its rank.
+ *      wn_comm_attach takes an ncclComm_t the caller already owns (e.g. TensorFlow's or torch's) instead.
+ *      wn_allreduce_grads: ncclAllReduce(SUM, fp32) in place over wn_grads_dev() on `stream`; a no-op for one replica.
+ *      wn_comm_fuse_allreduce(on): wn_train_step(n_replicas > 1) enqueues that all-reduce itself behind the backward pass,
+ *      inside the captured step graph (use when nothing — e.g. per-replica clipnorm — must run between the two). */
+int wn_nccl_unique_id(uint8_t* id128);
+int wn_comm_init(wn_handle* h, const uint8_t* id128, int nranks, int rank);
+int wn_comm_attach(wn_handle* h, void* nccl_comm /* ncclComm_t or NULL to detach */, int nranks, int rank);
+int wn_comm_fuse_allreduce(wn_handle* h, int on);
+int wn_allreduce_grads(wn_handle* h, void* stream);
+const char* wn_nccl_info(void);   /* "NCCL <version> from <path>" or "unavailable: ..." */
 
 /* ---- WaveNetLayer.call (layers.py:178-224) and its adjoint, block granularity -------------
  * x (B,T,R) fp32; cond (B,Cc) fp32 time-constant conditioning or NULL;

@@ -22,6 +22,8 @@ EXPORTS = [
   'wn_get_grad', 'wn_params_changed', 'wn_quantize', 'wn_forward', 'wn_train_step', 'wn_test_step',
   'wn_train_step_host', 'wn_layer_forward', 'wn_layer_backward', 'wn_last_launch_count',
   'wn_fused_forward_blocks', 'wn_grouped_wgrad_tiles', 'wn_stack_forward_layers', 'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_num_frames', 'wn_preprocess_frames', 'wn_inverse_mu_law', 'wn_one_hot', 'wn_sample_waveform', 'wn_sample_last_step', 'wn_generate', 'wn_adam_init', 'wn_clip_grads', 'wn_adam_step', 'wn_adam_state', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
+  'wn_forward_ex', 'wn_loss_fn', 'wn_adam_restore', 'wn_nccl_unique_id', 'wn_comm_init', 'wn_comm_attach', 'wn_comm_fuse_allreduce',
+  'wn_allreduce_grads', 'wn_nccl_info',
 ]
 
 
@@ -81,6 +83,15 @@ def load():
   lib.wn_params_changed.argtypes = [vp, vp]
   lib.wn_quantize.argtypes = [vp, vp, i64, i32, vp]
   lib.wn_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+  lib.wn_forward_ex.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+  lib.wn_loss_fn.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp]
+  lib.wn_adam_restore.argtypes = [vp, vp, vp, i64]
+  lib.wn_nccl_unique_id.argtypes = [vp]
+  lib.wn_comm_init.argtypes = [vp, vp, i32, i32]
+  lib.wn_comm_attach.argtypes = [vp, vp, i32, i32]
+  lib.wn_comm_fuse_allreduce.argtypes = [vp, i32]
+  lib.wn_allreduce_grads.argtypes = [vp, vp]
+  lib.wn_nccl_info.restype = C.c_char_p
   lib.wn_train_step.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
   lib.wn_test_step.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
   lib.wn_train_step_host.argtypes = [vp, vp, vp, i32, i32, i32, vp]

@@ -16,13 +16,13 @@ LIB = os.path.join(HERE, 'libwavenet_b200.so')
 STAMP = os.path.join(HERE, '.libwavenet_b200.stamp')
 
 SOURCES = ['wn_api.cu']
-HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'gemm_tc_stack.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh',
+HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'gemm_tc_stack.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh', 'nccl_dl.cuh',
            os.path.join('..', '..', 'include', 'wavenet_b200.h')]
 
 NVCC_FLAGS = [
   '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
   '-Xcompiler', '-fPIC', '-shared', '--expt-relaxed-constexpr',
-  '-Xptxas', '-v',
+  '-Xptxas', '-v', '-ldl',
 ]
 
 

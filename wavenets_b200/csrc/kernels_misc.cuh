@@ -607,6 +607,27 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ WaveNet.loss_fn on materialised probabilities (model.py:516)
+// tf.keras.losses.sparse_categorical_crossentropy(target, probs), Keras 3 semantics [TF-internal, restated]: the probabilities
+// are clipped to [1e-7, 1 - 1e-7], their logarithm is taken as logits of sparse_softmax_cross_entropy_with_logits:
+//   l = log(sum_i clip(p_i)) - log(clip(p_y)).   One warp per row; the target is an int64 class index or, when idx == null,
+// a waveform sample quantised like prepare_target (model.py:151-155).
+__global__ void __launch_bounds__(256) ce_probs_rows_kernel(const float* __restrict__ probs, int C, const long long* __restrict__ idx,
+                                                            const float* __restrict__ wave, int bits, long long rows, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float* p = probs + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += fminf(fmaxf(p[c], 1e-7f), 1.0f - 1e-7f);
+  s = warp_sum(s);
+  if (lane == 0) {
+    long long y = idx ? idx[row] : (long long)wn_quantize_idx(wave[row], bits);
+    y = y < 0 ? 0 : (y >= C ? C - 1 : y);
+    out[row] = logf(s) - logf(fminf(fmaxf(p[y], 1e-7f), 1.0f - 1e-7f));
+  }
+}
+
 // ------------------------------------------------------------------ mixture losses (model.py:517-547)
 // One thread per row; pred fp32 [rows][ldp] = [weights M | means M | log-scales M].
 // kind: 1 logistic, 2 gaussian.  SQRT2PI is the fp32 value of sqrt(2*3.14159265359) (model.py:9).
@@ -614,14 +635,16 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
 template <class TD>
 __global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restrict__ pred, int ldp, int M, const float* __restrict__ frames,
                                                            int Tn, long long rows, int bits, int kind, float scale, TD* __restrict__ dpred,
-                                                           int ldd, float* __restrict__ loss_partial) {
+                                                           int ldd, float* __restrict__ loss_partial, int frame_stride, int frame_off,
+                                                           float* __restrict__ row_out) {
   __shared__ float wsum[4];
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float loss = 0.f;
   if (row < rows) {
     const float* p = pred + row * ldp;
     const long long b = row / Tn, t = row % Tn;
-    const float y = frames[b * (Tn + 1) + t + 1];
+    // training / test step: the target of position t is frames[b][t+1] (model.py:319); loss_fn: a dense (B,T) target
+    const float y = frames[b * frame_stride + t + frame_off];
     float pi[WN_MAX_MIX], comp[WN_MAX_MIX];
     float wmax = -INFINITY;
     for (int m = 0; m < M; ++m) wmax = fmaxf(wmax, p[m]);
@@ -648,6 +671,7 @@ __global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restri
       lik += pi[m] * comp[m];
     }
     loss = -logf(lik);
+    if (row_out) row_out[row] = loss;
     if (dpred) {
       const float linv = 1.0f / lik;
       TD* d = dpred + row * ldd;

@@ -28,6 +28,7 @@
 #include "gemm_tc_stack.cuh"
 #include "kernels_misc.cuh"
 #include "generate.cuh"
+#include "nccl_dl.cuh"
 
 // ============================================================================ errors
 static thread_local char g_err[512] = "";
@@ -243,6 +244,9 @@ struct wn_handle {
   TcWgradFinish pend_finish{}; bool pend_valid = false; int pend_blocks = 0; long long pend_partial_elems = 0, pend_cs_elems = 0;
   std::vector<PackJob> pack_jobs;
   PackJob* d_pack_jobs = nullptr; long long pack_blocks = 0; bool pack_ready = false;
+  // data parallelism (train.py:203): NCCL communicator of the replicas; the gradient all-reduce is the only collective
+  wn_ncclComm_t comm = nullptr; bool comm_owned = false; int comm_nranks = 1, comm_rank = 0;
+  int ar_in_step = 0;       // wn_train_step enqueues the all-reduce itself, behind the backward pass (inside the step graph)
 };
 
 enum { CLS_DILATED = 1, CLS_GEMM = 2, CLS_LOSS = 3, CLS_MISC = 4 };
@@ -683,6 +687,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
 extern "C" void wn_destroy(wn_handle* h) {
   if (!h) return;
   cudaDeviceSynchronize();
+  if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto& p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto e : h->ev_blk_in) cudaEventDestroy(e);
@@ -1315,7 +1320,7 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
       nparts = cdiv(rows, 128);
       mixture_loss_kernel<T><<<nparts, 128, 0, st>>>(h->logits, h->ldl, c.num_mixtures, frames, Tn, rows, c.bits,
                                                     c.sampling_function == WN_GAUSSIAN ? 2 : 1, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
-                                                    loss_out ? h->loss_partial : nullptr);
+                                                    loss_out ? h->loss_partial : nullptr, Tn + 1, 1, nullptr);
     }
   }
   if (loss_out) {
@@ -1854,6 +1859,13 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   return WN_OK;
 }
 
+// captured step graphs bake in the launch sequence: anything that changes it (communicator, fused all-reduce) drops them
+static void drop_graphs_fwd(wn_handle* h) {
+  cudaDeviceSynchronize();
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
 // ============================================================================ public entry points
 static int check_bt(wn_handle* h, int B, int T) {
   if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
@@ -2165,6 +2177,18 @@ extern "C" int wn_adam_state(wn_handle* h, float** m_dev, float** v_dev, float**
   return WN_OK;
 }
 
+// optimizer state of another handle of the same model (a rebuild for a larger workspace keeps training where it was)
+extern "C" int wn_adam_restore(wn_handle* h, const float* m_dev, const float* v_dev, int64_t step) {
+  if (!h || !h->opt_m) { set_err("call wn_adam_init first"); return WN_ERR_STATE; }
+  if (!m_dev || !v_dev || step < 0) { set_err("bad optimizer state"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t bytes = (size_t)h->n_scalars * 4;
+  CK(cudaMemcpy(h->opt_m, m_dev, bytes, cudaMemcpyDeviceToDevice));
+  CK(cudaMemcpy(h->opt_v, v_dev, bytes, cudaMemcpyDeviceToDevice));
+  h->opt_t = step;
+  return WN_OK;
+}
+
 static void drop_graphs(wn_handle* h) {
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   h->graphs.clear();
@@ -2200,9 +2224,22 @@ extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int 
   return WN_OK;
 }
 
+// fresh Philox keep-masks for a training pass (unless the caller injected masks): bumps the device step counter
+static void draw_dropout_masks(wn_handle* h, cudaStream_t st, int B, int Tn) {
+  if (!h->drop_active || h->drop_injected) return;
+  const size_t rows_cap = (size_t)h->maxB * h->maxT;
+  const long long n4 = ((long long)B * Tn * h->R + 3) / 4;
+  { LaunchScope ls(h, st, CLS_MISC); dropout_step_bump<<<1, 1, 0, st>>>(h->d_drop_ctr); }
+  LaunchScope ls(h, st, CLS_MISC);
+  dropout_mask_philox<<<dim3(cdiv(n4, 256), h->L), 256, 0, st>>>(h->drop_mask, n4, (long long)rows_cap * h->R, h->cfg.dropout, h->drop_seed,
+                                                                h->d_drop_ctr);
+}
+
 template <class T>
-static int forward_entry(wn_handle* h, const float* x, const float* cond, int B, int Tn, float* out, cudaStream_t st) {
-  h->drop_active = false;   // WaveNet.call(training=False)
+static int forward_entry(wn_handle* h, const float* x, const float* cond, int B, int Tn, int training, float* out, cudaStream_t st) {
+  // WaveNet.call(inputs, training): Keras Dropout is active only under training=True (layers.py:195-196)
+  h->drop_active = training && h->cfg.dropout > 0.f;
+  draw_dropout_masks(h, st, B, Tn);
   RET(model_forward<T>(h, st, x, Tn, cond, B, Tn));
   if (h->cfg.sampling_function == WN_CATEGORICAL) {
     RET(loss_forward<T>(h, st, nullptr, B, Tn, 0.f, false, out, nullptr));
@@ -2212,37 +2249,124 @@ static int forward_entry(wn_handle* h, const float* x, const float* cond, int B,
   return WN_OK;
 }
 
-extern "C" int wn_forward(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, float* out_dev, void* stream) {
+extern "C" int wn_forward_ex(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, int training, float* out_dev, void* stream) {
   RET(check_bt(h, B, T));
   if (!h->cfg.has_head || !h->cfg.has_input_conv) { set_err("wn_forward needs a full model handle"); return WN_ERR_STATE; }
   if (h->cfg.conditioning && !cond_dev) { set_err("Conditioning must be provided."); return WN_ERR_VALUE; }
+  if (training && h->cfg.dropout >= 1.f) { set_err("dropout must be < 1 for training"); return WN_ERR_VALUE; }
   CK(cudaSetDevice(h->cfg.device));
   h->launches = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int r = h->cfg.precision == WN_BF16 ? forward_entry<bf16>(h, x_dev, cond_dev, B, T, out_dev, st) : forward_entry<float>(h, x_dev, cond_dev, B, T, out_dev, st);
+  int r = h->cfg.precision == WN_BF16 ? forward_entry<bf16>(h, x_dev, cond_dev, B, T, training, out_dev, st)
+                                      : forward_entry<float>(h, x_dev, cond_dev, B, T, training, out_dev, st);
   RET(r);
   CK(cudaGetLastError());
   h->fwd_valid = false;
+  h->drop_active = false;
   return WN_OK;
+}
+extern "C" int wn_forward(wn_handle* h, const float* x_dev, const float* cond_dev, int B, int T, float* out_dev, void* stream) {
+  return wn_forward_ex(h, x_dev, cond_dev, B, T, 0, out_dev, stream);
+}
+
+// WaveNet.loss_fn(target, pred) (model.py:505-551) on materialised predictions, per (b, t), no reduction
+extern "C" int wn_loss_fn(wn_handle* h, const void* target_dev, int target_is_int64, const float* pred_dev, int B, int T, float* out_dev, void* stream) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if (!h->cfg.has_head) { set_err("wn_loss_fn needs a full model handle"); return WN_ERR_STATE; }
+  if (B < 1 || T < 1 || !target_dev || !pred_dev || !out_dev) { set_err("bad loss_fn arguments"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const wn_config& c = h->cfg;
+  const long long rows = (long long)B * T;
+  if (c.sampling_function == WN_CATEGORICAL) {
+    ce_probs_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(pred_dev, h->Cout, target_is_int64 ? (const long long*)target_dev : nullptr,
+                                                       target_is_int64 ? nullptr : (const float*)target_dev, c.bits, rows, out_dev);
+  } else {
+    if (target_is_int64) { set_err("mixture losses take the waveform itself as target (model.py:155)"); return WN_ERR_VALUE; }
+    mixture_loss_kernel<float><<<cdiv(rows, 128), 128, 0, st>>>(pred_dev, h->Cout, c.num_mixtures, (const float*)target_dev, T, rows, c.bits,
+                                                               c.sampling_function == WN_GAUSSIAN ? 2 : 1, 1.0f, nullptr, 0, nullptr, T, 0, out_dev);
+  }
+  CK(cudaGetLastError());
+  return WN_OK;
+}
+
+// MirroredStrategy's gradient reduction (train.py:203, model.py:336): the loss is already divided by the GLOBAL batch
+// (model.py:328), so the replicas' gradients are SUMMED — one ncclAllReduce over the flat fp32 buffer, in place
+static int allreduce_grads(wn_handle* h, cudaStream_t st) {
+  if (!h->comm) { set_err("no communicator: call wn_comm_init / wn_comm_attach first"); return WN_ERR_STATE; }
+  h->launches++;
+  const int r = g_nccl.AllReduce(h->d_grads, h->d_grads, (size_t)h->n_scalars, WN_NCCL_FLOAT32, WN_NCCL_SUM, h->comm, st);
+  if (r != 0) { set_err("ncclAllReduce failed (%d): %s", r, nccl_errstr(r)); return WN_ERR_CUDA; }
+  return WN_OK;
+}
+
+extern "C" int wn_nccl_unique_id(uint8_t* id128) {
+  if (!id128) { set_err("null argument"); return WN_ERR_VALUE; }
+  char err[256];
+  if (nccl_load(err, sizeof(err)) != 0) { set_err("%s", err); return WN_ERR_CUDA; }
+  wn_ncclUniqueId id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) { set_err("ncclGetUniqueId failed (%d): %s", r, nccl_errstr(r)); return WN_ERR_CUDA; }
+  memcpy(id128, id.internal, 128);
+  return WN_OK;
+}
+extern "C" int wn_comm_init(wn_handle* h, const uint8_t* id128, int nranks, int rank) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_err("bad communicator arguments"); return WN_ERR_VALUE; }
+  char err[256];
+  if (nccl_load(err, sizeof(err)) != 0) { set_err("%s", err); return WN_ERR_CUDA; }
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->comm && h->comm_owned) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  wn_ncclUniqueId id;
+  memcpy(id.internal, id128, 128);
+  wn_ncclComm_t c = nullptr;
+  const int r = g_nccl.CommInitRank(&c, nranks, id, rank);
+  if (r != 0) { set_err("ncclCommInitRank failed (%d): %s", r, nccl_errstr(r)); return WN_ERR_CUDA; }
+  h->comm = c; h->comm_owned = true; h->comm_nranks = nranks; h->comm_rank = rank;
+  drop_graphs_fwd(h);
+  return WN_OK;
+}
+extern "C" int wn_comm_attach(wn_handle* h, void* nccl_comm, int nranks, int rank) {
+  if (!h || nranks < 1) { set_err("bad communicator arguments"); return WN_ERR_VALUE; }
+  char err[256];
+  if (nccl_comm && nccl_load(err, sizeof(err)) != 0) { set_err("%s", err); return WN_ERR_CUDA; }
+  if (h->comm && h->comm_owned) g_nccl.CommDestroy(h->comm);
+  h->comm = (wn_ncclComm_t)nccl_comm; h->comm_owned = false; h->comm_nranks = nccl_comm ? nranks : 1; h->comm_rank = rank;
+  drop_graphs_fwd(h);
+  return WN_OK;
+}
+extern "C" int wn_comm_fuse_allreduce(wn_handle* h, int on) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if ((on != 0) != (h->ar_in_step != 0)) { h->ar_in_step = on ? 1 : 0; drop_graphs_fwd(h); }
+  return WN_OK;
+}
+extern "C" int wn_allreduce_grads(wn_handle* h, void* stream) {
+  if (!h) { set_err("null handle"); return WN_ERR_VALUE; }
+  if (h->comm_nranks <= 1) return WN_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  return allreduce_grads(h, (cudaStream_t)stream);
+}
+extern "C" const char* wn_nccl_info(void) {
+  static char buf[400];
+  char err[256];
+  if (nccl_load(err, sizeof(err)) != 0) { snprintf(buf, sizeof(buf), "unavailable: %s", err); return buf; }
+  int v = 0;
+  if (g_nccl.GetVersion) g_nccl.GetVersion(&v);
+  snprintf(buf, sizeof(buf), "NCCL %d from %s", v, g_nccl.where);
+  return buf;
 }
 
 template <class T>
 static int step_entry(wn_handle* h, const float* frames, const float* cond, int B, int Tn, int nrep, float* loss, cudaStream_t st, bool train) {
   const float scale = 1.0f / ((float)B * (float)nrep);
   h->drop_active = train && h->cfg.dropout > 0.f;
-  if (h->drop_active && !h->drop_injected) {
-    const size_t rows_cap = (size_t)h->maxB * h->maxT;
-    const long long n4 = ((long long)B * Tn * h->R + 3) / 4;
-    { LaunchScope ls(h, st, CLS_MISC); dropout_step_bump<<<1, 1, 0, st>>>(h->d_drop_ctr); }
-    LaunchScope ls(h, st, CLS_MISC);
-    dropout_mask_philox<<<dim3(cdiv(n4, 256), h->L), 256, 0, st>>>(h->drop_mask, n4, (long long)rows_cap * h->R, h->cfg.dropout, h->drop_seed,
-                                                                  h->d_drop_ctr);
-  }
+  draw_dropout_masks(h, st, B, Tn);
   RET(model_forward<T>(h, st, frames, Tn + 1, cond, B, Tn));
   RET(loss_forward<T>(h, st, frames, B, Tn, scale, train, nullptr, loss));
   if (train) {
     const float l2coef = h->cfg.l2_reg_factor > 0.f ? 2.0f * h->cfg.l2_reg_factor / (float)nrep : 0.f;
     RET(model_backward<T>(h, st, frames, Tn + 1, cond, B, Tn, l2coef));
+    if (h->ar_in_step && h->comm && h->comm_nranks > 1 && nrep > 1) RET(allreduce_grads(h, st));
   }
   return WN_OK;
 }

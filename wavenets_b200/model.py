@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import warnings
 from typing import Optional
 
 import numpy as np
@@ -42,6 +43,13 @@ class _PendingLogs:
         out[metric.name] = metric.result()
       self._out = out
     return self._out
+
+
+class _RawView:
+  """Zero-copy view of `n` fp32 values at a device address owned by the C library."""
+
+  def __init__(self, ptr: int, n: int):
+    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2, 'strides': None}
 
 
 class WaveNet:
@@ -129,7 +137,11 @@ class WaveNet:
     self._pin_logs, self._pin_events, self._pending_slot = None, None, 0
     self._last_frames, self._last_rows = None, 0
     self.n_replicas = 1          # MirroredStrategy replica count (train.py:203); set by parallel.attach()
-    self._process_group = None
+    self.replica_rank = 0        # this process's replica index: folded into the dropout key (independent masks per replica)
+    self._process_group = None   # torch.distributed group (gloo tests / fallback when NCCL cannot be loaded)
+    self._comm = None            # (id bytes, nranks, rank) of the NCCL communicator living inside the C library
+    self._dropout_seed = 0x243F6A8885A308D3
+    self._ar_fused = False
 
   # ------------------------------------------------------------------ compile (model.py:157-169)
   def compile(self, **kwargs):
@@ -182,12 +194,31 @@ class WaveNet:
     cfg.max_batch = B
     cfg.max_time = T
     cfg.device = self.device_index
-    old = None
+    old, old_opt = None, None
     if self._handle is not None:
+      # a rebuild (larger batch / longer segments than the workspace was sized for) moves every device buffer: views handed
+      # out earlier (trainable_variables, handle.flat_grads, ...) die with the old handle; weights and Adam's state move over
+      warnings.warn(f'wavenets_b200: workspace rebuilt for (batch, time) = ({B}, {T}); device views of the previous handle '
+                    '(trainable_variables, flat_grads, flat_params) are invalid now — pass max_batch / max_time to size it once')
       old = self._handle.get_weights()
+      opt = self.optimizer
+      if opt is not None and getattr(opt, '_handle', None) is self._handle:
+        m, v, step = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self._handle.lib.wn_adam_state(self._handle.h, C.byref(m), C.byref(v), None, C.byref(step)))
+        n = self._handle.n_scalars
+        torch.cuda.synchronize(self._handle.device)
+        old_opt = (torch.as_tensor(_RawView(m.value, n), device=self._handle.device).clone(),
+                   torch.as_tensor(_RawView(v.value, n), device=self._handle.device).clone(), int(step.value))
       self._handle.close()
+      self._staging = {}
     self._handle = Handle(cfg)
+    self._ar_fused = False
     assert self._handle.lib.wn_receptive_field(self._handle.h) == self.receptive_field
+    if self.dropout > 0:
+      # tf.distribute draws independent dropout masks on every replica: the replica index is part of the Philox key
+      _lib.check(self._handle.lib.wn_set_dropout_seed(self._handle.h, C.c_uint64((self._dropout_seed + self.replica_rank) & (2 ** 64 - 1))))
+    if self._comm is not None:
+      self._init_comm(*self._comm)
     if old is not None:
       self._handle.set_weights(old)
     elif self._pending_weights is not None:
@@ -202,6 +233,16 @@ class WaveNet:
       self._pin_events = [torch.cuda.Event() for _ in range(4)]
     if self.optimizer is not None and hasattr(self.optimizer, 'build'):
       self.optimizer.build(self)      # model.py:211
+      if old_opt is not None:
+        h = self._handle
+        _lib.check(h.lib.wn_adam_restore(h.h, h.ptr(old_opt[0]), h.ptr(old_opt[1]), old_opt[2]))
+
+  def _init_comm(self, id_bytes: bytes, nranks: int, rank: int):
+    """NCCL communicator of the replicas inside the C library (wn_comm_init): the gradient all-reduce of MirroredStrategy
+    (train.py:203, model.py:336) then runs behind the C ABI (wn_allreduce_grads)."""
+    h = self._handle
+    buf = (C.c_uint8 * 128).from_buffer_copy(id_bytes)
+    _lib.check(h.lib.wn_comm_init(h.h, buf, int(nranks), int(rank)))
 
   def _ensure_built(self, x, cond):
     B, T = int(x.shape[0]), int(x.shape[1])
@@ -255,8 +296,11 @@ class WaveNet:
     _lib.check(h.lib.wn_set_dropout_masks(h.h, a.ctypes.data_as(C.c_void_p), B, T))
 
   def set_dropout_seed(self, seed: int):
-    h = self.handle
-    _lib.check(h.lib.wn_set_dropout_seed(h.h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+    """Base seed of the dropout masks; every replica adds its rank (independent masks per replica, like tf.distribute)."""
+    self._dropout_seed = int(seed)
+    if self._handle is not None:
+      h = self.handle
+      _lib.check(h.lib.wn_set_dropout_seed(h.h, C.c_uint64((self._dropout_seed + self.replica_rank) & (2 ** 64 - 1))))
 
   # ------------------------------------------------------------------ call (model.py:213-239)
   def _unpack(self, inputs):
@@ -278,13 +322,12 @@ class WaveNet:
       x2 = x
     cond = as_dev(cond, dev) if cond is not None else None
     self._ensure_built(x2, cond)
-    if training and self.dropout > 0:
-      raise NotImplementedError('call(training=True) with dropout>0 is only available fused inside train_step')
     h = self.handle
     B, T = x2.shape
     cout = 3 * self.num_mixtures if self.num_mixtures is not None else 2 ** self.bits
     out = torch.empty((B, T, cout), dtype=torch.float32, device=dev)
-    _lib.check(h.lib.wn_forward(h.h, h.ptr(x2), h.ptr(cond), B, T, h.ptr(out), h.stream_ptr()))
+    # training=True: Keras runs the blocks' Dropout layers (layers.py:195-196) — fresh masks per call
+    _lib.check(h.lib.wn_forward_ex(h.h, h.ptr(x2), h.ptr(cond), B, T, 1 if training else 0, h.ptr(out), h.stream_ptr()))
     return out
 
   __call__ = call
@@ -332,12 +375,23 @@ class WaveNet:
     h = self.handle
     self._last_frames, self._last_rows = frames, B * T
     fn = h.lib.wn_train_step if train else h.lib.wn_test_step
+    if train and self._comm is not None:
+      # nothing runs between backward and all-reduce unless the optimizer clips per replica first
+      fuse = not (self.optimizer is not None and getattr(self.optimizer, 'clipnorm', None))
+      if fuse != self._ar_fused:
+        _lib.check(h.lib.wn_comm_fuse_allreduce(h.h, 1 if fuse else 0))
+        self._ar_fused = fuse
     _lib.check(fn(h.h, h.ptr(frames), h.ptr(cond), B, T, self.n_replicas, h.ptr(h._loss), h.stream_ptr()))
-    if train and self.optimizer is not None and getattr(self.optimizer, 'clipnorm', None):
+    clip = train and self.optimizer is not None and getattr(self.optimizer, 'clipnorm', None)
+    if clip:
       self.optimizer.clip(self)      # Keras: each replica clips its own gradients, then they are summed
-    if train and self._process_group is not None:
-      # MirroredStrategy's gradient all-reduce (SUM: the loss is already divided by the global batch)
-      torch.distributed.all_reduce(h.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self._process_group)
+    if train and self.n_replicas > 1:
+      # MirroredStrategy's gradient all-reduce (SUM: the loss is already divided by the global batch, model.py:328)
+      if self._comm is not None:
+        if not self._ar_fused:       # (fused: wn_train_step enqueued it behind the backward pass, inside the step graph)
+          _lib.check(h.lib.wn_allreduce_grads(h.h, h.stream_ptr()))
+      elif self._process_group is not None:
+        torch.distributed.all_reduce(h.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self._process_group)
     return h._loss[:2]
 
   def train_step(self, data):
@@ -410,7 +464,34 @@ class WaveNet:
     return out
 
   def loss_fn(self, target, pred):
-    raise NotImplementedError('stand-alone loss_fn on materialised predictions is not built: the loss is fused into train_step/test_step')
+    """model.py:505-551 on materialised predictions: `pred` (B,T,C) as `call` returns it (softmax probabilities or mixture
+    parameters), `target` as `prepare_target` returns it ((B,T,1) int64 bins, or the waveform for mixtures).  Returns the
+    un-reduced (B,T) loss tensor like the reference (train_step applies compute_average_loss to it, model.py:328)."""
+    dev = torch.device('cuda', self.device_index)
+    pred = as_dev(pred, dev)
+    if pred.dim() != 3:
+      raise ValueError('pred must be (batch, samples, channels)')
+    B, T, Cp = (int(v) for v in pred.shape)
+    cout = 3 * self.num_mixtures if self.num_mixtures is not None else 2 ** self.bits
+    if Cp != cout:
+      raise ValueError(f'pred has {Cp} channels, the model predicts {cout}')
+    is_idx = False
+    if isinstance(target, torch.Tensor):
+      is_idx = not target.dtype.is_floating_point
+    else:
+      target = np.asarray(target)
+      is_idx = target.dtype.kind in 'iu'
+    if is_idx and self.num_mixtures is not None:
+      raise ValueError('mixture losses take the waveform itself as target (model.py:155)')
+    tgt = as_dev(target, dev, dtype=torch.int64 if is_idx else torch.float32).reshape(-1)
+    if tgt.numel() != B * T:
+      raise ValueError('target must hold one value per (batch, sample)')
+    if not self.built:
+      raise ValueError('Model is not built')
+    h = self.handle
+    out = torch.empty((B, T), dtype=torch.float32, device=dev)
+    _lib.check(h.lib.wn_loss_fn(h.h, h.ptr(tgt), 1 if is_idx else 0, h.ptr(pred), B, T, h.ptr(out), h.stream_ptr()))
+    return out
 
   def compute_receptive_field(self, sampling_frequency):
     return self.receptive_field / sampling_frequency

@@ -58,14 +58,41 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
   return flat
 
 
-def attach(model, group=None):
+def attach(model, group=None, native: Optional[bool] = None):
   """Make `model.train_step` behave like a MirroredStrategy replica: losses are divided by
-  B_local * n_replicas and gradients are SUM-all-reduced after the backward pass."""
+  B_local * n_replicas and gradients are SUM-all-reduced after the backward pass.
+
+  On GPUs the all-reduce runs behind the C ABI (`wn_comm_init` / `wn_allreduce_grads`): rank 0 draws an NCCL unique id in
+  the C library, torch.distributed only carries those 128 bytes to the other ranks.  `native=False` (and every CPU / gloo
+  process group) keeps `torch.distributed.all_reduce` on the flat gradient buffer instead."""
   world = dist.get_world_size(group) if dist.is_initialized() else 1
+  rank = dist.get_rank(group) if dist.is_initialized() else 0
   model.n_replicas = world
-  model._process_group = group if world > 1 else None
-  if world > 1 and group is None:
-    model._process_group = dist.group.WORLD
+  model.replica_rank = rank
+  model._process_group = None
+  model._comm = None
+  if world > 1:
+    model._process_group = group if group is not None else dist.group.WORLD
+    if native is None:
+      native = torch.cuda.is_available() and dist.get_backend(group) == 'nccl'
+    if native:
+      from . import _lib
+      lib = _lib.load()
+      idbuf = torch.zeros(128, dtype=torch.uint8)
+      if rank == 0:
+        import ctypes as C
+        raw = (C.c_uint8 * 128)()
+        _lib.check(lib.wn_nccl_unique_id(raw))
+        idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+      dev = torch.device('cuda', torch.cuda.current_device())
+      idbuf = idbuf.to(dev)
+      dist.broadcast(idbuf, src=dist.get_global_rank(model._process_group, 0) if hasattr(dist, 'get_global_rank') else 0,
+                     group=model._process_group)
+      model._comm = (bytes(idbuf.cpu().tolist()), world, rank)
+      if getattr(model, '_handle', None) is not None:
+        model._init_comm(*model._comm)
+  if getattr(model, '_handle', None) is not None and getattr(model, 'dropout', 0) > 0:
+    model.set_dropout_seed(model._dropout_seed)     # re-key with this replica's rank
   return model
 
 
