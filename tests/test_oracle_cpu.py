@@ -151,3 +151,43 @@ def test_adam_known_answer():
   p2, st2 = wo.adam_step({'w': np.array([3.0, 4.0])}, {'w': np.array([3.0, 4.0])}, {}, lr=0.1, clipnorm=1.0)
   assert np.allclose(st2['m']['w'], 0.1 * np.array([0.6, 0.8]))
   assert np.allclose(wo.clip_by_norm(np.array([0.3, 0.4]), 1.0), [0.3, 0.4])
+
+
+@pytest.mark.parametrize('name', sorted(SMALL_MODELS))
+def test_faithful_oracle_exact_mode_equals_oracle(name):
+  """oracle/faithful.py with every rounding switched off is the same function as the NumPy oracle (hand-derived backward)
+  — the bf16-faithful mode then differs from it ONLY by the roundings listed in its header."""
+  from oracle import faithful
+  kw = SMALL_MODELS[name]
+  cond_in = COND_IN if kw.get('conditioning') else 0
+  cfg = oracle_config(kw, cond_in)
+  p = wo.init_params(cfg, seed=1)
+  x, cond = make_inputs(2, 40, cond_in)
+  _, g0, aux = wo.train_step(p, cfg, x.astype(np.float64), None if cond is None else cond.astype(np.float64))
+  l1, g1 = faithful.train_step(p, cfg, x, cond, faithful=False)
+  assert abs(l1 - aux['loss_no_reg']) <= 1e-9 * abs(l1)
+  for k in g0:
+    assert rel_err(g1[k], g0[k]) < 1e-9, k
+  # faithful mode: bf16 storage moves every gradient a little, never a lot (and never not at all)
+  l2, g2 = faithful.train_step(p, cfg, x, cond, faithful=True)
+  assert 0 < abs(l2 - l1) <= 1e-2 * abs(l1)
+  y1 = faithful.forward(p, cfg, x[:, :-1], cond, faithful=False)
+  y2 = faithful.forward(p, cfg, x[:, :-1], cond, faithful=True)
+  assert y1.shape == y2.shape and 0 < np.abs(y1 - y2).max() < 5e-2 * np.abs(y1).max() + 1e-3
+
+
+def test_faithful_rounding_ops():
+  """the rounding operators round where they say: value only / gradient only / both"""
+  import torch
+  from oracle import faithful
+  R = faithful.Rounding(True)
+  x = torch.tensor([1.0 + 2.0 ** -10, -3.0 - 2.0 ** -9], dtype=torch.float64, requires_grad=True)
+  w = torch.tensor([1.0 + 2.0 ** -12, 0.3], dtype=torch.float64)
+  (R.fwd(x) * w).sum().backward()
+  assert torch.equal(x.grad, w)                                  # value rounded, gradient untouched
+  y = R.fwd(x).detach()
+  assert float(y[0]) == 1.0 and float(y[1]) == -3.0              # bf16 keeps 8 significant bits (round to nearest even)
+  x.grad = None
+  (R.bwd(x) * w).sum().backward()
+  assert torch.equal(x.grad, w.to(torch.bfloat16).to(torch.float64))
+  assert torch.equal(R.bwd(x).detach(), x.detach())
