@@ -11,6 +11,7 @@ Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -25,11 +26,17 @@ if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
 METRIC = 'audio samples/sec fwd+bwd WaveNet stack'
-# dram__bytes_read + write per launch, mean over the launches of the dilated-conv kernel class in one C2 step (ncu launch list,
-# cold cache, profiles/launches_r1_c2_v7_summary.txt): the stack forward (3.99 GB: 30 blocks in one launch), 30 dgrads
-# (108.2 MB each), the 7 grouped weight-gradient launches (6.00 GB together) and their finish (0.25 GB) = 13.49 GB over 39 launches
-TRAFFIC_C2 = 3.46e8
 UNIT = 'samples/s'
+# label of wn_profile_get -> the kernel it names (for the JSON line)
+HBM_PHASES = {
+  'loss': 'softmax_ce_reg_kernel / softmax_ce_kernel / mixture_loss_kernel (loss + d logits, one pass)',
+  'skip_sum': 'tc_conv_gemm_staged_kernel<bias_act_res>: skip accumulation as ONE K = L*D GEMM over the cached gate outputs',
+  'head_fwd': 'tc_conv_gemm_staged_kernel<bias_act_res> x head convs (last one writes fp32 logits)',
+  'head_bwd': 'tc_conv_gemm_staged_kernel<dgrad> x head convs (+ their weight gradients when not in the grouped launch)',
+  'input_conv_fwd': 'input_conv_fwd_rows',
+  'input_conv_bwd': 'input_conv_bwd_stage1_wide + reduce_parts_tall x2',
+  'wgrad_group_finish': 'tc_wgrad_group_finish (sums the row splits of every 256x256 gradient tile, L2 term, bias column sums)',
+}
 
 
 def load_peaks():
@@ -147,12 +154,16 @@ class ClockSampler:
             'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
-def work_model(cfg_kw, cond_in):
-  """Algorithmic FLOPs per audio sample (SURVEY.md 8d / BASELINE.md): F = 3 x F_fwd."""
-  from oracle import wavenet_oracle as wo   # flop accounting only (no compute)
-  from tests.util import oracle_config
-  ocfg = oracle_config(cfg_kw, cond_in)
-  return wo.flops_fwd_per_sample(ocfg), ocfg
+def load_dram_profile(config, precision):
+  """Per-kernel DRAM bytes of ONE step from the committed ncu launch list of this workload (profiles/dram_<cfg>.json, written
+  by scripts/ncu_dram_summary.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`):
+  {kernel: {launches, dram_read, dram_write, ms}}; None when no capture of this config is committed."""
+  path = os.path.join(ROOT, 'profiles', f'dram_{config}.json')
+  if not os.path.exists(path):
+    return None
+  with open(path) as f:
+    d = json.load(f)
+  return d if d.get('precision', precision) == precision else None
 
 
 def cpu_reference_run(cfg, kw, cond_in, steps, warmup, budget_s, threads=None):
@@ -161,12 +172,11 @@ def cpu_reference_run(cfg, kw, cond_in, steps, warmup, budget_s, threads=None):
   import torch
   from oracle import wavenet_oracle as wo
   from oracle import torch_ref
-  from tests.util import oracle_config
-  from wavenets_b200 import synth
+  from wavenets_b200 import synth, workmodel
   threads = threads or os.cpu_count()
   torch.set_num_threads(threads)
-  ocfg = oracle_config(kw, cond_in)
-  flops = 3 * wo.flops_fwd_per_sample(ocfg)['total']
+  ocfg = wo.config_from_kwargs(kw, cond_in)
+  flops = 3 * workmodel.flops_fwd_per_sample(kw)['total']
   # size the sample for a few seconds per step (~4e11 FLOP), within [512, recording_length]
   T_full = cfg['recording_length']
   T_s = int(min(T_full, max(512, 4.0e11 / flops)))
@@ -191,6 +201,64 @@ def cpu_reference_run(cfg, kw, cond_in, steps, warmup, budget_s, threads=None):
           'ms_per_step': dt * 1e3, 'steps': len(times)}
 
 
+def model_allreduce_kind(model):
+  if model.n_replicas <= 1:
+    return 'none (1 replica)'
+  if model._comm is not None:
+    return 'ncclAllReduce(SUM, fp32) over the flat gradient buffer behind the C ABI (wn_allreduce_grads), ' + (
+      'enqueued by wn_train_step inside the step graph' if model._ar_fused else 'after per-replica clipnorm')
+  return 'torch.distributed.all_reduce(SUM) on the flat gradient buffer'
+
+
+def check_grads(model, kw, precision, local, rank, world, frames_np, cond_np, B_local, T, cond_in):
+  """SURVEY.md 8e scaling check: the all-reduced gradients of the N shards == the 1-GPU gradients of the concatenated batch
+  (compute_average_loss divides by the GLOBAL batch, model.py:328, so the replicas' gradients are summed)."""
+  import torch
+  import torch.distributed as dist
+  from wavenets_b200 import WaveNet
+  dev = torch.device('cuda', local)
+  data = (torch.from_numpy(frames_np).to(dev), torch.from_numpy(cond_np).to(dev)) if cond_np is not None else torch.from_numpy(frames_np).to(dev)
+  model.train_step_async(data)
+  g_dp = model.handle.flat_grads.clone()
+  # gather every rank's shard on rank 0 (plumbing) and run the whole batch on ONE GPU
+  fr = torch.from_numpy(frames_np).to(dev)
+  parts = [torch.empty_like(fr) for _ in range(world)] if world > 1 else [fr]
+  if world > 1:
+    dist.all_gather(parts, fr)
+  allx = torch.cat(parts, 0)
+  allc = None
+  if cond_np is not None:
+    cd = torch.from_numpy(cond_np).to(dev)
+    cparts = [torch.empty_like(cd) for _ in range(world)] if world > 1 else [cd]
+    if world > 1:
+      dist.all_gather(cparts, cd)
+    allc = torch.cat(cparts, 0)
+  res = None
+  if rank == 0:
+    m1 = WaveNet(**kw, precision=precision, device=local, max_batch=B_local * world, max_time=T)
+    m1.build(((B_local * world, T, 1), (B_local * world, cond_in)) if cond_in else (B_local * world, T, 1))
+    m1.set_weights(model.get_weights())
+    m1.train_step_async((allx, allc) if allc is not None else allx)
+    g1 = m1.handle.flat_grads
+    hh = model.handle
+    worst, who = 0.0, None
+    for name, shape, off in zip(hh.names, hh.shapes, hh.offsets):
+      n = int(np.prod(shape))
+      a, b = g_dp[off:off + n].double(), g1[off:off + n].double()
+      den = float(b.norm())
+      if den == 0.0:
+        continue
+      e = float((a - b).norm()) / den
+      if e > worst:
+        worst, who = e, name
+    res = {'worst_rel_l2': worst, 'tensor': who, 'global_rel_l2': float((g_dp.double() - g1.double()).norm() / g1.double().norm()),
+           'n_replicas': world, 'global_batch': B_local * world}
+    del m1
+  if world > 1:
+    dist.barrier()
+  return res
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -204,6 +272,9 @@ def main():
   ap.add_argument('--channels', type=int, default=None)
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--profile-steps', type=int, default=2)
+  ap.add_argument('--sustain-seconds', type=float, default=3.0, help='length of the additional seconds-long timed region (0 = off)')
+  ap.add_argument('--dropout', type=float, default=None, help="override the config's dropout (defaults.yaml:17 trains with 0.1)")
+  ap.add_argument('--check-grads', action='store_true', help='compare the all-reduced N-GPU gradients with a 1-GPU step on the concatenated batch')
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == 'b200':
     args.warmup = 3   # timing rule: W >= 3
@@ -216,6 +287,8 @@ def main():
     cfg['channels'] = args.channels
     if cfg.get('skip_channels'):
       cfg['skip_channels'] = args.channels
+  if args.dropout is not None:
+    cfg['dropout'] = args.dropout
   precision = args.precision or cfg.get('precision', 'bf16')
   B_local = args.batch or cfg['batch_size']
   T = cfg['recording_length']
@@ -316,7 +389,6 @@ def main():
   sync_all()
   ms_total = max_over_ranks(e0.elapsed_time(e1))
   launches = int(h.lib.wn_last_launch_count(h.h)) * args.steps
-  import ctypes as C
   side_l = C.c_int(0)
   wg_tiles = int(h.lib.wn_grouped_wgrad_tiles(h.h, C.byref(side_l)))   # of the timed (graph-replayed) step
   stack_layers = int(h.lib.wn_stack_forward_layers(h.h))
@@ -350,12 +422,35 @@ def main():
   ms_e2e_sync = max_over_ranks(es0.elapsed_time(es1))
 
   h2d = frames_pin.numel() * 4 + (cond_pin.numel() * 4 if cond_pin is not None else 0)
+  rows = B_local * T
+  step_ms = ms_total / args.steps
 
-  # ---- roofline of the dominant kernel class: the dilated-conv GEMMs (fwd + dgrad + wgrad)
-  flops, ocfg = work_model(kw, cond_in)
+  # ---- timed region 3: a seconds-long run (clocks settled under the power cap): the number the SUSTAINED tensor peak of
+  # MEASURED_PEAKS.json is the matching denominator for (the K-step region above is a fraction of a second: burst peak)
+  sustained = None
+  if args.sustain_seconds > 0:
+    n_sus = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / step_ms)))
+    sync_all()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler2 = ClockSampler(local) if (rank == 0 and not os.environ.get('WN_BENCH_NO_CLOCKS')) else None
+    if sampler2:
+      sampler2.start()
+    s0.record()
+    for i in range(n_sus):
+      model.train_step_async(data_dev)      # (no host sync inside the region: one graph launch per step)
+    s1.record()
+    sync_all()
+    ms_sus = max_over_ranks(s0.elapsed_time(s1))
+    clocks2 = sampler2.stop() if sampler2 else None
+    sustained = {'steps': n_sus, 'seconds': ms_sus * 1e-3, 'ms_per_step': ms_sus / n_sus, 'value': world * rows * n_sus / (ms_sus * 1e-3), 'unit': UNIT,
+                 'clocks': clocks2}
+
+  # ---- per-launch CUDA-event records (eager, single stream): kernel classes and phases
+  from wavenets_b200 import workmodel
+  flops = workmodel.flops_fwd_per_sample(kw)
   peaks = load_peaks()
-  import ctypes as C
   prof = {}
+  by_label = {}
   for tag, name in ((1, 'dilated'), (2, 'gemm_all'), (4, 'all')):
     h.lib.wn_profile_begin(h.h, tag)
     for _ in range(args.profile_steps):
@@ -364,59 +459,120 @@ def main():
     n = C.c_int64()
     h.lib.wn_profile_end(h.h, C.byref(ms), C.byref(n))
     prof[name] = (ms.value / args.profile_steps, n.value // args.profile_steps)
-  rows = B_local * T
-  # grouped weight gradients: ONE launch (+ side launches) computes the gated-conv, conv1, conv_skip and head filter
-  # gradients as 256 x 256 tiles; the launch is timed in this class, so all of its products count as the class's work
-  dil_flops_step = (2.0 * flops['dilated'] + (wg_tiles * 2.0 * 256 * 256 if wg_tiles else flops['dilated'])) * rows
-  # the fused block-forward kernel (gated conv + gate + conv1 + residual in one launch) is timed in this class: its
-  # conv1 products are algorithmic work of the class too (forward only; their adjoints run in other kernels)
-  fused_blocks = int(h.lib.wn_fused_forward_blocks(h.h))
-  dmodel = kw['dilation_channels'] or kw['channels']
-  dil_flops_step += fused_blocks * 2.0 * dmodel * kw['channels'] * rows
-  dil_ms_eager, dil_launches = prof['dilated']
+    if tag == 4:
+      lab = C.create_string_buffer(64)
+      d = C.c_double()
+      nrec = int(h.lib.wn_profile_get(h.h, 0, C.byref(d), lab, 64))
+      for i in range(nrec):
+        h.lib.wn_profile_get(h.h, i, C.byref(d), lab, 64)
+        e = by_label.setdefault(lab.value.decode(), [0.0, 0])
+        e[0] += d.value / args.profile_steps
+        e[1] += 1
+      for e in by_label.values():
+        e[1] = e[1] // args.profile_steps
+  kernels = {k: {'ms_per_step': v[0], 'launches_per_step': v[1]} for k, v in sorted(by_label.items(), key=lambda kv: -kv[1][0])}
+  tiles_c, parts_c, side_c = C.c_int(0), C.c_int(0), C.c_int(0)
+  h.lib.wn_grouped_wgrad_info(h.h, C.byref(tiles_c), C.byref(parts_c), C.byref(side_c))
+  e_bytes = 2 if precision == 'bf16' else 4
+  dram = load_dram_profile(args.config, precision) if (not args.time and not args.channels and not args.batch) else None
+
+  # ---- roofline of the dominant kernel class
   # The timed region replays the step as a CUDA graph (two streams), where single kernels cannot be bracketed by events.
   # Each launch is therefore timed with an event pair in an eager, single-stream pass over the same inputs; that pass pays
-  # a few microseconds of launch gap per kernel, so the class is charged its SHARE of the eager pass times the measured
-  # graph-replay step (the ncu launch list under profiles/ must show the same share).
+  # a few microseconds of launch gap per kernel, so a class is charged its SHARE of the eager pass times the measured
+  # graph-replay step (the ncu launch list under profiles/ shows the same share).
+  fused_blocks = int(h.lib.wn_fused_forward_blocks(h.h))
+  dmodel = kw['dilation_channels'] or kw['channels']
+  dil_ms_eager, dil_launches = prof['dilated']
   share = dil_ms_eager / prof['all'][0] if prof['all'][0] > 0 else 0.0
-  dil_ms = share * (ms_total / args.steps)
-  achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
-  roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
-              'frac': achieved / peaks['tensor'],
-              # dram__bytes_read+write per launch, mean over the class's kernels, from one `ncu --set full` capture of the C2
-              # step (cold cache; profiles/ncu_full_r1e_c2_{blockfwd,bwd}.txt): fused block forward 98.0 MB, dgrad 110.5 MB,
-              # dilated wgrad 107.5 MB, its finish 19.1 MB.  Only valid for the default workload.
-              'traffic': TRAFFIC_C2 if (precision == 'bf16' and args.config == 'c2' and B_local == 8 and not args.time and not args.channels and stack_layers and wg_tiles) else None,
-              'kernel': (('tc_stack_fwd_kernel (gated conv + gate + conv1 + residual of ALL layers in one persistent launch, CTA pairs) + ' if stack_layers else
-                          'tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ') if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + ')
-              + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + '
-              + ('tc_wgrad_group_kernel (+ finish): gated-conv, conv1, conv_skip and head filter gradients of all blocks in one launch'
-                 if wg_tiles else 'tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs')
-              if precision == 'bf16' else 'conv_gemm_simt + wgrad_simt on the dilated convs',
-              'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles, 'stack_forward_layers': stack_layers, 'wgrad_side_launches': int(side_l.value), 'ms_per_step_in_kernel': dil_ms, 'fused_forward_blocks': fused_blocks,
-              'ms_per_step_in_kernel_eager_events': dil_ms_eager, 'ms_per_step_all_launches_eager_events': prof['all'][0],
-              'flops_per_step': dil_flops_step, 'peak_source': f'{peaks["source"]} bf16 sustained (cuBLAS, MEASURED_PEAKS.json)',
-              'share_of_step': share}
-  step_ms = ms_total / args.steps
   total_flops_step = 3.0 * flops['total'] * rows
+  alg_bytes_step = workmodel.alg_bytes_per_sample(kw, e_bytes) * rows
+  if precision == 'bf16':
+    # grouped weight gradients: ONE launch (+ side launches) computes the gated-conv, conv1, conv_skip and head filter
+    # gradients as 256 x 256 tiles; the launch is timed in this class, so all of its products count as the class's work;
+    # the fused forward kernels' conv1 products likewise (forward only; their adjoints run in other kernels)
+    dil_flops_step = (2.0 * flops['dilated'] + (wg_tiles * 2.0 * 256 * 256 if wg_tiles else flops['dilated'])) * rows
+    dil_flops_step += fused_blocks * 2.0 * dmodel * kw['channels'] * rows
+    dil_ms = share * step_ms
+    achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
+    top = None
+    if dram:
+      top = max(dram['kernels'].items(), key=lambda kv: kv[1]['ms'])
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor_burst'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tensor_burst'],
+                'peak_source': f'{peaks["source"]} bf16 BURST (cuBLAS 8192^3 best of 10, MEASURED_PEAKS.json): the timed region is {ms_total * 1e-3:.2f} s long',
+                # dram bytes (read + write) of the class's dominant kernel, per launch, from the committed ncu capture
+                'traffic': (top[1]['dram_read'] + top[1]['dram_write']) / max(1, top[1]['launches']) if top else None,
+                'traffic_kernel': top[0] if top else None,
+                'kernel': ('tc_stack_fwd_kernel (gated conv + gate + conv1 + residual of ALL layers, one persistent launch, CTA pairs) + ' if stack_layers else
+                           ('tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ' if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + '))
+                + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + '
+                + ('tc_wgrad_group_kernel (+ finish): gated-conv, conv1, conv_skip and head filter gradients of all blocks in one launch'
+                   if wg_tiles else 'tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'),
+                'class': 'dilated-conv GEMMs (fwd + dgrad + wgrad)', 'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles,
+                'stack_forward_layers': stack_layers, 'wgrad_side_launches': int(side_l.value), 'fused_forward_blocks': fused_blocks,
+                'ms_per_step_in_kernel': dil_ms, 'ms_per_step_in_kernel_eager_events': dil_ms_eager,
+                'ms_per_step_all_launches_eager_events': prof['all'][0], 'share_of_step': share, 'flops_per_step': dil_flops_step}
+    if sustained:
+      a_s = dil_flops_step / (share * sustained['ms_per_step'] * 1e-3) / 1e12 if share > 0 else 0.0
+      roofline['sustained'] = {'achieved': a_s, 'peak': peaks['tensor'], 'frac': a_s / peaks['tensor'],
+                               'peak_source': f'{peaks["source"]} bf16 SUSTAINED (cuBLAS back to back for 4 s): region of {sustained["seconds"]:.1f} s'}
+  else:
+    # fp32 tier at the reference's default width (R = 32): AI of the whole block is below the ridge -> HBM roofline
+    # over the block-fused algorithmic bytes of the WHOLE step
+    achieved = alg_bytes_step / (step_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm'],
+                'peak_source': f'{peaks["source"]} HBM copy bandwidth (MEASURED_PEAKS.json)', 'traffic': None,
+                'kernel': 'whole step (conv_gemm_simt + wgrad_simt FFMA tier): block-fused algorithmic bytes / step time',
+                'alg_bytes_per_step': alg_bytes_step, 'launches_per_step': prof['all'][1],
+                'tensor_equivalent_tflops': total_flops_step / (step_ms * 1e-3) / 1e12}
+  if dram:
+    roofline['traffic_by_kernel'] = {k: {'launches_per_step': v['launches'], 'dram_bytes_per_step': v['dram_read'] + v['dram_write'], 'ncu_ms_per_step': v['ms']}
+                                     for k, v in dram['kernels'].items()}
+    roofline['dram_bytes_per_step'] = sum(v['dram_read'] + v['dram_write'] for v in dram['kernels'].values())
+    roofline['alg_bytes_per_step'] = alg_bytes_step
+    roofline['traffic_source'] = dram.get('source')
+
+  # ---- HBM-bound phases (north star item 3): achieved GB/s = bytes the phase must move as launched / its CUDA-event time
+  head_grouped = bool(wg_tiles) and len(kw['final_layers_channels']) <= 2 and all(w % 256 == 0 for w in workmodel.head_widths(kw))
+  phase_bytes = workmodel.hbm_phase_bytes_per_sample(kw, e_bytes, head_grouped)
+  roofline_hbm = {}
+  for lab, what in HBM_PHASES.items():
+    if lab not in by_label or by_label[lab][0] <= 0:
+      continue
+    ms_l, n_l = by_label[lab]
+    if lab == 'wgrad_group_finish':
+      nbytes = (parts_c.value + tiles_c.value) * 65536 * 4
+    else:
+      nbytes = phase_bytes.get(lab, 0) * rows
+    if nbytes <= 0:
+      continue
+    gbs = nbytes / (ms_l * 1e-3) / 1e9
+    roofline_hbm[lab] = {'kernel': what, 'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm'],
+                         'bytes_per_step': nbytes, 'ms_per_step': ms_l, 'launches_per_step': n_l}
   whole = {'tflops_all_gemms_whole_step': total_flops_step / (step_ms * 1e-3) / 1e12,
-           'frac_of_tensor_peak_whole_step': total_flops_step / (step_ms * 1e-3) / 1e12 / peaks['tensor'],
-           'gemm_ms_per_step': prof['gemm_all'][0]}
+           'frac_of_burst_tensor_peak': total_flops_step / (step_ms * 1e-3) / 1e12 / peaks['tensor_burst'],
+           'alg_bytes_per_step': alg_bytes_step, 'alg_gbs_whole_step': alg_bytes_step / (step_ms * 1e-3) / 1e9,
+           'gemm_ms_per_step_eager_events': prof['gemm_all'][0]}
+  if sustained:
+    whole['frac_of_sustained_tensor_peak_sustained_region'] = total_flops_step / (sustained['ms_per_step'] * 1e-3) / 1e12 / peaks['tensor']
 
   line = {
     'metric': METRIC, 'value': world * rows * args.steps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
     'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
     'dtype': 'bf16' if precision == 'bf16' else 'f32', 'data': 'synthetic',
     'config': {'workload': workload, 'global_batch': B_local * world, 'segment': T, 'receptive_field': model.receptive_field,
-               'params': int(h.n_scalars), 'parallelism': f'dp{world}',
-               'l2': 'per-step working set (activations cached for backward) is GBs >> 126 MB L2; no explicit flush needed',
-               'flops_per_sample_fwd_bwd': 3 * flops['total']},
+               'params': int(h.n_scalars), 'parallelism': f'dp{world}', 'dropout': float(kw['dropout']),
+               'l2': 'per-step working set (activations cached for backward) is GBs >> 126 MB L2; no explicit flush needed'
+                     if rows * kw['channels'] * kw['blocks'] * e_bytes > 2.5e8 else 'per-step working set fits L2: steps run back to back on a warm L2 (as in training)',
+               'flops_per_sample_fwd_bwd': 3 * flops['total'], 'allreduce': model_allreduce_kind(model)},
     'e2e': {'value': world * rows * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
             'ms_per_step': ms_e2e / args.steps, 'api': 'WaveNet.train_step_deferred(host buffers) + .result(): logs of step k read after step k+1 is enqueued',
             'sync_per_step_ms': ms_e2e_sync / args.steps},
-    'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'whole_step': whole,
-    'loss': {'first': loss0, 'last': loss_last, 'e2e_last': out['loss']},
+    'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_hbm': roofline_hbm, 'sustained': sustained, 'kernels': kernels,
+    'whole_step': whole, 'loss': {'first': loss0, 'last': loss_last, 'e2e_last': out['loss']},
   }
+  if args.check_grads:
+    line['grad_check'] = check_grads(model, kw, precision, local, rank, world, frames_np, cond_np, B_local, T, cond_in)
   # ---- informational: one FULL training iteration as the reference runs it (model.py:309-348): the step above plus
   # per-variable clipnorm, Adam on the fp32 master weights, weight re-pack and the sampled-waveform MSE metric
   if world == 1:

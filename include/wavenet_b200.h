@@ -240,13 +240,17 @@ int wn_fused_forward_blocks(const wn_handle* h);  /* blocks of the last forward 
  * step computed in the grouped launch behind the dgrad chain; 0 = per-block launches. side_launches (may be null): how many
  * of the launches ran beside the chain on the SMs it leaves idle */
 int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches);
+/* the same plus the number of 256x256 fp32 partial tiles (tiles x row splits) the finish launch reads (its HBM traffic) */
+int wn_grouped_wgrad_info(const wn_handle* h, int* tiles, int* partial_tiles, int* side_launches);
 /* layers of the last forward (block loop of WaveNet.call, model.py:229-234) that ran inside the ONE persistent stack launch;
  * 0 = one launch (or more) per block */
 int wn_stack_forward_layers(const wn_handle* h);
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
 /* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a
- * short label ("gate", "bias_act_res", "gate_bwd", "dgrad", "wgrad_dilated", "wgrad_1x1", "misc") of launch i */
+ * short label of launch i: the phase ("input_conv_fwd", "cond_fwd", "skip_sum", "head_fwd", "loss", "loss_finalize",
+ * "head_bwd", "wgrad_group_finish", "input_conv_bwd", "cond_bwd") or, inside the block loop, the kernel ("stack_fwd",
+ * "block_fwd", "gate", "bias_act_res", "gate_bwd", "dgrad", "wgrad_dilated", "wgrad_1x1", "wgrad_group", "misc") */
 int wn_profile_get(wn_handle* h, int i, double* ms, char* label, int label_len);
 const char* wn_build_info(void);
 

@@ -101,6 +101,21 @@ class Config:
     return ml[-1] if ml else self.cond_in
 
 
+def config_from_kwargs(kw: dict, cond_in: int = 0) -> Config:
+  """Config from the WaveNet(...) kwargs of model.py:14-34 (what train.py:206-224 passes)."""
+  return Config(
+    kernel_size=kw.get('kernel_size', 2), channels=kw.get('channels', 32), blocks=kw.get('blocks', 10),
+    layers_per_block=kw.get('layers_per_block', 1), activation=kw.get('activation'),
+    conditioning=kw.get('conditioning'), mapping_layers=kw.get('mapping_layers'),
+    mapping_activation=kw.get('mapping_activation'), dropout=kw.get('dropout', 0.0),
+    dilation_bound=kw.get('dilation_bound', 512), num_mixtures=kw.get('num_mixtures'),
+    sampling_function=kw.get('sampling_function', 'categorical'), bits=kw.get('bits', 8),
+    skip_channels=kw.get('skip_channels'), dilation_channels=kw.get('dilation_channels'),
+    use_residual=kw.get('use_residual', True), use_skip=kw.get('use_skip', True),
+    final_layers_channels=kw.get('final_layers_channels', []), l2_reg_factor=kw.get('l2_reg_factor', 0.0),
+    cond_in=cond_in)
+
+
 def dilation_schedule(cfg: Config) -> Tuple[List[List[int]], int]:
   """model.py:79-81,93-94,122.  Returns (per-block dilation lists, receptive field)."""
   max_power = int(math.log(cfg.dilation_bound, cfg.kernel_size))

@@ -5,17 +5,7 @@ from oracle import wavenet_oracle as wo
 
 
 def oracle_config(kw: dict, cond_in: int = 0) -> wo.Config:
-  return wo.Config(
-    kernel_size=kw.get('kernel_size', 2), channels=kw.get('channels', 32), blocks=kw.get('blocks', 10),
-    layers_per_block=kw.get('layers_per_block', 1), activation=kw.get('activation'),
-    conditioning=kw.get('conditioning'), mapping_layers=kw.get('mapping_layers'),
-    mapping_activation=kw.get('mapping_activation'), dropout=kw.get('dropout', 0.0),
-    dilation_bound=kw.get('dilation_bound', 512), num_mixtures=kw.get('num_mixtures'),
-    sampling_function=kw.get('sampling_function', 'categorical'), bits=kw.get('bits', 8),
-    skip_channels=kw.get('skip_channels'), dilation_channels=kw.get('dilation_channels'),
-    use_residual=kw.get('use_residual', True), use_skip=kw.get('use_skip', True),
-    final_layers_channels=kw.get('final_layers_channels', []), l2_reg_factor=kw.get('l2_reg_factor', 0.0),
-    cond_in=cond_in)
+  return wo.config_from_kwargs(kw, cond_in)
 
 
 def make_inputs(B, T, cond_in=0, seed=0):

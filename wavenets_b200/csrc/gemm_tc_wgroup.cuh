@@ -306,7 +306,7 @@ struct TcWgJobDesc {         // one weight-gradient problem dW[k * Cin + c, n] =
 
 struct TcWgGroupPlan {
   int B = 0, T = 0;
-  int nunits = 0, ntiles = 0, ncs = 0, nsplit = 1;
+  int nunits = 0, ntiles = 0, ncs = 0, nsplit = 1, npartial = 0;
   int final_units = 0;                                   // units [0, final_units): the launch at the end
   std::vector<std::pair<int, int>> side;                 // per side group: (first unit, units)
   CUtensorMap* d_maps = nullptr; TcWgUnit* d_units = nullptr; TcWgFinTile* d_tiles = nullptr; TcWgFinCs* d_css = nullptr;
@@ -508,6 +508,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
             up((void**)&plan->d_tiles, tiles.data(), tiles.size() * sizeof(TcWgFinTile)) && up((void**)&plan->d_css, css.data(), css.size() * sizeof(TcWgFinCs));
   size_t npart = 0;
   for (int i = 0; i < ntiles; ++i) npart += (size_t)tiles[i].nsplit;
+  plan->npartial = (int)npart;
   ok = ok && cudaMalloc((void**)&plan->d_partial, npart * 65536 * 4) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&plan->d_cs, (size_t)(cs_rows > 0 ? cs_rows : 1) * 256 * 4) == cudaSuccess;
   if (!ok) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: plan allocation failed: %s", cudaGetErrorString(cudaGetLastError())); plan->release(); return -23; }

@@ -192,6 +192,7 @@ struct wn_handle {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   std::vector<const char*> prof_labels;   // what was launched in each timed slot
   const char* cur_label = "misc";
+  const char* outer_label = nullptr;      // set by OuterLabel: names a whole phase (skip sum, head, loss, ...) for the per-launch records
   std::vector<float> prof_ms;             // per-slot durations of the last wn_profile_end
   std::vector<const char*> prof_last_labels;
   size_t prof_used = 0;
@@ -225,6 +226,7 @@ struct wn_handle {
   std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
   int dskip_l2_last = 0;
   int wg_last_tiles = 0, wg_last_side = 0;   // grouped tiles / side launches of the last backward pass
+  int wg_last_partials = 0;                  // fp32 partial tiles (tiles x row splits) its finish launch reads
   int wg_cur_group = -1;              // side group of the jobs block_backward appends (-1: final launch)
   int wg_side_every = 5;              // every n-th block hands its weight gradients to a side launch (WN_TC_GROUP_SIDE_EVERY, 0 = off)
   cudaEvent_t ev_wg_side = nullptr;
@@ -265,7 +267,7 @@ struct LaunchScope {
       }
       slot = h->prof_used++;
       if (h->prof_labels.size() <= slot) h->prof_labels.resize(slot + 1);
-      h->prof_labels[slot] = h->cur_label;
+      h->prof_labels[slot] = h->outer_label ? h->outer_label : h->cur_label;
       cudaEventRecord(h->prof_events[slot].first, st);
       timed = true;
       h->prof_launches++;
@@ -274,6 +276,13 @@ struct LaunchScope {
   ~LaunchScope() {
     if (timed) cudaEventRecord(h->prof_events[slot].second, st);
   }
+};
+
+// names every launch issued while it lives (wins over the per-kernel labels): bench.py groups the timed launches by it
+struct OuterLabel {
+  wn_handle* h; const char* prev;
+  OuterLabel(wn_handle* h_, const char* l) : h(h_), prev(h_->outer_label) { h->outer_label = l; }
+  ~OuterLabel() { h->outer_label = prev; }
 };
 
 // ============================================================================ build
@@ -1187,6 +1196,7 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   h->fused_fwd_launches = 0;
   const float* cond = nullptr;
   if (c.conditioning) {
+    OuterLabel ol(h, "cond_fwd");
     RET(cond_forward(h, st, cond_in, B, true, &cond));
     {
       LaunchScope ls(h, st, CLS_MISC);
@@ -1196,6 +1206,7 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   }
   h->last_cond = cond;
   {
+    OuterLabel ol(h, "input_conv_fwd");
     LaunchScope ls(h, st, CLS_MISC);
     const long long total = (long long)B * Tn * h->R;
     if (h->R % 8 == 0 && h->R / 8 <= 256)
@@ -1274,10 +1285,12 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   const void* head_in = cur;
   int head_w = h->R;
   if (c.use_skip) {
+    OuterLabel ol(h, "skip_sum");
     RET((skip_gemm<T, T>(h, st, 0, h->L, (T*)h->skipsum, h->Sp, h->bskip_sum, B, Tn)));
     head_in = h->skipsum;
     head_w = h->Sp;
   }
+  OuterLabel ol_head(h, "head_fwd");
   for (size_t i = 0; i < h->head.size(); ++i) {
     const ConvP& hc = h->head[i];
     const bool last = i + 1 == h->head.size();
@@ -1307,6 +1320,7 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
   const long long rows = (long long)B * Tn;
   int nparts;
   {
+    OuterLabel ol(h, "loss");
     LaunchScope ls(h, st, CLS_LOSS);
     if (c.sampling_function == WN_CATEGORICAL) {
       nparts = cdiv(rows, 8);
@@ -1335,6 +1349,7 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
       }
       l2coef = c.l2_reg_factor * scale * (float)B;   // reg / n_replicas
     }
+    OuterLabel ol(h, "loss_finalize");
     LaunchScope ls(h, st, CLS_LOSS);
     loss_finalize<<<1, 1024, 0, st>>>(h->loss_partial, nparts, scale, l2coef != 0.f ? h->l2_sum : nullptr, l2coef, loss_out);
   }
@@ -1682,6 +1697,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   const void* dcur = h->dlogits;
   int dw = h->ldd;
   for (int i = (int)h->head.size() - 1; i >= 0; --i) {
+    OuterLabel ol_head(h, "head_bwd");
     const ConvP& hc = h->head[i];
     const void* a_in;
     int a_w;
@@ -1780,6 +1796,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   // beside the final grouped weight-gradient launch (its CTAs fit next to the tensor kernel's on the same SMs)
   bool input_conv_done = false;
   auto input_conv_bwd = [&](cudaStream_t s_) {
+    OuterLabel ol(h, "input_conv_bwd");
     const bool wide = h->R % 2 == 0 && h->R / 2 <= 256 && ld_dx % 2 == 0;
     const int chunks = cdiv(Tn, 64);
     const int nparts = wide ? cdiv((long long)B * Tn, ICB_ROWS) : B * chunks;
@@ -1833,7 +1850,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
         struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, "wgrad_group");
         {
           LaunchScope ls(h, st, CLS_DILATED);
-          h->wg_last_tiles = plan->ntiles;
+          h->wg_last_tiles = plan->ntiles; h->wg_last_partials = plan->npartial;
           // without side launches (first call of a shape, profiling passes, WN_SIDE_STREAM=0) the side groups' units, which
           // follow the final group's in the table, run in the same launch
           int r = tc_wgrad_group_launch(st, *plan, 0, side_now ? plan->final_units : plan->nunits);
@@ -1845,6 +1862,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
           CK(cudaStreamWaitEvent(st, h->ev_wg_side, 0));
         }
         {
+          OuterLabel ol(h, "wgrad_group_finish");
           LaunchScope ls(h, st, CLS_DILATED);
           int r = tc_wgrad_group_finish_launch(st, *plan, l2coef);
           if (r != 0) { set_err("grouped wgrad finish failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
@@ -1855,7 +1873,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   // join: every side-stream wgrad (and its finish kernel) is complete before anything below reads the gradients
   if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
   if (!input_conv_done) input_conv_bwd(st);
-  if (c.conditioning) RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef));
+  if (c.conditioning) { OuterLabel ol(h, "cond_bwd"); RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef)); }
   return WN_OK;
 }
 
@@ -2658,6 +2676,15 @@ extern "C" int wn_stack_forward_layers(const wn_handle* h) { return h ? h->stack
 extern "C" int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches) {
   if (side_launches) *side_launches = h ? h->wg_last_side : 0;
   return h ? h->wg_last_tiles : 0;
+}
+// grouped weight gradients of the last backward pass: output tiles, fp32 partial tiles the finish launch reads (tiles x row
+// splits), side launches
+extern "C" int wn_grouped_wgrad_info(const wn_handle* h, int* tiles, int* partial_tiles, int* side_launches) {
+  if (!h) return WN_ERR_VALUE;
+  if (tiles) *tiles = h->wg_last_tiles;
+  if (side_launches) *side_launches = h->wg_last_side;
+  if (partial_tiles) *partial_tiles = h->wg_last_partials;
+  return WN_OK;
 }
 // per-launch record of the last wn_profile_end: returns the number of timed launches; i in [0,n): duration + label
 extern "C" int wn_profile_get(wn_handle* h, int i, double* ms, char* label, int label_len) {

@@ -58,18 +58,45 @@ def alg_bytes_per_sample(kw: dict, elem_bytes: int) -> int:
   return fwd + bwd
 
 
-def hbm_kernel_bytes_per_sample(kw: dict, elem_bytes: int) -> Dict[str, int]:
-  """Algorithmic HBM bytes per audio sample of the HBM-bound kernels of the pass (north star item 3): what each kernel must
-  read + write once.  e = activation element size of the tier (2 for bf16, 4 for fp32)."""
-  R, K = kw.get('channels', 32), kw.get('kernel_size', 2)
-  C = out_channels(kw)
+def head_widths(kw: dict) -> List[int]:
+  """[input width, hidden widths..., output channels] of the head (model.py:105-119)."""
+  R = kw.get('channels', 32)
+  S = kw.get('skip_channels')
+  cin = (S if S is not None else R) if kw.get('use_skip', True) else R
+  return [cin] + list(kw.get('final_layers_channels') or []) + [out_channels(kw)]
+
+
+def hbm_phase_bytes_per_sample(kw: dict, elem_bytes: int, head_wgrads_grouped: bool = False) -> Dict[str, int]:
+  """HBM bytes per audio sample each non-block phase of the step must move AS LAUNCHED (every launch reads its inputs
+  and writes its outputs once; weights are negligible): the numerators of bench.py's `roofline_hbm` (north star item 3:
+  skip accumulation, head and loss kernels with achieved HBM GB/s).  Keys = the phase labels of wn_profile_get.
+  e = activation element size of the tier (2 bf16, 4 fp32); logits are always fp32."""
+  R = kw.get('channels', 32)
+  D = kw.get('dilation_channels') or R
+  S = kw.get('skip_channels')
+  L = kw.get('blocks', 10)
   e = elem_bytes
+  C = out_channels(kw)
   ldd = (C + 63) // 64 * 64 if e == 2 else C
-  return {
-    # softmax-CE / mixture loss: reads fp32 logits + the target sample, writes dlogits (tier type)
-    'loss': 4 * C + 4 + e * ldd,
-    # input causal conv forward: reads K audio samples (cached: counted once), writes (R) activations
-    'input_conv_fwd': 4 + e * R,
-    # its weight gradient: reads d h0 (R) and the audio sample
-    'input_conv_bwd': 4 + e * R,
+  hw = head_widths(kw)
+  act = kw.get('activation') not in (None, 'linear')
+  out = {
+    'loss': 4 * C + 4 + e * ldd,                 # reads fp32 logits + the target sample, writes d logits
+    'input_conv_fwd': 4 + e * R,                 # reads the audio sample (taps hit L1), writes h0
+    'input_conv_bwd': 4 + e * R,                 # reads d h0 and the audio sample; the reduction partials are small
   }
+  if kw.get('use_skip', True):
+    sp = S if S is not None else R
+    out['skip_sum'] = (L * D + sp) * e           # ONE K = L*D GEMM over the cached gate outputs (model.py:236)
+  fwd = 0
+  for i in range(len(hw) - 1):
+    fwd += hw[i] * e + (4 * hw[i + 1] if i == len(hw) - 2 else hw[i + 1] * e)
+  out['head_fwd'] = fwd
+  bwd = 0
+  for i in range(len(hw) - 2, -1, -1):
+    gout = ldd if i == len(hw) - 2 else hw[i + 1]
+    bwd += (gout + hw[i] + (hw[i] if (act and i > 0) else 0)) * e        # dgrad: reads dY (and the cached output), writes dX
+    if not head_wgrads_grouped:
+      bwd += (hw[i] + gout) * e                                          # its weight gradient: reads X and dY
+  out['head_bwd'] = bwd
+  return out
