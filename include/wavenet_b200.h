@@ -220,6 +220,10 @@ int wn_layer_backward(wn_handle* h, int block, const float* dx_out_dev, const fl
  *   conv_gemm: out[(b,t), n] = sum_s A[(b, t+shifts[s]), 0:K] . W[n, s*K : (s+1)*K]   (rows outside [0,T) are zero)
  *   wgrad    : out[s*K + c, n] = sum_{b,t} A[(b, t+shifts[s]), c] * G[(b,t), n]
  * A (B,T,lda) bf16, W [N16][nseg*K] bf16, G (B,T,ldg) bf16, out fp32.  Synchronous. */
+/* an intermediate tensor of the last step as fp32 on the host (rows = B*T of that step); returns the row width.
+ * name: "h0", "z"(l), "g"(l), "xout"(l), "skipsum", "hact"(i), "logits", "dlogits", "dskip", "dz"(l), "dx"(l),
+ * "act"(16 l + j: output of pre-stack conv j of block l) */
+int wn_debug_tensor(wn_handle* h, const char* name, int index, float* out_host, int64_t capacity);
 int wn_debug_conv_gemm(const void* a_bf16_dev, int lda, int B, int T, int nseg, const int* shifts, int K,
                        const void* w_bf16_dev, int N, int N16, int tile, float* out_dev, void* stream);
 int wn_debug_wgrad(const void* a_bf16_dev, int lda, const void* g_bf16_dev, int ldg, int B, int T, int nseg,

@@ -84,9 +84,10 @@ class _Act(torch.autograd.Function):
   """y = bf16(act(pre)); d pre = bf16(d y * act'(y)) with act' taken from the cached bf16 output (TcEpiActBwd)."""
 
   @staticmethod
-  def forward(ctx, pre, name):
+  def forward(ctx, pre, name, slope_mask=None):
     y = _bf16(torch_ref._act(name, pre))
     ctx.name = name
+    ctx.mask = slope_mask
     ctx.save_for_backward(y)
     return y
 
@@ -97,16 +98,16 @@ class _Act(torch.autograd.Function):
     if n is None or n == 'linear':
       d = dy
     elif n == 'relu':
-      d = dy * (y > 0).to(dy.dtype)
+      d = dy * ((y > 0) if ctx.mask is None else ctx.mask).to(dy.dtype)
     elif n == 'leaky_relu':
-      d = dy * torch.where(y >= 0, torch.ones_like(y), torch.full_like(y, wo.LEAKY_SLOPE))
+      d = dy * torch.where((y >= 0) if ctx.mask is None else ctx.mask, torch.ones_like(y), torch.full_like(y, wo.LEAKY_SLOPE))
     elif n == 'tanh':
       d = dy * (1.0 - y * y)
     elif n == 'sigmoid':
       d = dy * y * (1.0 - y)
     else:
       raise NotImplementedError(n)
-    return _bf16(d), None
+    return _bf16(d), None, None
 
 
 class Rounding:
@@ -121,8 +122,18 @@ class Rounding:
   def bwd(self, x):
     return _RoundBwd.apply(x) if self.on else x
 
-  def both(self, x):
-    return _RoundBwd.apply(_RoundFwd.apply(x)) if self.on else x
+  def both(self, x, tap=None, key=None):
+    """`tap[key]` receives the stored tensor: its value is the bf16 value, its .grad (after backward) the bf16 gradient"""
+    if not self.on:
+      if tap is not None:
+        x.retain_grad()
+        tap[key] = x
+      return x
+    t = _RoundFwd.apply(x)
+    if tap is not None:
+      t.retain_grad()
+      tap[key] = t
+    return _RoundBwd.apply(t)
 
   def gate(self, z):
     if self.on:
@@ -130,8 +141,13 @@ class Rounding:
     D = z.shape[-1] // 2
     return torch.tanh(z[..., :D]) * torch.sigmoid(z[..., D:])
 
-  def act(self, pre, name):
-    return _Act.apply(pre, name) if self.on else torch_ref._act(name, pre)
+  def act(self, pre, name, slope_mask=None):
+    """slope_mask (bool tensor, optional): which elements take the derivative of the POSITIVE branch of relu / leaky_relu in
+    the backward pass, instead of the sign of this oracle's own output.  The derivative of a piecewise-linear activation
+    is discontinuous at 0: a pre-activation within one rounding flip of zero lands on different sides in two correct
+    implementations, and each such element changes a gradient by a factor 5 (leaky) — with the mask taken from the
+    implementation under test the backward arithmetic is compared like for like (the forward values are checked separately)."""
+    return _Act.apply(pre, name, slope_mask) if self.on else torch_ref._act(name, pre)
 
 
 def _conv(x, W, b, d):
@@ -147,8 +163,19 @@ def _conv(x, W, b, d):
   return out + b
 
 
-def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding):
-  """x (B,T,1) -> logits (B,T,C)."""
+def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding, tap=None, slope_masks=None):
+  """x (B,T,1) -> logits (B,T,C).  tap: optional dict that receives the intermediate tensors the kernels store
+  ('h0', ('z', l), ('g', l), ('xout', l), 'skipsum', ('hact', i), 'logits'), each with retain_grad()."""
+  def keep(key, t):
+    if tap is not None:
+      t.retain_grad()
+      tap[key] = t
+    return t
+
+  def mask(key):
+    if not slope_masks or key not in slope_masks:
+      return None
+    return torch.as_tensor(np.asarray(slope_masks[key]), dtype=torch.bool)
   per_block, _ = wo.dilation_schedule(cfg)
   q = lambda name: R.fwd(p[name])     # bf16 copy of a GEMM weight
   cond = None
@@ -156,40 +183,43 @@ def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding):
     cond = cond_in
     for i, _ in enumerate(list(cfg.mapping_layers or [])):
       cond = torch_ref._act(cfg.mapping_activation, cond @ p[f'mapping{i}/kernel'] + p[f'mapping{i}/bias'])   # fp32 path
-  h = R.both(_conv(x, p['causal/kernel'], p['causal/bias'], 1))        # element-wise fp32 kernel, stored bf16
+  h = R.both(_conv(x, p['causal/kernel'], p['causal/bias'], 1), tap, 'h0')        # element-wise fp32 kernel, stored bf16
   skips = []
   for b, dils in enumerate(per_block):
     res = h
     act = cfg.activation if len(dils) > 1 else None
     a = h
     for j, d in enumerate(dils[:-1]):
-      a = R.act(_conv(a, q(f'block{b}/dil{j}/kernel'), p[f'block{b}/dil{j}/bias'], d), act)
+      a = keep(('act', b, j), R.act(_conv(a, q(f'block{b}/dil{j}/kernel'), p[f'block{b}/dil{j}/bias'], d), act, mask(('act', b, j))))
     j = len(dils) - 1
     z = _conv(a, q(f'block{b}/dil{j}/kernel'), p[f'block{b}/dil{j}/bias'], dils[-1])
     if cond is not None:
       z = z + (cond @ p[f'block{b}/conv_cond/kernel'][0] + p[f'block{b}/conv_cond/bias'])[:, None, :]
-    g = R.fwd(R.gate(z))
+    keep(('z', b), z)
+    g = keep(('g', b), R.fwd(R.gate(z)))
     o = R.bwd(g @ q(f'block{b}/conv1/kernel')[0] + p[f'block{b}/conv1/bias'])
     if cfg.skip_channels is not None:
       skip = g @ q(f'block{b}/conv_skip/kernel')[0] + p[f'block{b}/conv_skip/bias']
     else:
       skip = o
-    h = R.both(o + res if cfg.use_residual else o)
+    h = R.both(o + res if cfg.use_residual else o, tap, ('xout', b))
     skips.append(skip)
   if cfg.use_skip:
     s = skips[0]
     for t in skips[1:]:
       s = s + t
-    h = R.both(s)
+    h = R.both(s, tap, 'skipsum')
   nfin = len(cfg.final_layers_channels)
   for i in range(nfin + 1):
     lin = h @ q(f'final{i}/kernel')[0] + p[f'final{i}/bias']
-    h = R.act(lin, cfg.activation) if i < nfin else R.bwd(lin)
+    keep(('lin', i), lin)
+    h = keep(('hact', i), R.act(lin, cfg.activation, mask(('hact', i)))) if i < nfin else R.bwd(lin)
   return h
 
 
-def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, faithful=True, threads=None):
-  """WaveNet.train_step up to the gradients (model.py:309-335).  Returns (loss, grads dict)."""
+def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, faithful=True, threads=None, tap=None, slope_masks=None):
+  """WaveNet.train_step up to the gradients (model.py:309-335).  Returns (loss, grads dict).
+  slope_masks: {('hact', i) | ('act', block, j): bool (B,T,C)} — see Rounding.act."""
   if threads:
     torch.set_num_threads(threads)
   R = Rounding(faithful)
@@ -197,7 +227,7 @@ def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, faith
   p = {k: torch.tensor(np.asarray(v), dtype=dt, requires_grad=True) for k, v in p_np.items()}
   x = torch.tensor(np.asarray(x_frames), dtype=dt)
   c = None if cond_in is None else torch.tensor(np.asarray(cond_in), dtype=dt)
-  logits = forward_logits(p, cfg, x[:, :-1, :], c, R)
+  logits = forward_logits(p, cfg, x[:, :-1, :], c, R, tap, slope_masks)
   if faithful:
     logits = logits.to(torch.float32).to(dt)      # the logits live in fp32
   loss = torch_ref.loss_per_sample(cfg, logits, x[:, 1:, :]).sum() / (x.shape[0] * n_replicas)

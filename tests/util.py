@@ -55,3 +55,39 @@ SMALL_MODELS = {
              l2_reg_factor=0.01, conditioning='global', mapping_layers=[4], mapping_activation='tanh'),
 }
 COND_IN = 5
+
+
+def device_tensor(model, name, index, B, T, width):
+  """An intermediate tensor of the model's last step from the device (wn_debug_tensor), (B,T,width) fp32, or None."""
+  import ctypes as C
+  h = model.handle
+  buf = np.empty(B * T * width, dtype=np.float32)
+  w = h.lib.wn_debug_tensor(h.h, name.encode(), index, buf.ctypes.data_as(C.c_void_p), buf.size)
+  if w < 0:
+    return None
+  return buf[:B * T * w].reshape(B, T, w)
+
+
+def device_slope_masks(model, kw, B, T):
+  """Which elements of every relu / leaky_relu output of the model's LAST step sit on the positive branch, read back from the
+  device: {('hact', i) | ('act', block, j): bool (B,T,C)} for oracle.faithful.train_step(slope_masks=...).  The derivative of
+  a piecewise-linear activation is discontinuous: a pre-activation within one bf16 rounding flip of zero falls on different
+  sides in two correct implementations and changes that gradient element five-fold (leaky_relu).  With the masks of the
+  implementation under test, its backward arithmetic is compared like for like; its forward values are checked separately."""
+  act = kw.get('activation')
+  if act not in ('relu', 'leaky_relu'):
+    return None
+  pos = (lambda y: y > 0) if act == 'relu' else (lambda y: y >= 0)
+  masks = {}
+  for i, w in enumerate(kw.get('final_layers_channels') or []):
+    y = device_tensor(model, 'hact', i, B, T, w)
+    if y is not None:
+      masks[('hact', i)] = pos(y)
+  lpb = kw.get('layers_per_block', 1)
+  D = kw.get('dilation_channels') or kw.get('channels', 32)
+  for b in range(kw.get('blocks', 10)):
+    for j in range(lpb - 1):
+      y = device_tensor(model, 'act', 16 * b + j, B, T, D)
+      if y is not None:
+        masks[('act', b, j)] = pos(y)
+  return masks

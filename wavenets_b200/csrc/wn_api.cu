@@ -2579,6 +2579,51 @@ extern "C" int wn_layer_backward(wn_handle* h, int block, const float* dx_out_de
 // ---------------------------------------------------------------- kernel-level test hooks (bf16 tier)
 // Raw contractions of gemm_tc.cuh without a model around them, so tests can compare each
 // tcgen05 mainloop against a plain torch fp32 matmul on the same bf16 inputs.
+// Test hook: an intermediate tensor of the LAST step (wn_train_step / wn_forward), converted to fp32 on the host, rows = B*T of
+// that step.  name: "h0" | "z" (l) | "g" (l) | "xout" (l) | "skipsum" | "hact" (i) | "logits" | "dlogits" | "dskip" |
+// "dz" (l) | "dx" (l: d x_out of block l) — the last two only when the step kept them (grouped weight gradients).
+// Returns the row width (columns copied per row), or a negative status.
+extern "C" int wn_debug_tensor(wn_handle* h, const char* name, int index, float* out_host, int64_t capacity) {
+  if (!h || !name || !out_host) { set_err("bad debug_tensor arguments"); return WN_ERR_VALUE; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  const long long rows = (long long)h->lastB * h->lastT;
+  const size_t rows_cap = (size_t)h->maxB * h->maxT;
+  const bool bf = h->cfg.precision == WN_BF16;
+  const size_t es = bf ? 2 : 4;
+  const std::string n(name);
+  const void* src = nullptr; int width = 0, ld = 0; bool f32 = false;
+  const bool lok = index >= 0 && index < h->L;
+  if (n == "h0") { src = h->h0; width = ld = h->R; }
+  else if (n == "z" && lok) { src = h->zbuf[index]; width = ld = 2 * h->D; }
+  else if (n == "g" && lok) { src = (const char*)h->G_all + (size_t)index * rows_cap * h->D * es; width = ld = h->D; }
+  else if (n == "xout" && lok) { src = h->xout[index]; width = ld = h->R; }
+  else if (n == "skipsum") { src = h->skipsum; width = ld = h->Sp; }
+  else if (n == "hact" && index >= 0 && index < (int)h->hact.size()) { src = h->hact[index]; width = ld = h->head[index].cout; }
+  else if (n == "act" && index >= 0 && index / 16 < h->L && index % 16 < (int)h->acts[index / 16].size()) {   // output of pre-stack conv j of block l: index = 16 l + j
+    src = h->acts[index / 16][index % 16]; width = ld = h->D;
+  }
+  else if (n == "logits") { src = h->logits; width = h->Cout; ld = h->ldl; f32 = true; }
+  else if (n == "dlogits") { src = h->dlogits; width = h->Cout; ld = h->ldd; }
+  else if (n == "dskip") { src = h->dskip; width = ld = h->Sp; }
+  else if (n == "dz" && lok && h->dz_all) { src = (const char*)h->dz_all + (size_t)index * rows_cap * 2 * h->D * es; width = ld = 2 * h->D; }
+  else if (n == "dx" && lok && h->dx_all) { src = (const char*)h->dx_all + (size_t)index * rows_cap * h->R * es; width = ld = h->R; }
+  if (!src || rows < 1) { set_err("debug_tensor: no tensor '%s'[%d] in this handle / step", name, index); return WN_ERR_STATE; }
+  if ((long long)capacity < rows * width) { set_err("debug_tensor: capacity %lld < %lld", (long long)capacity, rows * width); return WN_ERR_VALUE; }
+  const size_t e2 = f32 ? 4 : es;
+  std::vector<char> tmp((size_t)rows * ld * e2);
+  CK(cudaMemcpy(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost));
+  for (long long r = 0; r < rows; ++r)
+    for (int c = 0; c < width; ++c) {
+      const char* p = tmp.data() + ((size_t)r * ld + c) * e2;
+      float v;
+      if (e2 == 4) memcpy(&v, p, 4);
+      else { uint16_t u; memcpy(&u, p, 2); uint32_t w = (uint32_t)u << 16; memcpy(&v, &w, 4); }
+      out_host[r * width + c] = v;
+    }
+  return width;
+}
+
 extern "C" int wn_debug_conv_gemm(const void* a_bf16_dev, int lda, int B, int T, int nseg, const int* shifts, int K, const void* w_bf16_dev, int N,
                                   int N16, int tile, float* out_dev, void* stream) {
   if (!a_bf16_dev || !w_bf16_dev || !out_dev || !shifts || nseg < 1 || nseg > TC_MAX_SEG) { set_err("bad debug gemm arguments"); return WN_ERR_VALUE; }
