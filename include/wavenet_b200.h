@@ -249,6 +249,9 @@ int wn_grouped_wgrad_info(const wn_handle* h, int* tiles, int* partial_tiles, in
 /* layers of the last forward (block loop of WaveNet.call, model.py:229-234) that ran inside the ONE persistent stack launch;
  * 0 = one launch (or more) per block */
 int wn_stack_forward_layers(const wn_handle* h);
+/* blocks whose backward chain (gate adjoint + dgrad: the autodiff of layers.py:199-224) ran inside the ONE persistent
+ * stack-backward launch of the last training step; 0 = two launches per block */
+int wn_stack_backward_layers(const wn_handle* h);
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
 /* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a

@@ -67,7 +67,7 @@ def run(name):
   side = C.c_int(0)
   res = {'config': name, 'precision': precision, 'loss': out['loss'], 'stack_layers': int(h.lib.wn_stack_forward_layers(h.h)),
          'grouped_tiles': int(h.lib.wn_grouped_wgrad_tiles(h.h, C.byref(side))), 'side_launches': side.value, 'blocks': m.blocks,
-         'want_stack': want_stack, 'want_group': want_group, 'build': h.lib.wn_build_info().decode()}
+         'want_stack': want_stack, 'want_group': want_group, 'stack_bwd_layers': int(h.lib.wn_stack_backward_layers(h.h)), 'build': h.lib.wn_build_info().decode()}
   l64, g64 = faithful.train_step(p, ocfg, x, cond, faithful=False)
   e64 = errors(g, g64)
   res.update(loss_fp64=l64, worst_fp64=e64[0][0], worst_fp64_tensor=e64[0][1], top_fp64=e64[:6])

@@ -19,7 +19,7 @@ STAMP = os.path.join(HERE, '.libwavenet_b200.stamp')
 FLAVOURS = {'': [], 'precise': ['-DWN_PRECISE_MATH']}
 
 SOURCES = ['wn_api.cu']
-HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'gemm_tc_stack.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh', 'nccl_dl.cuh',
+HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'gemm_tc_stack.cuh', 'gemm_tc_stack_bwd.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh', 'nccl_dl.cuh',
            os.path.join('..', '..', 'include', 'wavenet_b200.h')]
 
 NVCC_FLAGS = [

@@ -1,0 +1,587 @@
+// gemm_tc_stack_bwd.cuh — the backward chain of the whole residual stack (the autodiff of the block loop of WaveNet.call,
+// model.py:229-234,335, i.e. of WaveNetLayer.call, layers.py:199-224, for every block) as ONE persistent launch: the mirror
+// image of gemm_tc_stack.cuh.
+//
+// Per block l (from the last to the first) and 256-row tile m (CTA pair, 128 rows per CTA):
+//
+//   dg   = [d x_out_l | d skip] . [Wr^T ; Ws^T]                      DG tile   (M = 256, N = D, K = R + S)
+//   d z  = gate'(z_l) * dg                                           DG epilogue: z_f / z_s panels arrive by TMA, d z goes
+//                                                                    into a K-major 128B-swizzled operand buffer in shared
+//                                                                    memory (and from there, by TMA, to HBM once: the
+//                                                                    grouped weight gradients read it later)
+//   d x_out_{l-1} = d x_out_l . I                                    OUT tile, residual through the identity block
+//                 + d z[t]       . W_{K-1}^T                         ... the un-shifted tap straight from the operand buffer
+//                 + d z[t + s_k] . W_k^T,  k < K-1                   ... the anti-causal taps by TMA from HBM / L2 (rows of
+//                                                                    LATER tiles of the same block, and the peer's half)
+//
+// Before: per block one gate-adjoint launch (reads d x_out, d skip and z, writes d z) and one dgrad launch (reads d z twice and
+// d x_out again), 60 launches with their fill and drain, d z making an extra L2 -> SM trip.  Here a CTA pair walks the
+// (block, tile) list of all blocks, blocks descending, tiles of a sequence in DESCENDING time order, so that every
+// dependency points to a smaller tile id:
+//   DG(l, m)        needs d x_out_l rows of tile m            <- OUT(l+1, m)           flags_dx[l+1][m]
+//   shifted taps    need d z_l rows t0+s .. t0+s+255          <- DG epilogue (l, m') with m' >= m (its own tile included)
+// Tiles are published like in the forward kernel (TMA stores complete -> proxy fence -> red.release.gpu) and acquired by the
+// producer warp before the first dependent load.  All CTAs are resident (grid <= SMs, 1 CTA per SM), ids ascend per pair.
+//
+// TMEM: columns [0, D) = DG accumulator, [256, 256 + R) = OUT accumulator (one stage each: the OUT accumulator is held from
+// the identity products until its epilogue has read it; the next tile's DG products run under that epilogue).
+// Warps: 0 TMA producer (operand ring) | 1 MMA issuer (leader CTA) | 2 TMEM allocator, then TMA-store warp + tile publisher |
+//        3 z-panel producer | 4-11 epilogue (DG: gate adjoint; OUT: pack) | 12 pair hand-off of the d z slabs
+#pragma once
+#include "gemm_tc_stack.cuh"
+
+struct alignas(128) TcStackBwdLayer {
+  CUtensorMap tmDX, tmDS, tmWdg, tmZf, tmZs, tmDZ, tmWb, tmI, tmO;
+  int shift[TC_MAX_SEG];      // row shift of tap k (k < nseg - 1: positive; tap nseg - 1: 0)
+  int has_dx, has_ds, has_res;
+  int wait_dx;                // d x_out_l is written by this launch (every block but the last): acquire its tile flag first
+};
+
+struct TcStackBwdParams {
+  int B, T, tiles_t, num_mtiles, L;
+  int nseg;                   // taps of the gated conv
+  int kb_dx, kb_ds;           // 64-wide k blocks of the DG contraction over d x_out (R) and d skip (S)
+  unsigned long long pol_dx, pol_ds, pol_w, pol_z, pol_dz_ld, pol_dz_st, pol_o;
+};
+
+template <int D_, int R_> struct TcStackBwdCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
+  static constexpr int B_BYTES = 128 * BK * 2;                 // this CTA's half of a 256-row weight tile: 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int NSLAB = 2 * D_ / 64;                    // 64-column slabs of d z (filter slabs first, then gate slabs)
+  static constexpr int NPAIR = D_ / 64;                        // slab pairs (f_p, s_p) = two 32-channel epilogue steps each
+  static constexpr int DZ_SLOTS = 4;                           // operand buffer: two slab pairs
+  static constexpr int DZ_BYTES = DZ_SLOTS * A_BYTES;          // 64 KB
+  static constexpr int PANEL = 128 * 64;                       // 128 rows x 32 bf16
+  static constexpr int IN_SLOTS = 3, OUT_SLOTS = 2;            // z ring: (z_f, z_s) panels per slot; out ring: one d x panel per slot
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + DZ_BYTES + IN_SLOTS * 2 * PANEL + OUT_SLOTS * PANEL + 512;
+  static_assert(D_ % 128 == 0 && D_ <= 256 && R_ % 64 == 0 && R_ <= 256, "stack backward kernel: D in {128,256}, R <= 256");
+  static_assert(SMEM_BYTES <= 232448, "stack backward kernel does not fit shared memory");
+};
+
+template <int D_, int R_>
+__global__ void __launch_bounds__(416, 1)
+tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict__ flags_dx, int* __restrict__ flags_dz, const TcStackBwdParams p) {
+  using Cfg = TcStackBwdCfg<D_, R_>;
+  constexpr int STAGES = Cfg::STAGES, NEPI = 8, NPAIR = Cfg::NPAIR;
+  constexpr int KB_R = R_ / 64, KB_Z = Cfg::NSLAB;
+  extern __shared__ __align__(1024) uint8_t smem_sb[];
+  uint8_t* smem = smem_sb;
+  if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("libwavenet_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+  uint8_t* dzbuf = smem + STAGES * Cfg::STAGE_BYTES;                    // [4 slots][128 rows][128 B], 128B swizzle
+  uint8_t* in_ring = dzbuf + Cfg::DZ_BYTES;
+  uint8_t* out_ring = in_ring + Cfg::IN_SLOTS * 2 * Cfg::PANEL;
+  uint64_t* full_bar = (uint64_t*)(out_ring + Cfg::OUT_SLOTS * Cfg::PANEL);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* dg_full = empty_bar + STAGES;            // DG accumulator complete (both CTAs)
+  uint64_t* dg_empty = dg_full + 1;                  // leader's: both CTAs' epilogues have read the DG accumulator
+  uint64_t* out_full = dg_empty + 1;
+  uint64_t* out_empty = out_full + 1;
+  uint64_t* in_full = out_empty + 1;                 // [IN_SLOTS]
+  uint64_t* in_empty = in_full + Cfg::IN_SLOTS;
+  uint64_t* oslot_empty = in_empty + Cfg::IN_SLOTS;  // [OUT_SLOTS] output panel has been read by its TMA store
+  uint64_t* slab_done = oslot_empty + Cfg::OUT_SLOTS;   // [2] local: this CTA's epilogue has written (and fenced) slab pair slot ps
+  uint64_t* slab_full = slab_done + 2;               // [2] leader's: both CTAs' slabs of pair slot ps are complete
+  uint64_t* slab_cons = slab_full + 2;               // [2] local: the MMAs reading pair slot ps have completed
+  uint64_t* slab_free = slab_cons + 2;               // [2] local: the TMA stores of pair slot ps have read the buffer
+  uint32_t* tmem_ptr = (uint32_t*)(slab_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int tile_first = (int)blockIdx.x >> 1, tile_stride = (int)gridDim.x >> 1;
+  const int pair_row0 = (int)crank * Cfg::BM;
+  const int total_tiles = p.L * p.num_mtiles;
+  const int n_tiles = tile_first < total_tiles ? (total_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
+
+  // tile id -> (layer, m tile): layers from the last to the first, the tiles of a sequence in descending time order
+  auto locate = [&](int j, int& ly, int& mt, int& b, int& tb) {
+    const int gt = tile_first + j * tile_stride;
+    const int lr = gt / p.num_mtiles, mr = gt - lr * p.num_mtiles;
+    ly = p.L - 1 - lr;
+    b = mr / p.tiles_t;
+    tb = p.tiles_t - 1 - (mr - b * p.tiles_t);
+    mt = b * p.tiles_t + tb;
+  };
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(dg_full, 1); mbar_init(dg_empty, NEPI * 2); mbar_init(out_full, 1); mbar_init(out_empty, NEPI * 2);
+    for (int i = 0; i < Cfg::IN_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], NEPI); }
+    for (int i = 0; i < Cfg::OUT_SLOTS; ++i) mbar_init(&oslot_empty[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&slab_done[i], NEPI); mbar_init(&slab_full[i], 2); mbar_init(&slab_cons[i], 1); mbar_init(&slab_free[i], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  auto wait_flag = [&](const int* f, int ly, int mt) {
+    const long long spin0 = clock64();
+    while (ld_acquire_gpu(f) < 2) {
+      __nanosleep(32);
+      if (clock64() - spin0 > 6000000000ll) { printf("libwavenet_b200: stack backward waited > 3 s for tile (%d, %d)\n", ly, mt); __trap(); }
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (operand ring) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      auto next = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1; } };
+      constexpr int WDG_BYTES = (D_ / 2) * 64 * 2, WB_BYTES = (R_ / 2) * 64 * 2;
+      for (int j = 0; j < n_tiles; ++j) {
+        int ly, mt, b, tb;
+        locate(j, ly, mt, b, tb);
+        const TcStackBwdLayer& Ly = layers[ly];
+        const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+        // ---- DG: [d x_out | d skip] . Wdg
+        if (Ly.has_dx) {
+          if (Ly.wait_dx) {
+            // d x_out_l tile m was written by the OUT tile (l+1, m) of this launch
+            wait_flag(flags_dx + (size_t)(ly + 1) * p.num_mtiles + mt, ly + 1, mt);
+            fence_proxy_async_global();
+          }
+          for (int kb = 0; kb < p.kb_dx; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WDG_BYTES));
+            tma_load_4d_pair_h(sa, &Ly.tmDX, &full_bar[stage], kb * 64, t0, b, 0, p.pol_dx);
+            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmWdg, &full_bar[stage], kb * 64, (int)crank * (D_ / 2), p.pol_w);
+            next();
+          }
+        }
+        if (Ly.has_ds) {
+          const int k0 = Ly.has_dx ? p.kb_dx * 64 : 0;
+          for (int kb = 0; kb < p.kb_ds; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WDG_BYTES));
+            tma_load_4d_pair_h(sa, &Ly.tmDS, &full_bar[stage], kb * 64, t0, b, 0, p.pol_ds);
+            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmWdg, &full_bar[stage], k0 + kb * 64, (int)crank * (D_ / 2), p.pol_w);
+            next();
+          }
+        }
+        // ---- OUT, residual gradient through the identity block
+        if (Ly.has_dx && Ly.has_res) {
+          for (int kb = 0; kb < KB_R; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WB_BYTES));
+            tma_load_4d_pair_h(sa, &Ly.tmDX, &full_bar[stage], kb * 64, t0, b, 0, p.pol_dx);
+            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmI, &full_bar[stage], kb * 64, (int)crank * (R_ / 2), p.pol_w);
+            next();
+          }
+        }
+        // ---- OUT, un-shifted tap: only the weights (the A operand is the d z buffer), slab pairs in production order
+        const int kloc = (p.nseg - 1) * 2 * D_;
+        for (int pr = 0; pr < NPAIR; ++pr) {
+          for (int hh = 0; hh < 2; ++hh) {
+            const int slab = hh == 0 ? pr : NPAIR + pr;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * WB_BYTES);
+            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmWb, &full_bar[stage], kloc + slab * 64, (int)crank * (R_ / 2), p.pol_w);
+            next();
+          }
+        }
+        // ---- OUT, shifted taps: d z rows of this and of later tiles of the same sequence, written by this launch
+        for (int s = 0; s < p.nseg - 1; ++s) {
+          const int lo = tb * (2 * Cfg::BM) + Ly.shift[s];
+          const int t_lo = lo / (2 * Cfg::BM);
+          int t_hi = (lo + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
+          if (t_hi > p.tiles_t - 1) t_hi = p.tiles_t - 1;
+          for (int tt = t_lo; tt <= t_hi; ++tt) wait_flag(flags_dz + (size_t)ly * p.num_mtiles + b * p.tiles_t + tt, ly, b * p.tiles_t + tt);
+          fence_proxy_async_global();
+          for (int kb = 0; kb < KB_Z; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WB_BYTES));
+            tma_load_3d_pair_h(sa, &Ly.tmDZ, &full_bar[stage], kb * 64, t0 + Ly.shift[s], b, p.pol_dz_ld);
+            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmWb, &full_bar[stage], s * 2 * D_ + kb * 64, (int)crank * (R_ / 2), p.pol_w);
+            next();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (leader) {
+      constexpr uint32_t idesc_g = umma_idesc_bf16(256, D_, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(256, R_, 0, 0);
+      const uint32_t t_dg = tmem_base, t_out = tmem_base + 256u;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t n_sf[2] = {0u, 0u};       // completed waits on slab_full[ps]
+      auto kstep = [&](uint32_t d_tmem, uint32_t idesc, bool a_from_dz, int slot, bool first, uint64_t* extra0, uint64_t* extra1) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_addr = a_from_dz ? smem_u32(dzbuf) + (uint32_t)slot * (uint32_t)Cfg::A_BYTES : sa;
+          const uint64_t adesc = umma_smem_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k)
+            umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (extra0) umma_commit_pair(extra0);
+          if (extra1) umma_commit_pair(extra1);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        int ly, mt, b, tb;
+        locate(j, ly, mt, b, tb);
+        const TcStackBwdLayer& Ly = layers[ly];
+        const uint32_t par = (uint32_t)(j & 1);
+        // ---- DG
+        mbar_wait(dg_empty, par ^ 1);
+        tc_fence_after();
+        const int ks_dg = (Ly.has_dx ? p.kb_dx : 0) + (Ly.has_ds ? p.kb_ds : 0);
+        for (int ks = 0; ks < ks_dg; ++ks) kstep(t_dg, idesc_g, false, 0, ks == 0, ks == ks_dg - 1 ? dg_full : nullptr, nullptr);
+        // ---- OUT
+        mbar_wait(out_empty, par ^ 1);
+        tc_fence_after();
+        const int ks_id = (Ly.has_dx && Ly.has_res) ? KB_R : 0;
+        const int ks_sh = (p.nseg - 1) * KB_Z;
+        bool first = true;
+        for (int ks = 0; ks < ks_id; ++ks) { kstep(t_out, idesc_o, false, 0, first, nullptr, nullptr); first = false; }
+        for (int pr = 0; pr < NPAIR; ++pr) {
+          const int ps = pr & 1;
+          mbar_wait(&slab_full[ps], n_sf[ps] & 1u); ++n_sf[ps];     // both CTAs' slab pair is in shared memory
+          tc_fence_after();
+          const bool last = ks_sh == 0 && pr == NPAIR - 1;
+          kstep(t_out, idesc_o, true, 2 * ps, first, nullptr, nullptr); first = false;
+          kstep(t_out, idesc_o, true, 2 * ps + 1, false, &slab_cons[ps], last ? out_full : nullptr);
+        }
+        for (int ks = 0; ks < ks_sh; ++ks) kstep(t_out, idesc_o, false, 0, false, ks == ks_sh - 1 ? out_full : nullptr, nullptr);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== TMA-store warp + tile publisher =====================
+    int oslot = 0;
+    uint64_t* pend = nullptr;       // barrier to release once the previously committed store group has read shared memory
+    auto committed = [&](uint64_t* rel) {
+      bulk_commit_group();
+      if (pend) { bulk_wait_group_read<1>(); mbar_arrive(pend); }
+      pend = rel;
+    };
+    auto publish = [&](int* flag) {
+      // every store of this thread so far has landed -> visible to the async proxy of other SMs -> count this CTA in
+      bulk_wait_group<0>();
+      if (pend) { mbar_arrive(pend); pend = nullptr; }
+      fence_proxy_async_global();
+      __threadfence();
+      red_release_gpu_add(flag, 1);
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      int ly, mt, b, tb;
+      locate(j, ly, mt, b, tb);
+      const TcStackBwdLayer& Ly = layers[ly];
+      const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+      for (int pr = 0; pr < NPAIR; ++pr) {
+        const int ps = pr & 1;
+        named_bar_sync(8 + ps, NEPI * 32 + 32);
+        if (lane == 0) {
+          tma_store_3d_h(dzbuf + (2 * ps) * Cfg::A_BYTES, &Ly.tmDZ, pr * 64, t0, b, p.pol_dz_st);
+          tma_store_3d_h(dzbuf + (2 * ps + 1) * Cfg::A_BYTES, &Ly.tmDZ, D_ + pr * 64, t0, b, p.pol_dz_st);
+          committed(&slab_free[ps]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) publish(flags_dz + (size_t)ly * p.num_mtiles + mt);
+      __syncwarp();
+      for (int step = 0; step < R_ / 32; ++step) {
+        named_bar_sync(3 + oslot, NEPI * 32 + 32);
+        if (lane == 0) {
+          tma_store_3d_h(out_ring + oslot * Cfg::PANEL, &Ly.tmO, step * 32, t0, b, p.pol_o);
+          committed(&oslot_empty[oslot]);
+        }
+        __syncwarp();
+        if (++oslot == Cfg::OUT_SLOTS) oslot = 0;
+      }
+      if (lane == 0) publish(flags_dx + (size_t)ly * p.num_mtiles + mt);
+      __syncwarp();
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  } else if (warp == 3) {
+    // ===================== z-panel producer (gate adjoint inputs) =====================
+    if (lane == 0) {
+      int islot = 0; uint32_t iphase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        int ly, mt, b, tb;
+        locate(j, ly, mt, b, tb);
+        const TcStackBwdLayer& Ly = layers[ly];
+        const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+        for (int step = 0; step < D_ / 32; ++step) {
+          mbar_wait(&in_empty[islot], iphase ^ 1);
+          mbar_expect_tx(&in_full[islot], 2u * Cfg::PANEL);
+          uint8_t* dst = in_ring + islot * 2 * Cfg::PANEL;
+          tma_load_3d_h(dst, &Ly.tmZf, &in_full[islot], step * 32, t0, b, p.pol_z);
+          tma_load_3d_h(dst + Cfg::PANEL, &Ly.tmZs, &in_full[islot], step * 32, t0, b, p.pol_z);
+          if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ===================== pair hand-off of the d z slabs =====================
+    if (lane == 0) {
+      uint32_t n_sd[2] = {0u, 0u};
+      for (int j = 0; j < n_tiles; ++j)
+        for (int pr = 0; pr < NPAIR; ++pr) {
+          const int ps = pr & 1;
+          mbar_wait(&slab_done[ps], n_sd[ps] & 1u); ++n_sd[ps];
+          if (leader) mbar_arrive(&slab_full[ps]);
+          else mbar_arrive_remote(&slab_full[ps], 0u);
+        }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int quarter = warp & 3;
+    const int q = e >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 64u;
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    const uint32_t u0 = (uint32_t)(2 * q), u1 = u0 + 1;
+    const uint32_t off0 = row_off + ((u0 ^ sw) << 4), off1 = row_off + ((u1 ^ sw) << 4);
+    const uint32_t grow = (uint32_t)row * 128u, gsw = (uint32_t)(row & 7);
+    int islot = 0; uint32_t iphase = 0;
+    int oslot = 0; uint32_t ophase = 0;
+    uint32_t n_use[2] = {0u, 0u};      // fills of slab pair slot ps so far
+    const TcEpiGateBwd<true>::Params pg{D_};
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      // ---- DG epilogue: d z = gate'(z) * dg -> operand buffer
+      mbar_wait(dg_full, par);
+      tc_fence_after();
+      {
+        TmemAccRow acc{tmem_base + lane_base, true};
+#pragma unroll 1
+        for (int step = 0; step < D_ / 32; ++step) {
+          const int pr = step >> 1, ps = pr & 1;
+          float in[2][16];
+          float out[2][16];
+          mbar_wait(&in_full[islot], iphase);
+          {
+            const uint8_t* ib = in_ring + islot * 2 * Cfg::PANEL;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint4 a = *reinterpret_cast<const uint4*>(ib + k * Cfg::PANEL + off0);
+              const uint4 c = *reinterpret_cast<const uint4*>(ib + k * Cfg::PANEL + off1);
+              const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                in[k][2 * i] = __uint_as_float(w[i] << 16);
+                in[k][2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&in_empty[islot]);
+          if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+          TcEpiGateBwd<true>::chunk(pg, acc, 0, step * 32 + q * 16, 0, 0, 3u, in, out, nullptr);
+          if ((step & 1) == 0 && n_use[ps] > 0) {
+            // the slot still holds an earlier slab pair: its MMAs must have completed and its TMA stores read the buffer
+            mbar_wait(&slab_cons[ps], (n_use[ps] - 1u) & 1u);
+            mbar_wait(&slab_free[ps], (n_use[ps] - 1u) & 1u);
+          }
+          {
+            // channels [ch, ch+16) of this row: 16-byte units (ch % 64) / 8 and +1 of the 128B-swizzled 64-column slab
+            const int ch = (step & 1) * 32 + q * 16;
+            const uint32_t j0 = (uint32_t)(ch >> 3);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              uint8_t* gs = dzbuf + (2 * ps + k) * Cfg::A_BYTES + grow;
+              uint4 a, c;
+              a.x = pack_bf16x2(out[k][0], out[k][1]); a.y = pack_bf16x2(out[k][2], out[k][3]);
+              a.z = pack_bf16x2(out[k][4], out[k][5]); a.w = pack_bf16x2(out[k][6], out[k][7]);
+              c.x = pack_bf16x2(out[k][8], out[k][9]); c.y = pack_bf16x2(out[k][10], out[k][11]);
+              c.z = pack_bf16x2(out[k][12], out[k][13]); c.w = pack_bf16x2(out[k][14], out[k][15]);
+              *reinterpret_cast<uint4*>(gs + ((j0 ^ gsw) << 4)) = a;
+              *reinterpret_cast<uint4*>(gs + (((j0 + 1) ^ gsw) << 4)) = c;
+            }
+          }
+          if (step & 1) {
+            // slab pair complete in this CTA: store warp (HBM copy) and, through the hand-off warp, the MMA side
+            fence_proxy_async();
+            named_bar_arrive(8 + ps, NEPI * 32 + 32);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slab_done[ps]);
+            ++n_use[ps];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_relaxed(dg_empty, 0u);
+      // ---- OUT epilogue: d x_out_{l-1}
+      mbar_wait(out_full, par);
+      tc_fence_after();
+      {
+        TmemAccRow acc{tmem_base + 256u + lane_base, true};
+#pragma unroll 1
+        for (int step = 0; step < R_ / 32; ++step) {
+          float v[16];
+          acc.load16(step * 32 + q * 16, v);
+          uint8_t* ob = out_ring + oslot * Cfg::PANEL;
+          mbar_wait(&oslot_empty[oslot], ophase ^ 1);
+          uint4 a, c;
+          a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+          c.x = pack_bf16x2(v[8], v[9]); c.y = pack_bf16x2(v[10], v[11]); c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
+          *reinterpret_cast<uint4*>(ob + off0) = a;
+          *reinterpret_cast<uint4*>(ob + off1) = c;
+          fence_proxy_async();
+          named_bar_arrive(3 + oslot, NEPI * 32 + 32);
+          if (++oslot == Cfg::OUT_SLOTS) { oslot = 0; ophase ^= 1; }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_relaxed(out_empty, 0u);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------- host side
+struct TcStackBwdDesc {       // one block
+  int B, T, nseg, shift[TC_MAX_SEG], D, R, S;
+  const bf16* dxo;            // d x_out_l (B,T,R) or null (last block under use_skip)
+  const bf16* dskip; int lds; // d skip (B,T,S) or null
+  const bf16* z;              // cached gate pre-activations (B,T,2D)
+  bf16* dz;                   // (B,T,2D), kept for the grouped weight gradients
+  bf16* dx;                   // d x_out_{l-1} (B,T,R)
+  const bf16* Wdg; int k_dg;  // [D][k_dg] = [Wr^T | Ws^T] rows (first k = R, or S when dxo == null and the pointer is offset)
+  const bf16* Wb; int k_b;    // [R][k_b]: dgrad operand of the gated conv, contraction (tap, 2D)
+  const bf16* ident; int ld_ident;   // [R][ld_ident] holding the R x R identity (columns 0..R-1 from this pointer), or null
+};
+
+struct TcStackBwdPlan {
+  int B = 0, T = 0, L = 0, num_mtiles = 0;
+  TcStackBwdLayer* d_layers = nullptr; int* d_flags = nullptr;
+  void release() { cudaFree(d_layers); cudaFree(d_flags); d_layers = nullptr; d_flags = nullptr; }
+};
+
+template <int D_, int R_>
+static int tc_stack_bwd_build_t(TmapCache& tc, const std::vector<TcStackBwdDesc>& descs, TcStackBwdPlan* plan) {
+  std::vector<TcStackBwdLayer> tab(descs.size());
+  for (size_t l = 0; l < descs.size(); ++l) {
+    const TcStackBwdDesc& d = descs[l];
+    TcStackBwdLayer& t = tab[l];
+    memset(&t, 0, sizeof(t));
+    const CUtensorMap* mDZ = tc_slab_map(tc, d.dz, 2 * d.D, 2 * d.D, d.T, d.B);
+    const TcEpiIo zf{d.z, 2 * d.D, d.D, 0}, zs{d.z + d.D, 2 * d.D, d.D, 0}, xo{d.dx, d.R, d.R, 0};
+    const CUtensorMap* mZf = tc_panel_map(tc, zf, d.T, d.B);
+    const CUtensorMap* mZs = tc_panel_map(tc, zs, d.T, d.B);
+    const CUtensorMap* mO = tc_panel_map(tc, xo, d.T, d.B);
+    uint64_t wd[2] = {(uint64_t)d.k_dg, (uint64_t)d.D}, ws[1] = {(uint64_t)d.k_dg * 2};
+    uint32_t wb[2] = {64, (uint32_t)(D_ / 2)};
+    const CUtensorMap* mWdg = tc.get(d.Wdg, 2, wd, ws, wb);
+    uint64_t bd[2] = {(uint64_t)d.k_b, (uint64_t)d.R}, bs[1] = {(uint64_t)d.k_b * 2};
+    uint32_t bb[2] = {64, (uint32_t)(R_ / 2)};
+    const CUtensorMap* mWb = tc.get(d.Wb, 2, bd, bs, bb);
+    if (!mDZ || !mZf || !mZs || !mO || !mWdg || !mWb) return -10;
+    t.tmDZ = *mDZ; t.tmZf = *mZf; t.tmZs = *mZs; t.tmO = *mO; t.tmWdg = *mWdg; t.tmWb = *mWb;
+    t.tmDX = *mDZ; t.tmDS = *mDZ; t.tmI = *mWb;       // placeholders for absent operands (never dereferenced)
+    if (d.dxo) {
+      const CUtensorMap* m = tc_act_map(tc, d.dxo, d.R, d.R, d.T, d.B, 1, 0, 128);
+      if (!m) return -10;
+      t.tmDX = *m;
+    }
+    if (d.dskip) {
+      const CUtensorMap* m = tc_act_map(tc, d.dskip, d.lds, d.S, d.T, d.B, 1, 0, 128);
+      if (!m) return -10;
+      t.tmDS = *m;
+    }
+    if (d.ident) {
+      uint64_t id[2] = {(uint64_t)d.R, (uint64_t)d.R}, is[1] = {(uint64_t)d.ld_ident * 2};
+      const CUtensorMap* m = tc.get(d.ident, 2, id, is, bb);
+      if (!m) return -10;
+      t.tmI = *m;
+    }
+    for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
+    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = d.ident != nullptr;
+    t.wait_dx = (d.dxo != nullptr && l + 1 < descs.size()) ? 1 : 0;
+  }
+  const TcStackBwdDesc& d0 = descs[0];
+  plan->release();
+  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256);
+  if (cudaMalloc((void**)&plan->d_layers, tab.size() * sizeof(TcStackBwdLayer)) != cudaSuccess ||
+      cudaMemcpy(plan->d_layers, tab.data(), tab.size() * sizeof(TcStackBwdLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc((void**)&plan->d_flags, (size_t)2 * plan->L * plan->num_mtiles * sizeof(int)) != cudaSuccess) {
+    snprintf(g_tc_err, sizeof(g_tc_err), "stack backward: plan allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    plan->release();
+    return -23;
+  }
+  return 0;
+}
+
+template <int D_, int R_>
+static int tc_stack_bwd_launch_t(cudaStream_t st, const TcStackBwdPlan& plan, const TcStackBwdDesc& d0) {
+  using Cfg = TcStackBwdCfg<D_, R_>;
+  TcStackBwdParams p{};
+  p.B = d0.B; p.T = d0.T; p.tiles_t = (d0.T + 255) / 256; p.num_mtiles = d0.B * p.tiles_t; p.L = plan.L;
+  p.nseg = d0.nseg; p.kb_dx = d0.R / 64; p.kb_ds = d0.S / 64;
+  p.pol_dx = tc_policy(TC_L2_NORMAL); p.pol_ds = tc_policy(TC_L2_LAST); p.pol_w = tc_policy(TC_L2_LAST); p.pol_z = tc_policy(TC_L2_FIRST);
+  p.pol_dz_ld = tc_policy(TC_L2_NORMAL); p.pol_dz_st = tc_policy(TC_L2_LAST); p.pol_o = tc_policy(TC_L2_LAST);
+  auto kern = tc_stack_bwd_kernel<D_, R_>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
+    attr_done = true;
+  }
+  const int pairs = tc_num_sms() / 2;
+  if (p.num_mtiles <= pairs) return -100;
+  {
+    // every CTA pair of the launch must be resident at the same time (tiles wait for tiles of other pairs)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t oc{};
+      oc.gridDim = dim3(tc_num_sms()); oc.blockDim = dim3(416); oc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute oa[1];
+      oa[0].id = cudaLaunchAttributeClusterDimension;
+      oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+      oc.attrs = oa; oc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &oc) != cudaSuccess) { n = 0; cudaGetLastError(); }
+      max_clusters = n;
+    }
+    if (pairs > max_clusters) return -100;
+  }
+  const size_t nflags = (size_t)plan.L * plan.num_mtiles;
+  if (cudaMemsetAsync(plan.d_flags, 0, 2 * nflags * sizeof(int), st) != cudaSuccess) return -14;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(416); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 2);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const TcStackBwdLayer*)plan.d_layers, plan.d_flags, plan.d_flags + nflags, p);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "stack backward launch: %s", cudaGetErrorString(e)); return -13; }
+  return 0;
+}
+
+static inline int tc_stack_bwd_build(TmapCache& tc, const std::vector<TcStackBwdDesc>& descs, TcStackBwdPlan* plan) {
+  const TcStackBwdDesc& d = descs[0];
+  if (d.D == 256 && d.R == 256) return tc_stack_bwd_build_t<256, 256>(tc, descs, plan);
+  if (d.D == 128 && d.R == 128) return tc_stack_bwd_build_t<128, 128>(tc, descs, plan);
+  return -100;
+}
+static inline int tc_stack_bwd_launch(cudaStream_t st, const TcStackBwdPlan& plan, const TcStackBwdDesc& d) {
+  if (d.D == 256 && d.R == 256) return tc_stack_bwd_launch_t<256, 256>(st, plan, d);
+  if (d.D == 128 && d.R == 128) return tc_stack_bwd_launch_t<128, 128>(st, plan, d);
+  return -100;
+}

@@ -26,6 +26,7 @@
 #include "gemm_tc_block.cuh"
 #include "gemm_tc_wgroup.cuh"
 #include "gemm_tc_stack.cuh"
+#include "gemm_tc_stack_bwd.cuh"
 #include "kernels_misc.cuh"
 #include "generate.cuh"
 #include "nccl_dl.cuh"
@@ -212,6 +213,9 @@ struct wn_handle {
   int stack_fwd_layers = 0;   // layers of the last forward inside the stack launch
   int use_stack_fwd = 1;    // WN_TC_STACK_FWD=0: one fused launch per block instead of one for the whole stack (gemm_tc_stack.cuh)
   std::vector<TcStackPlan> stack_plans;
+  // backward chain (gate adjoint + dgrad of every block) as one persistent launch (gemm_tc_stack_bwd.cuh); WN_TC_STACK_BWD=0: per-block launches
+  int use_stack_bwd = 1, stack_bwd_layers = 0;
+  std::vector<TcStackBwdPlan> stack_bwd_plans;
   int tile_gate_bwd = 0, tile_dgrad = 0;   // forced CTA tile widths of the two backward conv GEMMs (0 = widest that divides N)
   int fused_fwd_launches = 0;  // fused block-forward launches of the last step (0: separate gate / conv1 kernels)
   // grouped weight gradients (gemm_tc_wgroup.cuh): d z and d x_out of EVERY block are kept (no ping-pong) and all block
@@ -221,7 +225,7 @@ struct wn_handle {
   void* dx_all = nullptr;     // [L][rows][R]: d x_out of block l
   void* do_all = nullptr;     // [L][rows][R]: d x_out + d skip of block l (skip_channels=None with use_skip: skip = conv1 output)
   std::vector<std::vector<void*>> dp_keep;   // [block][j]: gradient wrt the output of pre-stack conv j (B,T,D)
-  struct WgPlan { int B, T; bool drop; TcWgGroupPlan plan; };
+  struct WgPlan { int B, T; bool drop; bool sb; TcWgGroupPlan plan; };
   std::vector<WgPlan> wg_plans;
   std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
   int dskip_l2_last = 0;
@@ -659,6 +663,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
   { const char* e = getenv("WN_TC_FUSED_FWD"); if (e && e[0] == '0') h->use_fused_fwd = 0; }
   { const char* e = getenv("WN_TC_STACK_FWD"); if (e && e[0] == '0') h->use_stack_fwd = 0; }
+  { const char* e = getenv("WN_TC_STACK_BWD"); if (e && e[0] == '0') h->use_stack_bwd = 0; }
   { const char* e = getenv("WN_TC_TILE_GATE_BWD"); if (e) h->tile_gate_bwd = atoi(e); }
   { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
@@ -709,6 +714,7 @@ extern "C" void wn_destroy(wn_handle* h) {
   for (void* a : h->gen.allocs) cudaFree(a);
   for (auto& wp : h->wg_plans) wp.plan.release();
   for (auto& sp : h->stack_plans) sp.release();
+  for (auto& sp : h->stack_bwd_plans) sp.release();
   cudaFree(h->d_pack_jobs);
   cudaFree(h->opt_m); cudaFree(h->opt_v); cudaFree(h->opt_chunks); cudaFree(h->opt_var_first);
   cudaFree(h->opt_partial); cudaFree(h->opt_scale); cudaFree(h->opt_norms);
@@ -1388,7 +1394,9 @@ struct BwdSide {
 template <class T>
 static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in, const void* dxout, int ldxo, const void* dskip, int ldsk,
                           void* dx_in, int ldxi, int B, int Tn, float l2coef, void* dzbuf = nullptr, const BwdSide* sd = nullptr,
-                          bool group = false) {
+                          bool group = false, bool skip_chain = false) {
+  // skip_chain: the gate adjoint and the dgrad of this block run inside the persistent stack-backward launch
+  // (gemm_tc_stack_bwd.cuh): only the weight-gradient problems are collected here
   // group: the weight gradients of conv1, conv_skip and the gated conv are not launched here; their operands stay in
   // per-block buffers and the problems are appended to h->wg_jobs for the grouped launch (gemm_tc_wgroup.cuh)
   BlockP& b = h->blocks[l];
@@ -1479,7 +1487,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
     }
   }
   // ---- dz = gate'(z) * (d_o Wr^T + dskip Ws^T)
-  {
+  if (!skip_chain) {
     GemmH g;
     g.B = B; g.T = Tn; g.N = D; g.nseg = 0;
     int koff = 0;
@@ -1544,7 +1552,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       RET(run_wgrad<T>(h, side2 ? sd->side : st, CLS_DILATED, w));
     }
     // dgrad
-    const bool need = j > 0 || dx_in != nullptr;
+    const bool need = (j > 0 || dx_in != nullptr) && !skip_chain;
     if (need) {
       GemmH g;
       g.B = B; g.T = Tn; g.N = c.cin; g.nseg = c.K;
@@ -1679,8 +1687,21 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   // (256 tiles: 4 rounds on 74 or on 64 pairs), and the pairs left over run the weight gradients of every n-th block
   // beside the chain.  The plan (unit ranges per side group) exists from the second call on; the first call launches
   // every group at the end.
+  // Backward chain as ONE persistent launch (gemm_tc_stack_bwd.cuh): single-dilation blocks, D = R in {128, 256}, d z / d x_out
+  // of every block kept (grouped weight gradients), more 256-row tiles per layer than CTA pairs.  It takes every SM for the
+  // whole chain, so the weight gradients all run in the one grouped launch behind it (no side launches).
+  bool sb_ok = false;
+  if constexpr (sizeof(T) == 2) {
+    sb_ok = group && !cat && h->use_stack_bwd && tc_cta_group() == 2 && !h->drop_active && h->L >= 2 && h->D == h->R && (h->D == 256 || h->D == 128) &&
+            !(h->alias_skip && c.use_skip) && h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
+    for (auto& b : h->blocks) {
+      if (!sb_ok) break;
+      sb_ok = b.stack.size() == 1 && b.stack[0].cin % 64 == 0 && (!b.has_skip || h->S % 64 == 0) && (!c.use_residual || b.Wres16 != nullptr);
+    }
+  }
+  h->stack_bwd_layers = 0;
   int side_pairs = 0;
-  if (group && h->use_side && h->side_stream != nullptr && h->wg_side_every > 0) {
+  if (group && !sb_ok && h->use_side && h->side_stream != nullptr && h->wg_side_every > 0) {
     const int pairs = tc_num_sms() / 2, tiles = B * cdiv(Tn, 256);
     if (tiles > pairs) {
       const int rounds = cdiv(tiles, pairs);
@@ -1690,7 +1711,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   }
   auto side_group_of = [&](int l) -> int { return (side_pairs > 0 && (h->L - 1 - l) % h->wg_side_every == 0) ? (h->L - 1 - l) / h->wg_side_every : -1; };
   TcWgGroupPlan* wplan = nullptr;
-  if (group) for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active) wplan = &wp.plan;
+  if (group) for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active && wp.sb == sb_ok) wplan = &wp.plan;
   const bool side_now = wplan != nullptr && side_pairs > 0 && h->prof_tag == 0 && !wplan->side.empty();
   g_tc_balance = side_now ? 1 : 0;
   // ---- head
@@ -1766,6 +1787,55 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   } else {
     const void* dskip = c.use_skip ? h->dskip : nullptr;
     dxout = c.use_skip ? nullptr : (group ? dx_of(h->L - 1) : h->dxA);
+    bool stacked = false;
+    if constexpr (sizeof(T) == 2) {
+      if (sb_ok) {
+        auto desc_of = [&](int l) {
+          BlockP& b = h->blocks[l];
+          const ConvP& cv = b.stack[0];
+          TcStackBwdDesc d{};
+          d.B = B; d.T = Tn; d.nseg = cv.K; d.D = h->D; d.R = h->R; d.S = b.has_skip && dskip ? h->S : 0;
+          for (int k = 0; k < cv.K; ++k) d.shift[k] = (cv.K - 1 - k) * cv.dil;
+          d.dxo = l == h->L - 1 ? (const bf16*)dxout : (const bf16*)dx_of(l);
+          d.dskip = (b.has_skip && dskip) ? (const bf16*)dskip : nullptr; d.lds = h->Sp;
+          d.z = (const bf16*)h->zbuf[l]; d.dz = (bf16*)dz_of(l); d.dx = (bf16*)(l > 0 ? dx_of(l - 1) : h->dxA);
+          const int rs = h->R + (b.has_skip ? h->S : 0), koff = d.dxo ? 0 : h->R;
+          d.Wdg = b.Wdg16 + koff; d.k_dg = rup(rs, 64);
+          d.Wb = cv.Wb16; d.k_b = rup(cv.Kb16, 64);
+          d.ident = (c.use_residual && d.dxo) ? b.Wres16 + h->D : nullptr; d.ld_ident = h->D + h->R;
+          return d;
+        };
+        TcStackBwdPlan* sp = nullptr;
+        for (auto& q : h->stack_bwd_plans) if (q.B == B && q.T == Tn) sp = &q;
+        int r = 0;
+        if (!sp) {
+          cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+          cudaStreamIsCapturing(st, &cs);
+          if (cs == cudaStreamCaptureStatusNone) {
+            if (h->stack_bwd_plans.size() >= 4) {
+              CK(cudaDeviceSynchronize());
+              for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+              h->graphs.clear();
+              for (auto& q : h->stack_bwd_plans) q.release();
+              h->stack_bwd_plans.clear();
+            }
+            std::vector<TcStackBwdDesc> descs;
+            for (int l = 0; l < h->L; ++l) descs.push_back(desc_of(l));
+            h->stack_bwd_plans.push_back(TcStackBwdPlan{});
+            r = tc_stack_bwd_build(h->tmaps, descs, &h->stack_bwd_plans.back());
+            if (r == 0) sp = &h->stack_bwd_plans.back(); else h->stack_bwd_plans.pop_back();
+          }
+        }
+        if (sp) {
+          struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_bwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
+          LaunchScope ls(h, st, CLS_DILATED);
+          r = tc_stack_bwd_launch(st, *sp, desc_of(0));
+          if (r == 0) { stacked = true; h->stack_bwd_layers = h->L; }
+          else if (r == -100) h->launches--;
+          else { set_err("stack backward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+        } else if (r != 0 && r != -100) { set_err("stack backward plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+      }
+    }
     for (int l = h->L - 1; l >= 0; --l) {
       const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
       // grouped weight gradients: d x_out and d z of every block keep their own buffers until the grouped launch below
@@ -1773,7 +1843,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       BwdSide sd; const BwdSide* sdp = side_setup(h, st, l, use_side, &sd);
       h->wg_cur_group = side_group_of(l);
       RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef, group ? dz_of(l) : ((l & 1) ? h->dz2 : h->dz), sdp,
-                            group));
+                            group, stacked));
       if constexpr (sizeof(T) == 2) {
         if (side_now && h->wg_cur_group >= 0 && h->wg_cur_group < (int)wplan->side.size() && wplan->side[h->wg_cur_group].second > 0) {
           // d z_l and d x_out_l are complete behind this block's kernels: its weight gradients start on the side stream
@@ -1841,7 +1911,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
           for (auto& wp : h->wg_plans) wp.plan.release();
           h->wg_plans.clear();
         }
-        h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, TcWgGroupPlan{}});
+        h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, sb_ok, TcWgGroupPlan{}});
         plan = &h->wg_plans.back().plan;
         int r = tc_wgrad_group_build(h->tmaps, h->wg_jobs, B, Tn, h->wg_force_split, h->wg_pair_tiles != 0, side_pairs, plan);
         if (r != 0) { h->wg_plans.pop_back(); set_err("grouped wgrad plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
@@ -2718,6 +2788,7 @@ extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->laun
 // number of blocks whose gated conv + conv1 ran as ONE fused launch in the last enqueued forward (0 = separate kernels)
 extern "C" int wn_fused_forward_blocks(const wn_handle* h) { return h ? h->fused_fwd_launches : 0; }
 extern "C" int wn_stack_forward_layers(const wn_handle* h) { return h ? h->stack_fwd_layers : 0; }
+extern "C" int wn_stack_backward_layers(const wn_handle* h) { return h ? h->stack_bwd_layers : 0; }
 extern "C" int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches) {
   if (side_launches) *side_launches = h ? h->wg_last_side : 0;
   return h ? h->wg_last_tiles : 0;
