@@ -10,12 +10,12 @@ are bf16 values, so fp64 accumulation is the exact value the fp32 accumulators a
 
 Rounding points of the bf16 tier (wavenets_b200/csrc):
   forward   GEMM weights (packed bf16 copies of the fp32 masters; biases stay fp32); h0 (input conv output); the outputs
-            of the pre-stack convs (after the activation); z (cached for the backward pass ONLY: the gate itself is
-            evaluated on the un-rounded accumulator); g; x_out; the skip sum; the head's hidden activations.
+            of the pre-stack convs (after the activation); the gate's derivative coefficients P, Q (cached for the backward pass
+            INSTEAD of z; they and the gate itself are evaluated on the un-rounded accumulator); g; x_out; the skip sum; the head's hidden activations.
             NOT rounded: the input conv's and the conditioning path's weights and arithmetic (fp32), the logits (fp32).
   backward  d logits; the gradient wrt every head / pre-stack PRE-activation (dgrad epilogue: (dY W^T) * act'(cached bf16
             output)); d skip; d(conv1 output) (= d x_out + d skip when the skip aliases conv1, one rounded sum);
-            d z (gate adjoint evaluated at the CACHED bf16 z); d x_out of every block (dgrad + residual gradient, one
+            d z (= d g times the CACHED bf16 coefficients P, Q); d x_out of every block (dgrad + residual gradient, one
             rounded sum); d h0.  NOT rounded: d g (lives in the accumulator), every weight / bias gradient (fp32 sums of
             products / column sums of the rounded tensors above).
 With `faithful=False` all roundings are identities and the module is a plain fp64 model (checked against
@@ -63,21 +63,22 @@ class _RoundBwd(torch.autograd.Function):
 
 
 class _Gate(torch.autograd.Function):
-  """g = tanh(z_f) * sigmoid(z_s) on the un-rounded accumulator (layers.py:208-210); the adjoint is evaluated at the
-  cached bf16 z and d z is stored in bf16 (TcEpiGate / TcEpiGateBwd, csrc/tc_epilogues.cuh)."""
+  """g = tanh(z_f) * sigmoid(z_s) on the un-rounded accumulator (layers.py:208-210).  The forward pass caches the gate's two
+  derivative coefficients P = dg/dz_f = sig(z_s)(1 - tanh(z_f)^2), Q = dg/dz_s = tanh(z_f) sig(z_s)(1 - sig(z_s)), evaluated
+  on the un-rounded accumulator and stored in bf16; the adjoint is d z = [dg P | dg Q], stored in bf16
+  (TcEpiGate / TcEpiGateBwd, csrc/tc_epilogues.cuh)."""
 
   @staticmethod
   def forward(ctx, z):
     D = z.shape[-1] // 2
-    ctx.save_for_backward(_bf16(z))
-    return torch.tanh(z[..., :D]) * torch.sigmoid(z[..., D:])
+    th, sg = torch.tanh(z[..., :D]), torch.sigmoid(z[..., D:])
+    ctx.save_for_backward(_bf16(sg * (1.0 - th * th)), _bf16(th * sg * (1.0 - sg)))
+    return th * sg
 
   @staticmethod
   def backward(ctx, dg):
-    (zr,) = ctx.saved_tensors
-    D = zr.shape[-1] // 2
-    th, sg = torch.tanh(zr[..., :D]), torch.sigmoid(zr[..., D:])
-    return _bf16(torch.cat([dg * sg * (1.0 - th * th), dg * th * sg * (1.0 - sg)], dim=-1))
+    P, Q = ctx.saved_tensors
+    return _bf16(torch.cat([dg * P, dg * Q], dim=-1))
 
 
 class _Act(torch.autograd.Function):

@@ -3,6 +3,7 @@ relative L2 error against oracle/faithful.py on a small C2-shaped model: python 
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import torch
 from oracle import faithful, wavenet_oracle as wo
 from tests.util import make_inputs, oracle_config, rel_l2
 from wavenets_b200 import WaveNet
@@ -42,7 +43,9 @@ def cmp(label, a, ref):
 Wd = 512
 cmp('h0', dev('h0', 0, Wd), tap['h0'])
 for l in range(L):
-  cmp(f'z[{l}]', dev('z', l, Wd), faithful._bf16(tap[('z', l)].detach()))
+  zz = tap[('z', l)].detach(); Dh = zz.shape[-1] // 2      # the device caches the gate's derivative coefficients [P | Q], not z
+  th_, sg_ = torch.tanh(zz[..., :Dh]), torch.sigmoid(zz[..., Dh:])
+  cmp(f'PQ[{l}]', dev('z', l, Wd), faithful._bf16(torch.cat([sg_ * (1 - th_ * th_), th_ * sg_ * (1 - sg_)], -1)))
   cmp(f'g[{l}]', dev('g', l, Wd), tap[('g', l)])
   cmp(f'xout[{l}]', dev('xout', l, Wd), tap[('xout', l)])
 cmp('skipsum', dev('skipsum', 0, Wd), tap['skipsum'])

@@ -72,37 +72,90 @@ def test_fullsize_batch_permutation(c2):
   assert num <= 2e-3 * den, num / den
 
 
-def test_fullsize_schedules_agree(c2):
-  """C2 at full size through the default schedules (stack forward as one persistent launch, grouped weight gradients with
-  side launches) against one launch per block for everything (WN_TC_STACK_FWD=0, WN_TC_GROUP_WGRAD=0): the forward is the
-  same tile arithmetic (loss bit-equal), the gradients differ by fp32 summation order only."""
+def _with_env(env, fn):
   import os
-  from wavenets_b200 import CONFIGS, WaveNet, model_kwargs
-  m, x, c, B, T = c2
-  m.n_replicas = 1
-  for _ in range(3):                                     # plan built, side launches, graph replay
-    l_new = m.train_step((x, c))['loss']
-  g_new = m.get_grads()
-  old = {k: os.environ.get(k) for k in ('WN_TC_STACK_FWD', 'WN_TC_GROUP_WGRAD')}
-  os.environ['WN_TC_STACK_FWD'] = '0'
-  os.environ['WN_TC_GROUP_WGRAD'] = '0'
+  old = {k: os.environ.get(k) for k in env}
+  os.environ.update(env)
   try:
-    kw = model_kwargs(dict(CONFIGS['c2']))
-    m2 = WaveNet(**kw, precision='bf16', max_batch=B, max_time=T)     # the switches are read at wn_create
-    m2.build(((B, T, 1), (B, 109)))
-    m2.set_weights(m.get_weights())
-    l_old = m2.train_step((x, c))['loss']
-    g_old = m2.get_grads()
+    return fn()
   finally:
     for k, v in old.items():
       if v is None:
         os.environ.pop(k, None)
       else:
         os.environ[k] = v
-  assert int(m.handle.lib.wn_stack_forward_layers(m.handle.h)) == 30 and int(m2.handle.lib.wn_stack_forward_layers(m2.handle.h)) == 0
-  assert int(m.handle.lib.wn_grouped_wgrad_tiles(m.handle.h, None)) > 0 and int(m2.handle.lib.wn_grouped_wgrad_tiles(m2.handle.h, None)) == 0
-  assert l_new == l_old
-  for k in g_old:
-    ref = g_old[k]
-    err = float(np.abs(g_new[k] - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+def _debug_tensor(m, name, index, rows, width):
+  import ctypes as C
+  out = np.empty((rows, width), np.float32)
+  r = m.handle.lib.wn_debug_tensor(m.handle.h, name.encode(), index, out.ctypes.data_as(C.POINTER(C.c_float)), out.size)
+  assert r == width, (name, index, r, m.handle.lib.wn_last_error())
+  return out
+
+
+def test_fullsize_schedules_agree(c2):
+  """C2 at full size, three schedules of the same arithmetic:
+    A  default: stack forward and stack backward as one persistent launch each, grouped weight gradients;
+    B  WN_TC_STACK_BWD=0: the backward chain as one gate-adjoint + one dgrad launch per block (round 1's schedule);
+    C  WN_TC_STACK_FWD=0, WN_TC_GROUP_WGRAD=0: one launch per block for everything.
+  The forward is the same tile arithmetic everywhere (loss bit-equal).  B vs C: the same chain kernels, gradients differ by the
+  fp32 summation order of the weight-gradient splits only.  A vs B: the fused chain adds the taps, the residual (identity block of
+  the contraction instead of an epilogue add) and the two DG halves in another fp32 order; a sum that lands on the other side of
+  a bf16 rounding boundary flips one stored d z / d x_out element by one ulp, and those flips travel down 30 blocks: the first
+  block the chain processes must agree almost everywhere; further down the two chains' roundings decorrelate and the distance
+  approaches the bf16 storage error itself (the sharp check of the fused chain at depth is tests/test_gpu_configs.py: every
+  gradient against the bf16-faithful oracle at this topology)."""
+  from wavenets_b200 import CONFIGS, WaveNet, model_kwargs
+  m, x, c, B, T = c2
+  m.n_replicas = 1
+  lib = m.handle.lib
+  for _ in range(3):                                     # plan built, side launches, graph replay
+    l_a = m.train_step((x, c))['loss']
+  g_a = m.get_grads()
+  assert int(lib.wn_stack_forward_layers(m.handle.h)) == 30 and int(lib.wn_stack_backward_layers(m.handle.h)) == 30
+  assert int(lib.wn_grouped_wgrad_tiles(m.handle.h, None)) > 0
+  rows = B * T
+  dx_a = {l: _debug_tensor(m, 'dx', l, rows, 256) for l in (28, 14)}     # d x_out of block l (written by block l+1's tiles)
+  dz_a = _debug_tensor(m, 'dz', 29, rows, 512)
+
+  def other(env):
+    def make():
+      kw = model_kwargs(dict(CONFIGS['c2']))
+      m2 = WaveNet(**kw, precision='bf16', max_batch=B, max_time=T)     # the switches are read at wn_create
+      m2.build(((B, T, 1), (B, 109)))
+      m2.set_weights(m.get_weights())
+      for _ in range(3):
+        l2 = m2.train_step((x, c))['loss']
+      return m2, l2
+    return _with_env(env, make)
+
+  m_b, l_b = other({'WN_TC_STACK_BWD': '0'})
+  g_b = m_b.get_grads()
+  assert int(lib.wn_stack_forward_layers(m_b.handle.h)) == 30 and int(lib.wn_stack_backward_layers(m_b.handle.h)) == 0
+  assert l_a == l_b
+  # the last block's d z is the first thing either chain computes: no flips have accumulated yet
+  dz_b = _debug_tensor(m_b, 'dz', 29, rows, 512)
+  e = float(np.linalg.norm(dz_a - dz_b) / np.linalg.norm(dz_b))
+  assert e < 2e-4, ('dz[29]', e)
+  for l, tol in ((28, 5e-4), (14, 2e-2)):
+    dx_b = _debug_tensor(m_b, 'dx', l, rows, 256)
+    e = float(np.linalg.norm(dx_a[l] - dx_b) / np.linalg.norm(dx_b))
+    print(f'stack backward vs per-block chain: d x_out[{l}] rel-L2 {e:.2e}')
+    assert e < tol, ('dx', l, e)
+  worst = 0.0
+  for k in g_b:
+    err = float(np.linalg.norm(g_a[k] - g_b[k]) / (np.linalg.norm(g_b[k]) + 1e-30))
+    worst = max(worst, err)
+    assert err < 1.5e-2, (k, err)     # two correct bf16 chains decorrelate to ~ the bf16 storage error (measured: d x_out[14] 7e-3)
+  print(f'stack backward vs per-block chain: worst gradient tensor rel-L2 {worst:.2e}')
+  del dx_a, dz_a, dz_b
+
+  m_c, l_c = other({'WN_TC_STACK_FWD': '0', 'WN_TC_GROUP_WGRAD': '0'})
+  g_c = m_c.get_grads()
+  assert int(lib.wn_stack_forward_layers(m_c.handle.h)) == 0 and int(lib.wn_grouped_wgrad_tiles(m_c.handle.h, None)) == 0
+  assert l_b == l_c
+  for k in g_c:
+    ref = g_c[k]
+    err = float(np.abs(g_b[k] - ref).max() / (np.abs(ref).max() + 1e-30))
     assert err < 3e-4, (k, err)       # 64,000 rows per gradient entry, fp32 chains of different lengths

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, 'libwavenet_b200.so')
 STAMP = os.path.join(HERE, '.libwavenet_b200.stamp')
 # flavours: '' = the product; 'precise' = same sources with -DWN_PRECISE_MATH (accurate tanh / sigmoid in the bf16 tier's gates
 # instead of MUFU.TANH) — test infrastructure for the bf16-faithful parity tests, loaded with WN_LIB=<path>
-FLAVOURS = {'': [], 'precise': ['-DWN_PRECISE_MATH']}
+FLAVOURS = {'': [], 'precise': ['-DWN_PRECISE_MATH'], 'tl': ['-DTC_TIMELINE']}   # 'tl': in-kernel clock64 phase accounting (printf), diagnostics only
 
 SOURCES = ['wn_api.cu']
 HEADERS = ['common.cuh', 'generate.cuh', 'epilogues.cuh', 'gemm_simt.cuh', 'gemm_tc.cuh', 'gemm_tc_block.cuh', 'gemm_tc_wgroup.cuh', 'gemm_tc_stack.cuh', 'gemm_tc_stack_bwd.cuh', 'tc_common.cuh', 'tc_epilogues.cuh', 'kernels_misc.cuh', 'nccl_dl.cuh',

@@ -88,8 +88,16 @@ template <class T, bool FAST> struct EpiGate {
         if (i < nv) {
           float zf = f[i] + p.bias[ch + i], zs = s[i] + p.bias[p.D + ch + i];
           if (cb) { zf += cb[ch + i]; zs += cb[p.D + ch + i]; }
-          f[i] = zf; s[i] = zs;
-          g[i] = wn_tanh<FAST>(zf) * wn_sigmoid<FAST>(zs);
+          if constexpr (sizeof(T) == 2) {
+            // bf16 tier: cache the gate's derivative coefficients P, Q instead of z (csrc/tc_epilogues.cuh: TcEpiGate)
+            const float th = wn_tanh<FAST>(zf), sg = wn_sigmoid<FAST>(zs);
+            g[i] = th * sg;
+            f[i] = fmaf(-sg * th, th, sg);
+            s[i] = fmaf(-g[i], sg, g[i]);
+          } else {
+            f[i] = zf; s[i] = zs;
+            g[i] = wn_tanh<FAST>(zf) * wn_sigmoid<FAST>(zs);
+          }
         } else {
           g[i] = 0.f;
         }
@@ -125,9 +133,14 @@ template <class T, bool FAST> struct EpiGateBwd {
       load16<T>(zrow + p.D + ch, s, nv, p.vec);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float th = wn_tanh<FAST>(f[i]), sg = wn_sigmoid<FAST>(s[i]);
-        f[i] = dg[i] * sg * (1.0f - th * th);
-        s[i] = dg[i] * th * sg * (1.0f - sg);
+        if constexpr (sizeof(T) == 2) {
+          f[i] = dg[i] * f[i];      // cached P, Q
+          s[i] = dg[i] * s[i];
+        } else {
+          const float th = wn_tanh<FAST>(f[i]), sg = wn_sigmoid<FAST>(s[i]);
+          f[i] = dg[i] * sg * (1.0f - th * th);
+          s[i] = dg[i] * th * sg * (1.0f - sg);
+        }
       }
       T* drow = p.dz + grow * 2 * p.D;
       store16<T>(drow + ch, f, nv, p.vec);

@@ -9,7 +9,8 @@
 //                                                                    into a K-major 128B-swizzled operand buffer in shared
 //                                                                    memory (and from there, by TMA, to HBM once: the
 //                                                                    grouped weight gradients read it later)
-//   d x_out_{l-1} = d x_out_l . I                                    OUT tile, residual through the identity block
+//   d x_out_{l-1} = d x_out_l                                        OUT tile: the residual gradient is added in the OUT epilogue
+//                                                                    (d x_out panels arrive by TMA in the ring the P, Q panels use)
 //                 + d z[t]       . W_{K-1}^T                         ... the un-shifted tap straight from the operand buffer
 //                 + d z[t + s_k] . W_k^T,  k < K-1                   ... the anti-causal taps by TMA from HBM / L2 (rows of
 //                                                                    LATER tiles of the same block, and the peer's half)
@@ -24,14 +25,23 @@
 // producer warp before the first dependent load.  All CTAs are resident (grid <= SMs, 1 CTA per SM), ids ascend per pair.
 //
 // TMEM: columns [0, D) = DG accumulator, [256, 256 + R) = OUT accumulator (one stage each: the OUT accumulator is held from
-// the identity products until its epilogue has read it; the next tile's DG products run under that epilogue).
+// the first un-shifted tap product until its epilogue has read it; the next tile's DG products run under that epilogue).
 // Warps: 0 TMA producer (operand ring) | 1 MMA issuer (leader CTA) | 2 TMEM allocator, then TMA-store warp + tile publisher |
 //        3 z-panel producer | 4-11 epilogue (DG: gate adjoint; OUT: pack) | 12 pair hand-off of the d z slabs
 #pragma once
 #include "gemm_tc_stack.cuh"
 
+// in-kernel phase accounting (clock64 sums over all tiles of one CTA, printed by CTAs 0 and 41): -DTC_TIMELINE builds only
+#ifdef TC_TIMELINE
+#define SBT_DECL(n) long long sbt[n] = {}; long long sbt_prev = clock64();
+#define SBT(i) { const long long sbt_now = clock64(); sbt[i] += sbt_now - sbt_prev; sbt_prev = sbt_now; }
+#else
+#define SBT_DECL(n)
+#define SBT(i)
+#endif
+
 struct alignas(128) TcStackBwdLayer {
-  CUtensorMap tmDX, tmDS, tmWdg, tmZf, tmZs, tmDZ, tmWb, tmI, tmO;
+  CUtensorMap tmDX, tmDS, tmWdg, tmZf, tmZs, tmDZ, tmWb, tmDXp, tmO;   // tmZf / tmZs: the cached gate derivative coefficients P / Q; tmDXp: d x_out as 32-column panels
   int shift[TC_MAX_SEG];      // row shift of tap k (k < nseg - 1: positive; tap nseg - 1: 0)
   int has_dx, has_ds, has_res;
   int wait_dx;                // d x_out_l is written by this launch (every block but the last): acquire its tile flag first
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(416, 1)
 tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict__ flags_dx, int* __restrict__ flags_dz, const TcStackBwdParams p) {
   using Cfg = TcStackBwdCfg<D_, R_>;
   constexpr int STAGES = Cfg::STAGES, NEPI = 8, NPAIR = Cfg::NPAIR;
-  constexpr int KB_R = R_ / 64, KB_Z = Cfg::NSLAB;
+  constexpr int KB_Z = Cfg::NSLAB;
   extern __shared__ __align__(1024) uint8_t smem_sb[];
   uint8_t* smem = smem_sb;
   if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("libwavenet_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -137,6 +147,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       auto next = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1; } };
+      SBT_DECL(4)
       constexpr int WDG_BYTES = (D_ / 2) * 64 * 2, WB_BYTES = (R_ / 2) * 64 * 2;
       for (int j = 0; j < n_tiles; ++j) {
         int ly, mt, b, tb;
@@ -147,8 +158,10 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         if (Ly.has_dx) {
           if (Ly.wait_dx) {
             // d x_out_l tile m was written by the OUT tile (l+1, m) of this launch
+            SBT(0)
             wait_flag(flags_dx + (size_t)(ly + 1) * p.num_mtiles + mt, ly + 1, mt);
             fence_proxy_async_global();
+            SBT(1)
           }
           for (int kb = 0; kb < p.kb_dx; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -170,17 +183,6 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
             next();
           }
         }
-        // ---- OUT, residual gradient through the identity block
-        if (Ly.has_dx && Ly.has_res) {
-          for (int kb = 0; kb < KB_R; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WB_BYTES));
-            tma_load_4d_pair_h(sa, &Ly.tmDX, &full_bar[stage], kb * 64, t0, b, 0, p.pol_dx);
-            tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmI, &full_bar[stage], kb * 64, (int)crank * (R_ / 2), p.pol_w);
-            next();
-          }
-        }
         // ---- OUT, un-shifted tap: only the weights (the A operand is the d z buffer), slab pairs in production order
         const int kloc = (p.nseg - 1) * 2 * D_;
         for (int pr = 0; pr < NPAIR; ++pr) {
@@ -199,8 +201,10 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           const int t_lo = lo / (2 * Cfg::BM);
           int t_hi = (lo + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
           if (t_hi > p.tiles_t - 1) t_hi = p.tiles_t - 1;
+          SBT(0)
           for (int tt = t_lo; tt <= t_hi; ++tt) wait_flag(flags_dz + (size_t)ly * p.num_mtiles + b * p.tiles_t + tt, ly, b * p.tiles_t + tt);
           fence_proxy_async_global();
+          SBT(2)
           for (int kb = 0; kb < KB_Z; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -211,6 +215,11 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           }
         }
       }
+      SBT(0)
+#ifdef TC_TIMELINE
+      if (blockIdx.x == 0 || blockIdx.x == 41)
+        printf("SBWD cta %d producer: tiles %d  ring+issue %lld  wait_flag_dx %lld  wait_flag_dz %lld\n", blockIdx.x, n_tiles, sbt[0], sbt[1], sbt[2]);
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -220,8 +229,15 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       const uint32_t t_dg = tmem_base, t_out = tmem_base + 256u;
       int stage = 0; uint32_t phase = 0;
       uint32_t n_sf[2] = {0u, 0u};       // completed waits on slab_full[ps]
+      SBT_DECL(10)
       auto kstep = [&](uint32_t d_tmem, uint32_t idesc, bool a_from_dz, int slot, bool first, uint64_t* extra0, uint64_t* extra1) {
+#ifdef TC_TIMELINE
+        const long long w0 = clock64();
+#endif
         mbar_wait(&full_bar[stage], phase);
+#ifdef TC_TIMELINE
+        sbt[9] += clock64() - w0;
+#endif
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -244,27 +260,37 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         const TcStackBwdLayer& Ly = layers[ly];
         const uint32_t par = (uint32_t)(j & 1);
         // ---- DG
+        SBT(0)
         mbar_wait(dg_empty, par ^ 1);
+        SBT(1)
         tc_fence_after();
         const int ks_dg = (Ly.has_dx ? p.kb_dx : 0) + (Ly.has_ds ? p.kb_ds : 0);
         for (int ks = 0; ks < ks_dg; ++ks) kstep(t_dg, idesc_g, false, 0, ks == 0, ks == ks_dg - 1 ? dg_full : nullptr, nullptr);
         // ---- OUT
+        SBT(2)
         mbar_wait(out_empty, par ^ 1);
+        SBT(3)
         tc_fence_after();
-        const int ks_id = (Ly.has_dx && Ly.has_res) ? KB_R : 0;
         const int ks_sh = (p.nseg - 1) * KB_Z;
         bool first = true;
-        for (int ks = 0; ks < ks_id; ++ks) { kstep(t_out, idesc_o, false, 0, first, nullptr, nullptr); first = false; }
         for (int pr = 0; pr < NPAIR; ++pr) {
           const int ps = pr & 1;
           mbar_wait(&slab_full[ps], n_sf[ps] & 1u); ++n_sf[ps];     // both CTAs' slab pair is in shared memory
+          SBT(5)
           tc_fence_after();
           const bool last = ks_sh == 0 && pr == NPAIR - 1;
           kstep(t_out, idesc_o, true, 2 * ps, first, nullptr, nullptr); first = false;
           kstep(t_out, idesc_o, true, 2 * ps + 1, false, &slab_cons[ps], last ? out_full : nullptr);
+          SBT(6)
         }
         for (int ks = 0; ks < ks_sh; ++ks) kstep(t_out, idesc_o, false, 0, false, ks == ks_sh - 1 ? out_full : nullptr, nullptr);
+        SBT(7)
       }
+#ifdef TC_TIMELINE
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 40))
+        printf("SBWD cta %d mma: tiles %d  wait_dg_empty %lld  DG ksteps %lld  wait_out_empty %lld  wait_slab_full %lld  unshifted %lld  shifted %lld  (of the ksteps: wait_full_bar %lld)\n",
+               blockIdx.x, n_tiles, sbt[1], sbt[2], sbt[3], sbt[5], sbt[6], sbt[7], sbt[9]);
+#endif
     }
   } else if (warp == 2) {
     // ===================== TMA-store warp + tile publisher =====================
@@ -330,6 +356,19 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           tma_load_3d_h(dst + Cfg::PANEL, &Ly.tmZs, &in_full[islot], step * 32, t0, b, p.pol_z);
           if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
         }
+        if (Ly.has_dx && Ly.has_res) {
+          // residual gradient: d x_out_l panels for the OUT epilogue (one panel per slot)
+          if (Ly.wait_dx) {
+            wait_flag(flags_dx + (size_t)(ly + 1) * p.num_mtiles + mt, ly + 1, mt);      // (long set: the operand producer waited for it before DG)
+            fence_proxy_async_global();
+          }
+          for (int step = 0; step < R_ / 32; ++step) {
+            mbar_wait(&in_empty[islot], iphase ^ 1);
+            mbar_expect_tx(&in_full[islot], (uint32_t)Cfg::PANEL);
+            tma_load_3d_h(in_ring + islot * 2 * Cfg::PANEL, &Ly.tmDXp, &in_full[islot], step * 32, t0, b, p.pol_dx);
+            if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 12) {
@@ -360,10 +399,19 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     uint32_t n_use[2] = {0u, 0u};      // fills of slab pair slot ps so far
     const TcEpiGateBwd<true>::Params pg{D_};
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    SBT_DECL(10)
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
-      // ---- DG epilogue: d z = gate'(z) * dg -> operand buffer
+      bool add_res;
+      {
+        int ly, mt, b, tb;
+        locate(j, ly, mt, b, tb);
+        add_res = layers[ly].has_dx != 0 && layers[ly].has_res != 0;
+      }
+      // ---- DG epilogue: d z = d g * [P | Q] -> operand buffer
+      SBT(0)
       mbar_wait(dg_full, par);
+      SBT(1)
       tc_fence_after();
       {
         TmemAccRow acc{tmem_base + lane_base, true};
@@ -372,7 +420,9 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           const int pr = step >> 1, ps = pr & 1;
           float in[2][16];
           float out[2][16];
+          SBT(2)
           mbar_wait(&in_full[islot], iphase);
+          SBT(3)
           {
             const uint8_t* ib = in_ring + islot * 2 * Cfg::PANEL;
 #pragma unroll
@@ -391,11 +441,13 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           if (lane == 0) mbar_arrive(&in_empty[islot]);
           if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
           TcEpiGateBwd<true>::chunk(pg, acc, 0, step * 32 + q * 16, 0, 0, 3u, in, out, nullptr);
+          SBT(2)
           if ((step & 1) == 0 && n_use[ps] > 0) {
             // the slot still holds an earlier slab pair: its MMAs must have completed and its TMA stores read the buffer
             mbar_wait(&slab_cons[ps], (n_use[ps] - 1u) & 1u);
             mbar_wait(&slab_free[ps], (n_use[ps] - 1u) & 1u);
           }
+          SBT(4)
           {
             // channels [ch, ch+16) of this row: 16-byte units (ch % 64) / 8 and +1 of the 128B-swizzled 64-column slab
             const int ch = (step & 1) * 32 + q * 16;
@@ -426,7 +478,9 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(dg_empty, 0u);
       // ---- OUT epilogue: d x_out_{l-1}
+      SBT(2)
       mbar_wait(out_full, par);
+      SBT(5)
       tc_fence_after();
       {
         TmemAccRow acc{tmem_base + 256u + lane_base, true};
@@ -434,8 +488,25 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         for (int step = 0; step < R_ / 32; ++step) {
           float v[16];
           acc.load16(step * 32 + q * 16, v);
+          if (add_res) {
+            mbar_wait(&in_full[islot], iphase);
+            const uint8_t* ib = in_ring + islot * 2 * Cfg::PANEL;
+            const uint4 a = *reinterpret_cast<const uint4*>(ib + off0);
+            const uint4 c = *reinterpret_cast<const uint4*>(ib + off1);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[2 * i] += __uint_as_float(w[i] << 16);
+              v[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&in_empty[islot]);
+            if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
+          }
           uint8_t* ob = out_ring + oslot * Cfg::PANEL;
+          SBT(6)
           mbar_wait(&oslot_empty[oslot], ophase ^ 1);
+          SBT(7)
           uint4 a, c;
           a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
           c.x = pack_bf16x2(v[8], v[9]); c.y = pack_bf16x2(v[10], v[11]); c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
@@ -449,7 +520,13 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(out_empty, 0u);
+      SBT(6)
     }
+#ifdef TC_TIMELINE
+    if (lane == 0 && warp == 4 && (blockIdx.x == 0 || blockIdx.x == 41))
+      printf("SBWD cta %d epilogue warp 4: wait_dg_full %lld  DG epi work %lld (+ wait z panels %lld, wait slab slot %lld)  wait_out_full %lld  OUT epi work %lld (+ wait out slot %lld)\n",
+             blockIdx.x, sbt[1], sbt[2], sbt[3], sbt[4], sbt[5], sbt[6], sbt[7]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -467,7 +544,7 @@ struct TcStackBwdDesc {       // one block
   bf16* dx;                   // d x_out_{l-1} (B,T,R)
   const bf16* Wdg; int k_dg;  // [D][k_dg] = [Wr^T | Ws^T] rows (first k = R, or S when dxo == null and the pointer is offset)
   const bf16* Wb; int k_b;    // [R][k_b]: dgrad operand of the gated conv, contraction (tap, 2D)
-  const bf16* ident; int ld_ident;   // [R][ld_ident] holding the R x R identity (columns 0..R-1 from this pointer), or null
+  int has_res;                // use_residual: d x_out_{l-1} += d x_out_l
 };
 
 struct TcStackBwdPlan {
@@ -496,25 +573,21 @@ static int tc_stack_bwd_build_t(TmapCache& tc, const std::vector<TcStackBwdDesc>
     const CUtensorMap* mWb = tc.get(d.Wb, 2, bd, bs, bb);
     if (!mDZ || !mZf || !mZs || !mO || !mWdg || !mWb) return -10;
     t.tmDZ = *mDZ; t.tmZf = *mZf; t.tmZs = *mZs; t.tmO = *mO; t.tmWdg = *mWdg; t.tmWb = *mWb;
-    t.tmDX = *mDZ; t.tmDS = *mDZ; t.tmI = *mWb;       // placeholders for absent operands (never dereferenced)
+    t.tmDX = *mDZ; t.tmDS = *mDZ; t.tmDXp = *mO;       // placeholders for absent operands (never dereferenced)
     if (d.dxo) {
       const CUtensorMap* m = tc_act_map(tc, d.dxo, d.R, d.R, d.T, d.B, 1, 0, 128);
-      if (!m) return -10;
-      t.tmDX = *m;
+      const TcEpiIo xi{d.dxo, d.R, d.R, 0};
+      const CUtensorMap* mp = tc_panel_map(tc, xi, d.T, d.B);
+      if (!m || !mp) return -10;
+      t.tmDX = *m; t.tmDXp = *mp;
     }
     if (d.dskip) {
       const CUtensorMap* m = tc_act_map(tc, d.dskip, d.lds, d.S, d.T, d.B, 1, 0, 128);
       if (!m) return -10;
       t.tmDS = *m;
     }
-    if (d.ident) {
-      uint64_t id[2] = {(uint64_t)d.R, (uint64_t)d.R}, is[1] = {(uint64_t)d.ld_ident * 2};
-      const CUtensorMap* m = tc.get(d.ident, 2, id, is, bb);
-      if (!m) return -10;
-      t.tmI = *m;
-    }
     for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
-    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = d.ident != nullptr;
+    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = (d.has_res && d.dxo != nullptr) ? 1 : 0;
     t.wait_dx = (d.dxo != nullptr && l + 1 < descs.size()) ? 1 : 0;
   }
   const TcStackBwdDesc& d0 = descs[0];

@@ -74,7 +74,14 @@ template <bool FAST> struct TcEpiBiasActRes {
   }
 };
 
-// gated activation (layers.py:203-210): tile = [filter half | gate half]; outputs z_f, z_s, g
+// gated activation (layers.py:203-210): tile = [filter half | gate half]; outputs P, Q, g.
+// bf16 tier: the backward pass needs z only to evaluate the gate's derivative.  Instead of z the forward pass caches the
+// two derivative coefficients themselves, computed from the un-rounded fp32 accumulator it holds anyway:
+//   P = d g / d z_f = sigmoid(z_s) (1 - tanh(z_f)^2)        Q = d g / d z_s = tanh(z_f) sigmoid(z_s) (1 - sigmoid(z_s))
+// (same bytes as z_f, z_s).  The gate adjoint becomes d z_f = d g * P, d z_s = d g * Q: no tanh / sigmoid recomputation
+// (2 MUFU + ~20 issue slots per element: the stack-backward kernel's DG epilogue was instruction bound at 8.3 k cycles per
+// 256-row tile, MUFU floor 4.1 k), and the coefficients carry bf16's 2^-9 relative error instead of the error of a derivative
+// evaluated at a bf16-rounded z (up to 1.2 %).  The fp32 tier keeps z (csrc/epilogues.cuh).
 template <bool FAST> struct TcEpiGate {
   static constexpr int NIN = 0, NOUT = 3;
   static constexpr int kInPanels = 0, kOutSlots = 3;
@@ -110,14 +117,16 @@ template <bool FAST> struct TcEpiGate {
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      out[0][i] = f[i];
-      out[1][i] = s[i];
-      out[2][i] = wn_tanh<FAST>(f[i]) * wn_sigmoid<FAST>(s[i]);
+      const float th = wn_tanh<FAST>(f[i]), sg = wn_sigmoid<FAST>(s[i]);
+      const float g = th * sg;
+      out[0][i] = fmaf(-sg * th, th, sg);      // P = sg (1 - th^2)
+      out[1][i] = fmaf(-g, sg, g);             // Q = th sg (1 - sg)
+      out[2][i] = g;
     }
   }
 };
 
-// adjoint of the gate: acc = dg; inputs cached z_f, z_s; outputs dz_f, dz_s
+// adjoint of the gate: acc = dg; inputs the cached derivative coefficients P, Q (see TcEpiGate); outputs dz_f, dz_s
 #ifndef TC_GATEBWD_IN_PANELS
 #define TC_GATEBWD_IN_PANELS 8
 #endif
@@ -147,9 +156,8 @@ template <bool FAST> struct TcEpiGateBwd {
     acc.load16(acc_col, dg);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float th = wn_tanh<FAST>(in[0][i]), sg = wn_sigmoid<FAST>(in[1][i]);
-      out[0][i] = dg[i] * sg * (1.0f - th * th);
-      out[1][i] = dg[i] * th * sg * (1.0f - sg);
+      out[0][i] = dg[i] * in[0][i];
+      out[1][i] = dg[i] * in[1][i];
     }
   }
 };

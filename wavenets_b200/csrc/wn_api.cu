@@ -1696,7 +1696,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
             !(h->alias_skip && c.use_skip) && h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!sb_ok) break;
-      sb_ok = b.stack.size() == 1 && b.stack[0].cin % 64 == 0 && (!b.has_skip || h->S % 64 == 0) && (!c.use_residual || b.Wres16 != nullptr);
+      sb_ok = b.stack.size() == 1 && b.stack[0].cin % 64 == 0 && (!b.has_skip || h->S % 64 == 0);
     }
   }
   h->stack_bwd_layers = 0;
@@ -1802,7 +1802,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
           const int rs = h->R + (b.has_skip ? h->S : 0), koff = d.dxo ? 0 : h->R;
           d.Wdg = b.Wdg16 + koff; d.k_dg = rup(rs, 64);
           d.Wb = cv.Wb16; d.k_b = rup(cv.Kb16, 64);
-          d.ident = (c.use_residual && d.dxo) ? b.Wres16 + h->D : nullptr; d.ld_ident = h->D + h->R;
+          d.has_res = c.use_residual ? 1 : 0;
           return d;
         };
         TcStackBwdPlan* sp = nullptr;
