@@ -164,9 +164,12 @@ def _conv(x, W, b, d):
   return out + b
 
 
-def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding, tap=None, slope_masks=None):
+def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding, tap=None, slope_masks=None, keep_masks=None):
   """x (B,T,1) -> logits (B,T,C).  tap: optional dict that receives the intermediate tensors the kernels store
-  ('h0', ('z', l), ('g', l), ('xout', l), 'skipsum', ('hact', i), 'logits'), each with retain_grad()."""
+  ('h0', ('z', l), ('g', l), ('xout', l), 'skipsum', ('hact', i), 'logits'), each with retain_grad().
+  keep_masks: per-block dropout keep-masks (B,T,R) of a training pass (layers.py:195-196: the conv branch sees
+  keep * x / (1 - rate), the residual is taken before it, layers.py:192-193); the kernels store that masked input in bf16 (it is
+  the operand of the gated conv and of its weight gradient) and keep its gradient in the fp32 accumulator."""
   def keep(key, t):
     if tap is not None:
       t.retain_grad()
@@ -190,6 +193,8 @@ def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding, tap=None, slope_m
     res = h
     act = cfg.activation if len(dils) > 1 else None
     a = h
+    if keep_masks is not None and cfg.dropout > 0:
+      a = R.fwd(h * torch.as_tensor(np.asarray(keep_masks[b]), dtype=h.dtype) / (1.0 - cfg.dropout))
     for j, d in enumerate(dils[:-1]):
       a = keep(('act', b, j), R.act(_conv(a, q(f'block{b}/dil{j}/kernel'), p[f'block{b}/dil{j}/bias'], d), act, mask(('act', b, j))))
     j = len(dils) - 1
@@ -218,7 +223,8 @@ def forward_logits(p, cfg: wo.Config, x, cond_in, R: Rounding, tap=None, slope_m
   return h
 
 
-def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, faithful=True, threads=None, tap=None, slope_masks=None):
+def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, faithful=True, threads=None, tap=None, slope_masks=None,
+               keep_masks=None):
   """WaveNet.train_step up to the gradients (model.py:309-335).  Returns (loss, grads dict).
   slope_masks: {('hact', i) | ('act', block, j): bool (B,T,C)} — see Rounding.act."""
   if threads:
@@ -228,7 +234,7 @@ def train_step(p_np, cfg: wo.Config, x_frames, cond_in=None, n_replicas=1, faith
   p = {k: torch.tensor(np.asarray(v), dtype=dt, requires_grad=True) for k, v in p_np.items()}
   x = torch.tensor(np.asarray(x_frames), dtype=dt)
   c = None if cond_in is None else torch.tensor(np.asarray(cond_in), dtype=dt)
-  logits = forward_logits(p, cfg, x[:, :-1, :], c, R, tap, slope_masks)
+  logits = forward_logits(p, cfg, x[:, :-1, :], c, R, tap, slope_masks, keep_masks)
   if faithful:
     logits = logits.to(torch.float32).to(dt)      # the logits live in fp32
   loss = torch_ref.loss_per_sample(cfg, logits, x[:, 1:, :]).sum() / (x.shape[0] * n_replicas)

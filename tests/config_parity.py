@@ -21,9 +21,10 @@ SHAPES = {
 }
 
 
-def setup(name):
+def setup(name, dropout=0.0):
   from wavenets_b200 import CONFIGS, WaveNet, model_kwargs, synth
   cfg = dict(CONFIGS[name])
+  cfg['dropout'] = dropout
   kw = model_kwargs(cfg)
   B, T, want_stack, want_group = SHAPES[name]
   cond_in = cfg.get('n_speakers', 109) if kw['conditioning'] == 'global' else 0
@@ -56,10 +57,17 @@ def errors(g, ref):
   return sorted(out, reverse=True)
 
 
-def run(name):
-  m, ocfg, p, x, cond, precision, want_stack, want_group, kw = setup(name)
+def run(name, dropout=0.0):
+  """dropout > 0: a TRAINING pass with injected keep-masks (TF's RNG stream cannot be reproduced): the same masks go to the oracle"""
+  m, ocfg, p, x, cond, precision, want_stack, want_group, kw = setup(name, dropout)
   data = (x, cond) if cond is not None else x
   h = m.handle
+  keep = None
+  if dropout > 0:
+    B, T = SHAPES[name][:2]
+    rng = np.random.default_rng(17)
+    keep = [(rng.random((B, T, kw['channels'])) >= dropout).astype(np.uint8) for _ in range(kw['blocks'])]
+    m.set_dropout_masks(keep)
   # three steps: eager; plans built -> side launches; CUDA-graph replay.  The third is the one compared.
   for _ in range(3):
     out = m.train_step(data)
@@ -68,14 +76,14 @@ def run(name):
   res = {'config': name, 'precision': precision, 'loss': out['loss'], 'stack_layers': int(h.lib.wn_stack_forward_layers(h.h)),
          'grouped_tiles': int(h.lib.wn_grouped_wgrad_tiles(h.h, C.byref(side))), 'side_launches': side.value, 'blocks': m.blocks,
          'want_stack': want_stack, 'want_group': want_group, 'stack_bwd_layers': int(h.lib.wn_stack_backward_layers(h.h)), 'build': h.lib.wn_build_info().decode()}
-  l64, g64 = faithful.train_step(p, ocfg, x, cond, faithful=False)
+  l64, g64 = faithful.train_step(p, ocfg, x, cond, faithful=False, keep_masks=keep)
   e64 = errors(g, g64)
   res.update(loss_fp64=l64, worst_fp64=e64[0][0], worst_fp64_tensor=e64[0][1], top_fp64=e64[:6])
   if precision != 'fp32':
     # (the derivative masks of relu / leaky_relu come from the device: tests/util.py:device_slope_masks)
     B, T = SHAPES[name][:2]
     masks = device_slope_masks(m, kw, B, T)
-    lf, gf = faithful.train_step(p, ocfg, x, cond, faithful=True, slope_masks=masks)
+    lf, gf = faithful.train_step(p, ocfg, x, cond, faithful=True, slope_masks=masks, keep_masks=keep)
     ef = errors(g, gf)
     res['slope_mask_sites'] = 0 if not masks else len(masks)
     glob = float(np.sqrt(sum(np.sum((g[k].astype(np.float64) - gf[k]) ** 2) for k in gf) / sum(np.sum(gf[k] ** 2) for k in gf)))
@@ -85,4 +93,4 @@ def run(name):
 
 
 if __name__ == '__main__':
-  print(json.dumps(run(sys.argv[1])))
+  print(json.dumps(run(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 0.0)))

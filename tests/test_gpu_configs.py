@@ -38,6 +38,8 @@ TOL_FP32 = 1e-4
 TOL_LOSS_BF16, TOL_GRAD_BF16 = 1e-2, 6e-2              # shipped library vs float64: stated bf16 tolerance
 TOL_LOSS_FAITHFUL = 5e-5                               # vs the bf16-faithful oracle: loss
 TOL_GRAD_FAITHFUL, TOL_GLOBAL_FAITHFUL = 8e-3, 4e-3    # worst gradient tensor / all gradients together (measured: <= 4.7e-3 / 2.1e-3)
+TOL_GRAD_FAITHFUL_DROPOUT, TOL_GLOBAL_FAITHFUL_DROPOUT = 1.2e-2, 5e-3   # training pass with dropout 0.1: every block's masked, 1/(1-p)-scaled input
+                                                                        # is one more bf16 rounding of x_out (measured C2 4.4e-3 / 2.4e-3, C5's 40 blocks 8.1e-3 / 3.5e-3)
 TOL_GRAD_PRECISE, TOL_GLOBAL_PRECISE = 8e-3, 4e-3      # precise flavour (measured on C2: 3.4e-3 / 1.6e-3, shipped 3.3e-3 / 1.7e-3)
 
 
@@ -62,6 +64,23 @@ def test_config_topology_vs_oracle(name):
   assert abs(r['loss'] - r['loss_faithful']) <= TOL_LOSS_FAITHFUL * abs(r['loss_faithful']), r
   assert r['worst_faithful'] <= TOL_GRAD_FAITHFUL, r
   assert r['global_faithful'] <= TOL_GLOBAL_FAITHFUL, r
+
+
+@pytest.mark.parametrize('name', ['c2', 'c5'])
+def test_config_topology_training_pass_with_dropout(name):
+  """defaults.yaml:17 / train.py:22-50 train with dropout 0.1 (layers.py:109-112,192-196).  The keep-masks are applied INSIDE the
+  persistent stack launches (forward: the epilogue that produces x_out also writes the next block's masked conv-branch input;
+  backward: the OUT epilogue masks the branch gradient before adding the residual gradient), so both stay on the checked path;
+  masks injected (TF's RNG stream cannot be reproduced), the same masks in the oracle."""
+  r = config_parity.run(name, dropout=0.1)
+  print(json.dumps(r))
+  _check_paths(r)
+  assert r['stack_bwd_layers'] == r['blocks'], 'the persistent stack-backward launch must be on the checked path'
+  assert abs(r['loss'] - r['loss_fp64']) <= TOL_LOSS_BF16 * abs(r['loss_fp64']), r
+  assert r['worst_fp64'] <= TOL_GRAD_BF16, r
+  assert abs(r['loss'] - r['loss_faithful']) <= TOL_LOSS_FAITHFUL * abs(r['loss_faithful']), r
+  assert r['worst_faithful'] <= TOL_GRAD_FAITHFUL_DROPOUT, r
+  assert r['global_faithful'] <= TOL_GLOBAL_FAITHFUL_DROPOUT, r
 
 
 @pytest.mark.parametrize('name', ['c2'])

@@ -41,6 +41,7 @@ struct TcBlockParams {
   int Cin, D, R, has_res;
   const float* bias_g; const float* cbias; const float* bias_r;   // [2D], [B][2D] or null, [R]
   unsigned long long pol_a, pol_w, pol_z, pol_g, pol_o;
+  float drop_scale;              // 1 / (1 - rate) of the inverted dropout (stack forward with dropout only)
 };
 
 template <int D_, int R_> struct TcBlockCfg {
@@ -414,6 +415,9 @@ struct TcBlockDesc {
   const bf16* W2;                    // [R][D + R] = [Wr^T | I]
   bf16* z; bf16* g; bf16* xout;      // (B,T,2D), (B,T,D), (B,T,R)
   const float* bias_g; const float* cbias; const float* bias_r;
+  // training-mode dropout of the NEXT block's conv branch (layers.py:195-196), applied where x_out is produced (stack forward
+  // only): keep-mask bytes [b*T+t][R] of the next block, its masked-and-scaled input (B,T,R), 1 / (1 - rate); null / 0 = off
+  const uint8_t* mask_next; bf16* xdrop_next; float drop_scale;
 };
 
 // SW128 tile map over a (B,T,ld) tensor for 64-channel x 128-row boxes (TMA store of the g operand slabs)

@@ -14,9 +14,10 @@
 #include "gemm_tc_block.cuh"
 
 struct alignas(128) TcStackLayer {
-  CUtensorMap tmA, tmX, tmW1, tmW2, tmZf, tmZs, tmG, tmO;
+  CUtensorMap tmA, tmX, tmW1, tmW2, tmZf, tmZs, tmG, tmO, tmOd;
   int shift[TC_MAX_SEG];
   const float* bias_g; const float* cbias; const float* bias_r;
+  const uint8_t* mask_next;      // dropout keep-mask of the next block's conv branch, or null (tmOd: its masked input)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -235,7 +236,8 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
           __syncwarp();
         }
       } else {
-        for (int step = 0; step < R_ / 32; ++step) step_store(&Ly.tmO, nullptr, step * 32, t0, b, p.pol_o);
+        // (with dropout: second panel = the next block's conv-branch input keep * x_out / (1 - rate), layers.py:195-196)
+        for (int step = 0; step < R_ / 32; ++step) step_store(&Ly.tmO, Ly.mask_next ? &Ly.tmOd : nullptr, step * 32, t0, b, p.pol_o);
         // this CTA's 128 rows of x_out are the next layer's operand: published behind the NEXT tile's stores (below), so
         // that the store warp never waits for a write to land while the epilogue warps are filling the output slots
         if (ly + 1 < L) pend_flag = ly * p.num_mtiles + mt;
@@ -361,6 +363,12 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             float in[1][16];
             float out[1][16];
             TcEpiBiasActRes<true>::chunk(po, acc, bsafe, step * 32 + q * 16, 0, 0, 0u, in, out, bs);
+            uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+            if (Ly.mask_next) {
+              const int tt = (mt % p.tiles_t) * (2 * Cfg::BM) + pair_row0 + row;
+              if (tt < p.T && b < p.B)
+                mk = __ldg(reinterpret_cast<const uint4*>(Ly.mask_next + ((size_t)b * p.T + tt) * R_ + step * 32 + q * 16));
+            }
             uint8_t* ob = out_ring + oslot * Cfg::SLOT_PANELS * Cfg::PANEL;
             mbar_wait(&out_empty[oslot], ophase ^ 1);
             uint4 a, c;
@@ -370,6 +378,21 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             c.z = pack_bf16x2(out[0][12], out[0][13]); c.w = pack_bf16x2(out[0][14], out[0][15]);
             *reinterpret_cast<uint4*>(ob + off0) = a;
             *reinterpret_cast<uint4*>(ob + off1) = c;
+            if (Ly.mask_next) {
+              // keep * (the bf16 value just stored) / (1 - rate), rounded once more: what dropout_apply makes of x_out
+              const uint32_t xw[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+              const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+              uint32_t dw[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t k0 = (mw[i >> 1] >> (16 * (i & 1))) & 0xffu, k1 = (mw[i >> 1] >> (16 * (i & 1) + 8)) & 0xffu;
+                const float v0 = k0 ? __uint_as_float(xw[i] << 16) * p.drop_scale : 0.f;
+                const float v1 = k1 ? __uint_as_float(xw[i] & 0xffff0000u) * p.drop_scale : 0.f;
+                dw[i] = pack_bf16x2(v0, v1);
+              }
+              *reinterpret_cast<uint4*>(ob + Cfg::PANEL + off0) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+              *reinterpret_cast<uint4*>(ob + Cfg::PANEL + off1) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+            }
             fence_proxy_async();
             named_bar_arrive(3 + oslot, NEPI * 32 + 32);
             if (++oslot == Cfg::OUT_SLOTS) { oslot = 0; ophase ^= 1; }
@@ -390,7 +413,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
 
 
 struct TcStackPlan {
-  int B = 0, T = 0, L = 0, num_mtiles = 0; bool cb = false;
+  int B = 0, T = 0, L = 0, num_mtiles = 0; bool cb = false, drop = false;
   TcStackLayer* d_layers = nullptr; int* d_flags = nullptr;
   void release() { cudaFree(d_layers); cudaFree(d_flags); d_layers = nullptr; d_flags = nullptr; }
 };
@@ -416,13 +439,20 @@ static int tc_stack_build_t(TmapCache& tc, const std::vector<TcBlockDesc>& descs
     const CUtensorMap* mG = tc_slab_map(tc, d.g, d.D, d.D, d.T, d.B);
     if (!mA || !mX || !mW1 || !mW2 || !mZf || !mZs || !mO || !mG) return -10;
     TcStackLayer& t = tab[l];
-    t.tmA = *mA; t.tmX = *mX; t.tmW1 = *mW1; t.tmW2 = *mW2; t.tmZf = *mZf; t.tmZs = *mZs; t.tmG = *mG; t.tmO = *mO;
+    memset(&t, 0, sizeof(t));
+    t.tmA = *mA; t.tmX = *mX; t.tmW1 = *mW1; t.tmW2 = *mW2; t.tmZf = *mZf; t.tmZs = *mZs; t.tmG = *mG; t.tmO = *mO; t.tmOd = *mO;
+    if (d.mask_next && d.xdrop_next) {
+      const TcEpiIo xd{d.xdrop_next, d.R, d.R, 0};
+      const CUtensorMap* mOd = tc_panel_map(tc, xd, d.T, d.B);
+      if (!mOd) return -10;
+      t.tmOd = *mOd; t.mask_next = d.mask_next;
+    }
     for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
     t.bias_g = d.bias_g; t.cbias = d.cbias; t.bias_r = d.bias_r;
   }
   const TcBlockDesc& d0 = descs[0];
   plan->release();
-  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->cb = d0.cbias != nullptr;
+  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->cb = d0.cbias != nullptr; plan->drop = d0.mask_next != nullptr;
   if (cudaMalloc((void**)&plan->d_layers, tab.size() * sizeof(TcStackLayer)) != cudaSuccess ||
       cudaMemcpy(plan->d_layers, tab.data(), tab.size() * sizeof(TcStackLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMalloc((void**)&plan->d_flags, (size_t)plan->L * plan->num_mtiles * sizeof(int)) != cudaSuccess) {
@@ -442,7 +472,7 @@ static int tc_stack_launch_t(cudaStream_t st, const TcStackPlan& plan, const TcB
   TcBlockParams p{};
   p.B = d0.B; p.T = d0.T; p.tiles_t = (d0.T + 255) / 256; p.num_mtiles = d0.B * p.tiles_t;
   p.nseg = d0.nseg;
-  p.Cin = d0.Cin; p.D = d0.D; p.R = d0.R; p.has_res = d0.has_res;
+  p.Cin = d0.Cin; p.D = d0.D; p.R = d0.R; p.has_res = d0.has_res; p.drop_scale = d0.drop_scale;
   p.pol_a = tc_policy(TC_L2_NORMAL); p.pol_w = tc_policy(TC_L2_LAST);
   p.pol_z = tc_policy(TC_L2_FIRST); p.pol_g = tc_policy(TC_L2_FIRST); p.pol_o = tc_policy(TC_L2_LAST);
   auto kern = tc_stack_fwd_kernel<D_, R_>;

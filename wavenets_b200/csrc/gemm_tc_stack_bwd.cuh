@@ -45,6 +45,7 @@ struct alignas(128) TcStackBwdLayer {
   int shift[TC_MAX_SEG];      // row shift of tap k (k < nseg - 1: positive; tap nseg - 1: 0)
   int has_dx, has_ds, has_res;
   int wait_dx;                // d x_out_l is written by this launch (every block but the last): acquire its tile flag first
+  const uint8_t* mask;        // dropout keep-mask of this block's conv branch [b*T+t][R], or null
 };
 
 struct TcStackBwdParams {
@@ -52,6 +53,7 @@ struct TcStackBwdParams {
   int nseg;                   // taps of the gated conv
   int kb_dx, kb_ds;           // 64-wide k blocks of the DG contraction over d x_out (R) and d skip (S)
   unsigned long long pol_dx, pol_ds, pol_w, pol_z, pol_dz_ld, pol_dz_st, pol_o;
+  float drop_scale;           // 1 / (1 - rate)
 };
 
 template <int D_, int R_> struct TcStackBwdCfg {
@@ -403,10 +405,13 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
       bool add_res;
+      const uint8_t* mrow = nullptr;       // this row's keep-mask bytes (dropout on the conv branch this tile differentiates)
       {
         int ly, mt, b, tb;
         locate(j, ly, mt, b, tb);
         add_res = layers[ly].has_dx != 0 && layers[ly].has_res != 0;
+        const int tt = tb * (2 * Cfg::BM) + pair_row0 + row;
+        if (layers[ly].mask && tt < p.T && b < p.B) mrow = layers[ly].mask + ((size_t)b * p.T + tt) * R_;
       }
       // ---- DG epilogue: d z = d g * [P | Q] -> operand buffer
       SBT(0)
@@ -488,6 +493,13 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         for (int step = 0; step < R_ / 32; ++step) {
           float v[16];
           acc.load16(step * 32 + q * 16, v);
+          if (mrow) {
+            // adjoint of the inverted dropout (layers.py:195-196): the conv branch saw keep * x / (1 - rate)
+            const uint4 mk = __ldg(reinterpret_cast<const uint4*>(mrow + step * 32 + q * 16));
+            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) ? v[i] * p.drop_scale : 0.f;
+          }
           if (add_res) {
             mbar_wait(&in_full[islot], iphase);
             const uint8_t* ib = in_ring + islot * 2 * Cfg::PANEL;
@@ -545,10 +557,11 @@ struct TcStackBwdDesc {       // one block
   const bf16* Wdg; int k_dg;  // [D][k_dg] = [Wr^T | Ws^T] rows (first k = R, or S when dxo == null and the pointer is offset)
   const bf16* Wb; int k_b;    // [R][k_b]: dgrad operand of the gated conv, contraction (tap, 2D)
   int has_res;                // use_residual: d x_out_{l-1} += d x_out_l
+  const uint8_t* mask; float drop_scale;    // dropout on this block's conv branch (null / 0 = off)
 };
 
 struct TcStackBwdPlan {
-  int B = 0, T = 0, L = 0, num_mtiles = 0;
+  int B = 0, T = 0, L = 0, num_mtiles = 0; bool drop = false;
   TcStackBwdLayer* d_layers = nullptr; int* d_flags = nullptr;
   void release() { cudaFree(d_layers); cudaFree(d_flags); d_layers = nullptr; d_flags = nullptr; }
 };
@@ -589,10 +602,11 @@ static int tc_stack_bwd_build_t(TmapCache& tc, const std::vector<TcStackBwdDesc>
     for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
     t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = (d.has_res && d.dxo != nullptr) ? 1 : 0;
     t.wait_dx = (d.dxo != nullptr && l + 1 < descs.size()) ? 1 : 0;
+    t.mask = d.mask;
   }
   const TcStackBwdDesc& d0 = descs[0];
   plan->release();
-  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256);
+  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->drop = d0.mask != nullptr;
   if (cudaMalloc((void**)&plan->d_layers, tab.size() * sizeof(TcStackBwdLayer)) != cudaSuccess ||
       cudaMemcpy(plan->d_layers, tab.data(), tab.size() * sizeof(TcStackBwdLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMalloc((void**)&plan->d_flags, (size_t)2 * plan->L * plan->num_mtiles * sizeof(int)) != cudaSuccess) {
@@ -608,7 +622,7 @@ static int tc_stack_bwd_launch_t(cudaStream_t st, const TcStackBwdPlan& plan, co
   using Cfg = TcStackBwdCfg<D_, R_>;
   TcStackBwdParams p{};
   p.B = d0.B; p.T = d0.T; p.tiles_t = (d0.T + 255) / 256; p.num_mtiles = d0.B * p.tiles_t; p.L = plan.L;
-  p.nseg = d0.nseg; p.kb_dx = d0.R / 64; p.kb_ds = d0.S / 64;
+  p.nseg = d0.nseg; p.kb_dx = d0.R / 64; p.kb_ds = d0.S / 64; p.drop_scale = d0.drop_scale;
   p.pol_dx = tc_policy(TC_L2_NORMAL); p.pol_ds = tc_policy(TC_L2_LAST); p.pol_w = tc_policy(TC_L2_LAST); p.pol_z = tc_policy(TC_L2_FIRST);
   p.pol_dz_ld = tc_policy(TC_L2_NORMAL); p.pol_dz_st = tc_policy(TC_L2_LAST); p.pol_o = tc_policy(TC_L2_LAST);
   auto kern = tc_stack_bwd_kernel<D_, R_>;

@@ -1228,7 +1228,7 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   if constexpr (sizeof(T) == 2) {
     // the whole residual stack as ONE persistent launch (gemm_tc_stack.cuh) when every block takes the fused forward
     // and a layer has more 256-row tiles than the GPU has CTA pairs
-    bool ok = h->use_stack_fwd && h->use_fused_fwd && tc_cta_group() == 2 && !h->drop_active && c.use_residual && h->L >= 2 && h->D == h->R &&
+    bool ok = h->use_stack_fwd && h->use_fused_fwd && tc_cta_group() == 2 && c.use_residual && h->L >= 2 && h->D == h->R &&
               (h->D == 256 || h->D == 128) && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!ok) break;
@@ -1250,10 +1250,17 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
         d.z = (bf16*)h->zbuf[l]; d.g = (bf16*)h->G_all + (size_t)l * rows_cap * h->D; d.xout = (bf16*)h->xout[l];
         d.bias_g = P_(h, cv.b_idx); d.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
         d.bias_r = P_(h, b.conv1.b_idx);
+        if (h->drop_active) {
+          // training-mode dropout without leaving the launch: the conv branch of block l reads xdrop[l] = keep_l * x / (1 - rate),
+          // written by the OUT epilogue of block l-1 next to x_out (block 0: by dropout_apply on h0 below); the residual reads x
+          d.A = (const bf16*)h->xdrop[l];
+          d.drop_scale = 1.0f / (1.0f - c.dropout);
+          if (l + 1 < h->L) { d.mask_next = h->drop_mask + (size_t)(l + 1) * rows_cap * h->R; d.xdrop_next = (bf16*)h->xdrop[l + 1]; }
+        }
         return d;
       };
       TcStackPlan* sp = nullptr;
-      for (auto& q : h->stack_plans) if (q.B == B && q.T == Tn && q.cb == has_cb) sp = &q;
+      for (auto& q : h->stack_plans) if (q.B == B && q.T == Tn && q.cb == has_cb && q.drop == (h->drop_active && h->L > 1)) sp = &q;
       int r = 0;
       if (!sp) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1272,6 +1279,12 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
           r = tc_stack_build(h->tmaps, descs, &h->stack_plans.back());
           if (r == 0) sp = &h->stack_plans.back(); else h->stack_plans.pop_back();
         }
+      }
+      if (sp && h->drop_active) {
+        // block 0's masked input from the input conv's output (every later block's comes out of the launch itself)
+        LaunchScope ls(h, st, CLS_MISC);
+        const long long n = (long long)B * Tn * h->R;
+        dropout_apply<bf16><<<cdiv(n, 256), 256, 0, st>>>((const bf16*)h->h0, h->drop_mask, (bf16*)h->xdrop[0], n, 1.0f / (1.0f - c.dropout));
       }
       if (sp) {
         struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_fwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
@@ -1692,7 +1705,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   // whole chain, so the weight gradients all run in the one grouped launch behind it (no side launches).
   bool sb_ok = false;
   if constexpr (sizeof(T) == 2) {
-    sb_ok = group && !cat && h->use_stack_bwd && tc_cta_group() == 2 && !h->drop_active && h->L >= 2 && h->D == h->R && (h->D == 256 || h->D == 128) &&
+    sb_ok = group && !cat && h->use_stack_bwd && tc_cta_group() == 2 && h->L >= 2 && h->D == h->R && (h->D == 256 || h->D == 128) &&
             !(h->alias_skip && c.use_skip) && h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!sb_ok) break;
@@ -1803,10 +1816,11 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
           d.Wdg = b.Wdg16 + koff; d.k_dg = rup(rs, 64);
           d.Wb = cv.Wb16; d.k_b = rup(cv.Kb16, 64);
           d.has_res = c.use_residual ? 1 : 0;
+          if (h->drop_active) { d.mask = h->drop_mask + (size_t)l * rows_cap * h->R; d.drop_scale = 1.0f / (1.0f - c.dropout); }
           return d;
         };
         TcStackBwdPlan* sp = nullptr;
-        for (auto& q : h->stack_bwd_plans) if (q.B == B && q.T == Tn) sp = &q;
+        for (auto& q : h->stack_bwd_plans) if (q.B == B && q.T == Tn && q.drop == h->drop_active) sp = &q;
         int r = 0;
         if (!sp) {
           cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
