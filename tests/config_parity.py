@@ -15,7 +15,7 @@ from tests.util import device_slope_masks, oracle_config, rel_l2
 SHAPES = {
   'c1': (1, 8000, False, False),      # BASELINE configs[0] exactly: defaults.yaml topology, batch 1, fp32
   'c2': (3, 6400, True, True),
-  'c3': (3, 2048, False, True),
+  'c3': (3, 6400, True, True),        # 5 x 5 dilations per block: 20 plain convs + 5 gated convs in the one stack-forward launch
   'c4': (3, 6400, True, True),
   'c5': (3, 6400, True, True),
 }

@@ -128,6 +128,20 @@ def test_stack_backward_vs_per_block_chain():
   print(f'stack backward vs per-block chain (6 blocks): worst gradient tensor rel-L2 {worst:.2e}')
 
 
+def test_stack_forward_multi_dilation_equals_per_block_launches():
+  """Blocks with several dilated convs (layers.py:64-88): the convs in front of the gated conv run as PLAIN layers of the same
+  persistent launch (one 256 x 256 tile per m tile, bias + activation epilogue, tile flags towards the next conv).  Same tile
+  arithmetic as the separate conv launches: loss and gradients bit-equal."""
+  kw = dict(channels=256, blocks=3, layers_per_block=3, dilation_bound=32, skip_channels=256, final_layers_channels=[128], activation='leaky_relu')
+  B, T = 3, 6500
+  a = _run(kw, B, T, True)
+  b = _run(kw, B, T, True, {'WN_TC_STACK_FWD': '0'})
+  for i in range(3):
+    assert a[i][0] == b[i][0]
+    for k in b[i][1]:
+      assert np.array_equal(a[i][1][k], b[i][1][k]), (k, i)
+
+
 def test_plan_cache_eviction_keeps_results():
   """More (B, T) shapes than the handle caches plans for (4): the grouped-wgrad / stack-forward plans and the CUDA graphs that
   hold pointers into them are dropped and rebuilt; every shape reproduces its first result bit for bit."""

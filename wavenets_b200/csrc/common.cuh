@@ -47,6 +47,24 @@ template <bool FAST> __device__ __forceinline__ float wn_act(int act, float x) {
     default: return x;
   }
 }
+// 16 values at once with ONE dispatch on the activation.  (A per-element `switch (act)` inside an unrolled loop compiles to a
+// branch chain per element: measured 21 k cycles per 256 x 256 epilogue tile of a leaky_relu conv in the stack-forward kernel
+// against 4 k for the same tile without activation — in-kernel clock64 accounting, profiles/r2.)
+template <bool FAST> __device__ __forceinline__ void wn_act16(int act, float* v) {
+  if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.0f ? v[i] : WN_LEAKY_SLOPE * v[i];
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (act == ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = wn_tanh<FAST>(v[i]);
+  } else if (act == ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = wn_sigmoid<FAST>(v[i]);
+  }
+}
 // derivative expressed through the activation OUTPUT y
 __device__ __forceinline__ float wn_act_grad_from_out(int act, float y) {
   switch (act) {
@@ -55,6 +73,22 @@ __device__ __forceinline__ float wn_act_grad_from_out(int act, float y) {
     case ACT_TANH: return 1.0f - y * y;
     case ACT_SIGMOID: return y * (1.0f - y);
     default: return 1.0f;
+  }
+}
+// v[i] *= act'(y[i]) for 16 values, one dispatch (see wn_act16)
+__device__ __forceinline__ void wn_act_grad16(int act, const float* y, float* v) {
+  if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = y[i] >= 0.0f ? v[i] : WN_LEAKY_SLOPE * v[i];
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = y[i] > 0.0f ? v[i] : 0.0f;
+  } else if (act == ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= 1.0f - y[i] * y[i];
+  } else if (act == ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= y[i] * (1.0f - y[i]);
   }
 }
 

@@ -44,8 +44,7 @@ template <class T, class TO, bool FAST> struct EpiBiasActRes {
         for (int i = 0; i < 16; ++i) if (i < nv) v[i] += cb[i];
       }
       if (p.act != ACT_LINEAR) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = wn_act<FAST>(p.act, v[i]);
+        wn_act16<FAST>(p.act, v);
       }
       if (p.res) {
         float r[16];
@@ -177,8 +176,7 @@ template <class T, class TO> struct EpiActBwd {
       if (p.y && p.act != ACT_LINEAR) {
         float y[16];
         load16<T>(p.y + grow * p.ldy + n, y, nv, p.vec);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= wn_act_grad_from_out(p.act, y[i]);
+        wn_act_grad16(p.act, y, v);
       }
       store16<TO>(p.out + grow * p.ldo + n, v, nv, p.vec);
     }

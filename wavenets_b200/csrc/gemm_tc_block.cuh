@@ -418,6 +418,9 @@ struct TcBlockDesc {
   // training-mode dropout of the NEXT block's conv branch (layers.py:195-196), applied where x_out is produced (stack forward
   // only): keep-mask bytes [b*T+t][R] of the next block, its masked-and-scaled input (B,T,R), 1 / (1 - rate); null / 0 = off
   const uint8_t* mask_next; bf16* xdrop_next; float drop_scale;
+  // stack forward only: plain != 0 describes a conv IN FRONT of the gated conv of a multi-dilation block (layers.py:64-74):
+  // xout = act(A taps . W1^T + bias_g), W1 [D][nseg*Cin]; X, W2, z, g, cbias, bias_r unused
+  int plain, act;
 };
 
 // SW128 tile map over a (B,T,ld) tensor for 64-channel x 128-row boxes (TMA store of the g operand slabs)

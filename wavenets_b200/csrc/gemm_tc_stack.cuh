@@ -10,14 +10,72 @@
 // Dependencies point to smaller ids and every pair walks its ids in ascending order with all CTAs resident (grid <= SMs,
 // 1 CTA per SM), so the wait graph has no cycle as long as a layer has more m tiles than the launch has pairs (the
 // pipelined order issues G_0 of a pair's NEXT tile before OUT of its current one: that next tile must not depend on it).
+//
+// Multiple dilations per block (layers.py:64-88,199-200; the reference's shipped topology is 5 blocks x 5): a "layer" of the
+// launch is one CONV of the model.  The convs in front of a block's gated conv (Conv1D + bias + activation) are PLAIN layers:
+// one 256 x 256 tile per m tile (same operand loads as a gate tile of the kind-0 half, K = taps * Cin), whose epilogue
+// applies bias and activation and stores the bf16 output for the next conv (and for the backward pass).  The block's last
+// conv is the GATED layer as before; its residual operand X is the BLOCK input (the previous block's x_out), its A operand
+// the previous conv's output.  flags[layer][m] therefore count conv outputs, of either kind.
 #pragma once
 #include "gemm_tc_block.cuh"
 
+// in-kernel phase accounting (clock64 sums over all tiles of one CTA, printed by a few CTAs): -DTC_TIMELINE builds only
+#ifdef TC_TIMELINE
+#define SFT_DECL(n) long long sft[n] = {}; long long sft_prev = clock64();
+#define SFT(i) { const long long sft_now = clock64(); sft[i] += sft_now - sft_prev; sft_prev = sft_now; }
+#else
+#define SFT_DECL(n)
+#define SFT(i)
+#endif
+
+#define TC_STACK_MAX_LAYERS 256
 struct alignas(128) TcStackLayer {
   CUtensorMap tmA, tmX, tmW1, tmW2, tmZf, tmZs, tmG, tmO, tmOd;
   int shift[TC_MAX_SEG];
   const float* bias_g; const float* cbias; const float* bias_r;
   const uint8_t* mask_next;      // dropout keep-mask of the next block's conv branch, or null (tmOd: its masked input)
+  int kind;                      // 0: gated conv + gate + conv1 (+ residual) = block tail; 1: plain conv + bias + activation
+  int act;                       // activation of a plain layer (ACT_*)
+};
+
+// Sub-tile sequence of one CTA pair over its (layer, m tile) list t_0 .. t_{n-1}: first(t_0), rest(t_0), then for every j:
+// first(t_{j+1}), OUT(t_j), rest(t_{j+1}).  first = gate sub-tile 0 or the PLAIN tile; rest = gate sub-tiles 1..NT1-1; OUT only
+// for gated tiles.  (All gated: the order of gemm_tc_block.cuh's blk_tile.)  kind < NT1: gate sub-tile; NT1: OUT; NT1 + 1: PLAIN.
+// kmask: one bit per layer (1 = plain), in shared memory (the sequence is walked by four roles on their critical paths: no
+// global loads here)
+template <int NT1> struct TcStackSeq {
+  const uint32_t* kmask; int n, tile_first, tile_stride, num_mtiles;
+  int j, ph, r;
+  __device__ __forceinline__ TcStackSeq(const uint32_t* km, int n_, int tf, int ts, int nm) : kmask(km), n(n_), tile_first(tf), tile_stride(ts), num_mtiles(nm), j(0), ph(0), r(1) {}
+  __device__ __forceinline__ bool plain(int jj) const {
+    const int ly = (tile_first + jj * tile_stride) / num_mtiles;
+    return ((kmask[ly >> 5] >> (ly & 31)) & 1u) != 0u;
+  }
+  __device__ __forceinline__ bool next(int& kind, int& jj) {
+    for (;;) {
+      switch (ph) {
+        case 0:
+          if (n <= 0) return false;
+          ph = 1; r = 1; kind = plain(0) ? NT1 + 1 : 0; jj = 0; return true;
+        case 1:
+          if (!plain(0) && r < NT1) { kind = r++; jj = 0; return true; }
+          ph = 2; j = 0; break;
+        case 2:
+          ph = 3;
+          if (j + 1 < n) { kind = plain(j + 1) ? NT1 + 1 : 0; jj = j + 1; return true; }
+          break;
+        case 3:
+          ph = 4; r = 1;
+          if (!plain(j)) { kind = NT1; jj = j; return true; }
+          break;
+        default:
+          if (j + 1 < n && !plain(j + 1) && r < NT1) { kind = r++; jj = j + 1; return true; }
+          if (++j >= n) return false;
+          ph = 2; break;
+      }
+    }
+  }
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -54,6 +112,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
   uint64_t* g_cons = g_free + 1;                     // [2] local: OUT has consumed the slabs written by gate tile h
   uint32_t* tmem_ptr = (uint32_t*)(g_cons + 2);
   float* bias_s = (float*)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);
+  uint32_t* kmask = (uint32_t*)(bias_s + 512);       // [TC_STACK_MAX_LAYERS / 32] layer kinds, behind the two bias tables
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -63,7 +122,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
   const int kb_a = p.Cin / 64;                        // k-blocks per tap of the gated conv
   const int total_tiles = L * p.num_mtiles;            // (layer, m tile) in layer-major order: dependencies always point to smaller ids
   const int n_mt = tile_first < total_tiles ? (total_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
-  const int n_pos = n_mt * (NT1 + 1);
+  constexpr int K_OUT = NT1, K_PLAIN = NT1 + 1;
 
   if (warp == 0 && lane == 0 && n_mt > 0) {
     const TcStackLayer& L0 = layers[tile_first / p.num_mtiles];
@@ -77,6 +136,13 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + TC_STACK_MAX_LAYERS / 32) {
+    // layer kinds (the table was written by the host when the plan was built, long before this launch)
+    const int w = (int)threadIdx.x - 128;
+    uint32_t m = 0u;
+    for (int l = w * 32; l < L && l < w * 32 + 32; ++l) if (layers[l].kind != 0) m |= 1u << (l & 31);
+    kmask[w] = m;
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -91,14 +157,17 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
       int stage = 0; uint32_t phase = 0;
       auto next = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1; } };
       constexpr int W2_BYTES = (R_ / 2) * 64 * 2;
-      for (int pos = 0; pos < n_pos; ++pos) {
-        int kind, j;
-        blk_tile<NT1>(pos, n_mt, kind, j);
+      TcStackSeq<NT1> seq(kmask, n_mt, tile_first, tile_stride, p.num_mtiles);
+      int kind, j;
+      SFT_DECL(4)
+      while (seq.next(kind, j)) {
         const int gt = tile_first + j * tile_stride, ly = gt / p.num_mtiles, mt = gt - ly * p.num_mtiles;
         const TcStackLayer& Ly = layers[ly];
         const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (2 * Cfg::BM) + pair_row0;
-        if (kind < NT1) {
-          if (kind == 0 && ly > 0) {
+        SFT(0)
+        if (kind != K_OUT) {
+          const int wrow = kind == K_PLAIN ? 0 : kind * Cfg::BN;      // first weight row (output column) of this sub-tile
+          if ((kind == 0 || kind == K_PLAIN) && ly > 0) {
             // the rows the taps (and the residual) read are x_out tiles of the previous layer, written by other CTA pairs
             // of this launch: wait for both CTAs of each of those tiles (ids are smaller than this tile's: no cycles)
             const int tb = mt % p.tiles_t, row0 = tb * (2 * Cfg::BM);
@@ -119,6 +188,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
               }
             }
             fence_proxy_async_global();
+            SFT(1)
           }
           int wk = 0;
           for (int s = 0; s < p.nseg; ++s) {
@@ -127,7 +197,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
               tma_load_4d_pair_h(sa, &Ly.tmA, &full_bar[stage], kb * 64, t0 + Ly.shift[s], b, 0, p.pol_a);
-              tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmW1, &full_bar[stage], wk + kb * 64, kind * Cfg::BN + (int)crank * (Cfg::BN / 2), p.pol_w);
+              tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmW1, &full_bar[stage], wk + kb * 64, wrow + (int)crank * (Cfg::BN / 2), p.pol_w);
               next();
             }
             wk += p.Cin;
@@ -153,6 +223,10 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
           }
         }
       }
+      SFT(0)
+#ifdef TC_TIMELINE
+      if (blockIdx.x == 0 || blockIdx.x == 41) printf("SFWD cta %d producer: tiles %d  ring+issue %lld  wait_flags %lld\n", blockIdx.x, n_mt, sft[0], sft[1]);
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -164,18 +238,23 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
       uint32_t gphase = 0;
       const int ksteps_g = p.nseg * kb_a;
       const int ksteps_o = KB_G + (p.has_res ? KB_X : 0);
-      for (int pos = 0; pos < n_pos; ++pos) {
+      TcStackSeq<NT1> seq(kmask, n_mt, tile_first, tile_stride, p.num_mtiles);
+      int kind, j;
+      SFT_DECL(8)
+      while (seq.next(kind, j)) {
         {
-          int kind, j;
-          blk_tile<NT1>(pos, n_mt, kind, j);
-          const bool is_out = kind == NT1;
+          const bool is_out = kind == K_OUT;
           const int ksteps = is_out ? ksteps_o : ksteps_g;
+          SFT(0)
           mbar_wait(&tempty_bar[as], aphase ^ 1);
+          SFT(1)
           if (is_out) { mbar_wait(g_full, gphase); gphase ^= 1; }     // both CTAs' g tiles are in shared memory
+          SFT(2)
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * Cfg::BN);
           for (int ks = 0; ks < ksteps; ++ks) {
             mbar_wait(&full_bar[stage], phase);
+            SFT(3)
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -196,10 +275,15 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
           if (++as == 2) { as = 0; aphase ^= 1; }
         }
       }
+#ifdef TC_TIMELINE
+      if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 40))
+        printf("SFWD cta %d mma: tiles %d  wait_tempty %lld  wait_g_full %lld  wait_full_bar %lld  issue+other %lld\n", blockIdx.x, n_mt, sft[1], sft[2], sft[3], sft[0]);
+#endif
     }
   } else if (warp == 2) {
     // ===================== TMA-store warp =====================
-    int oslot = 0, prev = -1, pend_flag = -1;
+    int oslot = 0, prev = -1, pend_flag = -1, pend_new = -1;
+    const bool delay_publish = p.num_mtiles > 2 * tile_stride;
     auto step_store = [&](const CUtensorMap* m0, const CUtensorMap* m1, int c0, int t0, int b, unsigned long long pol) {
       named_bar_sync(3 + oslot, NEPI * 32 + 32);
       if (lane == 0) {
@@ -213,13 +297,17 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
       __syncwarp();
       if (++oslot == Cfg::OUT_SLOTS) oslot = 0;
     };
-    for (int pos = 0; pos < n_pos; ++pos) {
-      int kind, j;
-      blk_tile<NT1>(pos, n_mt, kind, j);
+    TcStackSeq<NT1> seq(kmask, n_mt, tile_first, tile_stride, p.num_mtiles);
+    int kind, j;
+    while (seq.next(kind, j)) {
       const int gt = tile_first + j * tile_stride, ly = gt / p.num_mtiles, mt = gt - ly * p.num_mtiles;
       const TcStackLayer& Ly = layers[ly];
       const int b = mt / p.tiles_t, t0 = (mt % p.tiles_t) * (2 * Cfg::BM) + pair_row0;
-      if (kind < NT1) {
+      if (kind == K_PLAIN) {
+        // plain conv: 256 output channels, one panel per step; the tile is the next conv's operand
+        for (int step = 0; step < Cfg::BN / 32; ++step) step_store(&Ly.tmO, nullptr, step * 32, t0, b, p.pol_o);
+        if (ly + 1 < L) pend_new = ly * p.num_mtiles + mt;
+      } else if (kind < NT1) {
         for (int step = 0; step < Cfg::BN / 64; ++step) step_store(&Ly.tmZf, &Ly.tmZs, kind * (Cfg::BN / 2) + step * 32, t0, b, p.pol_z);
         if (kind == NT1 - 1) {
           // g: the whole 128 x D tile straight out of the operand buffer (same 128B-swizzled K-major slabs as a TMA box)
@@ -240,12 +328,26 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
         for (int step = 0; step < R_ / 32; ++step) step_store(&Ly.tmO, Ly.mask_next ? &Ly.tmOd : nullptr, step * 32, t0, b, p.pol_o);
         // this CTA's 128 rows of x_out are the next layer's operand: published behind the NEXT tile's stores (below), so
         // that the store warp never waits for a write to land while the epilogue warps are filling the output slots
-        if (ly + 1 < L) pend_flag = ly * p.num_mtiles + mt;
+        if (ly + 1 < L) pend_new = ly * p.num_mtiles + mt;
       }
-      if (kind < NT1 && pend_flag >= 0) {
-        // a gate tile commits at least BN/64 = 4 store groups: once at most 4 are pending, the OUT tile's have completed
+      if (pend_flag >= 0) {
+        // every sub-tile commits at least BN/64 = 4 store groups: once at most 4 are pending, the groups of the sub-tile
+        // before this one (the OUT / PLAIN tile whose flag is pending) have completed
         if (lane == 0) {
           bulk_wait_group<4>();
+          fence_proxy_async_global();
+          __threadfence();
+          red_release_gpu_add(flags + pend_flag, 1);
+        }
+        __syncwarp();
+      }
+      pend_flag = pend_new; pend_new = -1;
+      if (pend_flag >= 0 && !delay_publish) {
+        // The sub-tile behind this one may belong to this pair's tile id + 2 * stride (a plain tile has no second sub-tile),
+        // which reads layer - 1 tiles down to id + 2 * stride - num_mtiles: with num_mtiles <= 2 * stride that can be THIS
+        // tile, so its flag cannot wait for that sub-tile's stores
+        if (lane == 0) {
+          bulk_wait_group<0>();
           fence_proxy_async_global();
           __threadfence();
           red_release_gpu_add(flags + pend_flag, 1);
@@ -268,6 +370,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
     if (lane == 0) {
       uint32_t dphase = 0;
       for (int j = 0; j < n_mt; ++j) {
+        { const int ly = (tile_first + j * tile_stride) / p.num_mtiles; if ((kmask[ly >> 5] >> (ly & 31)) & 1u) continue; }     // plain convs produce no g
         mbar_wait(g_done, dphase); dphase ^= 1;
         if (leader) mbar_arrive(g_full);
         else mbar_arrive_remote(g_full, 0u);
@@ -286,23 +389,37 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
     const uint32_t grow = (uint32_t)row * 128u, gsw = (uint32_t)(row & 7);
     int as = 0; uint32_t aphase = 0;
     int oslot = 0; uint32_t ophase = 0;
+    int ng = 0, ng_j = -1;      // gated tiles of this CTA before tile ng_j (the g buffer hand-shakes count gated tiles only)
+    SFT_DECL(8)
 
-    for (int pos = 0; pos < n_pos; ++pos) {
-      int nt, j;
-      blk_tile<NT1>(pos, n_mt, nt, j);
+    TcStackSeq<NT1> seq(kmask, n_mt, tile_first, tile_stride, p.num_mtiles);
+    int nt, j;
+    while (seq.next(nt, j)) {
       const int gt = tile_first + j * tile_stride, ly = gt / p.num_mtiles, mt = gt - ly * p.num_mtiles;
       const TcStackLayer& Ly = layers[ly];
       const int b = mt / p.tiles_t;
       const int bsafe = b < p.B ? b : p.B - 1;
+      const bool is_plain = nt == K_PLAIN;
+      if (nt == 0) {
+        // first sub-tile of a gated tile: ng = number of gated tiles this CTA has started before it
+        if (ng_j >= 0) ++ng;
+        ng_j = j;
+      }
       const TcEpiGate<true>::Params pg{Ly.bias_g, Ly.cbias, D_};
-      const TcEpiBiasActRes<true>::Params po{Ly.bias_r, nullptr, 0, ACT_LINEAR, R_};
+      // OUT: conv1 bias, linear; PLAIN: the conv's own bias and activation (both 256 = BN columns wide)
+      const TcEpiBiasActRes<true>::Params po{is_plain ? Ly.bias_g : Ly.bias_r, nullptr, 0, is_plain ? Ly.act : ACT_LINEAR, is_plain ? Cfg::BN : R_};
       {
-        const bool is_out = nt == NT1;
+        const bool is_out = nt == K_OUT || is_plain;      // one-panel-per-step epilogue
         const int tid = (int)threadIdx.x - 128;
         float bias_reg = 0.f;
-        if (is_out) { if (tid < R_) bias_reg = TcEpiBiasActRes<true>::bias_load(po, bsafe, 0, R_, tid); }
+        if (is_out) { if (tid < po.N) bias_reg = TcEpiBiasActRes<true>::bias_load(po, bsafe, 0, po.N, tid); }
         else bias_reg = TcEpiGate<true>::bias_load(pg, bsafe, nt * (Cfg::BN / 2), Cfg::BN, tid);
+#ifdef TC_TIMELINE
+        const int wb = is_plain ? 7 : (nt == K_OUT ? 6 : 5);
+#endif
+        SFT(4)            // sequence + layer-table reads + bias loads of this sub-tile
         mbar_wait(&tfull_bar[as], aphase);
+        SFT(1)
         tc_fence_after();
         // table double-buffered by tile parity: a warp that runs ahead into the next tile must not overwrite entries
         // other warps still read (the epilogue warps only meet at this barrier, once per tile)
@@ -311,11 +428,13 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
         named_bar_sync(2, NEPI * 32);
         TmemAccRow acc{tmem_base + (uint32_t)(as * Cfg::BN) + ((uint32_t)(quarter * 32) << 16), true};
         if (!is_out) {
-          if (j > 0) {
-            // this tile's half of the g buffer still holds the previous m tile's g: wait until OUT has consumed it and
+          if (ng > 0) {
+            // this tile's half of the g buffer still holds the previous gated tile's g: wait until OUT has consumed it and
             // (first gate tile) until the TMA stores of that g have read the buffer
-            mbar_wait(&g_cons[nt], (uint32_t)((j - 1) & 1));
-            if (nt == 0) mbar_wait(g_free, (uint32_t)((j - 1) & 1));
+            SFT(wb)
+            mbar_wait(&g_cons[nt], (uint32_t)((ng - 1) & 1));
+            if (nt == 0) mbar_wait(g_free, (uint32_t)((ng - 1) & 1));
+            SFT(2)
           }
 #pragma unroll 1
           for (int step = 0; step < Cfg::BN / 64; ++step) {
@@ -323,7 +442,9 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             float out[3][16];
             TcEpiGate<true>::chunk(pg, acc, bsafe, step * 32 + q * 16, Cfg::BN / 2, 0, 0u, in, out, bs);
             uint8_t* ob = out_ring + oslot * Cfg::SLOT_PANELS * Cfg::PANEL;
+            SFT(wb)
             mbar_wait(&out_empty[oslot], ophase ^ 1);
+            SFT(3)
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               uint4 a, c;
@@ -358,19 +479,22 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             if (lane == 0) mbar_arrive(g_done);
           }
         } else {
+          const uint8_t* const mask_next = is_plain ? nullptr : Ly.mask_next;
 #pragma unroll 1
-          for (int step = 0; step < R_ / 32; ++step) {
+          for (int step = 0; step < po.N / 32; ++step) {
             float in[1][16];
             float out[1][16];
             TcEpiBiasActRes<true>::chunk(po, acc, bsafe, step * 32 + q * 16, 0, 0, 0u, in, out, bs);
             uint4 mk = make_uint4(0u, 0u, 0u, 0u);
-            if (Ly.mask_next) {
+            if (mask_next) {
               const int tt = (mt % p.tiles_t) * (2 * Cfg::BM) + pair_row0 + row;
               if (tt < p.T && b < p.B)
-                mk = __ldg(reinterpret_cast<const uint4*>(Ly.mask_next + ((size_t)b * p.T + tt) * R_ + step * 32 + q * 16));
+                mk = __ldg(reinterpret_cast<const uint4*>(mask_next + ((size_t)b * p.T + tt) * R_ + step * 32 + q * 16));
             }
             uint8_t* ob = out_ring + oslot * Cfg::SLOT_PANELS * Cfg::PANEL;
+            SFT(wb)
             mbar_wait(&out_empty[oslot], ophase ^ 1);
+            SFT(3)
             uint4 a, c;
             a.x = pack_bf16x2(out[0][0], out[0][1]); a.y = pack_bf16x2(out[0][2], out[0][3]);
             a.z = pack_bf16x2(out[0][4], out[0][5]); a.w = pack_bf16x2(out[0][6], out[0][7]);
@@ -378,7 +502,7 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
             c.z = pack_bf16x2(out[0][12], out[0][13]); c.w = pack_bf16x2(out[0][14], out[0][15]);
             *reinterpret_cast<uint4*>(ob + off0) = a;
             *reinterpret_cast<uint4*>(ob + off1) = c;
-            if (Ly.mask_next) {
+            if (mask_next) {
               // keep * (the bf16 value just stored) / (1 - rate), rounded once more: what dropout_apply makes of x_out
               const uint32_t xw[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
               const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
@@ -402,8 +526,16 @@ tc_stack_fwd_kernel(const TcStackLayer* __restrict__ layers, const int L, int* _
         __syncwarp();
         if (lane == 0) mbar_arrive_remote_relaxed(&tempty_bar[as], 0u);
         if (++as == 2) { as = 0; aphase ^= 1; }
+#ifdef TC_TIMELINE
+        SFT(wb)
+#endif
       }
     }
+#ifdef TC_TIMELINE
+    if (lane == 0 && warp == 4 && (blockIdx.x == 0 || blockIdx.x == 41))
+      printf("SFWD cta %d epilogue warp 4: setup(seq, table, bias) %lld  wait_tfull %lld  wait_g_cons/free %lld  wait_out_slot %lld  work: gate sub-tiles %lld  OUT %lld  plain %lld\n",
+             blockIdx.x, sft[4], sft[1], sft[2], sft[3], sft[5], sft[6], sft[7]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -418,41 +550,51 @@ struct TcStackPlan {
   void release() { cudaFree(d_layers); cudaFree(d_flags); d_layers = nullptr; d_flags = nullptr; }
 };
 
-// layers[l]: the TcBlockDesc of block l (same shapes for every block)
+// layers[l]: the TcBlockDesc of conv layer l (a block's gated conv + tail, or one of the plain convs in front of it); same
+// Cin = D = R, taps and B, T for every layer
 template <int D_, int R_>
 static int tc_stack_build_t(TmapCache& tc, const std::vector<TcBlockDesc>& descs, TcStackPlan* plan) {
   std::vector<TcStackLayer> tab(descs.size());
   for (size_t l = 0; l < descs.size(); ++l) {
     const TcBlockDesc& d = descs[l];
-    const CUtensorMap* mA = tc_act_map(tc, d.A, d.lda, d.Cin, d.T, d.B, 1, 0, 128);
-    const CUtensorMap* mX = tc_act_map(tc, d.X, d.ldx, d.R, d.T, d.B, 1, 0, 128);
-    uint64_t w1d[2] = {(uint64_t)d.k1, (uint64_t)(2 * d.D)}, w1s[1] = {(uint64_t)d.k1 * 2};
-    uint32_t w1b[2] = {64, 128};
-    const CUtensorMap* mW1 = tc.get(d.W1, 2, w1d, w1s, w1b);
-    uint64_t w2d[2] = {(uint64_t)(d.D + d.R), (uint64_t)d.R}, w2s[1] = {(uint64_t)(d.D + d.R) * 2};
-    uint32_t w2b[2] = {64, (uint32_t)(R_ / 2)};
-    const CUtensorMap* mW2 = tc.get(d.W2, 2, w2d, w2s, w2b);
-    const TcEpiIo zf{d.z, 2 * d.D, d.D, 0}, zs{d.z + d.D, 2 * d.D, d.D, 0}, xo{d.xout, d.R, d.R, 0};
-    const CUtensorMap* mZf = tc_panel_map(tc, zf, d.T, d.B);
-    const CUtensorMap* mZs = tc_panel_map(tc, zs, d.T, d.B);
-    const CUtensorMap* mO = tc_panel_map(tc, xo, d.T, d.B);
-    const CUtensorMap* mG = tc_slab_map(tc, d.g, d.D, d.D, d.T, d.B);
-    if (!mA || !mX || !mW1 || !mW2 || !mZf || !mZs || !mO || !mG) return -10;
     TcStackLayer& t = tab[l];
     memset(&t, 0, sizeof(t));
-    t.tmA = *mA; t.tmX = *mX; t.tmW1 = *mW1; t.tmW2 = *mW2; t.tmZf = *mZf; t.tmZs = *mZs; t.tmG = *mG; t.tmO = *mO; t.tmOd = *mO;
-    if (d.mask_next && d.xdrop_next) {
-      const TcEpiIo xd{d.xdrop_next, d.R, d.R, 0};
-      const CUtensorMap* mOd = tc_panel_map(tc, xd, d.T, d.B);
-      if (!mOd) return -10;
-      t.tmOd = *mOd; t.mask_next = d.mask_next;
+    const CUtensorMap* mA = tc_act_map(tc, d.A, d.lda, d.Cin, d.T, d.B, 1, 0, 128);
+    uint64_t w1d[2] = {(uint64_t)d.k1, (uint64_t)(d.plain ? d.D : 2 * d.D)}, w1s[1] = {(uint64_t)d.k1 * 2};
+    uint32_t w1b[2] = {64, 128};
+    const CUtensorMap* mW1 = tc.get(d.W1, 2, w1d, w1s, w1b);
+    const TcEpiIo xo{d.xout, d.plain ? d.D : d.R, d.plain ? d.D : d.R, 0};
+    const CUtensorMap* mO = tc_panel_map(tc, xo, d.T, d.B);
+    if (!mA || !mW1 || !mO) return -10;
+    t.tmA = *mA; t.tmW1 = *mW1; t.tmO = *mO; t.tmOd = *mO;
+    t.tmX = *mA; t.tmW2 = *mW1; t.tmZf = *mO; t.tmZs = *mO; t.tmG = *mO;      // placeholders (a plain layer never touches them)
+    t.kind = d.plain ? 1 : 0; t.act = d.act;
+    if (!d.plain) {
+      const CUtensorMap* mX = tc_act_map(tc, d.X, d.ldx, d.R, d.T, d.B, 1, 0, 128);
+      uint64_t w2d[2] = {(uint64_t)(d.D + d.R), (uint64_t)d.R}, w2s[1] = {(uint64_t)(d.D + d.R) * 2};
+      uint32_t w2b[2] = {64, (uint32_t)(R_ / 2)};
+      const CUtensorMap* mW2 = tc.get(d.W2, 2, w2d, w2s, w2b);
+      const TcEpiIo zf{d.z, 2 * d.D, d.D, 0}, zs{d.z + d.D, 2 * d.D, d.D, 0};
+      const CUtensorMap* mZf = tc_panel_map(tc, zf, d.T, d.B);
+      const CUtensorMap* mZs = tc_panel_map(tc, zs, d.T, d.B);
+      const CUtensorMap* mG = tc_slab_map(tc, d.g, d.D, d.D, d.T, d.B);
+      if (!mX || !mW2 || !mZf || !mZs || !mG) return -10;
+      t.tmX = *mX; t.tmW2 = *mW2; t.tmZf = *mZf; t.tmZs = *mZs; t.tmG = *mG;
+      if (d.mask_next && d.xdrop_next) {
+        const TcEpiIo xd{d.xdrop_next, d.R, d.R, 0};
+        const CUtensorMap* mOd = tc_panel_map(tc, xd, d.T, d.B);
+        if (!mOd) return -10;
+        t.tmOd = *mOd; t.mask_next = d.mask_next;
+      }
     }
     for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
     t.bias_g = d.bias_g; t.cbias = d.cbias; t.bias_r = d.bias_r;
   }
   const TcBlockDesc& d0 = descs[0];
+  if (descs.size() > TC_STACK_MAX_LAYERS) return -100;
   plan->release();
-  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->cb = d0.cbias != nullptr; plan->drop = d0.mask_next != nullptr;
+  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->cb = false; plan->drop = false;
+  for (const TcBlockDesc& d : descs) { if (d.cbias) plan->cb = true; if (d.mask_next) plan->drop = true; }
   if (cudaMalloc((void**)&plan->d_layers, tab.size() * sizeof(TcStackLayer)) != cudaSuccess ||
       cudaMemcpy(plan->d_layers, tab.data(), tab.size() * sizeof(TcStackLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMalloc((void**)&plan->d_flags, (size_t)plan->L * plan->num_mtiles * sizeof(int)) != cudaSuccess) {

@@ -62,8 +62,7 @@ template <bool FAST> struct TcEpiBiasActRes {
       for (int i = 0; i < 16; ++i) v[i] += t[i];
     }
     if (p.act != ACT_LINEAR) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = wn_act<FAST>(p.act, v[i]);
+      wn_act16<FAST>(p.act, v);
     }
     if (in_mask & 1u) {
 #pragma unroll
@@ -180,8 +179,7 @@ struct TcEpiActBwd {
       for (int i = 0; i < 16; ++i) v[i] += in[0][i];
     }
     if (in_mask & 2u) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= wn_act_grad_from_out(p.act, in[1][i]);
+      wn_act_grad16(p.act, in[1], v);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) out[0][i] = v[i];

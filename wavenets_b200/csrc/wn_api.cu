@@ -1227,38 +1227,59 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
   h->stack_fwd_layers = 0;
   if constexpr (sizeof(T) == 2) {
     // the whole residual stack as ONE persistent launch (gemm_tc_stack.cuh) when every block takes the fused forward
-    // and a layer has more 256-row tiles than the GPU has CTA pairs
+    // and a layer has more 256-row tiles than the GPU has CTA pairs.  Multi-dilation blocks (layers.py:64-88): every conv in
+    // front of the gated conv is a PLAIN layer of the same launch (its output is kept for the backward pass, as before).
     bool ok = h->use_stack_fwd && h->use_fused_fwd && tc_cta_group() == 2 && c.use_residual && h->L >= 2 && h->D == h->R &&
               (h->D == 256 || h->D == 128) && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!ok) break;
       const ConvP& cv = b.stack.back();
-      ok = b.stack.size() == 1 && b.Wres16 != nullptr && cv.tileN16 == 256 && cv.K <= TC_MAX_SEG && cv.cin % 64 == 0;
+      ok = b.Wres16 != nullptr && cv.tileN16 == 256 && cv.K <= TC_MAX_SEG && cv.cin % 64 == 0;
+      for (size_t j = 0; ok && j + 1 < b.stack.size(); ++j) {
+        const ConvP& pc = b.stack[j];
+        // plain layers run as one 256-wide tile per m tile: D = 256 only; all convs share K and the input width
+        ok = h->D == 256 && pc.cout == h->D && pc.cin == cv.cin && pc.K == cv.K && pc.Wf16 != nullptr && pc.N16 == 256 && b.stack.size() <= 16;
+      }
     }
     if (ok) {
       const size_t rows_cap = (size_t)h->maxB * h->maxT;
       const bool has_cb = c.conditioning != 0;
-      auto desc_of = [&](int l) {
-        BlockP& b = h->blocks[l];
-        const ConvP& cv = b.stack[0];
-        const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
-        TcBlockDesc d{};
-        d.B = B; d.T = Tn; d.nseg = cv.K; d.Cin = cv.cin; d.D = h->D; d.R = h->R; d.has_res = 1;
-        for (int k = 0; k < cv.K; ++k) d.shift[k] = -(cv.K - 1 - k) * cv.dil;
-        d.A = (const bf16*)x_in; d.lda = h->R; d.X = (const bf16*)x_in; d.ldx = h->R;
-        d.W1 = cv.Wf16; d.k1 = cv.Kf16; d.W2 = b.Wres16;
-        d.z = (bf16*)h->zbuf[l]; d.g = (bf16*)h->G_all + (size_t)l * rows_cap * h->D; d.xout = (bf16*)h->xout[l];
-        d.bias_g = P_(h, cv.b_idx); d.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
-        d.bias_r = P_(h, b.conv1.b_idx);
-        if (h->drop_active) {
+      // one desc per CONV: the plain convs of block l, then its gated conv + tail
+      auto build_descs = [&](std::vector<TcBlockDesc>& descs) {
+        descs.clear();
+        for (int l = 0; l < h->L; ++l) {
+          BlockP& b = h->blocks[l];
+          const void* x_in = l > 0 ? h->xout[l - 1] : h->h0;
           // training-mode dropout without leaving the launch: the conv branch of block l reads xdrop[l] = keep_l * x / (1 - rate),
           // written by the OUT epilogue of block l-1 next to x_out (block 0: by dropout_apply on h0 below); the residual reads x
-          d.A = (const bf16*)h->xdrop[l];
-          d.drop_scale = 1.0f / (1.0f - c.dropout);
-          if (l + 1 < h->L) { d.mask_next = h->drop_mask + (size_t)(l + 1) * rows_cap * h->R; d.xdrop_next = (bf16*)h->xdrop[l + 1]; }
+          const void* cur = h->drop_active ? (const void*)h->xdrop[l] : x_in;
+          const int depth = (int)b.stack.size();
+          for (int j = 0; j < depth; ++j) {
+            const ConvP& cv = b.stack[j];
+            TcBlockDesc d{};
+            d.B = B; d.T = Tn; d.nseg = cv.K; d.Cin = cv.cin; d.D = h->D; d.R = h->R; d.has_res = 1;
+            for (int k = 0; k < cv.K; ++k) d.shift[k] = -(cv.K - 1 - k) * cv.dil;
+            d.A = (const bf16*)cur; d.lda = j == 0 ? h->R : h->D;
+            d.W1 = cv.Wf16; d.k1 = cv.Kf16;
+            d.bias_g = P_(h, cv.b_idx);
+            if (h->drop_active) d.drop_scale = 1.0f / (1.0f - c.dropout);
+            if (j < depth - 1) {
+              d.plain = 1; d.act = c.activation;
+              d.xout = (bf16*)h->acts[l][j];
+              cur = h->acts[l][j];
+            } else {
+              d.X = (const bf16*)x_in; d.ldx = h->R; d.W2 = b.Wres16;
+              d.z = (bf16*)h->zbuf[l]; d.g = (bf16*)h->G_all + (size_t)l * rows_cap * h->D; d.xout = (bf16*)h->xout[l];
+              d.cbias = has_cb ? h->cb + (size_t)l * h->maxB * 2 * h->D : nullptr;
+              d.bias_r = P_(h, b.conv1.b_idx);
+              if (h->drop_active && l + 1 < h->L) { d.mask_next = h->drop_mask + (size_t)(l + 1) * rows_cap * h->R; d.xdrop_next = (bf16*)h->xdrop[l + 1]; }
+            }
+            descs.push_back(d);
+          }
         }
-        return d;
       };
+      std::vector<TcBlockDesc> descs;
+      build_descs(descs);
       TcStackPlan* sp = nullptr;
       for (auto& q : h->stack_plans) if (q.B == B && q.T == Tn && q.cb == has_cb && q.drop == (h->drop_active && h->L > 1)) sp = &q;
       int r = 0;
@@ -1273,8 +1294,6 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
             for (auto& q : h->stack_plans) q.release();
             h->stack_plans.clear();
           }
-          std::vector<TcBlockDesc> descs;
-          for (int l = 0; l < h->L; ++l) descs.push_back(desc_of(l));
           h->stack_plans.push_back(TcStackPlan{});
           r = tc_stack_build(h->tmaps, descs, &h->stack_plans.back());
           if (r == 0) sp = &h->stack_plans.back(); else h->stack_plans.pop_back();
@@ -1289,7 +1308,7 @@ static int model_forward(wn_handle* h, cudaStream_t st, const float* x, int ldx,
       if (sp) {
         struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_fwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
         LaunchScope ls(h, st, CLS_DILATED);
-        r = tc_stack_launch(st, *sp, desc_of(0));
+        r = tc_stack_launch(st, *sp, descs[0]);
         if (r == 0) { stacked = true; h->fused_fwd_launches = h->L; h->stack_fwd_layers = h->L; cur = h->xout[h->L - 1]; }
         else if (r == -100) h->launches--;
         else { set_err("stack forward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
