@@ -28,6 +28,9 @@ struct TcWgUnit {            // 64 B: one CTA pair's work = one 256-channel A ti
                              // cs[(cs_row0 + batch - first batch) * 256 + col]
   int c_begin, c_end;        // 64-row chunks [c_begin, c_end) of the flattened (b, t) axis
   int cs_r0, cs_r1;          // rows of every 64-row chunk this unit adds up for the column sums
+  int share_g, shift2;       // share_g != 0 (nh == 2): the two products are two TAPS of one conv against the SAME G tile — the second
+                             // A tile (same channels, time shift shift2) takes the second G slot of the stage; one G load for two
+                             // products (the plain convs of a multi-dilation block have one 256-column G tile and K taps)
 };
 
 struct TcWgGroupParams {
@@ -94,7 +97,10 @@ tc_wgrad_group_kernel(const __grid_constant__ CUtensorMap tmP, const TcWgGroupPa
         // sibling units (other taps / column tiles of the same block) read the same boxes at about the same time: normal policy
         tma_load_4d_pair_h(sa, tmA, &full_bar[stage], 0, t0 + u.shift, a_atom, b, TC_POL_NORMAL);
         tma_load_4d_pair_h(sa + Cfg::A_BYTES, tmG0, &full_bar[stage], 0, t0, g_atom0, b, TC_POL_NORMAL);
-        if (u.nh > 1) tma_load_4d_pair_h(sa + Cfg::A_BYTES + Cfg::GH_BYTES, tmG1, &full_bar[stage], 0, t0, g_atom1, b, TC_POL_NORMAL);
+        if (u.nh > 1) {
+          if (u.share_g) tma_load_4d_pair_h(sa + Cfg::A_BYTES + Cfg::GH_BYTES, tmA, &full_bar[stage], 0, t0 + u.shift2, a_atom, b, TC_POL_NORMAL);
+          else tma_load_4d_pair_h(sa + Cfg::A_BYTES + Cfg::GH_BYTES, tmG1, &full_bar[stage], 0, t0, g_atom1, b, TC_POL_NORMAL);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (++ct == p.chunks_t) { ct = 0; ++b; }
       }
@@ -108,9 +114,9 @@ tc_wgrad_group_kernel(const __grid_constant__ CUtensorMap tmP, const TcWgGroupPa
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc(sa, 8192, 1024);
           for (int hh = 0; hh < u.nh; ++hh) {
-            const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES + hh * Cfg::GH_BYTES, 8192, 1024);
+            const uint64_t adesc = umma_smem_desc((u.share_g && hh) ? sa + Cfg::A_BYTES + Cfg::GH_BYTES : sa, 8192, 1024);
+            const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES + (u.share_g ? 0 : hh) * Cfg::GH_BYTES, 8192, 1024);
 #pragma unroll
             for (int k = 0; k < Cfg::BKT / 16; ++k)
               umma_bf16_pair(tmem_base + (uint32_t)(hh * BN), adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (it | k) != 0);
@@ -397,12 +403,13 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   // ---- pair up tiles that read the same A tile (same rows, channels and shift): one unit, one A load for two products.
   // Column-sum duty needs equal row slices in both halves (the unit has one [cs_r0, cs_r1)); otherwise the second loses it...
   // so only tiles with the same slice (or no duty on one side) are paired.
-  struct UnitT { int t[2]; int nh; };
+  static_assert(TcWgradPairCfg<256, 2>::A_BYTES == TcWgradPairCfg<256, 2>::GH_BYTES, "share_g units put an A tile into a G slot");
+  struct UnitT { int t[2]; int nh; int share_g; };
   std::vector<UnitT> ut;
   for (int i = 0; i < ntiles; ++i) {
     if (tl[i].used) continue;
     tl[i].used = true;
-    UnitT uu{{i, -1}, 1};
+    UnitT uu{{i, -1}, 1, 0};
     if (pair_tiles)
       for (int k = i + 1; k < ntiles && k < i + 64; ++k) {
         if (tl[k].used) continue;
@@ -411,6 +418,17 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
         const bool cx = x.cs_entry >= 0, cy = y.cs_entry >= 0;
         if (cx && cy && (x.cs_r0 != y.cs_r0 || x.cs_r1 != y.cs_r1)) continue;
         uu.t[1] = k; uu.nh = 2; tl[k].used = true;
+        break;
+      }
+    if (pair_tiles && uu.nh == 1)
+      // no partner on the same A tile: two taps of the same conv against the same G tile (same A channels, another time shift)
+      for (int k = i + 1; k < ntiles && k < i + 64; ++k) {
+        if (tl[k].used) continue;
+        const Tile &x = tl[i], &y = tl[k];
+        if (x.g_map != y.g_map || x.g_atom != y.g_atom || x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift == y.shift || x.group != y.group) continue;
+        // column-sum duty: both name the same G tile; their row slices must be adjacent (the unit sums one range)
+        if (x.cs_entry != y.cs_entry || (x.cs_entry >= 0 && x.cs_r1 != y.cs_r0)) continue;
+        uu.t[1] = k; uu.nh = 2; uu.share_g = 1; tl[k].used = true;
         break;
       }
     ut.push_back(uu);
@@ -473,12 +491,14 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
         u.c_begin = z * cps; u.c_end = std::min(total_chunks, (z + 1) * cps);
         const int b0 = u.c_begin / chunks_t, b1 = (u.c_end - 1) / chunks_t;
         u.cs_r0 = u.cs_r1 = 0;
+        u.share_g = uu.share_g; u.shift2 = uu.share_g ? tl[uu.t[1]].shift : 0;
         for (int hh = 0; hh < 2; ++hh) {
           const Tile& t = tl[uu.t[hh] >= 0 ? uu.t[hh] : uu.t[0]];
           u.g_map[hh] = t.g_map; u.g_atom[hh] = t.g_atom; u.out_tile[hh] = uu.t[hh] >= 0 ? tiles[uu.t[hh]].tile0 + z : 0;
           u.cs_row0[hh] = -1;
+          if (uu.share_g && hh == 1) continue;      // one G tile: its column sums belong to slot 0 (rows of both taps' slices)
           if (uu.t[hh] >= 0 && t.cs_entry >= 0 && t.cs_r1 > t.cs_r0) {
-            u.cs_r0 = t.cs_r0; u.cs_r1 = t.cs_r1;
+            u.cs_r0 = t.cs_r0; u.cs_r1 = (uu.share_g && tl[uu.t[1]].cs_entry >= 0) ? tl[uu.t[1]].cs_r1 : t.cs_r1;
             TcWgFinCs& e = css[t.cs_entry];
             if (e.nsrc >= TC_WG_MAX_CS_SRC) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: too many column-sum sources"); return -22; }
             u.cs_row0[hh] = cs_rows;

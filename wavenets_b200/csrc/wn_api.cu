@@ -1045,11 +1045,11 @@ static void run_colsum(wn_handle* h, cudaStream_t st, const void* G, int ldg, in
   const int chunks = cdiv(Tn, 256);
   {
     LaunchScope ls(h, st, CLS_MISC);
-    colsum_stage1<T><<<dim3(cdiv(N, 128), chunks, B), 128, 0, st>>>((const T*)G, ldg, h->colpart, Tn, N, 256);
+    colsum_stage1<T><<<dim3(cdiv(N, 32), chunks, B), 256, 0, st>>>((const T*)G, ldg, h->colpart, Tn, N, 256);
   }
   {
     LaunchScope ls(h, st, CLS_MISC);
-    colsum_stage2<<<cdiv(N, 128), 128, 0, st>>>(h->colpart, B, chunks, N, per_batch, ldpb, total);
+    colsum_stage2<<<cdiv(N, 32), 256, 0, st>>>(h->colpart, B, chunks, N, per_batch, ldpb, total);
   }
 }
 
