@@ -392,6 +392,8 @@ def main():
   side_l = C.c_int(0)
   wg_tiles = int(h.lib.wn_grouped_wgrad_tiles(h.h, C.byref(side_l)))   # of the timed (graph-replayed) step
   stack_layers = int(h.lib.wn_stack_forward_layers(h.h))
+  stack_bwd_layers = int(h.lib.wn_stack_backward_layers(h.h))
+  ar_early = int(h.lib.wn_allreduce_buckets(h.h))
   clocks = sampler.stop() if sampler else None
   loss_last = float(loss_t[0].item())
 
@@ -494,7 +496,8 @@ def main():
   share = dil_ms_eager / prof['all'][0] if prof['all'][0] > 0 else 0.0
   total_flops_step = 3.0 * flops['total'] * rows
   alg_bytes_step = workmodel.alg_bytes_per_sample(kw, e_bytes) * rows
-  if precision == 'bf16':
+  narrow = kw['channels'] < 128      # reference default width: AI of the un-fused layers is below the ridge -> HBM roofline
+  if precision == 'bf16' and not narrow:
     # grouped weight gradients: ONE launch (+ side launches) computes the gated-conv, conv1, conv_skip and head filter
     # gradients as 256 x 256 tiles; the launch is timed in this class, so all of its products count as the class's work;
     # the fused forward kernels' conv1 products likewise (forward only; their adjoints run in other kernels)
@@ -529,7 +532,8 @@ def main():
     achieved = alg_bytes_step / (step_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm'],
                 'peak_source': f'{peaks["source"]} HBM copy bandwidth (MEASURED_PEAKS.json)', 'traffic': None,
-                'kernel': 'whole step (conv_gemm_simt + wgrad_simt FFMA tier): block-fused algorithmic bytes / step time',
+                'kernel': ('whole step (tc_conv_gemm_staged_kernel + tc_wgrad_kernel, tcgen05 tier; 64-channel k-blocks padded in shared memory by TMA zero fill)'
+                           if precision == 'bf16' else 'whole step (conv_gemm_simt + wgrad_simt FFMA tier)') + ': block-fused algorithmic bytes / step time',
                 'alg_bytes_per_step': alg_bytes_step, 'launches_per_step': prof['all'][1],
                 'tensor_equivalent_tflops': total_flops_step / (step_ms * 1e-3) / 1e12}
   if dram:
@@ -571,7 +575,9 @@ def main():
                'params': int(h.n_scalars), 'parallelism': f'dp{world}', 'dropout': float(kw['dropout']),
                'l2': 'per-step working set (activations cached for backward) is GBs >> 126 MB L2; no explicit flush needed'
                      if rows * kw['channels'] * kw['blocks'] * e_bytes > 2.5e8 else 'per-step working set fits L2: steps run back to back on a warm L2 (as in training)',
-               'flops_per_sample_fwd_bwd': 3 * flops['total'], 'allreduce': model_allreduce_kind(model)},
+               'flops_per_sample_fwd_bwd': 3 * flops['total'], 'allreduce': model_allreduce_kind(model),
+               # gradient slices all-reduced EARLY on the communication stream, beside the next weight-gradient bucket's kernels
+               'allreduce_early_buckets': ar_early, 'stack_backward_layers': stack_bwd_layers},
     'e2e': {'value': world * rows * args.steps / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 16,
             'ms_per_step': ms_e2e / args.steps, 'api': 'WaveNet.train_step_deferred(host buffers) + .result(): logs of step k read after step k+1 is enqueued',
             'sync_per_step_ms': ms_e2e_sync / args.steps},

@@ -252,6 +252,13 @@ int wn_stack_forward_layers(const wn_handle* h);
 /* blocks whose backward chain (gate adjoint + dgrad: the autodiff of layers.py:199-224) ran inside the ONE persistent
  * stack-backward launch of the last training step; 0 = two launches per block */
 int wn_stack_backward_layers(const wn_handle* h);
+/* Gradient slices the last training step all-reduced EARLY, on its communication stream, beside the kernels of the next
+ * weight-gradient bucket (0: one all-reduce behind the backward pass).  With a communicator that reduces inside the step
+ * (wn_comm_fuse_allreduce) and the persistent stack-backward launch, the grouped weight-gradient launch runs in WN_AR_BUCKETS
+ * (default 2) groups of blocks; only the last group's slice (+ head, input conv, mapping) is reduced after the pass.
+ * Replaces: the overlap of gradient reduction with backprop that tf.distribute.MirroredStrategy gets from per-variable
+ * all-reduces (train.py:203, model.py:336). */
+int wn_allreduce_buckets(const wn_handle* h);
 int wn_profile_begin(wn_handle* h, int tag);
 int wn_profile_end(wn_handle* h, double* ms, int64_t* launches);
 /* per-launch record of the last wn_profile_end: returns the number of timed launches; fills duration (ms) and a

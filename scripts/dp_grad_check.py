@@ -17,6 +17,10 @@ CASES = {
   # bf16 tier, grouped weight gradients + fused forward: sequences are independent, so the shards' roundings are the 1-GPU run's
   'bf16_r256': (dict(channels=256, blocks=4, layers_per_block=1, dilation_bound=16, skip_channels=256, final_layers_channels=[256],
                      conditioning='global', mapping_layers=[8], mapping_activation='tanh'), 'bf16', 2, 2048, 2e-5),
+  # the persistent stack launches (75 row tiles per replica > 74 CTA pairs) with the BUCKETED all-reduce: the grouped weight-gradient
+  # launch runs in two groups of blocks, the first group's slice of the flat gradient buffer is reduced beside the second group's kernels
+  'bf16_stack_buckets': (dict(channels=256, blocks=6, layers_per_block=1, dilation_bound=16, skip_channels=256, final_layers_channels=[256],
+                              conditioning='global', mapping_layers=[8], mapping_activation='tanh'), 'bf16', 3, 6400, 3e-5),
   # dropout with injected keep-masks: every replica gets its rows of the global masks (Philox masks differ per replica by design)
   'fp32_dropout_masks': (dict(channels=32, blocks=3, layers_per_block=1, dilation_bound=8, final_layers_channels=[32], dropout=0.25), 'fp32', 2, 600, 1e-5),
 }
@@ -68,6 +72,7 @@ def run_case(name, rank, local, world, native):
         worst, who = e, nm
     res = {'case': name, 'n_replicas': world, 'precision': precision, 'global_batch': B, 'T': T, 'worst_rel_l2': worst, 'tensor': who, 'tol': tol,
            'loss_sum_of_replicas': float(loss_dp.item()), 'loss_single_gpu': l1, 'allreduce': 'C ABI (wn_allreduce_grads, NCCL)' if m._comm is not None else 'torch.distributed',
+           'early_allreduce_buckets': int(hh.lib.wn_allreduce_buckets(hh.h)), 'stack_backward_layers': int(hh.lib.wn_stack_backward_layers(hh.h)),
            'ok': bool(worst <= tol and abs(float(loss_dp.item()) - l1) <= 1e-5 * abs(l1))}
     print(json.dumps(res), flush=True)
   dist.barrier()

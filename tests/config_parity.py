@@ -23,7 +23,12 @@ SHAPES = {
 
 def setup(name, dropout=0.0):
   from wavenets_b200 import CONFIGS, WaveNet, model_kwargs, synth
+  precision = None
+  if name.endswith('_bf16'):       # 'c1_bf16': the defaults.yaml topology (32 channels) on the tcgen05 tier
+    name, precision = name[:-5], 'bf16'
   cfg = dict(CONFIGS[name])
+  if precision:
+    cfg['precision'] = precision
   cfg['dropout'] = dropout
   kw = model_kwargs(cfg)
   B, T, want_stack, want_group = SHAPES[name]
@@ -60,6 +65,7 @@ def errors(g, ref):
 def run(name, dropout=0.0):
   """dropout > 0: a TRAINING pass with injected keep-masks (TF's RNG stream cannot be reproduced): the same masks go to the oracle"""
   m, ocfg, p, x, cond, precision, want_stack, want_group, kw = setup(name, dropout)
+  name = name[:-5] if name.endswith('_bf16') else name
   data = (x, cond) if cond is not None else x
   h = m.handle
   keep = None

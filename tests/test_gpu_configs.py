@@ -36,6 +36,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL_FP32 = 1e-4
 TOL_LOSS_BF16, TOL_GRAD_BF16 = 1e-2, 6e-2              # shipped library vs float64: stated bf16 tolerance
+TOL_GRAD_BF16_NARROW = 1e-1                            # = TOL_GRAD_PWL of tests/test_gpu_parity_bf16.py (relu / leaky_relu models)
 TOL_LOSS_FAITHFUL = 5e-5                               # vs the bf16-faithful oracle: loss
 TOL_GRAD_FAITHFUL, TOL_GLOBAL_FAITHFUL = 8e-3, 4e-3    # worst gradient tensor / all gradients together (measured: <= 4.7e-3 / 2.1e-3)
 TOL_GRAD_FAITHFUL_DROPOUT, TOL_GLOBAL_FAITHFUL_DROPOUT = 1.2e-2, 5e-3   # training pass with dropout 0.1: every block's masked, 1/(1-p)-scaled input
@@ -50,7 +51,7 @@ def _check_paths(r):
     assert r['grouped_tiles'] > 0, 'the grouped weight-gradient launch must be on the checked path'
 
 
-@pytest.mark.parametrize('name', ['c1', 'c2', 'c3', 'c4', 'c5'])
+@pytest.mark.parametrize('name', ['c1', 'c1_bf16', 'c2', 'c3', 'c4', 'c5'])
 def test_config_topology_vs_oracle(name):
   r = config_parity.run(name)
   print(json.dumps(r))
@@ -60,7 +61,9 @@ def test_config_topology_vs_oracle(name):
     assert r['worst_fp64'] <= TOL_FP32, r
     return
   assert abs(r['loss'] - r['loss_fp64']) <= TOL_LOSS_BF16 * abs(r['loss_fp64']), r
-  assert r['worst_fp64'] <= TOL_GRAD_BF16, r
+  # c1_bf16: 32-entry bias vectors of leaky_relu convs, one sequence — the handful of derivative flips of bf16 storage weighs more in a
+  # tensor that small (measured 6.5e-2 on block3/dil1/bias against float64, 3.1e-3 against the bf16-faithful oracle)
+  assert r['worst_fp64'] <= (TOL_GRAD_BF16_NARROW if name == 'c1_bf16' else TOL_GRAD_BF16), r
   assert abs(r['loss'] - r['loss_faithful']) <= TOL_LOSS_FAITHFUL * abs(r['loss_faithful']), r
   assert r['worst_faithful'] <= TOL_GRAD_FAITHFUL, r
   assert r['global_faithful'] <= TOL_GLOBAL_FAITHFUL, r

@@ -33,6 +33,9 @@ def test_two_gpu_allreduced_grads_equal_single_gpu(native):
   r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
   lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{')]
   assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
-  assert len(lines) == 3 and all(l['ok'] for l in lines), lines
+  assert len(lines) == 4 and all(l['ok'] for l in lines), lines
   if native:
     assert all('C ABI' in l['allreduce'] for l in lines)
+    # the bucketed all-reduce (first group of blocks reduced beside the second group's weight-gradient kernels) is on the checked path
+    bk = [l for l in lines if l['case'] == 'bf16_stack_buckets'][0]
+    assert bk['stack_backward_layers'] == 6 and bk['early_allreduce_buckets'] >= 1, bk

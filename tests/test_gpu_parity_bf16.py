@@ -57,6 +57,12 @@ BF16_MODELS = {
   'group256_multidil': dict(channels=256, blocks=2, layers_per_block=2, dilation_bound=8, skip_channels=256, final_layers_channels=[128],
                             activation='tanh'),
   'group256_alias_multidil': dict(channels=256, blocks=2, layers_per_block=3, dilation_bound=8, final_layers_channels=[128], activation='tanh'),
+  # the reference's default width (defaults.yaml:10): 32 channels — k-blocks padded to 64 in shared memory by TMA zero fill
+  'narrow32_defaults': dict(channels=32, blocks=2, layers_per_block=3, dilation_bound=8, activation='leaky_relu', final_layers_channels=[128, 256]),
+  'narrow32_cond_skip96': dict(channels=32, blocks=3, layers_per_block=1, dilation_bound=8, skip_channels=96, dilation_channels=64,
+                               final_layers_channels=[32], conditioning='global', mapping_layers=[8], mapping_activation='tanh', activation='tanh'),
+  'narrow32_k3_gaussian': dict(channels=32, blocks=2, layers_per_block=2, dilation_bound=9, kernel_size=3, activation='tanh',
+                               final_layers_channels=[96], num_mixtures=4, sampling_function='gaussian', use_skip=False),
   'unfused256_nores': dict(channels=256, blocks=2, layers_per_block=1, dilation_bound=4, skip_channels=128, use_residual=False,
                            final_layers_channels=[128]),
 }

@@ -24,6 +24,7 @@ EXPORTS = [
   'wn_fused_forward_blocks', 'wn_grouped_wgrad_tiles', 'wn_stack_forward_layers', 'wn_profile_begin', 'wn_profile_end', 'wn_profile_get', 'wn_build_info', 'wn_set_dropout_masks', 'wn_set_dropout_seed', 'wn_num_frames', 'wn_preprocess_frames', 'wn_inverse_mu_law', 'wn_one_hot', 'wn_sample_waveform', 'wn_sample_last_step', 'wn_generate', 'wn_adam_init', 'wn_clip_grads', 'wn_adam_step', 'wn_adam_state', 'wn_debug_conv_gemm', 'wn_debug_wgrad', 'wn_debug_bench',
   'wn_forward_ex', 'wn_loss_fn', 'wn_adam_restore', 'wn_nccl_unique_id', 'wn_comm_init', 'wn_comm_attach', 'wn_comm_fuse_allreduce',
   'wn_allreduce_grads', 'wn_nccl_info', 'wn_grouped_wgrad_info', 'wn_debug_tensor', 'wn_stack_backward_layers',
+  'wn_allreduce_buckets',
 ]
 
 
@@ -103,6 +104,7 @@ def load():
   lib.wn_grouped_wgrad_tiles.argtypes = [vp, C.POINTER(C.c_int)]
   lib.wn_stack_forward_layers.argtypes = [vp]
   lib.wn_stack_backward_layers.argtypes = [vp]
+  lib.wn_allreduce_buckets.argtypes = [vp]
   lib.wn_debug_tensor.argtypes = [vp, C.c_char_p, i32, vp, i64]
   lib.wn_grouped_wgrad_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
   lib.wn_profile_begin.argtypes = [vp, i32]

@@ -54,8 +54,12 @@ struct TcWgradDesc {
 };
 struct TcWgradPlan { int nsplit, chunks_per_split, chunks_t, slots, mtiles; };
 
+// Channel widths: multiples of 32 (the reference's default width, defaults.yaml:10).  A 64-channel k-block of a narrower
+// tensor is padded in SHARED memory, not in HBM: the TMA box reaches past the tensor's channel extent and the out-of-bounds
+// half arrives as zeros (same mechanism as the causal padding in time); the weight box of the same k-block then also covers
+// the next tap's rows, which meet those zeros.  Output panels are 32 columns wide.
 static inline int tc_check_config(int R, int D, int S, int K) {
-  if (R % 64 || D % 64 || S % 64) return -1;
+  if (R % 32 || D % 32 || S % 32) return -1;
   if (K > TC_MAX_SEG) return -2;
   return 0;
 }

@@ -13,6 +13,7 @@
 // Units and tensor maps come from tables in global memory (built once per (B, T) on the host).  Deterministic: the
 // finish kernel sums the splits of a tile in a fixed order, no atomics.
 #pragma once
+#include <algorithm>
 #include <map>
 #include <tuple>
 #include <unordered_map>
@@ -304,6 +305,8 @@ struct TcWgJobDesc {         // one weight-gradient problem dW[k * Cin + c, n] =
   float* dst; const float* w;            // [ntaps * cin][N] fp32 gradient (Keras layout), weights for L2 (or null)
   float* bias;                           // [N] column sums of G, or null
   float* per_batch; int ldpb;            // [B][ldpb] per-batch column sums of G, or null
+  int bucket = 0;                        // final-launch jobs only: the final launch runs as one launch + finish per bucket, in bucket
+                                         // order, so that the gradients of bucket k can be all-reduced while bucket k + 1 is computed
   int group = -1;                        // -1: the launch at the end of the backward pass; g >= 0: side launch g (one per block
                                          // that hands its weight gradients to the SMs the dgrad chain leaves idle)
   // several problems may share one G (conv_skip of every block reads d skip): the column sums are computed once, by the
@@ -314,6 +317,8 @@ struct TcWgGroupPlan {
   int B = 0, T = 0;
   int nunits = 0, ntiles = 0, ncs = 0, nsplit = 1, npartial = 0;
   int final_units = 0;                                   // units [0, final_units): the launch at the end
+  struct Bucket { int unit0, nunits, tile0, ntiles, cs0, ncs; };
+  std::vector<Bucket> buckets;                           // the final launch, bucket by bucket (tiles / column-sum entries of a bucket are contiguous)
   std::vector<std::pair<int, int>> side;                 // per side group: (first unit, units)
   CUtensorMap* d_maps = nullptr; TcWgUnit* d_units = nullptr; TcWgFinTile* d_tiles = nullptr; TcWgFinCs* d_css = nullptr;
   float* d_partial = nullptr; float* d_cs = nullptr;
@@ -327,9 +332,17 @@ struct TcWgGroupPlan {
 // every problem must have cin % 256 == 0 and N % 256 == 0
 static inline bool tc_wgrad_group_ok(int cin, int N) { return cin % 256 == 0 && N % 256 == 0; }
 
-static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& jobs, int B, int T, int force_split, bool pair_tiles, int side_pairs, TcWgGroupPlan* plan) {
+static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& jobs_in, int B, int T, int force_split, bool pair_tiles, int side_pairs, TcWgGroupPlan* plan) {
   plan->release();
   plan->B = B; plan->T = T;
+  // final-launch jobs in bucket order (stable), side-launch jobs behind them
+  std::vector<TcWgJobDesc> jobs(jobs_in);
+  std::stable_sort(jobs.begin(), jobs.end(), [](const TcWgJobDesc& a, const TcWgJobDesc& b) {
+    const int ka = a.group >= 0 ? (1 << 20) + a.group : a.bucket, kb = b.group >= 0 ? (1 << 20) + b.group : b.bucket;
+    return ka < kb;
+  });
+  int nbuckets = 1;
+  for (const auto& j : jobs) if (j.group < 0 && j.bucket + 1 > nbuckets) nbuckets = j.bucket + 1;
   std::vector<CUtensorMap> maps;
   std::map<std::tuple<const void*, int, int>, int> map_of;
   auto map_idx = [&](const bf16* p, int ld, int width) -> int {
@@ -344,7 +357,8 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   };
   const int chunks_t = (T + 63) / 64, total_chunks = B * chunks_t;
   // ---- 256 x 256 output tiles, column-sum entries
-  struct Tile { int a_map, a_atom, shift, g_map, g_atom; int cs_entry; int cs_r0, cs_r1; bool used; int group; };
+  struct Tile { int a_map, a_atom, shift, g_map, g_atom; int cs_entry; int cs_r0, cs_r1; bool used; int group; int bucket; };
+  std::vector<int> cs_bucket;                            // bucket of every TcWgFinCs entry (side-launch jobs: the last bucket)
   std::vector<Tile> tl;
   std::vector<TcWgFinTile> tiles;
   std::vector<TcWgFinCs> css;
@@ -368,6 +382,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
           e.per_batch = j.per_batch ? j.per_batch + nt * 256 : nullptr;
           e.ldpb = j.ldpb; e.nsrc = 0;
           css.push_back(e);
+          cs_bucket.push_back(j.group < 0 ? j.bucket : nbuckets - 1);
         }
     }
     // the tiles that share a G tile split the 64 rows of a chunk between them for the column sums
@@ -385,7 +400,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
           t.a_map = am; t.a_atom = mt * 4; t.shift = j.shift[k]; t.g_map = gm; t.g_atom = nt * 4;
           t.cs_entry = own_cs ? cs0 + nt : -1;
           t.cs_r0 = (64 * sh) / sharers; t.cs_r1 = (64 * (sh + 1)) / sharers;
-          t.used = false; t.group = j.group;
+          t.used = false; t.group = j.group; t.bucket = j.group < 0 ? j.bucket : nbuckets - 1;
           tl.push_back(t);
         }
     if (want_cs && !own_cs) {
@@ -396,6 +411,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
         e.per_batch = j.per_batch ? j.per_batch + nt * 256 : nullptr;
         e.ldpb = j.ldpb; e.nsrc = -1 - (cs0 + nt);      // marks "copy of entry cs0 + nt"
         css.push_back(e);
+        cs_bucket.push_back(j.group < 0 ? j.bucket : nbuckets - 1);
       }
     }
   }
@@ -414,7 +430,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
       for (int k = i + 1; k < ntiles && k < i + 64; ++k) {
         if (tl[k].used) continue;
         const Tile &x = tl[i], &y = tl[k];
-        if (x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift != y.shift || x.group != y.group) continue;
+        if (x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift != y.shift || x.group != y.group || x.bucket != y.bucket) continue;
         const bool cx = x.cs_entry >= 0, cy = y.cs_entry >= 0;
         if (cx && cy && (x.cs_r0 != y.cs_r0 || x.cs_r1 != y.cs_r1)) continue;
         uu.t[1] = k; uu.nh = 2; tl[k].used = true;
@@ -425,7 +441,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
       for (int k = i + 1; k < ntiles && k < i + 64; ++k) {
         if (tl[k].used) continue;
         const Tile &x = tl[i], &y = tl[k];
-        if (x.g_map != y.g_map || x.g_atom != y.g_atom || x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift == y.shift || x.group != y.group) continue;
+        if (x.g_map != y.g_map || x.g_atom != y.g_atom || x.a_map != y.a_map || x.a_atom != y.a_atom || x.shift == y.shift || x.group != y.group || x.bucket != y.bucket) continue;
         // column-sum duty: both name the same G tile; their row slices must be adjacent (the unit sums one range)
         if (x.cs_entry != y.cs_entry || (x.cs_entry >= 0 && x.cs_r1 != y.cs_r0)) continue;
         uu.t[1] = k; uu.nh = 2; uu.share_g = 1; tl[k].used = true;
@@ -438,29 +454,36 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   for (const auto& t : tl) if (t.group + 1 > ngroups) ngroups = t.group + 1;
   std::vector<std::vector<int>> by_group(ngroups + 1);     // [0]: final, [1 + g]: side group g
   for (int i = 0; i < (int)ut.size(); ++i) by_group[tl[ut[i].t[0]].group + 1].push_back(i);
-  // ---- splits of the final launch: simulate the block scheduler (units in launch order onto the earliest free CTA pair)
+  // ---- splits of the final launch, per bucket: simulate the block scheduler (units in launch order onto the earliest free CTA pair)
   const int npairs = tc_num_sms() / 2;
-  int nsplit = 1;
-  if (force_split > 0) nsplit = force_split;
-  else if (!by_group[0].empty()) {
-    double best = 1e30;
-    for (int s = 1; s <= 8; ++s) {
-      if (s > total_chunks) break;
-      std::vector<double> free_at(npairs, 0.0);
-      for (int z0 : by_group[0])
-        for (int z = 0; z < s; ++z) {
-          auto it = std::min_element(free_at.begin(), free_at.end());
-          // mainloop chunks x products (+ a per-unit fixed cost: fill, partial store and its later reduction, in chunk units)
-          *it += (double)total_chunks / s * (ut[z0].nh == 2 ? 1.55 : 1.0) + 12.0 * ut[z0].nh;
-        }
-      const double mk = *std::max_element(free_at.begin(), free_at.end());
-      if (mk < best * 0.995) { best = mk; nsplit = s; }
-    }
-  }
-  if (nsplit > total_chunks) nsplit = total_chunks;
-  if (nsplit > 8) nsplit = 8;
   auto norm_split = [&](int s) { const int cps = (total_chunks + s - 1) / s; return (total_chunks + cps - 1) / cps; };
-  nsplit = norm_split(nsplit);
+  auto pick_split = [&](const std::vector<int>& us) -> int {
+    int ns = 1;
+    if (force_split > 0) ns = force_split;
+    else if (!us.empty()) {
+      double best = 1e30;
+      for (int s = 1; s <= 8; ++s) {
+        if (s > total_chunks) break;
+        std::vector<double> free_at(npairs, 0.0);
+        for (int z0 : us)
+          for (int z = 0; z < s; ++z) {
+            auto it = std::min_element(free_at.begin(), free_at.end());
+            // mainloop chunks x products (+ a per-unit fixed cost: fill, partial store and its later reduction, in chunk units)
+            *it += (double)total_chunks / s * (ut[z0].nh == 2 ? 1.55 : 1.0) + 12.0 * ut[z0].nh;
+          }
+        const double mk = *std::max_element(free_at.begin(), free_at.end());
+        if (mk < best * 0.995) { best = mk; ns = s; }
+      }
+    }
+    if (ns > total_chunks) ns = total_chunks;
+    if (ns > 8) ns = 8;
+    return norm_split(ns);
+  };
+  std::vector<std::vector<int>> by_bucket(nbuckets);
+  for (int ui : by_group[0]) by_bucket[tl[ut[ui].t[0]].bucket].push_back(ui);
+  std::vector<int> split_bk(nbuckets, 1);
+  for (int b = 0; b < nbuckets; ++b) split_bk[b] = pick_split(by_bucket[b]);
+  const int nsplit = split_bk[0];
   std::vector<int> split_of(ngroups + 1, nsplit);
   for (int g = 0; g < ngroups; ++g) {
     // a side launch never asks for more CTA pairs than the dgrad chain leaves free
@@ -473,17 +496,32 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   }
   {
     int t0 = 0;
-    for (int i = 0; i < ntiles; ++i) { const int s = split_of[tl[i].group + 1]; tiles[i].tile0 = t0; tiles[i].nsplit = s; t0 += s; }
+    for (int i = 0; i < ntiles; ++i) {
+      const int s = tl[i].group < 0 ? split_bk[tl[i].bucket] : split_of[tl[i].group + 1];
+      tiles[i].tile0 = t0; tiles[i].nsplit = s; t0 += s;
+    }
   }
   std::vector<TcWgUnit> units;
   int cs_rows = 0;
   plan->side.assign(ngroups, std::make_pair(0, 0));
+  plan->buckets.assign(nbuckets, TcWgGroupPlan::Bucket{0, 0, 0, 0, 0, 0});
+  // (launch order of the final group: bucket by bucket)
+  {
+    std::vector<int> ordered;
+    for (int b = 0; b < nbuckets; ++b) for (int ui : by_bucket[b]) ordered.push_back(ui);
+    by_group[0] = ordered;
+  }
   for (int gi = 0; gi <= ngroups; ++gi) {
     const int first = (int)units.size();
-    const int gs = split_of[gi];
-    const int cps = (total_chunks + gs - 1) / gs;
     for (int ui : by_group[gi]) {
       const UnitT& uu = ut[ui];
+      const int gs = gi == 0 ? split_bk[tl[uu.t[0]].bucket] : split_of[gi];
+      const int cps = (total_chunks + gs - 1) / gs;
+      if (gi == 0) {
+        TcWgGroupPlan::Bucket& bk = plan->buckets[tl[uu.t[0]].bucket];
+        if (bk.nunits == 0) bk.unit0 = (int)units.size();
+        bk.nunits += gs;
+      }
       for (int z = 0; z < gs; ++z) {
         TcWgUnit u{};
         const Tile& t0 = tl[uu.t[0]];
@@ -518,6 +556,15 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
       e.nsrc = o.nsrc;
       for (int i = 0; i < o.nsrc; ++i) { e.row0[i] = o.row0[i]; e.b_first[i] = o.b_first[i]; e.nb[i] = o.nb[i]; }
     }
+  // tiles and column-sum entries were created in job order = bucket order (side-launch jobs last: finished with the last bucket)
+  for (int b = 0; b < nbuckets; ++b) {
+    TcWgGroupPlan::Bucket& bk = plan->buckets[b];
+    bk.tile0 = ntiles; bk.ntiles = 0; bk.cs0 = (int)css.size(); bk.ncs = 0;
+    for (int i = 0; i < ntiles; ++i) if (tl[i].bucket == b) { if (bk.ntiles == 0) bk.tile0 = i; bk.ntiles++; }
+    for (int i = 0; i < (int)css.size(); ++i) if (cs_bucket[i] == b) { if (bk.ncs == 0) bk.cs0 = i; bk.ncs++; }
+    if (bk.ntiles == 0) bk.tile0 = 0;
+    if (bk.ncs == 0) bk.cs0 = 0;
+  }
   plan->nunits = (int)units.size(); plan->ntiles = ntiles; plan->ncs = (int)css.size(); plan->nsplit = nsplit;
   auto up = [&](void** d, const void* src, size_t bytes) -> bool {
     if (bytes == 0) { *d = nullptr; return true; }
@@ -562,12 +609,18 @@ static int tc_wgrad_group_launch(cudaStream_t st, const TcWgGroupPlan& plan, int
   return 0;
 }
 
-static int tc_wgrad_group_finish_launch(cudaStream_t st, const TcWgGroupPlan& plan, float l2coef) {
+// bucket < 0: every tile and column-sum entry of the plan; else those of one bucket of the final launch
+static int tc_wgrad_group_finish_launch(cudaStream_t st, const TcWgGroupPlan& plan, float l2coef, int bucket = -1) {
   TcWgFinParams f{};
   f.partial = plan.d_partial; f.cs = plan.d_cs; f.tiles = plan.d_tiles; f.ntiles = plan.ntiles; f.css = plan.d_css; f.ncs = plan.ncs;
+  if (bucket >= 0) {
+    const TcWgGroupPlan::Bucket& bk = plan.buckets[bucket];
+    f.tiles = plan.d_tiles + bk.tile0; f.ntiles = bk.ntiles; f.css = plan.d_css + bk.cs0; f.ncs = bk.ncs;
+  }
   f.l2coef = l2coef; f.B = plan.B;
+  if (f.ntiles * 64 + f.ncs <= 0) return 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(plan.ntiles * 64 + plan.ncs); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = dim3(f.ntiles * 64 + f.ncs); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr; cfg.numAttrs = tc_launch_attrs(attr, 1);
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_group_finish, f);

@@ -472,8 +472,8 @@ __global__ void cond_bias_all(const float* __restrict__ cond, int Cc, const floa
 // dWc_l[k][n] = sum_b cond[b][k] dcb_l[b][n] (+ l2coef * Wc_l[k][n]) ; dbc_l[n] = sum_b dcb_l[b][n]   (k == Cc => bias)
 __global__ void cond_wgrad_all(const float* __restrict__ cond, int Cc, const float* __restrict__ dcb, long long dcb_stride,
                                const float* __restrict__ params, float* __restrict__ grads, const int* __restrict__ offs, int B, int N,
-                               float l2coef) {
-  const int l = blockIdx.y;
+                               float l2coef, int l0) {
+  const int l = l0 + blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (Cc + 1) * N) return;
   const int k = i / N, n = i % N;

@@ -225,7 +225,7 @@ struct wn_handle {
   void* dx_all = nullptr;     // [L][rows][R]: d x_out of block l
   void* do_all = nullptr;     // [L][rows][R]: d x_out + d skip of block l (skip_channels=None with use_skip: skip = conv1 output)
   std::vector<std::vector<void*>> dp_keep;   // [block][j]: gradient wrt the output of pre-stack conv j (B,T,D)
-  struct WgPlan { int B, T; bool drop; bool sb; TcWgGroupPlan plan; };
+  struct WgPlan { int B, T; bool drop; bool sb; int nb; TcWgGroupPlan plan; };
   std::vector<WgPlan> wg_plans;
   std::vector<TcWgJobDesc> wg_jobs;   // collected by block_backward while a pass is enqueued
   int dskip_l2_last = 0;
@@ -253,6 +253,19 @@ struct wn_handle {
   // data parallelism (train.py:203): NCCL communicator of the replicas; the gradient all-reduce is the only collective
   wn_ncclComm_t comm = nullptr; bool comm_owned = false; int comm_nranks = 1, comm_rank = 0;
   int ar_in_step = 0;       // wn_train_step enqueues the all-reduce itself, behind the backward pass (inside the step graph)
+  // bucketed all-reduce (SURVEY.md 8e "overlap by launching per-bucket all-reduces"): with the stack-backward launch every filter
+  // gradient comes out of the grouped weight-gradient launch at the end of the pass; that launch runs bucket by bucket (blocks
+  // L-1 .. 0 in ar_buckets groups), and the gradients of a finished bucket are all-reduced on comm_stream while the next bucket
+  // is computed.  Only the last bucket's all-reduce (+ head, input conv, mapping) stays exposed.
+  int ar_buckets = 2;       // WN_AR_BUCKETS
+  bool ar_now = false;      // the step being enqueued all-reduces its gradients
+  long long ar_early_lo = -1, ar_early_hi = -1;   // scalars [lo, hi) of the flat buffer already all-reduced by model_backward
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_bucket[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_comm_done = nullptr;
+  int wg_cur_bucket = 0;
+  int last_ar_buckets = 0;        // gradient slices the last training step all-reduced EARLY (beside the next bucket's kernels)
+  bool cond_wgrad_done = false;   // the per-bucket launches of this pass already wrote the conditioning filter gradients
 };
 
 enum { CLS_DILATED = 1, CLS_GEMM = 2, CLS_LOSS = 3, CLS_MISC = 4 };
@@ -604,12 +617,12 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   if (c.precision == WN_BF16) {
     int r = tc_check_config(h->R, h->D, h->Sp, c.kernel_size);
     if (r != 0) {
-      set_err("bf16/tcgen05 tier needs channels, dilation_channels and skip_channels to be multiples of 64 (got R=%d D=%d S=%d); use precision=fp32", h->R, h->D, h->Sp);
+      set_err("bf16/tcgen05 tier needs channels, dilation_channels and skip_channels to be multiples of 32 (got R=%d D=%d S=%d); use precision=fp32", h->R, h->D, h->Sp);
       delete h;
       return WN_ERR_UNSUPPORTED;
     }
     for (auto& hc : h->head)
-      if (hc.cin % 64 != 0) { set_err("bf16 tier needs head widths that are multiples of 64"); delete h; return WN_ERR_UNSUPPORTED; }
+      if (hc.cin % 32 != 0) { set_err("bf16 tier needs head widths that are multiples of 32"); delete h; return WN_ERR_UNSUPPORTED; }
   }
 
   // ---- grouped weight gradients: bf16 tier, separate skip projection (or none), widths in whole 256-channel pair tiles
@@ -671,6 +684,10 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_TC_DSKIP_LAST"); if (e) h->dskip_l2_last = atoi(e); }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_wg_side, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&h->ev_bucket[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_comm_done, cudaEventDisableTiming);
+  { const char* e = getenv("WN_AR_BUCKETS"); if (e) { h->ar_buckets = atoi(e); if (h->ar_buckets < 1) h->ar_buckets = 1; if (h->ar_buckets > 8) h->ar_buckets = 8; } }
   for (int i = 0; i < h->L; ++i) {
     cudaEvent_t a, b2, c2;
     cudaEventCreateWithFlags(&a, cudaEventDisableTiming); cudaEventCreateWithFlags(&b2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c2, cudaEventDisableTiming);
@@ -709,6 +726,9 @@ extern "C" void wn_destroy(wn_handle* h) {
   for (auto e : h->ev_blk_done) cudaEventDestroy(e);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_wg_side) cudaEventDestroy(h->ev_wg_side);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  for (int i = 0; i < 8; ++i) if (h->ev_bucket[i]) cudaEventDestroy(h->ev_bucket[i]);
+  if (h->ev_comm_done) cudaEventDestroy(h->ev_comm_done);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   for (void* a : h->gen.allocs) cudaFree(a);
@@ -1469,7 +1489,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         j.A = (const bf16*)g_l; j.lda = D; j.cin = D; j.ntaps = 1; j.shift[0] = 0;
         j.G = (const bf16*)d_o; j.ldg = ld_o; j.N = R;
         j.dst = G_(h, b.conv1.w_idx); j.w = l2 ? P_(h, b.conv1.w_idx) : nullptr; j.bias = G_(h, b.conv1.b_idx);
-        j.group = h->wg_cur_group;
+        j.group = h->wg_cur_group; j.bucket = h->wg_cur_bucket;
         h->wg_jobs.push_back(j);
       } else {
         unused_conv_grads(h, st, b.conv1.w_idx, b.conv1.b_idx, l2coef);
@@ -1480,7 +1500,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
           j.A = (const bf16*)g_l; j.lda = D; j.cin = D; j.ntaps = 1; j.shift[0] = 0;
           j.G = (const bf16*)dskip; j.ldg = ldsk; j.N = S;
           j.dst = G_(h, b.conv_skip.w_idx); j.w = l2 ? P_(h, b.conv_skip.w_idx) : nullptr; j.bias = G_(h, b.conv_skip.b_idx);
-          j.group = h->wg_cur_group;
+          j.group = h->wg_cur_group; j.bucket = h->wg_cur_bucket;
           h->wg_jobs.push_back(j);
         } else {
           unused_conv_grads(h, st, b.conv_skip.w_idx, b.conv_skip.b_idx, l2coef);
@@ -1565,7 +1585,7 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         jd.G = (const bf16*)dcur; jd.ldg = dcw; jd.N = c.cout;
         jd.dst = G_(h, c.w_idx); jd.w = h->cfg.l2_reg_factor > 0.f ? P_(h, c.w_idx) : nullptr; jd.bias = G_(h, c.b_idx);
         if (j == depth - 1 && b.has_cond) { jd.per_batch = h->dcb + (size_t)l * h->maxB * 2 * D; jd.ldpb = 2 * D; }
-        jd.group = h->wg_cur_group;
+        jd.group = h->wg_cur_group; jd.bucket = h->wg_cur_bucket;
         h->wg_jobs.push_back(jd);
       }
     } else {
@@ -1632,13 +1652,13 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
 
 // conditioning adjoint: dWc_l, dbc_l from dcb; dcond = sum_l dcb_l Wc_l^T; then the mapping MLP
 static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, const float* cond, int B, int l0, int nl, bool run_mapping, float* dcond_out,
-                         float l2coef) {
+                         float l2coef, bool skip_wgrad = false) {
   const int n = 2 * h->D;
   if (l0 == 0 && nl == h->L) {
-    {
+    if (!skip_wgrad) {
       LaunchScope ls(h, st, CLS_MISC);
       cond_wgrad_all<<<dim3(cdiv((h->Cc + 1) * n, 128), h->L), 128, 0, st>>>(cond, h->Cc, h->dcb, (long long)h->maxB * n, h->d_params, h->d_grads,
-                                                                          h->d_cond_offsets, B, n, l2coef);
+                                                                          h->d_cond_offsets, B, n, l2coef, 0);
     }
     {
       LaunchScope ls(h, st, CLS_MISC);
@@ -1742,8 +1762,20 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     if (side_pairs < 6) side_pairs = 0;
   }
   auto side_group_of = [&](int l) -> int { return (side_pairs > 0 && (h->L - 1 - l) % h->wg_side_every == 0) ? (h->L - 1 - l) / h->wg_side_every : -1; };
+  // bucketed all-reduce: only with the stack-backward launch (every SM busy until the chain ends, all filter gradients in the
+  // final grouped launch) and a communicator that reduces inside this step
+  const int nb = (group && sb_ok && h->ar_now && h->prof_tag == 0 && h->comm_stream != nullptr) ? std::min(std::min(h->ar_buckets, h->L), 8) : 1;
+  auto bucket_of = [&](int l) -> int { return nb > 1 ? ((h->L - 1 - l) * nb) / h->L : 0; };
+  auto block_off = [&](int l) -> long long {
+    if (l < h->L) return h->params[h->blocks[l].stack[0].w_idx].offset;
+    if (!h->head.empty()) return h->params[h->head[0].w_idx].offset;
+    if (!h->map_w.empty()) return h->params[h->map_w[0]].offset;
+    return h->n_scalars;
+  };
+  h->ar_early_lo = h->ar_early_hi = -1;
+  h->last_ar_buckets = 0;
   TcWgGroupPlan* wplan = nullptr;
-  if (group) for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active && wp.sb == sb_ok) wplan = &wp.plan;
+  if (group) for (auto& wp : h->wg_plans) if (wp.B == B && wp.T == Tn && wp.drop == h->drop_active && wp.sb == sb_ok && wp.nb == nb) wplan = &wp.plan;
   const bool side_now = wplan != nullptr && side_pairs > 0 && h->prof_tag == 0 && !wplan->side.empty();
   g_tc_balance = side_now ? 1 : 0;
   // ---- head
@@ -1765,7 +1797,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
         j.A = (const bf16*)a_in; j.lda = a_w; j.cin = hc.cin; j.ntaps = 1; j.shift[0] = 0;
         j.G = (const bf16*)dcur; j.ldg = dw; j.N = hc.cout;
         j.dst = G_(h, hc.w_idx); j.w = c.l2_reg_factor > 0.f ? P_(h, hc.w_idx) : nullptr; j.bias = G_(h, hc.b_idx);
-        j.group = -1;
+        j.group = -1; j.bucket = nb - 1;      // (the head's gradients travel with the last bucket)
         h->wg_jobs.push_back(j);
         head_grouped = true;
       }
@@ -1875,6 +1907,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       void* dx_in = group ? (l > 0 ? dx_of(l - 1) : h->dxA) : ((dxout == h->dxA) ? h->dxB : h->dxA);
       BwdSide sd; const BwdSide* sdp = side_setup(h, st, l, use_side, &sd);
       h->wg_cur_group = side_group_of(l);
+      h->wg_cur_bucket = bucket_of(l);
       RET(block_backward<T>(h, st, l, x_in, dxout, h->R, dskip, h->Sp, dx_in, h->R, B, Tn, l2coef, group ? dz_of(l) : ((l & 1) ? h->dz2 : h->dz), sdp,
                             group, stacked));
       if constexpr (sizeof(T) == 2) {
@@ -1891,7 +1924,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       }
       dxout = dx_in;
     }
-    h->wg_cur_group = -1;
+    h->wg_cur_group = -1; h->wg_cur_bucket = 0;
     ld_dx = h->R;
   }
   g_tc_balance = 0;
@@ -1944,11 +1977,54 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
           for (auto& wp : h->wg_plans) wp.plan.release();
           h->wg_plans.clear();
         }
-        h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, sb_ok, TcWgGroupPlan{}});
+        h->wg_plans.push_back(wn_handle::WgPlan{B, Tn, h->drop_active, sb_ok, nb, TcWgGroupPlan{}});
         plan = &h->wg_plans.back().plan;
         int r = tc_wgrad_group_build(h->tmaps, h->wg_jobs, B, Tn, h->wg_force_split, h->wg_pair_tiles != 0, side_pairs, plan);
         if (r != 0) { h->wg_plans.pop_back(); set_err("grouped wgrad plan failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
       }
+      bool cond_wgrad_done = false;
+      if (nb > 1 && (int)plan->buckets.size() == nb && !side_now) {
+        // ---- bucket by bucket: launch, finish, (conditioning filter gradients of the bucket's blocks,) all-reduce on comm_stream
+        struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, "wgrad_group");
+        h->wg_last_tiles = plan->ntiles; h->wg_last_partials = plan->npartial;
+        for (int k = 0; k < nb; ++k) {
+          const TcWgGroupPlan::Bucket& bk = plan->buckets[k];
+          {
+            LaunchScope ls(h, st, CLS_DILATED);
+            int r = tc_wgrad_group_launch(st, *plan, bk.unit0, bk.nunits);
+            if (r != 0) { set_err("grouped wgrad launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+          }
+          {
+            OuterLabel ol(h, "wgrad_group_finish");
+            LaunchScope ls(h, st, CLS_DILATED);
+            int r = tc_wgrad_group_finish_launch(st, *plan, l2coef, k);
+            if (r != 0) { set_err("grouped wgrad finish failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
+          }
+          // blocks of this bucket: l_hi .. l_lo (descending walk: bucket 0 holds the last blocks)
+          int l_lo = h->L, l_hi = -1;
+          for (int l = 0; l < h->L; ++l) if (bucket_of(l) == k) { if (l < l_lo) l_lo = l; if (l > l_hi) l_hi = l; }
+          if (c.conditioning && l_hi >= l_lo) {
+            OuterLabel ol(h, "cond_bwd");
+            LaunchScope ls(h, st, CLS_MISC);
+            const int n = 2 * h->D;
+            cond_wgrad_all<<<dim3(cdiv((h->Cc + 1) * n, 128), l_hi - l_lo + 1), 128, 0, st>>>(h->last_cond, h->Cc, h->dcb, (long long)h->maxB * n, h->d_params,
+                                                                                         h->d_grads, h->d_cond_offsets, B, n, l2coef, l_lo);
+          }
+          if (k + 1 < nb && l_hi >= l_lo) {
+            // every gradient of blocks l_lo .. l_hi is final: reduce that slice of the flat buffer beside the next bucket's kernels
+            const long long lo = block_off(l_lo), hi = block_off(l_hi + 1);
+            CK(cudaEventRecord(h->ev_bucket[k], st));
+            CK(cudaStreamWaitEvent(h->comm_stream, h->ev_bucket[k], 0));
+            h->launches++;
+            const int r = g_nccl.AllReduce(h->d_grads + lo, h->d_grads + lo, (size_t)(hi - lo), WN_NCCL_FLOAT32, WN_NCCL_SUM, h->comm, h->comm_stream);
+            if (r != 0) { set_err("ncclAllReduce (bucket %d) failed (%d): %s", k, r, nccl_errstr(r)); return WN_ERR_CUDA; }
+            h->last_ar_buckets++;
+            if (h->ar_early_lo < 0 || lo < h->ar_early_lo) h->ar_early_lo = lo;
+            if (hi > h->ar_early_hi) h->ar_early_hi = hi;
+          }
+        }
+        cond_wgrad_done = c.conditioning != 0;
+      } else
       {
         struct Label { wn_handle* h; Label(wn_handle* h_, const char* l) : h(h_) { h->cur_label = l; } ~Label() { h->cur_label = "misc"; } } lab(h, "wgrad_group");
         {
@@ -1971,12 +2047,14 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
           if (r != 0) { set_err("grouped wgrad finish failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
         }
       }
+      h->cond_wgrad_done = cond_wgrad_done;
     }
   }
   // join: every side-stream wgrad (and its finish kernel) is complete before anything below reads the gradients
   if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
   if (!input_conv_done) input_conv_bwd(st);
-  if (c.conditioning) { OuterLabel ol(h, "cond_bwd"); RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef)); }
+  if (c.conditioning) { OuterLabel ol(h, "cond_bwd"); RET(cond_backward(h, st, cond_in, h->last_cond, B, 0, h->L, true, h->dcond, l2coef, h->cond_wgrad_done)); }
+  h->cond_wgrad_done = false;
   return WN_OK;
 }
 
@@ -2415,6 +2493,23 @@ extern "C" int wn_loss_fn(wn_handle* h, const void* target_dev, int target_is_in
 // (model.py:328), so the replicas' gradients are SUMMED — one ncclAllReduce over the flat fp32 buffer, in place
 static int allreduce_grads(wn_handle* h, cudaStream_t st) {
   if (!h->comm) { set_err("no communicator: call wn_comm_init / wn_comm_attach first"); return WN_ERR_STATE; }
+  if (h->ar_early_lo >= 0 && h->ar_early_hi > h->ar_early_lo) {
+    // model_backward already reduced scalars [lo, hi) on comm_stream, bucket by bucket: join, then the two slices around them
+    const long long lo = h->ar_early_lo, hi = h->ar_early_hi;
+    h->ar_early_lo = h->ar_early_hi = -1;
+    CK(cudaEventRecord(h->ev_comm_done, h->comm_stream));
+    CK(cudaStreamWaitEvent(st, h->ev_comm_done, 0));
+    g_nccl.GroupStart();
+    int r = 0;
+    if (lo > 0) { h->launches++; r = g_nccl.AllReduce(h->d_grads, h->d_grads, (size_t)lo, WN_NCCL_FLOAT32, WN_NCCL_SUM, h->comm, st); }
+    if (r == 0 && hi < h->n_scalars) {
+      h->launches++;
+      r = g_nccl.AllReduce(h->d_grads + hi, h->d_grads + hi, (size_t)(h->n_scalars - hi), WN_NCCL_FLOAT32, WN_NCCL_SUM, h->comm, st);
+    }
+    const int r2 = g_nccl.GroupEnd();
+    if (r != 0 || r2 != 0) { set_err("ncclAllReduce failed (%d): %s", r != 0 ? r : r2, nccl_errstr(r != 0 ? r : r2)); return WN_ERR_CUDA; }
+    return WN_OK;
+  }
   h->launches++;
   const int r = g_nccl.AllReduce(h->d_grads, h->d_grads, (size_t)h->n_scalars, WN_NCCL_FLOAT32, WN_NCCL_SUM, h->comm, st);
   if (r != 0) { set_err("ncclAllReduce failed (%d): %s", r, nccl_errstr(r)); return WN_ERR_CUDA; }
@@ -2486,8 +2581,10 @@ static int step_entry(wn_handle* h, const float* frames, const float* cond, int 
   RET(loss_forward<T>(h, st, frames, B, Tn, scale, train, nullptr, loss));
   if (train) {
     const float l2coef = h->cfg.l2_reg_factor > 0.f ? 2.0f * h->cfg.l2_reg_factor / (float)nrep : 0.f;
+    h->ar_now = h->ar_in_step && h->comm && h->comm_nranks > 1 && nrep > 1;
     RET(model_backward<T>(h, st, frames, Tn + 1, cond, B, Tn, l2coef));
-    if (h->ar_in_step && h->comm && h->comm_nranks > 1 && nrep > 1) RET(allreduce_grads(h, st));
+    if (h->ar_now) RET(allreduce_grads(h, st));
+    h->ar_now = false;
   }
   return WN_OK;
 }
@@ -2822,6 +2919,7 @@ extern "C" int64_t wn_last_launch_count(const wn_handle* h) { return h ? h->laun
 extern "C" int wn_fused_forward_blocks(const wn_handle* h) { return h ? h->fused_fwd_launches : 0; }
 extern "C" int wn_stack_forward_layers(const wn_handle* h) { return h ? h->stack_fwd_layers : 0; }
 extern "C" int wn_stack_backward_layers(const wn_handle* h) { return h ? h->stack_bwd_layers : 0; }
+extern "C" int wn_allreduce_buckets(const wn_handle* h) { return h ? h->last_ar_buckets : 0; }
 extern "C" int wn_grouped_wgrad_tiles(const wn_handle* h, int* side_launches) {
   if (side_launches) *side_launches = h ? h->wg_last_side : 0;
   return h ? h->wg_last_tiles : 0;
