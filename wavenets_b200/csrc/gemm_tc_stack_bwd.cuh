@@ -54,6 +54,7 @@ struct TcStackBwdParams {
   int kb_dx, kb_ds;           // 64-wide k blocks of the DG contraction over d x_out (R) and d skip (S)
   unsigned long long pol_dx, pol_ds, pol_w, pol_z, pol_dz_ld, pol_dz_st, pol_o;
   float drop_scale;           // 1 / (1 - rate)
+  int band, nbands;           // tile order: bands of `band` m tiles (the last one may be shorter); within a band all layers, last to first
 };
 
 template <int D_, int R_> struct TcStackBwdCfg {
@@ -109,10 +110,23 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
   const int total_tiles = p.L * p.num_mtiles;
   const int n_tiles = tile_first < total_tiles ? (total_tiles - tile_first + tile_stride - 1) / tile_stride : 0;
 
-  // tile id -> (layer, m tile): layers from the last to the first, the tiles of a sequence in descending time order
+  // tile id -> (layer, m tile).  Within a layer the tiles of a sequence run in descending time order (the anti-causal taps read
+  // d z of LATER rows).  The m tiles are cut into bands: a band walks all layers, last to first, before the next band starts, so
+  // that what a tile re-reads — d skip of its rows (the same for every layer) and d x_out written one layer earlier — was touched
+  // `band` tiles ago instead of `num_mtiles` tiles ago and is still in L2 (layer-major order: 50 % L2 hit rate, 4.9 GB read from
+  // DRAM per C2 pass against 2 GB of cached P, Q; bands of 128: 3.5 GB).  Dependencies still point to smaller ids: (l + 1, m)
+  // earlier in the same band, (l, m') with m' < m in the same band or in an earlier one.
   auto locate = [&](int j, int& ly, int& mt, int& b, int& tb) {
     const int gt = tile_first + j * tile_stride;
-    const int lr = gt / p.num_mtiles, mr = gt - lr * p.num_mtiles;
+    const int full = (p.nbands - 1) * p.band * p.L;      // tiles of the bands in front of the last one
+    int lr, mr;
+    if (gt < full) {
+      const int k = gt / (p.band * p.L), r = gt - k * (p.band * p.L);
+      lr = r / p.band; mr = k * p.band + (r - lr * p.band);
+    } else {
+      const int wl = p.num_mtiles - (p.nbands - 1) * p.band, r = gt - full;
+      lr = r / wl; mr = (p.nbands - 1) * p.band + (r - lr * wl);
+    }
     ly = p.L - 1 - lr;
     b = mr / p.tiles_t;
     tb = p.tiles_t - 1 - (mr - b * p.tiles_t);
@@ -634,6 +648,21 @@ static int tc_stack_bwd_launch_t(cudaStream_t st, const TcStackBwdPlan& plan, co
   }
   const int pairs = tc_num_sms() / 2;
   if (p.num_mtiles <= pairs) return -100;
+  {
+    // bands of ~WN_TC_SB_BAND m tiles (default 128; 0: one band = layer-major order), every band longer than the launch has pairs
+    // (a tile then never waits for a tile of the round its own pair is in).
+    // (Tried and dropped: issuing DG of a pair's next tile between the un-shifted and the shifted taps of the current one, to
+    // fill the d z round trip through L2 — the OUT epilogue then no longer runs under those DG products: 1.79 -> 2.03 ms.)
+    static int band_target = -1;
+    if (band_target < 0) { const char* e = getenv("WN_TC_SB_BAND"); band_target = e ? atoi(e) : 128; }
+    int nb = band_target > 0 ? p.num_mtiles / band_target : 1;
+    if (nb < 1) nb = 1;
+    for (; nb > 1; --nb) {
+      const int bw = (p.num_mtiles + nb - 1) / nb;
+      if (bw > pairs && p.num_mtiles - (nb - 1) * bw > pairs) break;
+    }
+    p.nbands = nb; p.band = (p.num_mtiles + nb - 1) / nb;
+  }
   {
     // every CTA pair of the launch must be resident at the same time (tiles wait for tiles of other pairs)
     static int max_clusters = -1;
