@@ -684,7 +684,16 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_TC_DSKIP_LAST"); if (e) h->dskip_l2_last = atoi(e); }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_wg_side, cudaEventDisableTiming);
-  cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
+  {
+    // highest priority: the blocks of an early bucket's all-reduce must be scheduled as soon as CTAs of the running weight-gradient
+    // launch retire, not behind the CTAs that launch still has pending (measured at 8 GPUs: without it the overlap won 0.02 ms)
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
+    }
+  }
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&h->ev_bucket[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_comm_done, cudaEventDisableTiming);
   { const char* e = getenv("WN_AR_BUCKETS"); if (e) { h->ar_buckets = atoi(e); if (h->ar_buckets < 1) h->ar_buckets = 1; if (h->ar_buckets > 8) h->ar_buckets = 8; } }
