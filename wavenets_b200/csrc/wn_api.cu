@@ -258,6 +258,7 @@ struct wn_handle {
   // L-1 .. 0 in ar_buckets groups), and the gradients of a finished bucket are all-reduced on comm_stream while the next bucket
   // is computed.  Only the last bucket's all-reduce (+ head, input conv, mapping) stays exposed.
   int ar_buckets = 2;       // WN_AR_BUCKETS
+  int ar_first_pct = 70;    // WN_AR_FIRST: share of the blocks in the first of two buckets
   bool ar_now = false;      // the step being enqueued all-reduces its gradients
   long long ar_early_lo = -1, ar_early_hi = -1;   // scalars [lo, hi) of the flat buffer already all-reduced by model_backward
   cudaStream_t comm_stream = nullptr;
@@ -696,6 +697,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   }
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&h->ev_bucket[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_comm_done, cudaEventDisableTiming);
+  { const char* e = getenv("WN_AR_FIRST"); if (e) { h->ar_first_pct = atoi(e); if (h->ar_first_pct < 10) h->ar_first_pct = 10; if (h->ar_first_pct > 90) h->ar_first_pct = 90; } }
   { const char* e = getenv("WN_AR_BUCKETS"); if (e) { h->ar_buckets = atoi(e); if (h->ar_buckets < 1) h->ar_buckets = 1; if (h->ar_buckets > 8) h->ar_buckets = 8; } }
   for (int i = 0; i < h->L; ++i) {
     cudaEvent_t a, b2, c2;
@@ -1774,7 +1776,13 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   // bucketed all-reduce: only with the stack-backward launch (every SM busy until the chain ends, all filter gradients in the
   // final grouped launch) and a communicator that reduces inside this step
   const int nb = (group && sb_ok && h->ar_now && h->prof_tag == 0 && h->comm_stream != nullptr) ? std::min(std::min(h->ar_buckets, h->L), 8) : 1;
-  auto bucket_of = [&](int l) -> int { return nb > 1 ? ((h->L - 1 - l) * nb) / h->L : 0; };
+  // two buckets: the first (last blocks, reduced beside the second bucket's kernels) takes ar_first_pct of the blocks — what stays
+  // exposed behind the pass is the second bucket's slice, so it is the smaller one; more buckets: equal groups
+  auto bucket_of = [&](int l) -> int {
+    if (nb <= 1) return 0;
+    if (nb == 2) return (h->L - 1 - l) * 100 < h->L * h->ar_first_pct ? 0 : 1;
+    return ((h->L - 1 - l) * nb) / h->L;
+  };
   auto block_off = [&](int l) -> long long {
     if (l < h->L) return h->params[h->blocks[l].stack[0].w_idx].offset;
     if (!h->head.empty()) return h->params[h->head[0].w_idx].offset;
@@ -1963,7 +1971,10 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       reduce_parts_tall<<<cdiv(h->R, 32), 256, 0, s_>>>(h->colpart + kr, nparts, (long long)(h->K + 1) * h->R, G_(h, h->input_conv.b_idx), h->R, nullptr, 0.f);
     }
   };
-  if (side_now) {
+  // (the stack-backward path has no side launches, but the same trick applies: d h0 is final behind the chain launch, and the
+  // three small launches run beside the grouped weight-gradient launch instead of behind it)
+  const bool icb_side = !side_now && h->stack_bwd_layers > 0 && h->use_side && h->side_stream != nullptr && h->prof_tag == 0 && group && !h->wg_jobs.empty();
+  if (side_now || icb_side) {
     CK(cudaEventRecord(h->ev_blk_in[0], st));
     CK(cudaStreamWaitEvent(h->side_stream, h->ev_blk_in[0], 0));
     input_conv_bwd(h->side_stream);
@@ -2058,6 +2069,11 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
       }
       h->cond_wgrad_done = cond_wgrad_done;
     }
+  }
+  if (icb_side) {
+    // join: the input conv's gradients are part of what the all-reduce behind this pass (and the caller) reads
+    CK(cudaEventRecord(h->ev_wg_side, h->side_stream));
+    CK(cudaStreamWaitEvent(st, h->ev_wg_side, 0));
   }
   // join: every side-stream wgrad (and its finish kernel) is complete before anything below reads the gradients
   if (use_side) CK(cudaStreamWaitEvent(st, h->ev_blk_done[0], 0));
@@ -2436,10 +2452,10 @@ extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int 
 static void draw_dropout_masks(wn_handle* h, cudaStream_t st, int B, int Tn) {
   if (!h->drop_active || h->drop_injected) return;
   const size_t rows_cap = (size_t)h->maxB * h->maxT;
-  const long long n4 = ((long long)B * Tn * h->R + 3) / 4;
+  const long long n8 = ((long long)B * Tn * h->R + 7) / 8;     // (the slabs are 16-byte aligned and padded: a last partial group stays inside)
   { LaunchScope ls(h, st, CLS_MISC); dropout_step_bump<<<1, 1, 0, st>>>(h->d_drop_ctr); }
   LaunchScope ls(h, st, CLS_MISC);
-  dropout_mask_philox<<<dim3(cdiv(n4, 256), h->L), 256, 0, st>>>(h->drop_mask, n4, (long long)rows_cap * h->R, h->cfg.dropout, h->drop_seed,
+  dropout_mask_philox<<<dim3(cdiv(n8, 256), h->L), 256, 0, st>>>(h->drop_mask, n8, (long long)rows_cap * h->R, h->cfg.dropout, h->drop_seed,
                                                                 h->d_drop_ctr);
 }
 
