@@ -142,6 +142,53 @@ def test_stack_forward_multi_dilation_equals_per_block_launches():
       assert np.array_equal(a[i][1][k], b[i][1][k]), (k, i)
 
 
+def test_stack_backward_multi_dilation_vs_per_block_chain_and_oracle():
+  """Blocks with several dilated convs in the persistent stack-BACKWARD launch: the convs in front of the gated conv are plain
+  layers (one OUT-type tile, all taps from L2, activation adjoint from the cached output of the conv in front; the residual
+  gradient joins at the block's first conv).  Against the per-block chain (bf16 storage error: different fp32 summation order)
+  and against the bf16-faithful oracle (every gradient tensor)."""
+  from oracle import faithful
+  from oracle import wavenet_oracle as wo
+  from tests.util import device_slope_masks, oracle_config, rel_l2
+  from wavenets_b200 import WaveNet
+  kw = dict(channels=256, blocks=3, layers_per_block=3, dilation_bound=32, skip_channels=256, final_layers_channels=[128], activation='leaky_relu')
+  B, T = 3, 6500
+  cfg = oracle_config(kw, 0)
+  p = wo.init_params(cfg, seed=1)
+  x, _ = make_inputs(B, T, 0)
+
+  def run(env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+      m = WaveNet(**kw, precision='bf16')
+      m.build(x[:, :-1].shape)
+      m.set_weights({k: v.astype(np.float32) for k, v in p.items()})
+      for _ in range(3):
+        out = m.train_step(x)
+      return m, out['loss'], m.get_grads(), int(m.handle.lib.wn_stack_backward_layers(m.handle.h))
+    finally:
+      for k, v in old.items():
+        if v is None:
+          os.environ.pop(k, None)
+        else:
+          os.environ[k] = v
+
+  m_a, l_a, g_a, n_a = run({})
+  m_b, l_b, g_b, n_b = run({'WN_TC_STACK_BWD': '0'})
+  assert n_a == 3 and n_b == 0
+  assert l_a == l_b
+  worst = max(rel_l2(g_a[k], g_b[k]) for k in g_b if np.linalg.norm(g_b[k]) > 0)
+  print(f'multi-dilation stack backward vs per-block chain: worst gradient tensor rel-L2 {worst:.2e}')
+  assert worst < 5e-3
+  p32 = {k: v.astype(np.float32).astype(np.float64) for k, v in p.items()}
+  l_f, g_f = faithful.train_step(p32, cfg, x, None, faithful=True, slope_masks=device_slope_masks(m_a, kw, B, T))
+  assert abs(l_a - l_f) <= 5e-5 * abs(l_f)
+  worst_f = max((rel_l2(g_a[k], g_f[k]), k) for k in g_f if np.linalg.norm(g_f[k]) > 0)
+  print(f'multi-dilation stack backward vs bf16-faithful oracle: worst gradient tensor {worst_f}')
+  assert worst_f[0] < 8e-3, worst_f
+
+
 def test_plan_cache_eviction_keeps_results():
   """More (B, T) shapes than the handle caches plans for (4): the grouped-wgrad / stack-forward plans and the CUDA graphs that
   hold pointers into them are dropped and rebuilt; every shape reproduces its first result bit for bit."""

@@ -46,6 +46,12 @@ struct alignas(128) TcStackBwdLayer {
   int has_dx, has_ds, has_res;
   int wait_dx;                // d x_out_l is written by this launch (every block but the last): acquire its tile flag first
   const uint8_t* mask;        // dropout keep-mask of this block's conv branch [b*T+t][R], or null
+  // multi-dilation blocks (layers.py:64-88): a "layer" of the launch is one CONV.  kind 0 = the block's gated conv (DG tile +
+  // gate adjoint + OUT tile), kind 1 = a plain conv in front of it: one OUT-type tile whose taps ALL come from L2 (tmDZ = the
+  // gradient wrt this conv's output, written by layer + 1 of this launch; kb_tap 64-wide k blocks per tap).
+  // OUT epilogue: out_mode 1 adds the residual gradient (tmDXp = d x_out of the block, guarded by flags_dx[in_flag_layer] when
+  // >= 0), out_mode 2 multiplies by act'(y) of the conv in front (tmDXp = its cached bf16 output), 0 neither.
+  int kind, out_mode, act, kb_tap, in_flag_layer;
 };
 
 struct TcStackBwdParams {
@@ -170,6 +176,29 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         locate(j, ly, mt, b, tb);
         const TcStackBwdLayer& Ly = layers[ly];
         const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+        if (Ly.kind) {
+          // ---- plain conv: every tap reads the gradient wrt this conv's output, tiles of layer + 1 of this launch
+          for (int s = 0; s < p.nseg; ++s) {
+            const int lo = tb * (2 * Cfg::BM) + Ly.shift[s];
+            const int t_lo = lo / (2 * Cfg::BM);
+            int t_hi = (lo + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
+            if (t_hi > p.tiles_t - 1) t_hi = p.tiles_t - 1;
+            SBT(0)
+            for (int tt = t_lo; tt <= t_hi; ++tt) wait_flag(flags_dx + (size_t)(ly + 1) * p.num_mtiles + b * p.tiles_t + tt, ly + 1, b * p.tiles_t + tt);
+            SBT(1)
+          }
+          fence_proxy_async_global();
+          for (int s = 0; s < p.nseg; ++s)
+            for (int kb = 0; kb < Ly.kb_tap; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WB_BYTES));
+              tma_load_3d_pair_h(sa, &Ly.tmDZ, &full_bar[stage], kb * 64, t0 + Ly.shift[s], b, p.pol_dz_ld);
+              tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmWb, &full_bar[stage], (s * Ly.kb_tap + kb) * 64, (int)crank * (R_ / 2), p.pol_w);
+              next();
+            }
+          continue;
+        }
         // ---- DG: [d x_out | d skip] . Wdg
         if (Ly.has_dx) {
           if (Ly.wait_dx) {
@@ -245,6 +274,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       const uint32_t t_dg = tmem_base, t_out = tmem_base + 256u;
       int stage = 0; uint32_t phase = 0;
       uint32_t n_sf[2] = {0u, 0u};       // completed waits on slab_full[ps]
+      uint32_t ng = 0u;                  // gated tiles so far
       SBT_DECL(10)
       auto kstep = [&](uint32_t d_tmem, uint32_t idesc, bool a_from_dz, int slot, bool first, uint64_t* extra0, uint64_t* extra1) {
 #ifdef TC_TIMELINE
@@ -275,9 +305,21 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         locate(j, ly, mt, b, tb);
         const TcStackBwdLayer& Ly = layers[ly];
         const uint32_t par = (uint32_t)(j & 1);
+        if (Ly.kind) {
+          // ---- plain conv: one OUT-type tile, all k-steps from the ring
+          SBT(2)
+          mbar_wait(out_empty, par ^ 1);
+          SBT(3)
+          tc_fence_after();
+          const int ks_p = p.nseg * Ly.kb_tap;
+          for (int ks = 0; ks < ks_p; ++ks) kstep(t_out, idesc_o, false, 0, ks == 0, ks == ks_p - 1 ? out_full : nullptr, nullptr);
+          SBT(7)
+          continue;
+        }
+        const uint32_t gpar = ng & 1u; ++ng;      // the DG accumulator hand-shakes count gated tiles only
         // ---- DG
         SBT(0)
-        mbar_wait(dg_empty, par ^ 1);
+        mbar_wait(dg_empty, gpar ^ 1);
         SBT(1)
         tc_fence_after();
         const int ks_dg = (Ly.has_dx ? p.kb_dx : 0) + (Ly.has_ds ? p.kb_ds : 0);
@@ -330,6 +372,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       locate(j, ly, mt, b, tb);
       const TcStackBwdLayer& Ly = layers[ly];
       const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+      if (!Ly.kind) {
       for (int pr = 0; pr < NPAIR; ++pr) {
         const int ps = pr & 1;
         named_bar_sync(8 + ps, NEPI * 32 + 32);
@@ -342,6 +385,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       }
       if (lane == 0) publish(flags_dz + (size_t)ly * p.num_mtiles + mt);
       __syncwarp();
+      }
       for (int step = 0; step < R_ / 32; ++step) {
         named_bar_sync(3 + oslot, NEPI * 32 + 32);
         if (lane == 0) {
@@ -364,6 +408,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         locate(j, ly, mt, b, tb);
         const TcStackBwdLayer& Ly = layers[ly];
         const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+        if (!Ly.kind)
         for (int step = 0; step < D_ / 32; ++step) {
           mbar_wait(&in_empty[islot], iphase ^ 1);
           mbar_expect_tx(&in_full[islot], 2u * Cfg::PANEL);
@@ -372,10 +417,11 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           tma_load_3d_h(dst + Cfg::PANEL, &Ly.tmZs, &in_full[islot], step * 32, t0, b, p.pol_z);
           if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
         }
-        if (Ly.has_dx && Ly.has_res) {
-          // residual gradient: d x_out_l panels for the OUT epilogue (one panel per slot)
-          if (Ly.wait_dx) {
-            wait_flag(flags_dx + (size_t)(ly + 1) * p.num_mtiles + mt, ly + 1, mt);      // (long set: the operand producer waited for it before DG)
+        if (Ly.out_mode) {
+          // OUT epilogue input, one panel per slot: the residual gradient d x_out of the block, or the cached output of the conv in
+          // front (activation adjoint)
+          if (Ly.in_flag_layer >= 0) {
+            wait_flag(flags_dx + (size_t)Ly.in_flag_layer * p.num_mtiles + mt, Ly.in_flag_layer, mt);      // (long set, by transitivity of the operand waits)
             fence_proxy_async_global();
           }
           for (int step = 0; step < R_ / 32; ++step) {
@@ -391,13 +437,15 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     // ===================== pair hand-off of the d z slabs =====================
     if (lane == 0) {
       uint32_t n_sd[2] = {0u, 0u};
-      for (int j = 0; j < n_tiles; ++j)
+      for (int j = 0; j < n_tiles; ++j) {
+        { int ly, mt, b, tb; locate(j, ly, mt, b, tb); if (layers[ly].kind) continue; }
         for (int pr = 0; pr < NPAIR; ++pr) {
           const int ps = pr & 1;
           mbar_wait(&slab_done[ps], n_sd[ps] & 1u); ++n_sd[ps];
           if (leader) mbar_arrive(&slab_full[ps]);
           else mbar_arrive_remote(&slab_full[ps], 0u);
         }
+      }
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue =====================
@@ -413,23 +461,26 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     int islot = 0; uint32_t iphase = 0;
     int oslot = 0; uint32_t ophase = 0;
     uint32_t n_use[2] = {0u, 0u};      // fills of slab pair slot ps so far
+    uint32_t nge = 0u;                 // gated tiles so far
     const TcEpiGateBwd<true>::Params pg{D_};
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     SBT_DECL(10)
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
-      bool add_res;
+      int out_mode, out_act, kind;
       const uint8_t* mrow = nullptr;       // this row's keep-mask bytes (dropout on the conv branch this tile differentiates)
       {
         int ly, mt, b, tb;
         locate(j, ly, mt, b, tb);
-        add_res = layers[ly].has_dx != 0 && layers[ly].has_res != 0;
+        out_mode = layers[ly].out_mode; out_act = layers[ly].act; kind = layers[ly].kind;
         const int tt = tb * (2 * Cfg::BM) + pair_row0 + row;
         if (layers[ly].mask && tt < p.T && b < p.B) mrow = layers[ly].mask + ((size_t)b * p.T + tt) * R_;
       }
+      if (!kind) {
+      const uint32_t gpar = nge & 1u; ++nge;      // the DG accumulator hand-shakes count gated tiles only
       // ---- DG epilogue: d z = d g * [P | Q] -> operand buffer
       SBT(0)
-      mbar_wait(dg_full, par);
+      mbar_wait(dg_full, gpar);
       SBT(1)
       tc_fence_after();
       {
@@ -496,7 +547,8 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(dg_empty, 0u);
-      // ---- OUT epilogue: d x_out_{l-1}
+      }
+      // ---- OUT epilogue: d x_out_{l-1} (or the gradient wrt the output of the conv in front)
       SBT(2)
       mbar_wait(out_full, par);
       SBT(5)
@@ -514,16 +566,23 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = ((mw[i >> 2] >> (8 * (i & 3))) & 0xffu) ? v[i] * p.drop_scale : 0.f;
           }
-          if (add_res) {
+          if (out_mode) {
             mbar_wait(&in_full[islot], iphase);
             const uint8_t* ib = in_ring + islot * 2 * Cfg::PANEL;
             const uint4 a = *reinterpret_cast<const uint4*>(ib + off0);
             const uint4 c = *reinterpret_cast<const uint4*>(ib + off1);
             const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+            float y[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              v[2 * i] += __uint_as_float(w[i] << 16);
-              v[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+              y[2 * i] = __uint_as_float(w[i] << 16);
+              y[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+            if (out_mode == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += y[i];          // residual gradient
+            } else {
+              wn_act_grad16(out_act, y, v);                       // activation adjoint from the cached output of the conv in front
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&in_empty[islot]);
@@ -572,6 +631,13 @@ struct TcStackBwdDesc {       // one block
   const bf16* Wb; int k_b;    // [R][k_b]: dgrad operand of the gated conv, contraction (tap, 2D)
   int has_res;                // use_residual: d x_out_{l-1} += d x_out_l
   const uint8_t* mask; float drop_scale;    // dropout on this block's conv branch (null / 0 = off)
+  // multi-dilation blocks: one desc per CONV, in forward order.  plain != 0: a conv in front of the gated conv —
+  //   gin (B,T,D) = gradient wrt this conv's output (written by the desc behind this one), Wb its dgrad operand [Cin][nseg*D],
+  //   dx (B,T,Cin) the gradient wrt its input.
+  // OUT epilogue input `ein` (B,T,R), both kinds: out_mode 1 = residual gradient d x_out of the block (ein_layer = index of the desc
+  // whose tile writes it, or -1: written before the launch), out_mode 2 = cached output of the conv in front (activation adjoint), 0 none
+  int plain; const bf16* gin;
+  int out_mode, act, ein_layer; const bf16* ein;
 };
 
 struct TcStackBwdPlan {
@@ -587,40 +653,56 @@ static int tc_stack_bwd_build_t(TmapCache& tc, const std::vector<TcStackBwdDesc>
     const TcStackBwdDesc& d = descs[l];
     TcStackBwdLayer& t = tab[l];
     memset(&t, 0, sizeof(t));
-    const CUtensorMap* mDZ = tc_slab_map(tc, d.dz, 2 * d.D, 2 * d.D, d.T, d.B);
-    const TcEpiIo zf{d.z, 2 * d.D, d.D, 0}, zs{d.z + d.D, 2 * d.D, d.D, 0}, xo{d.dx, d.R, d.R, 0};
-    const CUtensorMap* mZf = tc_panel_map(tc, zf, d.T, d.B);
-    const CUtensorMap* mZs = tc_panel_map(tc, zs, d.T, d.B);
+    const TcEpiIo xo{d.dx, d.R, d.R, 0};
     const CUtensorMap* mO = tc_panel_map(tc, xo, d.T, d.B);
-    uint64_t wd[2] = {(uint64_t)d.k_dg, (uint64_t)d.D}, ws[1] = {(uint64_t)d.k_dg * 2};
-    uint32_t wb[2] = {64, (uint32_t)(D_ / 2)};
-    const CUtensorMap* mWdg = tc.get(d.Wdg, 2, wd, ws, wb);
     uint64_t bd[2] = {(uint64_t)d.k_b, (uint64_t)d.R}, bs[1] = {(uint64_t)d.k_b * 2};
     uint32_t bb[2] = {64, (uint32_t)(R_ / 2)};
     const CUtensorMap* mWb = tc.get(d.Wb, 2, bd, bs, bb);
-    if (!mDZ || !mZf || !mZs || !mO || !mWdg || !mWb) return -10;
-    t.tmDZ = *mDZ; t.tmZf = *mZf; t.tmZs = *mZs; t.tmO = *mO; t.tmWdg = *mWdg; t.tmWb = *mWb;
-    t.tmDX = *mDZ; t.tmDS = *mDZ; t.tmDXp = *mO;       // placeholders for absent operands (never dereferenced)
+    if (!mO || !mWb) return -10;
+    t.tmO = *mO; t.tmWb = *mWb; t.tmDXp = *mO;
+    for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
+    t.mask = d.mask;
+    t.kind = d.plain ? 1 : 0; t.out_mode = d.out_mode; t.act = d.act; t.in_flag_layer = d.out_mode == 1 ? d.ein_layer : -1;
+    if (d.out_mode) {
+      const TcEpiIo ei{d.ein, d.R, d.R, 0};
+      const CUtensorMap* mp = tc_panel_map(tc, ei, d.T, d.B);
+      if (!mp) return -10;
+      t.tmDXp = *mp;
+    }
+    if (d.plain) {
+      const CUtensorMap* mG = tc_slab_map(tc, d.gin, d.D, d.D, d.T, d.B);
+      if (!mG) return -10;
+      t.tmDZ = *mG; t.kb_tap = d.D / 64;
+      t.tmDX = *mG; t.tmDS = *mG; t.tmWdg = *mWb; t.tmZf = *mO; t.tmZs = *mO;       // placeholders (a plain layer never touches them)
+      continue;
+    }
+    const CUtensorMap* mDZ = tc_slab_map(tc, d.dz, 2 * d.D, 2 * d.D, d.T, d.B);
+    const TcEpiIo zf{d.z, 2 * d.D, d.D, 0}, zs{d.z + d.D, 2 * d.D, d.D, 0};
+    const CUtensorMap* mZf = tc_panel_map(tc, zf, d.T, d.B);
+    const CUtensorMap* mZs = tc_panel_map(tc, zs, d.T, d.B);
+    uint64_t wd[2] = {(uint64_t)d.k_dg, (uint64_t)d.D}, ws[1] = {(uint64_t)d.k_dg * 2};
+    uint32_t wb[2] = {64, (uint32_t)(D_ / 2)};
+    const CUtensorMap* mWdg = tc.get(d.Wdg, 2, wd, ws, wb);
+    if (!mDZ || !mZf || !mZs || !mWdg) return -10;
+    t.tmDZ = *mDZ; t.tmZf = *mZf; t.tmZs = *mZs; t.tmWdg = *mWdg;
+    t.tmDX = *mDZ; t.tmDS = *mDZ;       // placeholders for absent operands (never dereferenced)
     if (d.dxo) {
       const CUtensorMap* m = tc_act_map(tc, d.dxo, d.R, d.R, d.T, d.B, 1, 0, 128);
-      const TcEpiIo xi{d.dxo, d.R, d.R, 0};
-      const CUtensorMap* mp = tc_panel_map(tc, xi, d.T, d.B);
-      if (!m || !mp) return -10;
-      t.tmDX = *m; t.tmDXp = *mp;
+      if (!m) return -10;
+      t.tmDX = *m;
     }
     if (d.dskip) {
       const CUtensorMap* m = tc_act_map(tc, d.dskip, d.lds, d.S, d.T, d.B, 1, 0, 128);
       if (!m) return -10;
       t.tmDS = *m;
     }
-    for (int s = 0; s < TC_MAX_SEG; ++s) t.shift[s] = s < d.nseg ? d.shift[s] : 0;
-    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = (d.has_res && d.dxo != nullptr) ? 1 : 0;
+    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = d.out_mode == 1 ? 1 : 0;
     t.wait_dx = (d.dxo != nullptr && l + 1 < descs.size()) ? 1 : 0;
-    t.mask = d.mask;
   }
   const TcStackBwdDesc& d0 = descs[0];
   plan->release();
-  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->drop = d0.mask != nullptr;
+  plan->B = d0.B; plan->T = d0.T; plan->L = (int)descs.size(); plan->num_mtiles = d0.B * ((d0.T + 255) / 256); plan->drop = false;
+  for (const TcStackBwdDesc& d : descs) if (d.mask) plan->drop = true;
   if (cudaMalloc((void**)&plan->d_layers, tab.size() * sizeof(TcStackBwdLayer)) != cudaSuccess ||
       cudaMemcpy(plan->d_layers, tab.data(), tab.size() * sizeof(TcStackBwdLayer), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMalloc((void**)&plan->d_flags, (size_t)2 * plan->L * plan->num_mtiles * sizeof(int)) != cudaSuccess) {

@@ -1615,6 +1615,11 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
       RET(run_wgrad<T>(h, side2 ? sd->side : st, CLS_DILATED, w));
     }
     // dgrad
+    if (skip_chain && j > 0) {
+      // the chain runs inside the stack-backward launch: the gradient wrt the output of conv j - 1 lands in its kept buffer
+      dcur = h->dp_keep[l][j - 1];
+      dcw = D;
+    }
     const bool need = (j > 0 || dx_in != nullptr) && !skip_chain;
     if (need) {
       GemmH g;
@@ -1759,7 +1764,11 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
             !(h->alias_skip && c.use_skip) && h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!sb_ok) break;
-      sb_ok = b.stack.size() == 1 && b.stack[0].cin % 64 == 0 && (!b.has_skip || h->S % 64 == 0);
+      // multi-dilation blocks (plain conv layers of the launch): all convs 256 wide; no dropout there yet (the mask belongs to the
+      // first conv of the block: a plain tile)
+      sb_ok = b.stack[0].cin % 64 == 0 && (!b.has_skip || h->S % 64 == 0) && b.stack.size() <= 16 &&
+              (b.stack.size() == 1 || (h->D == 256 && !h->drop_active && h->dp_keep.size() == (size_t)h->L));
+      for (size_t j = 0; sb_ok && j + 1 < b.stack.size(); ++j) sb_ok = b.stack[j].cout == h->D && b.stack[j].Wb16 != nullptr && b.stack[j].K == h->K;
     }
   }
   h->stack_bwd_layers = 0;
@@ -1871,22 +1880,48 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
     bool stacked = false;
     if constexpr (sizeof(T) == 2) {
       if (sb_ok) {
-        auto desc_of = [&](int l) {
-          BlockP& b = h->blocks[l];
-          const ConvP& cv = b.stack[0];
-          TcStackBwdDesc d{};
-          d.B = B; d.T = Tn; d.nseg = cv.K; d.D = h->D; d.R = h->R; d.S = b.has_skip && dskip ? h->S : 0;
-          for (int k = 0; k < cv.K; ++k) d.shift[k] = (cv.K - 1 - k) * cv.dil;
-          d.dxo = l == h->L - 1 ? (const bf16*)dxout : (const bf16*)dx_of(l);
-          d.dskip = (b.has_skip && dskip) ? (const bf16*)dskip : nullptr; d.lds = h->Sp;
-          d.z = (const bf16*)h->zbuf[l]; d.dz = (bf16*)dz_of(l); d.dx = (bf16*)(l > 0 ? dx_of(l - 1) : h->dxA);
-          const int rs = h->R + (b.has_skip ? h->S : 0), koff = d.dxo ? 0 : h->R;
-          d.Wdg = b.Wdg16 + koff; d.k_dg = rup(rs, 64);
-          d.Wb = cv.Wb16; d.k_b = rup(cv.Kb16, 64);
-          d.has_res = c.use_residual ? 1 : 0;
-          if (h->drop_active) { d.mask = h->drop_mask + (size_t)l * rows_cap * h->R; d.drop_scale = 1.0f / (1.0f - c.dropout); }
-          return d;
-        };
+        // one desc per CONV in forward order: the plain convs of block l, then its gated conv
+        std::vector<TcStackBwdDesc> bdescs;
+        {
+          int conv_index = 0;
+          for (int l = 0; l < h->L; ++l) {
+            BlockP& b = h->blocks[l];
+            const int depth = (int)b.stack.size();
+            const bf16* blk_dxo = l == h->L - 1 ? (const bf16*)dxout : (const bf16*)dx_of(l);      // d x_out of this block (or null)
+            bf16* blk_dx = (bf16*)(l > 0 ? dx_of(l - 1) : h->dxA);                                   // gradient wrt the block input
+            const int next_first = conv_index + depth;      // desc that writes blk_dxo (first conv of block l + 1), if any
+            const bool dxo_in_launch = blk_dxo != nullptr && l < h->L - 1;
+            for (int j = 0; j < depth; ++j, ++conv_index) {
+              const ConvP& cv = b.stack[j];
+              TcStackBwdDesc d{};
+              d.B = B; d.T = Tn; d.nseg = cv.K; d.D = h->D; d.R = h->R; d.S = (!h->alias_skip && dskip) ? h->S : 0;
+              for (int k = 0; k < cv.K; ++k) d.shift[k] = (cv.K - 1 - k) * cv.dil;
+              d.Wb = cv.Wb16; d.k_b = rup(cv.Kb16, 64);
+              d.drop_scale = h->drop_active ? 1.0f / (1.0f - c.dropout) : 0.f;
+              d.ein_layer = -1;
+              // what this conv's tile writes: the gradient wrt its input
+              d.dx = j == 0 ? blk_dx : (bf16*)h->dp_keep[l][j - 1];
+              if (j == 0) {
+                // first conv of the block: the block input is not activated; the residual gradient joins here
+                if (c.use_residual && blk_dxo) { d.out_mode = 1; d.ein = blk_dxo; d.ein_layer = dxo_in_launch ? next_first : -1; }
+                if (h->drop_active) d.mask = h->drop_mask + (size_t)l * rows_cap * h->R;
+              } else {
+                d.out_mode = 2; d.act = c.activation; d.ein = (const bf16*)h->acts[l][j - 1];
+              }
+              if (j < depth - 1) {
+                d.plain = 1; d.gin = (const bf16*)h->dp_keep[l][j];
+              } else {
+                d.dxo = blk_dxo;
+                d.dskip = (b.has_skip && dskip) ? (const bf16*)dskip : nullptr; d.lds = h->Sp;
+                d.z = (const bf16*)h->zbuf[l]; d.dz = (bf16*)dz_of(l);
+                const int rs = h->R + (b.has_skip ? h->S : 0), koff = d.dxo ? 0 : h->R;
+                d.Wdg = b.Wdg16 + koff; d.k_dg = rup(rs, 64);
+                d.has_res = (c.use_residual && depth == 1) ? 1 : 0;
+              }
+              bdescs.push_back(d);
+            }
+          }
+        }
         TcStackBwdPlan* sp = nullptr;
         for (auto& q : h->stack_bwd_plans) if (q.B == B && q.T == Tn && q.drop == h->drop_active) sp = &q;
         int r = 0;
@@ -1901,17 +1936,15 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
               for (auto& q : h->stack_bwd_plans) q.release();
               h->stack_bwd_plans.clear();
             }
-            std::vector<TcStackBwdDesc> descs;
-            for (int l = 0; l < h->L; ++l) descs.push_back(desc_of(l));
             h->stack_bwd_plans.push_back(TcStackBwdPlan{});
-            r = tc_stack_bwd_build(h->tmaps, descs, &h->stack_bwd_plans.back());
+            r = tc_stack_bwd_build(h->tmaps, bdescs, &h->stack_bwd_plans.back());
             if (r == 0) sp = &h->stack_bwd_plans.back(); else h->stack_bwd_plans.pop_back();
           }
         }
         if (sp) {
           struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_bwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
           LaunchScope ls(h, st, CLS_DILATED);
-          r = tc_stack_bwd_launch(st, *sp, desc_of(0));
+          r = tc_stack_bwd_launch(st, *sp, bdescs[0]);
           if (r == 0) { stacked = true; h->stack_bwd_layers = h->L; }
           else if (r == -100) h->launches--;
           else { set_err("stack backward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
