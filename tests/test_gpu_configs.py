@@ -47,6 +47,7 @@ TOL_GRAD_PRECISE, TOL_GLOBAL_PRECISE = 8e-3, 4e-3      # precise flavour (measur
 def _check_paths(r):
   if r['want_stack']:
     assert r['stack_layers'] == r['blocks'], 'the persistent stack-forward launch must be on the checked path'
+    assert r['stack_bwd_layers'] == r['blocks'], 'the persistent stack-backward launch must be on the checked path'
   if r['want_group']:
     assert r['grouped_tiles'] > 0, 'the grouped weight-gradient launch must be on the checked path'
 

@@ -52,6 +52,8 @@ struct alignas(128) TcStackBwdLayer {
   // OUT epilogue: out_mode 1 adds the residual gradient (tmDXp = d x_out of the block, guarded by flags_dx[in_flag_layer] when
   // >= 0), out_mode 2 multiplies by act'(y) of the conv in front (tmDXp = its cached bf16 output), 0 neither.
   int kind, out_mode, act, kb_tap, in_flag_layer;
+  int alias;                  // skip_channels=None: the skip IS conv1's output, d(conv1 output) = d x_out + d skip — both DG segments
+                              // meet the same Wr^T columns (no materialised sum)
 };
 
 struct TcStackBwdParams {
@@ -218,7 +220,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           }
         }
         if (Ly.has_ds) {
-          const int k0 = Ly.has_dx ? p.kb_dx * 64 : 0;
+          const int k0 = (Ly.has_dx && !Ly.alias) ? p.kb_dx * 64 : 0;
           for (int kb = 0; kb < p.kb_ds; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -638,6 +640,7 @@ struct TcStackBwdDesc {       // one block
   // whose tile writes it, or -1: written before the launch), out_mode 2 = cached output of the conv in front (activation adjoint), 0 none
   int plain; const bf16* gin;
   int out_mode, act, ein_layer; const bf16* ein;
+  int alias;                  // d skip is a second DG segment against the SAME weight columns as d x_out (Wdg = Wr^T only)
 };
 
 struct TcStackBwdPlan {
@@ -696,7 +699,7 @@ static int tc_stack_bwd_build_t(TmapCache& tc, const std::vector<TcStackBwdDesc>
       if (!m) return -10;
       t.tmDS = *m;
     }
-    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = d.out_mode == 1 ? 1 : 0;
+    t.has_dx = d.dxo != nullptr; t.has_ds = d.dskip != nullptr; t.has_res = d.out_mode == 1 ? 1 : 0; t.alias = d.alias;
     t.wait_dx = (d.dxo != nullptr && l + 1 < descs.size()) ? 1 : 0;
   }
   const TcStackBwdDesc& d0 = descs[0];

@@ -305,6 +305,10 @@ struct TcWgJobDesc {         // one weight-gradient problem dW[k * Cin + c, n] =
   float* dst; const float* w;            // [ntaps * cin][N] fp32 gradient (Keras layout), weights for L2 (or null)
   float* bias;                           // [N] column sums of G, or null
   float* per_batch; int ldpb;            // [B][ldpb] per-batch column sums of G, or null
+  // acc_prev: this problem's product is ADDED to the previous problem's gradient (same dst; both one 256 x 256 tile): its partial
+  // tiles follow the previous problem's and the finish sums them all — conv1 under skip_channels=None sees d x_out + d skip
+  // (layers.py:217-218), two G tensors against the same A.  bias_add_G: the column sums of that other G tensor are added to `bias`.
+  bool acc_prev = false; const bf16* bias_add_G = nullptr;
   int bucket = 0;                        // final-launch jobs only: the final launch runs as one launch + finish per bucket, in bucket
                                          // order, so that the gradients of bucket k can be all-reduced while bucket k + 1 is computed
   int group = -1;                        // -1: the launch at the end of the backward pass; g >= 0: side launch g (one per block
@@ -315,7 +319,7 @@ struct TcWgJobDesc {         // one weight-gradient problem dW[k * Cin + c, n] =
 
 struct TcWgGroupPlan {
   int B = 0, T = 0;
-  int nunits = 0, ntiles = 0, ncs = 0, nsplit = 1, npartial = 0;
+  int nunits = 0, ntiles = 0, nfin = 0, ncs = 0, nsplit = 1, npartial = 0;   // ntiles: 256 x 256 products; nfin: gradient tiles the finish writes
   int final_units = 0;                                   // units [0, final_units): the launch at the end
   struct Bucket { int unit0, nunits, tile0, ntiles, cs0, ncs; };
   std::vector<Bucket> buckets;                           // the final launch, bucket by bucket (tiles / column-sum entries of a bucket are contiguous)
@@ -363,7 +367,13 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   std::vector<TcWgFinTile> tiles;
   std::vector<TcWgFinCs> css;
   std::unordered_map<const void*, int> cs_of;            // G tensor -> index of its first TcWgFinCs entry (one per 256 columns)
+  std::vector<int> fin_of;                               // tile -> index of the finish tile that sums its partials
+  std::vector<std::pair<int, const void*>> cs_extra;     // (column-sum entry, other G tensor whose sums are added to it)
   for (const auto& j : jobs) {
+    if (j.acc_prev && (j.cin != 256 || j.N != 256 || j.ntaps != 1 || tiles.empty() || tiles.back().dst != j.dst)) {
+      snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: an accumulating problem must be one 256 x 256 tile behind the problem it adds to");
+      return -25;
+    }
     if (!tc_wgrad_group_ok(j.cin, j.N)) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: widths %d x %d not multiples of 256", j.cin, j.N); return -20; }
     const int am = map_idx(j.A, j.lda, j.cin), gm = map_idx(j.G, j.ldg, j.N);
     if (am < 0 || gm < 0) return -21;
@@ -381,6 +391,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
           e.bias = j.bias ? j.bias + nt * 256 : nullptr;
           e.per_batch = j.per_batch ? j.per_batch + nt * 256 : nullptr;
           e.ldpb = j.ldpb; e.nsrc = 0;
+          if (j.bias_add_G && nt == 0) cs_extra.push_back(std::make_pair((int)css.size(), (const void*)j.bias_add_G));
           css.push_back(e);
           cs_bucket.push_back(j.group < 0 ? j.bucket : nbuckets - 1);
         }
@@ -391,11 +402,16 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
     for (int k = 0; k < j.ntaps; ++k)
       for (int mt = 0; mt < j.cin / 256; ++mt, ++sh)
         for (int nt = 0; nt < j.N / 256; ++nt) {
-          TcWgFinTile ft{};
-          ft.dst = j.dst + ((long long)(k * j.cin + mt * 256)) * j.N + nt * 256;
-          ft.w = j.w ? j.w + ((long long)(k * j.cin + mt * 256)) * j.N + nt * 256 : nullptr;
-          ft.ld = j.N; ft.tile0 = 0; ft.nsplit = 0;
-          tiles.push_back(ft);
+          if (j.acc_prev) {
+            fin_of.push_back((int)tiles.size() - 1);      // no finish tile of its own: its partials extend the previous one's
+          } else {
+            TcWgFinTile ft{};
+            ft.dst = j.dst + ((long long)(k * j.cin + mt * 256)) * j.N + nt * 256;
+            ft.w = j.w ? j.w + ((long long)(k * j.cin + mt * 256)) * j.N + nt * 256 : nullptr;
+            ft.ld = j.N; ft.tile0 = 0; ft.nsplit = 0;
+            tiles.push_back(ft);
+            fin_of.push_back((int)tiles.size() - 1);
+          }
           Tile t{};
           t.a_map = am; t.a_atom = mt * 4; t.shift = j.shift[k]; t.g_map = gm; t.g_atom = nt * 4;
           t.cs_entry = own_cs ? cs0 + nt : -1;
@@ -494,12 +510,20 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
     if (s > total_chunks) s = total_chunks;
     split_of[1 + g] = norm_split(s);
   }
+  // partial tiles: one per (work tile, row split), in work-tile order; a finish tile sums the partials of its work tile(s) —
+  // an accumulating problem's tile directly follows the tile it adds to, so the range stays contiguous
+  std::vector<int> part0(ntiles, 0);
+  int npart_total = 0;
   {
     int t0 = 0;
     for (int i = 0; i < ntiles; ++i) {
       const int s = tl[i].group < 0 ? split_bk[tl[i].bucket] : split_of[tl[i].group + 1];
-      tiles[i].tile0 = t0; tiles[i].nsplit = s; t0 += s;
+      part0[i] = t0;
+      TcWgFinTile& ft = tiles[fin_of[i]];
+      if (ft.nsplit == 0) { ft.tile0 = t0; ft.nsplit = s; } else ft.nsplit += s;
+      t0 += s;
     }
+    npart_total = t0;
   }
   std::vector<TcWgUnit> units;
   int cs_rows = 0;
@@ -532,7 +556,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
         u.share_g = uu.share_g; u.shift2 = uu.share_g ? tl[uu.t[1]].shift : 0;
         for (int hh = 0; hh < 2; ++hh) {
           const Tile& t = tl[uu.t[hh] >= 0 ? uu.t[hh] : uu.t[0]];
-          u.g_map[hh] = t.g_map; u.g_atom[hh] = t.g_atom; u.out_tile[hh] = uu.t[hh] >= 0 ? tiles[uu.t[hh]].tile0 + z : 0;
+          u.g_map[hh] = t.g_map; u.g_atom[hh] = t.g_atom; u.out_tile[hh] = uu.t[hh] >= 0 ? part0[uu.t[hh]] + z : 0;
           u.cs_row0[hh] = -1;
           if (uu.share_g && hh == 1) continue;      // one G tile: its column sums belong to slot 0 (rows of both taps' slices)
           if (uu.t[hh] >= 0 && t.cs_entry >= 0 && t.cs_r1 > t.cs_r0) {
@@ -559,13 +583,25 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   // tiles and column-sum entries were created in job order = bucket order (side-launch jobs last: finished with the last bucket)
   for (int b = 0; b < nbuckets; ++b) {
     TcWgGroupPlan::Bucket& bk = plan->buckets[b];
-    bk.tile0 = ntiles; bk.ntiles = 0; bk.cs0 = (int)css.size(); bk.ncs = 0;
-    for (int i = 0; i < ntiles; ++i) if (tl[i].bucket == b) { if (bk.ntiles == 0) bk.tile0 = i; bk.ntiles++; }
+    bk.tile0 = 0; bk.ntiles = 0; bk.cs0 = (int)css.size(); bk.ncs = 0;
+    // (finish tiles of the bucket: those of its work tiles, a contiguous range)
+    int f_lo = (int)tiles.size(), f_hi = -1;
+    for (int i = 0; i < ntiles; ++i) if (tl[i].bucket == b) { f_lo = std::min(f_lo, fin_of[i]); f_hi = std::max(f_hi, fin_of[i]); }
+    if (f_hi >= f_lo) { bk.tile0 = f_lo; bk.ntiles = f_hi - f_lo + 1; }
     for (int i = 0; i < (int)css.size(); ++i) if (cs_bucket[i] == b) { if (bk.ncs == 0) bk.cs0 = i; bk.ncs++; }
     if (bk.ntiles == 0) bk.tile0 = 0;
     if (bk.ncs == 0) bk.cs0 = 0;
   }
-  plan->nunits = (int)units.size(); plan->ntiles = ntiles; plan->ncs = (int)css.size(); plan->nsplit = nsplit;
+  // column sums of another G tensor added to a bias (conv1 under skip_channels=None: d x_out + d skip): its owner's sources join
+  for (const auto& ce : cs_extra) {
+    auto it = cs_of.find(ce.second);
+    if (it == cs_of.end()) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: no problem computes the column sums a bias adds"); return -26; }
+    TcWgFinCs& e = css[ce.first];
+    const TcWgFinCs& o = css[it->second];
+    if (o.nsrc < 0 || e.nsrc < 0 || e.nsrc + o.nsrc > TC_WG_MAX_CS_SRC) { snprintf(g_tc_err, sizeof(g_tc_err), "grouped wgrad: too many column-sum sources"); return -22; }
+    for (int i = 0; i < o.nsrc; ++i) { e.row0[e.nsrc] = o.row0[i]; e.b_first[e.nsrc] = o.b_first[i]; e.nb[e.nsrc] = o.nb[i]; e.nsrc++; }
+  }
+  plan->nunits = (int)units.size(); plan->ntiles = ntiles; plan->nfin = (int)tiles.size(); plan->ncs = (int)css.size(); plan->nsplit = nsplit;
   auto up = [&](void** d, const void* src, size_t bytes) -> bool {
     if (bytes == 0) { *d = nullptr; return true; }
     if (cudaMalloc(d, bytes) != cudaSuccess) return false;
@@ -573,8 +609,7 @@ static int tc_wgrad_group_build(TmapCache& tc, const std::vector<TcWgJobDesc>& j
   };
   bool ok = up((void**)&plan->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap)) && up((void**)&plan->d_units, units.data(), units.size() * sizeof(TcWgUnit)) &&
             up((void**)&plan->d_tiles, tiles.data(), tiles.size() * sizeof(TcWgFinTile)) && up((void**)&plan->d_css, css.data(), css.size() * sizeof(TcWgFinCs));
-  size_t npart = 0;
-  for (int i = 0; i < ntiles; ++i) npart += (size_t)tiles[i].nsplit;
+  const size_t npart = (size_t)npart_total;
   plan->npartial = (int)npart;
   ok = ok && cudaMalloc((void**)&plan->d_partial, npart * 65536 * 4) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&plan->d_cs, (size_t)(cs_rows > 0 ? cs_rows : 1) * 256 * 4) == cudaSuccess;
@@ -612,7 +647,7 @@ static int tc_wgrad_group_launch(cudaStream_t st, const TcWgGroupPlan& plan, int
 // bucket < 0: every tile and column-sum entry of the plan; else those of one bucket of the final launch
 static int tc_wgrad_group_finish_launch(cudaStream_t st, const TcWgGroupPlan& plan, float l2coef, int bucket = -1) {
   TcWgFinParams f{};
-  f.partial = plan.d_partial; f.cs = plan.d_cs; f.tiles = plan.d_tiles; f.ntiles = plan.ntiles; f.css = plan.d_css; f.ncs = plan.ncs;
+  f.partial = plan.d_partial; f.cs = plan.d_cs; f.tiles = plan.d_tiles; f.ntiles = plan.nfin; f.css = plan.d_css; f.ncs = plan.ncs;
   if (bucket >= 0) {
     const TcWgGroupPlan::Bucket& bk = plan.buckets[bucket];
     f.tiles = plan.d_tiles + bk.tile0; f.ntiles = bk.ntiles; f.css = plan.d_css + bk.cs0; f.ncs = bk.ncs;

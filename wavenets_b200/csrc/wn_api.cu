@@ -1475,7 +1475,10 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
   // ---- d o  (gradient wrt conv1 output)
   const void* d_o = dxout;
   int ld_o = ldxo;
-  if (h->alias_skip) {
+  // (inside the stack-backward launch the sum d x_out + d skip is never materialised: both DG segments meet the same Wr^T columns,
+  // and conv1's weight gradient is two products accumulated by the grouped launch's finish)
+  const bool alias_split = h->alias_skip && skip_chain && dxout && dskip;
+  if (h->alias_skip && !alias_split) {
     if (dxout && dskip) {
       LaunchScope ls(h, st, CLS_MISC);
       // (grouped weight gradients read d_o at the end of the pass: one buffer per block instead of the shared scratch)
@@ -1501,7 +1504,13 @@ static int block_backward(wn_handle* h, cudaStream_t st, int l, const void* x_in
         j.G = (const bf16*)d_o; j.ldg = ld_o; j.N = R;
         j.dst = G_(h, b.conv1.w_idx); j.w = l2 ? P_(h, b.conv1.w_idx) : nullptr; j.bias = G_(h, b.conv1.b_idx);
         j.group = h->wg_cur_group; j.bucket = h->wg_cur_bucket;
+        if (alias_split) j.bias_add_G = (const bf16*)dskip;
         h->wg_jobs.push_back(j);
+        if (alias_split) {
+          TcWgJobDesc j2 = j;
+          j2.G = (const bf16*)dskip; j2.ldg = ldsk; j2.w = nullptr; j2.bias = nullptr; j2.bias_add_G = nullptr; j2.acc_prev = true;
+          h->wg_jobs.push_back(j2);
+        }
       } else {
         unused_conv_grads(h, st, b.conv1.w_idx, b.conv1.b_idx, l2coef);
       }
@@ -1761,7 +1770,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
   bool sb_ok = false;
   if constexpr (sizeof(T) == 2) {
     sb_ok = group && !cat && h->use_stack_bwd && tc_cta_group() == 2 && h->L >= 2 && h->D == h->R && (h->D == 256 || h->D == 128) &&
-            !(h->alias_skip && c.use_skip) && h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
+            h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!sb_ok) break;
       // multi-dilation blocks (plain conv layers of the launch): all convs 256 wide; no dropout there yet (the mask belongs to the
@@ -1894,7 +1903,8 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
             for (int j = 0; j < depth; ++j, ++conv_index) {
               const ConvP& cv = b.stack[j];
               TcStackBwdDesc d{};
-              d.B = B; d.T = Tn; d.nseg = cv.K; d.D = h->D; d.R = h->R; d.S = (!h->alias_skip && dskip) ? h->S : 0;
+              const bool alias = h->alias_skip && dskip != nullptr;      // skip = conv1's output: d skip joins d x_out in front of Wr^T
+              d.B = B; d.T = Tn; d.nseg = cv.K; d.D = h->D; d.R = h->R; d.S = dskip ? (alias ? h->R : h->S) : 0;
               for (int k = 0; k < cv.K; ++k) d.shift[k] = (cv.K - 1 - k) * cv.dil;
               d.Wb = cv.Wb16; d.k_b = rup(cv.Kb16, 64);
               d.drop_scale = h->drop_active ? 1.0f / (1.0f - c.dropout) : 0.f;
@@ -1912,9 +1922,10 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
                 d.plain = 1; d.gin = (const bf16*)h->dp_keep[l][j];
               } else {
                 d.dxo = blk_dxo;
-                d.dskip = (b.has_skip && dskip) ? (const bf16*)dskip : nullptr; d.lds = h->Sp;
+                d.dskip = ((b.has_skip || alias) && dskip) ? (const bf16*)dskip : nullptr; d.lds = h->Sp;
+                d.alias = alias ? 1 : 0;
                 d.z = (const bf16*)h->zbuf[l]; d.dz = (bf16*)dz_of(l);
-                const int rs = h->R + (b.has_skip ? h->S : 0), koff = d.dxo ? 0 : h->R;
+                const int rs = h->R + (b.has_skip ? h->S : 0), koff = (d.dxo || alias) ? 0 : h->R;
                 d.Wdg = b.Wdg16 + koff; d.k_dg = rup(rs, 64);
                 d.has_res = (c.use_residual && depth == 1) ? 1 : 0;
               }
