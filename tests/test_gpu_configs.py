@@ -70,7 +70,7 @@ def test_config_topology_vs_oracle(name):
   assert r['global_faithful'] <= TOL_GLOBAL_FAITHFUL, r
 
 
-@pytest.mark.parametrize('name', ['c2', 'c5'])
+@pytest.mark.parametrize('name', ['c2', 'c3', 'c5'])
 def test_config_topology_training_pass_with_dropout(name):
   """defaults.yaml:17 / train.py:22-50 train with dropout 0.1 (layers.py:109-112,192-196).  The keep-masks are applied INSIDE the
   persistent stack launches (forward: the epilogue that produces x_out also writes the next block's masked conv-branch input;

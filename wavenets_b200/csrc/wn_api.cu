@@ -1773,10 +1773,9 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
             h->K <= TC_MAX_SEG && B * cdiv(Tn, 256) > tc_num_sms() / 2;
     for (auto& b : h->blocks) {
       if (!sb_ok) break;
-      // multi-dilation blocks (plain conv layers of the launch): all convs 256 wide; no dropout there yet (the mask belongs to the
-      // first conv of the block: a plain tile)
+      // multi-dilation blocks (plain conv layers of the launch): all convs 256 wide
       sb_ok = b.stack[0].cin % 64 == 0 && (!b.has_skip || h->S % 64 == 0) && b.stack.size() <= 16 &&
-              (b.stack.size() == 1 || (h->D == 256 && !h->drop_active && h->dp_keep.size() == (size_t)h->L));
+              (b.stack.size() == 1 || (h->D == 256 && h->dp_keep.size() == (size_t)h->L));
       for (size_t j = 0; sb_ok && j + 1 < b.stack.size(); ++j) sb_ok = b.stack[j].cout == h->D && b.stack[j].Wb16 != nullptr && b.stack[j].K == h->K;
     }
   }
