@@ -503,6 +503,14 @@ def main():
     # the fused forward kernels' conv1 products likewise (forward only; their adjoints run in other kernels)
     dil_flops_step = (2.0 * flops['dilated'] + (wg_tiles * 2.0 * 256 * 256 if wg_tiles else flops['dilated'])) * rows
     dil_flops_step += fused_blocks * 2.0 * dmodel * kw['channels'] * rows
+    if stack_bwd_layers:
+      # the stack-backward launch also holds the adjoints of conv1 / conv_skip (the DG tile: d g = [d x_out | d skip] . [Wr^T ; Ws^T]);
+      # like the fused forward's conv1 products they cannot be separated from the launch's time, so they count as its work.
+      # Last block under use_skip: conv1's output is unused, only the skip term exists.
+      use_skip = kw.get('use_skip', True)
+      s_w = (kw['skip_channels'] or kw['channels']) if use_skip else 0      # skip_channels=None: d skip meets Wr^T (a second R-wide segment)
+      per_block = [((kw['channels'] if (l < kw['blocks'] - 1 or not use_skip) else 0) + s_w) for l in range(kw['blocks'])]
+      dil_flops_step += sum(2.0 * dmodel * k for k in per_block) * rows
     dil_ms = share * step_ms
     achieved = dil_flops_step / (dil_ms * 1e-3) / 1e12 if dil_ms > 0 else 0.0
     top = None
@@ -515,10 +523,10 @@ def main():
                 'traffic_kernel': top[0] if top else None,
                 'kernel': ('tc_stack_fwd_kernel (gated conv + gate + conv1 + residual of ALL layers, one persistent launch, CTA pairs) + ' if stack_layers else
                            ('tc_block_fwd_kernel (gated conv + gate + conv1 + residual, CTA pairs) + ' if fused_blocks else 'tc_conv_gemm_staged_kernel<gate> + '))
-                + 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + '
+                + ('tc_stack_bwd_kernel (gate adjoint + dgrad of ALL layers, one persistent launch, CTA pairs) + ' if stack_bwd_layers else 'tc_conv_gemm_staged_kernel<dgrad, cta_group::2> + ')
                 + ('tc_wgrad_group_kernel (+ finish): gated-conv, conv1, conv_skip and head filter gradients of all blocks in one launch'
                    if wg_tiles else 'tc_wgrad_pair_kernel (+ tc_wgrad_finish) on the dilated convs'),
-                'class': 'dilated-conv GEMMs (fwd + dgrad + wgrad)', 'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles,
+                'class': 'dilated-conv GEMMs (fwd + dgrad + wgrad) and the 1x1 products fused into the same launches (conv1 forward, conv1 / conv_skip adjoints, conv1 / conv_skip / head weight gradients)', 'launches_per_step': dil_launches, 'grouped_wgrad_tiles': wg_tiles,
                 'stack_forward_layers': stack_layers, 'wgrad_side_launches': int(side_l.value), 'fused_forward_blocks': fused_blocks,
                 'ms_per_step_in_kernel': dil_ms, 'ms_per_step_in_kernel_eager_events': dil_ms_eager,
                 'ms_per_step_all_launches_eager_events': prof['all'][0], 'share_of_step': share, 'flops_per_step': dil_flops_step}
