@@ -26,6 +26,10 @@ def save_weights(model, path: str) -> str:
 
 
 def load_weights(model, path: str, strict: bool = True) -> None:
+  if path.endswith(('.h5', '.hdf5', '.keras')):
+    # the reference's ModelCheckpoint writes Keras `.weights.h5` files (train.py:149-154); h5py is not a dependency here
+    raise ValueError(f'{path}: Keras HDF5 checkpoints are not read here (export the variables in trainable_variables order to .npz: '
+                     'np.savez(path, **{name.replace("/", "__"): array}) with the names of WaveNet.variable_names)')
   z = np.load(path)
   w = {k.replace('__', '/'): z[k] for k in z.files}
   if model.built:
@@ -43,7 +47,8 @@ def find_last_checkpoint(results_dir: str) -> Optional[Tuple[str, int, float]]:
     checkpoints = sorted(os.listdir(results_dir))
   except FileNotFoundError:
     return None
-  checkpoints = [c for c in checkpoints if '.weights' in c]
+  # (only the files this module can read: a directory shared with a reference run also holds `.weights.h5` files)
+  checkpoints = [c for c in checkpoints if '.weights' in c and c.endswith('.npz')]
   if not checkpoints:
     return None
   name = checkpoints[-1]

@@ -62,18 +62,27 @@ struct TcStackBwdParams {
   int kb_dx, kb_ds;           // 64-wide k blocks of the DG contraction over d x_out (R) and d skip (S)
   unsigned long long pol_dx, pol_ds, pol_w, pol_z, pol_dz_ld, pol_dz_st, pol_o;
   float drop_scale;           // 1 / (1 - rate)
+  int relaxed_handoff;        // the peer CTA's slab hand-off arrives without the cluster-scope release (see warp 12)
   int band, nbands;           // tile order: bands of `band` m tiles (the last one may be shorter); within a band all layers, last to first
 };
 
-template <int D_, int R_> struct TcStackBwdCfg {
+// V2 (round 2, the default; WN_TC_STACK_BWD=1 selects the first version): no separate d z operand buffer.  An un-shifted-tap k-step only loads weights, the A half of its ring
+// stage is idle — the DG epilogue writes the d z slab straight into it (and the TMA store to HBM reads it from there).  The 64 KB of
+// the operand buffer become two more ring stages (5 instead of 3): up to five slabs in flight between epilogue and MMA instead of two
+// slab pairs, and a deeper ring for the DG / shifted-tap k-steps.  Measured (in-kernel phase accounting, C2): DG k-steps 9.3 k -> 7.0 k
+// cycles per tile, but the pair hand-off chain (epilogue -> hand-off warp -> cluster-scope arrive -> MMA) still paces the
+// un-shifted tap at ~10 k cycles per tile: step -0.3 .. -0.9 % same-box.  WN_TC_HANDOFF_RELAXED=1 drops the cluster-scope release
+// from the peer's hand-off arrive (hand-off waits -25 %, step within noise; off by default: it leans on shared-memory writes being
+// physically complete before the local barrier that the hand-off warp acquires, not on the PTX memory model).
+template <int D_, int R_, bool V2 = false> struct TcStackBwdCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
   static constexpr int B_BYTES = 128 * BK * 2;                 // this CTA's half of a 256-row weight tile: 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = V2 ? 5 : 3;
   static constexpr int NSLAB = 2 * D_ / 64;                    // 64-column slabs of d z (filter slabs first, then gate slabs)
   static constexpr int NPAIR = D_ / 64;                        // slab pairs (f_p, s_p) = two 32-channel epilogue steps each
-  static constexpr int DZ_SLOTS = 4;                           // operand buffer: two slab pairs
+  static constexpr int DZ_SLOTS = V2 ? 0 : 4;                  // operand buffer: two slab pairs
   static constexpr int DZ_BYTES = DZ_SLOTS * A_BYTES;          // 64 KB
   static constexpr int PANEL = 128 * 64;                       // 128 rows x 32 bf16
   static constexpr int IN_SLOTS = 3, OUT_SLOTS = 2;            // z ring: (z_f, z_s) panels per slot; out ring: one d x panel per slot
@@ -83,10 +92,10 @@ template <int D_, int R_> struct TcStackBwdCfg {
   static_assert(SMEM_BYTES <= 232448, "stack backward kernel does not fit shared memory");
 };
 
-template <int D_, int R_>
+template <int D_, int R_, bool V2>
 __global__ void __launch_bounds__(416, 1)
 tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict__ flags_dx, int* __restrict__ flags_dz, const TcStackBwdParams p) {
-  using Cfg = TcStackBwdCfg<D_, R_>;
+  using Cfg = TcStackBwdCfg<D_, R_, V2>;
   constexpr int STAGES = Cfg::STAGES, NEPI = 8, NPAIR = Cfg::NPAIR;
   constexpr int KB_Z = Cfg::NSLAB;
   extern __shared__ __align__(1024) uint8_t smem_sb[];
@@ -108,7 +117,18 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
   uint64_t* slab_full = slab_done + 2;               // [2] leader's: both CTAs' slabs of pair slot ps are complete
   uint64_t* slab_cons = slab_full + 2;               // [2] local: the MMAs reading pair slot ps have completed
   uint64_t* slab_free = slab_cons + 2;               // [2] local: the TMA stores of pair slot ps have read the buffer
-  uint32_t* tmem_ptr = (uint32_t*)(slab_free + 2);
+  // V2: per ring stage — a_done (local, 8 epilogue warps: this CTA's d z slab is in the stage's A half), a_ready (leader's, both CTAs),
+  // sfree (local: the TMA store of the slab has read the stage)
+  uint64_t* a_done = slab_free + 2;
+  uint64_t* a_ready = a_done + STAGES;
+  uint64_t* sfree = a_ready + STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(sfree + STAGES);
+  // k-steps of a tile in ring order (all roles walk the same sequence): DG, un-shifted tap (one per d z slab), shifted taps / plain taps
+  auto tile_ksteps = [&](const TcStackBwdLayer& Ly, int& n_dg, int& n_un, int& n_sh) {
+    if (Ly.kind) { n_dg = 0; n_un = 0; n_sh = p.nseg * Ly.kb_tap; }
+    else { n_dg = (Ly.has_dx ? p.kb_dx : 0) + (Ly.has_ds ? p.kb_ds : 0); n_un = KB_Z; n_sh = (p.nseg - 1) * KB_Z; }
+  };
+  auto ring_adv = [&](int& rs, uint32_t& rp, int n) { rs += n; while (rs >= STAGES) { rs -= STAGES; rp ^= 1u; } };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -147,6 +167,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     for (int i = 0; i < Cfg::IN_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], NEPI); }
     for (int i = 0; i < Cfg::OUT_SLOTS; ++i) mbar_init(&oslot_empty[i], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&slab_done[i], NEPI); mbar_init(&slab_full[i], 2); mbar_init(&slab_cons[i], 1); mbar_init(&slab_free[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&a_done[i], NEPI); mbar_init(&a_ready[i], 2); mbar_init(&sfree[i], 1); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_ptr);
@@ -171,6 +192,13 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       auto next = [&]() { if (++stage == STAGES) { stage = 0; phase ^= 1; } };
+      // V2: a stage whose last use carried a d z slab is free again once the slab's TMA store has read it (bit per stage:
+      // un_pend = that wait is outstanding, un_wpar = parity to wait for, un_npar = parity of the stage's next slab use)
+      uint32_t un_pend = 0u, un_wpar = 0u, un_npar = 0u;
+      auto stage_wait = [&]() {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (V2 && ((un_pend >> stage) & 1u)) { mbar_wait(&sfree[stage], (un_wpar >> stage) & 1u); un_pend &= ~(1u << stage); }
+      };
       SBT_DECL(4)
       constexpr int WDG_BYTES = (D_ / 2) * 64 * 2, WB_BYTES = (R_ / 2) * 64 * 2;
       for (int j = 0; j < n_tiles; ++j) {
@@ -192,7 +220,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           fence_proxy_async_global();
           for (int s = 0; s < p.nseg; ++s)
             for (int kb = 0; kb < Ly.kb_tap; ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+              stage_wait();
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WB_BYTES));
               tma_load_3d_pair_h(sa, &Ly.tmDZ, &full_bar[stage], kb * 64, t0 + Ly.shift[s], b, p.pol_dz_ld);
@@ -211,7 +239,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
             SBT(1)
           }
           for (int kb = 0; kb < p.kb_dx; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            stage_wait();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WDG_BYTES));
             tma_load_4d_pair_h(sa, &Ly.tmDX, &full_bar[stage], kb * 64, t0, b, 0, p.pol_dx);
@@ -222,7 +250,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         if (Ly.has_ds) {
           const int k0 = (Ly.has_dx && !Ly.alias) ? p.kb_dx * 64 : 0;
           for (int kb = 0; kb < p.kb_ds; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            stage_wait();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WDG_BYTES));
             tma_load_4d_pair_h(sa, &Ly.tmDS, &full_bar[stage], kb * 64, t0, b, 0, p.pol_ds);
@@ -235,10 +263,14 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         for (int pr = 0; pr < NPAIR; ++pr) {
           for (int hh = 0; hh < 2; ++hh) {
             const int slab = hh == 0 ? pr : NPAIR + pr;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            stage_wait();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * WB_BYTES);
             tma_load_2d_pair_h(sa + Cfg::A_BYTES, &Ly.tmWb, &full_bar[stage], kloc + slab * 64, (int)crank * (R_ / 2), p.pol_w);
+            if (V2) {      // this stage's A half receives a d z slab from the epilogue
+              un_wpar = (un_wpar & ~(1u << stage)) | (((un_npar >> stage) & 1u) << stage);
+              un_npar ^= 1u << stage; un_pend |= 1u << stage;
+            }
             next();
           }
         }
@@ -253,7 +285,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           fence_proxy_async_global();
           SBT(2)
           for (int kb = 0; kb < KB_Z; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            stage_wait();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + WB_BYTES));
             tma_load_3d_pair_h(sa, &Ly.tmDZ, &full_bar[stage], kb * 64, t0 + Ly.shift[s], b, p.pol_dz_ld);
@@ -277,6 +309,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       int stage = 0; uint32_t phase = 0;
       uint32_t n_sf[2] = {0u, 0u};       // completed waits on slab_full[ps]
       uint32_t ng = 0u;                  // gated tiles so far
+      uint32_t ar_par = 0u;              // V2: per stage, parity of its next a_ready phase
       SBT_DECL(10)
       auto kstep = [&](uint32_t d_tmem, uint32_t idesc, bool a_from_dz, int slot, bool first, uint64_t* extra0, uint64_t* extra1) {
 #ifdef TC_TIMELINE
@@ -333,6 +366,17 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
         tc_fence_after();
         const int ks_sh = (p.nseg - 1) * KB_Z;
         bool first = true;
+        if constexpr (V2) {
+          for (int q = 0; q < KB_Z; ++q) {
+            // one hand-off per slab PAIR, on the barrier of the filter slab's stage: both CTAs' two slabs are in their stages' A halves
+            if ((q & 1) == 0) { mbar_wait(&a_ready[stage], (ar_par >> stage) & 1u); ar_par ^= 1u << stage; }
+            SBT(5)
+            tc_fence_after();
+            const bool last = ks_sh == 0 && q == KB_Z - 1;
+            kstep(t_out, idesc_o, false, 0, first, last ? out_full : nullptr, nullptr); first = false;
+            SBT(6)
+          }
+        } else
         for (int pr = 0; pr < NPAIR; ++pr) {
           const int ps = pr & 1;
           mbar_wait(&slab_full[ps], n_sf[ps] & 1u); ++n_sf[ps];     // both CTAs' slab pair is in shared memory
@@ -355,16 +399,18 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
   } else if (warp == 2) {
     // ===================== TMA-store warp + tile publisher =====================
     int oslot = 0;
-    uint64_t* pend = nullptr;       // barrier to release once the previously committed store group has read shared memory
-    auto committed = [&](uint64_t* rel) {
+    uint64_t* pend = nullptr;       // barrier(s) to release once the previously committed store group has read shared memory
+    uint64_t* pend2 = nullptr;
+    auto committed = [&](uint64_t* rel, uint64_t* rel2 = nullptr) {
       bulk_commit_group();
-      if (pend) { bulk_wait_group_read<1>(); mbar_arrive(pend); }
-      pend = rel;
+      if (pend) { bulk_wait_group_read<1>(); mbar_arrive(pend); if (pend2) mbar_arrive(pend2); }
+      pend = rel; pend2 = rel2;
     };
+    int s_rs = 0; uint32_t s_rp = 0u;      // V2: ring position at the start of the current tile
     auto publish = [&](int* flag) {
       // every store of this thread so far has landed -> visible to the async proxy of other SMs -> count this CTA in
       bulk_wait_group<0>();
-      if (pend) { mbar_arrive(pend); pend = nullptr; }
+      if (pend) { mbar_arrive(pend); if (pend2) mbar_arrive(pend2); pend = nullptr; pend2 = nullptr; }
       fence_proxy_async_global();
       __threadfence();
       red_release_gpu_add(flag, 1);
@@ -374,14 +420,29 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       locate(j, ly, mt, b, tb);
       const TcStackBwdLayer& Ly = layers[ly];
       const int t0 = tb * (2 * Cfg::BM) + pair_row0;
+      int n_dg, n_un, n_sh;
+      tile_ksteps(Ly, n_dg, n_un, n_sh);
       if (!Ly.kind) {
+      int u_rs = s_rs; uint32_t u_rp = s_rp;
+      ring_adv(u_rs, u_rp, n_dg);      // V2: stage of the first un-shifted-tap k-step
       for (int pr = 0; pr < NPAIR; ++pr) {
         const int ps = pr & 1;
+        if constexpr (V2) {
+          named_bar_sync(8 + pr, NEPI * 32 + 32);
+          const int sf = u_rs; ring_adv(u_rs, u_rp, 1);
+          const int ss = u_rs; ring_adv(u_rs, u_rp, 1);
+          if (lane == 0) {
+            tma_store_3d_h(smem + sf * Cfg::STAGE_BYTES, &Ly.tmDZ, pr * 64, t0, b, p.pol_dz_st);
+            tma_store_3d_h(smem + ss * Cfg::STAGE_BYTES, &Ly.tmDZ, D_ + pr * 64, t0, b, p.pol_dz_st);
+            committed(&sfree[sf], &sfree[ss]);
+          }
+        } else {
         named_bar_sync(8 + ps, NEPI * 32 + 32);
         if (lane == 0) {
           tma_store_3d_h(dzbuf + (2 * ps) * Cfg::A_BYTES, &Ly.tmDZ, pr * 64, t0, b, p.pol_dz_st);
           tma_store_3d_h(dzbuf + (2 * ps + 1) * Cfg::A_BYTES, &Ly.tmDZ, D_ + pr * 64, t0, b, p.pol_dz_st);
           committed(&slab_free[ps]);
+        }
         }
         __syncwarp();
       }
@@ -399,6 +460,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       }
       if (lane == 0) publish(flags_dx + (size_t)ly * p.num_mtiles + mt);
       __syncwarp();
+      ring_adv(s_rs, s_rp, n_dg + n_un + n_sh);
     }
     if (lane == 0) bulk_wait_group<0>();
   } else if (warp == 3) {
@@ -439,12 +501,29 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     // ===================== pair hand-off of the d z slabs =====================
     if (lane == 0) {
       uint32_t n_sd[2] = {0u, 0u};
+      int h_rs = 0; uint32_t h_rp = 0u, ad_par = 0u;      // V2: ring position, per-stage parity of the next a_done phase
       for (int j = 0; j < n_tiles; ++j) {
-        { int ly, mt, b, tb; locate(j, ly, mt, b, tb); if (layers[ly].kind) continue; }
+        int n_dg, n_un, n_sh;
+        { int ly, mt, b, tb; locate(j, ly, mt, b, tb); tile_ksteps(layers[ly], n_dg, n_un, n_sh); }
+        if constexpr (V2) {
+          int u_rs = h_rs; uint32_t u_rp = h_rp;
+          ring_adv(u_rs, u_rp, n_dg);
+          for (int q = 0; q < n_un; q += 2) {
+            mbar_wait(&a_done[u_rs], (ad_par >> u_rs) & 1u); ad_par ^= 1u << u_rs;
+            if (leader) mbar_arrive(&a_ready[u_rs]);
+            else if (p.relaxed_handoff) mbar_arrive_remote_relaxed(&a_ready[u_rs], 0u);
+            else mbar_arrive_remote(&a_ready[u_rs], 0u);
+            ring_adv(u_rs, u_rp, 2);
+          }
+          ring_adv(h_rs, h_rp, n_dg + n_un + n_sh);
+          continue;
+        }
+        if (n_un == 0) continue;
         for (int pr = 0; pr < NPAIR; ++pr) {
           const int ps = pr & 1;
           mbar_wait(&slab_done[ps], n_sd[ps] & 1u); ++n_sd[ps];
           if (leader) mbar_arrive(&slab_full[ps]);
+          else if (p.relaxed_handoff) mbar_arrive_remote_relaxed(&slab_full[ps], 0u);
           else mbar_arrive_remote(&slab_full[ps], 0u);
         }
       }
@@ -464,17 +543,23 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
     int oslot = 0; uint32_t ophase = 0;
     uint32_t n_use[2] = {0u, 0u};      // fills of slab pair slot ps so far
     uint32_t nge = 0u;                 // gated tiles so far
+    int e_rs = 0; uint32_t e_rp = 0u;                              // V2: ring position at the start of the current tile
+    uint32_t eu_pend = 0u, eu_wpar = 0u, eu_npar = 0u;             // V2: per-stage slab-store bookkeeping (see the producer)
+    uint8_t* slab_dst[2] = {nullptr, nullptr};                     // V2: A halves of the stages the current slab pair goes to
+    int slab_st[2] = {0, 0};
     const TcEpiGateBwd<true>::Params pg{D_};
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     SBT_DECL(10)
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
       int out_mode, out_act, kind;
+      int n_dg, n_un, n_sh;
       const uint8_t* mrow = nullptr;       // this row's keep-mask bytes (dropout on the conv branch this tile differentiates)
       {
         int ly, mt, b, tb;
         locate(j, ly, mt, b, tb);
         out_mode = layers[ly].out_mode; out_act = layers[ly].act; kind = layers[ly].kind;
+        tile_ksteps(layers[ly], n_dg, n_un, n_sh);
         const int tt = tb * (2 * Cfg::BM) + pair_row0 + row;
         if (layers[ly].mask && tt < p.T && b < p.B) mrow = layers[ly].mask + ((size_t)b * p.T + tt) * R_;
       }
@@ -485,6 +570,8 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       mbar_wait(dg_full, gpar);
       SBT(1)
       tc_fence_after();
+      int u_rs = e_rs; uint32_t u_rp = e_rp;
+      ring_adv(u_rs, u_rp, n_dg);          // V2: stage of the first un-shifted-tap k-step of this tile
       {
         TmemAccRow acc{tmem_base + lane_base, true};
 #pragma unroll 1
@@ -514,6 +601,21 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           if (++islot == Cfg::IN_SLOTS) { islot = 0; iphase ^= 1; }
           TcEpiGateBwd<true>::chunk(pg, acc, 0, step * 32 + q * 16, 0, 0, 3u, in, out, nullptr);
           SBT(2)
+          if constexpr (V2) {
+            if ((step & 1) == 0) {
+              // the two ring stages of this slab pair (filter slab, gate slab): free once the MMAs of their previous use have completed
+              // and, if that use carried a slab, its TMA store has read it
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                mbar_wait(&empty_bar[u_rs], u_rp ^ 1u);
+                if ((eu_pend >> u_rs) & 1u) { mbar_wait(&sfree[u_rs], (eu_wpar >> u_rs) & 1u); eu_pend &= ~(1u << u_rs); }
+                eu_wpar = (eu_wpar & ~(1u << u_rs)) | (((eu_npar >> u_rs) & 1u) << u_rs);
+                eu_npar ^= 1u << u_rs; eu_pend |= 1u << u_rs;
+                slab_st[k] = u_rs; slab_dst[k] = smem + u_rs * Cfg::STAGE_BYTES;
+                ring_adv(u_rs, u_rp, 1);
+              }
+            }
+          } else
           if ((step & 1) == 0 && n_use[ps] > 0) {
             // the slot still holds an earlier slab pair: its MMAs must have completed and its TMA stores read the buffer
             mbar_wait(&slab_cons[ps], (n_use[ps] - 1u) & 1u);
@@ -526,7 +628,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
             const uint32_t j0 = (uint32_t)(ch >> 3);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              uint8_t* gs = dzbuf + (2 * ps + k) * Cfg::A_BYTES + grow;
+              uint8_t* gs = (V2 ? slab_dst[k] : dzbuf + (2 * ps + k) * Cfg::A_BYTES) + grow;
               uint4 a, c;
               a.x = pack_bf16x2(out[k][0], out[k][1]); a.y = pack_bf16x2(out[k][2], out[k][3]);
               a.z = pack_bf16x2(out[k][4], out[k][5]); a.w = pack_bf16x2(out[k][6], out[k][7]);
@@ -539,9 +641,13 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
           if (step & 1) {
             // slab pair complete in this CTA: store warp (HBM copy) and, through the hand-off warp, the MMA side
             fence_proxy_async();
-            named_bar_arrive(8 + ps, NEPI * 32 + 32);
+            named_bar_arrive(8 + (V2 ? pr : ps), NEPI * 32 + 32);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&slab_done[ps]);
+            if constexpr (V2) {
+              if (lane == 0) mbar_arrive(&a_done[slab_st[0]]);      // (the pair's hand-off rides on the filter slab's stage)
+            } else {
+              if (lane == 0) mbar_arrive(&slab_done[ps]);
+            }
             ++n_use[ps];
           }
         }
@@ -607,6 +713,7 @@ tc_stack_bwd_kernel(const TcStackBwdLayer* __restrict__ layers, int* __restrict_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(out_empty, 0u);
+      ring_adv(e_rs, e_rp, n_dg + n_un + n_sh);
       SBT(6)
     }
 #ifdef TC_TIMELINE
@@ -716,15 +823,15 @@ static int tc_stack_bwd_build_t(TmapCache& tc, const std::vector<TcStackBwdDesc>
   return 0;
 }
 
-template <int D_, int R_>
+template <int D_, int R_, bool V2>
 static int tc_stack_bwd_launch_t(cudaStream_t st, const TcStackBwdPlan& plan, const TcStackBwdDesc& d0) {
-  using Cfg = TcStackBwdCfg<D_, R_>;
+  using Cfg = TcStackBwdCfg<D_, R_, V2>;
   TcStackBwdParams p{};
   p.B = d0.B; p.T = d0.T; p.tiles_t = (d0.T + 255) / 256; p.num_mtiles = d0.B * p.tiles_t; p.L = plan.L;
   p.nseg = d0.nseg; p.kb_dx = d0.R / 64; p.kb_ds = d0.S / 64; p.drop_scale = d0.drop_scale;
   p.pol_dx = tc_policy(TC_L2_NORMAL); p.pol_ds = tc_policy(TC_L2_LAST); p.pol_w = tc_policy(TC_L2_LAST); p.pol_z = tc_policy(TC_L2_FIRST);
   p.pol_dz_ld = tc_policy(TC_L2_NORMAL); p.pol_dz_st = tc_policy(TC_L2_LAST); p.pol_o = tc_policy(TC_L2_LAST);
-  auto kern = tc_stack_bwd_kernel<D_, R_>;
+  auto kern = tc_stack_bwd_kernel<D_, R_, V2>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -738,6 +845,9 @@ static int tc_stack_bwd_launch_t(cudaStream_t st, const TcStackBwdPlan& plan, co
     // (a tile then never waits for a tile of the round its own pair is in).
     // (Tried and dropped: issuing DG of a pair's next tile between the un-shifted and the shifted taps of the current one, to
     // fill the d z round trip through L2 — the OUT epilogue then no longer runs under those DG products: 1.79 -> 2.03 ms.)
+    static int relaxed = -1;
+    if (relaxed < 0) { const char* e = getenv("WN_TC_HANDOFF_RELAXED"); relaxed = (e && e[0] == '1') ? 1 : 0; }
+    p.relaxed_handoff = relaxed;
     static int band_target = -1;
     if (band_target < 0) { const char* e = getenv("WN_TC_SB_BAND"); band_target = e ? atoi(e) : 128; }
     int nb = band_target > 0 ? p.num_mtiles / band_target : 1;
@@ -781,8 +891,9 @@ static inline int tc_stack_bwd_build(TmapCache& tc, const std::vector<TcStackBwd
   if (d.D == 128 && d.R == 128) return tc_stack_bwd_build_t<128, 128>(tc, descs, plan);
   return -100;
 }
-static inline int tc_stack_bwd_launch(cudaStream_t st, const TcStackBwdPlan& plan, const TcStackBwdDesc& d) {
-  if (d.D == 256 && d.R == 256) return tc_stack_bwd_launch_t<256, 256>(st, plan, d);
-  if (d.D == 128 && d.R == 128) return tc_stack_bwd_launch_t<128, 128>(st, plan, d);
+// v2: d z slabs through the operand ring's A halves (5 stages, no separate operand buffer) — see TcStackBwdCfg
+static inline int tc_stack_bwd_launch(cudaStream_t st, const TcStackBwdPlan& plan, const TcStackBwdDesc& d, bool v2) {
+  if (d.D == 256 && d.R == 256) return v2 ? tc_stack_bwd_launch_t<256, 256, true>(st, plan, d) : tc_stack_bwd_launch_t<256, 256, false>(st, plan, d);
+  if (d.D == 128 && d.R == 128) return v2 ? tc_stack_bwd_launch_t<128, 128, true>(st, plan, d) : tc_stack_bwd_launch_t<128, 128, false>(st, plan, d);
   return -100;
 }

@@ -214,7 +214,7 @@ struct wn_handle {
   int use_stack_fwd = 1;    // WN_TC_STACK_FWD=0: one fused launch per block instead of one for the whole stack (gemm_tc_stack.cuh)
   std::vector<TcStackPlan> stack_plans;
   // backward chain (gate adjoint + dgrad of every block) as one persistent launch (gemm_tc_stack_bwd.cuh); WN_TC_STACK_BWD=0: per-block launches
-  int use_stack_bwd = 1, stack_bwd_layers = 0;
+  int use_stack_bwd = 2, stack_bwd_layers = 0;   // 2: d z slabs through the operand ring's A halves (5 stages), 1: separate operand buffer, 0: per-block chain
   std::vector<TcStackBwdPlan> stack_bwd_plans;
   int tile_gate_bwd = 0, tile_dgrad = 0;   // forced CTA tile widths of the two backward conv GEMMs (0 = widest that divides N)
   int fused_fwd_launches = 0;  // fused block-forward launches of the last step (0: separate gate / conv1 kernels)
@@ -677,7 +677,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   if (env_res && env_res[0] == '0') h->use_res_gemm = 0;
   { const char* e = getenv("WN_TC_FUSED_FWD"); if (e && e[0] == '0') h->use_fused_fwd = 0; }
   { const char* e = getenv("WN_TC_STACK_FWD"); if (e && e[0] == '0') h->use_stack_fwd = 0; }
-  { const char* e = getenv("WN_TC_STACK_BWD"); if (e && e[0] == '0') h->use_stack_bwd = 0; }
+  { const char* e = getenv("WN_TC_STACK_BWD"); if (e) h->use_stack_bwd = atoi(e); }      // 0: per-block chain, 1: first version, 2: slabs through the ring
   { const char* e = getenv("WN_TC_TILE_GATE_BWD"); if (e) h->tile_gate_bwd = atoi(e); }
   { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
@@ -1954,7 +1954,7 @@ static int model_backward(wn_handle* h, cudaStream_t st, const float* x, int ldx
         if (sp) {
           struct Label { wn_handle* h; Label(wn_handle* h_) : h(h_) { h->cur_label = "stack_bwd"; } ~Label() { h->cur_label = "misc"; } } lab(h);
           LaunchScope ls(h, st, CLS_DILATED);
-          r = tc_stack_bwd_launch(st, *sp, bdescs[0]);
+          r = tc_stack_bwd_launch(st, *sp, bdescs[0], h->use_stack_bwd >= 2);
           if (r == 0) { stacked = true; h->stack_bwd_layers = h->L; }
           else if (r == -100) h->launches--;
           else { set_err("stack backward launch failed (%d): %s", r, tc_last_error()); return WN_ERR_CUDA; }
