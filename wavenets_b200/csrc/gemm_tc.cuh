@@ -306,11 +306,10 @@ static int tc_conv_gemm_launch(TmapCache& tc, cudaStream_t st, const TcGemmDesc&
   p.nseg = d.nseg; p.n_outer = d.n_outer > 0 ? d.n_outer : 1;
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
   auto kern = tc_conv_gemm_kernel<Epi, BN, NEPI>;
-  static bool attr_done = false;   // per template instantiation
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;   // per template instantiation
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   const int grid = p.num_tiles < tc_num_sms() ? p.num_tiles : tc_num_sms();
   kern<<<grid, 128 + 32 * NEPI, Cfg::SMEM_BYTES, st>>>(*ma[0], *ma[1], *ma[2], *ma[3], *mw, p, ep);
@@ -794,11 +793,10 @@ static int tc_conv_gemm_staged_launch(TmapCache& tc, cudaStream_t st, const TcGe
   p.nseg = d.nseg; p.n_outer = d.n_outer > 0 ? d.n_outer : 1;
   for (int s = 0; s < d.nseg; ++s) { p.segK[s] = d.seg[s].K; p.segShift[s] = d.seg[s].shift; }
   auto kern = tc_conv_gemm_staged_kernel<Epi, BN, CG>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   const int slots = tc_balanced_slots(p.num_tiles, tc_num_sms() / CG);      // one CTA (or CTA pair) per SM (pair of SMs of a TPC)
   const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
@@ -1369,11 +1367,10 @@ static int tc_wgrad_pair_launch(TmapCache& tc, cudaStream_t st, const TcWgradDes
   const CUtensorMap* mp = tc.get(d.partial, 3, pd, ps, pb, 128, true);
   if (!mp) return -14;
   auto kern = tc_wgrad_pair_kernel<BN, NH>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * mpairs, ntiles, nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
@@ -1412,11 +1409,10 @@ template <int BN, int CL>
 static int tc_wgrad_launch_cl(const CUtensorMap* const* ma, const CUtensorMap* mg, const TcWgradParams& p, dim3 grid, cudaStream_t st) {
   using Cfg = TcWgradCfg<BN>;
   auto kern = tc_wgrad_kernel<BN, CL>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;

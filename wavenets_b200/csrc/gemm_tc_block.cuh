@@ -457,11 +457,10 @@ static int tc_block_fwd_launch(TmapCache& tc, cudaStream_t st, const TcBlockDesc
   p.pol_a = tc_policy(TC_L2_NORMAL); p.pol_w = tc_policy(TC_L2_LAST);
   p.pol_z = tc_policy(TC_L2_FIRST); p.pol_g = tc_policy(TC_L2_FIRST); p.pol_o = tc_policy(TC_L2_LAST);
   auto kern = tc_block_fwd_kernel<D_, R_>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   const int slots = tc_balanced_slots(p.num_mtiles, tc_num_sms() / 2);
   const int grid = (p.num_mtiles < slots ? p.num_mtiles : slots) * 2;

@@ -618,18 +618,19 @@ static int tc_stack_launch_t(cudaStream_t st, const TcStackPlan& plan, const TcB
   p.pol_a = tc_policy(TC_L2_NORMAL); p.pol_w = tc_policy(TC_L2_LAST);
   p.pol_z = tc_policy(TC_L2_FIRST); p.pol_g = tc_policy(TC_L2_FIRST); p.pol_o = tc_policy(TC_L2_LAST);
   auto kern = tc_stack_fwd_kernel<D_, R_>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   const int pairs = tc_stack_pairs(p.num_mtiles);
   if (p.num_mtiles <= pairs) return -100;
   {
     // every CTA pair of the launch must be resident at the same time (tiles wait for tiles of other pairs)
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
+    static int max_clusters_dev[64];
+    static unsigned long long mc_devs = 0ull;
+    int& max_clusters = max_clusters_dev[tc_current_device()];
+    if (tc_first_use_on_device(&mc_devs)) {
       cudaLaunchConfig_t oc{};
       oc.gridDim = dim3(tc_num_sms()); oc.blockDim = dim3(384); oc.dynamicSmemBytes = Cfg::SMEM_BYTES;
       cudaLaunchAttribute oa[1];

@@ -627,11 +627,10 @@ static int tc_wgrad_group_launch(cudaStream_t st, const TcWgGroupPlan& plan, int
   if (nunits <= 0) return 0;
   using Cfg = TcWgradPairCfg<256, 2>;
   auto kern = tc_wgrad_group_kernel;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return -12; }
-    attr_done = true;
   }
   TcWgGroupParams p{};
   p.maps = plan.d_maps; p.units = plan.d_units; p.cs = plan.d_cs; p.chunks_t = (plan.T + 63) / 64; p.unit_base = unit_base;

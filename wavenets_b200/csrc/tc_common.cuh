@@ -313,6 +313,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- host: per-device one-time setup
+// cudaFuncSetAttribute and occupancy queries are per DEVICE: a process may hold handles on several GPUs (WaveNet(device=...)), so the
+// "done once" state of every launcher is a bit per device ordinal, not a process-wide flag.  true the first time `mask` sees the
+// current device.
+static inline bool tc_first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  if ((*mask >> dev) & 1ull) return false;
+  *mask |= 1ull << dev;
+  return true;
+}
+static inline int tc_current_device() { int dev = 0; cudaGetDevice(&dev); return (dev < 0 || dev > 63) ? 0 : dev; }
+
 // ---------------------------------------------------------------- host: tensor maps
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -2180,8 +2180,8 @@ static int gen_alloc(wn_handle* h, int B, int cap) {
 
 static void gen_dense(cudaStream_t st, const GenVec& v, int B, const int* t_dev) {
   const size_t smem = (size_t)GEN_ROWS * v.K * v.Cin * 4;
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(gen_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_done = true; }
+  static unsigned long long attr_devs = 0ull;
+  if (tc_first_use_on_device(&attr_devs)) { cudaFuncSetAttribute(gen_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); }
   gen_dense_kernel<<<dim3(cdiv(v.N, 32), cdiv(B, GEN_ROWS)), 256, smem, st>>>(v, B, t_dev);
 }
 
