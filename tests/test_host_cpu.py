@@ -99,5 +99,10 @@ def test_checkpoint_names_and_resume_parse(tmp_path):
   assert ck.find_last_checkpoint(str(tmp_path / 'nope')) is None
   for e, lr in [(1, 0.0005), (12, 0.00025), (3, 0.0005)]:
     (tmp_path / ck.checkpoint_name(e, lr)).write_bytes(b'')
+  # a reference run's Keras file in the same directory sorts last but cannot be read here: it is not picked
+  (tmp_path / 'weights-e0099-lr0.0001.weights.h5').write_bytes(b'')
   path, epoch, lr = ck.find_last_checkpoint(str(tmp_path))
   assert path.endswith('weights-e0012-lr0.00025.weights.npz') and epoch == 12 and lr == 0.00025
+  import pytest
+  with pytest.raises(ValueError):
+    ck.load_weights(None, str(tmp_path / 'weights-e0099-lr0.0001.weights.h5'))

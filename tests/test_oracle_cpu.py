@@ -191,3 +191,43 @@ def test_faithful_rounding_ops():
   (R.bwd(x) * w).sum().backward()
   assert torch.equal(x.grad, w.to(torch.bfloat16).to(torch.float64))
   assert torch.equal(R.bwd(x).detach(), x.detach())
+
+
+def test_faithful_gate_caches_derivative_coefficients():
+  """The bf16 tier caches P = dg/dz_f and Q = dg/dz_s (evaluated on the un-rounded accumulator) instead of z; the faithful oracle's
+  gate adjoint is dz = bf16([dg * bf16(P) | dg * bf16(Q)]) — within bf16 rounding of the exact derivative, and exactly that formula."""
+  import torch
+  from oracle import faithful
+  rng = np.random.default_rng(3)
+  z = torch.tensor(rng.standard_normal((2, 5, 8)) * 2.0, dtype=torch.float64, requires_grad=True)
+  dg = torch.tensor(rng.standard_normal((2, 5, 4)), dtype=torch.float64)
+  g = faithful.Rounding(True).gate(z)
+  g.backward(dg)
+  D = 4
+  th, sg = torch.tanh(z[..., :D]).detach(), torch.sigmoid(z[..., D:]).detach()
+  P, Q = sg * (1 - th * th), th * sg * (1 - sg)
+  b = lambda t: t.to(torch.bfloat16).to(torch.float64)
+  want = b(torch.cat([dg * b(P), dg * b(Q)], -1))
+  assert torch.equal(z.grad, want)
+  exact = torch.cat([dg * P, dg * Q], -1)
+  assert float((z.grad - exact).abs().max()) <= 2.0 ** -7 * float(exact.abs().max())
+  assert torch.equal(g.detach(), th * sg)                      # the gate itself is evaluated on the un-rounded accumulator
+
+
+def test_faithful_oracle_dropout_equals_oracle():
+  """keep-masks: oracle/faithful.py in exact mode equals the NumPy oracle with the same injected masks (layers.py:192-196:
+  the conv branch sees keep * x / (1 - rate), the residual is taken before it)."""
+  from oracle import faithful
+  cfg = wo.Config(channels=16, blocks=3, layers_per_block=2, dilation_bound=4, skip_channels=16, final_layers_channels=[16], dropout=0.25,
+                  activation='leaky_relu')
+  p = wo.init_params(cfg, seed=1)
+  rng = np.random.default_rng(0)
+  x = np.clip(rng.standard_normal((2, 41, 1)) * 0.4, -1, 1)
+  keep = [(rng.random((2, 40, 16)) >= 0.25).astype(np.uint8) for _ in range(3)]
+  l0, g0, _ = wo.train_step(p, cfg, x, None, keep_masks=keep)
+  l1, g1 = faithful.train_step(p, cfg, x, None, faithful=False, keep_masks=keep)
+  assert abs(l0 - l1) <= 1e-12 * abs(l0)
+  for k in g0:
+    assert rel_err(g1[k], g0[k]) < 1e-9, k
+  l2, _ = faithful.train_step(p, cfg, x, None, faithful=False)
+  assert abs(l2 - l0) > 1e-6 * abs(l0)                         # the masks do something
