@@ -12,7 +12,5 @@ cap() {  # cfg kernel-regex name
 rm -f gpurun_out/*.ncu-rep
 python scripts/prof_step.py c2 3 > gpurun_out/plain_${TAG}.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_${TAG}.log; exit 1; }
 cap c2 tc_stack_bwd c2_stackbwd
-cap c2 tc_stack_fwd c2_stackfwd
-cap c2 tc_wgrad_group_kernel c2_wgroup
-cap c3 tc_stack_fwd c3_stackfwd
-cap c5 tc_stack_bwd c5_stackbwd
+cap c3 tc_stack_bwd c3_stackbwd
+cap c3 tc_wgrad_group_kernel c3_wgroup
