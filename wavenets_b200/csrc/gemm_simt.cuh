@@ -61,42 +61,58 @@ __global__ void __launch_bounds__(256) conv_gemm_simt(ConvGemmArgsF a, typename 
 
   const int lr = tid >> 2, lk = (tid & 3) << 2;   // A loader: row lr, k offset lk..lk+3
   const int wk = tid >> 4, wn = (tid & 15) << 2;  // W loader: k row wk, cols wn..wn+3
-  int wrow = 0;
-  for (int o = 0; o < a.n_outer; ++o) {
-    for (int s = 0; s < a.nseg; ++s) {
-      const SegF sg = a.seg[s];
-      const float* Ab = sg.A + (s == 0 ? (long long)o * a.a_outer_stride : 0);
-      const int ta = t0 + lr + sg.shift;
-      const bool rok = (ta >= 0) && (ta < a.T);
-      const float* arow = Ab + ((long long)b * a.T + ta) * sg.lda;
-      for (int k0 = 0; k0 < sg.K; k0 += 16) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = k0 + lk + i;
-          As[lk + i][lr] = (rok && k < sg.K) ? arow[k] : 0.f;
-        }
-        {
-          const int k = k0 + wk;
-          float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < sg.K) w = *reinterpret_cast<const float4*>(a.W + (long long)(wrow + k) * a.Npad + n0 + wn);
-          *reinterpret_cast<float4*>(&Bs[wk][wn]) = w;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty << 2]);
-          const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx << 2]);
-          const float aa[4] = {av.x, av.y, av.z, av.w};
-          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
-        }
-        __syncthreads();
-      }
-      wrow += sg.K;
+  // Software pipeline over the K chunks of all (outer, segment) pairs: the global loads of chunk i+1 are issued before the FMAs of
+  // chunk i.  At the reference's default width a CTA runs 8 chunks of 16 k: un-pipelined, every chunk paid a full global-load
+  // round trip between two barriers, which is most of an 11 us launch (the fp32 tier's C1 step is ~140 such launches).
+  struct Chunk { int o, s, k0, wrow; };
+  auto first = [&]() { return Chunk{0, 0, 0, 0}; };
+  auto valid = [&](const Chunk& c) { return c.o < a.n_outer; };
+  auto advance = [&](Chunk c) {
+    c.k0 += 16;
+    if (c.k0 >= a.seg[c.s].K) {
+      c.wrow += a.seg[c.s].K; c.k0 = 0; ++c.s;
+      if (c.s >= a.nseg) { c.s = 0; ++c.o; }
     }
+    return c;
+  };
+  auto fetch = [&](const Chunk& c, float (&ra)[4], float4& rw) {
+    const SegF sg = a.seg[c.s];
+    const float* Ab = sg.A + (c.s == 0 ? (long long)c.o * a.a_outer_stride : 0);
+    const int ta = t0 + lr + sg.shift;
+    const bool rok = (ta >= 0) && (ta < a.T);
+    const float* arow = Ab + ((long long)b * a.T + ta) * sg.lda;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = c.k0 + lk + i;
+      ra[i] = (rok && k < sg.K) ? arow[k] : 0.f;
+    }
+    const int k = c.k0 + wk;
+    rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < sg.K) rw = *reinterpret_cast<const float4*>(a.W + (long long)(c.wrow + k) * a.Npad + n0 + wn);
+  };
+  Chunk cur = first();
+  float ra[4]; float4 rw;
+  if (valid(cur)) fetch(cur, ra, rw);
+  while (valid(cur)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[lk + i][lr] = ra[i];
+    *reinterpret_cast<float4*>(&Bs[wk][wn]) = rw;
+    __syncthreads();
+    const Chunk nxt = advance(cur);
+    if (valid(nxt)) fetch(nxt, ra, rw);      // in flight while this chunk is multiplied
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty << 2]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx << 2]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+    cur = nxt;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -119,8 +135,11 @@ struct WgradArgsF {
   int nseg;
   SegF seg[WN_MAX_SEG];  // A operands; output rows are (seg, c)
   int ktot;
-  float* partial;   // [nsplit][ktot][N]
+  float* partial;   // [nsplit][ktot (+ 1)][N]
   int chunks_per_split;  // 16-row chunks handled by one blockIdx.z
+  int cs_row;       // != 0: row ktot of every partial holds the column sums of G over the split's rows (bias gradient rides along:
+                    // the G tile is in shared memory anyway — two extra launches per conv otherwise, and the fp32 tier at the
+                    // reference's default width is launch bound: 209 launches per C1 step)
 };
 
 // output tile 64 (k) x 64 (n); rows consumed in chunks of 16
@@ -147,9 +166,13 @@ __global__ void __launch_bounds__(256) wgrad_simt(WgradArgsF a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int chunks_per_b = (a.T + 15) >> 4;
   const int total = a.B * chunks_per_b;
+  const bool do_cs = a.cs_row != 0 && blockIdx.x == 0 && tid < 64;      // one k tile per (n tile, split) sums the columns
+  float csum = 0.f;
   const int c_begin = blockIdx.z * a.chunks_per_split;
   const int c_end = min(total, c_begin + a.chunks_per_split);
-  for (int ch = c_begin; ch < c_end; ++ch) {
+  // same software pipeline over the 16-row chunks: the loads of chunk ch+1 fly while chunk ch is multiplied
+  float ra[4], rg[4];
+  auto fetch = [&](int ch) {
     const int b = ch / chunks_per_b;
     const int t = ((ch % chunks_per_b) << 4) + lr;
     const int ta = t + sg.shift;
@@ -158,10 +181,20 @@ __global__ void __launch_bounds__(256) wgrad_simt(WgradArgsF a) {
     const float* grow = a.G + ((long long)b * a.T + t) * a.ldg + n0 + lc;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      As[lr][lc + i] = (aok && (k0 + lc + i) < sg.K) ? arow[i] : 0.f;
-      Gs[lr][lc + i] = ((t < a.T) && (n0 + lc + i) < a.N) ? grow[i] : 0.f;
+      ra[i] = (aok && (k0 + lc + i) < sg.K) ? arow[i] : 0.f;
+      rg[i] = ((t < a.T) && (n0 + lc + i) < a.N) ? grow[i] : 0.f;
     }
+  };
+  if (c_begin < c_end) fetch(c_begin);
+  for (int ch = c_begin; ch < c_end; ++ch) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[lr][lc + i] = ra[i]; Gs[lr][lc + i] = rg[i]; }
     __syncthreads();
+    if (ch + 1 < c_end) fetch(ch + 1);
+    if (do_cs) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) csum += Gs[r][tid];
+    }
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const float4 av = *reinterpret_cast<const float4*>(&As[r][ty << 2]);
@@ -175,7 +208,8 @@ __global__ void __launch_bounds__(256) wgrad_simt(WgradArgsF a) {
     }
     __syncthreads();
   }
-  float* out = a.partial + (long long)blockIdx.z * a.ktot * a.N;
+  float* out = a.partial + (long long)blockIdx.z * (a.ktot + (a.cs_row ? 1 : 0)) * a.N;
+  if (do_cs && n0 + tid < a.N) out[(long long)a.ktot * a.N + n0 + tid] = csum;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = k0 + (ty << 2) + i;

@@ -193,6 +193,24 @@ __global__ void reduce_parts(const float* __restrict__ partial, int n_parts, lon
   out[j] = s;
 }
 
+// two destinations: out0[j] for j < n0 (+ addend0[j]*add_coef), out1[j - n0] for n0 <= j < n0 + n1 (a filter gradient with its bias row)
+__global__ void reduce_parts2(const float* __restrict__ partial, int n_parts, long long stride, float* __restrict__ out0, long long n0,
+                              float* __restrict__ out1, long long n1, const float* __restrict__ addend0, float add_coef) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n0 + n1) return;
+  float s0 = 0.f, s1 = 0.f;
+  int i = 0;
+  for (; i + 1 < n_parts; i += 2) { s0 += partial[i * stride + j]; s1 += partial[(i + 1) * stride + j]; }
+  if (i < n_parts) s0 += partial[i * stride + j];
+  float s = s0 + s1;
+  if (j < n0) {
+    if (addend0) s = fmaf(add_coef, addend0[j], s);
+    out0[j] = s;
+  } else {
+    out1[j - n0] = s;
+  }
+}
+
 // same contract for MANY partials (hundreds): 32 outputs x 8 partial-lanes per block, fixed summation order
 __global__ void __launch_bounds__(256) reduce_parts_tall(const float* __restrict__ partial, int n_parts, long long stride, float* __restrict__ out,
                                                          long long n, const float* __restrict__ addend, float add_coef) {

@@ -470,7 +470,7 @@ static void layout_buffers(wn_handle* h) {
   h->colpart = (float*)W.take(colpart_elems * 4);
   // wgrad partials: nsplit * ktot * N, largest contraction
   long long maxkn = 0;
-  auto upd = [&](long long k, long long n) { if (k * n > maxkn) maxkn = k * n; };
+  auto upd = [&](long long k, long long n) { if ((k + 1) * n > maxkn) maxkn = (k + 1) * n; };      // (+ 1: the fp32 tier's column-sum row)
   for (auto& b : h->blocks) {
     for (auto& c : b.stack) upd((long long)c.K * c.cin, c.cout);
     upd(D, R);
@@ -1001,9 +1001,19 @@ static int run_wgrad(wn_handle* h, cudaStream_t st, int cls, const WgradH& g) {
     a.B = g.B; a.T = g.T; a.N = g.N; a.G = (const float*)g.G; a.ldg = g.ldg; a.nseg = g.nseg; a.ktot = ktot;
     for (int s = 0; s < g.nseg; ++s) a.seg[s] = SegF{(const float*)g.seg[s].A, g.seg[s].lda, g.seg[s].shift, g.seg[s].K};
     a.partial = h->wg_partial; a.chunks_per_split = cps;
+    // bias gradient = column sums of G: they ride along as row ktot of the partials (per-batch sums, i.e. conditioned gated convs,
+    // keep the separate column-sum launches)
+    const bool cs_row = g.bias_dst != nullptr && g.per_batch == nullptr;
+    a.cs_row = cs_row ? 1 : 0;
     {
       LaunchScope ls(h, st, cls);
       wgrad_simt<<<dim3(ktiles, ntiles, nsplit), 256, 0, st>>>(a);
+    }
+    if (cs_row) {
+      LaunchScope ls(h, st, cls);
+      const long long n = (long long)ktot * g.N;
+      reduce_parts2<<<cdiv(n + g.N, 256), 256, 0, st>>>(h->wg_partial, nsplit, n + g.N, g.dst, n, g.bias_dst, g.N, g.l2coef != 0.f ? g.w : nullptr, g.l2coef);
+      return WN_OK;
     }
     if (g.bias_dst || g.per_batch) run_colsum<T>(h, st, g.G, g.ldg, g.B, g.T, g.N, g.per_batch, g.ldpb, g.bias_dst);
   } else {
