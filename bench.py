@@ -609,7 +609,7 @@ def main():
       logs = model.train_step(data_dev)
     sync_all()
     line['full_iteration'] = {'ms': (time.perf_counter() - t0) / n_it * 1e3, 'includes': 'fwd+loss+bwd, clipnorm, Adam, re-pack, sampled-waveform MSE',
-                              'loss': logs['loss'], 'mean_squared_error': logs.get('mean_squared_error')}
+                              'loss': model.last_step_logs['loss'], 'mean_squared_error': logs.get('mean_squared_error')}
   sys.stdout.flush()
   os.dup2(saved_stdout, 1)
   os.close(saved_stdout)

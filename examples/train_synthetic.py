@@ -72,7 +72,12 @@ def main():
 
   rng = np.random.default_rng(1)
   t0, best, pending = time.perf_counter(), float('inf'), None
+  steps_per_epoch = 20                       # Keras `fit` resets the metric trackers every epoch; the logs are running means
   for step in range(args.steps):
+    if step and step % steps_per_epoch == 0:
+      if pending is not None:
+        pending.result()
+      model.reset_metrics()
     idx = torch.from_numpy(rng.choice(frames.shape[0], B, replace=frames.shape[0] < B)).to(frames.device)
     batch = (frames[idx], conds[idx]) if conds is not None else frames[idx]
     nxt = model.train_step_deferred(batch)
@@ -83,6 +88,7 @@ def main():
       best = min(best, logs['loss'])
     pending = nxt
   logs = pending.result()
+  logs = dict(model.last_step_logs)          # the last step's own values (the dict above holds the epoch's running means)
   torch.cuda.synchronize()
   dt = time.perf_counter() - t0
   print(f'{args.steps} steps in {dt:.2f} s ({args.steps * B * T / dt / 1e6:.2f} M samples/s incl. optimizer and metrics), last loss {logs["loss"]:.4f}')

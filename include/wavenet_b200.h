@@ -212,6 +212,11 @@ const char* wn_nccl_info(void);   /* "NCCL <version> from <path>" or "unavailabl
  * block are written into wn_grads_dev(). */
 int wn_layer_forward(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T,
                      float* x_out_dev, float* skip_dev, void* stream);
+/* WaveNetLayer.call(inputs, training) (layers.py:178,192-196): training != 0 applies the block's inverted dropout to the
+ * conv branch (the residual keeps the un-masked input); the keep-mask is the injected one (wn_set_dropout_masks) or a fresh
+ * Philox draw for this block, and wn_layer_backward of the block uses the same mask. */
+int wn_layer_forward_ex(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T, int training,
+                        float* x_out_dev, float* skip_dev, void* stream);
 int wn_layer_backward(wn_handle* h, int block, const float* dx_out_dev, const float* dskip_dev,
                       float* dx_dev, float* dcond_dev, void* stream);
 

@@ -64,7 +64,13 @@ CASES = {
   # dropout with an injected keep-mask (TF's RNG stream is not reproducible; the mask is part of the fixture)
   'dropout_mask': (dict(channels=16, blocks=2, layers_per_block=2, dilation_bound=4, final_layers_channels=[16],
                         activation='leaky_relu', dropout=0.25, skip_channels=16), 0, 2, 48, 1),
+  # saturated softmax: the logits conv is scaled up (WEIGHT_SCALE) until most class probabilities and a part of the TARGET
+  # probabilities leave [1e-7, 1 - 1e-7] -- Keras 3's clip inside sparse_categorical_crossentropy (model.py:516) is active
+  'cat_saturated': (dict(channels=16, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[32, 32],
+                         activation='tanh', skip_channels=16, bits=8), 0, 2, 96, 1),
 }
+# per-case multipliers on the seeded weights (stored scaled in the fixture)
+WEIGHT_SCALE = {'cat_saturated': {'final2/kernel': 150.0}}
 
 
 def make_inputs(B, T, cond_in, seed):
@@ -109,6 +115,8 @@ def run_case(name, kw, cond_in, B, T, nrep):
   model(inputs)                                   # build-by-call, like train.py:232-235
   # ---- weights: oracle-named, seeded, rounded to fp32 so every tier sees identical values
   p = {k: v.astype(np.float32) for k, v in wo.init_params(cfg, seed=1).items()}
+  for k, f in WEIGHT_SCALE.get(name, {}).items():
+    p[k] = (p[k] * np.float32(f)).astype(np.float32)
   pairs = ref_variables(model)
   assert [n for n, _ in pairs] == [n for n, _ in wo.param_specs(cfg)], 'variable naming / order'
   assert all(a is b for (_, a), b in zip(pairs, model.trainable_variables)), 'Keras tracking order'
@@ -168,9 +176,20 @@ def run_case(name, kw, cond_in, B, T, nrep):
     out['layer0/x'] = h0.numpy().astype(np.float32)
     out['layer0/x_out'] = xo.numpy().astype(np.float32)
     out['layer0/skip'] = sk.numpy().astype(np.float32)
+    if kw.get('dropout', 0) > 0 and ct is None:
+      # WaveNetLayer.call(training=True): dropout on the conv branch with the injected keep-mask of block 0 (layers.py:192-196)
+      xo, sk = blk(h0, training=True)
+      out['layer0/x_out_train'] = xo.numpy().astype(np.float32)
+      out['layer0/skip_train'] = sk.numpy().astype(np.float32)
+    if cfg.num_mixtures is None:
+      pn = pred.numpy()
+      out['clip_stats'] = np.array([((pn < 1e-7) | (pn > 1 - 1e-7)).mean(),
+                                    (np.take_along_axis(pn, tgt.numpy().reshape(B, T, 1).astype(np.int64), -1) < 1e-7).mean()])
   os.makedirs(OUT, exist_ok=True)
   np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
   nbytes = os.path.getsize(os.path.join(OUT, name + '.npz'))
+  if 'clip_stats' in out:
+    print(f'{name:22s} clipped probabilities {out["clip_stats"][0]:.3f}, clipped targets {out["clip_stats"][1]:.3f}')
   print(f'{name:22s} loss={out["train_loss"]:.6f} test={out["test_loss"]:.6f} rf={int(out["receptive_field"])} '
         f'params={sum(w.size for w in p.values())} file={nbytes / 1024:.0f} KB')
 
@@ -213,7 +232,10 @@ def known_answers():
 
 if __name__ == '__main__':
   torch.manual_seed(0)
+  only = sys.argv[1:]          # `python oracle/make_golden.py [case ...]`: regenerate only the named fixtures
   for name, (kw, cond_in, B, T, nrep) in CASES.items():
-    run_case(name, kw, cond_in, B, T, nrep)
+    if not only or name in only:
+      run_case(name, kw, cond_in, B, T, nrep)
   tf.set_num_replicas(1)
-  known_answers()
+  if not only or 'known_answers' in only:
+    known_answers()

@@ -85,8 +85,16 @@ def forward_logits(p, cfg: wo.Config, x, cond_in=None):
 def loss_per_sample(cfg: wo.Config, logits, y):
   """model.py:505-551 on logits; y (B,T,1)."""
   if cfg.sampling_function == 'categorical':
+    # sparse_categorical_crossentropy on the softmax output, Keras 3 [TF-internal, restated]: clip(p, 1e-7, 1 - 1e-7), log,
+    # then sparse softmax cross entropy on those "logits" (= plain cross entropy on the logits while nothing is clipped)
     idx = torch.from_numpy(wo.discretize(y[..., 0].detach().numpy(), cfg.bits))
-    return F.cross_entropy(logits.reshape(-1, logits.shape[-1]), idx.reshape(-1), reduction='none').reshape(idx.shape)
+    logp = torch.log_softmax(logits, dim=-1)
+    pr = torch.exp(logp)
+    inside = (pr >= 1e-7) & (pr <= 1.0 - 1e-7)
+    c = torch.clamp(pr, 1e-7, 1.0 - 1e-7)
+    logc = torch.where(inside, logp, torch.log(c))           # log(p) evaluated as logit - lse where the clip is inactive
+    lognorm = torch.log1p((c - pr).sum(-1))                  # log(sum_j c_j), sum_j p_j == 1
+    return lognorm - torch.gather(logc, -1, idx.long().unsqueeze(-1)).squeeze(-1)
   w, mu, ls = torch.chunk(logits, 3, dim=-1)
   pi = torch.softmax(w, dim=-1)
   ls = torch.clamp_min(ls, -7.0)

@@ -415,13 +415,31 @@ def loss_and_dlogits(cfg: Config, logits, y, scale):
   (x[:,1:,:], model.py:319-320)."""
   dt = logits.dtype
   if cfg.sampling_function == 'categorical':
+    # tf.keras.losses.sparse_categorical_crossentropy(target, probs) on the softmax OUTPUT (model.py:114-118,516), Keras 3
+    # TF backend [TF-internal, restated; the shim executes the same definition]: c = clip(p, 1e-7, 1 - 1e-7), then sparse
+    # softmax cross entropy with log(c) as logits:  l = log(sum_j c_j) - log(c_y).  The clip passes gradient only where
+    # 1e-7 <= p <= 1 - 1e-7.  With nothing clipped this is lse - logit_y and softmax - onehot.
     idx = discretize(y[..., 0], cfg.bits)
+    eps = 1e-7
     m = logits.max(axis=-1, keepdims=True)
     lse = m[..., 0] + np.log(np.exp(logits - m).sum(axis=-1))
-    picked = np.take_along_axis(logits, idx[..., None], axis=-1)[..., 0]
-    loss = lse - picked
-    d = np.exp(logits - lse[..., None])
-    np.put_along_axis(d, idx[..., None], np.take_along_axis(d, idx[..., None], -1) - 1.0, axis=-1)
+    logp = logits - lse[..., None]
+    p = np.exp(logp)
+    inside = ((p >= eps) & (p <= 1.0 - eps)).astype(dt)
+    c = np.clip(p, eps, 1.0 - eps)
+    # sum_j c_j = 1 + sum_j (c_j - p_j): only clipped entries contribute, so an unclipped row gives exactly lse - logit_y
+    S = 1.0 + (c - p).sum(axis=-1)
+    in_y = np.take_along_axis(inside, idx[..., None], axis=-1)[..., 0]
+    logp_y = np.take_along_axis(logp, idx[..., None], axis=-1)[..., 0]
+    c_y = np.take_along_axis(c, idx[..., None], axis=-1)[..., 0]
+    log_cy = np.where(in_y > 0, logp_y, np.log(c_y))
+    loss = np.log(S) - log_cy
+    # u_j = dl/dp_j = inside_j (1/S - [j == y]/c_y);  dl/dlogit_k = p_k (u_k - sum_j p_j u_j)
+    Pm = (inside * p).sum(axis=-1)
+    u = inside / S[..., None]
+    np.put_along_axis(u, idx[..., None], np.take_along_axis(u, idx[..., None], -1) - (in_y / c_y)[..., None], axis=-1)
+    dot = Pm / S - in_y          # in_y * p_y / c_y == in_y
+    d = p * (u - dot[..., None])
     return loss, d * scale
   M = cfg.num_mixtures
   w, mu, ls_raw = logits[..., :M], logits[..., M:2 * M], logits[..., 2 * M:]

@@ -31,6 +31,10 @@ CASES = {
                          activation='leaky_relu'), 0),
   'dropout_mask': (dict(channels=16, blocks=2, layers_per_block=2, dilation_bound=4, final_layers_channels=[16],
                         activation='leaky_relu', dropout=0.25, skip_channels=16), 0),
+  # logits conv scaled x150 in the fixture: 39 % of the class probabilities and 38 % of the target probabilities are
+  # outside [1e-7, 1 - 1e-7], so Keras 3's clip inside sparse_categorical_crossentropy (model.py:516) is active
+  'cat_saturated': (dict(channels=16, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[32, 32],
+                         activation='tanh', skip_channels=16, bits=8), 0),
 }
 
 
@@ -50,6 +54,9 @@ def load_case(name):
   c.reg_loss = float(z['reg_loss']) if 'reg_loss' in z.files else None
   c.layer0_x, c.layer0_x_out, c.layer0_skip = z['layer0/x'], z['layer0/x_out'].astype(np.float64), z['layer0/skip'].astype(np.float64)
   c.layer0_cond = z['layer0/cond'] if 'layer0/cond' in z.files else None
+  c.layer0_x_out_train = z['layer0/x_out_train'].astype(np.float64) if 'layer0/x_out_train' in z.files else None
+  c.layer0_skip_train = z['layer0/skip_train'].astype(np.float64) if 'layer0/skip_train' in z.files else None
+  c.clip_stats = z['clip_stats'] if 'clip_stats' in z.files else None
   c.keep_masks = None
   if kw.get('dropout', 0) > 0:
     n = B * T * kw['channels']

@@ -92,6 +92,58 @@ def test_layer_call_matches_reference_golden(name):
   assert rel_err(sk.cpu().numpy(), c.layer0_skip) < TOL
 
 
+def test_layer_call_training_dropout_matches_reference_golden():
+  """WaveNetLayer.call(training=True) (layers.py:178,192-196) with the fixture's injected keep-mask: forward against the
+  reference-source golden, the adjoint (dx and every weight gradient) against the oracle with the same mask; training=False and a
+  cleared mask behave as Keras does (no dropout / fresh masks per call)."""
+  from oracle import wavenet_oracle as wo
+  from wavenets_b200 import WaveNetLayer
+  c = load_case('dropout_mask')
+  kw = c.kw
+  lay = WaveNetLayer(kernel=2, dilation_rate=[int(d) for d in c.dilations[0]], activation=kw['activation'], channels=kw['channels'],
+                     skip_channels=kw['skip_channels'], dropout=kw['dropout'])
+  x = c.layer0_x
+  lay.build(x.shape)
+  w = {k[len('block0/'):]: v for k, v in c.weights.items() if k.startswith('block0/')}
+  lay.set_weights(w)
+  lay.set_dropout_mask(c.keep_masks[0])
+  xo, sk = lay.call(x, training=True)
+  assert rel_err(xo.cpu().numpy(), c.layer0_x_out_train) < TOL
+  assert rel_err(sk.cpu().numpy(), c.layer0_skip_train) < TOL
+  # adjoint with seeded cotangents
+  rng = np.random.default_rng(5)
+  dxo, dsk = rng.standard_normal(xo.shape).astype(np.float32), rng.standard_normal(sk.shape).astype(np.float32)
+  dx, _ = lay.backward(dxo, dsk)
+  p = {k: v.astype(np.float64) for k, v in c.weights.items()}
+  lc = wo._layer_cfgs(c.cfg)[0]
+  _, _, cache = wo.layer_forward(p, 'block0', lc, x.astype(np.float64), None, keep=c.keep_masks[0], rate=c.cfg.dropout)
+  dx_o, _, g_o = wo.layer_backward(p, 'block0', lc, cache, dxo.astype(np.float64), dsk.astype(np.float64))
+  assert rel_err(dx.cpu().numpy(), dx_o) < TOL
+  g = lay.get_grads()
+  for k, ref in g_o.items():
+    assert rel_err(g[k[len('block0/'):]], ref) < TOL, k
+  # inference mode ignores the mask
+  xo0, sk0 = lay.call(x, training=False)
+  assert rel_err(xo0.cpu().numpy(), c.layer0_x_out) < TOL and rel_err(sk0.cpu().numpy(), c.layer0_skip) < TOL
+  # built-in Philox masks: a new one per call, the conv branch really is masked
+  lay.set_dropout_mask(None)
+  a, _ = lay.call(x, training=True)
+  b, _ = lay.call(x, training=True)
+  assert float((a - b).abs().max()) > 1e-3
+  assert float((a - xo0).abs().max()) > 1e-3
+
+
+def test_saturated_softmax_takes_the_keras3_clip():
+  """`cat_saturated` also runs in the parametrised test above; here: the clipped rows really are on the clipped branch (the
+  per-row loss tops out at -log(1e-7) + log(sum of clipped probabilities)), through loss_fn on the model's own output too."""
+  c = load_case('cat_saturated')
+  m = _build(c, 'fp32')
+  pred = m(c.x[:, :-1])
+  per = m.loss_fn(m.prepare_target(c.x[:, 1:, :]), pred).cpu().numpy().reshape(c.B, c.T)
+  assert rel_err(per, c.loss_per_sample) < TOL
+  assert abs(per.max() + np.log(1e-7)) < 1e-3
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_dropout_philox_masks(precision):
   """Built-in masks: fresh per step (also under CUDA-graph replay), reproducible from the seed,

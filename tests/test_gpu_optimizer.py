@@ -29,7 +29,8 @@ def test_adam_clipnorm_trajectory(name, precision, tol):
   clipped_any = False
   for step in range(4):
     loss_o, g_o, aux = wo.train_step(p, cfg, x.astype(np.float64), c64)
-    out = m.train_step(data)
+    m.train_step(data)
+    out = m.last_step_logs          # (a compiled model's train_step returns Keras' running means, model.py:340-348)
     assert abs(out['loss'] - aux['loss_no_reg']) <= 10 * tol * abs(loss_o), (step, out['loss'], aux['loss_no_reg'])
     norms = opt.grad_norms(m)
     for k, g in g_o.items():
@@ -61,9 +62,16 @@ def test_adam_bf16_tier_trains():
   m = WaveNet(**kw, precision='bf16')
   m.compile(optimizer=Adam(learning_rate=2e-3, clipnorm=1.0))
   m.build(x[:, :-1].shape)
-  losses = [m.train_step(x)['loss'] for _ in range(12)]
+  losses, means = [], []
+  for _ in range(12):
+    means.append(m.train_step(x)['loss'])
+    losses.append(m.last_step_logs['loss'])
   assert losses[-1] < 0.97 * losses[0] and all(b < a for a, b in zip(losses, losses[1:])), losses
+  # the returned 'loss' is the running mean of the loss tracker (model.py:166,340-348) until reset_metrics()
+  assert all(abs(mu - np.mean(losses[:i + 1])) <= 1e-6 * abs(mu) for i, mu in enumerate(means))
+  m.reset_metrics()
   assert m.test_step(x)['loss'] < losses[0]
+  assert m.train_step(x)['loss'] != means[-1] and len(m.metrics) == 1
 
 
 def test_checkpoint_round_trip(tmp_path):
@@ -103,5 +111,7 @@ def test_train_step_deferred_matches_train_step():
   outs = [h.result() for h in handles]
   assert outs[0]['loss'] == ref['loss'] and outs[0]['reg_loss'] == ref['reg_loss']
   assert outs[0]['mean_squared_error'] == ref['mean_squared_error']
-  assert outs[1]['loss'] == ref['loss'] and outs[2]['loss'] == ref['loss']
+  # no optimizer: every step has the same loss, and so has the running mean
+  assert outs[1]['loss'] == ref['loss'] and abs(outs[2]['loss'] - ref['loss']) <= 1e-12 * abs(ref['loss'])
+  assert m.last_step_logs['loss'] == ref['loss'] and m.loss_tracker.count == 3
   assert handles[0].result() is outs[0]

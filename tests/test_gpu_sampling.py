@@ -90,5 +90,6 @@ def test_mse_metric_inside_train_step():
   assert abs(out['loss'] - c.train_loss) <= 1e-4 * abs(c.train_loss)
   sample = m._staging['sample'].cpu().numpy().reshape(c.B, c.T)
   assert abs(out['mean_squared_error'] - float(((c.x[:, 1:, 0] - sample) ** 2).mean())) < 1e-5
+  m.reset_metrics()               # (Keras `evaluate` does; otherwise 'loss' is the running mean over both steps)
   t = m.test_step(c.x)
   assert set(t) == {'loss', 'mean_squared_error'} and abs(t['loss'] - c.test_loss) <= 1e-4 * abs(c.test_loss)

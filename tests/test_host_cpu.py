@@ -63,6 +63,29 @@ def test_constructor_validation_matches_reference():
     m.compile(loss='mse')
 
 
+def test_compiled_model_reports_keras_running_means():
+  """model.py:166-168,340-360: a compiled model's logs are the running means of loss_tracker / reg_loss / compiled metrics
+  since the last reset_metrics(); test_step carries no reg_loss; the step's own values stay in last_step_logs."""
+  from wavenets_b200 import WaveNet
+  from wavenets_b200.metrics import MeanSquaredError
+  m = WaveNet(channels=8, blocks=2, final_layers_channels=[8], dilation_bound=2, l2_reg_factor=0.1)
+  raw = m._logs_from_values([4.0, 0.5, 0.0], train=True)
+  assert raw == {'loss': 4.0, 'reg_loss': 0.5}                       # not compiled: the step's own values
+  m.compile(metrics=[MeanSquaredError()])
+  assert [t.name for t in m.metrics] == ['mean_squared_error', 'loss', 'reg_loss'] and len(m.metrics) == 3
+  a = m._logs_from_values([4.0, 0.5, 1.0], train=True)
+  b = m._logs_from_values([2.0, 0.25, 3.0], train=True)
+  assert a == {'loss': 4.0, 'reg_loss': 0.5, 'mean_squared_error': 1.0}
+  assert b == {'loss': 3.0, 'reg_loss': 0.375, 'mean_squared_error': 2.0}
+  assert m.last_step_logs == {'loss': 2.0, 'reg_loss': 0.25, 'mean_squared_error': 3.0}
+  t = m._logs_from_values([1.0, 0.0, 5.0], train=False)              # test_step: the regulariser tracker is not fed
+  assert t['loss'] == 7.0 / 3 and t['reg_loss'] == 0.375 and m.reg_loss.count == 2
+  m.reset_metrics()
+  assert m._logs_from_values([6.0, 1.0, 2.0], train=True) == {'loss': 6.0, 'reg_loss': 1.0, 'mean_squared_error': 2.0}
+  m.compile()                                                        # fresh trackers, like Keras
+  assert m.loss_tracker.count == 0 and m.metrics[0].name == 'loss'
+
+
 def test_layer_attributes_and_errors():
   from wavenets_b200 import WaveNetLayer
   lay = WaveNetLayer(kernel=2, dilation_rate=[1, 2, 4], activation='leaky_relu', channels=16, skip_channels=None)

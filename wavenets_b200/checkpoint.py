@@ -19,6 +19,8 @@ def checkpoint_name(epoch: int, lr: float, ext: str = 'npz') -> str:
 
 def save_weights(model, path: str) -> str:
   w = model.get_weights()
+  if any('__' in k for k in w):
+    raise ValueError('variable names containing "__" cannot be stored ("/" is written as "__" in the .npz keys)')
   os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
   with open(path, 'wb') as f:
     np.savez(f, **{k.replace('/', '__'): v for k, v in w.items()})

@@ -320,12 +320,13 @@ __global__ void dropout_step_bump(unsigned long long* ctr) { ctr[0] += 1ull; }
 // n8 = groups of 8 elements per block slab; slab stride in bytes between blocks.  One Philox call serves 8 elements, 16 random
 // bits each: keep <=> u16 >= round(rate * 65536) (the drop probability is exact to 2^-17; 32 bits per element made this kernel
 // compute bound: 0.72 ms per C2 step for 492 MB of masks, ~70 integer operations per call)
+// layer0 = block index of slab blockIdx.y == 0 (the layer API draws one block's mask at a time)
 __global__ void dropout_mask_philox(uint8_t* __restrict__ mask, long long n8, long long slab_stride, float rate, unsigned long long seed,
-                                    const unsigned long long* __restrict__ step_ctr) {
+                                    const unsigned long long* __restrict__ step_ctr, int layer0) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const unsigned long long step = step_ctr[0];
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), blockIdx.y, (uint32_t)step),
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), blockIdx.y + layer0, (uint32_t)step),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
   const uint32_t thr = (uint32_t)fminf(fmaxf(rate * 65536.0f + 0.5f, 0.0f), 65536.0f);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -336,7 +337,7 @@ __global__ void dropout_mask_philox(uint8_t* __restrict__ mask, long long n8, lo
     const uint32_t two = a | (b << 8);
     if (k < 2) lo |= two << (16 * k); else hi |= two << (16 * (k - 2));
   }
-  reinterpret_cast<uint2*>(mask + (long long)blockIdx.y * slab_stride)[i] = make_uint2(lo, hi);
+  reinterpret_cast<uint2*>(mask + (long long)(blockIdx.y + layer0) * slab_stride)[i] = make_uint2(lo, hi);
 }
 // xd = keep ? x / (1 - rate) : 0
 template <class T>
@@ -541,6 +542,28 @@ __global__ void __launch_bounds__(256) cond_dgrad_all(const float* __restrict__ 
   }
 }
 
+// Keras 3's sparse_categorical_crossentropy on the softmax OUTPUT (model.py:114-118,516) [TF-internal, restated — the golden
+// case `cat_saturated` executes it from the reference source over the shim]: c = clip(p, 1e-7, 1 - 1e-7), then sparse softmax
+// cross entropy with log(c) as logits:  l = log(sum_j c_j) - log(c_y);  the clip passes gradient only where it is inactive:
+//   dl/dlogit_k = p_k (in_k / S - [k == y] in_y / c_y - (Pm / S - in_y)),   S = sum_j c_j = 1 + delta,   Pm = sum_j in_j p_j.
+// While no p_j of a row leaves [1e-7, 1 - 1e-7] this is lse - logit_y and softmax - onehot, evaluated as before (rows take the
+// clipped form warp-uniformly, only when one of their probabilities is clipped).
+#define WN_CE_EPS 1e-7f
+struct WnCeClip { float S_inv, dot, y_coef; };
+// returns the row loss; `loss_unclipped` = lse - logit_y, p_y = the target's probability as the row loop computes it
+__device__ __forceinline__ float wn_ce_clip(WnCeClip& cc, float delta, float pm, float p_y, float loss_unclipped) {
+  const bool in_y = p_y >= WN_CE_EPS && p_y <= 1.0f - WN_CE_EPS;
+  const float c_y = fminf(fmaxf(p_y, WN_CE_EPS), 1.0f - WN_CE_EPS);
+  cc.S_inv = 1.0f / (1.0f + delta);
+  cc.dot = pm * cc.S_inv - (in_y ? 1.0f : 0.0f);
+  cc.y_coef = in_y ? 1.0f / c_y : 0.0f;
+  return log1pf(delta) + (in_y ? loss_unclipped : -logf(c_y));
+}
+__device__ __forceinline__ float wn_ce_clip_grad(const WnCeClip& cc, float p, bool is_target) {
+  const bool in = p >= WN_CE_EPS && p <= 1.0f - WN_CE_EPS;
+  return p * ((in ? cc.S_inv : 0.0f) - (is_target ? cc.y_coef : 0.0f) - cc.dot);
+}
+
 // ------------------------------------------------------------------ softmax-256 cross entropy (model.py:114-118,516)
 // One warp per row.  logits fp32 [rows][C]; the target index is quantised on the fly from
 // frames[b][t+1] (model.py:319-320).  Writes per-block loss partials, dlogits (= scale *
@@ -568,20 +591,42 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
     }
     s = warp_sum(s);
     const float lse = m + logf(s);
+    const float inv = 1.0f / s;
+    // Keras 3 clip (see wn_ce_clip above): delta = sum_j (clip(p_j) - p_j), pm = sum of the un-clipped p_j
+    float delta = 0.f, pm = 0.f;
+    bool any_out = false;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(lp + c);
+      const float p[4] = {expf(v.x - m) * inv, expf(v.y - m) * inv, expf(v.z - m) * inv, expf(v.w - m) * inv};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool in = p[i] >= WN_CE_EPS && p[i] <= 1.0f - WN_CE_EPS;
+        any_out |= !in;
+        delta += fminf(fmaxf(p[i], WN_CE_EPS), 1.0f - WN_CE_EPS) - p[i];
+        pm += in ? p[i] : 0.f;
+      }
+    }
+    const bool clipped = __any_sync(0xffffffffu, any_out);
+    WnCeClip cc;
+    cc.S_inv = 1.f; cc.dot = 0.f; cc.y_coef = 1.f;
+    if (clipped) { delta = warp_sum(delta); pm = warp_sum(pm); }
     int idx = -1;
     if (frames) {
       const long long b = row / Tn, t = row % Tn;
       idx = wn_quantize_idx(frames[b * (Tn + 1) + t + 1], bits);
       loss = lse - lp[idx];
+      if (clipped) loss = wn_ce_clip(cc, delta, pm, expf(lp[idx] - m) * inv, loss);
+    } else if (clipped) {
+      wn_ce_clip(cc, delta, pm, 0.5f, 0.f);
     }
-    const float inv = 1.0f / s;
     for (int c = lane * 4; c < C; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(lp + c);
       float p[4] = {expf(v.x - m) * inv, expf(v.y - m) * inv, expf(v.z - m) * inv, expf(v.w - m) * inv};
       if (probs) *reinterpret_cast<float4*>(probs + row * C + c) = make_float4(p[0], p[1], p[2], p[3]);
       if (dlogits) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dlogits[row * ldd + c + i] = from_f<TD>((p[i] - (c + i == idx ? 1.0f : 0.0f)) * scale);
+        for (int i = 0; i < 4; ++i)
+          dlogits[row * ldd + c + i] = from_f<TD>((clipped ? wn_ce_clip_grad(cc, p[i], c + i == idx) : p[i] - (c + i == idx ? 1.0f : 0.0f)) * scale);
       }
     }
   }
@@ -623,13 +668,34 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
     s = warp_sum(s);
+    const float inv = 1.0f / s;
+    // Keras 3 clip (see wn_ce_clip above): delta = sum_j (clip(p_j) - p_j), pm = sum of the un-clipped p_j
+    float delta = 0.f, pm = 0.f;
+    bool any_out = false;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const float p[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = p[j] >= WN_CE_EPS && p[j] <= 1.0f - WN_CE_EPS;
+        any_out |= !in;
+        delta += fminf(fmaxf(p[j], WN_CE_EPS), 1.0f - WN_CE_EPS) - p[j];
+        pm += in ? p[j] : 0.f;
+      }
+    }
+    const bool clipped = __any_sync(0xffffffffu, any_out);   // warp-uniform; false for every row of an untrained model
+    WnCeClip cc;
+    cc.S_inv = 1.f; cc.dot = 0.f; cc.y_coef = 1.f;
+    if (clipped) { delta = warp_sum(delta); pm = warp_sum(pm); }
     int idx = -1;
     if (frames) {
       const long long b = row / Tn, t = row % Tn;
       idx = wn_quantize_idx(frames[b * (Tn + 1) + t + 1], bits);
       loss = (m + logf(s)) - lp[idx];
+      if (clipped) loss = wn_ce_clip(cc, delta, pm, expf(lp[idx] - m) * inv, loss);
+    } else if (clipped) {
+      wn_ce_clip(cc, delta, pm, 0.5f, 0.f);
     }
-    const float inv = 1.0f / s;
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = lane * 4 + i * 128;
@@ -638,7 +704,7 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
       if (dlogits) {
         float d[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = (p[j] - (c + j == idx ? 1.0f : 0.0f)) * scale;
+        for (int j = 0; j < 4; ++j) d[j] = (clipped ? wn_ce_clip_grad(cc, p[j], c + j == idx) : p[j] - (c + j == idx ? 1.0f : 0.0f)) * scale;
         if constexpr (sizeof(TD) == 2) {
           uint2 q;
           q.x = pack_bf16x2(d[0], d[1]); q.y = pack_bf16x2(d[2], d[3]);

@@ -186,6 +186,7 @@ struct wn_handle {
   int lastB = 0, lastT = 0;
   bool fwd_valid = false;
   bool layer_fwd_valid[WN_MAX_DILATIONS] = {};
+  bool layer_drop[WN_MAX_DILATIONS] = {};     // wn_layer_forward_ex ran block l with dropout active (its adjoint must too)
   const float* last_cond = nullptr;
   long long launches = 0;
   // profiling
@@ -2502,14 +2503,15 @@ extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int 
 }
 
 // fresh Philox keep-masks for a training pass (unless the caller injected masks): bumps the device step counter
-static void draw_dropout_masks(wn_handle* h, cudaStream_t st, int B, int Tn) {
+// only_block >= 0: the mask of that block alone (layer API: the other blocks' masks may still be waiting for their backward)
+static void draw_dropout_masks(wn_handle* h, cudaStream_t st, int B, int Tn, int only_block = -1) {
   if (!h->drop_active || h->drop_injected) return;
   const size_t rows_cap = (size_t)h->maxB * h->maxT;
   const long long n8 = ((long long)B * Tn * h->R + 7) / 8;     // (the slabs are 16-byte aligned and padded: a last partial group stays inside)
   { LaunchScope ls(h, st, CLS_MISC); dropout_step_bump<<<1, 1, 0, st>>>(h->d_drop_ctr); }
   LaunchScope ls(h, st, CLS_MISC);
-  dropout_mask_philox<<<dim3(cdiv(n8, 256), h->L), 256, 0, st>>>(h->drop_mask, n8, (long long)rows_cap * h->R, h->cfg.dropout, h->drop_seed,
-                                                                h->d_drop_ctr);
+  dropout_mask_philox<<<dim3(cdiv(n8, 256), only_block >= 0 ? 1 : h->L), 256, 0, st>>>(h->drop_mask, n8, (long long)rows_cap * h->R, h->cfg.dropout,
+                                                                                    h->drop_seed, h->d_drop_ctr, only_block >= 0 ? only_block : 0);
 }
 
 template <class T>
@@ -2761,8 +2763,12 @@ extern "C" int wn_train_step_host(wn_handle* h, const float* frames_host, const 
 
 // ---------------------------------------------------------------- layer-level API
 template <class T>
-static int layer_fwd_entry(wn_handle* h, int l, const float* x, const float* cond, int B, int Tn, float* x_out, float* skip, cudaStream_t st) {
-  h->drop_active = false;   // WaveNetLayer.call(training=False), layers.py:178
+static int layer_fwd_entry(wn_handle* h, int l, const float* x, const float* cond, int B, int Tn, int training, float* x_out, float* skip,
+                           cudaStream_t st) {
+  // WaveNetLayer.call(inputs, training): Keras Dropout is active only under training=True (layers.py:195-196)
+  h->drop_active = training && h->cfg.dropout > 0.f;
+  h->layer_drop[l] = h->drop_active;
+  draw_dropout_masks(h, st, B, Tn, l);
   const long long nR = (long long)B * Tn * h->R;
   const void* xin;
   // keep a private copy of the block input (needed by the backward pass)
@@ -2794,25 +2800,31 @@ static int layer_fwd_entry(wn_handle* h, int l, const float* x, const float* con
   return WN_OK;
 }
 
-extern "C" int wn_layer_forward(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T, float* x_out_dev, float* skip_dev,
-                                void* stream) {
+extern "C" int wn_layer_forward_ex(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T, int training, float* x_out_dev,
+                                   float* skip_dev, void* stream) {
   RET(check_bt(h, B, T));
   if (block < 0 || block >= h->L || !x_dev || !x_out_dev) { set_err("bad layer arguments"); return WN_ERR_VALUE; }
+  if (training && h->cfg.dropout >= 1.f) { set_err("dropout must be < 1 for training"); return WN_ERR_VALUE; }
   CK(cudaSetDevice(h->cfg.device));
   h->launches = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int r = h->cfg.precision == WN_BF16 ? layer_fwd_entry<bf16>(h, block, x_dev, cond_dev, B, T, x_out_dev, skip_dev, st)
-                                      : layer_fwd_entry<float>(h, block, x_dev, cond_dev, B, T, x_out_dev, skip_dev, st);
+  int r = h->cfg.precision == WN_BF16 ? layer_fwd_entry<bf16>(h, block, x_dev, cond_dev, B, T, training, x_out_dev, skip_dev, st)
+                                      : layer_fwd_entry<float>(h, block, x_dev, cond_dev, B, T, training, x_out_dev, skip_dev, st);
+  h->drop_active = false;
   RET(r);
   CK(cudaGetLastError());
   h->lastB = B; h->lastT = T;
   h->layer_fwd_valid[block] = true;
   return WN_OK;
 }
+extern "C" int wn_layer_forward(wn_handle* h, int block, const float* x_dev, const float* cond_dev, int B, int T, float* x_out_dev, float* skip_dev,
+                                void* stream) {
+  return wn_layer_forward_ex(h, block, x_dev, cond_dev, B, T, 0, x_out_dev, skip_dev, stream);
+}
 
 template <class T>
 static int layer_bwd_entry(wn_handle* h, int l, const float* dxo, const float* dsk, float* dx, float* dcond, cudaStream_t st) {
-  h->drop_active = false;
+  h->drop_active = h->layer_drop[l];   // adjoint of the forward this block last ran (its keep-mask is still in drop_mask)
   const int B = h->lastB, Tn = h->lastT;
   const long long nR = (long long)B * Tn * h->R, nS = (long long)B * Tn * h->Sp;
   const void *dxo_t = nullptr, *dsk_t = nullptr;
@@ -2849,6 +2861,7 @@ extern "C" int wn_layer_backward(wn_handle* h, int block, const float* dx_out_de
   cudaStream_t st = (cudaStream_t)stream;
   int r = h->cfg.precision == WN_BF16 ? layer_bwd_entry<bf16>(h, block, dx_out_dev, dskip_dev, dx_dev, dcond_dev, st)
                                       : layer_bwd_entry<float>(h, block, dx_out_dev, dskip_dev, dx_dev, dcond_dev, st);
+  h->drop_active = false;
   RET(r);
   CK(cudaGetLastError());
   return WN_OK;

@@ -138,6 +138,30 @@ class WaveNetLayer:
   def get_grads(self):
     return {n[len('block0/'):]: w for n, w in self._handle.get_grads().items()}
 
+  # ------------------------------------------------------------------ dropout (layers.py:109-112,195-196)
+  def set_dropout_mask(self, keep):
+    """Inject the keep-mask (B,T,channels) bool used by `call(training=True)` and its `backward` (parity runs); None returns
+    to fresh Philox masks per call."""
+    import ctypes as C
+    import numpy as np
+    if self.dropout is None:
+      raise ValueError('layer was built with dropout == 0')
+    if not self.built:
+      raise ValueError('Layer is not built')
+    h = self._handle
+    if keep is None:
+      _lib.check(h.lib.wn_set_dropout_masks(h.h, None, 1, 1))
+      return
+    a = np.ascontiguousarray(np.asarray(keep).astype(np.uint8))
+    if a.ndim != 3 or a.shape[2] != self.channels:
+      raise ValueError('keep-mask must be (batch, samples, channels)')
+    _lib.check(h.lib.wn_set_dropout_masks(h.h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]))
+
+  def set_dropout_seed(self, seed: int):
+    import ctypes as C
+    if self._handle is not None:
+      _lib.check(self._handle.lib.wn_set_dropout_seed(self._handle.h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+
   # ------------------------------------------------------------------ call (layers.py:178-224)
   def _split_inputs(self, inputs):
     if self.condition:
@@ -166,13 +190,14 @@ class WaveNetLayer:
         cond2 = cond
     if not self.built or (B, T) != self._built_for and (B > self._built_for[0] or T > self._built_for[1]):
       self.build((x.shape, cond.shape) if self.condition else x.shape)
-    if training and self.dropout is not None:
-      raise NotImplementedError('training with dropout>0 is not built (TF RNG stream is not reproducible); use dropout=0')
     h = self._handle
     skip_ch = self.channels if self.skip_channels is None else self.skip_channels
     x_out = torch.empty((B, T, self.channels), dtype=torch.float32, device=dev)
     skip = torch.empty((B, T, skip_ch), dtype=torch.float32, device=dev)
-    _lib.check(h.lib.wn_layer_forward(h.h, 0, h.ptr(x), h.ptr(cond2), B, T, h.ptr(x_out), h.ptr(skip), h.stream_ptr()))
+    # training=True: inverted dropout on the conv branch, residual from the un-masked input (layers.py:192-196); the keep-mask
+    # is a fresh Philox draw unless one was injected with set_dropout_mask (TF's RNG stream is not reproducible)
+    _lib.check(h.lib.wn_layer_forward_ex(h.h, 0, h.ptr(x), h.ptr(cond2), B, T, 1 if (training and self.dropout is not None) else 0,
+                                         h.ptr(x_out), h.ptr(skip), h.stream_ptr()))
     self._last = (x, cond2)
     return x_out, skip
 

@@ -22,6 +22,7 @@ import torch
 from . import _lib
 from ._engine import Handle, as_dev
 from .layers import WaveNetLayer  # noqa: F401  (re-export, like `from src.layers import WaveNetLayer`)
+from .metrics import Mean
 
 
 class _PendingLogs:
@@ -34,14 +35,7 @@ class _PendingLogs:
     if self._out is None:
       self._event.synchronize()
       m = self._model
-      vals = m._pin_logs[self._slot].tolist()
-      out = {'loss': vals[0]}
-      if m.regularization:
-        out['reg_loss'] = vals[1]
-      for metric in m._metrics_from_compilation:
-        metric.update_state(vals[2])
-        out[metric.name] = metric.result()
-      self._out = out
+      self._out = m._logs_from_values(m._pin_logs[self._slot].tolist(), train=True)
     return self._out
 
 
@@ -133,6 +127,9 @@ class WaveNet:
     self._pending_weights = None
     self._staging = {}
     self._metrics_from_compilation = []
+    self.loss_tracker = None          # created by compile(), like model.py:166-168
+    self.reg_loss = None
+    self.last_step_logs = {}
     self._sample_seed, self._sample_calls = 0x42, 0
     self._pin_logs, self._pin_events, self._pending_slot = None, None, 0
     self._last_frames, self._last_rows = None, 0
@@ -149,6 +146,10 @@ class WaveNet:
       raise ValueError('Loss must be set in the model init function.')
     self.optimizer = kwargs.get('optimizer', None)
     self._metrics_from_compilation = list(kwargs.get('metrics') or [])
+    # model.py:166-168: running means over the steps since the last reset_metrics() (Keras `fit` resets them every epoch);
+    # what train_step / test_step of a COMPILED model report as 'loss' / 'reg_loss'
+    self.loss_tracker = Mean(name='loss')
+    self.reg_loss = Mean(name='reg_loss') if self.regularization else None
     if self.optimizer is not None and self.built and hasattr(self.optimizer, 'build'):
       self.optimizer.build(self)
 
@@ -402,7 +403,7 @@ class WaveNet:
       self.optimizer.apply_gradients(self)
     return self._metrics_dict(loss)
 
-  def _metrics_dict(self, loss_dev):
+  def _metrics_dict(self, loss_dev, train=True):
     # model.py:338-348: 'loss' excludes the regulariser, which is reported as 'reg_loss'; every compiled metric is
     # fed (y_true, waveform sampled from this step's predictions)
     mse = None
@@ -413,13 +414,36 @@ class WaveNet:
       _lib.check(h.lib.wn_sample_last_step(h.h, h.ptr(self._last_frames), 0, C.c_uint64(self._sample_seed + self._sample_calls),
                                            h.ptr(out_buf), h.ptr(h._loss[2:]), h.stream_ptr()))
     vals = loss_dev.tolist() if not self._metrics_from_compilation else self.handle._loss.tolist()
-    out = {'loss': vals[0]}
+    return self._logs_from_values(vals, train=train)
+
+  def _logs_from_values(self, vals, train):
+    """The logs dict of one step from [loss, reg_loss, per-step metric value].  A compiled model reports what Keras does
+    (model.py:340-348): the running means of `loss_tracker` / `reg_loss` and of every compiled metric since the last
+    `reset_metrics()`; this step's own values stay readable as `last_step_logs`.  Without `compile()` (which the reference
+    cannot run at all: its trackers are created there) the dict holds the step's own values."""
+    step = {'loss': vals[0]}
     if self.regularization:
-      out['reg_loss'] = vals[1]
+      step['reg_loss'] = vals[1]
+    out = dict(step)
+    if self.loss_tracker is not None:
+      self.loss_tracker.update_state(vals[0])
+      out['loss'] = self.loss_tracker.result()
+      if self.reg_loss is not None:
+        if train:                      # (test_step has no regulariser value to feed, model.py:376-389)
+          self.reg_loss.update_state(vals[1])
+        out['reg_loss'] = self.reg_loss.result()
     for metric in self._metrics_from_compilation:
       metric.update_state(vals[2])
+      step[metric.name] = vals[2]
       out[metric.name] = metric.result()
+    self.last_step_logs = step
     return out
+
+  @property
+  def metrics(self):
+    """model.py:350-360: compiled metrics, then the loss trackers."""
+    extra = [t for t in (self.loss_tracker, self.reg_loss) if t is not None]
+    return list(self._metrics_from_compilation) + extra
 
   def _stage_like(self, name, shape):
     buf = self._staging.get(name)
@@ -430,7 +454,7 @@ class WaveNet:
     return buf
 
   def reset_metrics(self):
-    for metric in self._metrics_from_compilation:
+    for metric in self.metrics:
       metric.reset_state()
 
   def train_step_async(self, data):
@@ -459,7 +483,7 @@ class WaveNet:
     return _PendingLogs(self, slot, ev)
 
   def test_step(self, data):
-    out = self._metrics_dict(self._step(data, False))
+    out = self._metrics_dict(self._step(data, False), train=False)
     out.pop('reg_loss', None)     # model.py:384-389: test_step reports the loss and the compiled metrics only
     return out
 
