@@ -280,9 +280,12 @@ static inline const CUtensorMap* tc_atom_map(TmapCache& tc, const bf16* A, int l
 // Persistent kernels walk their tiles round-robin: with 256 tiles on 74 CTA pairs the last of 4 rounds keeps 34 pairs busy.
 // The same 4 rounds fit on 64 pairs; the SMs left over can run other work (the side-stream weight gradients) meanwhile.
 // g_tc_balance: 0 = always the whole GPU, 1 = the fewest CTAs (pairs) that keep the number of rounds.
-static int g_tc_balance = 0;
+// The switch belongs to the pass a host thread is enqueuing (set and cleared around the backward chain), so it is per thread:
+// handles driven from different threads do not see each other's setting.  WN_TC_BALANCE_GRID=1 forces it for every launch.
+static thread_local int g_tc_balance = 0;
+static int g_tc_balance_env = 0;
 static inline int tc_balanced_slots(int tiles, int slots) {
-  if (!g_tc_balance || tiles <= slots) return slots;
+  if (!(g_tc_balance || g_tc_balance_env) || tiles <= slots) return slots;
   const int rounds = (tiles + slots - 1) / slots;
   return (tiles + rounds - 1) / rounds;
 }

@@ -682,7 +682,7 @@ extern "C" int wn_create(const wn_config* cfg, wn_handle** out) {
   { const char* e = getenv("WN_TC_TILE_GATE_BWD"); if (e) h->tile_gate_bwd = atoi(e); }
   { const char* e = getenv("WN_TC_TILE_DGRAD"); if (e) h->tile_dgrad = atoi(e); }
   { const char* e = getenv("WN_TC_MERGED_FINISH"); if (e && e[0] == '1') h->use_merged_finish = 1; }
-  { const char* e = getenv("WN_TC_BALANCE_GRID"); if (e) g_tc_balance = atoi(e); }
+  { const char* e = getenv("WN_TC_BALANCE_GRID"); if (e) g_tc_balance_env = atoi(e); }
   { const char* e = getenv("WN_TC_DSKIP_LAST"); if (e) h->dskip_l2_last = atoi(e); }
   cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_wg_side, cudaEventDisableTiming);
@@ -2327,6 +2327,19 @@ extern "C" int wn_generate(wn_handle* h, const float* prime_dev, int n_prime, co
   return WN_OK;
 }
 
+// The entry points without a handle launch on the device that owns their buffers (a caller whose current device is another GPU
+// would otherwise get an invalid-argument launch failure).
+static int use_device_of(const void* dev_ptr) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, dev_ptr) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    set_err("argument is not a device pointer");
+    return WN_ERR_VALUE;
+  }
+  CK(cudaSetDevice(at.device));
+  return WN_OK;
+}
+
 // ============================================================================ device input pipeline (utils.py:31-70)
 extern "C" int64_t wn_num_frames(int64_t n_samples, int T) {
   if (T < 1 || n_samples < (int64_t)T + 1) return 0;
@@ -2337,6 +2350,7 @@ extern "C" int wn_preprocess_frames(const void* speech_dev, int is_int16, int64_
   const int64_t nf = wn_num_frames(n_samples, T);
   if (nf == 0) return WN_OK;      /* shorter than one frame: nothing to emit */
   if (!speech_dev || !frames_dev || !valid_dev || nf > 65535) { set_err("bad preprocess arguments (at most 65535 frames per call)"); return WN_ERR_VALUE; }
+  RET(use_device_of(frames_dev));
   cudaStream_t st = (cudaStream_t)stream;
   fill_int_kernel<<<cdiv(nf, 256), 256, 0, st>>>(valid_dev, (int)nf, 1);
   const dim3 grid(cdiv(T + 1, 256) < 64 ? cdiv(T + 1, 256) : 64, (unsigned)nf);
@@ -2348,6 +2362,7 @@ extern "C" int wn_preprocess_frames(const void* speech_dev, int is_int16, int64_
 extern "C" int wn_inverse_mu_law(const float* y_dev, float* x_dev, int64_t n, void* stream) {
   if (n == 0) return WN_OK;
   if (!y_dev || !x_dev || n < 0) { set_err("bad inverse_mu_law arguments"); return WN_ERR_VALUE; }
+  RET(use_device_of(x_dev));
   inverse_mu_law_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(y_dev, x_dev, n);
   CK(cudaGetLastError());
   return WN_OK;
@@ -2355,6 +2370,7 @@ extern "C" int wn_inverse_mu_law(const float* y_dev, float* x_dev, int64_t n, vo
 extern "C" int wn_one_hot(const int32_t* ids_dev, int n, int depth, float* out_dev, void* stream) {
   if (n == 0) return WN_OK;
   if (!ids_dev || !out_dev || n < 0 || depth < 1) { set_err("bad one_hot arguments"); return WN_ERR_VALUE; }
+  RET(use_device_of(out_dev));
   one_hot_kernel<<<cdiv((long long)n * depth, 256), 256, 0, (cudaStream_t)stream>>>(ids_dev, n, depth, out_dev);
   CK(cudaGetLastError());
   return WN_OK;
@@ -2497,6 +2513,7 @@ extern "C" int wn_set_dropout_seed(wn_handle* h, uint64_t seed) {
 extern "C" int wn_quantize(const float* x_dev, int64_t* idx_dev, int64_t n, int bits, void* stream) {
   if (n == 0) return WN_OK;  /* empty input: nothing to do */
   if (!x_dev || !idx_dev || n < 0 || bits < 1 || bits > 16) { set_err("bad quantize arguments"); return WN_ERR_VALUE; }
+  RET(use_device_of(idx_dev));
   quantize_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, (long long*)idx_dev, n, bits);
   CK(cudaGetLastError());
   return WN_OK;
