@@ -549,6 +549,15 @@ __global__ void __launch_bounds__(256) cond_dgrad_all(const float* __restrict__ 
 // While no p_j of a row leaves [1e-7, 1 - 1e-7] this is lse - logit_y and softmax - onehot, evaluated as before (rows take the
 // clipped form warp-uniformly, only when one of their probabilities is clipped).
 #define WN_CE_EPS 1e-7f
+// (b, t) of a flattened row; 32-bit division whenever the row count allows (a 64-bit division is ~100 instructions)
+__device__ __forceinline__ void wn_row_bt(long long row, long long rows, int Tn, long long& b, long long& t) {
+  if (rows <= 0x7fffffffLL) {
+    const unsigned r = (unsigned)row, q = r / (unsigned)Tn;
+    b = q; t = r - q * (unsigned)Tn;
+  } else {
+    b = row / Tn; t = row % Tn;
+  }
+}
 struct WnCeClip { float S_inv, dot, y_coef; };
 // returns the row loss; `loss_unclipped` = lse - logit_y, p_y = the target's probability as the row loop computes it
 __device__ __forceinline__ float wn_ce_clip(WnCeClip& cc, float delta, float pm, float p_y, float loss_unclipped) {
@@ -612,7 +621,8 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
     if (clipped) { delta = warp_sum(delta); pm = warp_sum(pm); }
     int idx = -1;
     if (frames) {
-      const long long b = row / Tn, t = row % Tn;
+      long long b, t;
+      wn_row_bt(row, rows, Tn, b, t);
       idx = wn_quantize_idx(frames[b * (Tn + 1) + t + 1], bits);
       loss = lse - lp[idx];
       if (clipped) loss = wn_ce_clip(cc, delta, pm, expf(lp[idx] - m) * inv, loss);
@@ -669,27 +679,32 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
     }
     s = warp_sum(s);
     const float inv = 1.0f / s;
-    // Keras 3 clip (see wn_ce_clip above): delta = sum_j (clip(p_j) - p_j), pm = sum of the un-clipped p_j
-    float delta = 0.f, pm = 0.f;
-    bool any_out = false;
+    // Keras 3 clip (see wn_ce_clip above).  Detection costs one min per element: the largest probability of the row is exactly
+    // `inv` (its exponent is exp(0) = 1), the smallest is min_j e_j * inv (x -> x * inv is monotonic).
+    float emin = INFINITY;
 #pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const float p[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool in = p[j] >= WN_CE_EPS && p[j] <= 1.0f - WN_CE_EPS;
-        any_out |= !in;
-        delta += fminf(fmaxf(p[j], WN_CE_EPS), 1.0f - WN_CE_EPS) - p[j];
-        pm += in ? p[j] : 0.f;
-      }
-    }
-    const bool clipped = __any_sync(0xffffffffu, any_out);   // warp-uniform; false for every row of an untrained model
+    for (int i = 0; i < NV4; ++i) emin = fminf(emin, fminf(fminf(v[i].x, v[i].y), fminf(v[i].z, v[i].w)));
+    const bool clipped = __any_sync(0xffffffffu, emin * inv < WN_CE_EPS || inv > 1.0f - WN_CE_EPS);   // warp-uniform
     WnCeClip cc;
     cc.S_inv = 1.f; cc.dot = 0.f; cc.y_coef = 1.f;
-    if (clipped) { delta = warp_sum(delta); pm = warp_sum(pm); }
+    float delta = 0.f, pm = 0.f;     // delta = sum_j (clip(p_j) - p_j), pm = sum of the un-clipped p_j
+    if (clipped) {
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const float p[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in = p[j] >= WN_CE_EPS && p[j] <= 1.0f - WN_CE_EPS;
+          delta += fminf(fmaxf(p[j], WN_CE_EPS), 1.0f - WN_CE_EPS) - p[j];
+          pm += in ? p[j] : 0.f;
+        }
+      }
+      delta = warp_sum(delta); pm = warp_sum(pm);
+    }
     int idx = -1;
     if (frames) {
-      const long long b = row / Tn, t = row % Tn;
+      long long b, t;
+      wn_row_bt(row, rows, Tn, b, t);
       idx = wn_quantize_idx(frames[b * (Tn + 1) + t + 1], bits);
       loss = (m + logf(s)) - lp[idx];
       if (clipped) loss = wn_ce_clip(cc, delta, pm, expf(lp[idx] - m) * inv, loss);
@@ -703,8 +718,13 @@ __global__ void __launch_bounds__(256) softmax_ce_reg_kernel(const float* __rest
       if (probs) *reinterpret_cast<float4*>(probs + row * C + c) = make_float4(p[0], p[1], p[2], p[3]);
       if (dlogits) {
         float d[4];
+        if (clipped) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) d[j] = (clipped ? wn_ce_clip_grad(cc, p[j], c + j == idx) : p[j] - (c + j == idx ? 1.0f : 0.0f)) * scale;
+          for (int j = 0; j < 4; ++j) d[j] = wn_ce_clip_grad(cc, p[j], c + j == idx) * scale;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] = (p[j] - (c + j == idx ? 1.0f : 0.0f)) * scale;
+        }
         if constexpr (sizeof(TD) == 2) {
           uint2 q;
           q.x = pack_bf16x2(d[0], d[1]); q.y = pack_bf16x2(d[2], d[3]);
@@ -748,90 +768,128 @@ __global__ void __launch_bounds__(256) ce_probs_rows_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------ mixture losses (model.py:517-547)
-// One thread per row; pred fp32 [rows][ldp] = [weights M | means M | log-scales M].
-// kind: 1 logistic, 2 gaussian.  SQRT2PI is the fp32 value of sqrt(2*3.14159265359) (model.py:9).
+// pred fp32 [rows][ldp] = [weights M | means M | log-scales M].  kind: 1 logistic, 2 gaussian.  SQRT2PI is the fp32 value of
+// sqrt(2*3.14159265359) (model.py:9).
+// G lanes per row (G = 4 / 8 / 16 / 32 >= M), lane m owns mixture component m: the three parameter loads and the three
+// gradient stores of a row are coalesced, softmax over the weights and the likelihood sum are G-wide shuffle reductions, and
+// the chain of exp / log / sigmoid per row is one component long.  (Round 1-2: one thread per row walking all M components
+// through local-memory arrays — 53 us per C4 step at 20 % of the warps active, 8 MB read; ncu_full_r3a_c4_mixture_loss.txt.)
 #define WN_MAX_MIX 32
-template <class TD>
-__global__ void __launch_bounds__(128) mixture_loss_kernel(const float* __restrict__ pred, int ldp, int M, const float* __restrict__ frames,
+template <int G>
+__device__ __forceinline__ float wn_group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float wn_group_max(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <class TD, int G>
+__global__ void __launch_bounds__(256) mixture_loss_kernel(const float* __restrict__ pred, int ldp, int M, const float* __restrict__ frames,
                                                            int Tn, long long rows, int bits, int kind, float scale, TD* __restrict__ dpred,
                                                            int ldd, float* __restrict__ loss_partial, int frame_stride, int frame_off,
                                                            float* __restrict__ row_out) {
-  __shared__ float wsum[4];
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float wsum[8];
+  constexpr int RPB = 256 / G;                       // rows per block
+  const int gl = threadIdx.x & (G - 1);              // component of this lane
+  const long long row = (long long)blockIdx.x * RPB + threadIdx.x / G;
+  const bool rok = row < rows;                       // uniform over the G lanes of a row (every lane takes part in the shuffles)
+  const bool act = rok && gl < M;
   float loss = 0.f;
-  if (row < rows) {
-    const float* p = pred + row * ldp;
-    const long long b = row / Tn, t = row % Tn;
+  float y = 0.f, w = -INFINITY, mu = 0.f, lsr = 0.f;
+  if (rok) {
+    long long b, t;
+    wn_row_bt(row, rows, Tn, b, t);
     // training / test step: the target of position t is frames[b][t+1] (model.py:319); loss_fn: a dense (B,T) target
-    const float y = frames[b * frame_stride + t + frame_off];
-    float pi[WN_MAX_MIX], comp[WN_MAX_MIX];
-    float wmax = -INFINITY;
-    for (int m = 0; m < M; ++m) wmax = fmaxf(wmax, p[m]);
-    float wsumv = 0.f;
-    for (int m = 0; m < M; ++m) { pi[m] = expf(p[m] - wmax); wsumv += pi[m]; }
-    const float winv = 1.0f / wsumv;
-    float lik = 0.f;
-    const float SQRT2PI = 2.50662827463100050242f;
-    const float h = 0.5f / (float)(1 << bits);
-    for (int m = 0; m < M; ++m) {
-      pi[m] *= winv;
-      const float mu = p[M + m];
-      const float ls = fmaxf(p[2 * M + m], -7.0f);
-      if (kind == 2) {
-        const float sc = expf(ls);
-        const float xx = fminf((y - mu) / sc, 1e8f);
-        comp[m] = expf(-0.5f * xx * xx) / (sc * SQRT2PI);
-      } else {
-        // sigma(a) - sigma(b) == sigma(a) * sigma(-b) * (1 - exp(-(a-b))), a-b = 2h*e: the same
-        // quantity as model.py:543-544 without the fp32 cancellation of two nearly equal sigmoids
-        const float e = expf(-ls);
-        comp[m] = wn_sigmoid<false>((y - mu + h) * e) * wn_sigmoid<false>(-(y - mu - h) * e) * (-expm1f(-2.0f * h * e));
-      }
-      lik += pi[m] * comp[m];
+    y = frames[b * frame_stride + t + frame_off];
+  }
+  if (act) {
+    const float* p = pred + row * ldp;
+    w = p[gl]; mu = p[M + gl]; lsr = p[2 * M + gl];
+  }
+  const float wmax = wn_group_max<G>(w);
+  float pi = act ? expf(w - wmax) : 0.f;
+  const float wsumv = wn_group_sum<G>(pi);
+  pi = rok ? pi / wsumv : 0.f;
+  const float SQRT2PI = 2.50662827463100050242f;
+  const float h = 0.5f / (float)(1 << bits);
+  const float ls = fmaxf(lsr, -7.0f);
+  float comp = 0.f, sc = 1.f, e = 1.f;
+  if (act) {
+    if (kind == 2) {
+      sc = expf(ls);
+      const float xx = fminf((y - mu) / sc, 1e8f);
+      comp = expf(-0.5f * xx * xx) / (sc * SQRT2PI);
+    } else {
+      // sigma(a) - sigma(b) == sigma(a) * sigma(-b) * (1 - exp(-(a-b))), a-b = 2h*e: the same
+      // quantity as model.py:543-544 without the fp32 cancellation of two nearly equal sigmoids
+      e = expf(-ls);
+      comp = wn_sigmoid<false>((y - mu + h) * e) * wn_sigmoid<false>(-(y - mu - h) * e) * (-expm1f(-2.0f * h * e));
     }
+  }
+  const float lik = wn_group_sum<G>(pi * comp);
+  if (rok) {
     loss = -logf(lik);
-    if (row_out) row_out[row] = loss;
+    if (row_out && gl == 0) row_out[row] = loss;
     if (dpred) {
-      const float linv = 1.0f / lik;
       TD* d = dpred + row * ldd;
-      for (int m = 0; m < M; ++m) {
-        const float mu = p[M + m];
-        const float lsr = p[2 * M + m];
-        const float ls = fmaxf(lsr, -7.0f);
+      if (act) {
+        const float linv = 1.0f / lik;
         const float pass = lsr >= -7.0f ? 1.0f : 0.0f;
-        const float r = pi[m] * comp[m] * linv;
+        const float r = pi * comp * linv;
         float dmu, dls;
         if (kind == 2) {
-          const float sc = expf(ls);
           const float xr = (y - mu) / sc;
           const float nc = xr <= 1e8f ? 1.0f : 0.0f;
           const float xx = fminf(xr, 1e8f);
           dmu = -r * xx / sc * nc;
           dls = -r * (xx * xx * nc - 1.0f) * pass;
         } else {
-          const float e = expf(-ls);
           const float a = (y - mu + h) * e, bq = (y - mu - h) * e, dab = 2.0f * h * e;
           const float sa = wn_sigmoid<false>(a), snb = wn_sigmoid<false>(-bq);
-          // sigma'(a) - sigma'(b) = (sigma(a)-sigma(b)) * (1 - sigma(a) - sigma(b)) ; comp[m] holds sigma(a)-sigma(b)
-          const float dd = comp[m] * (snb - sa);
+          // sigma'(a) - sigma'(b) = (sigma(a)-sigma(b)) * (1 - sigma(a) - sigma(b)) ; comp holds sigma(a)-sigma(b)
+          const float dd = comp * (snb - sa);
           const float dsb = snb * (1.0f - snb);
-          const float c = pi[m] * linv;
+          const float c = pi * linv;
           dmu = c * e * dd;
           dls = c * (a * dd + dab * dsb) * pass;
         }
-        d[m] = from_f<TD>((pi[m] - r) * scale);
-        d[M + m] = from_f<TD>(dmu * scale);
-        d[2 * M + m] = from_f<TD>(dls * scale);
+        d[gl] = from_f<TD>((pi - r) * scale);
+        d[M + gl] = from_f<TD>(dmu * scale);
+        d[2 * M + gl] = from_f<TD>(dls * scale);
       }
-      for (int m = 3 * M; m < ldd; ++m) d[m] = from_f<TD>(0.f);
+      for (int m = 3 * M + gl; m < ldd; m += G) d[m] = from_f<TD>(0.f);      // padding columns of the gradient operand
     }
   }
   if (loss_partial) {
-    loss = warp_sum(loss);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = loss;
+    // one value per row (lane 0 of its group), fixed order: warp shuffle tree, then the 8 warps in sequence
+    float v = (rok && gl == 0) ? loss : 0.f;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
     __syncthreads();
-    if (threadIdx.x == 0) loss_partial[blockIdx.x] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot += wsum[i];
+      loss_partial[blockIdx.x] = tot;
+    }
   }
+}
+// lanes per row for M components
+static inline int mixture_lanes(int M) { return M <= 4 ? 4 : (M <= 8 ? 8 : (M <= 16 ? 16 : 32)); }
+template <class TD>
+static void mixture_loss_launch(cudaStream_t st, int* nparts_out, const float* pred, int ldp, int M, const float* frames, int Tn, long long rows, int bits,
+                                int kind, float scale, TD* dpred, int ldd, float* loss_partial, int frame_stride, int frame_off, float* row_out) {
+  const int G = mixture_lanes(M);
+  const int nparts = (int)((rows + 256 / G - 1) / (256 / G));
+  if (nparts_out) *nparts_out = nparts;
+#define WN_MIX_GO(GG) mixture_loss_kernel<TD, GG><<<nparts, 256, 0, st>>>(pred, ldp, M, frames, Tn, rows, bits, kind, scale, dpred, ldd, loss_partial, \
+                                                                          frame_stride, frame_off, row_out)
+  if (G == 4) WN_MIX_GO(4); else if (G == 8) WN_MIX_GO(8); else if (G == 16) WN_MIX_GO(16); else WN_MIX_GO(32);
+#undef WN_MIX_GO
 }
 
 // final loss: out[0] = scale * sum(partial) (metric 'loss'), out[1] = extra_coef * extra (metric 'reg_loss', model.py:340-344)

@@ -1411,10 +1411,8 @@ static int loss_forward(wn_handle* h, cudaStream_t st, const float* frames, int 
         softmax_ce_kernel<T><<<nparts, 256, 0, st>>>(h->logits, h->Cout, frames, Tn, rows, c.bits, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
                                                     probs, loss_out ? h->loss_partial : nullptr);
     } else {
-      nparts = cdiv(rows, 128);
-      mixture_loss_kernel<T><<<nparts, 128, 0, st>>>(h->logits, h->ldl, c.num_mixtures, frames, Tn, rows, c.bits,
-                                                    c.sampling_function == WN_GAUSSIAN ? 2 : 1, scale, want_grad ? (T*)h->dlogits : nullptr, h->ldd,
-                                                    loss_out ? h->loss_partial : nullptr, Tn + 1, 1, nullptr);
+      mixture_loss_launch<T>(st, &nparts, h->logits, h->ldl, c.num_mixtures, frames, Tn, rows, c.bits, c.sampling_function == WN_GAUSSIAN ? 2 : 1, scale,
+                             want_grad ? (T*)h->dlogits : nullptr, h->ldd, loss_out ? h->loss_partial : nullptr, Tn + 1, 1, nullptr);
     }
   }
   if (loss_out) {
@@ -2579,8 +2577,8 @@ extern "C" int wn_loss_fn(wn_handle* h, const void* target_dev, int target_is_in
                                                        target_is_int64 ? nullptr : (const float*)target_dev, c.bits, rows, out_dev);
   } else {
     if (target_is_int64) { set_err("mixture losses take the waveform itself as target (model.py:155)"); return WN_ERR_VALUE; }
-    mixture_loss_kernel<float><<<cdiv(rows, 128), 128, 0, st>>>(pred_dev, h->Cout, c.num_mixtures, (const float*)target_dev, T, rows, c.bits,
-                                                               c.sampling_function == WN_GAUSSIAN ? 2 : 1, 1.0f, nullptr, 0, nullptr, T, 0, out_dev);
+    mixture_loss_launch<float>(st, nullptr, pred_dev, h->Cout, c.num_mixtures, (const float*)target_dev, T, rows, c.bits,
+                               c.sampling_function == WN_GAUSSIAN ? 2 : 1, 1.0f, nullptr, 0, nullptr, T, 0, out_dev);
   }
   CK(cudaGetLastError());
   return WN_OK;
