@@ -467,6 +467,75 @@ __global__ void dense_small_wgrad(const float* __restrict__ x, int ldx, const fl
   if (k < K) dW[(long long)k * N + n] = s;
   else if (db) db[n] = s;
 }
+// The whole conditioning MLP (model.py:141-148: Dense + activation per mapping layer) in ONE single-block launch each way, for the
+// sizes it really has (batch x [109 -> 8 -> 16 -> 32]: ~12 k multiply-adds): per layer the separate kernels above cost three
+// dependent launches of a few us at the very start (forward) and the very end (backward: 8 launches behind the last
+// weight-gradient kernel) of every step.  Same arithmetic order as dense_small_fwd / _actgrad / _wgrad (bit-identical there);
+// the dgrad sums run serially over n instead of as a warp tree.
+struct MapArgs {
+  int n_layers, B, cond_in, act;
+  float l2coef;
+  const float* x0;                 // (B, cond_in)
+  int width[WN_MAX_LIST];
+  const float* W[WN_MAX_LIST];     // (K_i, width_i), K_0 = cond_in, K_i = width_{i-1}
+  const float* bias[WN_MAX_LIST];
+  float* gW[WN_MAX_LIST];
+  float* gb[WN_MAX_LIST];
+  float* actv[WN_MAX_LIST];        // (B, width_i): activated outputs (written by the forward, read by the backward)
+  float* d0;                       // backward: gradient wrt actv[n_layers - 1] on entry (overwritten)
+  float* d1;
+  float* d2;
+};
+__global__ void __launch_bounds__(256) mapping_fwd_fused(MapArgs a) {
+  const float* cur = a.x0;
+  int K = a.cond_in;
+  for (int i = 0; i < a.n_layers; ++i) {
+    const int N = a.width[i];
+    const float* W = a.W[i];
+    for (int j = threadIdx.x; j < a.B * N; j += 256) {
+      const int b = j / N, n = j % N;
+      float s = a.bias[i][n];
+      // (unrolled: the loads of 8 steps are in flight together, the FMA order stays that of dense_small_fwd)
+#pragma unroll 8
+      for (int k = 0; k < K; ++k) s = fmaf(cur[(long long)b * K + k], W[(long long)k * N + n], s);
+      a.actv[i][j] = wn_act<false>(a.act, s);
+    }
+    __syncthreads();
+    cur = a.actv[i];
+    K = N;
+  }
+}
+__global__ void __launch_bounds__(256) mapping_bwd_fused(MapArgs a) {
+  float* dcur = a.d0;
+  for (int i = a.n_layers - 1; i >= 0; --i) {
+    const int N = a.width[i];
+    const int K = i > 0 ? a.width[i - 1] : a.cond_in;
+    const float* inp = i > 0 ? a.actv[i - 1] : a.x0;
+    const float* W = a.W[i];
+    for (int j = threadIdx.x; j < a.B * N; j += 256) dcur[j] *= wn_act_grad_from_out(a.act, a.actv[i][j]);
+    __syncthreads();
+    for (int j = threadIdx.x; j < (K + 1) * N; j += 256) {
+      const int k = j / N, n = j % N;
+      float s = 0.f;
+#pragma unroll 8
+      for (int b = 0; b < a.B; ++b) s = fmaf(k < K ? inp[(long long)b * K + k] : 1.0f, dcur[(long long)b * N + n], s);
+      if (k < K) a.gW[i][j] = a.l2coef != 0.f ? fmaf(a.l2coef, W[j], s) : s;
+      else a.gb[i][n] = s;
+    }
+    if (i > 0) {
+      float* dn = (dcur == a.d1) ? a.d2 : a.d1;
+      for (int j = threadIdx.x; j < a.B * K; j += 256) {
+        const int b = j / K, k = j % K;
+        float s = 0.f;
+#pragma unroll 8
+        for (int n = 0; n < N; ++n) s = fmaf(dcur[(long long)b * N + n], W[(long long)k * N + n], s);
+        dn[j] = s;
+      }
+      __syncthreads();
+      dcur = dn;
+    }
+  }
+}
 // dx[b][k] (+)= sum_n dpre[b][n] W[k][n] ; one warp per output, lanes stride over n (coalesced rows of W)
 __global__ void __launch_bounds__(128) dense_small_dgrad(const float* __restrict__ dpre, int ldd, const float* __restrict__ W, float* __restrict__ dx,
                                                          int ldx, int B, int K, int N, int accumulate) {

@@ -1108,10 +1108,34 @@ static void fill_w(GemmH& g, const ConvP& c, bool dgrad) {
 
 // conditioning: mapping MLP (model.py:141-148,222) and the per-block time-constant bias
 // cb[l][b][:] = cond[b] @ Wc_l + bc_l  (layers.py:203-204 with cond constant in time)
+// one single-block launch each way for the conditioning MLP while it is as small as it really is (WN_FUSED_MAPPING=0: per layer)
+static bool mapping_args(wn_handle* h, const float* cond_in, int B, float l2coef, MapArgs* a) {
+  static const int enabled = [] { const char* e = getenv("WN_FUSED_MAPPING"); return e ? atoi(e) : 1; }();
+  const int nl = (int)h->map_w.size();
+  if (!enabled || nl < 1 || nl > WN_MAX_LIST) return false;
+  long long macs = 0;
+  int k = h->cfg.cond_in;
+  for (int i = 0; i < nl; ++i) { macs += (long long)B * k * h->map_width[i]; k = h->map_width[i]; }
+  if (macs > (1 << 20)) return false;
+  a->n_layers = nl; a->B = B; a->cond_in = h->cfg.cond_in; a->act = h->cfg.mapping_activation; a->l2coef = l2coef; a->x0 = cond_in;
+  for (int i = 0; i < nl; ++i) {
+    a->width[i] = h->map_width[i];
+    a->W[i] = P_(h, h->map_w[i]); a->bias[i] = P_(h, h->map_b[i]);
+    a->gW[i] = G_(h, h->map_w[i]); a->gb[i] = G_(h, h->map_b[i]);
+    a->actv[i] = h->cond_act[i];
+  }
+  a->d0 = h->dcond; a->d1 = h->cond_dact; a->d2 = h->cond_dact2;
+  return true;
+}
 static int cond_forward(wn_handle* h, cudaStream_t st, const float* cond_in, int B, bool run_mapping, const float** cond_out) {
   const float* cur = cond_in;
   int width = h->cfg.cond_in;
-  if (run_mapping) {
+  MapArgs ma;
+  if (run_mapping && mapping_args(h, cond_in, B, 0.f, &ma)) {
+    LaunchScope ls(h, st, CLS_MISC);
+    mapping_fwd_fused<<<1, 256, 0, st>>>(ma);
+    cur = h->cond_act[ma.n_layers - 1];
+  } else if (run_mapping) {
     for (size_t i = 0; i < h->map_w.size(); ++i) {
       LaunchScope ls(h, st, CLS_MISC);
       const int n = h->map_width[i];
@@ -1717,6 +1741,12 @@ static int cond_backward(wn_handle* h, cudaStream_t st, const float* cond_in, co
     }
   }
   if (!run_mapping) return WN_OK;
+  MapArgs ma;
+  if (dcond_out == h->dcond && mapping_args(h, cond_in, B, l2coef, &ma)) {
+    LaunchScope ls(h, st, CLS_MISC);
+    mapping_bwd_fused<<<1, 256, 0, st>>>(ma);
+    return WN_OK;
+  }
   float* dcur = dcond_out;
   for (int i = (int)h->map_w.size() - 1; i >= 0; --i) {
     const int nn = h->map_width[i];
