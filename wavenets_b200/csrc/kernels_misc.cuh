@@ -5,6 +5,16 @@
 #pragma once
 #include "common.cuh"
 
+// (b, t) of a flattened row; 32-bit division whenever the row count allows (a 64-bit division is ~100 instructions)
+__device__ __forceinline__ void wn_row_bt(long long row, long long rows, int Tn, long long& b, long long& t) {
+  if (rows <= 0x7fffffffLL) {
+    const unsigned r = (unsigned)row, q = r / (unsigned)Tn;
+    b = q; t = r - q * (unsigned)Tn;
+  } else {
+    b = row / Tn; t = row % Tn;
+  }
+}
+
 // ------------------------------------------------------------------ input causal conv (model.py:84-88,228)
 // h[b,t,c] = sum_k W[k,0,c] * x[b, t-(K-1-k)] + bias[c] ; x (B,T) fp32 with row stride ldx
 template <class T>
@@ -45,7 +55,9 @@ __global__ void __launch_bounds__(256) input_conv_fwd_rows(const float* __restri
   const long long rows = (long long)B * Tn;
   const long long r_end = min(rows, ((long long)blockIdx.x + 1) * ICF_ROWS);
   for (long long row = (long long)blockIdx.x * ICF_ROWS + rg; row < r_end; row += groups) {
-    const int t = (int)(row % Tn), b = (int)(row / Tn);
+    long long bq, tq;
+    wn_row_bt(row, rows, Tn, bq, tq);          // (two 64-bit divisions per row were most of this kernel's instructions)
+    const int t = (int)tq, b = (int)bq;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = bv[j];
@@ -618,15 +630,6 @@ __global__ void __launch_bounds__(256) cond_dgrad_all(const float* __restrict__ 
 // While no p_j of a row leaves [1e-7, 1 - 1e-7] this is lse - logit_y and softmax - onehot, evaluated as before (rows take the
 // clipped form warp-uniformly, only when one of their probabilities is clipped).
 #define WN_CE_EPS 1e-7f
-// (b, t) of a flattened row; 32-bit division whenever the row count allows (a 64-bit division is ~100 instructions)
-__device__ __forceinline__ void wn_row_bt(long long row, long long rows, int Tn, long long& b, long long& t) {
-  if (rows <= 0x7fffffffLL) {
-    const unsigned r = (unsigned)row, q = r / (unsigned)Tn;
-    b = q; t = r - q * (unsigned)Tn;
-  } else {
-    b = row / Tn; t = row % Tn;
-  }
-}
 struct WnCeClip { float S_inv, dot, y_coef; };
 // returns the row loss; `loss_unclipped` = lse - logit_y, p_y = the target's probability as the row loop computes it
 __device__ __forceinline__ float wn_ce_clip(WnCeClip& cc, float delta, float pm, float p_y, float loss_unclipped) {
