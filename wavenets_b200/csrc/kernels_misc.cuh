@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) input_conv_fwd_rows(const float* __restri
     for (int j = 0; j < 8; ++j) w[k][j] = k < K ? W[k * R + c + j] : 0.f;
   const long long rows = (long long)B * Tn;
   const long long r_end = min(rows, ((long long)blockIdx.x + 1) * ICF_ROWS);
+#pragma unroll 4
   for (long long row = (long long)blockIdx.x * ICF_ROWS + rg; row < r_end; row += groups) {
     long long bq, tq;
     wn_row_bt(row, rows, Tn, bq, tq);          // (two 64-bit divisions per row were most of this kernel's instructions)
