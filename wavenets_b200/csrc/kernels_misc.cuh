@@ -499,7 +499,17 @@ struct MapArgs {
   float* d1;
   float* d2;
 };
+// hint: pull n floats towards L2 (one 128-byte line per thread and step) — the layers below run as dependent phases, each of which
+// would otherwise meet its operands cold in DRAM (the step's GBs of activations evict the parameters from L2 every step)
+__device__ __forceinline__ void wn_prefetch_l2(const float* p, long long n) {
+  for (long long i = (long long)threadIdx.x * 32; i < n; i += 256 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
+}
 __global__ void __launch_bounds__(256) mapping_fwd_fused(MapArgs a) {
+  {
+    int k = a.cond_in;
+    wn_prefetch_l2(a.x0, (long long)a.B * k);
+    for (int i = 0; i < a.n_layers; ++i) { wn_prefetch_l2(a.W[i], (long long)k * a.width[i]); wn_prefetch_l2(a.bias[i], a.width[i]); k = a.width[i]; }
+  }
   const float* cur = a.x0;
   int K = a.cond_in;
   for (int i = 0; i < a.n_layers; ++i) {
@@ -519,6 +529,15 @@ __global__ void __launch_bounds__(256) mapping_fwd_fused(MapArgs a) {
   }
 }
 __global__ void __launch_bounds__(256) mapping_bwd_fused(MapArgs a) {
+  {
+    int k = a.cond_in;
+    wn_prefetch_l2(a.x0, (long long)a.B * k);
+    for (int i = 0; i < a.n_layers; ++i) {
+      wn_prefetch_l2(a.W[i], (long long)k * a.width[i]);
+      wn_prefetch_l2(a.actv[i], (long long)a.B * a.width[i]);
+      k = a.width[i];
+    }
+  }
   float* dcur = a.d0;
   for (int i = a.n_layers - 1; i >= 0; --i) {
     const int N = a.width[i];
