@@ -44,6 +44,11 @@ SMALL_MODELS = {
                           num_mixtures=4, sampling_function='gaussian', use_skip=False, skip_channels=5),
   'k3_nores': dict(channels=8, blocks=3, layers_per_block=1, dilation_bound=9, final_layers_channels=[],
                    use_residual=False, kernel_size=3),
+  # more mixture components than a half warp: the mixture-loss kernel runs with 32 lanes per row (17, 20 components)
+  'logistic_m20': dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[16], num_mixtures=20,
+                       sampling_function='logistic', bits=16),
+  'gaussian_m17': dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[16], num_mixtures=17,
+                       sampling_function='gaussian'),
   'wide_ragged': dict(channels=40, blocks=2, layers_per_block=2, activation='sigmoid', dilation_bound=4,
                       final_layers_channels=[70], skip_channels=72, dilation_channels=36, bits=8),
   # L2 on convs whose output nothing reads: conv1 of the last block under use_skip, conv_skip without use_skip —
