@@ -69,6 +69,35 @@ def test_train_step_matches_oracle(name, BT):
   assert abs(m.test_step((x, cond) if cond is not None else x)['loss'] - aux['loss_no_reg']) <= TOL * abs(loss_o)
 
 
+@pytest.mark.parametrize('bits,scale', [(6, 150.0), (8, 300.0)])
+def test_saturated_softmax_keras3_clip(bits, scale):
+  """Keras 3's clip inside sparse_categorical_crossentropy (model.py:516) on a saturated softmax — logits conv scaled until a
+  large part of the class AND target probabilities leave [1e-7, 1 - 1e-7] — against the oracle (itself pinned to the reference-source
+  golden `cat_saturated`): 64 classes run the generic loss kernel, 256 the register-resident one."""
+  from wavenets_b200 import WaveNet
+  kw = dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[16, 16], activation='tanh', bits=bits)
+  B, T = 2, 120
+  cfg = oracle_config(kw, 0)
+  p = {k: v.astype(np.float32).astype(np.float64) for k, v in wo.init_params(cfg, seed=1).items()}
+  p['final2/kernel'] = (p['final2/kernel'] * scale).astype(np.float32).astype(np.float64)
+  x, _ = make_inputs(B, T, 0)
+  m = WaveNet(**kw)
+  m.build(x[:, :-1].shape)
+  m.set_weights({k: v.astype(np.float32) for k, v in p.items()})
+  loss_o, g_o, aux = wo.train_step(p, cfg, x.astype(np.float64), None)
+  pred_o, _ = wo.model_forward(p, cfg, x[:, :-1].astype(np.float64), None)
+  tgt = wo.discretize(x[:, 1:, 0], bits)
+  p_y = np.take_along_axis(pred_o, tgt[..., None], -1)[..., 0]
+  assert 0.1 < (p_y < 1e-7).mean() < 0.9 and (pred_o < 1e-7).mean() > 0.1          # clipped and un-clipped targets both present
+  assert abs(aux['loss_per_sample'].max() + np.log(1e-7)) < 1e-3                    # the clipped rows sit at -log(1e-7) (+ log sum)
+  out = m.train_step(x)
+  assert abs(out['loss'] - aux['loss_no_reg']) <= TOL * abs(loss_o), (out['loss'], aux['loss_no_reg'])
+  g = m.get_grads()
+  for k in g_o:
+    assert rel_err(g[k], g_o[k]) < TOL, (k, rel_err(g[k], g_o[k]))
+  assert abs(m.test_step(x)['loss'] - aux['loss_no_reg']) <= TOL * abs(loss_o)
+
+
 LAYERS = {
   'single': dict(dilation_rate=4, channels=8),
   'multi_leaky': dict(dilation_rate=[1, 2, 4], activation='leaky_relu', channels=8, dilation_channels=12, skip_channels=6),
