@@ -123,6 +123,39 @@ def test_manual_backward_matches_autograd_and_fd(name):
     assert abs(num - g[pname][idx]) <= 1e-4 * max(1.0, abs(num)) + 5e-3 * abs(num), (pname, num, g[pname][idx])
 
 
+def test_saturated_categorical_loss_three_way():
+  """Keras 3's clip inside sparse_categorical_crossentropy with the clip ACTIVE (logits conv scaled x150: clipped class and target
+  probabilities): the hand-derived gradient of the NumPy oracle against torch autograd of the independently written torch
+  restatement and against central finite differences.  (The golden case `cat_saturated` pins both to the reference source.)"""
+  kw = dict(channels=8, blocks=2, layers_per_block=1, dilation_bound=4, final_layers_channels=[16, 16], activation='tanh', bits=6)
+  cfg = oracle_config(kw, 0)
+  p = wo.init_params(cfg, seed=1)
+  p['final2/kernel'] = p['final2/kernel'] * 150.0
+  x, _ = make_inputs(2, 60, 0)
+  x = x.astype(np.float64)
+  loss, g, aux = wo.train_step(p, cfg, x, None)
+  pred, _ = wo.model_forward(p, cfg, x[:, :-1], None)
+  p_y = np.take_along_axis(pred, wo.discretize(x[:, 1:, 0], 6)[..., None], -1)[..., 0]
+  assert 0.1 < (p_y < 1e-7).mean() < 0.9 and (pred < 1e-7).mean() > 0.1
+  # a clipped target contributes -log(1e-7) + log(sum of clipped probabilities) and no gradient through its own probability
+  assert abs(aux['loss_per_sample'].max() + np.log(1e-7)) < 1e-3
+  loss_t, g_t = tr.train_step(p, cfg, x, None)
+  assert abs(loss - loss_t) <= 1e-9 * abs(loss_t)
+  for k in g:
+    assert rel_err(g[k], g_t[k]) < 1e-7, k
+  rng = np.random.default_rng(6)
+  for pname in ('final2/kernel', 'final2/bias', 'final1/kernel', 'block1/dil0/kernel', 'causal/kernel'):
+    idx = tuple(int(rng.integers(0, s)) for s in p[pname].shape)
+    eps = 1e-7
+    pp = {k: v.copy() for k, v in p.items()}
+    pp[pname][idx] += eps
+    lp, _, _ = wo.train_step(pp, cfg, x, None)
+    pp[pname][idx] -= 2 * eps
+    lm, _, _ = wo.train_step(pp, cfg, x, None)
+    num = (lp - lm) / (2 * eps)
+    assert abs(num - g[pname][idx]) <= 1e-4 * max(1.0, abs(num)) + 5e-3 * abs(num), (pname, num, g[pname][idx])
+
+
 def test_replica_scaling():
   # compute_average_loss divides by B*replicas: two replicas' grads SUM to the 1-replica grads
   kw = SMALL_MODELS['categorical_multidil']
